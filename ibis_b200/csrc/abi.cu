@@ -1,0 +1,831 @@
+// abi.cu -- the extern "C" surface of libibis_b200.so (include/ibis_b200.h): context and
+// buffer management, conversion of the reference GridBlock arrays into the device SoA
+// layout, and the orchestration of one residual evaluation / one Runge-Kutta step on the
+// context's stream.
+#include <math.h>
+#include <stdio.h>
+
+#include <algorithm>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "comm.h"
+#include "context.h"
+
+using namespace ib;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(ibis_b200_ctx* c, int code, const std::string& msg) {
+    if (c) c->last_error = msg;
+    g_last_error = msg;
+    return code;
+}
+
+#define GPU_TRY(c, expr)                                                                  \
+    do {                                                                                  \
+        int e__ = (expr);                                                                 \
+        if (e__ != 0)                                                                     \
+            return fail(c, IBIS_B200_ECUDA, std::string(#expr) + ": " + gpu::error_string(e__)); \
+    } while (0)
+
+int64_t pad_to(int64_t n, int64_t m) { return (n + m - 1) / m * m; }
+
+template <typename T>
+int upload_vec(ibis_b200_ctx* c, const std::vector<T>& h, T** d) {
+    void* p = nullptr;
+    if (gpu::dev_malloc(&p, h.size() * sizeof(T)) != 0) return IBIS_B200_ENOMEM;
+    c->owned_allocs.push_back(p);
+    if (!h.empty() && gpu::h2d(p, h.data(), h.size() * sizeof(T), c->stream) != 0) return IBIS_B200_ECUDA;
+    if (gpu::stream_sync(c->stream) != 0) return IBIS_B200_ECUDA;   // h dies with the caller
+    *d = static_cast<T*>(p);
+    return 0;
+}
+
+template <typename T>
+int dev_alloc_zero(ibis_b200_ctx* c, int64_t n, T** d) {
+    void* p = nullptr;
+    if (gpu::dev_malloc(&p, (size_t)n * sizeof(T)) != 0) return IBIS_B200_ENOMEM;
+    c->owned_allocs.push_back(p);
+    if (n > 0 && gpu::memset_async(p, 0, (size_t)n * sizeof(T), c->stream) != 0) return IBIS_B200_ECUDA;
+    *d = static_cast<T*>(p);
+    return 0;
+}
+
+Buffer* get_buf(ibis_b200_ctx* c, int h, BufKind kind) {
+    if (h <= 0 || h >= (int)c->bufs.size()) return nullptr;
+    Buffer* b = &c->bufs[h];
+    if (b->kind != kind) return nullptr;
+    return b;
+}
+
+template <typename S>
+void comp_ptrs(const Buffer* b, S** out /* [7] */) {
+    for (int i = 0; i < 7; i++)
+        out[i] = i < b->ncomp ? static_cast<S*>(b->d) + (int64_t)i * b->stride : nullptr;
+}
+
+int new_buffer(ibis_b200_ctx* c, BufKind kind, bool is_dual, int ncomp, int64_t n, int64_t stride, int* handle) {
+    Buffer b;
+    b.kind = kind;
+    b.is_dual = is_dual;
+    b.ncomp = ncomp;
+    b.n = n;
+    b.stride = stride;
+    const size_t bytes = (size_t)ncomp * stride * (is_dual ? 16 : 8);
+    if (gpu::dev_malloc(&b.d, bytes) != 0) return fail(c, IBIS_B200_ENOMEM, "out of device memory");
+    GPU_TRY(c, gpu::memset_async(b.d, 0, bytes, c->stream));
+    for (size_t i = 1; i < c->bufs.size(); i++)
+        if (c->bufs[i].kind == BUF_FREE) {
+            c->bufs[i] = b;
+            *handle = (int)i;
+            return 0;
+        }
+    c->bufs.push_back(b);
+    *handle = (int)c->bufs.size() - 1;
+    return 0;
+}
+
+int ensure_stage(ibis_b200_ctx* c, int64_t elems) {
+    if (elems <= c->stage_elems) return 0;
+    if (c->d_stage) gpu::dev_free(c->d_stage);
+    void* p = nullptr;
+    if (gpu::dev_malloc(&p, (size_t)elems * sizeof(double)) != 0) {
+        c->d_stage = nullptr;
+        c->stage_elems = 0;
+        return fail(c, IBIS_B200_ENOMEM, "out of device memory (staging)");
+    }
+    c->d_stage = static_cast<double*>(p);
+    c->stage_elems = elems;
+    return 0;
+}
+
+template <typename S>
+FvArgs<S> make_args(ibis_b200_ctx* c, Buffer* fs, Buffer* dudt, bool allow_reconstruction) {
+    FvArgs<S> A;
+    A.g = c->g;
+    S* p[7];
+    comp_ptrs<S>(fs, p);
+    for (int i = 0; i < 7; i++) A.fs[i] = p[i];
+    if (dudt) {
+        comp_ptrs<S>(dudt, p);
+        for (int i = 0; i < 5; i++) A.dudt[i] = p[i];
+    } else {
+        for (int i = 0; i < 5; i++) A.dudt[i] = nullptr;
+    }
+    if (sizeof(S) == sizeof(double)) {
+        A.grad = reinterpret_cast<S*>(c->grad_r);
+        A.lim = reinterpret_cast<S*>(c->lim_r);
+        A.flux = reinterpret_cast<S*>(c->flux_r);
+    } else {
+        A.grad = reinterpret_cast<S*>(c->grad_d);
+        A.lim = reinterpret_cast<S*>(c->lim_d);
+        A.flux = reinterpret_cast<S*>(c->flux_d);
+    }
+    A.face_T = c->face_T;
+    A.face_rho = c->face_rho;
+    A.gas.R = S(c->cfg.R);
+    A.gas.Cv = S(c->cfg.Cv);
+    A.gas.Cp = S(c->cfg.Cp);
+    A.gas.gamma = S(c->cfg.gamma);
+    A.mu0 = S(c->cfg.mu0);
+    A.T0 = S(c->cfg.T0);
+    A.Ts = S(c->cfg.Ts);
+    A.Pr = S(c->cfg.Pr);
+    A.eps = c->cfg.limiter_epsilon;
+    A.delta = c->cfg.ldfss_delta;
+    A.signal_factor = c->cfg.viscous_signal_factor;
+    A.thermo = c->cfg.thermo_interpolator;
+    A.th2 = (A.thermo == THERMO_RHO_P) ? F_P : (A.thermo == THERMO_RHO_T) ? F_T : F_E;
+    A.limiter_on = c->cfg.limiter == IBIS_B200_LIMITER_BARTH_JESPERSEN;
+    A.order2 = allow_reconstruction && c->cfg.reconstruction_order == 2;
+    A.viscous = c->cfg.viscous != 0;
+    return A;
+}
+
+// lazily allocated FiniteVolume temporaries for one scalar type
+template <typename S>
+int ensure_fv_temporaries(ibis_b200_ctx* c) {
+    const bool need_grad = c->cfg.reconstruction_order > 1 || c->cfg.viscous;
+    S** grad = (sizeof(S) == 8) ? reinterpret_cast<S**>(&c->grad_r) : reinterpret_cast<S**>(&c->grad_d);
+    S** lim = (sizeof(S) == 8) ? reinterpret_cast<S**>(&c->lim_r) : reinterpret_cast<S**>(&c->lim_d);
+    S** flux = (sizeof(S) == 8) ? reinterpret_cast<S**>(&c->flux_r) : reinterpret_cast<S**>(&c->flux_d);
+    if (need_grad && !*grad) {
+        int rc = dev_alloc_zero<S>(c, (int64_t)NVARS * 3 * c->cstride, grad);
+        if (rc) return fail(c, rc, "out of device memory (gradients)");
+        rc = dev_alloc_zero<S>(c, (int64_t)NVARS * c->cstride, lim);
+        if (rc) return fail(c, rc, "out of device memory (limiters)");
+    }
+    if (c->cfg.viscous && !*flux) {
+        int rc = dev_alloc_zero<S>(c, (int64_t)5 * c->fstride, flux);
+        if (rc) return fail(c, rc, "out of device memory (face flux)");
+    }
+    if (c->cfg.viscous && !c->face_T) {
+        int rc = dev_alloc_zero<double>(c, c->fstride, &c->face_T);
+        if (rc) return fail(c, rc, "out of device memory (face_fs)");
+        rc = dev_alloc_zero<double>(c, c->fstride, &c->face_rho);
+        if (rc) return fail(c, rc, "out of device memory (face_fs)");
+    }
+    return 0;
+}
+
+// FiniteVolume<T>::compute_dudt (finite_volume.cpp:57-96)
+template <typename S>
+int compute_dudt_impl(ibis_b200_ctx* c, Buffer* fs, Buffer* dudt, bool allow_reconstruction) {
+    int rc = ensure_fv_temporaries<S>(c);
+    if (rc) return rc;
+    FvArgs<S> A = make_args<S>(c, fs, dudt, allow_reconstruction);
+    rc = comm::halo_exchange<S>(c, A.fs);
+    if (rc) return rc;
+    launch_bc(c, A, IBIS_B200_PHASE_PRE_RECONSTRUCTION);
+    if (A.order2) launch_grad_limit(c, A, false);
+    if (A.viscous) {
+        launch_face_flux(c, A);
+        if (c->has_previscous) launch_bc(c, A, IBIS_B200_PHASE_PRE_VISCOUS_GRAD);
+        launch_grad_limit(c, A, true);
+        launch_face_viscous(c, A);
+        launch_integral(c, A);
+    } else {
+        launch_residual(c, A);
+    }
+    if (!c->last_error.empty()) return IBIS_B200_ECUDA;
+    return 0;
+}
+
+int fetch_scalars(ibis_b200_ctx* c, int first, int count, double* out) {
+    GPU_TRY(c, gpu::d2h(c->h_scalars + first, c->d_scalars + first, count * sizeof(double), c->stream));
+    GPU_TRY(c, gpu::stream_sync(c->stream));
+    for (int i = 0; i < count; i++) out[i] = c->h_scalars[first + i];
+    return 0;
+}
+
+// slots in d_scalars
+enum { SC_DT_STABLE = 0, SC_DT = 1, SC_BAD = 2, SC_DOT = 4, SC_NORM = 6, SC_L2 = 8, SC_H = 16, SC_Y = 16 };
+constexpr int N_SCALARS = 16 + 1024;   // h / y of up to 1023 Krylov vectors
+
+}  // namespace
+
+extern "C" {
+
+const char* ibis_b200_last_error(const ibis_b200_ctx* c) {
+    return c ? c->last_error.c_str() : g_last_error.c_str();
+}
+
+int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd, const ibis_b200_config* cfg, int device) {
+    if (!out || !gd || !cfg) return fail(nullptr, IBIS_B200_EINVAL, "null argument");
+    if (gd->dim != 2 && gd->dim != 3) return fail(nullptr, IBIS_B200_EINVAL, "dim must be 2 or 3");
+    if (cfg->thermo_interpolator == IBIS_B200_THERMO_P_T)
+        return fail(nullptr, IBIS_B200_EINVAL,
+                    "thermo_interpolator p_T is broken in the reference (convective_flux.cpp:53-55) and unsupported");
+    if (cfg->reconstruction_order != 1 && cfg->reconstruction_order != 2)
+        return fail(nullptr, IBIS_B200_EINVAL, "Invalid reconstruction order");
+    if (cfg->flux_calculator < 0 || cfg->flux_calculator > 3)
+        return fail(nullptr, IBIS_B200_EINVAL, "Unknown flux calculator");
+    const int64_t n_total = gd->n_cells + gd->n_ghost;
+    if (n_total >= (int64_t)1 << 31 || gd->n_faces >= (int64_t)1 << 31)
+        return fail(nullptr, IBIS_B200_EINVAL, "grid too large for 32-bit ids on one GPU");
+
+    ibis_b200_ctx* c = new (std::nothrow) ibis_b200_ctx();
+    if (!c) return fail(nullptr, IBIS_B200_ENOMEM, "out of host memory");
+    c->bufs.resize(1);
+    int rc = gpu::set_device(device);
+    if (rc != 0) { delete c; return fail(nullptr, IBIS_B200_ECUDA, std::string("cudaSetDevice: ") + gpu::error_string(rc)); }
+    gpu::get_device(&c->device);
+    rc = gpu::stream_create(&c->stream);
+    if (rc != 0) { delete c; return fail(nullptr, IBIS_B200_ECUDA, std::string("cudaStreamCreate: ") + gpu::error_string(rc)); }
+
+    c->cfg = *cfg;
+    c->bc_actions.assign(cfg->bc_actions, cfg->bc_actions + cfg->n_bc_actions);
+    c->cfg.bc_actions = nullptr;
+    c->dim = gd->dim;
+    c->n_cons = gd->dim + 2;
+    c->n_tags = gd->n_tags;
+    c->n_cells = gd->n_cells;
+    c->n_owned = gd->n_owned > 0 ? gd->n_owned : gd->n_cells;
+    c->n_ghost = gd->n_ghost;
+    c->n_total = n_total;
+    c->n_faces = gd->n_faces;
+    c->cstride = pad_to(std::max<int64_t>(n_total, 1), 32);
+    c->fstride = pad_to(std::max<int64_t>(gd->n_faces, 1), 32);
+    const int64_t cs = c->cstride, fs = c->fstride;
+
+    // ---- cell -> face ELL ----
+    int max_faces = 0;
+    for (int64_t i = 0; i < gd->n_cells; i++)
+        max_faces = std::max<int>(max_faces, (int)(gd->cell_face_offsets[i + 1] - gd->cell_face_offsets[i]));
+    if (max_faces > MAXF) { ibis_b200_destroy(c); return fail(nullptr, IBIS_B200_EINVAL, "cell with more than 6 faces"); }
+    if (max_faces == 0) max_faces = 1;
+    std::vector<int> cf_face((size_t)max_faces * cs, -1), cf_nbr((size_t)max_faces * cs, 0);
+    std::vector<signed char> cf_out((size_t)max_faces * cs, 0);
+    int64_t n_grad = 0;
+    bool grad_prefix_open = true;
+    for (int64_t i = 0; i < gd->n_cells; i++) {
+        const int64_t o = gd->cell_face_offsets[i];
+        const int nf = (int)(gd->cell_face_offsets[i + 1] - o);
+        for (int j = 0; j < nf; j++) {
+            cf_face[(size_t)j * cs + i] = (int)gd->cell_face_ids[o + j];
+            cf_nbr[(size_t)j * cs + i] = (int)gd->cell_neighbours[o + j];
+            cf_out[(size_t)j * cs + i] = (signed char)gd->cell_outsigns[o + j];
+        }
+        // cells with their full face list come first; halo cells of the outer layer carry none
+        if (nf > 0 && grad_prefix_open) n_grad = i + 1; else if (nf == 0) grad_prefix_open = false;
+    }
+    std::vector<double> cxyz((size_t)3 * cs, 0.0), vol((size_t)cs, 1.0);
+    for (int64_t i = 0; i < n_total; i++)
+        for (int d = 0; d < 3; d++) cxyz[(size_t)d * cs + i] = gd->cell_centroid[3 * i + d];
+    for (int64_t i = 0; i < gd->n_cells; i++) vol[i] = gd->cell_volume[i];
+
+    // ---- faces SoA ----
+    std::vector<int> fl(fs, 0), fr(fs, 0);
+    std::vector<double> fa(fs, 0.0), fn((size_t)3 * fs, 0.0), ft1((size_t)3 * fs, 0.0), ft2((size_t)3 * fs, 0.0),
+        fc((size_t)3 * fs, 0.0);
+    for (int64_t f = 0; f < gd->n_faces; f++) {
+        fl[f] = (int)gd->face_left[f];
+        fr[f] = (int)gd->face_right[f];
+        fa[f] = gd->face_area[f];
+        for (int d = 0; d < 3; d++) {
+            fn[(size_t)d * fs + f] = gd->face_norm[3 * f + d];
+            ft1[(size_t)d * fs + f] = gd->face_tan1[3 * f + d];
+            ft2[(size_t)d * fs + f] = gd->face_tan2[3 * f + d];
+            fc[(size_t)d * fs + f] = gd->face_centre[3 * f + d];
+        }
+    }
+    // ---- boundary faces and action tables ----
+    const int64_t n_bf = gd->n_tags > 0 ? gd->tag_offsets[gd->n_tags] : 0;
+    std::vector<int> bf_face(std::max<int64_t>(n_bf, 1), 0), bf_tag(std::max<int64_t>(n_bf, 1), 0);
+    for (int t = 0; t < gd->n_tags; t++)
+        for (int64_t k = gd->tag_offsets[t]; k < gd->tag_offsets[t + 1]; k++) {
+            bf_face[k] = (int)gd->tag_faces[k];
+            bf_tag[k] = t;
+        }
+    std::vector<BcAction> acts;
+    std::vector<int> act_off((size_t)2 * (gd->n_tags + 1), 0);
+    for (int phase = 0; phase < 2; phase++) {
+        for (int t = 0; t < gd->n_tags; t++) {
+            act_off[(size_t)phase * (gd->n_tags + 1) + t] = (int)acts.size();
+            for (const auto& a : c->bc_actions)
+                if (a.tag == t && a.phase == phase) {
+                    if (a.type < 0 || a.type > IBIS_B200_BC_SUBSONIC_OUTFLOW) {
+                        ibis_b200_destroy(c);
+                        return fail(nullptr, IBIS_B200_EINVAL, "Unknown boundary action");
+                    }
+                    BcAction b;
+                    b.type = a.type;
+                    b.pad = 0;
+                    for (int q = 0; q < 7; q++) b.params[q] = a.params[q];
+                    acts.push_back(b);
+                    if (phase == 1) c->has_previscous = true;
+                }
+        }
+        act_off[(size_t)phase * (gd->n_tags + 1) + gd->n_tags] = (int)acts.size();
+    }
+    if (acts.empty()) acts.push_back(BcAction());
+
+    GridDev& g = c->g;
+    g.dim = gd->dim;
+    g.n_owned = (int)c->n_owned;
+    g.n_grad = (int)n_grad;
+    g.n_cells = (int)gd->n_cells;
+    g.n_total = (int)n_total;
+    g.n_faces = (int)gd->n_faces;
+    g.n_bfaces = (int)n_bf;
+    g.max_faces = max_faces;
+    g.cstride = cs;
+    g.fstride = fs;
+    g.n_tags = gd->n_tags;
+    c->n_bfaces = n_bf;
+    int* di = nullptr;
+    signed char* dc = nullptr;
+    double* dd = nullptr;
+    BcAction* da = nullptr;
+#define UP(vec, ptr, field)                                                        \
+    rc = upload_vec(c, vec, &ptr);                                                 \
+    if (rc) { ibis_b200_destroy(c); return fail(nullptr, rc, "grid upload failed"); } \
+    g.field = ptr;
+    UP(cf_face, di, cf_face) UP(cf_nbr, di, cf_nbr) UP(cf_out, dc, cf_out)
+    UP(vol, dd, volume)
+    UP(cxyz, dd, cx)
+    g.cy = g.cx + cs;
+    g.cz = g.cx + 2 * cs;
+    UP(fl, di, f_left) UP(fr, di, f_right) UP(fa, dd, f_area)
+    UP(fn, dd, f_n) UP(ft1, dd, f_t1) UP(ft2, dd, f_t2) UP(fc, dd, f_c)
+    UP(bf_face, di, bf_face) UP(bf_tag, di, bf_tag)
+    UP(acts, da, act) UP(act_off, di, act_off)
+#undef UP
+    // WLS r-factors on the device (GridBlock::allocate_gradient_weights, grid.h:499-503)
+    double* r = nullptr;
+    rc = dev_alloc_zero<double>(c, 6 * cs, &r);
+    if (rc) { ibis_b200_destroy(c); return fail(nullptr, rc, "out of device memory"); }
+    g.wls_r = r;
+    launch_wls_r(c, r);
+
+    // reductions
+    c->n_red_blocks = 148 * 8;
+    rc = dev_alloc_zero<double>(c, (int64_t)c->n_red_blocks * 8, &c->d_partials);
+    if (!rc) rc = dev_alloc_zero<double>(c, N_SCALARS, &c->d_scalars);
+    if (rc) { ibis_b200_destroy(c); return fail(nullptr, rc, "out of device memory"); }
+    void* hp = nullptr;
+    if (gpu::host_malloc(&hp, N_SCALARS * sizeof(double)) != 0) {
+        ibis_b200_destroy(c);
+        return fail(nullptr, IBIS_B200_ENOMEM, "pinned allocation failed");
+    }
+    c->h_scalars = static_cast<double*>(hp);
+    rc = gpu::stream_sync(c->stream);
+    if (rc != 0 || !c->last_error.empty()) {
+        std::string msg = c->last_error.empty() ? gpu::error_string(rc) : c->last_error;
+        ibis_b200_destroy(c);
+        return fail(nullptr, IBIS_B200_ECUDA, msg);
+    }
+    *out = c;
+    return 0;
+}
+
+int ibis_b200_destroy(ibis_b200_ctx* c) {
+    if (!c) return 0;
+    gpu::set_device(c->device);
+    if (c->stream) gpu::stream_sync(c->stream);
+    comm::destroy(c);
+    for (auto& b : c->bufs)
+        if (b.kind != BUF_FREE && b.d) gpu::dev_free(b.d);
+    for (void* p : c->owned_allocs) gpu::dev_free(p);
+    if (c->d_stage) gpu::dev_free(c->d_stage);
+    if (c->h_scalars) gpu::host_free(c->h_scalars);
+    if (c->stream) gpu::stream_destroy(c->stream);
+    delete c;
+    return 0;
+}
+
+int ibis_b200_sync(ibis_b200_ctx* c) {
+    GPU_TRY(c, gpu::stream_sync(c->stream));
+    if (!c->last_error.empty()) return IBIS_B200_ECUDA;
+    return 0;
+}
+
+int64_t ibis_b200_launch_count(const ibis_b200_ctx* c) { return c->launches; }
+void* ibis_b200_stream(ibis_b200_ctx* c) { return (void*)c->stream; }
+
+// ---- buffers ----
+int ibis_b200_fs_create(ibis_b200_ctx* c, int is_dual, int* h) {
+    return new_buffer(c, BUF_FS, is_dual != 0, 7, c->n_total, c->cstride, h);
+}
+int ibis_b200_cq_create(ibis_b200_ctx* c, int is_dual, int* h) {
+    return new_buffer(c, BUF_CQ, is_dual != 0, 5, c->n_total, c->cstride, h);
+}
+int ibis_b200_vec_create(ibis_b200_ctx* c, int64_t n, int* h) {
+    return new_buffer(c, BUF_VEC, false, 1, n, pad_to(std::max<int64_t>(n, 1), 32), h);
+}
+int ibis_b200_basis_create(ibis_b200_ctx* c, int64_t n, int n_cols, int* h) {
+    if (n_cols + 2 > 1024) return fail(c, IBIS_B200_EINVAL, "too many Krylov vectors");
+    return new_buffer(c, BUF_BASIS, false, n_cols, n, pad_to(std::max<int64_t>(n, 1), 32), h);
+}
+int ibis_b200_free(ibis_b200_ctx* c, int h) {
+    if (h <= 0 || h >= (int)c->bufs.size() || c->bufs[h].kind == BUF_FREE)
+        return fail(c, IBIS_B200_EHANDLE, "bad handle");
+    gpu::stream_sync(c->stream);
+    gpu::dev_free(c->bufs[h].d);
+    c->bufs[h] = Buffer();
+    return 0;
+}
+
+static const int FS_MAP[7] = {0, 1, 2, 3, 4, 5, 6};
+static const int CQ_MAP3[5] = {0, 1, 2, 3, 4};
+static const int CQ_MAP2[4] = {0, 1, 2, 4};
+
+static int upload_rows(ibis_b200_ctx* c, Buffer* b, const int* map, int ncomp_ref, const double* re_, const double* du_) {
+    if (!re_) return fail(c, IBIS_B200_EINVAL, "null host array");
+    const int64_t n = b->n, elems = n * ncomp_ref;
+    int rc = ensure_stage(c, 2 * elems);
+    if (rc) return rc;
+    GPU_TRY(c, gpu::h2d(c->d_stage, re_, elems * sizeof(double), c->stream));
+    const double* d_du = nullptr;
+    if (b->is_dual && du_) {
+        GPU_TRY(c, gpu::h2d(c->d_stage + elems, du_, elems * sizeof(double), c->stream));
+        d_du = c->d_stage + elems;
+    }
+    if (b->is_dual) {
+        dual* p[7];
+        comp_ptrs<dual>(b, p);
+        launch_pack_in<dual>(c, c->d_stage, d_du, p, map, ncomp_ref, n);
+    } else {
+        double* p[7];
+        comp_ptrs<double>(b, p);
+        launch_pack_in<double>(c, c->d_stage, nullptr, p, map, ncomp_ref, n);
+    }
+    GPU_TRY(c, gpu::stream_sync(c->stream));    // the host arrays may be pageable
+    return c->last_error.empty() ? 0 : IBIS_B200_ECUDA;
+}
+
+static int download_rows(ibis_b200_ctx* c, Buffer* b, const int* map, int ncomp_ref, double* re_, double* du_) {
+    const int64_t n = b->n, elems = n * ncomp_ref;
+    int rc = ensure_stage(c, 2 * elems);
+    if (rc) return rc;
+    if (b->is_dual) {
+        dual* p[7];
+        comp_ptrs<dual>(b, p);
+        launch_pack_out<dual>(c, p, map, ncomp_ref, n, c->d_stage, c->d_stage + elems);
+    } else {
+        double* p[7];
+        comp_ptrs<double>(b, p);
+        launch_pack_out<double>(c, p, map, ncomp_ref, n, c->d_stage, nullptr);
+    }
+    if (re_) GPU_TRY(c, gpu::d2h(re_, c->d_stage, elems * sizeof(double), c->stream));
+    if (du_) {
+        if (b->is_dual) GPU_TRY(c, gpu::d2h(du_, c->d_stage + elems, elems * sizeof(double), c->stream));
+    }
+    GPU_TRY(c, gpu::stream_sync(c->stream));
+    if (du_ && !b->is_dual) memset(du_, 0, elems * sizeof(double));
+    return c->last_error.empty() ? 0 : IBIS_B200_ECUDA;
+}
+
+int ibis_b200_fs_upload(ibis_b200_ctx* c, int h, const double* re_, const double* du_) {
+    Buffer* b = get_buf(c, h, BUF_FS);
+    if (!b) return fail(c, IBIS_B200_EHANDLE, "not a FlowStates handle");
+    return upload_rows(c, b, FS_MAP, 7, re_, du_);
+}
+int ibis_b200_fs_download(ibis_b200_ctx* c, int h, double* re_, double* du_) {
+    Buffer* b = get_buf(c, h, BUF_FS);
+    if (!b) return fail(c, IBIS_B200_EHANDLE, "not a FlowStates handle");
+    return download_rows(c, b, FS_MAP, 7, re_, du_);
+}
+int ibis_b200_cq_upload(ibis_b200_ctx* c, int h, const double* re_, const double* du_) {
+    Buffer* b = get_buf(c, h, BUF_CQ);
+    if (!b) return fail(c, IBIS_B200_EHANDLE, "not a ConservedQuantities handle");
+    return upload_rows(c, b, c->dim == 3 ? CQ_MAP3 : CQ_MAP2, c->n_cons, re_, du_);
+}
+int ibis_b200_cq_download(ibis_b200_ctx* c, int h, double* re_, double* du_) {
+    Buffer* b = get_buf(c, h, BUF_CQ);
+    if (!b) return fail(c, IBIS_B200_EHANDLE, "not a ConservedQuantities handle");
+    return download_rows(c, b, c->dim == 3 ? CQ_MAP3 : CQ_MAP2, c->n_cons, re_, du_);
+}
+int ibis_b200_vec_upload(ibis_b200_ctx* c, int h, const double* x) {
+    Buffer* b = get_buf(c, h, BUF_VEC);
+    if (!b || !x) return fail(c, IBIS_B200_EHANDLE, "not a vector handle");
+    GPU_TRY(c, gpu::h2d(b->d, x, b->n * sizeof(double), c->stream));
+    GPU_TRY(c, gpu::stream_sync(c->stream));
+    return 0;
+}
+int ibis_b200_vec_download(ibis_b200_ctx* c, int h, double* x) {
+    Buffer* b = get_buf(c, h, BUF_VEC);
+    if (!b || !x) return fail(c, IBIS_B200_EHANDLE, "not a vector handle");
+    GPU_TRY(c, gpu::d2h(x, b->d, b->n * sizeof(double), c->stream));
+    GPU_TRY(c, gpu::stream_sync(c->stream));
+    return c->last_error.empty() ? 0 : IBIS_B200_ECUDA;
+}
+int ibis_b200_copy(ibis_b200_ctx* c, int dst, int src) {
+    if (dst <= 0 || src <= 0 || dst >= (int)c->bufs.size() || src >= (int)c->bufs.size())
+        return fail(c, IBIS_B200_EHANDLE, "bad handle");
+    Buffer &d = c->bufs[dst], &s = c->bufs[src];
+    if (d.kind != s.kind || d.kind == BUF_FREE || d.is_dual != s.is_dual || d.n != s.n || d.ncomp != s.ncomp)
+        return fail(c, IBIS_B200_EHANDLE, "copy between different buffer kinds");
+    GPU_TRY(c, gpu::d2d(d.d, s.d, (size_t)s.ncomp * s.stride * (s.is_dual ? 16 : 8), c->stream));
+    return 0;
+}
+int ibis_b200_zero(ibis_b200_ctx* c, int h) {
+    if (h <= 0 || h >= (int)c->bufs.size() || c->bufs[h].kind == BUF_FREE) return fail(c, IBIS_B200_EHANDLE, "bad handle");
+    Buffer& b = c->bufs[h];
+    GPU_TRY(c, gpu::memset_async(b.d, 0, (size_t)b.ncomp * b.stride * (b.is_dual ? 16 : 8), c->stream));
+    return 0;
+}
+
+// ---- the residual ----
+int ibis_b200_compute_dudt(ibis_b200_ctx* c, int fs, int dudt, int allow_reconstruction) {
+    Buffer* f = get_buf(c, fs, BUF_FS);
+    Buffer* d = get_buf(c, dudt, BUF_CQ);
+    if (!f || !d) return fail(c, IBIS_B200_EHANDLE, "compute_dudt: bad handle");
+    if (f->is_dual != d->is_dual) return fail(c, IBIS_B200_EINVAL, "compute_dudt: fs and dudt differ in scalar type");
+    if (f->is_dual) return compute_dudt_impl<dual>(c, f, d, allow_reconstruction != 0);
+    return compute_dudt_impl<double>(c, f, d, allow_reconstruction != 0);
+}
+
+static int estimate_dt_device(ibis_b200_ctx* c, Buffer* f) {
+    if (c->cfg.viscous && !c->face_T) {
+        int rc = ensure_fv_temporaries<double>(c);
+        if (rc) return rc;
+    }
+    if (f->is_dual) {
+        FvArgs<dual> A = make_args<dual>(c, f, nullptr, true);
+        launch_local_dt_min(c, A, c->d_scalars + SC_DT_STABLE);
+    } else {
+        FvArgs<double> A = make_args<double>(c, f, nullptr, true);
+        launch_local_dt_min(c, A, c->d_scalars + SC_DT_STABLE);
+    }
+    return comm::allreduce(c, c->d_scalars + SC_DT_STABLE, 1, comm::OP_MIN);
+}
+
+int ibis_b200_estimate_dt(ibis_b200_ctx* c, int fs, double* dt) {
+    Buffer* f = get_buf(c, fs, BUF_FS);
+    if (!f || !dt) return fail(c, IBIS_B200_EHANDLE, "estimate_dt: bad handle");
+    int rc = estimate_dt_device(c, f);
+    if (rc) return rc;
+    return fetch_scalars(c, SC_DT_STABLE, 1, dt);
+}
+
+int ibis_b200_count_bad_cells(ibis_b200_ctx* c, int fs, uint64_t* n_bad) {
+    Buffer* f = get_buf(c, fs, BUF_FS);
+    if (!f || !n_bad) return fail(c, IBIS_B200_EHANDLE, "count_bad_cells: bad handle");
+    if (f->is_dual) { dual* p[7]; comp_ptrs<dual>(f, p); launch_count_bad<dual>(c, p, c->n_owned, c->d_scalars + SC_BAD); }
+    else { double* p[7]; comp_ptrs<double>(f, p); launch_count_bad<double>(c, p, c->n_owned, c->d_scalars + SC_BAD); }
+    int rc = comm::allreduce(c, c->d_scalars + SC_BAD, 1, comm::OP_SUM);
+    if (rc) return rc;
+    double v = 0;
+    rc = fetch_scalars(c, SC_BAD, 1, &v);
+    *n_bad = (uint64_t)v;
+    return rc;
+}
+
+int ibis_b200_cons_to_prim(ibis_b200_ctx* c, int cq, int fs) {
+    Buffer* q = get_buf(c, cq, BUF_CQ);
+    Buffer* f = get_buf(c, fs, BUF_FS);
+    if (!q || !f || q->is_dual != f->is_dual) return fail(c, IBIS_B200_EHANDLE, "cons_to_prim: bad handles");
+    if (f->is_dual) { dual *a[7], *b[7]; comp_ptrs<dual>(q, a); comp_ptrs<dual>(f, b); launch_cons_to_prim<dual>(c, a, b, c->n_total); }
+    else { double *a[7], *b[7]; comp_ptrs<double>(q, a); comp_ptrs<double>(f, b); launch_cons_to_prim<double>(c, a, b, c->n_total); }
+    return c->last_error.empty() ? 0 : IBIS_B200_ECUDA;
+}
+
+int ibis_b200_prim_to_cons(ibis_b200_ctx* c, int cq, int fs) {
+    Buffer* q = get_buf(c, cq, BUF_CQ);
+    Buffer* f = get_buf(c, fs, BUF_FS);
+    if (!q || !f || q->is_dual != f->is_dual) return fail(c, IBIS_B200_EHANDLE, "prim_to_cons: bad handles");
+    if (f->is_dual) { dual *a[7], *b[7]; comp_ptrs<dual>(q, a); comp_ptrs<dual>(f, b); launch_prim_to_cons<dual>(c, a, b, c->n_total); }
+    else { double *a[7], *b[7]; comp_ptrs<double>(q, a); comp_ptrs<double>(f, b); launch_prim_to_cons<double>(c, a, b, c->n_total); }
+    return c->last_error.empty() ? 0 : IBIS_B200_ECUDA;
+}
+
+static int apply_dt(ibis_b200_ctx* c, Buffer* u0, Buffer* u1, Buffer* k, double dt, const double* d_dt, double scale) {
+    if (u0->is_dual) { dual *a[7], *b[7], *kk[7]; comp_ptrs<dual>(u0, a); comp_ptrs<dual>(u1, b); comp_ptrs<dual>(k, kk);
+        launch_apply_dt<dual>(c, a, b, kk, dt, d_dt, scale, c->n_total); }
+    else { double *a[7], *b[7], *kk[7]; comp_ptrs<double>(u0, a); comp_ptrs<double>(u1, b); comp_ptrs<double>(k, kk);
+        launch_apply_dt<double>(c, a, b, kk, dt, d_dt, scale, c->n_total); }
+    return c->last_error.empty() ? 0 : IBIS_B200_ECUDA;
+}
+
+int ibis_b200_apply_time_derivative(ibis_b200_ctx* c, int u0, int u1, int dudt, double dt) {
+    Buffer *a = get_buf(c, u0, BUF_CQ), *b = get_buf(c, u1, BUF_CQ), *k = get_buf(c, dudt, BUF_CQ);
+    if (!a || !b || !k || a->is_dual != b->is_dual || a->is_dual != k->is_dual)
+        return fail(c, IBIS_B200_EHANDLE, "apply_time_derivative: bad handles");
+    return apply_dt(c, a, b, k, dt, nullptr, 1.0);
+}
+
+static int l2_norms_device(ibis_b200_ctx* c, Buffer* q) {
+    if (q->is_dual) { dual* p[7]; comp_ptrs<dual>(q, p); launch_l2_norms<dual>(c, p, c->n_owned, c->d_scalars + SC_L2); }
+    else { double* p[7]; comp_ptrs<double>(q, p); launch_l2_norms<double>(c, p, c->n_owned, c->d_scalars + SC_L2); }
+    return comm::allreduce(c, c->d_scalars + SC_L2, 6, comm::OP_SUM);
+}
+
+int ibis_b200_l2_norms(ibis_b200_ctx* c, int cq, double out[6]) {
+    Buffer* q = get_buf(c, cq, BUF_CQ);
+    if (!q || !out) return fail(c, IBIS_B200_EHANDLE, "l2_norms: bad handle");
+    // the reference sums over all n_total rows; ghost (and halo) rows of a dudt are zero
+    int rc = l2_norms_device(c, q);
+    if (rc) return rc;
+    rc = fetch_scalars(c, SC_L2, 6, out);
+    for (int i = 0; i < 6; i++) out[i] = sqrt(out[i]);
+    return rc;
+}
+
+int ibis_b200_debug_gradients(ibis_b200_ctx* c, int var, double* grad, double* limiter) {
+    if (var < 0 || var >= NVARS || !c->grad_r) return fail(c, IBIS_B200_EINVAL, "no gradients available");
+    int rc = ensure_stage(c, 3 * c->n_cells);
+    if (rc) return rc;
+    if (grad) {
+        launch_gather_debug(c, c->grad_r + (int64_t)var * 3 * c->cstride, 3, c->n_cells, c->d_stage);
+        GPU_TRY(c, gpu::d2h(grad, c->d_stage, 3 * c->n_cells * sizeof(double), c->stream));
+        GPU_TRY(c, gpu::stream_sync(c->stream));
+    }
+    if (limiter) {
+        GPU_TRY(c, gpu::d2h(limiter, c->lim_r + (int64_t)var * c->cstride, c->n_cells * sizeof(double), c->stream));
+        GPU_TRY(c, gpu::stream_sync(c->stream));
+    }
+    return 0;
+}
+
+// ---- fused explicit step: RungeKutta::take_step (solvers/runge_kutta.cpp:131-203) ----
+int ibis_b200_rk_step(ibis_b200_ctx* c, int fs, int cq, int n_stages, const double* a, const double* b,
+                      double cfl, double dt_prev, double t_remaining, double* dt, double* dt_stable) {
+    Buffer* F = get_buf(c, fs, BUF_FS);
+    Buffer* U = get_buf(c, cq, BUF_CQ);
+    if (!F || !U || F->is_dual || U->is_dual || n_stages < 1 || !b) return fail(c, IBIS_B200_EHANDLE, "rk_step: bad arguments");
+    // k_[stages], k_tmp_, flow_tmp_ (runge_kutta.cpp:45-52)
+    while ((int)c->rk_k.size() < n_stages) {
+        int h = 0;
+        int rc = ibis_b200_cq_create(c, 0, &h);
+        if (rc) return rc;
+        c->rk_k.push_back(h);
+    }
+    if (n_stages > 1 && !c->rk_ktmp) {
+        int rc = ibis_b200_cq_create(c, 0, &c->rk_ktmp);
+        if (!rc) rc = ibis_b200_fs_create(c, 0, &c->rk_fstmp);
+        if (rc) return rc;
+    }
+    F = get_buf(c, fs, BUF_FS);           // bufs may have been reallocated
+    U = get_buf(c, cq, BUF_CQ);
+    int rc = compute_dudt_impl<double>(c, F, &c->bufs[c->rk_k[0]], true);             // :143
+    if (rc) return rc;
+    rc = estimate_dt_device(c, F);                                                     // :147
+    if (rc) return rc;
+    double* d_dt = c->d_scalars + SC_DT;
+    launch_rk_dt(c, c->d_scalars + SC_DT_STABLE, cfl, dt_prev, t_remaining, d_dt);
+    int row = 0;    // a(i, j) = a[row(i) + j], row(i) = i(i-1)/2 for i = 1..stages-1
+    for (int i = 1; i < n_stages; i++) {
+        Buffer* ktmp = &c->bufs[c->rk_ktmp];
+        Buffer* ftmp = &c->bufs[c->rk_fstmp];
+        rc = apply_dt(c, U, ktmp, &c->bufs[c->rk_k[0]], 0.0, d_dt, a[row + 0]);       // :155
+        if (rc) return rc;
+        for (int j = 1; j < i; j++) {
+            if (a[row + j] < 1e-14) continue;                                          // :166
+            rc = apply_dt(c, ktmp, ktmp, &c->bufs[c->rk_k[j]], 0.0, d_dt, a[row + j]); // :169
+            if (rc) return rc;
+        }
+        {
+            double *q[7], *p[7];
+            comp_ptrs<double>(ktmp, q);
+            comp_ptrs<double>(ftmp, p);
+            launch_cons_to_prim<double>(c, q, p, c->n_total);                          // :177
+        }
+        rc = compute_dudt_impl<double>(c, ftmp, &c->bufs[c->rk_k[i]], true);          // :181
+        if (rc) return rc;
+        row += i;
+    }
+    for (int i = 0; i < n_stages; i++) {
+        rc = apply_dt(c, U, U, &c->bufs[c->rk_k[i]], 0.0, d_dt, b[i]);                // :185-186
+        if (rc) return rc;
+    }
+    {
+        double *q[7], *p[7];
+        comp_ptrs<double>(U, q);
+        comp_ptrs<double>(F, p);
+        launch_cons_to_prim<double>(c, q, p, c->n_total);                              // :193
+    }
+    double out[2];
+    rc = fetch_scalars(c, SC_DT_STABLE, 2, out);
+    if (dt_stable) *dt_stable = out[0];
+    if (dt) *dt = out[1];
+    if (rc) return rc;
+    return c->last_error.empty() ? 0 : IBIS_B200_ECUDA;
+}
+
+int ibis_b200_rk_residual_norms(ibis_b200_ctx* c, double out[6]) {
+    if (c->rk_k.empty()) return fail(c, IBIS_B200_EINVAL, "rk_residual_norms before rk_step");
+    return ibis_b200_l2_norms(c, c->rk_k[0], out);
+}
+
+// ---- JFNK ----
+int ibis_b200_jfnk_set_dual(ibis_b200_ctx* c, int cq, int vec, int cq_tmp) {
+    Buffer *q = get_buf(c, cq, BUF_CQ), *v = get_buf(c, vec, BUF_VEC), *t = get_buf(c, cq_tmp, BUF_CQ);
+    if (!q || !v || !t || !q->is_dual || !t->is_dual || v->n != c->n_cells * c->n_cons)
+        return fail(c, IBIS_B200_EHANDLE, "jfnk_set_dual: bad handles");
+    dual *a[7], *b[7];
+    comp_ptrs<dual>(q, a);
+    comp_ptrs<dual>(t, b);
+    launch_jfnk_set_dual(c, a, static_cast<double*>(v->d), b);
+    return c->last_error.empty() ? 0 : IBIS_B200_ECUDA;
+}
+int ibis_b200_jfnk_set_vector(ibis_b200_ctx* c, int residual, int vec, double dt_star, int result) {
+    Buffer *r = get_buf(c, residual, BUF_CQ), *v = get_buf(c, vec, BUF_VEC), *o = get_buf(c, result, BUF_VEC);
+    if (!r || !v || !o || !r->is_dual || v->n != c->n_cells * c->n_cons || o->n != v->n)
+        return fail(c, IBIS_B200_EHANDLE, "jfnk_set_vector: bad handles");
+    dual* a[7];
+    comp_ptrs<dual>(r, a);
+    launch_jfnk_set_vector(c, a, static_cast<double*>(v->d), dt_star, static_cast<double*>(o->d));
+    return c->last_error.empty() ? 0 : IBIS_B200_ECUDA;
+}
+int ibis_b200_jfnk_eval_rhs(ibis_b200_ctx* c, int residual, int rhs) {
+    Buffer *r = get_buf(c, residual, BUF_CQ), *o = get_buf(c, rhs, BUF_VEC);
+    if (!r || !o || !r->is_dual || o->n != c->n_cells * c->n_cons)
+        return fail(c, IBIS_B200_EHANDLE, "jfnk_eval_rhs: bad handles");
+    dual* a[7];
+    comp_ptrs<dual>(r, a);
+    launch_jfnk_eval_rhs(c, a, static_cast<double*>(o->d));
+    return c->last_error.empty() ? 0 : IBIS_B200_ECUDA;
+}
+int ibis_b200_jfnk_apply_update(ibis_b200_ctx* c, int cq, int du_) {
+    Buffer *q = get_buf(c, cq, BUF_CQ), *v = get_buf(c, du_, BUF_VEC);
+    if (!q || !v || !q->is_dual || v->n != c->n_cells * c->n_cons)
+        return fail(c, IBIS_B200_EHANDLE, "jfnk_apply_update: bad handles");
+    dual* a[7];
+    comp_ptrs<dual>(q, a);
+    launch_jfnk_apply_update(c, a, static_cast<double*>(v->d));
+    return c->last_error.empty() ? 0 : IBIS_B200_ECUDA;
+}
+
+// ---- vectors ----
+int ibis_b200_vec_dot(ibis_b200_ctx* c, int a, int b, double* out) {
+    Buffer *x = get_buf(c, a, BUF_VEC), *y = get_buf(c, b, BUF_VEC);
+    if (!x || !y || x->n != y->n || !out) return fail(c, IBIS_B200_EHANDLE, "vec_dot: bad handles");
+    launch_dot(c, static_cast<double*>(x->d), static_cast<double*>(y->d), x->n, c->d_scalars + SC_DOT, 0);
+    return fetch_scalars(c, SC_DOT, 1, out);
+}
+int ibis_b200_vec_norm2(ibis_b200_ctx* c, int a, double* out) {
+    Buffer* x = get_buf(c, a, BUF_VEC);
+    if (!x || !out) return fail(c, IBIS_B200_EHANDLE, "vec_norm2: bad handle");
+    launch_dot(c, static_cast<double*>(x->d), static_cast<double*>(x->d), x->n, c->d_scalars + SC_NORM, 1);
+    return fetch_scalars(c, SC_NORM, 1, out);
+}
+int ibis_b200_vec_axpy(ibis_b200_ctx* c, int y, int x, double s) {
+    Buffer *a = get_buf(c, y, BUF_VEC), *b = get_buf(c, x, BUF_VEC);
+    if (!a || !b || a->n != b->n) return fail(c, IBIS_B200_EHANDLE, "vec_axpy: bad handles");
+    launch_axpy(c, static_cast<double*>(a->d), static_cast<double*>(b->d), s, nullptr, 1.0, a->n);
+    return c->last_error.empty() ? 0 : IBIS_B200_ECUDA;
+}
+int ibis_b200_vec_scale(ibis_b200_ctx* c, int x, int result, double s) {
+    Buffer *a = get_buf(c, x, BUF_VEC), *r = get_buf(c, result, BUF_VEC);
+    if (!a || !r || a->n != r->n) return fail(c, IBIS_B200_EHANDLE, "vec_scale: bad handles");
+    launch_scale(c, static_cast<double*>(a->d), static_cast<double*>(r->d), s, nullptr, a->n);
+    return c->last_error.empty() ? 0 : IBIS_B200_ECUDA;
+}
+int ibis_b200_vec_sub(ibis_b200_ctx* c, int a, int b, int result) {
+    Buffer *x = get_buf(c, a, BUF_VEC), *y = get_buf(c, b, BUF_VEC), *r = get_buf(c, result, BUF_VEC);
+    if (!x || !y || !r || x->n != y->n || x->n != r->n) return fail(c, IBIS_B200_EHANDLE, "vec_sub: bad handles");
+    launch_sub(c, static_cast<double*>(x->d), static_cast<double*>(y->d), static_cast<double*>(r->d), x->n);
+    return c->last_error.empty() ? 0 : IBIS_B200_ECUDA;
+}
+int ibis_b200_basis_set_col(ibis_b200_ctx* c, int basis, int col, int vec) {
+    Buffer *B = get_buf(c, basis, BUF_BASIS), *v = get_buf(c, vec, BUF_VEC);
+    if (!B || !v || col < 0 || col >= B->ncomp || v->n != B->n) return fail(c, IBIS_B200_EHANDLE, "basis_set_col: bad handles");
+    GPU_TRY(c, gpu::d2d(static_cast<double*>(B->d) + (int64_t)col * B->stride, v->d, v->n * sizeof(double), c->stream));
+    return 0;
+}
+
+// modified Gram-Schmidt of gmres.cpp:144-150, all on the stream, one host synchronisation
+int ibis_b200_arnoldi_mgs(ibis_b200_ctx* c, int basis, int j, int w, int v, double* h) {
+    Buffer *B = get_buf(c, basis, BUF_BASIS), *W = get_buf(c, w, BUF_VEC), *V = get_buf(c, v, BUF_VEC);
+    if (!B || !W || !V || j < 0 || j + 1 >= B->ncomp || W->n != B->n || V->n != B->n || !h)
+        return fail(c, IBIS_B200_EHANDLE, "arnoldi_mgs: bad arguments");
+    double* wd = static_cast<double*>(W->d);
+    double* vd = static_cast<double*>(V->d);
+    double* hs = c->d_scalars + SC_H;
+    for (int i = 0; i <= j; i++) {
+        const double* vi = static_cast<double*>(B->d) + (int64_t)i * B->stride;
+        launch_dot(c, wd, vi, W->n, hs + i, 0);                      // H(i,j) = dot(w, V_i)
+        launch_axpy(c, wd, vi, 0.0, hs + i, -1.0, W->n);             // w += V_i * (-H(i,j))
+    }
+    launch_dot(c, wd, wd, W->n, hs + j + 1, 2);                      // H(j+1,j) = norm2(w); hs[j+2] = 1/H
+    launch_scale(c, wd, vd, 0.0, hs + j + 2, W->n);                  // v = w * (1.0 / H(j+1,j))
+    GPU_TRY(c, gpu::d2d(static_cast<double*>(B->d) + (int64_t)(j + 1) * B->stride, vd, V->n * sizeof(double), c->stream));
+    return fetch_scalars(c, SC_H, j + 2, h);
+}
+
+int ibis_b200_basis_gemv(ibis_b200_ctx* c, int basis, int m, const double* y, int out) {
+    Buffer *B = get_buf(c, basis, BUF_BASIS), *O = get_buf(c, out, BUF_VEC);
+    if (!B || !O || m < 0 || m > B->ncomp || O->n != B->n || (m > 0 && !y)) return fail(c, IBIS_B200_EHANDLE, "basis_gemv: bad arguments");
+    for (int i = 0; i < m; i++) c->h_scalars[SC_Y + i] = y[i];
+    if (m > 0) GPU_TRY(c, gpu::h2d(c->d_scalars + SC_Y, c->h_scalars + SC_Y, m * sizeof(double), c->stream));
+    launch_gemv(c, static_cast<double*>(B->d), B->n, B->stride, m, c->d_scalars + SC_Y, static_cast<double*>(O->d));
+    GPU_TRY(c, gpu::stream_sync(c->stream));                         // h_scalars is reused by the next call
+    return c->last_error.empty() ? 0 : IBIS_B200_ECUDA;
+}
+
+// ---- domain decomposition ----
+int ibis_b200_halo_setup(ibis_b200_ctx* c, int n_peers, const int32_t* peer_ranks, const int64_t* send_offsets,
+                         const int64_t* send_cells, const int64_t* recv_offsets, const int64_t* recv_cells) {
+    return comm::halo_setup(c, n_peers, peer_ranks, send_offsets, send_cells, recv_offsets, recv_cells);
+}
+int ibis_b200_comm_init(ibis_b200_ctx* c, const void* id, int rank, int n_ranks) {
+    return comm::init(c, id, rank, n_ranks);
+}
+int ibis_b200_nccl_unique_id(void* out) { return comm::unique_id(out); }
+
+}  // extern "C"

@@ -1,0 +1,172 @@
+// comm.cu -- see comm.h
+#include <dlfcn.h>
+
+#include <string>
+#include <vector>
+
+#include "comm.h"
+
+namespace ib {
+namespace comm {
+
+namespace {
+
+// the few NCCL entry points used, resolved with dlsym (ABI of nccl.h 2.x)
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { ncclSuccess = 0 };
+enum { ncclInt8 = 0, ncclFloat64 = 8 };
+enum { ncclSum = 0, ncclMin = 3 };
+
+struct Nccl {
+    void* lib = nullptr;
+    int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+
+Nccl& nccl() {
+    static Nccl n;
+    if (n.lib) return n;
+    // prefer a libnccl already in the process (torch's bundled one), then the system one
+    n.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+    if (!n.lib) n.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!n.lib) n.lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!n.lib) return n;
+#define SYM(field, name) n.field = reinterpret_cast<decltype(n.field)>(dlsym(n.lib, name))
+    SYM(GetUniqueId, "ncclGetUniqueId");
+    SYM(CommInitRank, "ncclCommInitRank");
+    SYM(CommDestroy, "ncclCommDestroy");
+    SYM(AllReduce, "ncclAllReduce");
+    SYM(Send, "ncclSend");
+    SYM(Recv, "ncclRecv");
+    SYM(GroupStart, "ncclGroupStart");
+    SYM(GroupEnd, "ncclGroupEnd");
+    SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+    n.ok = n.GetUniqueId && n.CommInitRank && n.CommDestroy && n.AllReduce && n.Send && n.Recv &&
+           n.GroupStart && n.GroupEnd;
+    return n;
+}
+
+int comm_fail(ibis_b200_ctx* c, const std::string& msg) {
+    if (c) c->last_error = msg;
+    return IBIS_B200_ECOMM;
+}
+
+#define NCCL_TRY(c, expr)                                                                     \
+    do {                                                                                      \
+        int r__ = (expr);                                                                     \
+        if (r__ != ncclSuccess)                                                               \
+            return comm_fail(c, std::string(#expr) + ": " +                                   \
+                                    (nccl().GetErrorString ? nccl().GetErrorString(r__) : "NCCL error")); \
+    } while (0)
+
+}  // namespace
+
+int unique_id(void* out) {
+    Nccl& n = nccl();
+    if (!n.ok) return IBIS_B200_ECOMM;
+    ncclUniqueId id;
+    if (n.GetUniqueId(&id) != ncclSuccess) return IBIS_B200_ECOMM;
+    memcpy(out, &id, sizeof id);
+    return 0;
+}
+
+int init(ibis_b200_ctx* c, const void* id_bytes, int rank, int n_ranks) {
+    if (n_ranks <= 1) { c->rank = 0; c->n_ranks = 1; return 0; }
+    Nccl& n = nccl();
+    if (!n.ok) return comm_fail(c, "libnccl.so.2 could not be loaded");
+    ncclUniqueId id;
+    memcpy(&id, id_bytes, sizeof id);
+    ncclComm_t comm = nullptr;
+    cudaSetDevice(c->device);
+    NCCL_TRY(c, n.CommInitRank(&comm, n_ranks, id, rank));
+    c->nccl_comm = comm;
+    c->rank = rank;
+    c->n_ranks = n_ranks;
+    return 0;
+}
+
+int destroy(ibis_b200_ctx* c) {
+    if (c->nccl_comm) {
+        nccl().CommDestroy(static_cast<ncclComm_t>(c->nccl_comm));
+        c->nccl_comm = nullptr;
+    }
+    Halo& h = c->halo;
+    if (h.d_send_cells) cudaFree(h.d_send_cells);
+    if (h.d_recv_cells) cudaFree(h.d_recv_cells);
+    if (h.d_send_buf) cudaFree(h.d_send_buf);
+    if (h.d_recv_buf) cudaFree(h.d_recv_buf);
+    h = Halo();
+    return 0;
+}
+
+int allreduce(ibis_b200_ctx* c, double* d_buf, int count, int op) {
+    if (c->n_ranks <= 1) return 0;
+    if (!c->nccl_comm) return comm_fail(c, "allreduce before comm_init");
+    NCCL_TRY(c, nccl().AllReduce(d_buf, d_buf, (size_t)count, ncclFloat64, op == OP_MIN ? ncclMin : ncclSum,
+                                 static_cast<ncclComm_t>(c->nccl_comm), c->stream));
+    return 0;
+}
+
+int halo_setup(ibis_b200_ctx* c, int n_peers, const int32_t* peer_ranks, const int64_t* send_offsets,
+               const int64_t* send_cells, const int64_t* recv_offsets, const int64_t* recv_cells) {
+    Halo& h = c->halo;
+    h.n_peers = n_peers;
+    h.peer_ranks.assign(peer_ranks, peer_ranks + n_peers);
+    h.send_off.assign(send_offsets, send_offsets + n_peers + 1);
+    h.recv_off.assign(recv_offsets, recv_offsets + n_peers + 1);
+    h.n_send = h.send_off[n_peers];
+    h.n_recv = h.recv_off[n_peers];
+    std::vector<int> s(h.n_send), r(h.n_recv);
+    for (int64_t i = 0; i < h.n_send; i++) s[i] = (int)send_cells[i];
+    for (int64_t i = 0; i < h.n_recv; i++) r[i] = (int)recv_cells[i];
+    if (cudaMalloc(&h.d_send_cells, std::max<size_t>(s.size(), 1) * sizeof(int)) != cudaSuccess ||
+        cudaMalloc(&h.d_recv_cells, std::max<size_t>(r.size(), 1) * sizeof(int)) != cudaSuccess ||
+        cudaMalloc(&h.d_send_buf, std::max<size_t>(s.size(), 1) * 7 * 16) != cudaSuccess ||
+        cudaMalloc(&h.d_recv_buf, std::max<size_t>(r.size(), 1) * 7 * 16) != cudaSuccess)
+        return comm_fail(c, "out of device memory (halo buffers)");
+    cudaMemcpyAsync(h.d_send_cells, s.data(), s.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream);
+    cudaMemcpyAsync(h.d_recv_cells, r.data(), r.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream);
+    cudaStreamSynchronize(c->stream);
+    return 0;
+}
+
+template <typename S>
+int halo_exchange(ibis_b200_ctx* c, S* const* fs) {
+    Halo& h = c->halo;
+    if (h.n_peers == 0 || c->n_ranks <= 1) return 0;
+    if (!c->nccl_comm) return comm_fail(c, "halo exchange before comm_init");
+    Nccl& n = nccl();
+    S* sbuf = reinterpret_cast<S*>(h.d_send_buf);
+    S* rbuf = reinterpret_cast<S*>(h.d_recv_buf);
+    launch_halo_pack<S>(c, fs, h.d_send_cells, h.n_send, sbuf);
+    const size_t per_cell = 7 * sizeof(S) / sizeof(double);     // doubles per cell
+    NCCL_TRY(c, n.GroupStart());
+    for (int p = 0; p < h.n_peers; p++) {
+        const int64_t so = h.send_off[p], sn = h.send_off[p + 1] - so;
+        const int64_t ro = h.recv_off[p], rn = h.recv_off[p + 1] - ro;
+        if (sn > 0)
+            NCCL_TRY(c, n.Send(reinterpret_cast<double*>(sbuf) + so * per_cell, (size_t)sn * per_cell, ncclFloat64,
+                               h.peer_ranks[p], static_cast<ncclComm_t>(c->nccl_comm), c->stream));
+        if (rn > 0)
+            NCCL_TRY(c, n.Recv(reinterpret_cast<double*>(rbuf) + ro * per_cell, (size_t)rn * per_cell, ncclFloat64,
+                               h.peer_ranks[p], static_cast<ncclComm_t>(c->nccl_comm), c->stream));
+    }
+    NCCL_TRY(c, n.GroupEnd());
+    launch_halo_unpack<S>(c, fs, h.d_recv_cells, h.n_recv, rbuf);
+    return c->last_error.empty() ? 0 : IBIS_B200_ECUDA;
+}
+template int halo_exchange<double>(ibis_b200_ctx*, double* const*);
+template int halo_exchange<dual>(ibis_b200_ctx*, dual* const*);
+
+}  // namespace comm
+}  // namespace ib

@@ -1,0 +1,153 @@
+// context.h -- host-side state behind the opaque ibis_b200_ctx and the launcher
+// interface between the C ABI (abi.cu) and the kernel translation units.
+#pragma once
+
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "backend.h"
+#include "fv_bodies.h"
+#include "ibis_b200.h"
+
+namespace ib {
+
+enum BufKind { BUF_FREE = 0, BUF_FS = 1, BUF_CQ = 2, BUF_VEC = 3, BUF_BASIS = 4 };
+
+struct Buffer {
+    BufKind kind = BUF_FREE;
+    bool is_dual = false;
+    int ncomp = 0;         // FS 7, CQ 5 (internal: mz slot always present), VEC 1, BASIS n_cols
+    int64_t n = 0;         // entries per component
+    int64_t stride = 0;    // component stride (entries)
+    void* d = nullptr;     // double* or dual*
+};
+
+struct Halo {
+    int n_peers = 0;
+    std::vector<int> peer_ranks;
+    std::vector<int64_t> send_off, recv_off;   // per peer offsets into the index lists
+    int* d_send_cells = nullptr;               // internal ids
+    int* d_recv_cells = nullptr;
+    double* d_send_buf = nullptr;              // packed [peer][var][cell], real or dual
+    double* d_recv_buf = nullptr;
+    int64_t n_send = 0, n_recv = 0;
+};
+
+}  // namespace ib
+
+struct ibis_b200_ctx {
+    int device = 0;
+    ib::gpu::stream_t stream = nullptr;
+    std::string last_error;
+    int64_t launches = 0;
+
+    // sizes
+    int dim = 0, n_cons = 0, n_tags = 0;
+    int64_t n_owned = 0, n_cells = 0, n_ghost = 0, n_total = 0, n_faces = 0, n_bfaces = 0;
+    int64_t cstride = 0, fstride = 0;
+    ibis_b200_config cfg;
+    std::vector<ibis_b200_bc_action> bc_actions;
+    bool has_previscous = false;
+
+    ib::GridDev g;                       // device pointers + sizes
+    std::vector<void*> owned_allocs;     // everything to free at destroy
+
+    // FiniteVolume-owned temporaries (finite_volume.h:116-141), real and dual
+    double* grad_r = nullptr;
+    double* lim_r = nullptr;
+    double* flux_r = nullptr;
+    ib::dual* grad_d = nullptr;
+    ib::dual* lim_d = nullptr;
+    ib::dual* flux_d = nullptr;
+    double* face_T = nullptr;
+    double* face_rho = nullptr;
+
+    // reductions
+    double* d_partials = nullptr;        // [n_blocks * 8]
+    double* d_scalars = nullptr;         // results of final reductions (64 doubles)
+    double* h_scalars = nullptr;         // pinned mirror
+    int n_red_blocks = 0;
+
+    // I/O staging (reference AoS <-> internal SoA)
+    double* d_stage = nullptr;
+    int64_t stage_elems = 0;
+
+    // explicit solver scratch: k_[stages], k_tmp_, flow_tmp_ (runge_kutta.cpp:45-52)
+    std::vector<int> rk_k;
+    int rk_ktmp = 0, rk_fstmp = 0;
+
+    std::vector<ib::Buffer> bufs;        // handle = index (0 unused)
+    ib::Halo halo;
+    void* nccl_comm = nullptr;
+    int rank = 0, n_ranks = 1;
+};
+
+namespace ib {
+
+// ---- launchers implemented in fv_kernels.cu (CUDA) / tests/emu (host loops) ----
+template <typename S>
+void launch_bc(ibis_b200_ctx* c, const FvArgs<S>& A, int phase);
+void launch_wls_r(ibis_b200_ctx* c, double* r_out);
+template <typename S>
+void launch_grad_limit(ibis_b200_ctx* c, const FvArgs<S>& A, bool viscous_pass);
+template <typename S>
+void launch_residual(ibis_b200_ctx* c, const FvArgs<S>& A);        // fused inviscid path
+template <typename S>
+void launch_face_flux(ibis_b200_ctx* c, const FvArgs<S>& A);       // general path
+template <typename S>
+void launch_face_viscous(ibis_b200_ctx* c, const FvArgs<S>& A);
+template <typename S>
+void launch_integral(ibis_b200_ctx* c, const FvArgs<S>& A);
+template <typename S>
+void launch_local_dt_min(ibis_b200_ctx* c, const FvArgs<S>& A, double* d_out);
+
+// ---- launchers implemented in solver_kernels.cu ----
+template <typename S>
+void launch_cons_to_prim(ibis_b200_ctx* c, S* const* cq, S* const* fs, int64_t n);
+template <typename S>
+void launch_prim_to_cons(ibis_b200_ctx* c, S* const* cq, S* const* fs, int64_t n);
+template <typename S>
+void launch_apply_dt(ibis_b200_ctx* c, S* const* u0, S* const* u1, S* const* k, double dt,
+                     const double* d_dt, double scale, int64_t n);
+template <typename S>
+void launch_l2_norms(ibis_b200_ctx* c, S* const* cq, int64_t n, double* d_out6);
+template <typename S>
+void launch_count_bad(ibis_b200_ctx* c, S* const* fs, int64_t n, double* d_out);
+void launch_rk_dt(ibis_b200_ctx* c, const double* d_dt_stable, double cfl, double dt_prev,
+                  double t_remaining, double* d_dt);
+// AoS (reference numbering) <-> SoA (internal), ncomp_ref components per row
+template <typename S>
+void launch_pack_in(ibis_b200_ctx* c, const double* d_re, const double* d_du, S* const* comps,
+                    const int* comp_map, int ncomp_ref, int64_t n);
+template <typename S>
+void launch_pack_out(ibis_b200_ctx* c, S* const* comps, const int* comp_map, int ncomp_ref,
+                     int64_t n, double* d_re, double* d_du);
+void launch_gather_debug(ibis_b200_ctx* c, const double* src, int ncomp, int64_t n, double* out);
+// vectors
+void launch_dot(ibis_b200_ctx* c, const double* a, const double* b, int64_t n, double* d_out,
+                int post);   // post: 0 none, 1 sqrt, 2 sqrt and also store 1/sqrt at d_out[1]
+void launch_axpy(ibis_b200_ctx* c, double* y, const double* x, double s, const double* d_s,
+                 double sign, int64_t n);
+void launch_scale(ibis_b200_ctx* c, const double* x, double* r, double s, const double* d_s,
+                  int64_t n);
+void launch_sub(ibis_b200_ctx* c, const double* a, const double* b, double* r, int64_t n);
+void launch_gemv(ibis_b200_ctx* c, const double* basis, int64_t n, int64_t stride, int m,
+                 const double* d_y, double* out);
+void launch_fill(ibis_b200_ctx* c, double* p, double v, int64_t n);
+// JFNK
+void launch_jfnk_set_dual(ibis_b200_ctx* c, dual* const* cq, const double* vec, dual* const* cq_tmp);
+void launch_jfnk_set_vector(ibis_b200_ctx* c, dual* const* res, const double* vec, double dt_star,
+                            double* result);
+void launch_jfnk_eval_rhs(ibis_b200_ctx* c, dual* const* res, double* rhs);
+void launch_jfnk_apply_update(ibis_b200_ctx* c, dual* const* cq, const double* dU);
+// halo
+template <typename S>
+void launch_halo_pack(ibis_b200_ctx* c, S* const* fs, const int* cells, int64_t n, S* buf);
+template <typename S>
+void launch_halo_unpack(ibis_b200_ctx* c, S* const* fs, const int* cells, int64_t n, const S* buf);
+
+int reduction_blocks(int64_t n);
+
+}  // namespace ib

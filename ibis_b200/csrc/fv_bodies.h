@@ -1,0 +1,630 @@
+// fv_bodies.h -- per-index bodies of the finite-volume kernels (one boundary face, one
+// cell or one interface per call).  The __global__ wrappers in fv_kernels.cu map one
+// thread to one index.  The functions are __host__ __device__ only so that the very same
+// source can be exercised on the host by tests/emu (the development container has no
+// GPU); the shipped library never runs them on the CPU.
+#pragma once
+
+#include <stdint.h>
+
+#include "physics.h"
+
+namespace ib {
+
+constexpr int MAXF = 6;       // faces per cell: hex 6, wedge/pyramid 5, tet/quad 4, tri 3
+constexpr int NVARS = 6;      // gradient slots: rho, thermo-2, vx, vy, vz, T(viscous)
+enum { V_RHO = 0, V_TH2 = 1, V_VX = 2, V_VY = 3, V_VZ = 4, V_TVISC = 5 };
+enum { F_RHO = 0, F_P = 1, F_T = 2, F_E = 3, F_VX = 4, F_VY = 5, F_VZ = 6 };
+enum { BC_FLOW_STATE_COPY = 0, BC_INTERNAL_COPY = 1, BC_REFLECT_NORMAL = 2, BC_VEL_REFLECT = 3,
+       BC_FIX_TEMPERATURE = 4, BC_SUBSONIC_INFLOW = 5, BC_SUBSONIC_OUTFLOW = 6 };
+
+struct BcAction {
+    int type;
+    int pad;
+    double params[7];
+};
+
+// Device-resident grid: int32 ids, SoA geometry.  Cell ids: [0, n_owned) owned,
+// [n_owned, n_cells) halo copies, [n_cells, n_total) boundary ghosts.
+struct GridDev {
+    int dim, n_owned, n_grad, n_cells, n_total, n_faces, n_bfaces, max_faces;
+    long cstride;               // padded n_total: stride of every per-cell SoA component
+    long fstride;               // padded n_faces
+    // per cell, ELL [slot][cell] with stride cstride (slot < max_faces)
+    const int* cf_face;         // face id, -1 past the cell's last face
+    const int* cf_nbr;          // neighbour across that face (cells.neighbour_cells_)
+    const signed char* cf_out;  // outsign
+    const double* volume;       // n_cells
+    const double* cx;           // centroids, n_total each
+    const double* cy;
+    const double* cz;
+    const double* wls_r;        // [6][cstride] r11 r12 r22 r13 r23 r33 (grid/gradient.h:153-160)
+    // per face, SoA with stride fstride
+    const int* f_left;
+    const int* f_right;
+    const double* f_area;
+    const double* f_n;          // [3][fstride]
+    const double* f_t1;
+    const double* f_t2;
+    const double* f_c;          // centres
+    // boundary faces in (tag alphabetical, marker order)
+    const int* bf_face;
+    const int* bf_tag;
+    // actions: for phase p and tag t the actions are act[act_off[p*(n_tags+1)+t] ...)
+    const BcAction* act;
+    const int* act_off;
+    int n_tags;
+};
+
+template <typename S>
+struct FvArgs {
+    GridDev g;
+    S* fs[7];          // FlowStates: rho p T e vx vy vz
+    S* dudt[5];        // mass mx my mz energy
+    S* grad;           // [(var*3 + comp)*cstride + cell]
+    S* lim;            // [var*cstride + cell]
+    S* flux;           // general path: [comp*fstride + face]
+    double* face_T;    // face_fs of the viscous path (finite_volume.h:128), real parts
+    double* face_rho;
+    Gas<S> gas;
+    S mu0, T0, Ts, Pr;
+    double eps, delta, signal_factor;
+    int thermo;        // THERMO_*
+    int th2;           // index into fs[] of the second thermo variable (p, T or e)
+    int limiter_on;
+    int order2;        // reconstruction order 2 in effect for this evaluation
+    int viscous;
+};
+
+// ---------------------------------------------------------------------------------------
+// boundary conditions: one thread per boundary face applies its tag's action list in order
+// (finite_volume.cpp:187-218, boundaries/boundary.cpp:517-543)
+// ---------------------------------------------------------------------------------------
+template <typename S>
+IBIS_HD void bc_body(const FvArgs<S>& A, int k, int phase) {
+    const GridDev& g = A.g;
+    const int f = g.bf_face[k];
+    const int tag = g.bf_tag[k];
+    const int l = g.f_left[f], r = g.f_right[f];
+    int ghost, valid;
+    if (l < g.n_cells) { ghost = r; valid = l; } else { ghost = l; valid = r; }
+    const int a0 = g.act_off[phase * (g.n_tags + 1) + tag];
+    const int a1 = g.act_off[phase * (g.n_tags + 1) + tag + 1];
+    S* const* fs = A.fs;
+    typedef mem<S> M;
+    for (int a = a0; a < a1; a++) {
+        const BcAction& act = g.act[a];
+        switch (act.type) {
+            case BC_FLOW_STATE_COPY: {                       // boundary.cpp:26-45
+                M::store(fs[F_T], ghost, S(act.params[2]));
+                M::store(fs[F_P], ghost, S(act.params[1]));
+                M::store(fs[F_RHO], ghost, S(act.params[0]));
+                M::store(fs[F_E], ghost, S(act.params[3]));
+                M::store(fs[F_VX], ghost, S(act.params[4]));
+                M::store(fs[F_VY], ghost, S(act.params[5]));
+                M::store(fs[F_VZ], ghost, S(act.params[6]));
+                break;
+            }
+            case BC_INTERNAL_COPY: {                         // boundary.cpp:110-136
+                for (int q = 0; q < 7; q++) M::store(fs[q], ghost, M::load(fs[q], valid));
+                break;
+            }
+            case BC_REFLECT_NORMAL: {                        // boundary.cpp:152-205
+                for (int q = 0; q < 4; q++) M::store(fs[q], ghost, M::load(fs[q], valid));
+                S x = M::load(fs[F_VX], valid), y = M::load(fs[F_VY], valid),
+                  z = M::load(fs[F_VZ], valid);
+                S nx = S(g.f_n[f]), ny = S(g.f_n[g.fstride + f]), nz = S(g.f_n[2 * g.fstride + f]);
+                S t1x = S(g.f_t1[f]), t1y = S(g.f_t1[g.fstride + f]),
+                  t1z = S(g.f_t1[2 * g.fstride + f]);
+                S t2x = S(g.f_t2[f]), t2y = S(g.f_t2[g.fstride + f]),
+                  t2z = S(g.f_t2[2 * g.fstride + f]);
+                S xs = -(x * nx + y * ny + z * nz);
+                S ys = x * t1x + y * t1y + z * t1z;
+                S zs = x * t2x + y * t2y + z * t2z;
+                M::store(fs[F_VX], ghost, xs * nx + ys * t1x + zs * t2x);
+                M::store(fs[F_VY], ghost, xs * ny + ys * t1y + zs * t2y);
+                M::store(fs[F_VZ], ghost, xs * nz + ys * t1z + zs * t2z);
+                break;
+            }
+            case BC_VEL_REFLECT: {                           // boundary.cpp:219-240
+                M::store(fs[F_VX], ghost, -M::load(fs[F_VX], valid));
+                M::store(fs[F_VY], ghost, -M::load(fs[F_VY], valid));
+                M::store(fs[F_VZ], ghost, -M::load(fs[F_VZ], valid));
+                break;
+            }
+            case BC_FIX_TEMPERATURE: {                       // boundary.cpp:255-276
+                S Tw = S(act.params[0]);
+                M::store(fs[F_T], ghost, 2.0 * Tw - M::load(fs[F_T], valid));
+                break;
+            }
+            case BC_SUBSONIC_INFLOW: {                       // boundary.cpp:296-342
+                S in_rho = S(act.params[0]), in_p = S(act.params[1]);
+                S in_vx = S(act.params[4]), in_vy = S(act.params[5]), in_vz = S(act.params[6]);
+                S nx = S(g.f_n[f]), ny = S(g.f_n[g.fstride + f]), nz = S(g.f_n[2 * g.fstride + f]);
+                S vvx = M::load(fs[F_VX], valid), vvy = M::load(fs[F_VY], valid),
+                  vvz = M::load(fs[F_VZ], valid);
+                S vel_correct = nx * (in_vx - vvx) + ny * (in_vy - vvy) + nz * (in_vz - vvz);
+                S a = speed_of_sound(M::load(fs[F_T], valid), A.gas.R, A.gas.gamma);
+                S rho_ref = M::load(fs[F_RHO], valid);
+                S p_v = M::load(fs[F_P], valid);
+                S p_face = 0.5 * (in_p + p_v - rho_ref * a * vel_correct);
+                S rho_face = in_rho + (p_face - in_p) / a / a;
+                S vx_face = in_vx - nx * (in_p - p_face) / (rho_ref * a);
+                S vy_face = in_vy - ny * (in_p - p_face) / (rho_ref * a);
+                S vz_face = in_vz - nz * (in_p - p_face) / (rho_ref * a);
+                S pg = 2.0 * p_face - p_v;
+                S rg = 2.0 * rho_face - rho_ref;
+                S Tg = T_from_rhop(rg, pg, A.gas.R);
+                M::store(fs[F_P], ghost, pg);
+                M::store(fs[F_RHO], ghost, rg);
+                M::store(fs[F_T], ghost, Tg);
+                M::store(fs[F_E], ghost, A.gas.Cv * Tg);
+                M::store(fs[F_VX], ghost, 2.0 * vx_face - vvx);
+                M::store(fs[F_VY], ghost, 2.0 * vy_face - vvy);
+                M::store(fs[F_VZ], ghost, 2.0 * vz_face - vvz);
+                break;
+            }
+            case BC_SUBSONIC_OUTFLOW: {                      // boundary.cpp:359-399
+                S nx = S(g.f_n[f]), ny = S(g.f_n[g.fstride + f]), nz = S(g.f_n[2 * g.fstride + f]);
+                S p_face = S(act.params[0]);
+                S rho_ref = M::load(fs[F_RHO], valid);
+                S p_ref = M::load(fs[F_P], valid);
+                S a = speed_of_sound(M::load(fs[F_T], valid), A.gas.R, A.gas.gamma);
+                S vvx = M::load(fs[F_VX], valid), vvy = M::load(fs[F_VY], valid),
+                  vvz = M::load(fs[F_VZ], valid);
+                S rho_face = rho_ref + (p_face - p_ref) / a / a;
+                S vx_face = vvx + nx * (p_ref - p_face) / (rho_ref * a);
+                S vy_face = vvy + ny * (p_ref - p_face) / (rho_ref * a);
+                S vz_face = vvz + nz * (p_ref - p_face) / (rho_ref * a);
+                S pg = 2.0 * p_face - p_ref;
+                S rg = 2.0 * rho_face - rho_ref;
+                S Tg = T_from_rhop(rg, pg, A.gas.R);
+                M::store(fs[F_P], ghost, pg);
+                M::store(fs[F_RHO], ghost, rg);
+                M::store(fs[F_T], ghost, Tg);
+                M::store(fs[F_E], ghost, A.gas.Cv * Tg);
+                M::store(fs[F_VX], ghost, 2.0 * vx_face - vvx);
+                M::store(fs[F_VY], ghost, 2.0 * vy_face - vvy);
+                M::store(fs[F_VZ], ghost, 2.0 * vz_face - vvz);
+                break;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// WLS setup: r-factors of one cell (grid/gradient.h:119-162)
+// ---------------------------------------------------------------------------------------
+IBIS_HD void wls_r_body(const GridDev& g, double* r_out, int c) {
+    double sxx = 0.0, sxy = 0.0, sxz = 0.0, syy = 0.0, syz = 0.0, szz = 0.0;
+    const double xi = g.cx[c], yi = g.cy[c], zi = g.cz[c];
+    for (int j = 0; j < g.max_faces; j++) {
+        if (g.cf_face[j * g.cstride + c] < 0) break;
+        const int nb = g.cf_nbr[j * g.cstride + c];
+        const double dx = g.cx[nb] - xi, dy = g.cy[nb] - yi, dz = g.cz[nb] - zi;
+        sxx += dx * dx;
+        sxy += dx * dy;
+        sxz += dx * dz;
+        syy += dy * dy;
+        syz += dy * dz;
+        szz += dz * dz;
+    }
+    const double r11 = sqrt(sxx);
+    const double r12 = 1.0 / r11 * sxy;
+    const double r22 = sqrt(syy - r12 * r12);
+    const double r13 = 1.0 / r11 * sxz;
+    const double r23 = 1.0 / r22 * (syz - r12 / r11 * sxz);
+    const double r33 = sqrt(szz - (r13 * r13 + r23 * r23));
+    r_out[0 * g.cstride + c] = r11;
+    r_out[1 * g.cstride + c] = r12;
+    r_out[2 * g.cstride + c] = r22;
+    if (g.dim == 3) {
+        r_out[3 * g.cstride + c] = r13;
+        r_out[4 * g.cstride + c] = r23;
+        r_out[5 * g.cstride + c] = r33;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// pass G: WLS gradients (grid/gradient.h:66-116) of NV variables and their Barth-Jespersen
+// limiters (finite_volume/limiter.cpp:24-63) for one cell, fused: the neighbour ids,
+// centroids, r-factors and face centres are read once instead of once per variable.
+// vars[] lists the gradient slots to produce, src[] the fs[] component feeding each.
+// ---------------------------------------------------------------------------------------
+template <int DIM, int NV, typename S>
+IBIS_HD void grad_limit_body(const FvArgs<S>& A, int c, const int* vars, const int* src,
+                             bool do_limit) {
+    const GridDev& g = A.g;
+    typedef mem<S> M;
+    const long cs = g.cstride;
+    // geometry enters the reference's arithmetic as T (dual with zero dual part)
+    const S r11 = S(g.wls_r[c]), r12 = S(g.wls_r[cs + c]), r22 = S(g.wls_r[2 * cs + c]);
+    S r13 = S(0.0), r23 = S(0.0), r33 = S(0.0);
+    if (DIM == 3) {
+        r13 = S(g.wls_r[3 * cs + c]);
+        r23 = S(g.wls_r[4 * cs + c]);
+        r33 = S(g.wls_r[5 * cs + c]);
+    }
+    const S beta = (r12 * r23 - r13 * r23) / (r11 * r22);     // gradient.h:89 (sic)
+    const S xi = S(g.cx[c]), yi = S(g.cy[c]), zi = S(g.cz[c]);
+
+    S ui[NV], gx[NV], gy[NV], gz[NV], umin[NV], umax[NV];
+#pragma unroll
+    for (int v = 0; v < NV; v++) {
+        ui[v] = M::load(A.fs[src[v]], c);
+        gx[v] = S(0.0);
+        gy[v] = S(0.0);
+        gz[v] = S(0.0);
+        umin[v] = ui[v];
+        umax[v] = ui[v];
+    }
+    for (int j = 0; j < MAXF; j++) {
+        if (j >= g.max_faces) break;
+        if (g.cf_face[j * cs + c] < 0) break;
+        const int nb = g.cf_nbr[j * cs + c];
+        const S dx = S(g.cx[nb]) - xi;
+        const S dy = S(g.cy[nb]) - yi;
+        const S dz = S(g.cz[nb]) - zi;
+        const S alpha_1 = dx / (r11 * r11);
+        const S alpha_2 = 1.0 / (r22 * r22) * (dy - r12 / r11 * dx);
+        S alpha_3 = S(0.0);
+        if (DIM == 3) alpha_3 = 1.0 / (r33 * r33) * (dz - r23 / r22 * dy + beta * dx);
+        const S w_1 = alpha_1 - r12 / r11 * alpha_2 + beta * alpha_3;
+        const S w_2 = alpha_2 - r23 / r22 * alpha_3;
+        const S w_3 = alpha_3;
+#pragma unroll
+        for (int v = 0; v < NV; v++) {
+            const S un = M::load(A.fs[src[v]], nb);
+            const S diff_u = un - ui[v];
+            gx[v] += w_1 * diff_u;
+            gy[v] += w_2 * diff_u;
+            gz[v] += w_3 * diff_u;
+            umin[v] = min_(umin[v], un);                       // limiter.cpp:37-38
+            umax[v] = max_(umax[v], un);
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < NV; v++) {
+        M::store(A.grad, (vars[v] * 3 + 0) * cs + c, gx[v]);
+        M::store(A.grad, (vars[v] * 3 + 1) * cs + c, gy[v]);
+        M::store(A.grad, (vars[v] * 3 + 2) * cs + c, gz[v]);
+    }
+    if (!do_limit) return;
+
+    S phi[NV];
+#pragma unroll
+    for (int v = 0; v < NV; v++) phi[v] = S(1.0);
+    const long fs_ = g.fstride;
+    for (int j = 0; j < MAXF; j++) {
+        if (j >= g.max_faces) break;
+        const int f = g.cf_face[j * cs + c];
+        if (f < 0) break;
+        const S dx = S(g.f_c[f]) - xi;
+        const S dy = S(g.f_c[fs_ + f]) - yi;
+        const S dz = S(g.f_c[2 * fs_ + f]) - zi;
+#pragma unroll
+        for (int v = 0; v < NV; v++) {
+            S delta_2 = gx[v] * dx + gy[v] * dy + gz[v] * dz;
+            const int sgn = (re(delta_2) > 0.0) - (re(delta_2) < 0.0);
+            delta_2 = (double)sgn * (abs_(delta_2) + A.eps);
+            if (sgn > 0) {
+                phi[v] = min_(phi[v], (umax[v] - ui[v]) / delta_2);
+            } else if (sgn < 0) {
+                phi[v] = min_(phi[v], (umin[v] - ui[v]) / delta_2);
+            }
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < NV; v++) M::store(A.lim, vars[v] * cs + c, phi[v]);
+}
+
+// ---------------------------------------------------------------------------------------
+// reconstruction of one side of one face (convective_flux.cpp:212-420) -> Side in the
+// GLOBAL frame (u,v,w = vx,vy,vz); rotation is applied by the caller.
+// ---------------------------------------------------------------------------------------
+template <int DIM, typename S>
+IBIS_HD S interp(const FvArgs<S>& A, int var, int src, int cell, bool valid, bool limit,
+                 const S& dx, const S& dy, const S& dz) {
+    // linear_interpolate (convective_flux.cpp:243-255)
+    typedef mem<S> M;
+    const long cs = A.g.cstride;
+    S gx = S(0.0), gy = S(0.0), gz = S(0.0);
+    // 2-D: every z-gradient, and the whole vz gradient, is identically zero in the
+    // reference (never computed, convective_flux.cpp:206-208) and its vz limiter is 1
+    const bool vz2d = (DIM == 2 && var == V_VZ);
+    if (valid && !vz2d) {
+        gx = M::load(A.grad, (var * 3 + 0) * cs + cell);
+        gy = M::load(A.grad, (var * 3 + 1) * cs + cell);
+        if (DIM == 3) gz = M::load(A.grad, (var * 3 + 2) * cs + cell);
+    }
+    const S limiter = (limit && !vz2d) ? M::load(A.lim, var * cs + cell) : S(1.0);
+    return M::load(A.fs[src], cell) + limiter * (gx * dx + gy * dy + gz * dz);
+}
+
+template <int DIM, typename S>
+IBIS_HD Side<S> reconstruct_side(const FvArgs<S>& A, int f, int cell) {
+    typedef mem<S> M;
+    const GridDev& g = A.g;
+    Side<S> s;
+    if (!A.order2) {                                          // copy_reconstruct :212-240
+        s.T = M::load(A.fs[F_T], cell);
+        s.p = M::load(A.fs[F_P], cell);
+        s.rho = M::load(A.fs[F_RHO], cell);
+        s.e = M::load(A.fs[F_E], cell);
+        s.u = M::load(A.fs[F_VX], cell);
+        s.v = M::load(A.fs[F_VY], cell);
+        s.w = M::load(A.fs[F_VZ], cell);
+        return s;
+    }
+    const bool valid = cell < g.n_cells;
+    const bool limit = A.limiter_on && valid;
+    const S dx = S(g.f_c[f]) - S(g.cx[cell]);
+    const S dy = S(g.f_c[g.fstride + f]) - S(g.cy[cell]);
+    const S dz = S(g.f_c[2 * g.fstride + f]) - S(g.cz[cell]);
+    // the two thermodynamic variables, then the closure (gas_model.h:91-117)
+    s.p = S(0.0);
+    s.T = S(0.0);
+    s.e = S(0.0);
+    const S rho = interp<DIM>(A, V_RHO, F_RHO, cell, valid, limit, dx, dy, dz);
+    const S th2 = interp<DIM>(A, V_TH2, A.th2, cell, valid, limit, dx, dy, dz);
+    s.rho = rho;
+    if (A.thermo == THERMO_RHO_P) s.p = th2;
+    else if (A.thermo == THERMO_RHO_T) s.T = th2;
+    else s.e = th2;
+    thermo_close(A.thermo, A.gas, s.rho, s.p, s.T, s.e);
+    s.u = interp<DIM>(A, V_VX, F_VX, cell, valid, limit, dx, dy, dz);
+    s.v = interp<DIM>(A, V_VY, F_VY, cell, valid, limit, dx, dy, dz);
+    s.w = interp<DIM>(A, V_VZ, F_VZ, cell, valid, limit, dx, dy, dz);
+    return s;
+}
+
+// convective flux of one interface in the GLOBAL frame: reconstruct, rotate
+// (util/vector3.cpp:142-153), flux calculator, rotate back (convective_flux.cpp:148-164)
+template <int DIM, int FLUX, typename S>
+IBIS_HD Flux5<S> face_convective_flux(const FvArgs<S>& A, int f) {
+    const GridDev& g = A.g;
+    const long fs_ = g.fstride;
+    Side<S> L = reconstruct_side<DIM>(A, f, g.f_left[f]);
+    Side<S> R_ = reconstruct_side<DIM>(A, f, g.f_right[f]);
+    const S nx = S(g.f_n[f]), ny = S(g.f_n[fs_ + f]), nz = S(g.f_n[2 * fs_ + f]);
+    const S t1x = S(g.f_t1[f]), t1y = S(g.f_t1[fs_ + f]), t1z = S(g.f_t1[2 * fs_ + f]);
+    const S t2x = S(g.f_t2[f]), t2y = S(g.f_t2[fs_ + f]), t2z = S(g.f_t2[2 * fs_ + f]);
+    {
+        const S x = L.u * nx + L.v * ny + L.w * nz;
+        const S y = L.u * t1x + L.v * t1y + L.w * t1z;
+        const S z = L.u * t2x + L.v * t2y + L.w * t2z;
+        L.u = x; L.v = y; L.w = z;
+    }
+    {
+        const S x = R_.u * nx + R_.v * ny + R_.w * nz;
+        const S y = R_.u * t1x + R_.v * t1y + R_.w * t1z;
+        const S z = R_.u * t2x + R_.v * t2y + R_.w * t2z;
+        R_.u = x; R_.v = y; R_.w = z;
+    }
+    Flux5<S> F = flux_calc<FLUX>(L, R_, A.gas, A.delta);
+    const S px = F.mx, py = F.my;
+    const S pz = (DIM == 3) ? F.mz : S(0.0);
+    F.mx = px * nx + py * t1x + pz * t2x;
+    F.my = px * ny + py * t1y + pz * t2y;
+    F.mz = px * nz + py * t1z + pz * t2z;
+    return F;
+}
+
+// ---------------------------------------------------------------------------------------
+// viscous flux of one interface (finite_volume/viscous_flux.cpp:16-184), subtracted from F
+// ---------------------------------------------------------------------------------------
+template <typename S>
+struct Vec3 {
+    S x, y, z;
+};
+
+template <typename S>
+IBIS_HD Vec3<S> hasselbacher(const FvArgs<S>& A, int var, const S& vl, const S& vr, int l, int r,
+                             const Vec3<S>& ehat, const Vec3<S>& n, const S& len_e,
+                             const S& ehat_dot_n) {
+    typedef mem<S> M;
+    const long cs = A.g.cstride;
+    S ax = 0.5 * (M::load(A.grad, (var * 3 + 0) * cs + l) + M::load(A.grad, (var * 3 + 0) * cs + r));
+    S ay = 0.5 * (M::load(A.grad, (var * 3 + 1) * cs + l) + M::load(A.grad, (var * 3 + 1) * cs + r));
+    S az = 0.5 * (M::load(A.grad, (var * 3 + 2) * cs + l) + M::load(A.grad, (var * 3 + 2) * cs + r));
+    S avg_dot_ehat = ax * ehat.x + ay * ehat.y + az * ehat.z;
+    S correction = avg_dot_ehat - (vr - vl) / len_e;
+    Vec3<S> o;
+    o.x = ax - correction * n.x / ehat_dot_n;
+    o.y = ay - correction * n.y / ehat_dot_n;
+    o.z = az - correction * n.z / ehat_dot_n;
+    return o;
+}
+
+template <int DIM, typename S>
+IBIS_HD void face_viscous_flux(const FvArgs<S>& A, int f, Flux5<S>& F) {
+    typedef mem<S> M;
+    const GridDev& g = A.g;
+    const long cs = g.cstride, fs_ = g.fstride;
+    const int l = g.f_left[f], r = g.f_right[f];
+    const bool lv = l < g.n_cells, rv = r < g.n_cells;
+    const Vec3<S> n = {S(g.f_n[f]), S(g.f_n[fs_ + f]), S(g.f_n[2 * fs_ + f])};
+    Vec3<S> gT, gvx, gvy, gvz;
+    if (!lv || !rv) {                                         // viscous_flux.cpp:94-96
+        const int ic = lv ? l : r;
+        gT = {M::load(A.grad, (V_TVISC * 3 + 0) * cs + ic), M::load(A.grad, (V_TVISC * 3 + 1) * cs + ic),
+              M::load(A.grad, (V_TVISC * 3 + 2) * cs + ic)};
+        gvx = {M::load(A.grad, (V_VX * 3 + 0) * cs + ic), M::load(A.grad, (V_VX * 3 + 1) * cs + ic),
+               M::load(A.grad, (V_VX * 3 + 2) * cs + ic)};
+        gvy = {M::load(A.grad, (V_VY * 3 + 0) * cs + ic), M::load(A.grad, (V_VY * 3 + 1) * cs + ic),
+               M::load(A.grad, (V_VY * 3 + 2) * cs + ic)};
+        gvz = {M::load(A.grad, (V_VZ * 3 + 0) * cs + ic), M::load(A.grad, (V_VZ * 3 + 1) * cs + ic),
+               M::load(A.grad, (V_VZ * 3 + 2) * cs + ic)};
+    } else {                                                  // viscous_flux.cpp:53-80
+        const S ex = S(g.cx[r]) - S(g.cx[l]);
+        const S ey = S(g.cy[r]) - S(g.cy[l]);
+        const S ez = S(g.cz[r]) - S(g.cz[l]);
+        const S len_e = sqrt_(ex * ex + ey * ey + ez * ez);
+        const Vec3<S> ehat = {ex / len_e, ey / len_e, ez / len_e};
+        const S ehat_dot_n = ehat.x * n.x + ehat.y * n.y + ehat.z * n.z;
+        gvx = hasselbacher(A, V_VX, M::load(A.fs[F_VX], l), M::load(A.fs[F_VX], r), l, r, ehat, n,
+                           len_e, ehat_dot_n);
+        gvy = hasselbacher(A, V_VY, M::load(A.fs[F_VY], l), M::load(A.fs[F_VY], r), l, r, ehat, n,
+                           len_e, ehat_dot_n);
+        gvz = hasselbacher(A, V_VZ, M::load(A.fs[F_VZ], l), M::load(A.fs[F_VZ], r), l, r, ehat, n,
+                           len_e, ehat_dot_n);
+        gT = hasselbacher(A, V_TVISC, M::load(A.fs[F_T], l), M::load(A.fs[F_T], r), l, r, ehat, n,
+                          len_e, ehat_dot_n);
+    }
+    // face flow state: average_flow_states_pT + update_thermo_from_pT
+    // (gas/flow_state.h:89-91, gas/gas_state.h:108-113, viscous_flux.cpp:103-104)
+    const S p = 0.5 * (M::load(A.fs[F_P], l) + M::load(A.fs[F_P], r));
+    const S T = 0.5 * (M::load(A.fs[F_T], l) + M::load(A.fs[F_T], r));
+    const S rho = rho_from_pT(p, T, A.gas.R);
+    // Vector3s::average_vectors (util/vector3.h)
+    const S vx = 0.5 * (M::load(A.fs[F_VX], l) + M::load(A.fs[F_VX], r));
+    const S vy = 0.5 * (M::load(A.fs[F_VY], l) + M::load(A.fs[F_VY], r));
+    const S vz = 0.5 * (M::load(A.fs[F_VZ], l) + M::load(A.fs[F_VZ], r));
+    A.face_T[f] = re(T);
+    A.face_rho[f] = re(rho);
+
+    const S mu = viscosity(T, A.mu0, A.T0, A.Ts);
+    const S k = conductivity(viscosity(T, A.mu0, A.T0, A.Ts), A.gas.Cp, A.Pr);
+    const S lambda = -2.0 / 3.0 * mu;
+    const S bulk = lambda * (gvx.x + gvy.y + gvz.z);
+    const S tau_xx = 2.0 * mu * gvx.x + bulk;
+    const S tau_yy = 2.0 * mu * gvy.y + bulk;
+    const S tau_zz = 2.0 * mu * gvz.z + bulk;
+    const S tau_xy = mu * (gvx.y + gvy.x);
+    const S tau_xz = mu * (gvx.z + gvz.x);
+    const S tau_yz = mu * (gvy.z + gvz.y);
+    const S theta_x = vx * tau_xx + vy * tau_xy + vz * tau_xz + k * gT.x;
+    const S theta_y = vx * tau_xy + vy * tau_yy + vz * tau_yz + k * gT.y;
+    const S theta_z = vx * tau_xz + vy * tau_yz + vz * tau_zz + k * gT.z;
+    F.mx -= n.x * tau_xx + n.y * tau_xy + n.z * tau_xz;
+    F.my -= n.x * tau_xy + n.y * tau_yy + n.z * tau_yz;
+    if (DIM == 3) F.mz -= n.x * tau_xz + n.y * tau_yz + n.z * tau_zz;
+    F.energy -= n.x * theta_x + n.y * theta_y + n.z * theta_z;
+}
+
+// ---------------------------------------------------------------------------------------
+// general path, interface kernels: write / update the face flux array
+// ---------------------------------------------------------------------------------------
+template <int DIM, int FLUX, typename S>
+IBIS_HD void face_flux_body(const FvArgs<S>& A, int f) {
+    typedef mem<S> M;
+    const long fs_ = A.g.fstride;
+    Flux5<S> F = face_convective_flux<DIM, FLUX>(A, f);
+    M::store(A.flux, 0 * fs_ + f, F.mass);
+    M::store(A.flux, 1 * fs_ + f, F.mx);
+    M::store(A.flux, 2 * fs_ + f, F.my);
+    if (DIM == 3) M::store(A.flux, 3 * fs_ + f, F.mz);
+    M::store(A.flux, 4 * fs_ + f, F.energy);
+}
+
+template <int DIM, typename S>
+IBIS_HD void face_viscous_body(const FvArgs<S>& A, int f) {
+    typedef mem<S> M;
+    const long fs_ = A.g.fstride;
+    Flux5<S> F;
+    F.mass = S(0.0);
+    F.mx = M::load(A.flux, 1 * fs_ + f);
+    F.my = M::load(A.flux, 2 * fs_ + f);
+    F.mz = (DIM == 3) ? M::load(A.flux, 3 * fs_ + f) : S(0.0);
+    F.energy = M::load(A.flux, 4 * fs_ + f);
+    face_viscous_flux<DIM>(A, f, F);
+    M::store(A.flux, 1 * fs_ + f, F.mx);
+    M::store(A.flux, 2 * fs_ + f, F.my);
+    if (DIM == 3) M::store(A.flux, 3 * fs_ + f, F.mz);
+    M::store(A.flux, 4 * fs_ + f, F.energy);
+}
+
+// flux_surface_integral from the stored face fluxes (finite_volume.cpp:221-256)
+template <int DIM, typename S>
+IBIS_HD void integral_body(const FvArgs<S>& A, int c) {
+    typedef mem<S> M;
+    const GridDev& g = A.g;
+    const long cs = g.cstride, fs_ = g.fstride;
+    S d_mass = S(0.0), d_mx = S(0.0), d_my = S(0.0), d_mz = S(0.0), d_e = S(0.0);
+    for (int j = 0; j < MAXF; j++) {
+        if (j >= g.max_faces) break;
+        const int f = g.cf_face[j * cs + c];
+        if (f < 0) break;
+        const S area = -S(g.f_area[f]) * (double)g.cf_out[j * cs + c];
+        d_mass += M::load(A.flux, 0 * fs_ + f) * area;
+        d_mx += M::load(A.flux, 1 * fs_ + f) * area;
+        d_my += M::load(A.flux, 2 * fs_ + f) * area;
+        if (DIM == 3) d_mz += M::load(A.flux, 3 * fs_ + f) * area;
+        d_e += M::load(A.flux, 4 * fs_ + f) * area;
+    }
+    const S vol = S(g.volume[c]);
+    M::store(A.dudt[0], c, d_mass / vol);
+    M::store(A.dudt[1], c, d_mx / vol);
+    M::store(A.dudt[2], c, d_my / vol);
+    if (DIM == 3) M::store(A.dudt[3], c, d_mz / vol);
+    M::store(A.dudt[4], c, d_e / vol);
+}
+
+// ---------------------------------------------------------------------------------------
+// fast path (inviscid): owner-computes flux + surface integral of one cell, no face
+// temporaries in memory.  Same per-face arithmetic, same in-cell summation order.
+// ---------------------------------------------------------------------------------------
+template <int DIM, int FLUX, typename S>
+IBIS_HD void cell_residual_body(const FvArgs<S>& A, int c) {
+    typedef mem<S> M;
+    const GridDev& g = A.g;
+    const long cs = g.cstride;
+    S d_mass = S(0.0), d_mx = S(0.0), d_my = S(0.0), d_mz = S(0.0), d_e = S(0.0);
+    for (int j = 0; j < MAXF; j++) {
+        if (j >= g.max_faces) break;
+        const int f = g.cf_face[j * cs + c];
+        if (f < 0) break;
+        const Flux5<S> F = face_convective_flux<DIM, FLUX>(A, f);
+        const S area = -S(g.f_area[f]) * (double)g.cf_out[j * cs + c];
+        d_mass += F.mass * area;
+        d_mx += F.mx * area;
+        d_my += F.my * area;
+        if (DIM == 3) d_mz += F.mz * area;
+        d_e += F.energy * area;
+    }
+    const S vol = S(g.volume[c]);
+    M::store(A.dudt[0], c, d_mass / vol);
+    M::store(A.dudt[1], c, d_mx / vol);
+    M::store(A.dudt[2], c, d_my / vol);
+    if (DIM == 3) M::store(A.dudt[3], c, d_mz / vol);
+    M::store(A.dudt[4], c, d_e / vol);
+}
+
+// ---------------------------------------------------------------------------------------
+// estimate_dt: local time step of one cell (finite_volume.cpp:145-180)
+// ---------------------------------------------------------------------------------------
+// The reduction takes real_part(local_dt); real parts of a dual evaluation equal the double
+// evaluation, so this runs in double on the real parts for both scalar types.
+template <typename S>
+IBIS_HD double local_dt_body(const FvArgs<S>& A, int c) {
+    typedef mem<S> M;
+    const GridDev& g = A.g;
+    const long cs = g.cstride, fs_ = g.fstride;
+    const double vx = re(M::load(A.fs[F_VX], c)), vy = re(M::load(A.fs[F_VY], c)),
+                 vz = re(M::load(A.fs[F_VZ], c));
+    double sr_c = 0.0, sr_v = 0.0;
+    const double volume = g.volume[c];
+    const double R = re(A.gas.R), gamma = re(A.gas.gamma), Cp = re(A.gas.Cp);
+    const double a = speed_of_sound(re(M::load(A.fs[F_T], c)), R, gamma);
+    for (int j = 0; j < MAXF; j++) {
+        if (j >= g.max_faces) break;
+        const int f = g.cf_face[j * cs + c];
+        if (f < 0) break;
+        const double area = g.f_area[f];
+        const double dot = vx * g.f_n[f] + vy * g.f_n[fs_ + f] + vz * g.f_n[2 * fs_ + f];
+        const double sig_vel = fabs(dot) + a;
+        sr_c += sig_vel * area;
+        if (A.viscous) {
+            const double Tf = A.face_T[f];
+            const double mu = viscosity(Tf, re(A.mu0), re(A.T0), re(A.Ts));
+            const double k = conductivity(mu, Cp, re(A.Pr));
+            const double rho = A.face_rho[f];
+            const double Pr = mu * Cp / k;
+            const double tmp = (gamma / rho) * (mu / Pr) * area * area;
+            sr_v += tmp / volume;
+        }
+    }
+    return volume / (sr_c + A.signal_factor * sr_v);
+}
+
+}  // namespace ib

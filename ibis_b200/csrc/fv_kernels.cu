@@ -1,0 +1,227 @@
+// fv_kernels.cu -- sm_100a kernels of the finite-volume residual:
+//   k_bc            ghost-cell fills of every boundary tag in one launch
+//   k_wls_r         least-squares r-factors (setup)
+//   k_grad_limit    pass G: all WLS gradients + Barth-Jespersen limiters of a cell, fused
+//   k_residual      pass F: reconstruct + rotate + flux + rotate back + surface integral,
+//                   owner-computes per cell (no face temporaries, no atomics)
+//   k_face_flux / k_face_viscous / k_integral   general (viscous) path through a face array
+//   k_local_dt_min  local time step + block min
+// One thread per cell / face, SoA loads coalesced along the cell index, neighbour gathers
+// served by L1/L2.  Built with --fmad=false: arithmetic is bit-for-bit the reference's.
+#include <cuda_runtime.h>
+
+#include "context.h"
+
+namespace ib {
+
+#define CUDA_CHECK_LAUNCH(c)                                                             \
+    do {                                                                                 \
+        cudaError_t e__ = cudaGetLastError();                                            \
+        if (e__ != cudaSuccess && (c)->last_error.empty())                               \
+            (c)->last_error = std::string("kernel launch: ") + cudaGetErrorString(e__);  \
+        (c)->launches++;                                                                 \
+    } while (0)
+
+static inline int nblocks(int64_t n, int bs) { return (int)((n + bs - 1) / bs); }
+
+template <typename S>
+__global__ void __launch_bounds__(128) k_bc(const FvArgs<S> A, int phase) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < A.g.n_bfaces) bc_body(A, k, phase);
+}
+
+__global__ void __launch_bounds__(256) k_wls_r(const GridDev g, double* r_out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < g.n_cells) wls_r_body(g, r_out, c);
+}
+
+struct VarList {
+    int vars[5];
+    int src[5];
+};
+
+template <int DIM, int NV, typename S>
+__global__ void __launch_bounds__(256) k_grad_limit(const FvArgs<S> A, const VarList vl,
+                                                     const int do_limit) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < A.g.n_grad) grad_limit_body<DIM, NV>(A, c, vl.vars, vl.src, do_limit != 0);
+}
+
+template <int DIM, int FLUX, typename S>
+__global__ void __launch_bounds__(128) k_residual(const FvArgs<S> A) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < A.g.n_owned) cell_residual_body<DIM, FLUX>(A, c);
+}
+
+template <int DIM, int FLUX, typename S>
+__global__ void __launch_bounds__(128) k_face_flux(const FvArgs<S> A) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f < A.g.n_faces) face_flux_body<DIM, FLUX>(A, f);
+}
+
+template <int DIM, typename S>
+__global__ void __launch_bounds__(128) k_face_viscous(const FvArgs<S> A) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f < A.g.n_faces) face_viscous_body<DIM>(A, f);
+}
+
+template <int DIM, typename S>
+__global__ void __launch_bounds__(256) k_integral(const FvArgs<S> A) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < A.g.n_owned) integral_body<DIM>(A, c);
+}
+
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double w = __shfl_xor_sync(0xffffffffu, v, o);
+        v = (w < v) ? w : v;
+    }
+    return v;
+}
+
+// local dt of every owned cell, min over the block -> partial[blockIdx.x]
+template <typename S>
+__global__ void __launch_bounds__(256) k_local_dt_min(const FvArgs<S> A, double* partial) {
+    __shared__ double sm[8];
+    double v = INFINITY;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < A.g.n_owned;
+         c += gridDim.x * blockDim.x) {
+        const double d = local_dt_body(A, c);
+        v = (d < v) ? d : v;                                   // Kokkos::min(dt_local, dt_utd)
+    }
+    v = warp_min(v);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        v = (threadIdx.x < (blockDim.x >> 5)) ? sm[threadIdx.x] : INFINITY;
+        v = warp_min(v);
+        if (threadIdx.x == 0) partial[blockIdx.x] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_final_min(const double* partial, int n, double* out) {
+    __shared__ double sm[8];
+    double v = INFINITY;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) v = (partial[i] < v) ? partial[i] : v;
+    v = warp_min(v);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        v = (threadIdx.x < (blockDim.x >> 5)) ? sm[threadIdx.x] : INFINITY;
+        v = warp_min(v);
+        if (threadIdx.x == 0) out[0] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------
+template <typename S>
+void launch_bc(ibis_b200_ctx* c, const FvArgs<S>& A, int phase) {
+    if (A.g.n_bfaces == 0) return;
+    k_bc<S><<<nblocks(A.g.n_bfaces, 128), 128, 0, c->stream>>>(A, phase);
+    CUDA_CHECK_LAUNCH(c);
+}
+template void launch_bc<double>(ibis_b200_ctx*, const FvArgs<double>&, int);
+template void launch_bc<dual>(ibis_b200_ctx*, const FvArgs<dual>&, int);
+
+void launch_wls_r(ibis_b200_ctx* c, double* r_out) {
+    k_wls_r<<<nblocks(c->g.n_cells, 256), 256, 0, c->stream>>>(c->g, r_out);
+    CUDA_CHECK_LAUNCH(c);
+}
+
+template <typename S>
+void launch_grad_limit(ibis_b200_ctx* c, const FvArgs<S>& A, bool viscous_pass) {
+    VarList vl;
+    const int nb = nblocks(A.g.n_grad, 256);
+    if (viscous_pass) {
+        // ViscousFlux::compute_viscous_gradient (viscous_flux.cpp:122-130): T, vx, vy, vz
+        const int vars[4] = {V_TVISC, V_VX, V_VY, V_VZ};
+        const int src[4] = {F_T, F_VX, F_VY, F_VZ};
+        for (int i = 0; i < 4; i++) { vl.vars[i] = vars[i]; vl.src[i] = src[i]; }
+        if (A.g.dim == 3)
+            k_grad_limit<3, 4, S><<<nb, 256, 0, c->stream>>>(A, vl, 0);
+        else
+            k_grad_limit<2, 3, S><<<nb, 256, 0, c->stream>>>(A, vl, 0);   // vz == 0 in 2-D
+    } else {
+        // compute_convective_gradient + compute_limiters (convective_flux.cpp:181-209,423-462)
+        const int vars[5] = {V_RHO, V_TH2, V_VX, V_VY, V_VZ};
+        const int src[5] = {F_RHO, A.th2, F_VX, F_VY, F_VZ};
+        for (int i = 0; i < 5; i++) { vl.vars[i] = vars[i]; vl.src[i] = src[i]; }
+        if (A.g.dim == 3)
+            k_grad_limit<3, 5, S><<<nb, 256, 0, c->stream>>>(A, vl, A.limiter_on);
+        else
+            k_grad_limit<2, 4, S><<<nb, 256, 0, c->stream>>>(A, vl, A.limiter_on);
+    }
+    CUDA_CHECK_LAUNCH(c);
+}
+template void launch_grad_limit<double>(ibis_b200_ctx*, const FvArgs<double>&, bool);
+template void launch_grad_limit<dual>(ibis_b200_ctx*, const FvArgs<dual>&, bool);
+
+#define DISPATCH_FLUX(KERNEL, DIMV, N, BS)                                                   \
+    switch (c->cfg.flux_calculator) {                                                        \
+        case FLUX_HANEL: KERNEL<DIMV, FLUX_HANEL, S><<<nblocks(N, BS), BS, 0, c->stream>>>(A); break;   \
+        case FLUX_AUSMDV: KERNEL<DIMV, FLUX_AUSMDV, S><<<nblocks(N, BS), BS, 0, c->stream>>>(A); break; \
+        case FLUX_LDFSS2: KERNEL<DIMV, FLUX_LDFSS2, S><<<nblocks(N, BS), BS, 0, c->stream>>>(A); break; \
+        default: KERNEL<DIMV, FLUX_RUSANOV, S><<<nblocks(N, BS), BS, 0, c->stream>>>(A); break;         \
+    }
+
+template <typename S>
+void launch_residual(ibis_b200_ctx* c, const FvArgs<S>& A) {
+    if (A.g.dim == 3) {
+        DISPATCH_FLUX(k_residual, 3, A.g.n_owned, 128)
+    } else {
+        DISPATCH_FLUX(k_residual, 2, A.g.n_owned, 128)
+    }
+    CUDA_CHECK_LAUNCH(c);
+}
+template void launch_residual<double>(ibis_b200_ctx*, const FvArgs<double>&);
+template void launch_residual<dual>(ibis_b200_ctx*, const FvArgs<dual>&);
+
+template <typename S>
+void launch_face_flux(ibis_b200_ctx* c, const FvArgs<S>& A) {
+    if (A.g.dim == 3) {
+        DISPATCH_FLUX(k_face_flux, 3, A.g.n_faces, 128)
+    } else {
+        DISPATCH_FLUX(k_face_flux, 2, A.g.n_faces, 128)
+    }
+    CUDA_CHECK_LAUNCH(c);
+}
+template void launch_face_flux<double>(ibis_b200_ctx*, const FvArgs<double>&);
+template void launch_face_flux<dual>(ibis_b200_ctx*, const FvArgs<dual>&);
+
+template <typename S>
+void launch_face_viscous(ibis_b200_ctx* c, const FvArgs<S>& A) {
+    if (A.g.dim == 3)
+        k_face_viscous<3, S><<<nblocks(A.g.n_faces, 128), 128, 0, c->stream>>>(A);
+    else
+        k_face_viscous<2, S><<<nblocks(A.g.n_faces, 128), 128, 0, c->stream>>>(A);
+    CUDA_CHECK_LAUNCH(c);
+}
+template void launch_face_viscous<double>(ibis_b200_ctx*, const FvArgs<double>&);
+template void launch_face_viscous<dual>(ibis_b200_ctx*, const FvArgs<dual>&);
+
+template <typename S>
+void launch_integral(ibis_b200_ctx* c, const FvArgs<S>& A) {
+    if (A.g.dim == 3)
+        k_integral<3, S><<<nblocks(A.g.n_owned, 256), 256, 0, c->stream>>>(A);
+    else
+        k_integral<2, S><<<nblocks(A.g.n_owned, 256), 256, 0, c->stream>>>(A);
+    CUDA_CHECK_LAUNCH(c);
+}
+template void launch_integral<double>(ibis_b200_ctx*, const FvArgs<double>&);
+template void launch_integral<dual>(ibis_b200_ctx*, const FvArgs<dual>&);
+
+template <typename S>
+void launch_local_dt_min(ibis_b200_ctx* c, const FvArgs<S>& A, double* d_out) {
+    const int nb = reduction_blocks(A.g.n_owned);
+    k_local_dt_min<S><<<nb, 256, 0, c->stream>>>(A, c->d_partials);
+    CUDA_CHECK_LAUNCH(c);
+    k_final_min<<<1, 256, 0, c->stream>>>(c->d_partials, nb, d_out);
+    CUDA_CHECK_LAUNCH(c);
+}
+template void launch_local_dt_min<double>(ibis_b200_ctx*, const FvArgs<double>&, double*);
+template void launch_local_dt_min<dual>(ibis_b200_ctx*, const FvArgs<dual>&, double*);
+
+}  // namespace ib

@@ -1,0 +1,81 @@
+// solver_bodies.h -- per-index bodies of the state-vector kernels: primitive/conserved
+// conversion, Runge-Kutta updates, norms, bad-cell test, JFNK pack/unpack.
+#pragma once
+
+#include "fv_bodies.h"
+
+namespace ib {
+
+// conserved_to_primatives (finite_volume/primative_conserved_conversion.cpp:5-23); runs
+// over ALL rows including ghosts (fs.gas.size()), where 0/0 gives NaN as in the reference.
+template <int DIM, typename S>
+IBIS_HD void cons_to_prim_body(S* const* cq, S* const* fs, const Gas<S>& gas, long i) {
+    typedef mem<S> M;
+    const S rho = M::load(cq[0], i);
+    const S vx = M::load(cq[1], i) / rho;
+    const S vy = M::load(cq[2], i) / rho;
+    const S vz = (DIM == 3) ? M::load(cq[3], i) / rho : S(0.0);
+    const S ke = 0.5 * (vx * vx + vy * vy + vz * vz);
+    const S u = M::load(cq[4], i) / rho - ke;
+    M::store(fs[F_RHO], i, rho);
+    M::store(fs[F_VX], i, vx);
+    M::store(fs[F_VY], i, vy);
+    M::store(fs[F_VZ], i, vz);
+    M::store(fs[F_E], i, u);
+    const S T = u / gas.Cv;                                   // update_thermo_from_rhou
+    M::store(fs[F_T], i, T);
+    M::store(fs[F_P], i, p_from_rhoT(rho, T, gas.R));
+}
+
+// primatives_to_conserved (primative_conserved_conversion.cpp:32-50)
+template <int DIM, typename S>
+IBIS_HD void prim_to_cons_body(S* const* cq, S* const* fs, long i) {
+    typedef mem<S> M;
+    const S vx = M::load(fs[F_VX], i), vy = M::load(fs[F_VY], i), vz = M::load(fs[F_VZ], i);
+    const S rho = M::load(fs[F_RHO], i);
+    M::store(cq[0], i, rho);
+    M::store(cq[1], i, rho * vx);
+    M::store(cq[2], i, rho * vy);
+    if (DIM == 3) M::store(cq[3], i, rho * vz);
+    const S ke = 0.5 * (vx * vx + vy * vy + vz * vz);
+    M::store(cq[4], i, rho * (ke + M::load(fs[F_E], i)));
+}
+
+// U1 = U0 + dUdt*dt (conserved_quantities.cpp:80-94; in place: :26-38)
+template <int DIM, typename S>
+IBIS_HD void apply_dt_body(S* const* u0, S* const* u1, S* const* k, double dt, long i) {
+    typedef mem<S> M;
+#pragma unroll
+    for (int q = 0; q < 5; q++) {
+        if (DIM == 2 && q == 3) continue;
+        M::store(u1[q], i, M::load(u0[q], i) + M::load(k[q], i) * dt);
+    }
+}
+
+// L2_norms contributions (conserved_quantities.cpp:43-58), real parts:
+// out = {global, mass, mx, my, mz, energy}
+template <int DIM, typename S>
+IBIS_HD void l2_body(S* const* cq, long i, double* out) {
+    typedef mem<S> M;
+    const double m = re(M::load(cq[0], i)), mx = re(M::load(cq[1], i)), my = re(M::load(cq[2], i));
+    const double mz = (DIM == 3) ? re(M::load(cq[3], i)) : 0.0;
+    const double e = re(M::load(cq[4], i));
+    out[1] = m * m;
+    out[2] = mx * mx;
+    out[3] = my * my;
+    out[4] = mz * mz;
+    out[5] = e * e;
+    out[0] = m * m + mx * mx + my * my + mz * mz + e * e;
+}
+
+// count_bad_cells predicate (finite_volume.cpp:263-266; dual: isnan/isinf test both parts,
+// util/dual.h:306-314)
+IBIS_HD bool bad_cell(double T, double rho) {
+    return T < 0.0 || rho < 0.0 || isnan(rho) || isinf(rho);
+}
+IBIS_HD bool bad_cell(const dual& T, const dual& rho) {
+    return T.re < 0.0 || rho.re < 0.0 || isnan(rho.re) || isnan(rho.du) || isinf(rho.re) ||
+           isinf(rho.du);
+}
+
+}  // namespace ib

@@ -1,0 +1,442 @@
+"""ctypes binding of libibis_b200.so (include/ibis_b200.h) and the flattening of the
+reference's grid arrays + config.json into its POD structs.
+
+The product path loads ``ibis_b200/lib/libibis_b200.so`` (sm_100a CUDA).  There is no CPU
+fallback: if the library is missing or no CUDA device is usable, calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_LIB = os.path.join(HERE, "lib", "libibis_b200.so")
+
+FLUX = {"hanel": 0, "ausmdv": 1, "ldfss2": 2, "rusanov": 3}
+LIMITER = {"unlimited": 0, "barth_jespersen": 1}
+THERMO = {"rho_p": 0, "rho_T": 1, "rho_u": 2, "p_T": 3}
+BC = {"flow_state_copy": 0, "internal_copy": 1, "internal_copy_reflect_normal": 2,
+      "internal_vel_copy_reflect": 3, "fix_temperature": 4, "subsonic_inflow": 5,
+      "subsonic_outflow": 6}
+PHASE = {"pre_reconstruction": 0, "pre_viscous_grad": 1}
+
+
+class IbisB200Error(RuntimeError):
+    pass
+
+
+class BcAction(C.Structure):
+    _fields_ = [("tag", C.c_int32), ("phase", C.c_int32), ("type", C.c_int32),
+                ("reserved", C.c_int32), ("params", C.c_double * 8)]
+
+
+_i64p = C.POINTER(C.c_int64)
+_i32p = C.POINTER(C.c_int32)
+_dp = C.POINTER(C.c_double)
+
+
+class GridDesc(C.Structure):
+    _fields_ = [("dim", C.c_int32), ("n_tags", C.c_int32), ("n_cells", C.c_int64),
+                ("n_ghost", C.c_int64), ("n_faces", C.c_int64),
+                ("face_left", _i64p), ("face_right", _i64p), ("face_area", _dp),
+                ("face_norm", _dp), ("face_tan1", _dp), ("face_tan2", _dp), ("face_centre", _dp),
+                ("cell_face_offsets", _i64p), ("cell_face_ids", _i64p), ("cell_outsigns", _i32p),
+                ("cell_neighbours", _i64p), ("cell_volume", _dp), ("cell_centroid", _dp),
+                ("tag_offsets", _i64p), ("tag_faces", _i64p), ("n_owned", C.c_int64)]
+
+
+class Config(C.Structure):
+    _fields_ = [("flux_calculator", C.c_int32), ("reconstruction_order", C.c_int32),
+                ("limiter", C.c_int32), ("thermo_interpolator", C.c_int32),
+                ("limiter_epsilon", C.c_double), ("ldfss_delta", C.c_double),
+                ("viscous", C.c_int32), ("n_bc_actions", C.c_int32),
+                ("viscous_signal_factor", C.c_double),
+                ("R", C.c_double), ("Cv", C.c_double), ("Cp", C.c_double), ("gamma", C.c_double),
+                ("mu0", C.c_double), ("T0", C.c_double), ("Ts", C.c_double), ("Pr", C.c_double),
+                ("bc_actions", C.POINTER(BcAction))]
+
+
+def _flow_state_params(fs):
+    return [fs["rho"], fs["p"], fs["T"], fs["energy"], fs["vx"], fs["vy"], fs["vz"], 0.0]
+
+
+def flatten_config(config, tags):
+    """config: dict with the reference's config.json schema; tags: boundary tags in the
+    order of the grid's tag list (alphabetical).  Unknown names raise like the reference's
+    factories do (flux_calc.cpp:20-21, limiter.cpp:16-17, boundary.cpp:474-476)."""
+    cf = config["convective_flux"]
+    fc = cf["flux_calculator"]
+    if fc["type"] not in FLUX:
+        raise IbisB200Error("Unknown flux calculator")
+    cfgs = Config()
+    cfgs.flux_calculator = FLUX[fc["type"]]
+    cfgs.ldfss_delta = float(fc.get("delta", 2.0))
+    cfgs.reconstruction_order = int(cf["reconstruction_order"])
+    cfgs.limiter = LIMITER["barth_jespersen"]
+    cfgs.limiter_epsilon = 1e-25
+    cfgs.thermo_interpolator = THERMO["rho_u"]
+    if cfgs.reconstruction_order > 1:
+        lim = cf["limiter"]
+        if lim["type"] not in LIMITER:
+            raise IbisB200Error("Unknown limiter")
+        cfgs.limiter = LIMITER[lim["type"]]
+        cfgs.limiter_epsilon = float(lim.get("epsilon", 1e-25))
+        if cf["thermo_interpolator"] not in THERMO:
+            raise IbisB200Error("Unknown thermo interpolator")
+        cfgs.thermo_interpolator = THERMO[cf["thermo_interpolator"]]
+    vf = config["viscous_flux"]
+    cfgs.viscous = int(bool(vf["enabled"]))
+    cfgs.viscous_signal_factor = float(vf["signal_factor"])
+    gm = config["gas_model"]
+    cfgs.R, cfgs.Cv, cfgs.Cp, cfgs.gamma = (float(gm[k]) for k in ("R", "Cv", "Cp", "gamma"))
+    tp = config["transport_properties"]
+    if tp["viscosity"]["type"] != "sutherland":
+        raise IbisB200Error("Unkown viscosity model")
+    if tp["thermal_conductivity"]["type"] != "constant_prandtl_number":
+        raise IbisB200Error("Unkown thermal conductivity model")
+    cfgs.mu0 = float(tp["viscosity"]["mu_0"])
+    cfgs.T0 = float(tp["viscosity"]["T_0"])
+    cfgs.Ts = float(tp["viscosity"]["T_s"])
+    cfgs.Pr = float(tp["thermal_conductivity"]["Pr"])
+    actions = []
+    bnds = config["grid"]["boundaries"]
+    for t, tag in enumerate(tags):
+        b = bnds[tag]
+        if b.get("post_convective_flux"):
+            raise IbisB200Error("post_convective_flux actions (constant_flux) are not on the hot path")
+        for phase in ("pre_reconstruction", "pre_viscous_grad"):
+            for act in b.get(phase, []):
+                if act["type"] not in BC:
+                    raise IbisB200Error("Unknown boundary action")
+                a = BcAction()
+                a.tag, a.phase, a.type = t, PHASE[phase], BC[act["type"]]
+                p = [0.0] * 8
+                if act["type"] in ("flow_state_copy", "subsonic_inflow"):
+                    p = _flow_state_params(act["flow_state"])
+                elif act["type"] == "fix_temperature":
+                    p[0] = float(act["temperature"])
+                elif act["type"] == "subsonic_outflow":
+                    p[0] = float(act["pressure"])
+                for i in range(8):
+                    a.params[i] = p[i]
+                actions.append(a)
+    arr = (BcAction * max(len(actions), 1))(*actions)
+    cfgs.n_bc_actions = len(actions)
+    cfgs.bc_actions = C.cast(arr, C.POINTER(BcAction))
+    cfgs._keepalive = arr
+    return cfgs
+
+
+def _as(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+def flatten_grid(g, n_owned=0):
+    """g: ibis_b200.grid.Grid (or a dict from the reference with the same keys)."""
+    get = (lambda k: g[k]) if isinstance(g, dict) else (lambda k: getattr(g, k))
+    tags = get("tags")
+    names = sorted(tags.keys())
+    keep = {}
+
+    def p(name, dtype, ptr):
+        a = _as(get(name), dtype)
+        keep[name] = a
+        return a.ctypes.data_as(ptr)
+
+    d = GridDesc()
+    d.dim = int(get("dim"))
+    d.n_tags = len(names)
+    d.n_cells = int(get("n_cells"))
+    d.n_ghost = int(get("n_ghost"))
+    d.n_faces = int(get("n_faces"))
+    d.face_left = p("face_left", np.int64, _i64p)
+    d.face_right = p("face_right", np.int64, _i64p)
+    d.face_area = p("face_area", np.float64, _dp)
+    d.face_norm = p("face_norm", np.float64, _dp)
+    d.face_tan1 = p("face_tan1", np.float64, _dp)
+    d.face_tan2 = p("face_tan2", np.float64, _dp)
+    d.face_centre = p("face_centre", np.float64, _dp)
+    d.cell_face_offsets = p("cell_face_offsets", np.int64, _i64p)
+    d.cell_face_ids = p("cell_face_ids", np.int64, _i64p)
+    d.cell_outsigns = p("cell_outsigns", np.int32, _i32p)
+    d.cell_neighbours = p("cell_neighbours", np.int64, _i64p)
+    d.cell_volume = p("cell_volume", np.float64, _dp)
+    d.cell_centroid = p("cell_centroid", np.float64, _dp)
+    offs = np.zeros(len(names) + 1, np.int64)
+    faces = []
+    for i, t in enumerate(names):
+        faces.append(_as(tags[t]["faces"], np.int64))
+        offs[i + 1] = offs[i] + len(faces[-1])
+    tf = np.concatenate(faces) if faces else np.zeros(0, np.int64)
+    tf = _as(tf, np.int64)
+    keep["tag_offsets"], keep["tag_faces"] = offs, tf
+    d.tag_offsets = offs.ctypes.data_as(_i64p)
+    d.tag_faces = tf.ctypes.data_as(_i64p)
+    d.n_owned = int(n_owned)
+    d._keepalive = keep
+    return d, names
+
+
+class Library:
+    """The loaded shared library with argtypes set."""
+
+    _cache = {}
+
+    @classmethod
+    def load(cls, path=None):
+        path = os.path.abspath(path or os.environ.get("IBIS_B200_LIB", DEFAULT_LIB))
+        if path not in cls._cache:
+            cls._cache[path] = cls(path)
+        return cls._cache[path]
+
+    def __init__(self, path):
+        if not os.path.exists(path):
+            raise IbisB200Error(
+                f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`"
+                " (nvcc, sm_100a). ibis_b200 has no CPU fallback.")
+        self.path = path
+        L = self.lib = C.CDLL(path)
+        vp, i, d, i64 = C.c_void_p, C.c_int, C.c_double, C.c_int64
+        ip = C.POINTER(C.c_int)
+        sig = {
+            "ibis_b200_create": [C.POINTER(vp), C.POINTER(GridDesc), C.POINTER(Config), i],
+            "ibis_b200_destroy": [vp], "ibis_b200_sync": [vp],
+            "ibis_b200_fs_create": [vp, i, ip], "ibis_b200_cq_create": [vp, i, ip],
+            "ibis_b200_vec_create": [vp, i64, ip], "ibis_b200_free": [vp, i],
+            "ibis_b200_fs_upload": [vp, i, vp, vp], "ibis_b200_fs_download": [vp, i, vp, vp],
+            "ibis_b200_cq_upload": [vp, i, vp, vp], "ibis_b200_cq_download": [vp, i, vp, vp],
+            "ibis_b200_vec_upload": [vp, i, vp], "ibis_b200_vec_download": [vp, i, vp],
+            "ibis_b200_copy": [vp, i, i], "ibis_b200_zero": [vp, i],
+            "ibis_b200_compute_dudt": [vp, i, i, i],
+            "ibis_b200_estimate_dt": [vp, i, C.POINTER(d)],
+            "ibis_b200_count_bad_cells": [vp, i, C.POINTER(C.c_uint64)],
+            "ibis_b200_cons_to_prim": [vp, i, i], "ibis_b200_prim_to_cons": [vp, i, i],
+            "ibis_b200_apply_time_derivative": [vp, i, i, i, d],
+            "ibis_b200_l2_norms": [vp, i, vp],
+            "ibis_b200_debug_gradients": [vp, i, vp, vp],
+            "ibis_b200_rk_step": [vp, i, i, i, vp, vp, d, d, d, C.POINTER(d), C.POINTER(d)],
+            "ibis_b200_rk_residual_norms": [vp, vp],
+            "ibis_b200_jfnk_set_dual": [vp, i, i, i],
+            "ibis_b200_jfnk_set_vector": [vp, i, i, d, i],
+            "ibis_b200_jfnk_eval_rhs": [vp, i, i], "ibis_b200_jfnk_apply_update": [vp, i, i],
+            "ibis_b200_vec_dot": [vp, i, i, C.POINTER(d)], "ibis_b200_vec_norm2": [vp, i, C.POINTER(d)],
+            "ibis_b200_vec_axpy": [vp, i, i, d], "ibis_b200_vec_scale": [vp, i, i, d],
+            "ibis_b200_vec_sub": [vp, i, i, i],
+            "ibis_b200_basis_create": [vp, i64, i, ip], "ibis_b200_basis_set_col": [vp, i, i, i],
+            "ibis_b200_arnoldi_mgs": [vp, i, i, i, i, vp],
+            "ibis_b200_basis_gemv": [vp, i, i, vp, i],
+            "ibis_b200_halo_setup": [vp, i, vp, vp, vp, vp, vp],
+            "ibis_b200_comm_init": [vp, vp, i, i], "ibis_b200_nccl_unique_id": [vp],
+        }
+        for name, args in sig.items():
+            f = getattr(L, name)
+            f.argtypes = args
+            f.restype = C.c_int
+        L.ibis_b200_last_error.argtypes = [vp]
+        L.ibis_b200_last_error.restype = C.c_char_p
+        L.ibis_b200_launch_count.argtypes = [vp]
+        L.ibis_b200_launch_count.restype = C.c_int64
+        L.ibis_b200_stream.argtypes = [vp]
+        L.ibis_b200_stream.restype = vp
+
+    EXPORTS = ["ibis_b200_last_error", "ibis_b200_launch_count", "ibis_b200_stream"]
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One ibis_b200_ctx: device grid + configuration + buffers.  Thin, 1:1 with the C ABI."""
+
+    def __init__(self, grid, config, device=-1, lib_path=None, n_owned=0):
+        self.L = Library.load(lib_path)
+        self.lib = self.L.lib
+        gd, self.tags = flatten_grid(grid, n_owned)
+        cf = flatten_config(config, self.tags)
+        self.dim = gd.dim
+        self.n_cons = gd.dim + 2
+        self.n_cells, self.n_ghost, self.n_faces = gd.n_cells, gd.n_ghost, gd.n_faces
+        self.n_total = gd.n_cells + gd.n_ghost
+        self.h = C.c_void_p()
+        rc = self.lib.ibis_b200_create(C.byref(self.h), C.byref(gd), C.byref(cf), int(device))
+        if rc != 0:
+            raise IbisB200Error(f"ibis_b200_create failed ({rc}): "
+                                f"{self.lib.ibis_b200_last_error(None).decode()}")
+
+    def close(self):
+        if self.h:
+            self.lib.ibis_b200_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, what):
+        if rc != 0:
+            raise IbisB200Error(f"{what} failed ({rc}): {self.lib.ibis_b200_last_error(self.h).decode()}")
+
+    # buffers
+    def fs_create(self, dual=False):
+        h = C.c_int(0)
+        self._ck(self.lib.ibis_b200_fs_create(self.h, int(dual), C.byref(h)), "fs_create")
+        return h.value
+
+    def cq_create(self, dual=False):
+        h = C.c_int(0)
+        self._ck(self.lib.ibis_b200_cq_create(self.h, int(dual), C.byref(h)), "cq_create")
+        return h.value
+
+    def vec_create(self, n):
+        h = C.c_int(0)
+        self._ck(self.lib.ibis_b200_vec_create(self.h, int(n), C.byref(h)), "vec_create")
+        return h.value
+
+    def basis_create(self, n, n_cols):
+        h = C.c_int(0)
+        self._ck(self.lib.ibis_b200_basis_create(self.h, int(n), int(n_cols), C.byref(h)), "basis_create")
+        return h.value
+
+    def free(self, h):
+        self._ck(self.lib.ibis_b200_free(self.h, h), "free")
+
+    def fs_upload(self, h, prim, prim_du=None):
+        a = _as(prim, np.float64).reshape(self.n_total, 7)
+        b = None if prim_du is None else _as(prim_du, np.float64).reshape(self.n_total, 7)
+        self._ck(self.lib.ibis_b200_fs_upload(self.h, h, _ptr(a), _ptr(b)), "fs_upload")
+
+    def fs_download(self, h, dual=False):
+        a = np.zeros((self.n_total, 7))
+        b = np.zeros((self.n_total, 7)) if dual else None
+        self._ck(self.lib.ibis_b200_fs_download(self.h, h, _ptr(a), _ptr(b)), "fs_download")
+        return (a, b) if dual else a
+
+    def cq_upload(self, h, cons, cons_du=None):
+        a = _as(cons, np.float64).reshape(self.n_total, self.n_cons)
+        b = None if cons_du is None else _as(cons_du, np.float64).reshape(self.n_total, self.n_cons)
+        self._ck(self.lib.ibis_b200_cq_upload(self.h, h, _ptr(a), _ptr(b)), "cq_upload")
+
+    def cq_download(self, h, dual=False):
+        a = np.zeros((self.n_total, self.n_cons))
+        b = np.zeros((self.n_total, self.n_cons)) if dual else None
+        self._ck(self.lib.ibis_b200_cq_download(self.h, h, _ptr(a), _ptr(b)), "cq_download")
+        return (a, b) if dual else a
+
+    def vec_upload(self, h, x):
+        a = _as(x, np.float64)
+        self._ck(self.lib.ibis_b200_vec_upload(self.h, h, _ptr(a)), "vec_upload")
+
+    def vec_download(self, h, n):
+        a = np.zeros(int(n))
+        self._ck(self.lib.ibis_b200_vec_download(self.h, h, _ptr(a)), "vec_download")
+        return a
+
+    def copy(self, dst, src):
+        self._ck(self.lib.ibis_b200_copy(self.h, dst, src), "copy")
+
+    def zero(self, h):
+        self._ck(self.lib.ibis_b200_zero(self.h, h), "zero")
+
+    def sync(self):
+        self._ck(self.lib.ibis_b200_sync(self.h), "sync")
+
+    def launch_count(self):
+        return int(self.lib.ibis_b200_launch_count(self.h))
+
+    # hot path
+    def compute_dudt(self, fs, dudt, allow_reconstruction=True):
+        self._ck(self.lib.ibis_b200_compute_dudt(self.h, fs, dudt, int(allow_reconstruction)), "compute_dudt")
+
+    def estimate_dt(self, fs):
+        v = C.c_double(0)
+        self._ck(self.lib.ibis_b200_estimate_dt(self.h, fs, C.byref(v)), "estimate_dt")
+        return v.value
+
+    def count_bad_cells(self, fs):
+        v = C.c_uint64(0)
+        self._ck(self.lib.ibis_b200_count_bad_cells(self.h, fs, C.byref(v)), "count_bad_cells")
+        return int(v.value)
+
+    def cons_to_prim(self, cq, fs):
+        self._ck(self.lib.ibis_b200_cons_to_prim(self.h, cq, fs), "cons_to_prim")
+
+    def prim_to_cons(self, cq, fs):
+        self._ck(self.lib.ibis_b200_prim_to_cons(self.h, cq, fs), "prim_to_cons")
+
+    def apply_time_derivative(self, u0, u1, dudt, dt):
+        self._ck(self.lib.ibis_b200_apply_time_derivative(self.h, u0, u1, dudt, float(dt)), "apply_time_derivative")
+
+    def l2_norms(self, cq):
+        out = np.zeros(6)
+        self._ck(self.lib.ibis_b200_l2_norms(self.h, cq, _ptr(out)), "l2_norms")
+        return out
+
+    def debug_gradients(self, var):
+        g = np.zeros((self.n_cells, 3))
+        l = np.zeros(self.n_cells)
+        self._ck(self.lib.ibis_b200_debug_gradients(self.h, var, _ptr(g), _ptr(l)), "debug_gradients")
+        return g, l
+
+    def rk_step(self, fs, cq, a_rows, b, cfl, dt_prev, t_remaining):
+        a = np.array([x for row in a_rows for x in row], dtype=np.float64)
+        if a.size == 0:
+            a = np.zeros(1)
+        bb = _as(b, np.float64)
+        dt, dts = C.c_double(0), C.c_double(0)
+        self._ck(self.lib.ibis_b200_rk_step(self.h, fs, cq, len(bb), _ptr(a), _ptr(bb), float(cfl),
+                                            float(dt_prev), float(t_remaining), C.byref(dt), C.byref(dts)),
+                 "rk_step")
+        return dt.value, dts.value
+
+    def rk_residual_norms(self):
+        out = np.zeros(6)
+        self._ck(self.lib.ibis_b200_rk_residual_norms(self.h, _ptr(out)), "rk_residual_norms")
+        return out
+
+    # JFNK
+    def jfnk_set_dual(self, cq, vec, cq_tmp):
+        self._ck(self.lib.ibis_b200_jfnk_set_dual(self.h, cq, vec, cq_tmp), "jfnk_set_dual")
+
+    def jfnk_set_vector(self, residual, vec, dt_star, result):
+        self._ck(self.lib.ibis_b200_jfnk_set_vector(self.h, residual, vec, float(dt_star), result), "jfnk_set_vector")
+
+    def jfnk_eval_rhs(self, residual, rhs):
+        self._ck(self.lib.ibis_b200_jfnk_eval_rhs(self.h, residual, rhs), "jfnk_eval_rhs")
+
+    def jfnk_apply_update(self, cq, du):
+        self._ck(self.lib.ibis_b200_jfnk_apply_update(self.h, cq, du), "jfnk_apply_update")
+
+    # vectors
+    def vec_dot(self, a, b):
+        v = C.c_double(0)
+        self._ck(self.lib.ibis_b200_vec_dot(self.h, a, b, C.byref(v)), "vec_dot")
+        return v.value
+
+    def vec_norm2(self, a):
+        v = C.c_double(0)
+        self._ck(self.lib.ibis_b200_vec_norm2(self.h, a, C.byref(v)), "vec_norm2")
+        return v.value
+
+    def vec_axpy(self, y, x, s):
+        self._ck(self.lib.ibis_b200_vec_axpy(self.h, y, x, float(s)), "vec_axpy")
+
+    def vec_scale(self, x, result, s):
+        self._ck(self.lib.ibis_b200_vec_scale(self.h, x, result, float(s)), "vec_scale")
+
+    def vec_sub(self, a, b, result):
+        self._ck(self.lib.ibis_b200_vec_sub(self.h, a, b, result), "vec_sub")
+
+    def basis_set_col(self, basis, col, vec):
+        self._ck(self.lib.ibis_b200_basis_set_col(self.h, basis, col, vec), "basis_set_col")
+
+    def arnoldi_mgs(self, basis, j, w, v):
+        h = np.zeros(j + 2)
+        self._ck(self.lib.ibis_b200_arnoldi_mgs(self.h, basis, j, w, v, _ptr(h)), "arnoldi_mgs")
+        return h
+
+    def basis_gemv(self, basis, m, y, out):
+        yy = _as(y, np.float64)
+        self._ck(self.lib.ibis_b200_basis_gemv(self.h, basis, int(m), _ptr(yy), out), "basis_gemv")

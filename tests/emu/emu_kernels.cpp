@@ -1,0 +1,313 @@
+// tests/emu/emu_kernels.cpp -- TEST HARNESS, not product code.
+//
+// Host stand-ins for the kernel launchers of ibis_b200/csrc/{fv,solver}_kernels.cu: the
+// same per-index bodies (fv_bodies.h, solver_bodies.h, physics.h, scalar.h) run in plain
+// loops, and the C-ABI layer (abi.cu) is compiled against host memory (IBIS_B200_EMU).
+// Purpose: the development container has no GPU, so this lets the numerics and the ABI
+// plumbing be checked against the reference before spending GPU time.  The result,
+// tests/emu/_build/libibis_b200_emu.so, is loaded only by tests (tests/emu_util.py) and is
+// never a fallback of the product: ibis_b200/lib.py loads libibis_b200.so or raises.
+#include <math.h>
+
+#include <algorithm>
+
+#include "comm.h"
+#include "context.h"
+#include "solver_bodies.h"
+
+namespace ib {
+
+int reduction_blocks(int64_t) { return 1; }
+
+template <typename S>
+void launch_bc(ibis_b200_ctx* c, const FvArgs<S>& A, int phase) {
+    for (int k = 0; k < A.g.n_bfaces; k++) bc_body(A, k, phase);
+    c->launches++;
+}
+template void launch_bc<double>(ibis_b200_ctx*, const FvArgs<double>&, int);
+template void launch_bc<dual>(ibis_b200_ctx*, const FvArgs<dual>&, int);
+
+void launch_wls_r(ibis_b200_ctx* c, double* r_out) {
+    for (int i = 0; i < c->g.n_cells; i++) wls_r_body(c->g, r_out, i);
+    c->launches++;
+}
+
+template <typename S>
+void launch_grad_limit(ibis_b200_ctx* c, const FvArgs<S>& A, bool viscous_pass) {
+    if (viscous_pass) {
+        const int vars[4] = {V_TVISC, V_VX, V_VY, V_VZ};
+        const int src[4] = {F_T, F_VX, F_VY, F_VZ};
+#pragma omp parallel for
+        for (int i = 0; i < A.g.n_grad; i++) {
+            if (A.g.dim == 3) grad_limit_body<3, 4>(A, i, vars, src, false);
+            else grad_limit_body<2, 3>(A, i, vars, src, false);
+        }
+    } else {
+        const int vars[5] = {V_RHO, V_TH2, V_VX, V_VY, V_VZ};
+        const int src[5] = {F_RHO, A.th2, F_VX, F_VY, F_VZ};
+#pragma omp parallel for
+        for (int i = 0; i < A.g.n_grad; i++) {
+            if (A.g.dim == 3) grad_limit_body<3, 5>(A, i, vars, src, A.limiter_on != 0);
+            else grad_limit_body<2, 4>(A, i, vars, src, A.limiter_on != 0);
+        }
+    }
+    c->launches++;
+}
+template void launch_grad_limit<double>(ibis_b200_ctx*, const FvArgs<double>&, bool);
+template void launch_grad_limit<dual>(ibis_b200_ctx*, const FvArgs<dual>&, bool);
+
+#define EMU_FLUX_LOOP(BODY, N)                                                          \
+    _Pragma("omp parallel for") for (int i = 0; i < (N); i++) {                         \
+        if (A.g.dim == 3) {                                                             \
+            switch (c->cfg.flux_calculator) {                                           \
+                case FLUX_HANEL: BODY<3, FLUX_HANEL>(A, i); break;                      \
+                case FLUX_AUSMDV: BODY<3, FLUX_AUSMDV>(A, i); break;                    \
+                case FLUX_LDFSS2: BODY<3, FLUX_LDFSS2>(A, i); break;                    \
+                default: BODY<3, FLUX_RUSANOV>(A, i); break;                            \
+            }                                                                           \
+        } else {                                                                        \
+            switch (c->cfg.flux_calculator) {                                           \
+                case FLUX_HANEL: BODY<2, FLUX_HANEL>(A, i); break;                      \
+                case FLUX_AUSMDV: BODY<2, FLUX_AUSMDV>(A, i); break;                    \
+                case FLUX_LDFSS2: BODY<2, FLUX_LDFSS2>(A, i); break;                    \
+                default: BODY<2, FLUX_RUSANOV>(A, i); break;                            \
+            }                                                                           \
+        }                                                                               \
+    }
+
+template <typename S>
+void launch_residual(ibis_b200_ctx* c, const FvArgs<S>& A) {
+    EMU_FLUX_LOOP(cell_residual_body, A.g.n_owned)
+    c->launches++;
+}
+template void launch_residual<double>(ibis_b200_ctx*, const FvArgs<double>&);
+template void launch_residual<dual>(ibis_b200_ctx*, const FvArgs<dual>&);
+
+template <typename S>
+void launch_face_flux(ibis_b200_ctx* c, const FvArgs<S>& A) {
+    EMU_FLUX_LOOP(face_flux_body, A.g.n_faces)
+    c->launches++;
+}
+template void launch_face_flux<double>(ibis_b200_ctx*, const FvArgs<double>&);
+template void launch_face_flux<dual>(ibis_b200_ctx*, const FvArgs<dual>&);
+
+template <typename S>
+void launch_face_viscous(ibis_b200_ctx* c, const FvArgs<S>& A) {
+    for (int f = 0; f < A.g.n_faces; f++) {
+        if (A.g.dim == 3) face_viscous_body<3>(A, f); else face_viscous_body<2>(A, f);
+    }
+    c->launches++;
+}
+template void launch_face_viscous<double>(ibis_b200_ctx*, const FvArgs<double>&);
+template void launch_face_viscous<dual>(ibis_b200_ctx*, const FvArgs<dual>&);
+
+template <typename S>
+void launch_integral(ibis_b200_ctx* c, const FvArgs<S>& A) {
+    for (int i = 0; i < A.g.n_owned; i++) {
+        if (A.g.dim == 3) integral_body<3>(A, i); else integral_body<2>(A, i);
+    }
+    c->launches++;
+}
+template void launch_integral<double>(ibis_b200_ctx*, const FvArgs<double>&);
+template void launch_integral<dual>(ibis_b200_ctx*, const FvArgs<dual>&);
+
+template <typename S>
+void launch_local_dt_min(ibis_b200_ctx* c, const FvArgs<S>& A, double* d_out) {
+    double v = INFINITY;
+    for (int i = 0; i < A.g.n_owned; i++) {
+        const double d = local_dt_body(A, i);
+        v = (d < v) ? d : v;
+    }
+    d_out[0] = v;
+    c->launches++;
+}
+template void launch_local_dt_min<double>(ibis_b200_ctx*, const FvArgs<double>&, double*);
+template void launch_local_dt_min<dual>(ibis_b200_ctx*, const FvArgs<dual>&, double*);
+
+template <typename S> static Gas<S> gas_of(const ibis_b200_ctx* c) {
+    Gas<S> g;
+    g.R = S(c->cfg.R); g.Cv = S(c->cfg.Cv); g.Cp = S(c->cfg.Cp); g.gamma = S(c->cfg.gamma);
+    return g;
+}
+
+template <typename S>
+void launch_cons_to_prim(ibis_b200_ctx* c, S* const* cq, S* const* fs, int64_t n) {
+    Gas<S> g = gas_of<S>(c);
+    for (int64_t i = 0; i < n; i++) {
+        if (c->dim == 3) cons_to_prim_body<3>(cq, fs, g, i); else cons_to_prim_body<2>(cq, fs, g, i);
+    }
+    c->launches++;
+}
+template void launch_cons_to_prim<double>(ibis_b200_ctx*, double* const*, double* const*, int64_t);
+template void launch_cons_to_prim<dual>(ibis_b200_ctx*, dual* const*, dual* const*, int64_t);
+
+template <typename S>
+void launch_prim_to_cons(ibis_b200_ctx* c, S* const* cq, S* const* fs, int64_t n) {
+    for (int64_t i = 0; i < n; i++) {
+        if (c->dim == 3) prim_to_cons_body<3>(cq, fs, i); else prim_to_cons_body<2>(cq, fs, i);
+    }
+    c->launches++;
+}
+template void launch_prim_to_cons<double>(ibis_b200_ctx*, double* const*, double* const*, int64_t);
+template void launch_prim_to_cons<dual>(ibis_b200_ctx*, dual* const*, dual* const*, int64_t);
+
+template <typename S>
+void launch_apply_dt(ibis_b200_ctx* c, S* const* u0, S* const* u1, S* const* k, double dt,
+                     const double* d_dt, double scale, int64_t n) {
+    const double dte = d_dt ? scale * d_dt[0] : dt;
+    for (int64_t i = 0; i < n; i++) {
+        if (c->dim == 3) apply_dt_body<3>(u0, u1, k, dte, i); else apply_dt_body<2>(u0, u1, k, dte, i);
+    }
+    c->launches++;
+}
+template void launch_apply_dt<double>(ibis_b200_ctx*, double* const*, double* const*, double* const*, double, const double*, double, int64_t);
+template void launch_apply_dt<dual>(ibis_b200_ctx*, dual* const*, dual* const*, dual* const*, double, const double*, double, int64_t);
+
+template <typename S>
+void launch_l2_norms(ibis_b200_ctx* c, S* const* cq, int64_t n, double* out) {
+    for (int q = 0; q < 6; q++) out[q] = 0.0;
+    for (int64_t i = 0; i < n; i++) {
+        double t[6];
+        if (c->dim == 3) l2_body<3>(cq, i, t); else l2_body<2>(cq, i, t);
+        for (int q = 0; q < 6; q++) out[q] += t[q];
+    }
+    c->launches++;
+}
+template void launch_l2_norms<double>(ibis_b200_ctx*, double* const*, int64_t, double*);
+template void launch_l2_norms<dual>(ibis_b200_ctx*, dual* const*, int64_t, double*);
+
+template <typename S>
+void launch_count_bad(ibis_b200_ctx* c, S* const* fs, int64_t n, double* out) {
+    double acc = 0;
+    for (int64_t i = 0; i < n; i++)
+        if (bad_cell(mem<S>::load(fs[F_T], i), mem<S>::load(fs[F_RHO], i))) acc += 1.0;
+    out[0] = acc;
+    c->launches++;
+}
+template void launch_count_bad<double>(ibis_b200_ctx*, double* const*, int64_t, double*);
+template void launch_count_bad<dual>(ibis_b200_ctx*, dual* const*, int64_t, double*);
+
+void launch_rk_dt(ibis_b200_ctx* c, const double* d_dt_stable, double cfl, double dt_prev,
+                  double t_remaining, double* d_dt) {
+    const double a = cfl * d_dt_stable[0];
+    const double b = 1.5 * dt_prev;
+    const double s = (b < a) ? b : a;
+    d_dt[0] = (t_remaining < s) ? t_remaining : s;
+    c->launches++;
+}
+
+template <typename S> static S mk(double r, double d);
+template <> double mk<double>(double r, double) { return r; }
+template <> dual mk<dual>(double r, double d) { return dual(r, d); }
+
+template <typename S>
+void launch_pack_in(ibis_b200_ctx* c, const double* re_, const double* du_, S* const* comps,
+                    const int* map, int ncomp_ref, int64_t n) {
+    for (int64_t i = 0; i < n; i++)
+        for (int q = 0; q < ncomp_ref; q++)
+            mem<S>::store(comps[map[q]], i, mk<S>(re_[i * ncomp_ref + q], du_ ? du_[i * ncomp_ref + q] : 0.0));
+    c->launches++;
+}
+template void launch_pack_in<double>(ibis_b200_ctx*, const double*, const double*, double* const*, const int*, int, int64_t);
+template void launch_pack_in<dual>(ibis_b200_ctx*, const double*, const double*, dual* const*, const int*, int, int64_t);
+
+template <typename S>
+void launch_pack_out(ibis_b200_ctx* c, S* const* comps, const int* map, int ncomp_ref, int64_t n,
+                     double* re_, double* du_) {
+    for (int64_t i = 0; i < n; i++)
+        for (int q = 0; q < ncomp_ref; q++) {
+            const S v = mem<S>::load(comps[map[q]], i);
+            if (re_) re_[i * ncomp_ref + q] = re(v);
+            if (du_) du_[i * ncomp_ref + q] = du(v);
+        }
+    c->launches++;
+}
+template void launch_pack_out<double>(ibis_b200_ctx*, double* const*, const int*, int, int64_t, double*, double*);
+template void launch_pack_out<dual>(ibis_b200_ctx*, dual* const*, const int*, int, int64_t, double*, double*);
+
+void launch_gather_debug(ibis_b200_ctx* c, const double* src, int ncomp, int64_t n, double* out) {
+    for (int64_t i = 0; i < n; i++)
+        for (int q = 0; q < ncomp; q++) out[i * ncomp + q] = src[q * c->cstride + i];
+}
+
+void launch_dot(ibis_b200_ctx* c, const double* a, const double* b, int64_t n, double* out, int post) {
+    double acc = 0.0;
+    for (int64_t i = 0; i < n; i++) acc += a[i] * b[i];
+    out[0] = post ? sqrt(acc) : acc;
+    if (post == 2) out[1] = 1.0 / out[0];
+    c->launches++;
+}
+void launch_axpy(ibis_b200_ctx* c, double* y, const double* x, double s, const double* d_s, double sign, int64_t n) {
+    const double f = sign * (d_s ? d_s[0] : s);
+    for (int64_t i = 0; i < n; i++) y[i] += x[i] * f;
+    c->launches++;
+}
+void launch_scale(ibis_b200_ctx* c, const double* x, double* r, double s, const double* d_s, int64_t n) {
+    const double f = d_s ? d_s[0] : s;
+    for (int64_t i = 0; i < n; i++) r[i] = x[i] * f;
+    c->launches++;
+}
+void launch_sub(ibis_b200_ctx* c, const double* a, const double* b, double* r, int64_t n) {
+    for (int64_t i = 0; i < n; i++) r[i] = a[i] - b[i];
+    c->launches++;
+}
+void launch_gemv(ibis_b200_ctx* c, const double* basis, int64_t n, int64_t stride, int m, const double* y, double* out) {
+    for (int64_t i = 0; i < n; i++) {
+        double dot = 0.0;
+        for (int col = 0; col < m; col++) dot += basis[col * stride + i] * y[col];
+        out[i] = dot;
+    }
+    c->launches++;
+}
+void launch_fill(ibis_b200_ctx* c, double* p, double v, int64_t n) {
+    for (int64_t i = 0; i < n; i++) p[i] = v;
+    c->launches++;
+}
+
+static inline int cq_slot(int nc, int q) { return (nc == 4 && q == 3) ? 4 : q; }
+
+void launch_jfnk_set_dual(ibis_b200_ctx* c, dual* const* cq, const double* vec, dual* const* tmp) {
+    const int nc = c->n_cons;
+    for (int64_t i = 0; i < c->n_cells; i++)
+        for (int q = 0; q < nc; q++) tmp[cq_slot(nc, q)][i] = dual(cq[cq_slot(nc, q)][i].re, vec[i * nc + q]);
+    c->launches++;
+}
+void launch_jfnk_set_vector(ibis_b200_ctx* c, dual* const* res, const double* vec, double dt_star, double* result) {
+    const int nc = c->n_cons;
+    for (int64_t i = 0; i < c->n_cells; i++)
+        for (int q = 0; q < nc; q++) result[i * nc + q] = 1 / dt_star * vec[i * nc + q] - res[cq_slot(nc, q)][i].du;
+    c->launches++;
+}
+void launch_jfnk_eval_rhs(ibis_b200_ctx* c, dual* const* res, double* rhs) {
+    const int nc = c->n_cons;
+    for (int64_t i = 0; i < c->n_cells; i++)
+        for (int q = 0; q < nc; q++) rhs[i * nc + q] = res[cq_slot(nc, q)][i].re;
+    c->launches++;
+}
+void launch_jfnk_apply_update(ibis_b200_ctx* c, dual* const* cq, const double* dU) {
+    const int nc = c->n_cons;
+    for (int64_t i = 0; i < c->n_cells; i++)
+        for (int q = 0; q < nc; q++) {
+            dual& v = cq[cq_slot(nc, q)][i];
+            v = dual(v.re + dU[i * nc + q], 0.0);
+        }
+    c->launches++;
+}
+
+template <typename S>
+void launch_halo_pack(ibis_b200_ctx*, S* const*, const int*, int64_t, S*) {}
+template <typename S>
+void launch_halo_unpack(ibis_b200_ctx*, S* const*, const int*, int64_t, const S*) {}
+
+namespace comm {
+int init(ibis_b200_ctx* c, const void*, int, int n_ranks) { c->n_ranks = 1; return n_ranks <= 1 ? 0 : IBIS_B200_ECOMM; }
+int destroy(ibis_b200_ctx*) { return 0; }
+int unique_id(void*) { return IBIS_B200_ECOMM; }
+int allreduce(ibis_b200_ctx*, double*, int, int) { return 0; }
+int halo_setup(ibis_b200_ctx*, int, const int32_t*, const int64_t*, const int64_t*, const int64_t*, const int64_t*) { return 0; }
+template <typename S> int halo_exchange(ibis_b200_ctx*, S* const*) { return 0; }
+template int halo_exchange<double>(ibis_b200_ctx*, double* const*);
+template int halo_exchange<dual>(ibis_b200_ctx*, dual* const*);
+}  // namespace comm
+
+}  // namespace ib
