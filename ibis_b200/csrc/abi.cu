@@ -405,6 +405,8 @@ int ibis_b200_sync(ibis_b200_ctx* c) {
 }
 
 int64_t ibis_b200_launch_count(const ibis_b200_ctx* c) { return c->launches; }
+int ibis_b200_profile_enable(ibis_b200_ctx* c, int on) { c->prof_on = on != 0; return 0; }
+int ibis_b200_profile_read(ibis_b200_ctx* c, double ms[2], int64_t count[2]) { return prof_read(c, ms, count); }
 void* ibis_b200_stream(ibis_b200_ctx* c) { return (void*)c->stream; }
 
 // ---- buffers ----
@@ -437,7 +439,7 @@ static const int CQ_MAP2[4] = {0, 1, 2, 4};
 static int upload_rows(ibis_b200_ctx* c, Buffer* b, const int* map, int ncomp_ref, const double* re_, const double* du_) {
     if (!re_) return fail(c, IBIS_B200_EINVAL, "null host array");
     const int64_t n = b->n, elems = n * ncomp_ref;
-    int rc = ensure_stage(c, 2 * elems);
+    int rc = ensure_stage(c, (b->is_dual ? 2 : 1) * elems);
     if (rc) return rc;
     GPU_TRY(c, gpu::h2d(c->d_stage, re_, elems * sizeof(double), c->stream));
     const double* d_du = nullptr;
@@ -460,7 +462,7 @@ static int upload_rows(ibis_b200_ctx* c, Buffer* b, const int* map, int ncomp_re
 
 static int download_rows(ibis_b200_ctx* c, Buffer* b, const int* map, int ncomp_ref, double* re_, double* du_) {
     const int64_t n = b->n, elems = n * ncomp_ref;
-    int rc = ensure_stage(c, 2 * elems);
+    int rc = ensure_stage(c, (b->is_dual ? 2 : 1) * elems);
     if (rc) return rc;
     if (b->is_dual) {
         dual* p[7];

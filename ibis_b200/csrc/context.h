@@ -78,6 +78,11 @@ struct ibis_b200_ctx {
     std::vector<int> rk_k;
     int rk_ktmp = 0, rk_fstmp = 0;
 
+    // optional per-kernel event timing (ibis_b200_profile_*)
+    bool prof_on = false;
+    std::vector<void*> prof_ev[2];       // event pairs (start, stop, start, stop, ...) per kind
+    size_t prof_used[2] = {0, 0};
+
     std::vector<ib::Buffer> bufs;        // handle = index (0 unused)
     ib::Halo halo;
     void* nccl_comm = nullptr;
@@ -149,5 +154,9 @@ template <typename S>
 void launch_halo_unpack(ibis_b200_ctx* c, S* const* fs, const int* cells, int64_t n, const S* buf);
 
 int reduction_blocks(int64_t n);
+// event bracket around a launch when profiling is on (kind 0 = pass G, 1 = pass F)
+void prof_begin(ibis_b200_ctx* c, int kind);
+void prof_end(ibis_b200_ctx* c, int kind);
+int prof_read(ibis_b200_ctx* c, double* ms, int64_t* count);
 
 }  // namespace ib

@@ -24,6 +24,39 @@ namespace ib {
 
 static inline int nblocks(int64_t n, int bs) { return (int)((n + bs - 1) / bs); }
 
+void prof_begin(ibis_b200_ctx* c, int kind) {
+    if (!c->prof_on) return;
+    auto& ev = c->prof_ev[kind];
+    if (c->prof_used[kind] + 2 > ev.size()) {
+        cudaEvent_t a, b;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        ev.push_back(a);
+        ev.push_back(b);
+    }
+    cudaEventRecord((cudaEvent_t)ev[c->prof_used[kind]], c->stream);
+}
+void prof_end(ibis_b200_ctx* c, int kind) {
+    if (!c->prof_on) return;
+    cudaEventRecord((cudaEvent_t)c->prof_ev[kind][c->prof_used[kind] + 1], c->stream);
+    c->prof_used[kind] += 2;
+}
+int prof_read(ibis_b200_ctx* c, double* ms, int64_t* count) {
+    cudaStreamSynchronize(c->stream);
+    for (int k = 0; k < 2; k++) {
+        double t = 0.0;
+        for (size_t i = 0; i + 1 < c->prof_used[k]; i += 2) {
+            float e = 0.f;
+            cudaEventElapsedTime(&e, (cudaEvent_t)c->prof_ev[k][i], (cudaEvent_t)c->prof_ev[k][i + 1]);
+            t += e;
+        }
+        ms[k] = t;
+        count[k] = (int64_t)(c->prof_used[k] / 2);
+        c->prof_used[k] = 0;
+    }
+    return 0;
+}
+
 template <typename S>
 __global__ void __launch_bounds__(128) k_bc(const FvArgs<S> A, int phase) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -149,10 +182,12 @@ void launch_grad_limit(ibis_b200_ctx* c, const FvArgs<S>& A, bool viscous_pass) 
         const int vars[5] = {V_RHO, V_TH2, V_VX, V_VY, V_VZ};
         const int src[5] = {F_RHO, A.th2, F_VX, F_VY, F_VZ};
         for (int i = 0; i < 5; i++) { vl.vars[i] = vars[i]; vl.src[i] = src[i]; }
+        prof_begin(c, 0);
         if (A.g.dim == 3)
             k_grad_limit<3, 5, S><<<nb, 256, 0, c->stream>>>(A, vl, A.limiter_on);
         else
             k_grad_limit<2, 4, S><<<nb, 256, 0, c->stream>>>(A, vl, A.limiter_on);
+        prof_end(c, 0);
     }
     CUDA_CHECK_LAUNCH(c);
 }
@@ -169,11 +204,13 @@ template void launch_grad_limit<dual>(ibis_b200_ctx*, const FvArgs<dual>&, bool)
 
 template <typename S>
 void launch_residual(ibis_b200_ctx* c, const FvArgs<S>& A) {
+    prof_begin(c, 1);
     if (A.g.dim == 3) {
         DISPATCH_FLUX(k_residual, 3, A.g.n_owned, 128)
     } else {
         DISPATCH_FLUX(k_residual, 2, A.g.n_owned, 128)
     }
+    prof_end(c, 1);
     CUDA_CHECK_LAUNCH(c);
 }
 template void launch_residual<double>(ibis_b200_ctx*, const FvArgs<double>&);

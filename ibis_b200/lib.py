@@ -226,6 +226,7 @@ class Library:
             "ibis_b200_arnoldi_mgs": [vp, i, i, i, i, vp],
             "ibis_b200_basis_gemv": [vp, i, i, vp, i],
             "ibis_b200_halo_setup": [vp, i, vp, vp, vp, vp, vp],
+            "ibis_b200_profile_enable": [vp, i], "ibis_b200_profile_read": [vp, vp, vp],
             "ibis_b200_comm_init": [vp, vp, i, i], "ibis_b200_nccl_unique_id": [vp],
         }
         for name, args in sig.items():
@@ -342,6 +343,24 @@ class Context:
 
     def sync(self):
         self._ck(self.lib.ibis_b200_sync(self.h), "sync")
+
+    def profile_enable(self, on=True):
+        self._ck(self.lib.ibis_b200_profile_enable(self.h, int(on)), "profile_enable")
+
+    def profile_read(self):
+        ms = np.zeros(2)
+        n = np.zeros(2, np.int64)
+        self._ck(self.lib.ibis_b200_profile_read(self.h, _ptr(ms), _ptr(n)), "profile_read")
+        return ms, n
+
+    def stream_ptr(self):
+        return int(self.lib.ibis_b200_stream(self.h) or 0)
+
+    def fs_upload_ptr(self, h, ptr):
+        self._ck(self.lib.ibis_b200_fs_upload(self.h, h, C.c_void_p(ptr), None), "fs_upload")
+
+    def fs_download_ptr(self, h, ptr):
+        self._ck(self.lib.ibis_b200_fs_download(self.h, h, C.c_void_p(ptr), None), "fs_download")
 
     def launch_count(self):
         return int(self.lib.ibis_b200_launch_count(self.h))

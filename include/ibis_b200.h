@@ -127,6 +127,13 @@ int64_t ibis_b200_launch_count(const ibis_b200_ctx* ctx);
 /* the CUDA stream all kernels are launched on, as a cudaStream_t cast to void* */
 void* ibis_b200_stream(ibis_b200_ctx* ctx);
 
+/* Per-kernel device timing for bench.py's roofline: when enabled, pass G (k_grad_limit) and
+ * pass F (k_residual) launches are bracketed by CUDA events on the context's stream.
+ * profile_read synchronises and returns the accumulated milliseconds and launch counts
+ * since the last read: ms[0]/count[0] = pass G, ms[1]/count[1] = pass F. */
+int ibis_b200_profile_enable(ibis_b200_ctx* ctx, int on);
+int ibis_b200_profile_read(ibis_b200_ctx* ctx, double ms[2], int64_t count[2]);
+
 /* ---- buffers ------------------------------------------------------------------------- */
 /* FlowStates<T>(num_total_cells) (gas/flow_state.h:62) */
 int ibis_b200_fs_create(ibis_b200_ctx*, int is_dual, int* handle);
