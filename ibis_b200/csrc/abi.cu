@@ -404,6 +404,14 @@ int ibis_b200_sync(ibis_b200_ctx* c) {
     return 0;
 }
 
+int ibis_b200_sizes(const ibis_b200_ctx* c, int32_t* dim, int64_t* n_cells, int64_t* n_ghost, int64_t* n_faces) {
+    if (!c) return IBIS_B200_EINVAL;
+    if (dim) *dim = c->dim;
+    if (n_cells) *n_cells = c->n_cells;
+    if (n_ghost) *n_ghost = c->n_ghost;
+    if (n_faces) *n_faces = c->n_faces;
+    return 0;
+}
 int64_t ibis_b200_launch_count(const ibis_b200_ctx* c) { return c->launches; }
 int ibis_b200_profile_enable(ibis_b200_ctx* c, int on) { c->prof_on = on != 0; return 0; }
 int ibis_b200_profile_read(ibis_b200_ctx* c, double ms[2], int64_t count[2]) { return prof_read(c, ms, count); }
@@ -650,13 +658,19 @@ int ibis_b200_rk_step(ibis_b200_ctx* c, int fs, int cq, int n_stages, const doub
     Buffer* F = get_buf(c, fs, BUF_FS);
     Buffer* U = get_buf(c, cq, BUF_CQ);
     if (!F || !U || F->is_dual || U->is_dual || n_stages < 1 || !b) return fail(c, IBIS_B200_EHANDLE, "rk_step: bad arguments");
-    // k_[stages], k_tmp_, flow_tmp_ (runge_kutta.cpp:45-52)
-    while ((int)c->rk_k.size() < n_stages) {
+    // k_[stages], k_tmp_, flow_tmp_ (runge_kutta.cpp:45-52).  The reference fills the vector
+    // k_ with COPIES of one ConservedQuantities (runge_kutta.cpp:49-50); Kokkos Views are
+    // reference-counted handles, so all its stages share ONE array.  rk_alias_stages (default)
+    // reproduces that; ibis_b200_rk_distinct_stages(ctx, 1) gives every stage its own array.
+    while ((int)c->rk_k_own.size() < (c->rk_alias_stages ? 1 : n_stages)) {
         int h = 0;
         int rc = ibis_b200_cq_create(c, 0, &h);
         if (rc) return rc;
-        c->rk_k.push_back(h);
+        c->rk_k_own.push_back(h);
     }
+    c->rk_k.assign(n_stages, c->rk_k_own[0]);
+    if (!c->rk_alias_stages)
+        for (int i = 0; i < n_stages; i++) c->rk_k[i] = c->rk_k_own[i];
     if (n_stages > 1 && !c->rk_ktmp) {
         int rc = ibis_b200_cq_create(c, 0, &c->rk_ktmp);
         if (!rc) rc = ibis_b200_fs_create(c, 0, &c->rk_fstmp);
@@ -707,6 +721,11 @@ int ibis_b200_rk_step(ibis_b200_ctx* c, int fs, int cq, int n_stages, const doub
     if (dt) *dt = out[1];
     if (rc) return rc;
     return c->last_error.empty() ? 0 : IBIS_B200_ECUDA;
+}
+
+int ibis_b200_rk_distinct_stages(ibis_b200_ctx* c, int distinct) {
+    c->rk_alias_stages = distinct == 0;
+    return 0;
 }
 
 int ibis_b200_rk_residual_norms(ibis_b200_ctx* c, double out[6]) {

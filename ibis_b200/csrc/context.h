@@ -75,7 +75,9 @@ struct ibis_b200_ctx {
     int64_t stage_elems = 0;
 
     // explicit solver scratch: k_[stages], k_tmp_, flow_tmp_ (runge_kutta.cpp:45-52)
-    std::vector<int> rk_k;
+    std::vector<int> rk_k;            // handle of stage i (all equal when the stages alias)
+    std::vector<int> rk_k_own;        // the buffers actually allocated
+    bool rk_alias_stages = true;      // the reference's k_ stages share one array
     int rk_ktmp = 0, rk_fstmp = 0;
 
     // optional per-kernel event timing (ibis_b200_profile_*)

@@ -215,7 +215,7 @@ class Library:
             "ibis_b200_l2_norms": [vp, i, vp],
             "ibis_b200_debug_gradients": [vp, i, vp, vp],
             "ibis_b200_rk_step": [vp, i, i, i, vp, vp, d, d, d, C.POINTER(d), C.POINTER(d)],
-            "ibis_b200_rk_residual_norms": [vp, vp],
+            "ibis_b200_rk_residual_norms": [vp, vp], "ibis_b200_rk_distinct_stages": [vp, i],
             "ibis_b200_jfnk_set_dual": [vp, i, i, i],
             "ibis_b200_jfnk_set_vector": [vp, i, i, d, i],
             "ibis_b200_jfnk_eval_rhs": [vp, i, i], "ibis_b200_jfnk_apply_update": [vp, i, i],

@@ -122,6 +122,9 @@ int ibis_b200_create(ibis_b200_ctx** ctx, const ibis_b200_grid_desc* grid,
 int ibis_b200_destroy(ibis_b200_ctx* ctx);
 const char* ibis_b200_last_error(const ibis_b200_ctx* ctx);   /* ctx may be NULL */
 int ibis_b200_sync(ibis_b200_ctx* ctx);
+/* GridBlock::dim / num_cells / num_ghost_cells / num_interfaces (grid/grid.h:617-621) */
+int ibis_b200_sizes(const ibis_b200_ctx* ctx, int32_t* dim, int64_t* n_cells, int64_t* n_ghost,
+                    int64_t* n_faces);
 /* number of kernels launched by this context since creation (bench.py: gpu_launches) */
 int64_t ibis_b200_launch_count(const ibis_b200_ctx* ctx);
 /* the CUDA stream all kernels are launched on, as a cudaStream_t cast to void* */
@@ -186,6 +189,13 @@ int ibis_b200_debug_gradients(ibis_b200_ctx*, int var, double* grad, double* lim
 int ibis_b200_rk_step(ibis_b200_ctx*, int fs, int cq, int n_stages, const double* a,
                       const double* b, double cfl, double dt_prev, double t_remaining,
                       double* dt, double* dt_stable);
+/* Reference quirk (runge_kutta.cpp:49-50): `k_` is a std::vector filled with copies of ONE
+ * ConservedQuantities, i.e. of one reference-counted Kokkos View, so all Runge-Kutta stages k_[i]
+ * alias the same array and every function evaluation overwrites "all" of them.  Schemes with up
+ * to two stages are unaffected; for three or more the reference therefore does not integrate the
+ * tableau it was given.  The default reproduces the reference bit for bit; distinct = 1 gives
+ * each stage its own array (the scheme the tableau describes). */
+int ibis_b200_rk_distinct_stages(ibis_b200_ctx*, int distinct);
 /* RungeKutta::L2_norms = k_[0].L2_norms() of the last rk_step (runge_kutta.cpp:264) */
 int ibis_b200_rk_residual_norms(ibis_b200_ctx*, double out[6]);
 

@@ -9,3 +9,8 @@ EMU_LIB = os.path.join(HERE, "emu", "_build", "libibis_b200_emu.so")
 def emu_lib():
     subprocess.run(["make", "-s", "-C", os.path.join(HERE, "emu")], check=True)
     return EMU_LIB
+
+
+def emu_host_lib():
+    emu_lib()
+    return os.path.join(HERE, "emu", "_build", "libibis_b200_host_emu.so")

@@ -1,0 +1,105 @@
+"""CPU tests of the C++ host solvers (ibis_b200/host: RungeKutta, SteadyState, Jfnk, Gmres,
+FGmres, CflSchedule) linked against the host-emulation build of the C ABI, versus the real
+reference's final flow snapshots and its GMRES known-answer tests."""
+import os
+
+import numpy as np
+import pytest
+
+import cases
+import solve_cases as sc
+import solve_parity
+from emu_util import emu_lib, emu_host_lib
+from ibis_b200 import host
+from ibis_b200.lib import Context
+
+
+@pytest.fixture(scope="module")
+def libs():
+    return emu_lib(), emu_host_lib()
+
+
+@pytest.mark.parametrize("name", sorted(sc.SOLVE_CASES))
+def test_solver_against_reference_snapshot(libs, name):
+    inviscid_rk = name.startswith("rk_") and "viscous" not in name
+    worst, rep = solve_parity.run_solve_case(name, lib_path=libs[0], host_lib=libs[1], exact=inviscid_rk)
+    assert rep["steps"] > 0
+
+
+@pytest.mark.parametrize("name", ["rk_wedge2d", "rk_ffs2d", "rk_box3d"])
+def test_unfused_step_sequence_matches_fused(libs, name):
+    """RungeKutta::take_step as the reference's sequence of kernels (one ABI call each)."""
+    solve_parity.run_solve_case(name, lib_path=libs[0], host_lib=libs[1], fused_step=False, exact=True)
+
+
+# the reference's own known-answer systems (linear_algebra/gmres.cpp:320-500)
+A5 = np.array([[2.0, 1.0, 0.0, 0.0, 0.0], [1.0, 3.0, 1.0, 0.0, 0.0], [0.0, 1.0, 4.0, 1.0, 0.0],
+               [0.0, 0.0, 1.0, 3.0, 1.0], [0.0, 0.0, 0.0, 1.0, 2.0]])
+
+
+def _tiny_ctx(lib):
+    mesh, config, g, prim = cases.build_case("quad2d_hanel")
+    return Context(g, config, lib_path=lib)
+
+
+@pytest.mark.parametrize("kind", ["gmres", "fgmres"])
+def test_gmres_known_answer(libs, kind):
+    ctx = _tiny_ctx(libs[0])
+    x_true = np.array([1.0, 0.0, -1.0, 1.5, 0.5])
+    b = A5 @ x_true
+    ls = ({"type": "gmres", "max_iters": 5, "tol": 1e-14} if kind == "gmres" else
+          {"type": "fgmres", "max_iters": 5, "tolerance": 1e-14, "max_preconditioner_iters": 5,
+           "preconditioner_tolerance": 1e-14})
+    x, ok, n_it, res = host.gmres_dense(ctx, A5, b, np.zeros(5), ls, host_lib=libs[1])
+    ctx.close()
+    assert ok and n_it <= 5
+    np.testing.assert_allclose(x, x_true, atol=1e-12)
+
+
+def test_gmres_hits_max_iters_without_overrun(libs):
+    """j = max_iters - 1 is where the reference writes one past the end of H."""
+    ctx = _tiny_ctx(libs[0])
+    rng = np.random.default_rng(3)
+    A = rng.normal(size=(12, 12)) + 12 * np.eye(12)
+    b = rng.normal(size=12)
+    x, ok, n_it, res = host.gmres_dense(ctx, A, b, np.zeros(12), {"type": "gmres", "max_iters": 4, "tol": 1e-14},
+                                        host_lib=libs[1])
+    ctx.close()
+    assert not ok and n_it == 4
+    # the iterate minimises the residual over the 4-dimensional Krylov space
+    K = np.stack([np.linalg.matrix_power(A, k) @ b for k in range(4)], axis=1)
+    y = np.linalg.lstsq(A @ K, b, rcond=None)[0]
+    np.testing.assert_allclose(np.linalg.norm(b - A @ x), np.linalg.norm(b - A @ K @ y), rtol=1e-8)
+
+
+@pytest.mark.ref
+def test_gmres_matches_reference_gmres(libs):
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import refharness as rh
+    if not rh.available():
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(5)
+    A = rng.normal(size=(20, 20)) + 8 * np.eye(20)
+    b = rng.normal(size=20)
+    # max_iters well above the iterations needed: the reference corrupts its heap when it runs
+    # out of iterations (gmres.cpp:53-54)
+    xr, okr, nr, rr = rh.RefLib.get().gmres_dense(A, b, np.zeros(20), 19, 1e-6)
+    ctx = _tiny_ctx(libs[0])
+    x, ok, n_it, res = host.gmres_dense(ctx, A, b, np.zeros(20), {"type": "gmres", "max_iters": 19, "tol": 1e-6},
+                                        host_lib=libs[1])
+    ctx.close()
+    assert (ok, n_it) == (okr, nr) and ok
+    np.testing.assert_allclose(x, xr, rtol=1e-10, atol=1e-13)
+    assert abs(res - rr) <= 1e-8 * abs(rr)
+
+
+def test_cfl_schedules_through_solver(libs):
+    """LinearSchedule interpolation (the reference's cfl.cpp:86-96 test) is exercised by
+    rk_box3d's linear_interpolate schedule; here: unknown schedule type raises."""
+    mesh, config, g, prim0, snap = sc.build_solve_case("rk_box3d")
+    config["solver"]["cfl"] = {"type": "nope"}
+    ctx = Context(g, config, lib_path=libs[0])
+    with pytest.raises(Exception, match="Unknown CFL schedule"):
+        host.solve(ctx, config, prim0, host_lib=libs[1])
+    ctx.close()

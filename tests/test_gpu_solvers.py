@@ -1,0 +1,51 @@
+"""GPU tests (-m gpu) of the whole solvers: the C++ host solvers of ibis_b200/host above the CUDA
+C ABI against the real reference's final flow snapshots (tests/golden/solve_*.npz): explicit
+Runge-Kutta runs (wedge, forward-facing step, viscous plate, viscous NACA O-mesh, 3-D box) and
+JFNK steady runs (GMRES and FGMRES).  Tolerance 1e-9 on the flow field; inviscid explicit runs are
+required to be bit-identical."""
+import numpy as np
+import pytest
+
+import cases
+import solve_cases as sc
+import solve_parity
+from ibis_b200 import host
+from ibis_b200.lib import Context
+
+pytestmark = pytest.mark.gpu
+
+
+def _require_cuda():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+
+
+@pytest.mark.parametrize("name", sorted(sc.SOLVE_CASES))
+def test_solver_against_reference_snapshot(name):
+    _require_cuda()
+    inviscid_rk = name.startswith("rk_") and "viscous" not in name
+    worst, rep = solve_parity.run_solve_case(name, exact=inviscid_rk)
+    assert rep["steps"] > 0
+
+
+@pytest.mark.parametrize("name", ["rk_wedge2d", "rk_box3d"])
+def test_unfused_step_sequence(name):
+    _require_cuda()
+    solve_parity.run_solve_case(name, fused_step=False, exact=True)
+
+
+def test_gmres_known_answer_on_device():
+    """linear_algebra/gmres.cpp:320-500: x = (1, 0, -1, 1.5, 0.5)."""
+    _require_cuda()
+    A5 = np.array([[2.0, 1.0, 0.0, 0.0, 0.0], [1.0, 3.0, 1.0, 0.0, 0.0], [0.0, 1.0, 4.0, 1.0, 0.0],
+                   [0.0, 0.0, 1.0, 3.0, 1.0], [0.0, 0.0, 0.0, 1.0, 2.0]])
+    x_true = np.array([1.0, 0.0, -1.0, 1.5, 0.5])
+    mesh, config, g, prim = cases.build_case("quad2d_hanel")
+    ctx = Context(g, config)
+    for ls in ({"type": "gmres", "max_iters": 5, "tol": 1e-14},
+               {"type": "fgmres", "max_iters": 5, "tolerance": 1e-14, "max_preconditioner_iters": 5,
+                "preconditioner_tolerance": 1e-14}):
+        x, ok, n_it, res = host.gmres_dense(ctx, A5, A5 @ x_true, np.zeros(5), ls)
+        assert ok
+        np.testing.assert_allclose(x, x_true, atol=1e-12)
+    ctx.close()
