@@ -12,6 +12,7 @@
 
 #include "comm.h"
 #include "context.h"
+#include "layout.h"
 
 using namespace ib;
 
@@ -214,8 +215,18 @@ const char* ibis_b200_last_error(const ibis_b200_ctx* c) {
     return c ? c->last_error.c_str() : g_last_error.c_str();
 }
 
-int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd, const ibis_b200_config* cfg, int device) {
-    if (!out || !gd || !cfg) return fail(nullptr, IBIS_B200_EINVAL, "null argument");
+int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd_ref, const ibis_b200_config* cfg, int device) {
+    if (!out || !gd_ref || !cfg) return fail(nullptr, IBIS_B200_EINVAL, "null argument");
+    // internal renumbering (layout.h); IBIS_B200_RENUMBER=0 keeps the reference numbering
+    const char* env_renumber = getenv("IBIS_B200_RENUMBER");
+    const bool morton = !(env_renumber && env_renumber[0] == '0');
+    Renumbered R;
+    {
+        const char* err = nullptr;
+        int rrc = renumber_grid(gd_ref, morton, R, &err);
+        if (rrc) return fail(nullptr, rrc, err ? err : "renumbering failed");
+    }
+    const ibis_b200_grid_desc* gd = &R.desc;
     if (gd->dim != 2 && gd->dim != 3) return fail(nullptr, IBIS_B200_EINVAL, "dim must be 2 or 3");
     if (cfg->thermo_interpolator == IBIS_B200_THERMO_P_T)
         return fail(nullptr, IBIS_B200_EINVAL,
@@ -324,6 +335,7 @@ int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd, const i
     }
     if (acts.empty()) acts.push_back(BcAction());
 
+    c->ref2int = R.ref2int;
     GridDev& g = c->g;
     g.dim = gd->dim;
     g.n_owned = (int)c->n_owned;
@@ -354,6 +366,10 @@ int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd, const i
     UP(fn, dd, f_n) UP(ft1, dd, f_t1) UP(ft2, dd, f_t2) UP(fc, dd, f_c)
     UP(bf_face, di, bf_face) UP(bf_tag, di, bf_tag)
     UP(acts, da, act) UP(act_off, di, act_off)
+    if (morton) {
+        rc = upload_vec(c, c->ref2int, &c->d_ref2int);
+        if (rc) { ibis_b200_destroy(c); return fail(nullptr, rc, "grid upload failed"); }
+    }
 #undef UP
     // WLS r-factors on the device (GridBlock::allocate_gradient_weights, grid.h:499-503)
     double* r = nullptr;
@@ -646,7 +662,8 @@ int ibis_b200_debug_gradients(ibis_b200_ctx* c, int var, double* grad, double* l
         GPU_TRY(c, gpu::stream_sync(c->stream));
     }
     if (limiter) {
-        GPU_TRY(c, gpu::d2h(limiter, c->lim_r + (int64_t)var * c->cstride, c->n_cells * sizeof(double), c->stream));
+        launch_gather_debug(c, c->lim_r + (int64_t)var * c->cstride, 1, c->n_cells, c->d_stage);
+        GPU_TRY(c, gpu::d2h(limiter, c->d_stage, c->n_cells * sizeof(double), c->stream));
         GPU_TRY(c, gpu::stream_sync(c->stream));
     }
     return 0;

@@ -127,8 +127,9 @@ int halo_setup(ibis_b200_ctx* c, int n_peers, const int32_t* peer_ranks, const i
     h.n_send = h.send_off[n_peers];
     h.n_recv = h.recv_off[n_peers];
     std::vector<int> s(h.n_send), r(h.n_recv);
-    for (int64_t i = 0; i < h.n_send; i++) s[i] = (int)send_cells[i];
-    for (int64_t i = 0; i < h.n_recv; i++) r[i] = (int)recv_cells[i];
+    // the lists arrive in reference numbering
+    for (int64_t i = 0; i < h.n_send; i++) s[i] = c->ref2int[send_cells[i]];
+    for (int64_t i = 0; i < h.n_recv; i++) r[i] = c->ref2int[recv_cells[i]];
     if (cudaMalloc(&h.d_send_cells, std::max<size_t>(s.size(), 1) * sizeof(int)) != cudaSuccess ||
         cudaMalloc(&h.d_recv_cells, std::max<size_t>(r.size(), 1) * sizeof(int)) != cudaSuccess ||
         cudaMalloc(&h.d_send_buf, std::max<size_t>(s.size(), 1) * 7 * 16) != cudaSuccess ||

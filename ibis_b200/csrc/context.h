@@ -51,6 +51,9 @@ struct ibis_b200_ctx {
     std::vector<ibis_b200_bc_action> bc_actions;
     bool has_previscous = false;
 
+    // internal renumbering (layout.h): reference cell id -> internal id, nullptr = identity
+    int* d_ref2int = nullptr;
+    std::vector<int> ref2int;
     ib::GridDev g;                       // device pointers + sizes
     std::vector<void*> owned_allocs;     // everything to free at destroy
 

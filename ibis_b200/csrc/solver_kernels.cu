@@ -137,35 +137,38 @@ struct CompMap { int m[8]; };
 
 template <typename S>
 __global__ void __launch_bounds__(256) k_pack_in(const double* re_, const double* du_, Comps7<S> comps,
-                                                  CompMap map, int ncomp_ref, long n) {
-    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+                                                  CompMap map, int ncomp_ref, long n, const int* perm) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;     // row in reference numbering
     if (i >= n) return;
+    const long p = perm ? perm[i] : i;                              // internal cell id
     for (int q = 0; q < ncomp_ref; q++) {
         const double r = re_[i * ncomp_ref + q];
         const double d = du_ ? du_[i * ncomp_ref + q] : 0.0;
         S v;
         if constexpr (sizeof(S) == sizeof(double)) v = r; else v = dual(r, d);
-        mem<S>::store(comps.p[map.m[q]], i, v);
+        mem<S>::store(comps.p[map.m[q]], p, v);
     }
 }
 
 template <typename S>
 __global__ void __launch_bounds__(256) k_pack_out(Comps7<S> comps, CompMap map, int ncomp_ref, long n,
-                                                   double* re_, double* du_) {
+                                                   double* re_, double* du_, const int* perm) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const long p = perm ? perm[i] : i;
     for (int q = 0; q < ncomp_ref; q++) {
-        const S v = mem<S>::load(comps.p[map.m[q]], i);
+        const S v = mem<S>::load(comps.p[map.m[q]], p);
         if (re_) re_[i * ncomp_ref + q] = re(v);
         if (du_) du_[i * ncomp_ref + q] = du(v);
     }
 }
 
 __global__ void __launch_bounds__(256) k_gather_debug(const double* src, long stride, int ncomp, long n,
-                                                       double* out) {
+                                                       double* out, const int* perm) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    for (int q = 0; q < ncomp; q++) out[i * ncomp + q] = src[q * stride + i];
+    const long p = perm ? perm[i] : i;
+    for (int q = 0; q < ncomp; q++) out[i * ncomp + q] = src[q * stride + p];
 }
 
 // ---- vectors ----
@@ -214,49 +217,54 @@ __global__ void __launch_bounds__(256) k_gemv(const double* basis, long n, long 
 
 // ---- JFNK (solvers/steady_state.cpp:60-68,102-110,142-149; solvers/jfnk.cpp:69-76) ----
 template <int NC>
-__global__ void __launch_bounds__(256) k_jfnk_set_dual(Comps5<dual> cq, const double* vec, Comps5<dual> tmp, long n) {
-    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) k_jfnk_set_dual(Comps5<dual> cq, const double* vec, Comps5<dual> tmp, long n,
+                                                        const int* perm) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;      // cell in reference numbering
     if (i >= n) return;
+    const long p = perm ? perm[i] : i;
 #pragma unroll
     for (int q = 0; q < NC; q++) {
         const int k = (NC == 4 && q == 3) ? 4 : q;            // 2-D: mass mx my energy
-        const dual v = mem<dual>::load(cq.p[k], i);
-        mem<dual>::store(tmp.p[k], i, dual(v.re, vec[i * NC + q]));
+        const dual v = mem<dual>::load(cq.p[k], p);
+        mem<dual>::store(tmp.p[k], p, dual(v.re, vec[i * NC + q]));
     }
 }
 
 template <int NC>
 __global__ void __launch_bounds__(256) k_jfnk_set_vector(Comps5<dual> res, const double* vec, double dt_star,
-                                                          double* result, long n) {
+                                                          double* result, long n, const int* perm) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const long p = perm ? perm[i] : i;
 #pragma unroll
     for (int q = 0; q < NC; q++) {
         const int k = (NC == 4 && q == 3) ? 4 : q;
-        result[i * NC + q] = 1 / dt_star * vec[i * NC + q] - mem<dual>::load(res.p[k], i).du;
+        result[i * NC + q] = 1 / dt_star * vec[i * NC + q] - mem<dual>::load(res.p[k], p).du;
     }
 }
 
 template <int NC>
-__global__ void __launch_bounds__(256) k_jfnk_eval_rhs(Comps5<dual> res, double* rhs, long n) {
+__global__ void __launch_bounds__(256) k_jfnk_eval_rhs(Comps5<dual> res, double* rhs, long n, const int* perm) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const long p = perm ? perm[i] : i;
 #pragma unroll
     for (int q = 0; q < NC; q++) {
         const int k = (NC == 4 && q == 3) ? 4 : q;
-        rhs[i * NC + q] = mem<dual>::load(res.p[k], i).re;
+        rhs[i * NC + q] = mem<dual>::load(res.p[k], p).re;
     }
 }
 
 template <int NC>
-__global__ void __launch_bounds__(256) k_jfnk_apply_update(Comps5<dual> cq, const double* dU, long n) {
+__global__ void __launch_bounds__(256) k_jfnk_apply_update(Comps5<dual> cq, const double* dU, long n, const int* perm) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const long p = perm ? perm[i] : i;
 #pragma unroll
     for (int q = 0; q < NC; q++) {
         const int k = (NC == 4 && q == 3) ? 4 : q;
-        const dual v = mem<dual>::load(cq.p[k], i);
-        mem<dual>::store(cq.p[k], i, dual(v.re + dU[i * NC + q], 0.0));
+        const dual v = mem<dual>::load(cq.p[k], p);
+        mem<dual>::store(cq.p[k], p, dual(v.re + dU[i * NC + q], 0.0));
     }
 }
 
@@ -353,7 +361,7 @@ void launch_pack_in(ibis_b200_ctx* c, const double* d_re, const double* d_du, S*
     for (int i = 0; i < 7; i++) cc.p[i] = comps[i];
     CompMap m;
     for (int i = 0; i < 8; i++) m.m[i] = i < ncomp_ref ? comp_map[i] : 0;
-    k_pack_in<S><<<nblocks(n, 256), 256, 0, c->stream>>>(d_re, d_du, cc, m, ncomp_ref, n);
+    k_pack_in<S><<<nblocks(n, 256), 256, 0, c->stream>>>(d_re, d_du, cc, m, ncomp_ref, n, c->d_ref2int);
     CUDA_CHECK_LAUNCH(c);
 }
 template void launch_pack_in<double>(ibis_b200_ctx*, const double*, const double*, double* const*, const int*, int, int64_t);
@@ -366,14 +374,14 @@ void launch_pack_out(ibis_b200_ctx* c, S* const* comps, const int* comp_map, int
     for (int i = 0; i < 7; i++) cc.p[i] = comps[i];
     CompMap m;
     for (int i = 0; i < 8; i++) m.m[i] = i < ncomp_ref ? comp_map[i] : 0;
-    k_pack_out<S><<<nblocks(n, 256), 256, 0, c->stream>>>(cc, m, ncomp_ref, n, d_re, d_du);
+    k_pack_out<S><<<nblocks(n, 256), 256, 0, c->stream>>>(cc, m, ncomp_ref, n, d_re, d_du, c->d_ref2int);
     CUDA_CHECK_LAUNCH(c);
 }
 template void launch_pack_out<double>(ibis_b200_ctx*, double* const*, const int*, int, int64_t, double*, double*);
 template void launch_pack_out<dual>(ibis_b200_ctx*, dual* const*, const int*, int, int64_t, double*, double*);
 
 void launch_gather_debug(ibis_b200_ctx* c, const double* src, int ncomp, int64_t n, double* out) {
-    k_gather_debug<<<nblocks(n, 256), 256, 0, c->stream>>>(src, c->cstride, ncomp, n, out);
+    k_gather_debug<<<nblocks(n, 256), 256, 0, c->stream>>>(src, c->cstride, ncomp, n, out, c->d_ref2int);
     CUDA_CHECK_LAUNCH(c);
 }
 
@@ -420,19 +428,19 @@ void launch_fill(ibis_b200_ctx* c, double* p, double v, int64_t n) {
 
 void launch_jfnk_set_dual(ibis_b200_ctx* c, dual* const* cq, const double* vec, dual* const* cq_tmp) {
     const long n = c->n_cells;
-    JFNK_DISPATCH(k_jfnk_set_dual, c5(cq), vec, c5(cq_tmp), n)
+    JFNK_DISPATCH(k_jfnk_set_dual, c5(cq), vec, c5(cq_tmp), n, c->d_ref2int)
 }
 void launch_jfnk_set_vector(ibis_b200_ctx* c, dual* const* res, const double* vec, double dt_star, double* result) {
     const long n = c->n_cells;
-    JFNK_DISPATCH(k_jfnk_set_vector, c5(res), vec, dt_star, result, n)
+    JFNK_DISPATCH(k_jfnk_set_vector, c5(res), vec, dt_star, result, n, c->d_ref2int)
 }
 void launch_jfnk_eval_rhs(ibis_b200_ctx* c, dual* const* res, double* rhs) {
     const long n = c->n_cells;
-    JFNK_DISPATCH(k_jfnk_eval_rhs, c5(res), rhs, n)
+    JFNK_DISPATCH(k_jfnk_eval_rhs, c5(res), rhs, n, c->d_ref2int)
 }
 void launch_jfnk_apply_update(ibis_b200_ctx* c, dual* const* cq, const double* dU) {
     const long n = c->n_cells;
-    JFNK_DISPATCH(k_jfnk_apply_update, c5(cq), dU, n)
+    JFNK_DISPATCH(k_jfnk_apply_update, c5(cq), dU, n, c->d_ref2int)
 }
 
 template <typename S>

@@ -116,6 +116,24 @@ int ibis_b200_host_gmres_dense(ibis_b200_ctx* ctx, const ibis_b200_linear_solver
                                double* residual);
 const char* ibis_b200_host_last_error(void);
 
+/* ---- synthetic box grid (BASELINE.json configs[4]) -------------------------------------------
+ * The GridBlock arrays (grid/grid.h:89-167) of the nx x ny x nz hex box "in unstructured form" of
+ * SURVEY.md appendix B.4, built in closed form (ibis_b200/host/box_grid.cpp) instead of through
+ * the reference's SU2 reader, bit-identical to it.  [k_lo, k_hi) selects the z-slab owned by this
+ * rank (0, nz = the whole box); a slab comes with its two-ring halo cells (numbered after the
+ * owned cells, ring 1 before ring 2) and the matching send / receive lists for
+ * ibis_b200_halo_setup.  Boundary tags are, in order: bottom east north south top west. */
+typedef struct ibis_b200_box ibis_b200_box;
+int ibis_b200_host_box_create(ibis_b200_box** out, int nx, int ny, int nz, double lx, double ly,
+                              double lz, int k_lo, int k_hi);
+const ibis_b200_grid_desc* ibis_b200_host_box_desc(const ibis_b200_box* box);
+/* peer_dir[p] = -1 (the rank below) / +1 (the rank above) */
+int ibis_b200_host_box_halo(const ibis_b200_box* box, int* n_peers, int32_t peer_dir[2],
+                            const int64_t** send_offsets, const int64_t** send_cells,
+                            const int64_t** recv_offsets, const int64_t** recv_cells);
+void ibis_b200_host_box_free(ibis_b200_box* box);
+const char* ibis_b200_host_box_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif

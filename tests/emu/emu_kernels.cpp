@@ -206,9 +206,11 @@ template <> dual mk<dual>(double r, double d) { return dual(r, d); }
 template <typename S>
 void launch_pack_in(ibis_b200_ctx* c, const double* re_, const double* du_, S* const* comps,
                     const int* map, int ncomp_ref, int64_t n) {
+    const int* perm = c->d_ref2int;
     for (int64_t i = 0; i < n; i++)
         for (int q = 0; q < ncomp_ref; q++)
-            mem<S>::store(comps[map[q]], i, mk<S>(re_[i * ncomp_ref + q], du_ ? du_[i * ncomp_ref + q] : 0.0));
+            mem<S>::store(comps[map[q]], perm ? perm[i] : i,
+                          mk<S>(re_[i * ncomp_ref + q], du_ ? du_[i * ncomp_ref + q] : 0.0));
     c->launches++;
 }
 template void launch_pack_in<double>(ibis_b200_ctx*, const double*, const double*, double* const*, const int*, int, int64_t);
@@ -217,9 +219,10 @@ template void launch_pack_in<dual>(ibis_b200_ctx*, const double*, const double*,
 template <typename S>
 void launch_pack_out(ibis_b200_ctx* c, S* const* comps, const int* map, int ncomp_ref, int64_t n,
                      double* re_, double* du_) {
+    const int* perm = c->d_ref2int;
     for (int64_t i = 0; i < n; i++)
         for (int q = 0; q < ncomp_ref; q++) {
-            const S v = mem<S>::load(comps[map[q]], i);
+            const S v = mem<S>::load(comps[map[q]], perm ? perm[i] : i);
             if (re_) re_[i * ncomp_ref + q] = re(v);
             if (du_) du_[i * ncomp_ref + q] = du(v);
         }
@@ -229,8 +232,9 @@ template void launch_pack_out<double>(ibis_b200_ctx*, double* const*, const int*
 template void launch_pack_out<dual>(ibis_b200_ctx*, dual* const*, const int*, int, int64_t, double*, double*);
 
 void launch_gather_debug(ibis_b200_ctx* c, const double* src, int ncomp, int64_t n, double* out) {
+    const int* perm = c->d_ref2int;
     for (int64_t i = 0; i < n; i++)
-        for (int q = 0; q < ncomp; q++) out[i * ncomp + q] = src[q * c->cstride + i];
+        for (int q = 0; q < ncomp; q++) out[i * ncomp + q] = src[q * c->cstride + (perm ? perm[i] : i)];
 }
 
 void launch_dot(ibis_b200_ctx* c, const double* a, const double* b, int64_t n, double* out, int post) {
@@ -271,29 +275,41 @@ static inline int cq_slot(int nc, int q) { return (nc == 4 && q == 3) ? 4 : q; }
 
 void launch_jfnk_set_dual(ibis_b200_ctx* c, dual* const* cq, const double* vec, dual* const* tmp) {
     const int nc = c->n_cons;
-    for (int64_t i = 0; i < c->n_cells; i++)
-        for (int q = 0; q < nc; q++) tmp[cq_slot(nc, q)][i] = dual(cq[cq_slot(nc, q)][i].re, vec[i * nc + q]);
+    const int* perm = c->d_ref2int;
+    for (int64_t i = 0; i < c->n_cells; i++) {
+        const int64_t p = perm ? perm[i] : i;
+        for (int q = 0; q < nc; q++) tmp[cq_slot(nc, q)][p] = dual(cq[cq_slot(nc, q)][p].re, vec[i * nc + q]);
+    }
     c->launches++;
 }
 void launch_jfnk_set_vector(ibis_b200_ctx* c, dual* const* res, const double* vec, double dt_star, double* result) {
     const int nc = c->n_cons;
-    for (int64_t i = 0; i < c->n_cells; i++)
-        for (int q = 0; q < nc; q++) result[i * nc + q] = 1 / dt_star * vec[i * nc + q] - res[cq_slot(nc, q)][i].du;
+    const int* perm = c->d_ref2int;
+    for (int64_t i = 0; i < c->n_cells; i++) {
+        const int64_t p = perm ? perm[i] : i;
+        for (int q = 0; q < nc; q++) result[i * nc + q] = 1 / dt_star * vec[i * nc + q] - res[cq_slot(nc, q)][p].du;
+    }
     c->launches++;
 }
 void launch_jfnk_eval_rhs(ibis_b200_ctx* c, dual* const* res, double* rhs) {
     const int nc = c->n_cons;
-    for (int64_t i = 0; i < c->n_cells; i++)
-        for (int q = 0; q < nc; q++) rhs[i * nc + q] = res[cq_slot(nc, q)][i].re;
+    const int* perm = c->d_ref2int;
+    for (int64_t i = 0; i < c->n_cells; i++) {
+        const int64_t p = perm ? perm[i] : i;
+        for (int q = 0; q < nc; q++) rhs[i * nc + q] = res[cq_slot(nc, q)][p].re;
+    }
     c->launches++;
 }
 void launch_jfnk_apply_update(ibis_b200_ctx* c, dual* const* cq, const double* dU) {
     const int nc = c->n_cons;
-    for (int64_t i = 0; i < c->n_cells; i++)
+    const int* perm = c->d_ref2int;
+    for (int64_t i = 0; i < c->n_cells; i++) {
+        const int64_t p = perm ? perm[i] : i;
         for (int q = 0; q < nc; q++) {
-            dual& v = cq[cq_slot(nc, q)][i];
+            dual& v = cq[cq_slot(nc, q)][p];
             v = dual(v.re + dU[i * nc + q], 0.0);
         }
+    }
     c->launches++;
 }
 
