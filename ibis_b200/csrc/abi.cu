@@ -126,6 +126,16 @@ FvArgs<S> make_args(ibis_b200_ctx* c, Buffer* fs, Buffer* dudt, bool allow_recon
         A.lim = reinterpret_cast<S*>(c->lim_d);
         A.flux = reinterpret_cast<S*>(c->flux_d);
     }
+    {   // the five reconstructed variables of pass F with their gradient / limiter arrays
+        const int src[5] = {F_RHO, (c->cfg.thermo_interpolator == THERMO_RHO_P) ? F_P
+                                   : (c->cfg.thermo_interpolator == THERMO_RHO_T) ? F_T : F_E,
+                            F_VX, F_VY, F_VZ};
+        for (int v = 0; v < 5; v++) {
+            A.rc.val[v] = A.fs[src[v]];
+            for (int k = 0; k < 3; k++) A.rc.g[v][k] = A.grad ? A.grad + (int64_t)(v * 3 + k) * c->cstride : nullptr;
+            A.rc.lim[v] = A.lim ? A.lim + (int64_t)v * c->cstride : nullptr;
+        }
+    }
     A.face_T = c->face_T;
     A.face_rho = c->face_rho;
     A.gas.R = S(c->cfg.R);
@@ -371,6 +381,67 @@ int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd_ref, con
         if (rc) { ibis_b200_destroy(c); return fail(nullptr, rc, "grid upload failed"); }
     }
 #undef UP
+    // ---- tiles of the tiled residual kernel (fv_bodies.h: GridDev::tile...) ----
+    {
+        int T = 256;
+        if (const char* e = getenv("IBIS_B200_TILE")) T = atoi(e);
+        if (T != 64 && T != 128 && T != 256) T = 256;
+        const int64_t n_owned = c->n_owned;
+        const int n_tiles = (int)((n_owned + T - 1) / T);
+        std::vector<int> home0(n_tiles + 1, 0), foreign_off(n_tiles + 1, 0);
+        for (int b = 0; b <= n_tiles; b++) home0[b] = (int)R.cell_first_face[std::min<int64_t>((int64_t)b * T, n_owned)];
+        std::vector<unsigned short> cf_slot((size_t)max_faces * cs, 0xFFFF);
+#pragma omp parallel for schedule(static)
+        for (int b = 0; b < n_tiles; b++) {
+            int nf = 0;
+            const int64_t c0 = (int64_t)b * T, c1 = std::min<int64_t>(c0 + T, n_owned);
+            for (int64_t i = c0; i < c1; i++)
+                for (int j = 0; j < max_faces; j++) {
+                    const int f = cf_face[(size_t)j * cs + i];
+                    if (f >= 0 && f < home0[b]) nf++;
+                }
+            foreign_off[b + 1] = nf;
+        }
+        for (int b = 0; b < n_tiles; b++) foreign_off[b + 1] += foreign_off[b];
+        std::vector<int> foreign(std::max(foreign_off[n_tiles], 1), 0);
+        int cap = 1;
+        bool too_many = false;
+#pragma omp parallel for schedule(static) reduction(max : cap) reduction(|| : too_many)
+        for (int b = 0; b < n_tiles; b++) {
+            const int nh = home0[b + 1] - home0[b];
+            int k = foreign_off[b];
+            const int64_t c0 = (int64_t)b * T, c1 = std::min<int64_t>(c0 + T, n_owned);
+            for (int64_t i = c0; i < c1; i++)
+                for (int j = 0; j < max_faces; j++) {
+                    const int f = cf_face[(size_t)j * cs + i];
+                    if (f < 0) continue;
+                    int slot;
+                    if (f < home0[b]) {
+                        slot = nh + (k - foreign_off[b]);
+                        foreign[k++] = f;
+                    } else {
+                        slot = f - home0[b];
+                    }
+                    if (slot >= 0xFFFF) too_many = true;
+                    cf_slot[(size_t)j * cs + i] = (unsigned short)slot;
+                }
+            cap = std::max(cap, nh + (foreign_off[b + 1] - foreign_off[b]));
+        }
+        if (too_many || (size_t)cap * (5 * 16 + 8) > 200 * 1024) {
+            ibis_b200_destroy(c);
+            return fail(nullptr, IBIS_B200_EINVAL, "tile has too many interfaces for shared memory");
+        }
+        g.tile = T;
+        g.n_tiles = n_tiles;
+        g.tile_cap = cap;
+        unsigned short* du16 = nullptr;
+#define UP2(vec, ptr, field)                                                        \
+    rc = upload_vec(c, vec, &ptr);                                                  \
+    if (rc) { ibis_b200_destroy(c); return fail(nullptr, rc, "grid upload failed"); } \
+    g.field = ptr;
+        UP2(home0, di, home0) UP2(foreign_off, di, foreign_off) UP2(foreign, di, foreign) UP2(cf_slot, du16, cf_slot)
+#undef UP2
+    }
     // WLS r-factors on the device (GridBlock::allocate_gradient_weights, grid.h:499-503)
     double* r = nullptr;
     rc = dev_alloc_zero<double>(c, 6 * cs, &r);

@@ -54,6 +54,34 @@ struct GridDev {
     const BcAction* act;
     const int* act_off;
     int n_tags;
+    // tiles of `tile` consecutive owned cells for the tiled residual kernel (pass F): the
+    // interfaces first listed by a cell of tile b ("home" interfaces) are the contiguous range
+    // [home0[b], home0[b+1]); the other interfaces of its cells ("foreign", homed in an earlier
+    // tile) are foreign[foreign_off[b] .. foreign_off[b+1]).  cf_slot is the ELL table of the
+    // tile-local flux slot of every cell face: home slot = face - home0[b], foreign slot =
+    // n_home + position in the foreign list; 0xFFFF past the cell's last face.
+    int tile, n_tiles, tile_cap;
+    const int* home0;
+    const int* foreign_off;
+    const int* foreign;
+    const unsigned short* cf_slot;
+};
+
+// the five reconstructed variables (rho, thermo-2, vx, vy, vz) of pass F, pointers resolved on
+// the host so that the unrolled kernels index them at compile time
+template <typename S>
+struct Recon {
+    const S* val[5];
+    const S* g[5][3];
+    const S* lim[5];
+};
+
+// one gradient pass (pass G): NV variables with their sources and destinations
+template <typename S, int NV>
+struct GradVars {
+    const S* src[NV];
+    S* g[NV][3];
+    S* lim[NV];
 };
 
 template <typename S>
@@ -66,6 +94,7 @@ struct FvArgs {
     S* flux;           // general path: [comp*fstride + face]
     double* face_T;    // face_fs of the viscous path (finite_volume.h:128), real parts
     double* face_rho;
+    Recon<S> rc;
     Gas<S> gas;
     S mu0, T0, Ts, Pr;
     double eps, delta, signal_factor;
@@ -229,52 +258,63 @@ IBIS_HD void wls_r_body(const GridDev& g, double* r_out, int c) {
 // pass G: WLS gradients (grid/gradient.h:66-116) of NV variables and their Barth-Jespersen
 // limiters (finite_volume/limiter.cpp:24-63) for one cell, fused: the neighbour ids,
 // centroids, r-factors and face centres are read once instead of once per variable.
-// vars[] lists the gradient slots to produce, src[] the fs[] component feeding each.
+//
+// Geometry (centroids, r-factors, face centres) is arithmetic on plain doubles also in the
+// dual instantiation: the reference carries it as duals with a zero dual part, and x + 0*y = x,
+// so values and derivatives are the same.  The loop-invariant factors of gradient.h:96-104
+// (1/r22^2, r12/r11, r23/r22, 1/r33^2) are evaluated once per cell instead of once per
+// neighbour -- same operations on the same operands, hence the same bits.
+// NF = ELL width (max faces per cell of the grid).
 // ---------------------------------------------------------------------------------------
-template <int DIM, int NV, typename S>
-IBIS_HD void grad_limit_body(const FvArgs<S>& A, int c, const int* vars, const int* src,
-                             bool do_limit) {
+template <int DIM, int NV, int NF, typename S>
+IBIS_HD void grad_limit_body(const FvArgs<S>& A, const GradVars<S, NV>& V, int c, bool do_limit) {
     const GridDev& g = A.g;
     typedef mem<S> M;
     const long cs = g.cstride;
-    // geometry enters the reference's arithmetic as T (dual with zero dual part)
-    const S r11 = S(g.wls_r[c]), r12 = S(g.wls_r[cs + c]), r22 = S(g.wls_r[2 * cs + c]);
-    S r13 = S(0.0), r23 = S(0.0), r33 = S(0.0);
+    const double r11 = g.wls_r[c], r12 = g.wls_r[cs + c], r22 = g.wls_r[2 * cs + c];
+    double r13 = 0.0, r23 = 0.0, r33 = 0.0;
     if (DIM == 3) {
-        r13 = S(g.wls_r[3 * cs + c]);
-        r23 = S(g.wls_r[4 * cs + c]);
-        r33 = S(g.wls_r[5 * cs + c]);
+        r13 = g.wls_r[3 * cs + c];
+        r23 = g.wls_r[4 * cs + c];
+        r33 = g.wls_r[5 * cs + c];
     }
-    const S beta = (r12 * r23 - r13 * r23) / (r11 * r22);     // gradient.h:89 (sic)
-    const S xi = S(g.cx[c]), yi = S(g.cy[c]), zi = S(g.cz[c]);
+    const double beta = (r12 * r23 - r13 * r23) / (r11 * r22);     // gradient.h:89 (sic)
+    const double r11sq = r11 * r11;
+    const double inv_r22sq = 1.0 / (r22 * r22);
+    const double r12_r11 = r12 / r11;
+    const double r23_r22 = r23 / r22;
+    const double inv_r33sq = (DIM == 3) ? 1.0 / (r33 * r33) : 0.0;
+    const double xi = g.cx[c], yi = g.cy[c], zi = g.cz[c];
 
     S ui[NV], gx[NV], gy[NV], gz[NV], umin[NV], umax[NV];
 #pragma unroll
     for (int v = 0; v < NV; v++) {
-        ui[v] = M::load(A.fs[src[v]], c);
+        ui[v] = M::ldg(V.src[v], c);
         gx[v] = S(0.0);
         gy[v] = S(0.0);
         gz[v] = S(0.0);
         umin[v] = ui[v];
         umax[v] = ui[v];
     }
-    for (int j = 0; j < MAXF; j++) {
-        if (j >= g.max_faces) break;
-        if (g.cf_face[j * cs + c] < 0) break;
+    int face[NF];
+#pragma unroll
+    for (int j = 0; j < NF; j++) {
+        face[j] = g.cf_face[j * cs + c];
+        if (face[j] < 0) continue;
         const int nb = g.cf_nbr[j * cs + c];
-        const S dx = S(g.cx[nb]) - xi;
-        const S dy = S(g.cy[nb]) - yi;
-        const S dz = S(g.cz[nb]) - zi;
-        const S alpha_1 = dx / (r11 * r11);
-        const S alpha_2 = 1.0 / (r22 * r22) * (dy - r12 / r11 * dx);
-        S alpha_3 = S(0.0);
-        if (DIM == 3) alpha_3 = 1.0 / (r33 * r33) * (dz - r23 / r22 * dy + beta * dx);
-        const S w_1 = alpha_1 - r12 / r11 * alpha_2 + beta * alpha_3;
-        const S w_2 = alpha_2 - r23 / r22 * alpha_3;
-        const S w_3 = alpha_3;
+        const double dx = g.cx[nb] - xi;
+        const double dy = g.cy[nb] - yi;
+        const double dz = g.cz[nb] - zi;
+        const double alpha_1 = dx / r11sq;
+        const double alpha_2 = inv_r22sq * (dy - r12_r11 * dx);
+        double alpha_3 = 0.0;
+        if (DIM == 3) alpha_3 = inv_r33sq * (dz - r23_r22 * dy + beta * dx);
+        const double w_1 = alpha_1 - r12_r11 * alpha_2 + beta * alpha_3;
+        const double w_2 = alpha_2 - r23_r22 * alpha_3;
+        const double w_3 = alpha_3;
 #pragma unroll
         for (int v = 0; v < NV; v++) {
-            const S un = M::load(A.fs[src[v]], nb);
+            const S un = M::ldg(V.src[v], nb);
             const S diff_u = un - ui[v];
             gx[v] += w_1 * diff_u;
             gy[v] += w_2 * diff_u;
@@ -285,9 +325,9 @@ IBIS_HD void grad_limit_body(const FvArgs<S>& A, int c, const int* vars, const i
     }
 #pragma unroll
     for (int v = 0; v < NV; v++) {
-        M::store(A.grad, (vars[v] * 3 + 0) * cs + c, gx[v]);
-        M::store(A.grad, (vars[v] * 3 + 1) * cs + c, gy[v]);
-        M::store(A.grad, (vars[v] * 3 + 2) * cs + c, gz[v]);
+        M::store(V.g[v][0], c, gx[v]);
+        M::store(V.g[v][1], c, gy[v]);
+        M::store(V.g[v][2], c, gz[v]);
     }
     if (!do_limit) return;
 
@@ -295,13 +335,13 @@ IBIS_HD void grad_limit_body(const FvArgs<S>& A, int c, const int* vars, const i
 #pragma unroll
     for (int v = 0; v < NV; v++) phi[v] = S(1.0);
     const long fs_ = g.fstride;
-    for (int j = 0; j < MAXF; j++) {
-        if (j >= g.max_faces) break;
-        const int f = g.cf_face[j * cs + c];
-        if (f < 0) break;
-        const S dx = S(g.f_c[f]) - xi;
-        const S dy = S(g.f_c[fs_ + f]) - yi;
-        const S dz = S(g.f_c[2 * fs_ + f]) - zi;
+#pragma unroll
+    for (int j = 0; j < NF; j++) {
+        const int f = face[j];
+        if (f < 0) continue;
+        const double dx = g.f_c[f] - xi;
+        const double dy = g.f_c[fs_ + f] - yi;
+        const double dz = g.f_c[2 * fs_ + f] - zi;
 #pragma unroll
         for (int v = 0; v < NV; v++) {
             S delta_2 = gx[v] * dx + gy[v] * dy + gz[v] * dz;
@@ -315,80 +355,81 @@ IBIS_HD void grad_limit_body(const FvArgs<S>& A, int c, const int* vars, const i
         }
     }
 #pragma unroll
-    for (int v = 0; v < NV; v++) M::store(A.lim, vars[v] * cs + c, phi[v]);
+    for (int v = 0; v < NV; v++) M::store(V.lim[v], c, phi[v]);
 }
 
 // ---------------------------------------------------------------------------------------
 // reconstruction of one side of one face (convective_flux.cpp:212-420) -> Side in the
-// GLOBAL frame (u,v,w = vx,vy,vz); rotation is applied by the caller.
+// GLOBAL frame (u,v,w = vx,vy,vz); rotation is applied by the caller.  All inputs go through
+// the read-only path: no thread of a flux kernel writes a FlowStates / gradient / limiter array.
 // ---------------------------------------------------------------------------------------
 template <int DIM, typename S>
-IBIS_HD S interp(const FvArgs<S>& A, int var, int src, int cell, bool valid, bool limit,
-                 const S& dx, const S& dy, const S& dz) {
-    // linear_interpolate (convective_flux.cpp:243-255)
+IBIS_HD S interp(const FvArgs<S>& A, int v, int cell, bool valid, bool limit, double dx, double dy,
+                 double dz) {
+    // linear_interpolate (convective_flux.cpp:243-255); v = 0 rho, 1 thermo-2, 2 vx, 3 vy, 4 vz
     typedef mem<S> M;
-    const long cs = A.g.cstride;
-    S gx = S(0.0), gy = S(0.0), gz = S(0.0);
-    // 2-D: every z-gradient, and the whole vz gradient, is identically zero in the
-    // reference (never computed, convective_flux.cpp:206-208) and its vz limiter is 1
-    const bool vz2d = (DIM == 2 && var == V_VZ);
-    if (valid && !vz2d) {
-        gx = M::load(A.grad, (var * 3 + 0) * cs + cell);
-        gy = M::load(A.grad, (var * 3 + 1) * cs + cell);
-        if (DIM == 3) gz = M::load(A.grad, (var * 3 + 2) * cs + cell);
-    }
-    const S limiter = (limit && !vz2d) ? M::load(A.lim, var * cs + cell) : S(1.0);
-    return M::load(A.fs[src], cell) + limiter * (gx * dx + gy * dy + gz * dz);
+    const S value = M::ldg(A.rc.val[v], cell);
+    // 2-D: every z-gradient, and the whole vz gradient, is identically zero in the reference
+    // (never computed, convective_flux.cpp:206-208) and its vz limiter is 1; a ghost cell has
+    // zero gradient and unit limiter (convective_flux.cpp:281-300): value + 1 * 0 = value
+    if (!valid || (DIM == 2 && v == 4)) return value;
+    const S gx = M::ldg(A.rc.g[v][0], cell);
+    const S gy = M::ldg(A.rc.g[v][1], cell);
+    S r;
+    if (DIM == 3) r = gx * dx + gy * dy + M::ldg(A.rc.g[v][2], cell) * dz;
+    else r = gx * dx + gy * dy + S(0.0) * dz;
+    if (limit) return value + M::ldg(A.rc.lim[v], cell) * r;
+    return value + S(1.0) * r;
 }
 
-template <int DIM, typename S>
+template <int DIM, bool O2, typename S>
 IBIS_HD Side<S> reconstruct_side(const FvArgs<S>& A, int f, int cell) {
     typedef mem<S> M;
     const GridDev& g = A.g;
     Side<S> s;
-    if (!A.order2) {                                          // copy_reconstruct :212-240
-        s.T = M::load(A.fs[F_T], cell);
-        s.p = M::load(A.fs[F_P], cell);
-        s.rho = M::load(A.fs[F_RHO], cell);
-        s.e = M::load(A.fs[F_E], cell);
-        s.u = M::load(A.fs[F_VX], cell);
-        s.v = M::load(A.fs[F_VY], cell);
-        s.w = M::load(A.fs[F_VZ], cell);
+    if (!O2) {                                                // copy_reconstruct :212-240
+        s.T = M::ldg(A.fs[F_T], cell);
+        s.p = M::ldg(A.fs[F_P], cell);
+        s.rho = M::ldg(A.fs[F_RHO], cell);
+        s.e = M::ldg(A.fs[F_E], cell);
+        s.u = M::ldg(A.fs[F_VX], cell);
+        s.v = M::ldg(A.fs[F_VY], cell);
+        s.w = M::ldg(A.fs[F_VZ], cell);
         return s;
     }
     const bool valid = cell < g.n_cells;
-    const bool limit = A.limiter_on && valid;
-    const S dx = S(g.f_c[f]) - S(g.cx[cell]);
-    const S dy = S(g.f_c[g.fstride + f]) - S(g.cy[cell]);
-    const S dz = S(g.f_c[2 * g.fstride + f]) - S(g.cz[cell]);
+    const bool limit = A.limiter_on != 0;
+    const double dx = g.f_c[f] - g.cx[cell];
+    const double dy = g.f_c[g.fstride + f] - g.cy[cell];
+    const double dz = g.f_c[2 * g.fstride + f] - g.cz[cell];
     // the two thermodynamic variables, then the closure (gas_model.h:91-117)
     s.p = S(0.0);
     s.T = S(0.0);
     s.e = S(0.0);
-    const S rho = interp<DIM>(A, V_RHO, F_RHO, cell, valid, limit, dx, dy, dz);
-    const S th2 = interp<DIM>(A, V_TH2, A.th2, cell, valid, limit, dx, dy, dz);
-    s.rho = rho;
+    s.rho = interp<DIM>(A, 0, cell, valid, limit, dx, dy, dz);
+    const S th2 = interp<DIM>(A, 1, cell, valid, limit, dx, dy, dz);
     if (A.thermo == THERMO_RHO_P) s.p = th2;
     else if (A.thermo == THERMO_RHO_T) s.T = th2;
     else s.e = th2;
     thermo_close(A.thermo, A.gas, s.rho, s.p, s.T, s.e);
-    s.u = interp<DIM>(A, V_VX, F_VX, cell, valid, limit, dx, dy, dz);
-    s.v = interp<DIM>(A, V_VY, F_VY, cell, valid, limit, dx, dy, dz);
-    s.w = interp<DIM>(A, V_VZ, F_VZ, cell, valid, limit, dx, dy, dz);
+    s.u = interp<DIM>(A, 2, cell, valid, limit, dx, dy, dz);
+    s.v = interp<DIM>(A, 3, cell, valid, limit, dx, dy, dz);
+    s.w = interp<DIM>(A, 4, cell, valid, limit, dx, dy, dz);
     return s;
 }
 
 // convective flux of one interface in the GLOBAL frame: reconstruct, rotate
-// (util/vector3.cpp:142-153), flux calculator, rotate back (convective_flux.cpp:148-164)
-template <int DIM, int FLUX, typename S>
+// (util/vector3.cpp:142-153), flux calculator, rotate back (convective_flux.cpp:148-164).
+// The face frame (n, t1, t2) enters as plain doubles (zero dual part in the reference).
+template <int DIM, int FLUX, bool O2, typename S>
 IBIS_HD Flux5<S> face_convective_flux(const FvArgs<S>& A, int f) {
     const GridDev& g = A.g;
     const long fs_ = g.fstride;
-    Side<S> L = reconstruct_side<DIM>(A, f, g.f_left[f]);
-    Side<S> R_ = reconstruct_side<DIM>(A, f, g.f_right[f]);
-    const S nx = S(g.f_n[f]), ny = S(g.f_n[fs_ + f]), nz = S(g.f_n[2 * fs_ + f]);
-    const S t1x = S(g.f_t1[f]), t1y = S(g.f_t1[fs_ + f]), t1z = S(g.f_t1[2 * fs_ + f]);
-    const S t2x = S(g.f_t2[f]), t2y = S(g.f_t2[fs_ + f]), t2z = S(g.f_t2[2 * fs_ + f]);
+    Side<S> L = reconstruct_side<DIM, O2>(A, f, g.f_left[f]);
+    Side<S> R_ = reconstruct_side<DIM, O2>(A, f, g.f_right[f]);
+    const double nx = g.f_n[f], ny = g.f_n[fs_ + f], nz = g.f_n[2 * fs_ + f];
+    const double t1x = g.f_t1[f], t1y = g.f_t1[fs_ + f], t1z = g.f_t1[2 * fs_ + f];
+    const double t2x = g.f_t2[f], t2y = g.f_t2[fs_ + f], t2z = g.f_t2[2 * fs_ + f];
     {
         const S x = L.u * nx + L.v * ny + L.w * nz;
         const S y = L.u * t1x + L.v * t1y + L.w * t1z;
@@ -505,11 +546,11 @@ IBIS_HD void face_viscous_flux(const FvArgs<S>& A, int f, Flux5<S>& F) {
 // ---------------------------------------------------------------------------------------
 // general path, interface kernels: write / update the face flux array
 // ---------------------------------------------------------------------------------------
-template <int DIM, int FLUX, typename S>
+template <int DIM, int FLUX, bool O2, typename S>
 IBIS_HD void face_flux_body(const FvArgs<S>& A, int f) {
     typedef mem<S> M;
     const long fs_ = A.g.fstride;
-    Flux5<S> F = face_convective_flux<DIM, FLUX>(A, f);
+    Flux5<S> F = face_convective_flux<DIM, FLUX, O2>(A, f);
     M::store(A.flux, 0 * fs_ + f, F.mass);
     M::store(A.flux, 1 * fs_ + f, F.mx);
     M::store(A.flux, 2 * fs_ + f, F.my);
@@ -561,27 +602,55 @@ IBIS_HD void integral_body(const FvArgs<S>& A, int c) {
 }
 
 // ---------------------------------------------------------------------------------------
-// fast path (inviscid): owner-computes flux + surface integral of one cell, no face
-// temporaries in memory.  Same per-face arithmetic, same in-cell summation order.
+// pass F, tiled (inviscid): one thread block owns a tile of consecutive cells.
+//   phase 1  every interface touching the tile -- its home range plus the foreign list -- gets
+//            its flux computed ONCE by one thread and staged in shared memory (5 components +
+//            the area), instead of once per adjacent cell;
+//   phase 2  every cell sums its faces' fluxes from shared memory in cell-face order:
+//            flux_surface_integral (finite_volume.cpp:221-256), owner computes, no atomics.
+// No face temporaries in global memory; same per-face arithmetic and the same in-cell
+// summation order as the reference.  sm = [5][cap] of S followed by [cap] doubles (area).
 // ---------------------------------------------------------------------------------------
-template <int DIM, int FLUX, typename S>
-IBIS_HD void cell_residual_body(const FvArgs<S>& A, int c) {
+template <int DIM, int FLUX, bool O2, typename S>
+IBIS_HD void tile_face_body(const FvArgs<S>& A, int tile, int slot, S* sm, double* sm_area) {
+    const GridDev& g = A.g;
+    const int h0 = g.home0[tile], nh = g.home0[tile + 1] - h0;
+    const int f = slot < nh ? h0 + slot : g.foreign[g.foreign_off[tile] + (slot - nh)];
+    const Flux5<S> F = face_convective_flux<DIM, FLUX, O2>(A, f);
+    const int cap = g.tile_cap;
+    sm[0 * cap + slot] = F.mass;
+    sm[1 * cap + slot] = F.mx;
+    sm[2 * cap + slot] = F.my;
+    if (DIM == 3) sm[3 * cap + slot] = F.mz;
+    sm[4 * cap + slot] = F.energy;
+    sm_area[slot] = g.f_area[f];
+}
+
+IBIS_HD int tile_num_slots(const GridDev& g, int tile) {
+    return (g.home0[tile + 1] - g.home0[tile]) + (g.foreign_off[tile + 1] - g.foreign_off[tile]);
+}
+
+template <int DIM, typename S>
+IBIS_HD void tile_cell_body(const FvArgs<S>& A, int c, const S* sm, const double* sm_area) {
     typedef mem<S> M;
     const GridDev& g = A.g;
     const long cs = g.cstride;
+    const int cap = g.tile_cap;
     S d_mass = S(0.0), d_mx = S(0.0), d_my = S(0.0), d_mz = S(0.0), d_e = S(0.0);
+#pragma unroll
     for (int j = 0; j < MAXF; j++) {
         if (j >= g.max_faces) break;
-        const int f = g.cf_face[j * cs + c];
-        if (f < 0) break;
-        const Flux5<S> F = face_convective_flux<DIM, FLUX>(A, f);
-        const S area = -S(g.f_area[f]) * (double)g.cf_out[j * cs + c];
-        d_mass += F.mass * area;
-        d_mx += F.mx * area;
-        d_my += F.my * area;
-        if (DIM == 3) d_mz += F.mz * area;
-        d_e += F.energy * area;
+        const int slot = g.cf_slot[j * cs + c];
+        if (slot == 0xFFFF) continue;
+        const double area = -sm_area[slot] * (double)g.cf_out[j * cs + c];
+        d_mass += sm[0 * cap + slot] * area;
+        d_mx += sm[1 * cap + slot] * area;
+        d_my += sm[2 * cap + slot] * area;
+        if (DIM == 3) d_mz += sm[3 * cap + slot] * area;
+        d_e += sm[4 * cap + slot] * area;
     }
+    // division by the volume stays a division by S (dual / dual rounds its dual part
+    // differently from dual / double, util/dual.h:169-180)
     const S vol = S(g.volume[c]);
     M::store(A.dudt[0], c, d_mass / vol);
     M::store(A.dudt[1], c, d_mx / vol);

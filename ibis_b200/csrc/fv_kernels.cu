@@ -68,28 +68,31 @@ __global__ void __launch_bounds__(256) k_wls_r(const GridDev g, double* r_out) {
     if (c < g.n_cells) wls_r_body(g, r_out, c);
 }
 
-struct VarList {
-    int vars[5];
-    int src[5];
-};
-
-template <int DIM, int NV, typename S>
-__global__ void __launch_bounds__(256) k_grad_limit(const FvArgs<S> A, const VarList vl,
+template <int DIM, int NV, int NF, typename S>
+__global__ void __launch_bounds__(256) k_grad_limit(const FvArgs<S> A, const GradVars<S, NV> V,
                                                      const int do_limit) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c < A.g.n_grad) grad_limit_body<DIM, NV>(A, c, vl.vars, vl.src, do_limit != 0);
+    if (c < A.g.n_grad) grad_limit_body<DIM, NV, NF>(A, V, c, do_limit != 0);
 }
 
-template <int DIM, int FLUX, typename S>
-__global__ void __launch_bounds__(128) k_residual(const FvArgs<S> A) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c < A.g.n_owned) cell_residual_body<DIM, FLUX>(A, c);
+// pass F, tiled: blockDim.x == A.g.tile; dynamic shared memory = tile_cap * (5 * sizeof(S) + 8)
+template <int DIM, int FLUX, bool O2, typename S>
+__global__ void __launch_bounds__(256, 2) k_residual_tile(const FvArgs<S> A) {
+    extern __shared__ double smem[];
+    S* sm = reinterpret_cast<S*>(smem);
+    double* sm_area = smem + (size_t)5 * A.g.tile_cap * (sizeof(S) / sizeof(double));
+    const int tile = blockIdx.x;
+    const int n = tile_num_slots(A.g, tile);
+    for (int s = threadIdx.x; s < n; s += blockDim.x) tile_face_body<DIM, FLUX, O2>(A, tile, s, sm, sm_area);
+    __syncthreads();
+    const int c = tile * A.g.tile + threadIdx.x;
+    if (c < A.g.n_owned) tile_cell_body<DIM>(A, c, sm, sm_area);
 }
 
-template <int DIM, int FLUX, typename S>
+template <int DIM, int FLUX, bool O2, typename S>
 __global__ void __launch_bounds__(128) k_face_flux(const FvArgs<S> A) {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f < A.g.n_faces) face_flux_body<DIM, FLUX>(A, f);
+    if (f < A.g.n_faces) face_flux_body<DIM, FLUX, O2>(A, f);
 }
 
 template <int DIM, typename S>
@@ -164,29 +167,64 @@ void launch_wls_r(ibis_b200_ctx* c, double* r_out) {
     CUDA_CHECK_LAUNCH(c);
 }
 
+template <int DIM, int NV, typename S>
+static void launch_grad_limit_nf(ibis_b200_ctx* c, const FvArgs<S>& A, const GradVars<S, NV>& V, int do_limit) {
+    const int nb = nblocks(A.g.n_grad, 256);
+    switch (A.g.max_faces) {
+        case 6: k_grad_limit<DIM, NV, 6, S><<<nb, 256, 0, c->stream>>>(A, V, do_limit); break;
+        case 5: k_grad_limit<DIM, NV, 5, S><<<nb, 256, 0, c->stream>>>(A, V, do_limit); break;
+        case 4: k_grad_limit<DIM, NV, 4, S><<<nb, 256, 0, c->stream>>>(A, V, do_limit); break;
+        default: k_grad_limit<DIM, NV, 3, S><<<nb, 256, 0, c->stream>>>(A, V, do_limit); break;
+    }
+}
+
 template <typename S>
 void launch_grad_limit(ibis_b200_ctx* c, const FvArgs<S>& A, bool viscous_pass) {
-    VarList vl;
-    const int nb = nblocks(A.g.n_grad, 256);
+    if (A.g.n_grad == 0) return;
+    const long cs = A.g.cstride;
     if (viscous_pass) {
         // ViscousFlux::compute_viscous_gradient (viscous_flux.cpp:122-130): T, vx, vy, vz
         const int vars[4] = {V_TVISC, V_VX, V_VY, V_VZ};
         const int src[4] = {F_T, F_VX, F_VY, F_VZ};
-        for (int i = 0; i < 4; i++) { vl.vars[i] = vars[i]; vl.src[i] = src[i]; }
-        if (A.g.dim == 3)
-            k_grad_limit<3, 4, S><<<nb, 256, 0, c->stream>>>(A, vl, 0);
-        else
-            k_grad_limit<2, 3, S><<<nb, 256, 0, c->stream>>>(A, vl, 0);   // vz == 0 in 2-D
+        if (A.g.dim == 3) {
+            GradVars<S, 4> V;
+            for (int i = 0; i < 4; i++) {
+                V.src[i] = A.fs[src[i]];
+                for (int k = 0; k < 3; k++) V.g[i][k] = A.grad + (vars[i] * 3 + k) * cs;
+                V.lim[i] = A.lim + vars[i] * cs;
+            }
+            launch_grad_limit_nf<3, 4, S>(c, A, V, 0);
+        } else {
+            GradVars<S, 3> V;                                  // vz == 0 in 2-D
+            for (int i = 0; i < 3; i++) {
+                V.src[i] = A.fs[src[i]];
+                for (int k = 0; k < 3; k++) V.g[i][k] = A.grad + (vars[i] * 3 + k) * cs;
+                V.lim[i] = A.lim + vars[i] * cs;
+            }
+            launch_grad_limit_nf<2, 3, S>(c, A, V, 0);
+        }
     } else {
         // compute_convective_gradient + compute_limiters (convective_flux.cpp:181-209,423-462)
         const int vars[5] = {V_RHO, V_TH2, V_VX, V_VY, V_VZ};
         const int src[5] = {F_RHO, A.th2, F_VX, F_VY, F_VZ};
-        for (int i = 0; i < 5; i++) { vl.vars[i] = vars[i]; vl.src[i] = src[i]; }
         prof_begin(c, 0);
-        if (A.g.dim == 3)
-            k_grad_limit<3, 5, S><<<nb, 256, 0, c->stream>>>(A, vl, A.limiter_on);
-        else
-            k_grad_limit<2, 4, S><<<nb, 256, 0, c->stream>>>(A, vl, A.limiter_on);
+        if (A.g.dim == 3) {
+            GradVars<S, 5> V;
+            for (int i = 0; i < 5; i++) {
+                V.src[i] = A.fs[src[i]];
+                for (int k = 0; k < 3; k++) V.g[i][k] = A.grad + (vars[i] * 3 + k) * cs;
+                V.lim[i] = A.lim + vars[i] * cs;
+            }
+            launch_grad_limit_nf<3, 5, S>(c, A, V, A.limiter_on);
+        } else {
+            GradVars<S, 4> V;
+            for (int i = 0; i < 4; i++) {
+                V.src[i] = A.fs[src[i]];
+                for (int k = 0; k < 3; k++) V.g[i][k] = A.grad + (vars[i] * 3 + k) * cs;
+                V.lim[i] = A.lim + vars[i] * cs;
+            }
+            launch_grad_limit_nf<2, 4, S>(c, A, V, A.limiter_on);
+        }
         prof_end(c, 0);
     }
     CUDA_CHECK_LAUNCH(c);
@@ -194,21 +232,36 @@ void launch_grad_limit(ibis_b200_ctx* c, const FvArgs<S>& A, bool viscous_pass) 
 template void launch_grad_limit<double>(ibis_b200_ctx*, const FvArgs<double>&, bool);
 template void launch_grad_limit<dual>(ibis_b200_ctx*, const FvArgs<dual>&, bool);
 
-#define DISPATCH_FLUX(KERNEL, DIMV, N, BS)                                                   \
-    switch (c->cfg.flux_calculator) {                                                        \
-        case FLUX_HANEL: KERNEL<DIMV, FLUX_HANEL, S><<<nblocks(N, BS), BS, 0, c->stream>>>(A); break;   \
-        case FLUX_AUSMDV: KERNEL<DIMV, FLUX_AUSMDV, S><<<nblocks(N, BS), BS, 0, c->stream>>>(A); break; \
-        case FLUX_LDFSS2: KERNEL<DIMV, FLUX_LDFSS2, S><<<nblocks(N, BS), BS, 0, c->stream>>>(A); break; \
-        default: KERNEL<DIMV, FLUX_RUSANOV, S><<<nblocks(N, BS), BS, 0, c->stream>>>(A); break;         \
+#define DISPATCH_FLUX_O2(KERNEL, DIMV, GRID, BS, SMEM)                                                        \
+    switch (c->cfg.flux_calculator) {                                                                          \
+        case FLUX_HANEL: LAUNCH_O2(KERNEL, DIMV, FLUX_HANEL, GRID, BS, SMEM) break;                            \
+        case FLUX_AUSMDV: LAUNCH_O2(KERNEL, DIMV, FLUX_AUSMDV, GRID, BS, SMEM) break;                          \
+        case FLUX_LDFSS2: LAUNCH_O2(KERNEL, DIMV, FLUX_LDFSS2, GRID, BS, SMEM) break;                          \
+        default: LAUNCH_O2(KERNEL, DIMV, FLUX_RUSANOV, GRID, BS, SMEM) break;                                  \
     }
+#define LAUNCH_O2(KERNEL, DIMV, FLUXV, GRID, BS, SMEM)                                                        \
+    if (A.order2) { launch_one(c, KERNEL<DIMV, FLUXV, true, S>, GRID, BS, SMEM, A); }                         \
+    else { launch_one(c, KERNEL<DIMV, FLUXV, false, S>, GRID, BS, SMEM, A); }
+
+template <typename K, typename S>
+static void launch_one(ibis_b200_ctx* c, K kernel, int grid, int bs, size_t smem, const FvArgs<S>& A) {
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess && c->last_error.empty())
+            c->last_error = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e);
+    }
+    kernel<<<grid, bs, smem, c->stream>>>(A);
+}
 
 template <typename S>
 void launch_residual(ibis_b200_ctx* c, const FvArgs<S>& A) {
+    if (A.g.n_tiles == 0) return;
+    const size_t smem = (size_t)A.g.tile_cap * (5 * sizeof(S) + sizeof(double));
     prof_begin(c, 1);
     if (A.g.dim == 3) {
-        DISPATCH_FLUX(k_residual, 3, A.g.n_owned, 128)
+        DISPATCH_FLUX_O2(k_residual_tile, 3, A.g.n_tiles, A.g.tile, smem)
     } else {
-        DISPATCH_FLUX(k_residual, 2, A.g.n_owned, 128)
+        DISPATCH_FLUX_O2(k_residual_tile, 2, A.g.n_tiles, A.g.tile, smem)
     }
     prof_end(c, 1);
     CUDA_CHECK_LAUNCH(c);
@@ -218,10 +271,11 @@ template void launch_residual<dual>(ibis_b200_ctx*, const FvArgs<dual>&);
 
 template <typename S>
 void launch_face_flux(ibis_b200_ctx* c, const FvArgs<S>& A) {
+    if (A.g.n_faces == 0) return;
     if (A.g.dim == 3) {
-        DISPATCH_FLUX(k_face_flux, 3, A.g.n_faces, 128)
+        DISPATCH_FLUX_O2(k_face_flux, 3, nblocks(A.g.n_faces, 128), 128, 0)
     } else {
-        DISPATCH_FLUX(k_face_flux, 2, A.g.n_faces, 128)
+        DISPATCH_FLUX_O2(k_face_flux, 2, nblocks(A.g.n_faces, 128), 128, 0)
     }
     CUDA_CHECK_LAUNCH(c);
 }

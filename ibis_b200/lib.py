@@ -253,7 +253,7 @@ class Context:
     def __init__(self, grid, config, device=-1, lib_path=None, n_owned=0):
         self.L = Library.load(lib_path)
         self.lib = self.L.lib
-        gd, self.tags = flatten_grid(grid, n_owned)
+        gd, self.tags = flatten_grid(grid, n_owned or getattr(grid, "n_owned", 0))
         cf = flatten_config(config, self.tags)
         self.dim = gd.dim
         self.n_cons = gd.dim + 2
@@ -414,6 +414,23 @@ class Context:
         out = np.zeros(6)
         self._ck(self.lib.ibis_b200_rk_residual_norms(self.h, _ptr(out)), "rk_residual_norms")
         return out
+
+    # domain decomposition
+    def nccl_unique_id(self):
+        buf = (C.c_char * 128)()
+        self._ck(self.lib.ibis_b200_nccl_unique_id(buf), "nccl_unique_id")
+        return bytes(buf)
+
+    def comm_init(self, unique_id, rank, n_ranks):
+        buf = (C.c_char * 128).from_buffer_copy(unique_id)
+        self._ck(self.lib.ibis_b200_comm_init(self.h, buf, int(rank), int(n_ranks)), "comm_init")
+
+    def halo_setup(self, peer_ranks, send_offsets, send_cells, recv_offsets, recv_cells):
+        pr = _as(peer_ranks, np.int32)
+        so, sc = _as(send_offsets, np.int64), _as(send_cells, np.int64)
+        ro, rc_ = _as(recv_offsets, np.int64), _as(recv_cells, np.int64)
+        self._ck(self.lib.ibis_b200_halo_setup(self.h, len(pr), _ptr(pr), _ptr(so), _ptr(sc), _ptr(ro), _ptr(rc_)),
+                 "halo_setup")
 
     # JFNK
     def jfnk_set_dual(self, cq, vec, cq_tmp):

@@ -10,6 +10,7 @@
 #include <math.h>
 
 #include <algorithm>
+#include <vector>
 
 #include "comm.h"
 #include "context.h"
@@ -35,52 +36,79 @@ void launch_wls_r(ibis_b200_ctx* c, double* r_out) {
     c->launches++;
 }
 
+template <int DIM, int NV, typename S>
+static void emu_grad_limit(const FvArgs<S>& A, const int* vars, const int* src, bool do_limit) {
+    GradVars<S, NV> V;
+    const long cs = A.g.cstride;
+    for (int i = 0; i < NV; i++) {
+        V.src[i] = A.fs[src[i]];
+        for (int k = 0; k < 3; k++) V.g[i][k] = A.grad + (vars[i] * 3 + k) * cs;
+        V.lim[i] = A.lim + vars[i] * cs;
+    }
+#pragma omp parallel for
+    for (int i = 0; i < A.g.n_grad; i++) {
+        switch (A.g.max_faces) {
+            case 6: grad_limit_body<DIM, NV, 6>(A, V, i, do_limit); break;
+            case 5: grad_limit_body<DIM, NV, 5>(A, V, i, do_limit); break;
+            case 4: grad_limit_body<DIM, NV, 4>(A, V, i, do_limit); break;
+            default: grad_limit_body<DIM, NV, 3>(A, V, i, do_limit); break;
+        }
+    }
+}
+
 template <typename S>
 void launch_grad_limit(ibis_b200_ctx* c, const FvArgs<S>& A, bool viscous_pass) {
     if (viscous_pass) {
         const int vars[4] = {V_TVISC, V_VX, V_VY, V_VZ};
         const int src[4] = {F_T, F_VX, F_VY, F_VZ};
-#pragma omp parallel for
-        for (int i = 0; i < A.g.n_grad; i++) {
-            if (A.g.dim == 3) grad_limit_body<3, 4>(A, i, vars, src, false);
-            else grad_limit_body<2, 3>(A, i, vars, src, false);
-        }
+        if (A.g.dim == 3) emu_grad_limit<3, 4>(A, vars, src, false);
+        else emu_grad_limit<2, 3>(A, vars, src, false);
     } else {
         const int vars[5] = {V_RHO, V_TH2, V_VX, V_VY, V_VZ};
         const int src[5] = {F_RHO, A.th2, F_VX, F_VY, F_VZ};
-#pragma omp parallel for
-        for (int i = 0; i < A.g.n_grad; i++) {
-            if (A.g.dim == 3) grad_limit_body<3, 5>(A, i, vars, src, A.limiter_on != 0);
-            else grad_limit_body<2, 4>(A, i, vars, src, A.limiter_on != 0);
-        }
+        if (A.g.dim == 3) emu_grad_limit<3, 5>(A, vars, src, A.limiter_on != 0);
+        else emu_grad_limit<2, 4>(A, vars, src, A.limiter_on != 0);
     }
     c->launches++;
 }
 template void launch_grad_limit<double>(ibis_b200_ctx*, const FvArgs<double>&, bool);
 template void launch_grad_limit<dual>(ibis_b200_ctx*, const FvArgs<dual>&, bool);
 
-#define EMU_FLUX_LOOP(BODY, N)                                                          \
-    _Pragma("omp parallel for") for (int i = 0; i < (N); i++) {                         \
-        if (A.g.dim == 3) {                                                             \
-            switch (c->cfg.flux_calculator) {                                           \
-                case FLUX_HANEL: BODY<3, FLUX_HANEL>(A, i); break;                      \
-                case FLUX_AUSMDV: BODY<3, FLUX_AUSMDV>(A, i); break;                    \
-                case FLUX_LDFSS2: BODY<3, FLUX_LDFSS2>(A, i); break;                    \
-                default: BODY<3, FLUX_RUSANOV>(A, i); break;                            \
-            }                                                                           \
-        } else {                                                                        \
-            switch (c->cfg.flux_calculator) {                                           \
-                case FLUX_HANEL: BODY<2, FLUX_HANEL>(A, i); break;                      \
-                case FLUX_AUSMDV: BODY<2, FLUX_AUSMDV>(A, i); break;                    \
-                case FLUX_LDFSS2: BODY<2, FLUX_LDFSS2>(A, i); break;                    \
-                default: BODY<2, FLUX_RUSANOV>(A, i); break;                            \
-            }                                                                           \
-        }                                                                               \
+// BODY<DIM, FLUX, O2>(A, i ...) for the configured flux calculator and reconstruction order
+#define EMU_FLUX_CALL(CALL)                                                              \
+    if (A.g.dim == 3) { EMU_FLUX_SW(3, CALL) } else { EMU_FLUX_SW(2, CALL) }
+#define EMU_FLUX_SW(D, CALL)                                                             \
+    switch (c->cfg.flux_calculator) {                                                    \
+        case FLUX_HANEL: EMU_O2(D, FLUX_HANEL, CALL) break;                              \
+        case FLUX_AUSMDV: EMU_O2(D, FLUX_AUSMDV, CALL) break;                            \
+        case FLUX_LDFSS2: EMU_O2(D, FLUX_LDFSS2, CALL) break;                            \
+        default: EMU_O2(D, FLUX_RUSANOV, CALL) break;                                    \
     }
+#define EMU_O2(D, F, CALL)                                                               \
+    if (A.order2) { CALL(D, F, true) } else { CALL(D, F, false) }
 
+// the tiled residual: per tile, stage every interface flux once, then gather per cell
 template <typename S>
 void launch_residual(ibis_b200_ctx* c, const FvArgs<S>& A) {
-    EMU_FLUX_LOOP(cell_residual_body, A.g.n_owned)
+    const GridDev& g = A.g;
+#pragma omp parallel
+    {
+        std::vector<S> sm((size_t)5 * g.tile_cap);
+        std::vector<double> sm_area(g.tile_cap);
+#pragma omp for
+        for (int t = 0; t < g.n_tiles; t++) {
+            const int n = tile_num_slots(g, t);
+#define TILE_FACES(D, F, O) for (int s = 0; s < n; s++) tile_face_body<D, F, O>(A, t, s, sm.data(), sm_area.data());
+            EMU_FLUX_CALL(TILE_FACES)
+#undef TILE_FACES
+            for (int k = 0; k < g.tile; k++) {
+                const int cell = t * g.tile + k;
+                if (cell >= g.n_owned) break;
+                if (g.dim == 3) tile_cell_body<3>(A, cell, sm.data(), sm_area.data());
+                else tile_cell_body<2>(A, cell, sm.data(), sm_area.data());
+            }
+        }
+    }
     c->launches++;
 }
 template void launch_residual<double>(ibis_b200_ctx*, const FvArgs<double>&);
@@ -88,7 +116,12 @@ template void launch_residual<dual>(ibis_b200_ctx*, const FvArgs<dual>&);
 
 template <typename S>
 void launch_face_flux(ibis_b200_ctx* c, const FvArgs<S>& A) {
-    EMU_FLUX_LOOP(face_flux_body, A.g.n_faces)
+#pragma omp parallel for
+    for (int i = 0; i < A.g.n_faces; i++) {
+#define FACE_FLUX(D, F, O) face_flux_body<D, F, O>(A, i);
+        EMU_FLUX_CALL(FACE_FLUX)
+#undef FACE_FLUX
+    }
     c->launches++;
 }
 template void launch_face_flux<double>(ibis_b200_ctx*, const FvArgs<double>&);

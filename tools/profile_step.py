@@ -19,7 +19,7 @@ def main():
     import cases
     from ibis_b200 import config as cfg
     from ibis_b200.lib import Context
-    mesh, g = bench.box_grid_host(args.n)
+    g = bench.box_grid_fast(args.n)
     prim = cases.perturbed_state(g, 3)
     ctx = Context(g, bench.box_config())
     if args.dual:
