@@ -279,8 +279,8 @@ int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd_ref, con
         max_faces = std::max<int>(max_faces, (int)(gd->cell_face_offsets[i + 1] - gd->cell_face_offsets[i]));
     if (max_faces > MAXF) { ibis_b200_destroy(c); return fail(nullptr, IBIS_B200_EINVAL, "cell with more than 6 faces"); }
     if (max_faces == 0) max_faces = 1;
-    std::vector<int> cf_face((size_t)max_faces * cs, -1), cf_nbr((size_t)max_faces * cs, 0);
-    std::vector<signed char> cf_out((size_t)max_faces * cs, 0);
+    std::vector<int> cf_face((size_t)max_faces * cs, -1), cf_nbr((size_t)max_faces * cs, -1);
+    std::vector<signed char> cf_out((size_t)MAXF * cs, 0);            // MAXF wide, see GridDev
     int64_t n_grad = 0;
     bool grad_prefix_open = true;
     for (int64_t i = 0; i < gd->n_cells; i++) {
@@ -383,14 +383,14 @@ int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd_ref, con
 #undef UP
     // ---- tiles of the tiled residual kernel (fv_bodies.h: GridDev::tile...) ----
     {
-        int T = 256;
+        int T = 128;
         if (const char* e = getenv("IBIS_B200_TILE")) T = atoi(e);
-        if (T != 64 && T != 128 && T != 256) T = 256;
+        if (T != 64 && T != 128 && T != 256) T = 128;
         const int64_t n_owned = c->n_owned;
         const int n_tiles = (int)((n_owned + T - 1) / T);
         std::vector<int> home0(n_tiles + 1, 0), foreign_off(n_tiles + 1, 0);
         for (int b = 0; b <= n_tiles; b++) home0[b] = (int)R.cell_first_face[std::min<int64_t>((int64_t)b * T, n_owned)];
-        std::vector<unsigned short> cf_slot((size_t)max_faces * cs, 0xFFFF);
+        std::vector<unsigned short> cf_slot((size_t)MAXF * cs, 0xFFFF);
 #pragma omp parallel for schedule(static)
         for (int b = 0; b < n_tiles; b++) {
             int nf = 0;
@@ -427,9 +427,49 @@ int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd_ref, con
                 }
             cap = std::max(cap, nh + (foreign_off[b + 1] - foreign_off[b]));
         }
-        if (too_many || (size_t)cap * (5 * 16 + 8) > 200 * 1024) {
+        if (too_many || cap >= 0x7FFF || (size_t)cap * (12 * 16) > 220 * 1024) {
             ibis_b200_destroy(c);
             return fail(nullptr, IBIS_B200_EINVAL, "tile has too many interfaces for shared memory");
+        }
+        // sides of the tile's interfaces that belong to cells outside the tile
+        std::vector<int> out_off(n_tiles + 1, 0);
+        auto face_of_slot = [&](int b, int slot) {
+            const int nh = home0[b + 1] - home0[b];
+            return slot < nh ? home0[b] + slot : foreign[foreign_off[b] + (slot - nh)];
+        };
+#pragma omp parallel for schedule(static)
+        for (int b = 0; b < n_tiles; b++) {
+            const int64_t c0 = (int64_t)b * T, c1 = std::min<int64_t>(c0 + T, n_owned);
+            const int ns = (home0[b + 1] - home0[b]) + (foreign_off[b + 1] - foreign_off[b]);
+            int n = 0;
+            for (int sl = 0; sl < ns; sl++) {
+                const int f = face_of_slot(b, sl);
+                if (!(fl[f] >= c0 && fl[f] < c1)) n++;
+                if (!(fr[f] >= c0 && fr[f] < c1)) n++;
+            }
+            out_off[b + 1] = n;
+        }
+        for (int b = 0; b < n_tiles; b++) out_off[b + 1] += out_off[b];
+        const int64_t n_out = std::max(out_off[n_tiles], 1);
+        std::vector<unsigned short> out_slot(n_out, 0);
+        std::vector<int> out_cell(n_out, 0);
+        std::vector<double> out_d((size_t)3 * n_out, 0.0);
+        auto set_out = [&](int k, int slot_side, int f, int cell) {
+            out_slot[k] = (unsigned short)slot_side;
+            out_cell[k] = cell;
+            for (int d = 0; d < 3; d++)     // face centre - centroid, as reconstruct_side computes it
+                out_d[(size_t)d * n_out + k] = fc[(size_t)d * fs + f] - cxyz[(size_t)d * cs + cell];
+        };
+#pragma omp parallel for schedule(static)
+        for (int b = 0; b < n_tiles; b++) {
+            const int64_t c0 = (int64_t)b * T, c1 = std::min<int64_t>(c0 + T, n_owned);
+            const int ns = (home0[b + 1] - home0[b]) + (foreign_off[b + 1] - foreign_off[b]);
+            int k = out_off[b];
+            for (int sl = 0; sl < ns; sl++) {
+                const int f = face_of_slot(b, sl);
+                if (!(fl[f] >= c0 && fl[f] < c1)) set_out(k++, sl, f, fl[f]);
+                if (!(fr[f] >= c0 && fr[f] < c1)) set_out(k++, sl | 0x8000, f, fr[f]);
+            }
         }
         g.tile = T;
         g.n_tiles = n_tiles;
@@ -440,6 +480,8 @@ int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd_ref, con
     if (rc) { ibis_b200_destroy(c); return fail(nullptr, rc, "grid upload failed"); } \
     g.field = ptr;
         UP2(home0, di, home0) UP2(foreign_off, di, foreign_off) UP2(foreign, di, foreign) UP2(cf_slot, du16, cf_slot)
+        UP2(out_off, di, out_off) UP2(out_slot, du16, out_slot) UP2(out_cell, di, out_cell) UP2(out_d, dd, out_d)
+        g.n_out = n_out;
 #undef UP2
     }
     // WLS r-factors on the device (GridBlock::allocate_gradient_weights, grid.h:499-503)
@@ -447,7 +489,14 @@ int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd_ref, con
     rc = dev_alloc_zero<double>(c, 6 * cs, &r);
     if (rc) { ibis_b200_destroy(c); return fail(nullptr, rc, "out of device memory"); }
     g.wls_r = r;
+    double *cfw = nullptr, *cfd = nullptr;
+    rc = dev_alloc_zero<double>(c, (int64_t)max_faces * 3 * cs, &cfw);
+    if (!rc) rc = dev_alloc_zero<double>(c, (int64_t)MAXF * 3 * cs, &cfd);           // MAXF wide, see GridDev
+    if (rc) { ibis_b200_destroy(c); return fail(nullptr, rc, "out of device memory"); }
+    g.cf_w = cfw;
+    g.cf_d = cfd;
     launch_wls_r(c, r);
+    launch_cell_static(c, cfw, cfd);
 
     // reductions
     c->n_red_blocks = 148 * 8;

@@ -100,6 +100,7 @@ namespace ib {
 template <typename S>
 void launch_bc(ibis_b200_ctx* c, const FvArgs<S>& A, int phase);
 void launch_wls_r(ibis_b200_ctx* c, double* r_out);
+void launch_cell_static(ibis_b200_ctx* c, double* w_out, double* d_out);   // cf_w, cf_d (after wls_r)
 template <typename S>
 void launch_grad_limit(ibis_b200_ctx* c, const FvArgs<S>& A, bool viscous_pass);
 template <typename S>

@@ -39,6 +39,10 @@ struct GridDev {
     const double* cy;
     const double* cz;
     const double* wls_r;        // [6][cstride] r11 r12 r22 r13 r23 r33 (grid/gradient.h:153-160)
+    // static per cell-face data, [(slot*3 + xyz)*cstride + cell], computed once at setup by
+    // cell_static_body with the reference's formulas (the grid does not move):
+    const double* cf_w;         // WLS weights w_1 w_2 w_3 of the neighbour across the face (gradient.h:96-108)
+    const double* cf_d;         // face centre - cell centroid (limiter.cpp:44-47, convective_flux.cpp:286-290)
     // per face, SoA with stride fstride
     const int* f_left;
     const int* f_right;
@@ -65,6 +69,17 @@ struct GridDev {
     const int* foreign_off;
     const int* foreign;
     const unsigned short* cf_slot;
+    // sides of the tile's interfaces whose cell is NOT a cell of the tile (neighbouring tiles,
+    // halo cells, boundary ghosts): entries [out_off[b], out_off[b+1]) of (slot | side << 15, cell)
+    // and the static offset face centre - centroid of that cell, out_d[xyz * n_out + e]
+    const int* out_off;
+    const unsigned short* out_slot;
+    const int* out_cell;
+    const double* out_d;
+    long n_out;
+    // NOTE cf_slot, cf_out and cf_d are always MAXF slots wide (absent slots: 0xFFFF / 0 / 0) so
+    // that the tiled kernel can load all slots unconditionally; cf_face, cf_nbr, cf_w are
+    // max_faces wide.
 };
 
 // the five reconstructed variables (rho, thermo-2, vx, vy, vz) of pass F, pointers resolved on
@@ -254,23 +269,13 @@ IBIS_HD void wls_r_body(const GridDev& g, double* r_out, int c) {
     }
 }
 
-// ---------------------------------------------------------------------------------------
-// pass G: WLS gradients (grid/gradient.h:66-116) of NV variables and their Barth-Jespersen
-// limiters (finite_volume/limiter.cpp:24-63) for one cell, fused: the neighbour ids,
-// centroids, r-factors and face centres are read once instead of once per variable.
-//
-// Geometry (centroids, r-factors, face centres) is arithmetic on plain doubles also in the
-// dual instantiation: the reference carries it as duals with a zero dual part, and x + 0*y = x,
-// so values and derivatives are the same.  The loop-invariant factors of gradient.h:96-104
-// (1/r22^2, r12/r11, r23/r22, 1/r33^2) are evaluated once per cell instead of once per
-// neighbour -- same operations on the same operands, hence the same bits.
-// NF = ELL width (max faces per cell of the grid).
-// ---------------------------------------------------------------------------------------
-template <int DIM, int NV, int NF, typename S>
-IBIS_HD void grad_limit_body(const FvArgs<S>& A, const GradVars<S, NV>& V, int c, bool do_limit) {
-    const GridDev& g = A.g;
-    typedef mem<S> M;
-    const long cs = g.cstride;
+// static per cell-face geometry: WLS weights of every face neighbour (gradient.h:84-108) and
+// the face-centre offsets.  Written once at setup; the formulas and their association are the
+// reference's, with the loop-invariant factors (1/r22^2, r12/r11, r23/r22, 1/r33^2) evaluated
+// once per cell -- the same operations on the same operands, hence the same bits.
+template <int DIM>
+IBIS_HD void cell_static_body(const GridDev& g, double* w_out, double* d_out, int c) {
+    const long cs = g.cstride, fs_ = g.fstride;
     const double r11 = g.wls_r[c], r12 = g.wls_r[cs + c], r22 = g.wls_r[2 * cs + c];
     double r13 = 0.0, r23 = 0.0, r33 = 0.0;
     if (DIM == 3) {
@@ -285,7 +290,40 @@ IBIS_HD void grad_limit_body(const FvArgs<S>& A, const GradVars<S, NV>& V, int c
     const double r23_r22 = r23 / r22;
     const double inv_r33sq = (DIM == 3) ? 1.0 / (r33 * r33) : 0.0;
     const double xi = g.cx[c], yi = g.cy[c], zi = g.cz[c];
+    for (int j = 0; j < g.max_faces; j++) {
+        const int f = g.cf_face[j * cs + c];
+        if (f < 0) break;
+        const int nb = g.cf_nbr[j * cs + c];
+        const double dx = g.cx[nb] - xi;
+        const double dy = g.cy[nb] - yi;
+        const double dz = g.cz[nb] - zi;
+        const double alpha_1 = dx / r11sq;
+        const double alpha_2 = inv_r22sq * (dy - r12_r11 * dx);
+        double alpha_3 = 0.0;
+        if (DIM == 3) alpha_3 = inv_r33sq * (dz - r23_r22 * dy + beta * dx);
+        w_out[(j * 3 + 0) * cs + c] = alpha_1 - r12_r11 * alpha_2 + beta * alpha_3;
+        w_out[(j * 3 + 1) * cs + c] = alpha_2 - r23_r22 * alpha_3;
+        w_out[(j * 3 + 2) * cs + c] = alpha_3;
+        d_out[(j * 3 + 0) * cs + c] = g.f_c[f] - xi;
+        d_out[(j * 3 + 1) * cs + c] = g.f_c[fs_ + f] - yi;
+        d_out[(j * 3 + 2) * cs + c] = g.f_c[2 * fs_ + f] - zi;
+    }
+}
 
+// ---------------------------------------------------------------------------------------
+// pass G: WLS gradients (grid/gradient.h:66-116) of NV variables and their Barth-Jespersen
+// limiters (finite_volume/limiter.cpp:24-63) for one cell, fused, from the static weights and
+// offsets: per cell the only gathers left are the neighbours' NV values.
+//
+// Geometry is arithmetic on plain doubles also in the dual instantiation: the reference
+// carries it as duals with a zero dual part, and x + 0*y = x, so values and derivatives are
+// the same.  NF = ELL width (max faces per cell of the grid).
+// ---------------------------------------------------------------------------------------
+template <int DIM, int NV, int NF, typename S>
+IBIS_HD void grad_limit_body(const FvArgs<S>& A, const GradVars<S, NV>& V, int c, bool do_limit) {
+    const GridDev& g = A.g;
+    typedef mem<S> M;
+    const long cs = g.cstride;
     S ui[NV], gx[NV], gy[NV], gz[NV], umin[NV], umax[NV];
 #pragma unroll
     for (int v = 0; v < NV; v++) {
@@ -296,22 +334,21 @@ IBIS_HD void grad_limit_body(const FvArgs<S>& A, const GradVars<S, NV>& V, int c
         umin[v] = ui[v];
         umax[v] = ui[v];
     }
-    int face[NF];
+    // Branch-free over the ELL slots so that every load of the cell can be in flight at once:
+    // an absent slot (cell with fewer than NF faces) has zero weights and zero offsets and is
+    // pointed at the cell itself, so it adds w * (u_i - u_i) = 0 and leaves min / max alone.
+    int nbr[NF];
 #pragma unroll
     for (int j = 0; j < NF; j++) {
-        face[j] = g.cf_face[j * cs + c];
-        if (face[j] < 0) continue;
         const int nb = g.cf_nbr[j * cs + c];
-        const double dx = g.cx[nb] - xi;
-        const double dy = g.cy[nb] - yi;
-        const double dz = g.cz[nb] - zi;
-        const double alpha_1 = dx / r11sq;
-        const double alpha_2 = inv_r22sq * (dy - r12_r11 * dx);
-        double alpha_3 = 0.0;
-        if (DIM == 3) alpha_3 = inv_r33sq * (dz - r23_r22 * dy + beta * dx);
-        const double w_1 = alpha_1 - r12_r11 * alpha_2 + beta * alpha_3;
-        const double w_2 = alpha_2 - r23_r22 * alpha_3;
-        const double w_3 = alpha_3;
+        nbr[j] = nb < 0 ? c : nb;
+    }
+#pragma unroll
+    for (int j = 0; j < NF; j++) {
+        const int nb = nbr[j];
+        const double w_1 = g.cf_w[(j * 3 + 0) * cs + c];
+        const double w_2 = g.cf_w[(j * 3 + 1) * cs + c];
+        const double w_3 = (DIM == 3) ? g.cf_w[(j * 3 + 2) * cs + c] : 0.0;
 #pragma unroll
         for (int v = 0; v < NV; v++) {
             const S un = M::ldg(V.src[v], nb);
@@ -334,14 +371,12 @@ IBIS_HD void grad_limit_body(const FvArgs<S>& A, const GradVars<S, NV>& V, int c
     S phi[NV];
 #pragma unroll
     for (int v = 0; v < NV; v++) phi[v] = S(1.0);
-    const long fs_ = g.fstride;
 #pragma unroll
     for (int j = 0; j < NF; j++) {
-        const int f = face[j];
-        if (f < 0) continue;
-        const double dx = g.f_c[f] - xi;
-        const double dy = g.f_c[fs_ + f] - yi;
-        const double dz = g.f_c[2 * fs_ + f] - zi;
+        // absent slot: zero offsets -> delta_2 = 0 -> sgn = 0 -> no constraint
+        const double dx = g.cf_d[(j * 3 + 0) * cs + c];
+        const double dy = g.cf_d[(j * 3 + 1) * cs + c];
+        const double dz = g.cf_d[(j * 3 + 2) * cs + c];
 #pragma unroll
         for (int v = 0; v < NV; v++) {
             S delta_2 = gx[v] * dx + gy[v] * dy + gz[v] * dz;
@@ -382,8 +417,10 @@ IBIS_HD S interp(const FvArgs<S>& A, int v, int cell, bool valid, bool limit, do
     return value + S(1.0) * r;
 }
 
+// one side from the cell's values / gradients / limiters and the offset (dx, dy, dz) = face
+// centre - cell centroid
 template <int DIM, bool O2, typename S>
-IBIS_HD Side<S> reconstruct_side(const FvArgs<S>& A, int f, int cell) {
+IBIS_HD Side<S> reconstruct_at(const FvArgs<S>& A, int cell, double dx, double dy, double dz) {
     typedef mem<S> M;
     const GridDev& g = A.g;
     Side<S> s;
@@ -399,9 +436,6 @@ IBIS_HD Side<S> reconstruct_side(const FvArgs<S>& A, int f, int cell) {
     }
     const bool valid = cell < g.n_cells;
     const bool limit = A.limiter_on != 0;
-    const double dx = g.f_c[f] - g.cx[cell];
-    const double dy = g.f_c[g.fstride + f] - g.cy[cell];
-    const double dz = g.f_c[2 * g.fstride + f] - g.cz[cell];
     // the two thermodynamic variables, then the closure (gas_model.h:91-117)
     s.p = S(0.0);
     s.T = S(0.0);
@@ -416,6 +450,18 @@ IBIS_HD Side<S> reconstruct_side(const FvArgs<S>& A, int f, int cell) {
     s.v = interp<DIM>(A, 3, cell, valid, limit, dx, dy, dz);
     s.w = interp<DIM>(A, 4, cell, valid, limit, dx, dy, dz);
     return s;
+}
+
+template <int DIM, bool O2, typename S>
+IBIS_HD Side<S> reconstruct_side(const FvArgs<S>& A, int f, int cell) {
+    const GridDev& g = A.g;
+    double dx = 0.0, dy = 0.0, dz = 0.0;
+    if (O2) {
+        dx = g.f_c[f] - g.cx[cell];
+        dy = g.f_c[g.fstride + f] - g.cy[cell];
+        dz = g.f_c[2 * g.fstride + f] - g.cz[cell];
+    }
+    return reconstruct_at<DIM, O2>(A, cell, dx, dy, dz);
 }
 
 // convective flux of one interface in the GLOBAL frame: reconstruct, rotate
@@ -602,56 +648,196 @@ IBIS_HD void integral_body(const FvArgs<S>& A, int c) {
 }
 
 // ---------------------------------------------------------------------------------------
-// pass F, tiled (inviscid): one thread block owns a tile of consecutive cells.
-//   phase 1  every interface touching the tile -- its home range plus the foreign list -- gets
-//            its flux computed ONCE by one thread and staged in shared memory (5 components +
-//            the area), instead of once per adjacent cell;
-//   phase 2  every cell sums its faces' fluxes from shared memory in cell-face order:
-//            flux_surface_integral (finite_volume.cpp:221-256), owner computes, no atomics.
-// No face temporaries in global memory; same per-face arithmetic and the same in-cell
-// summation order as the reference.  sm = [5][cap] of S followed by [cap] doubles (area).
+// pass F, tiled (inviscid): one thread block owns a tile of consecutive cells and stages the
+// face stencil in shared memory.  st = [2 sides][6][cap] of S.
+//   phase 1a  one thread per CELL: its own values, gradients and limiters (coalesced loads, no
+//             gather) are extrapolated to each of its faces (MUSCL, convective_flux.cpp:258-420)
+//             and the state (rho p T u v w) is written to that face's left or right slot;
+//   phase 1b  the sides that belong to cells outside the tile (neighbouring tiles, halo,
+//             boundary ghosts) are reconstructed from gathered data;
+//   phase 2   one thread per INTERFACE: rotate, flux calculator, rotate back -- each flux ONCE
+//             instead of once per adjacent cell; the flux replaces the left state in place;
+//   phase 3   one thread per cell: flux_surface_integral (finite_volume.cpp:221-256) from shared
+//             memory in cell-face order: owner computes, no atomics, no face arrays in HBM.
+// Same per-face arithmetic and the same in-cell summation order as the reference.
 // ---------------------------------------------------------------------------------------
-template <int DIM, int FLUX, bool O2, typename S>
-IBIS_HD void tile_face_body(const FvArgs<S>& A, int tile, int slot, S* sm, double* sm_area) {
+template <typename S>
+IBIS_HD void tile_store_side(S* st, int cap, int side, int slot, const Side<S>& s) {
+    S* p = st + (size_t)side * 6 * cap + slot;
+    p[0 * cap] = s.rho;
+    p[1 * cap] = s.p;
+    p[2 * cap] = s.T;
+    p[3 * cap] = s.u;
+    p[4 * cap] = s.v;
+    p[5 * cap] = s.w;
+}
+
+// phase 1a: cell c (a cell of the tile) -> one side of each of its faces.  Every load is
+// unconditional (the slot tables are MAXF wide) so that all of them can be in flight together;
+// only the shared-memory store is predicated on the slot being present.
+template <int DIM, bool O2, typename S>
+IBIS_HD void tile_recon_own_body(const FvArgs<S>& A, int c, S* st) {
+    typedef mem<S> M;
     const GridDev& g = A.g;
-    const int h0 = g.home0[tile], nh = g.home0[tile + 1] - h0;
-    const int f = slot < nh ? h0 + slot : g.foreign[g.foreign_off[tile] + (slot - nh)];
-    const Flux5<S> F = face_convective_flux<DIM, FLUX, O2>(A, f);
+    const long cs = g.cstride;
     const int cap = g.tile_cap;
-    sm[0 * cap + slot] = F.mass;
-    sm[1 * cap + slot] = F.mx;
-    sm[2 * cap + slot] = F.my;
-    if (DIM == 3) sm[3 * cap + slot] = F.mz;
-    sm[4 * cap + slot] = F.energy;
-    sm_area[slot] = g.f_area[f];
+    int slot[MAXF], side[MAXF];
+#pragma unroll
+    for (int j = 0; j < MAXF; j++) {
+        slot[j] = g.cf_slot[j * cs + c];
+        side[j] = g.cf_out[j * cs + c] > 0 ? 0 : 1;
+    }
+    if (!O2) {                                                // copy_reconstruct :212-240
+        Side<S> s;
+        s.T = M::ldg(A.fs[F_T], c);
+        s.p = M::ldg(A.fs[F_P], c);
+        s.rho = M::ldg(A.fs[F_RHO], c);
+        s.e = S(0.0);
+        s.u = M::ldg(A.fs[F_VX], c);
+        s.v = M::ldg(A.fs[F_VY], c);
+        s.w = M::ldg(A.fs[F_VZ], c);
+#pragma unroll
+        for (int j = 0; j < MAXF; j++)
+            if (slot[j] != 0xFFFF) tile_store_side(st, cap, side[j], slot[j], s);
+        return;
+    }
+    S val[5], gx[5], gy[5], gz[5], lim[5];
+#pragma unroll
+    for (int v = 0; v < 5; v++) {
+        val[v] = M::ldg(A.rc.val[v], c);
+        if (DIM == 2 && v == 4) continue;                     // vz: no gradient in 2-D
+        gx[v] = M::ldg(A.rc.g[v][0], c);
+        gy[v] = M::ldg(A.rc.g[v][1], c);
+        gz[v] = (DIM == 3) ? M::ldg(A.rc.g[v][2], c) : S(0.0);
+        lim[v] = A.limiter_on ? M::ldg(A.rc.lim[v], c) : S(1.0);
+    }
+    double d[MAXF][3];
+#pragma unroll
+    for (int j = 0; j < MAXF; j++)
+#pragma unroll
+        for (int k = 0; k < 3; k++) d[j][k] = g.cf_d[(j * 3 + k) * cs + c];
+#pragma unroll
+    for (int j = 0; j < MAXF; j++) {
+        const double dx = d[j][0], dy = d[j][1], dz = d[j][2];
+        S r[5];
+#pragma unroll
+        for (int v = 0; v < 5; v++) {
+            if (DIM == 2 && v == 4) { r[v] = val[v]; continue; }
+            r[v] = val[v] + lim[v] * (gx[v] * dx + gy[v] * dy + gz[v] * dz);   // linear_interpolate :243-255
+        }
+        Side<S> s;
+        s.p = S(0.0);
+        s.T = S(0.0);
+        s.e = S(0.0);
+        s.rho = r[0];
+        if (A.thermo == THERMO_RHO_P) s.p = r[1];
+        else if (A.thermo == THERMO_RHO_T) s.T = r[1];
+        else s.e = r[1];
+        thermo_close(A.thermo, A.gas, s.rho, s.p, s.T, s.e);
+        s.u = r[2];
+        s.v = r[3];
+        s.w = r[4];
+        if (slot[j] != 0xFFFF) tile_store_side(st, cap, side[j], slot[j], s);
+    }
 }
 
 IBIS_HD int tile_num_slots(const GridDev& g, int tile) {
     return (g.home0[tile + 1] - g.home0[tile]) + (g.foreign_off[tile + 1] - g.foreign_off[tile]);
 }
+IBIS_HD int tile_face_of_slot(const GridDev& g, int tile, int slot) {
+    const int h0 = g.home0[tile], nh = g.home0[tile + 1] - h0;
+    return slot < nh ? h0 + slot : g.foreign[g.foreign_off[tile] + (slot - nh)];
+}
 
+// phase 1b: entry e of the tile's outside-side list (gathers; the offset is static)
+template <int DIM, bool O2, typename S>
+IBIS_HD void tile_recon_outside_body(const FvArgs<S>& A, int e, S* st) {
+    const GridDev& g = A.g;
+    const int packed = g.out_slot[e];
+    const int slot = packed & 0x7FFF, side = packed >> 15;
+    const int cell = g.out_cell[e];
+    double dx = 0.0, dy = 0.0, dz = 0.0;
+    if (O2) {
+        dx = g.out_d[e];
+        dy = g.out_d[g.n_out + e];
+        dz = g.out_d[2 * g.n_out + e];
+    }
+    const Side<S> s = reconstruct_at<DIM, O2>(A, cell, dx, dy, dz);
+    tile_store_side(st, g.tile_cap, side, slot, s);
+}
+
+// phase 2: interface in slot `slot`: st[0][0..4][slot] <- flux (global frame), st[0][5][slot] <- area
+template <int DIM, int FLUX, typename S>
+IBIS_HD void tile_flux_body(const FvArgs<S>& A, int tile, int slot, S* st) {
+    const GridDev& g = A.g;
+    const long fs_ = g.fstride;
+    const int cap = g.tile_cap;
+    const int f = tile_face_of_slot(g, tile, slot);
+    Side<S> L, R_;
+    {
+        const S* p = st + slot;
+        L.rho = p[0 * cap]; L.p = p[1 * cap]; L.T = p[2 * cap]; L.u = p[3 * cap]; L.v = p[4 * cap]; L.w = p[5 * cap];
+        p += (size_t)6 * cap;
+        R_.rho = p[0 * cap]; R_.p = p[1 * cap]; R_.T = p[2 * cap]; R_.u = p[3 * cap]; R_.v = p[4 * cap]; R_.w = p[5 * cap];
+        L.e = S(0.0);
+        R_.e = S(0.0);
+    }
+    const double nx = g.f_n[f], ny = g.f_n[fs_ + f], nz = g.f_n[2 * fs_ + f];
+    const double t1x = g.f_t1[f], t1y = g.f_t1[fs_ + f], t1z = g.f_t1[2 * fs_ + f];
+    const double t2x = g.f_t2[f], t2y = g.f_t2[fs_ + f], t2z = g.f_t2[2 * fs_ + f];
+    {
+        const S x = L.u * nx + L.v * ny + L.w * nz;           // util/vector3.cpp:142-153
+        const S y = L.u * t1x + L.v * t1y + L.w * t1z;
+        const S z = L.u * t2x + L.v * t2y + L.w * t2z;
+        L.u = x; L.v = y; L.w = z;
+    }
+    {
+        const S x = R_.u * nx + R_.v * ny + R_.w * nz;
+        const S y = R_.u * t1x + R_.v * t1y + R_.w * t1z;
+        const S z = R_.u * t2x + R_.v * t2y + R_.w * t2z;
+        R_.u = x; R_.v = y; R_.w = z;
+    }
+    Flux5<S> F = flux_calc<FLUX>(L, R_, A.gas, A.delta);
+    const S px = F.mx, py = F.my;
+    const S pz = (DIM == 3) ? F.mz : S(0.0);
+    S* q = st + slot;
+    q[0 * cap] = F.mass;                                      // convective_flux.cpp:148-164
+    q[1 * cap] = px * nx + py * t1x + pz * t2x;
+    q[2 * cap] = px * ny + py * t1y + pz * t2y;
+    q[3 * cap] = px * nz + py * t1z + pz * t2z;
+    q[4 * cap] = F.energy;
+    q[5 * cap] = S(g.f_area[f]);
+}
+
+// phase 3
 template <int DIM, typename S>
-IBIS_HD void tile_cell_body(const FvArgs<S>& A, int c, const S* sm, const double* sm_area) {
+IBIS_HD void tile_cell_body(const FvArgs<S>& A, int c, const S* st) {
     typedef mem<S> M;
     const GridDev& g = A.g;
     const long cs = g.cstride;
     const int cap = g.tile_cap;
+    int slot[MAXF];
+    double out[MAXF];
+#pragma unroll
+    for (int j = 0; j < MAXF; j++) {
+        slot[j] = g.cf_slot[j * cs + c];
+        out[j] = (double)g.cf_out[j * cs + c];
+    }
+    const S vol = S(g.volume[c]);
     S d_mass = S(0.0), d_mx = S(0.0), d_my = S(0.0), d_mz = S(0.0), d_e = S(0.0);
 #pragma unroll
     for (int j = 0; j < MAXF; j++) {
-        if (j >= g.max_faces) break;
-        const int slot = g.cf_slot[j * cs + c];
-        if (slot == 0xFFFF) continue;
-        const double area = -sm_area[slot] * (double)g.cf_out[j * cs + c];
-        d_mass += sm[0 * cap + slot] * area;
-        d_mx += sm[1 * cap + slot] * area;
-        d_my += sm[2 * cap + slot] * area;
-        if (DIM == 3) d_mz += sm[3 * cap + slot] * area;
-        d_e += sm[4 * cap + slot] * area;
+        if (slot[j] == 0xFFFF) continue;
+        const S* q = st + slot[j];
+        const double area = -re(q[5 * cap]) * out[j];
+        d_mass += q[0 * cap] * area;
+        d_mx += q[1 * cap] * area;
+        d_my += q[2 * cap] * area;
+        if (DIM == 3) d_mz += q[3 * cap] * area;
+        d_e += q[4 * cap] * area;
     }
     // division by the volume stays a division by S (dual / dual rounds its dual part
     // differently from dual / double, util/dual.h:169-180)
-    const S vol = S(g.volume[c]);
     M::store(A.dudt[0], c, d_mass / vol);
     M::store(A.dudt[1], c, d_mx / vol);
     M::store(A.dudt[2], c, d_my / vol);

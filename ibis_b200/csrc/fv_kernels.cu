@@ -12,6 +12,20 @@
 
 #include "context.h"
 
+// tuning knobs (compile-time; tools/build_variants.sh builds alternatives for sweeps)
+#ifndef IBIS_G_BLOCK
+#define IBIS_G_BLOCK 256     // threads per block of pass G
+#endif
+#ifndef IBIS_G_MINB
+#define IBIS_G_MINB 2        // min resident blocks per SM of pass G (register cap)
+#endif
+#ifndef IBIS_F_MAXT
+#define IBIS_F_MAXT 256      // max threads per block of pass F (>= tile size)
+#endif
+#ifndef IBIS_F_MINB
+#define IBIS_F_MINB 2        // min resident blocks per SM of pass F (register cap)
+#endif
+
 namespace ib {
 
 #define CUDA_CHECK_LAUNCH(c)                                                             \
@@ -65,28 +79,38 @@ __global__ void __launch_bounds__(128) k_bc(const FvArgs<S> A, int phase) {
 
 __global__ void __launch_bounds__(256) k_wls_r(const GridDev g, double* r_out) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c < g.n_cells) wls_r_body(g, r_out, c);
+    if (c < g.n_grad) wls_r_body(g, r_out, c);
 }
 
 template <int DIM, int NV, int NF, typename S>
-__global__ void __launch_bounds__(256) k_grad_limit(const FvArgs<S> A, const GradVars<S, NV> V,
+__global__ void __launch_bounds__(IBIS_G_BLOCK, IBIS_G_MINB) k_grad_limit(const FvArgs<S> A, const GradVars<S, NV> V,
                                                      const int do_limit) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c < A.g.n_grad) grad_limit_body<DIM, NV, NF>(A, V, c, do_limit != 0);
 }
 
-// pass F, tiled: blockDim.x == A.g.tile; dynamic shared memory = tile_cap * (5 * sizeof(S) + 8)
+template <int DIM>
+__global__ void __launch_bounds__(256) k_cell_static(const GridDev g, double* w_out, double* d_out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < g.n_grad) cell_static_body<DIM>(g, w_out, d_out, c);
+}
+
+// pass F, tiled: blockDim.x == A.g.tile; dynamic shared memory = 12 * tile_cap * sizeof(S)
 template <int DIM, int FLUX, bool O2, typename S>
-__global__ void __launch_bounds__(256, 2) k_residual_tile(const FvArgs<S> A) {
+__global__ void __launch_bounds__(IBIS_F_MAXT, IBIS_F_MINB) k_residual_tile(const FvArgs<S> A) {
     extern __shared__ double smem[];
-    S* sm = reinterpret_cast<S*>(smem);
-    double* sm_area = smem + (size_t)5 * A.g.tile_cap * (sizeof(S) / sizeof(double));
+    S* st = reinterpret_cast<S*>(smem);
     const int tile = blockIdx.x;
-    const int n = tile_num_slots(A.g, tile);
-    for (int s = threadIdx.x; s < n; s += blockDim.x) tile_face_body<DIM, FLUX, O2>(A, tile, s, sm, sm_area);
-    __syncthreads();
     const int c = tile * A.g.tile + threadIdx.x;
-    if (c < A.g.n_owned) tile_cell_body<DIM>(A, c, sm, sm_area);
+    const bool has_cell = c < A.g.n_owned;
+    if (has_cell) tile_recon_own_body<DIM, O2>(A, c, st);
+    for (int e = A.g.out_off[tile] + threadIdx.x; e < A.g.out_off[tile + 1]; e += blockDim.x)
+        tile_recon_outside_body<DIM, O2>(A, e, st);
+    __syncthreads();
+    const int n = tile_num_slots(A.g, tile);
+    for (int s = threadIdx.x; s < n; s += blockDim.x) tile_flux_body<DIM, FLUX>(A, tile, s, st);
+    __syncthreads();
+    if (has_cell) tile_cell_body<DIM>(A, c, st);
 }
 
 template <int DIM, int FLUX, bool O2, typename S>
@@ -163,18 +187,26 @@ template void launch_bc<double>(ibis_b200_ctx*, const FvArgs<double>&, int);
 template void launch_bc<dual>(ibis_b200_ctx*, const FvArgs<dual>&, int);
 
 void launch_wls_r(ibis_b200_ctx* c, double* r_out) {
-    k_wls_r<<<nblocks(c->g.n_cells, 256), 256, 0, c->stream>>>(c->g, r_out);
+    if (c->g.n_grad == 0) return;
+    k_wls_r<<<nblocks(c->g.n_grad, 256), 256, 0, c->stream>>>(c->g, r_out);
+    CUDA_CHECK_LAUNCH(c);
+}
+
+void launch_cell_static(ibis_b200_ctx* c, double* w_out, double* d_out) {
+    if (c->g.n_grad == 0) return;
+    if (c->g.dim == 3) k_cell_static<3><<<nblocks(c->g.n_grad, 256), 256, 0, c->stream>>>(c->g, w_out, d_out);
+    else k_cell_static<2><<<nblocks(c->g.n_grad, 256), 256, 0, c->stream>>>(c->g, w_out, d_out);
     CUDA_CHECK_LAUNCH(c);
 }
 
 template <int DIM, int NV, typename S>
 static void launch_grad_limit_nf(ibis_b200_ctx* c, const FvArgs<S>& A, const GradVars<S, NV>& V, int do_limit) {
-    const int nb = nblocks(A.g.n_grad, 256);
+    const int nb = nblocks(A.g.n_grad, IBIS_G_BLOCK);
     switch (A.g.max_faces) {
-        case 6: k_grad_limit<DIM, NV, 6, S><<<nb, 256, 0, c->stream>>>(A, V, do_limit); break;
-        case 5: k_grad_limit<DIM, NV, 5, S><<<nb, 256, 0, c->stream>>>(A, V, do_limit); break;
-        case 4: k_grad_limit<DIM, NV, 4, S><<<nb, 256, 0, c->stream>>>(A, V, do_limit); break;
-        default: k_grad_limit<DIM, NV, 3, S><<<nb, 256, 0, c->stream>>>(A, V, do_limit); break;
+        case 6: k_grad_limit<DIM, NV, 6, S><<<nb, IBIS_G_BLOCK, 0, c->stream>>>(A, V, do_limit); break;
+        case 5: k_grad_limit<DIM, NV, 5, S><<<nb, IBIS_G_BLOCK, 0, c->stream>>>(A, V, do_limit); break;
+        case 4: k_grad_limit<DIM, NV, 4, S><<<nb, IBIS_G_BLOCK, 0, c->stream>>>(A, V, do_limit); break;
+        default: k_grad_limit<DIM, NV, 3, S><<<nb, IBIS_G_BLOCK, 0, c->stream>>>(A, V, do_limit); break;
     }
 }
 
@@ -256,7 +288,7 @@ static void launch_one(ibis_b200_ctx* c, K kernel, int grid, int bs, size_t smem
 template <typename S>
 void launch_residual(ibis_b200_ctx* c, const FvArgs<S>& A) {
     if (A.g.n_tiles == 0) return;
-    const size_t smem = (size_t)A.g.tile_cap * (5 * sizeof(S) + sizeof(double));
+    const size_t smem = (size_t)12 * A.g.tile_cap * sizeof(S);
     prof_begin(c, 1);
     if (A.g.dim == 3) {
         DISPATCH_FLUX_O2(k_residual_tile, 3, A.g.n_tiles, A.g.tile, smem)

@@ -32,7 +32,15 @@ template void launch_bc<double>(ibis_b200_ctx*, const FvArgs<double>&, int);
 template void launch_bc<dual>(ibis_b200_ctx*, const FvArgs<dual>&, int);
 
 void launch_wls_r(ibis_b200_ctx* c, double* r_out) {
-    for (int i = 0; i < c->g.n_cells; i++) wls_r_body(c->g, r_out, i);
+    for (int i = 0; i < c->g.n_grad; i++) wls_r_body(c->g, r_out, i);
+    c->launches++;
+}
+
+void launch_cell_static(ibis_b200_ctx* c, double* w_out, double* d_out) {
+    for (int i = 0; i < c->g.n_grad; i++) {
+        if (c->g.dim == 3) cell_static_body<3>(c->g, w_out, d_out, i);
+        else cell_static_body<2>(c->g, w_out, d_out, i);
+    }
     c->launches++;
 }
 
@@ -87,25 +95,26 @@ template void launch_grad_limit<dual>(ibis_b200_ctx*, const FvArgs<dual>&, bool)
 #define EMU_O2(D, F, CALL)                                                               \
     if (A.order2) { CALL(D, F, true) } else { CALL(D, F, false) }
 
-// the tiled residual: per tile, stage every interface flux once, then gather per cell
+// the tiled residual, phase by phase as the thread block runs it
 template <typename S>
 void launch_residual(ibis_b200_ctx* c, const FvArgs<S>& A) {
     const GridDev& g = A.g;
 #pragma omp parallel
     {
-        std::vector<S> sm((size_t)5 * g.tile_cap);
-        std::vector<double> sm_area(g.tile_cap);
+        std::vector<S> st((size_t)12 * g.tile_cap);
 #pragma omp for
         for (int t = 0; t < g.n_tiles; t++) {
+            const int c0 = t * g.tile, c1 = std::min(c0 + g.tile, g.n_owned);
             const int n = tile_num_slots(g, t);
-#define TILE_FACES(D, F, O) for (int s = 0; s < n; s++) tile_face_body<D, F, O>(A, t, s, sm.data(), sm_area.data());
-            EMU_FLUX_CALL(TILE_FACES)
-#undef TILE_FACES
-            for (int k = 0; k < g.tile; k++) {
-                const int cell = t * g.tile + k;
-                if (cell >= g.n_owned) break;
-                if (g.dim == 3) tile_cell_body<3>(A, cell, sm.data(), sm_area.data());
-                else tile_cell_body<2>(A, cell, sm.data(), sm_area.data());
+#define TILE_RECON(D, F, O)                                                                   \
+    for (int cell = c0; cell < c1; cell++) tile_recon_own_body<D, O>(A, cell, st.data());     \
+    for (int e = g.out_off[t]; e < g.out_off[t + 1]; e++) tile_recon_outside_body<D, O>(A, e, st.data()); \
+    for (int s = 0; s < n; s++) tile_flux_body<D, F>(A, t, s, st.data());
+            EMU_FLUX_CALL(TILE_RECON)
+#undef TILE_RECON
+            for (int cell = c0; cell < c1; cell++) {
+                if (g.dim == 3) tile_cell_body<3>(A, cell, st.data());
+                else tile_cell_body<2>(A, cell, st.data());
             }
         }
     }
