@@ -201,6 +201,7 @@ class Library:
         sig = {
             "ibis_b200_create": [C.POINTER(vp), C.POINTER(GridDesc), C.POINTER(Config), i],
             "ibis_b200_destroy": [vp], "ibis_b200_sync": [vp],
+            "ibis_b200_sizes": [vp, ip, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)],
             "ibis_b200_fs_create": [vp, i, ip], "ibis_b200_cq_create": [vp, i, ip],
             "ibis_b200_vec_create": [vp, i64, ip], "ibis_b200_free": [vp, i],
             "ibis_b200_fs_upload": [vp, i, vp, vp], "ibis_b200_fs_download": [vp, i, vp, vp],
@@ -275,6 +276,12 @@ class Context:
             self.close()
         except Exception:
             pass
+
+    def sizes(self):
+        """GridBlock::dim / num_cells / num_ghost_cells / num_interfaces as the context sees them."""
+        dim, nc, ng, nf = C.c_int(0), C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        self._ck(self.lib.ibis_b200_sizes(self.h, C.byref(dim), C.byref(nc), C.byref(ng), C.byref(nf)), "sizes")
+        return dim.value, nc.value, ng.value, nf.value
 
     def _ck(self, rc, what):
         if rc != 0:
