@@ -259,6 +259,7 @@ int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd_ref, con
     if (rc != 0) { delete c; return fail(nullptr, IBIS_B200_ECUDA, std::string("cudaStreamCreate: ") + gpu::error_string(rc)); }
 
     c->cfg = *cfg;
+    if (const char* e = getenv("IBIS_B200_ORDERED_DOT")) c->ordered_dot = e[0] == '1';
     c->bc_actions.assign(cfg->bc_actions, cfg->bc_actions + cfg->n_bc_actions);
     c->cfg.bc_actions = nullptr;
     c->dim = gd->dim;

@@ -85,6 +85,10 @@ struct ibis_b200_ctx {
 
     // optional per-kernel event timing (ibis_b200_profile_*)
     bool prof_on = false;
+    // parity knob (IBIS_B200_ORDERED_DOT=1): dot / norm2 summed in index order by one thread, the
+    // order of the reference's parallel_reduce with one OpenMP thread (tests of ill-conditioned
+    // Krylov solves); the default is the two-stage tree reduction
+    bool ordered_dot = false;
     std::vector<void*> prof_ev[2];       // event pairs (start, stop, start, stop, ...) per kind
     size_t prof_used[2] = {0, 0};
 

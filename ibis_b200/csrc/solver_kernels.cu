@@ -385,7 +385,19 @@ void launch_gather_debug(ibis_b200_ctx* c, const double* src, int ncomp, int64_t
     CUDA_CHECK_LAUNCH(c);
 }
 
+__global__ void k_dot_ordered(const double* a, const double* b, long n, double* out, int post) {
+    double acc = 0.0;
+    for (long i = 0; i < n; i++) acc += a[i] * b[i];
+    out[0] = post ? sqrt(acc) : acc;
+    if (post == 2) out[1] = 1.0 / out[0];
+}
+
 void launch_dot(ibis_b200_ctx* c, const double* a, const double* b, int64_t n, double* d_out, int post) {
+    if (c->ordered_dot && c->n_ranks <= 1) {
+        k_dot_ordered<<<1, 1, 0, c->stream>>>(a, b, n, d_out, post);
+        CUDA_CHECK_LAUNCH(c);
+        return;
+    }
     const int nb = reduction_blocks(n);
     k_dot_partial<<<nb, 256, 0, c->stream>>>(a, b, n, c->d_partials);
     CUDA_CHECK_LAUNCH(c);

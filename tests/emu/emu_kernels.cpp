@@ -281,7 +281,16 @@ void launch_gather_debug(ibis_b200_ctx* c, const double* src, int ncomp, int64_t
 
 void launch_dot(ibis_b200_ctx* c, const double* a, const double* b, int64_t n, double* out, int post) {
     double acc = 0.0;
-    for (int64_t i = 0; i < n; i++) acc += a[i] * b[i];
+    // IBIS_B200_EMU_DOT_LANES=4: another (equally valid) summation order, standing in for the
+    // device's tree reduction in tests of how sensitive a solve is to it
+    static const char* lanes_env = getenv("IBIS_B200_EMU_DOT_LANES");
+    if (lanes_env && lanes_env[0] == '4') {
+        double acc4[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int64_t i = 0; i < n; i++) acc4[i & 3] += a[i] * b[i];
+        acc = (acc4[0] + acc4[1]) + (acc4[2] + acc4[3]);
+    } else {
+        for (int64_t i = 0; i < n; i++) acc += a[i] * b[i];
+    }
     out[0] = post ? sqrt(acc) : acc;
     if (post == 2) out[1] = 1.0 / out[0];
     c->launches++;

@@ -17,7 +17,7 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 RTOL = 1e-9
 
 
-def run_solve_case(name, lib_path=None, host_lib=None, fused_step=True, exact=None):
+def run_solve_case(name, lib_path=None, host_lib=None, fused_step=True, exact=None, rtol=RTOL):
     mesh, config, g, prim0, snap = sc.build_solve_case(name)
     gold = dict(np.load(os.path.join(GOLDEN, "solve_" + name + ".npz")))
     ctx = Context(g, config, lib_path=lib_path)
@@ -37,7 +37,7 @@ def run_solve_case(name, lib_path=None, host_lib=None, fused_step=True, exact=No
         scale = vscale if k.startswith("v") else np.abs(b).max()
         err = np.abs(a - b).max() / scale
         worst = max(worst, err)
-        assert err <= RTOL, f"{name}: {k} differs by {err:.3e} relative after {rep['steps']} steps"
+        assert err <= rtol, f"{name}: {k} differs by {err:.3e} relative after {rep['steps']} steps"
         if exact:
             assert np.array_equal(a, b), f"{name}: {k} not bit-identical (max rel {err:.3e})"
     if config["solver"]["name"] == "runge_kutta":

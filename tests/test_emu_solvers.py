@@ -26,6 +26,29 @@ def test_solver_against_reference_snapshot(libs, name):
     assert rep["steps"] > 0
 
 
+def test_steady_wedge_is_order_sensitive():
+    """Why tests/test_gpu_solvers.py runs steady parity with IBIS_B200_ORDERED_DOT=1: summing the
+    dot products of GMRES in another order (4 interleaved partial sums instead of index order, both
+    correct to 1e-16) leaves the well-conditioned steady cases inside 1e-9 and moves steady_wedge2d
+    by ~1e-4.  Run in a subprocess because the emulation reads the knob once."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path[:0]=[%r, %r]\n"
+            "import solve_parity\nfrom emu_util import emu_lib, emu_host_lib\n"
+            "solve_parity.run_solve_case('steady_quad2d', lib_path=emu_lib(), host_lib=emu_host_lib())\n"
+            "try:\n"
+            "    solve_parity.run_solve_case('steady_wedge2d', lib_path=emu_lib(), host_lib=emu_host_lib())\n"
+            "    print('WEDGE_INSIDE_1E-9')\n"
+            "except AssertionError:\n"
+            "    solve_parity.run_solve_case('steady_wedge2d', lib_path=emu_lib(), host_lib=emu_host_lib(), rtol=2e-2)\n"
+            "    print('WEDGE_ORDER_SENSITIVE')\n") % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                                    os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, IBIS_B200_EMU_DOT_LANES="4")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "WEDGE_ORDER_SENSITIVE" in r.stdout
+
+
 @pytest.mark.parametrize("name", ["rk_wedge2d", "rk_ffs2d", "rk_box3d"])
 def test_unfused_step_sequence_matches_fused(libs, name):
     """RungeKutta::take_step as the reference's sequence of kernels (one ABI call each)."""

@@ -20,11 +20,32 @@ def _require_cuda():
     assert torch.cuda.is_available(), "GPU tests need a CUDA device"
 
 
+# steady_wedge2d: the exact derivative of the Barth-Jespersen limiter with epsilon = 1e-25 makes the
+# JFNK matrix so ill-conditioned in the uniform region ahead of the shock that a 1e-16 change of one
+# dot product moves the GMRES iterate by 1e-4 after ONE Newton step (the reference itself does this
+# between OMP_NUM_THREADS=1 and 8; tests/test_emu_solvers.py::test_steady_wedge_is_order_sensitive).
+# Parity at 1e-9 is therefore checked with the reference's summation order (IBIS_B200_ORDERED_DOT=1:
+# dot / norm2 summed in index order, as the one-thread reference that made the fixture); the default
+# two-stage tree reduction is checked at the sensitivity the case has.
+ORDER_SENSITIVE = {"steady_wedge2d": 2e-2}
+
+
 @pytest.mark.parametrize("name", sorted(sc.SOLVE_CASES))
-def test_solver_against_reference_snapshot(name):
+def test_solver_against_reference_snapshot(name, monkeypatch):
     _require_cuda()
     inviscid_rk = name.startswith("rk_") and "viscous" not in name
+    if name.startswith("steady_"):
+        monkeypatch.setenv("IBIS_B200_ORDERED_DOT", "1")
     worst, rep = solve_parity.run_solve_case(name, exact=inviscid_rk)
+    assert rep["steps"] > 0
+
+
+@pytest.mark.parametrize("name", sorted(n for n in sc.SOLVE_CASES if n.startswith("steady_")))
+def test_steady_solver_with_tree_reductions(name, monkeypatch):
+    """The production reductions (warp shuffles, two stages): 1e-9 on the well-conditioned cases."""
+    _require_cuda()
+    monkeypatch.delenv("IBIS_B200_ORDERED_DOT", raising=False)
+    worst, rep = solve_parity.run_solve_case(name, rtol=ORDER_SENSITIVE.get(name, solve_parity.RTOL))
     assert rep["steps"] > 0
 
 
