@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""One box workload under a profiler: build the N^3 box, run `--steps` RungeKutta steps.
-Used by tools/prof.sh under ncu (never for bench numbers)."""
+"""tools/profile_step.py --n N --steps K: K ssp-rk3 steps of the bench workload (bench.py's box,
+config and field) with nothing else around them -- the command ncu wraps (tools/prof.sh)."""
 import argparse
 import os
 import sys
@@ -13,7 +13,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=128)
     ap.add_argument("--steps", type=int, default=2)
-    ap.add_argument("--dual", action="store_true")
+    ap.add_argument("--dual", action="store_true", help="one dual (JFNK) evaluation per step instead")
     args = ap.parse_args()
     import bench
     import cases
@@ -21,22 +21,22 @@ def main():
     from ibis_b200.lib import Context
     g = bench.box_grid_fast(args.n)
     prim = cases.perturbed_state(g, 3)
-    ctx = Context(g, bench.box_config())
+    ctx = Context(g, bench.box_config(), device=0)
+    tab = cfg.BUTCHER["ssp-rk3"]
     if args.dual:
-        fs, dq = ctx.fs_create(True), ctx.cq_create(True)
-        ctx.fs_upload(fs, prim, cases.dual_seed(prim))
+        fs, dudt = ctx.fs_create(dual=True), ctx.cq_create(dual=True)
+        ctx.fs_upload(fs, prim, 1e-3 * prim)
         for _ in range(args.steps):
-            ctx.compute_dudt(fs, dq, True)
-        ctx.sync()
+            ctx.compute_dudt(fs, dudt, True)
     else:
         fs, cq = ctx.fs_create(), ctx.cq_create()
         ctx.fs_upload(fs, prim)
         ctx.prim_to_cons(cq, fs)
-        tab = cfg.BUTCHER["ssp-rk3"]
         dt = sys.float_info.max
         for _ in range(args.steps):
             dt, _ = ctx.rk_step(fs, cq, tab["a"], tab["b"], 0.5, dt, 1.0)
-        ctx.sync()
+    ctx.sync()
+    print("bad cells", ctx.count_bad_cells(fs))
     ctx.close()
 
 
