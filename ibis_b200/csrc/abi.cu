@@ -121,10 +121,12 @@ FvArgs<S> make_args(ibis_b200_ctx* c, Buffer* fs, Buffer* dudt, bool allow_recon
         A.grad = reinterpret_cast<S*>(c->grad_r);
         A.lim = reinterpret_cast<S*>(c->lim_r);
         A.flux = reinterpret_cast<S*>(c->flux_r);
+        A.sides = reinterpret_cast<S*>(c->sides_r);
     } else {
         A.grad = reinterpret_cast<S*>(c->grad_d);
         A.lim = reinterpret_cast<S*>(c->lim_d);
         A.flux = reinterpret_cast<S*>(c->flux_d);
+        A.sides = reinterpret_cast<S*>(c->sides_d);
     }
     {   // the five reconstructed variables of pass F with their gradient / limiter arrays
         const int src[5] = {F_RHO, (c->cfg.thermo_interpolator == THERMO_RHO_P) ? F_P
@@ -158,9 +160,22 @@ FvArgs<S> make_args(ibis_b200_ctx* c, Buffer* fs, Buffer* dudt, bool allow_recon
 }
 
 // lazily allocated FiniteVolume temporaries for one scalar type
+// second-order inviscid evaluations go through the sides path (fv_bodies.h)
+bool sides_path(const ibis_b200_ctx* c) {
+    return c->use_sides && c->cfg.reconstruction_order == 2 && !c->cfg.viscous;
+}
+
 template <typename S>
-int ensure_fv_temporaries(ibis_b200_ctx* c) {
-    const bool need_grad = c->cfg.reconstruction_order > 1 || c->cfg.viscous;
+int ensure_fv_temporaries(ibis_b200_ctx* c, bool want_grad = false) {
+    const bool need_grad = want_grad || c->cfg.viscous || (c->cfg.reconstruction_order > 1 && !sides_path(c));
+    if (sides_path(c)) {
+        S** sides = (sizeof(S) == 8) ? reinterpret_cast<S**>(&c->sides_r) : reinterpret_cast<S**>(&c->sides_d);
+        if (!*sides) {
+            int rc = dev_alloc_zero<S>(c, (int64_t)frec<S>::stride * std::max<int64_t>(c->n_faces, 1), sides);
+            if (rc) return fail(c, rc, "out of device memory (interface records)");
+            launch_frec_geom<S>(c, *sides);
+        }
+    }
     S** grad = (sizeof(S) == 8) ? reinterpret_cast<S**>(&c->grad_r) : reinterpret_cast<S**>(&c->grad_d);
     S** lim = (sizeof(S) == 8) ? reinterpret_cast<S**>(&c->lim_r) : reinterpret_cast<S**>(&c->lim_d);
     S** flux = (sizeof(S) == 8) ? reinterpret_cast<S**>(&c->flux_r) : reinterpret_cast<S**>(&c->flux_d);
@@ -192,6 +207,13 @@ int compute_dudt_impl(ibis_b200_ctx* c, Buffer* fs, Buffer* dudt, bool allow_rec
     rc = comm::halo_exchange<S>(c, A.fs);
     if (rc) return rc;
     launch_bc(c, A, IBIS_B200_PHASE_PRE_RECONSTRUCTION);
+    if (sizeof(S) == sizeof(double)) c->last_fs = (int)(fs - c->bufs.data());
+    if (A.order2 && sides_path(c)) {
+        launch_grad_sides(c, A);
+        launch_flux_tile(c, A);
+        if (!c->last_error.empty()) return IBIS_B200_ECUDA;
+        return 0;
+    }
     if (A.order2) launch_grad_limit(c, A, false);
     if (A.viscous) {
         launch_face_flux(c, A);
@@ -260,6 +282,7 @@ int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd_ref, con
 
     c->cfg = *cfg;
     if (const char* e = getenv("IBIS_B200_ORDERED_DOT")) c->ordered_dot = e[0] == '1';
+    if (const char* e = getenv("IBIS_B200_SIDES")) c->use_sides = e[0] != '0';
     c->bc_actions.assign(cfg->bc_actions, cfg->bc_actions + cfg->n_bc_actions);
     c->cfg.bc_actions = nullptr;
     c->dim = gd->dim;
@@ -270,7 +293,7 @@ int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd_ref, con
     c->n_ghost = gd->n_ghost;
     c->n_total = n_total;
     c->n_faces = gd->n_faces;
-    c->cstride = pad_to(std::max<int64_t>(n_total, 1), 32);
+    c->cstride = pad_to(std::max<int64_t>(n_total, 1), 256);   // whole blocks of pass G' stay in bounds
     c->fstride = pad_to(std::max<int64_t>(gd->n_faces, 1), 32);
     const int64_t cs = c->cstride, fs = c->fstride;
 
@@ -428,7 +451,7 @@ int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd_ref, con
                 }
             cap = std::max(cap, nh + (foreign_off[b + 1] - foreign_off[b]));
         }
-        if (too_many || cap >= 0x7FFF || (size_t)cap * (12 * 16) > 220 * 1024) {
+        if (too_many || cap >= 0x7FFF || (size_t)cap * frec<dual>::bytes > 220 * 1024) {
             ibis_b200_destroy(c);
             return fail(nullptr, IBIS_B200_EINVAL, "tile has too many interfaces for shared memory");
         }
@@ -774,7 +797,19 @@ int ibis_b200_l2_norms(ibis_b200_ctx* c, int cq, double out[6]) {
 }
 
 int ibis_b200_debug_gradients(ibis_b200_ctx* c, int var, double* grad, double* limiter) {
-    if (var < 0 || var >= NVARS || !c->grad_r) return fail(c, IBIS_B200_EINVAL, "no gradients available");
+    if (var < 0 || var >= NVARS) return fail(c, IBIS_B200_EINVAL, "no gradients available");
+    if (sides_path(c)) {
+        // the sides path keeps gradients and limiters in registers: evaluate them again, from the
+        // FlowStates of the last real evaluation (ghost rows still hold its boundary fill), with the
+        // gradient kernel of the gather path
+        Buffer* F = get_buf(c, c->last_fs, BUF_FS);
+        if (!F || F->is_dual) return fail(c, IBIS_B200_EINVAL, "no gradients available");
+        int rc0 = ensure_fv_temporaries<double>(c, true);
+        if (rc0) return rc0;
+        FvArgs<double> A = make_args<double>(c, F, nullptr, true);
+        launch_grad_limit(c, A, false);
+    }
+    if (!c->grad_r) return fail(c, IBIS_B200_EINVAL, "no gradients available");
     int rc = ensure_stage(c, 3 * c->n_cells);
     if (rc) return rc;
     if (grad) {

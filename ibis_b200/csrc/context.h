@@ -66,6 +66,11 @@ struct ibis_b200_ctx {
     ib::dual* flux_d = nullptr;
     double* face_T = nullptr;
     double* face_rho = nullptr;
+    // interface-side records of the sides path (fv_bodies.h), real and dual
+    double* sides_r = nullptr;
+    ib::dual* sides_d = nullptr;
+    bool use_sides = false;              // IBIS_B200_SIDES=1: second order through the interface-record path
+    int last_fs = 0;                     // FlowStates handle of the last real evaluation (debug_gradients)
 
     // reductions
     double* d_partials = nullptr;        // [n_blocks * 8]
@@ -108,7 +113,13 @@ void launch_cell_static(ibis_b200_ctx* c, double* w_out, double* d_out);   // cf
 template <typename S>
 void launch_grad_limit(ibis_b200_ctx* c, const FvArgs<S>& A, bool viscous_pass);
 template <typename S>
-void launch_residual(ibis_b200_ctx* c, const FvArgs<S>& A);        // fused inviscid path
+void launch_residual(ibis_b200_ctx* c, const FvArgs<S>& A);        // fused inviscid path (order 1)
+template <typename S>
+void launch_grad_sides(ibis_b200_ctx* c, const FvArgs<S>& A);      // sides path, pass G'
+template <typename S>
+void launch_flux_tile(ibis_b200_ctx* c, const FvArgs<S>& A);       // sides path, pass F'
+template <typename S>
+void launch_frec_geom(ibis_b200_ctx* c, S* sides);                 // static part of the interface records
 template <typename S>
 void launch_face_flux(ibis_b200_ctx* c, const FvArgs<S>& A);       // general path
 template <typename S>

@@ -12,6 +12,15 @@
 namespace ib {
 
 constexpr int MAXF = 6;       // faces per cell: hex 6, wedge/pyramid 5, tet/quad 4, tri 3
+// One record per interface in the sides array: [left rho p T vx vy vz | right ... | nx ny nz t1x t1y
+// t1z t2x t2y t2z area]: 12 scalars of type S written by pass G' every evaluation + the static
+// frame as 10 doubles, contiguous so that pass F' fetches an interface with one bulk copy
+// (176 bytes for double, 272 for dual; both multiples of 16).
+template <typename S>
+struct frec {
+    static constexpr int bytes = 12 * (int)sizeof(S) + 80;
+    static constexpr int stride = bytes / (int)sizeof(S);       // in units of S: 22 / 17
+};
 constexpr int NVARS = 6;      // gradient slots: rho, thermo-2, vx, vy, vz, T(viscous)
 enum { V_RHO = 0, V_TH2 = 1, V_VX = 2, V_VY = 3, V_VZ = 4, V_TVISC = 5 };
 enum { F_RHO = 0, F_P = 1, F_T = 2, F_E = 3, F_VX = 4, F_VY = 5, F_VZ = 6 };
@@ -107,6 +116,7 @@ struct FvArgs {
     S* grad;           // [(var*3 + comp)*cstride + cell]
     S* lim;            // [var*cstride + cell]
     S* flux;           // general path: [comp*fstride + face]
+    S* sides;          // sides path: [(face*2 + side)*6 + k], k = rho p T vx vy vz, side 0 = left
     double* face_T;    // face_fs of the viscous path (finite_volume.h:128), real parts
     double* face_rho;
     Recon<S> rc;
@@ -310,6 +320,74 @@ IBIS_HD void cell_static_body(const GridDev& g, double* w_out, double* d_out, in
     }
 }
 
+// Barth-Jespersen limiters of one cell from its gradients and neighbour extrema
+// (finite_volume/limiter.cpp:41-60).  Generic form: the reference's loop, one division per face.
+template <int DIM, int NV, int NF, typename S>
+IBIS_HD void bj_limiters(const GridDev& g, int c, double eps, const S* ui, const S* gx, const S* gy, const S* gz,
+                         const S* umin, const S* umax, S* phi) {
+    const long cs = g.cstride;
+#pragma unroll
+    for (int v = 0; v < NV; v++) phi[v] = S(1.0);
+#pragma unroll
+    for (int j = 0; j < NF; j++) {
+        // absent slot: zero offsets -> delta_2 = 0 -> sgn = 0 -> no constraint
+        const double dx = g.cf_d[(j * 3 + 0) * cs + c];
+        const double dy = g.cf_d[(j * 3 + 1) * cs + c];
+        const double dz = g.cf_d[(j * 3 + 2) * cs + c];
+#pragma unroll
+        for (int v = 0; v < NV; v++) {
+            S delta_2 = gx[v] * dx + gy[v] * dy + gz[v] * dz;
+            const int sgn = (re(delta_2) > 0.0) - (re(delta_2) < 0.0);
+            delta_2 = (double)sgn * (abs_(delta_2) + eps);
+            if (sgn > 0) {
+                phi[v] = min_(phi[v], (umax[v] - ui[v]) / delta_2);
+            } else if (sgn < 0) {
+                phi[v] = min_(phi[v], (umin[v] - ui[v]) / delta_2);
+            }
+        }
+    }
+}
+
+// Real numbers: the same limiter with TWO divisions per variable instead of one per face.
+// phi = min(1, min_{j: d_j > 0} (Umax - Ui) / (|d_j| + eps), min_{j: d_j < 0} (Umin - Ui) / -(|d_j| + eps)).
+// IEEE division is correctly rounded, hence monotonic: for a fixed numerator a >= 0 the smallest
+// quotient fl(a / m_j) is fl(a / max_j m_j), bit for bit, and fl((-a) / (-m)) = fl(a / m).  So the
+// minimum over the faces of one sign is the single quotient by the largest |delta_2| + eps of that
+// sign -- the same double the reference's loop ends with, at a third of the division count.
+template <int DIM, int NV, int NF>
+IBIS_HD void bj_limiters(const GridDev& g, int c, double eps, const double* ui, const double* gx, const double* gy,
+                         const double* gz, const double* umin, const double* umax, double* phi) {
+    const long cs = g.cstride;
+    // x -> |x| + eps is increasing in |x|, so the largest |delta_2| + eps among the faces of one
+    // sign belongs to the largest (most negative) delta_2 itself: track the signed extrema only.
+    // An absent ELL slot has zero offsets, delta_2 = 0, and changes neither extremum's sign.
+    double dmax[NV], dmin[NV];
+#pragma unroll
+    for (int v = 0; v < NV; v++) {
+        dmax[v] = 0.0;
+        dmin[v] = 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < NF; j++) {
+        const double dx = g.cf_d[(j * 3 + 0) * cs + c];
+        const double dy = g.cf_d[(j * 3 + 1) * cs + c];
+        const double dz = g.cf_d[(j * 3 + 2) * cs + c];
+#pragma unroll
+        for (int v = 0; v < NV; v++) {
+            const double delta_2 = gx[v] * dx + gy[v] * dy + gz[v] * dz;
+            dmax[v] = dmax[v] < delta_2 ? delta_2 : dmax[v];
+            dmin[v] = delta_2 < dmin[v] ? delta_2 : dmin[v];
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < NV; v++) {
+        double p = 1.0;
+        if (dmax[v] > 0.0) p = min_(p, (umax[v] - ui[v]) / (dmax[v] + eps));
+        if (dmin[v] < 0.0) p = min_(p, (umin[v] - ui[v]) / -(-dmin[v] + eps));
+        phi[v] = p;
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // pass G: WLS gradients (grid/gradient.h:66-116) of NV variables and their Barth-Jespersen
 // limiters (finite_volume/limiter.cpp:24-63) for one cell, fused, from the static weights and
@@ -369,26 +447,7 @@ IBIS_HD void grad_limit_body(const FvArgs<S>& A, const GradVars<S, NV>& V, int c
     if (!do_limit) return;
 
     S phi[NV];
-#pragma unroll
-    for (int v = 0; v < NV; v++) phi[v] = S(1.0);
-#pragma unroll
-    for (int j = 0; j < NF; j++) {
-        // absent slot: zero offsets -> delta_2 = 0 -> sgn = 0 -> no constraint
-        const double dx = g.cf_d[(j * 3 + 0) * cs + c];
-        const double dy = g.cf_d[(j * 3 + 1) * cs + c];
-        const double dz = g.cf_d[(j * 3 + 2) * cs + c];
-#pragma unroll
-        for (int v = 0; v < NV; v++) {
-            S delta_2 = gx[v] * dx + gy[v] * dy + gz[v] * dz;
-            const int sgn = (re(delta_2) > 0.0) - (re(delta_2) < 0.0);
-            delta_2 = (double)sgn * (abs_(delta_2) + A.eps);
-            if (sgn > 0) {
-                phi[v] = min_(phi[v], (umax[v] - ui[v]) / delta_2);
-            } else if (sgn < 0) {
-                phi[v] = min_(phi[v], (umin[v] - ui[v]) / delta_2);
-            }
-        }
-    }
+    bj_limiters<DIM, NV, NF>(g, c, A.eps, ui, gx, gy, gz, umin, umax, phi);
 #pragma unroll
     for (int v = 0; v < NV; v++) M::store(V.lim[v], c, phi[v]);
 }
@@ -810,31 +869,37 @@ IBIS_HD void tile_flux_body(const FvArgs<S>& A, int tile, int slot, S* st) {
 }
 
 // phase 3
-template <int DIM, typename S>
-IBIS_HD void tile_cell_body(const FvArgs<S>& A, int c, const S* st) {
-    typedef mem<S> M;
-    const GridDev& g = A.g;
-    const long cs = g.cstride;
-    const int cap = g.tile_cap;
+// what phase 3 needs of a cell besides the staged fluxes; loaded ahead of the flux phase
+struct CellFaces {
     int slot[MAXF];
     double out[MAXF];
+    double vol;
+};
+IBIS_HD void tile_cell_load(const GridDev& g, int c, CellFaces& F) {
+    const long cs = g.cstride;
 #pragma unroll
     for (int j = 0; j < MAXF; j++) {
-        slot[j] = g.cf_slot[j * cs + c];
-        out[j] = (double)g.cf_out[j * cs + c];
+        F.slot[j] = g.cf_slot[j * cs + c];
+        F.out[j] = (double)g.cf_out[j * cs + c];
     }
-    const S vol = S(g.volume[c]);
+    F.vol = g.volume[c];
+}
+// st[slot * ss + k * ks]: flux component k (5 = area) of the tile's interface `slot`
+template <int DIM, typename S>
+IBIS_HD void tile_cell_sum(const FvArgs<S>& A, int c, const CellFaces& F, const S* st, long ss, long ks) {
+    typedef mem<S> M;
+    const S vol = S(F.vol);
     S d_mass = S(0.0), d_mx = S(0.0), d_my = S(0.0), d_mz = S(0.0), d_e = S(0.0);
 #pragma unroll
     for (int j = 0; j < MAXF; j++) {
-        if (slot[j] == 0xFFFF) continue;
-        const S* q = st + slot[j];
-        const double area = -re(q[5 * cap]) * out[j];
-        d_mass += q[0 * cap] * area;
-        d_mx += q[1 * cap] * area;
-        d_my += q[2 * cap] * area;
-        if (DIM == 3) d_mz += q[3 * cap] * area;
-        d_e += q[4 * cap] * area;
+        if (F.slot[j] == 0xFFFF) continue;
+        const S* q = st + F.slot[j] * ss;
+        const double area = -re(q[5 * ks]) * F.out[j];
+        d_mass += q[0 * ks] * area;
+        d_mx += q[1 * ks] * area;
+        d_my += q[2 * ks] * area;
+        if (DIM == 3) d_mz += q[3 * ks] * area;
+        d_e += q[4 * ks] * area;
     }
     // division by the volume stays a division by S (dual / dual rounds its dual part
     // differently from dual / double, util/dual.h:169-180)
@@ -843,6 +908,272 @@ IBIS_HD void tile_cell_body(const FvArgs<S>& A, int c, const S* st) {
     M::store(A.dudt[2], c, d_my / vol);
     if (DIM == 3) M::store(A.dudt[3], c, d_mz / vol);
     M::store(A.dudt[4], c, d_e / vol);
+}
+template <int DIM, typename S>
+IBIS_HD void tile_cell_body(const FvArgs<S>& A, int c, const S* st, long ss, long ks) {
+    CellFaces F;
+    tile_cell_load(A.g, c, F);
+    tile_cell_sum<DIM>(A, c, F, st, ss, ks);
+}
+
+// ---------------------------------------------------------------------------------------
+// The "sides" path of the inviscid second-order residual (the default on the GPU):
+//   pass G'  grad_sides_body   one thread per cell: WLS gradients (grid/gradient.h:66-116),
+//            Barth-Jespersen limiters (limiter.cpp:24-63) AND the MUSCL extrapolation of the cell to
+//            each of its interfaces with the thermodynamic closure (convective_flux.cpp:243-420,
+//            gas_model.h:91-117), written as one 48-byte record (rho p T vx vy vz) per interface
+//            side.  The limiter's delta_2 = grad . (x_f - x_c) IS the reconstruction increment, so
+//            it is evaluated once.  Gradients and limiters never go to HBM.
+//   pass F'  flux_from_record + tile_cell_sum   one thread per interface of a tile: rotate,
+//            flux calculator, rotate back, staged in shared memory; then one thread per cell:
+//            flux_surface_integral (finite_volume.cpp:221-256).  No gathers of cell data at all.
+// Same per-face arithmetic and in-cell summation order as the reference, hence the same bits.
+// ---------------------------------------------------------------------------------------
+
+// Barth-Jespersen limiter of one variable from the face increments delta[j] (0 for an absent
+// slot): the reference's loop, one division per face (limiter.cpp:41-60).
+template <int NF, typename S>
+IBIS_HD S bj_phi(const S* delta, const S& ui, const S& umin, const S& umax, double eps) {
+    S phi = S(1.0);
+#pragma unroll
+    for (int j = 0; j < NF; j++) {
+        S delta_2 = delta[j];
+        const int sgn = (re(delta_2) > 0.0) - (re(delta_2) < 0.0);
+        delta_2 = (double)sgn * (abs_(delta_2) + eps);
+        if (sgn > 0) {
+            phi = min_(phi, (umax - ui) / delta_2);
+        } else if (sgn < 0) {
+            phi = min_(phi, (umin - ui) / delta_2);
+        }
+    }
+    return phi;
+}
+// Real numbers: two divisions instead of NF, bit-identical (see bj_limiters above).
+template <int NF>
+IBIS_HD double bj_phi(const double* delta, const double& ui, const double& umin, const double& umax, double eps) {
+    double dmax = 0.0, dmin = 0.0;
+#pragma unroll
+    for (int j = 0; j < NF; j++) {
+        dmax = dmax < delta[j] ? delta[j] : dmax;
+        dmin = delta[j] < dmin ? delta[j] : dmin;
+    }
+    double p = 1.0;
+    if (dmax > 0.0) p = min_(p, (umax - ui) / (dmax + eps));
+    if (dmin < 0.0) p = min_(p, (umin - ui) / -(-dmin + eps));
+    return p;
+}
+
+// The static per cell-face tables (WLS weights cf_w, offsets cf_d) as the kernel sees them:
+// element (j, k) of cell `idx` is base[(j*3 + k) * stride + idx].  On the device the block's slice
+// of both tables is staged in shared memory by bulk async copies (stride = block size, idx =
+// threadIdx.x); the host emulation points at the global tables (stride = cstride, idx = cell).
+template <int WSTRIDE>
+struct CellTables {
+    const double* w;
+    const double* d;
+    long stride_rt;
+    int idx;
+    IBIS_HD long stride() const { return WSTRIDE > 0 ? WSTRIDE : stride_rt; }
+    // staged tables are re-read from shared memory at every use (volatile): keeping all 36
+    // entries in registers across the five variables is what made the kernel spill
+    IBIS_HD double W(int j, int k) const {
+        if (WSTRIDE > 0) return *static_cast<const volatile double*>(w + (j * 3 + k) * WSTRIDE + idx);
+        return w[(j * 3 + k) * stride_rt + idx];
+    }
+    IBIS_HD double D(int j, int k) const {
+        if (WSTRIDE > 0) return *static_cast<const volatile double*>(d + (j * 3 + k) * WSTRIDE + idx);
+        return d[(j * 3 + k) * stride_rt + idx];
+    }
+};
+
+// everything pass G' gathers for one cell, issued before the tables are waited for
+template <int NF, typename S>
+struct CellGather {
+    int nbr[NF];
+    long rec[NF];                 // record of this cell's side of interface j, -1 if the slot is absent
+    int other[NF];                // offset from rec[j] to the record of the far side
+    bool ghost[NF];
+    S ui[5], un[5][NF];
+};
+
+template <int DIM, int NF, typename S>
+IBIS_HD void grad_sides_gather(const FvArgs<S>& A, int c, CellGather<NF, S>& G) {
+    typedef mem<S> M;
+    const GridDev& g = A.g;
+    const long cs = g.cstride;
+#pragma unroll
+    for (int j = 0; j < NF; j++) {
+        const int f = g.cf_face[j * cs + c];
+        const int nb = g.cf_nbr[j * cs + c];
+        const int side = g.cf_out[j * cs + c] > 0 ? 0 : 1;     // outsign +1: this cell is the left cell
+        G.nbr[j] = f < 0 ? c : nb;                             // absent slot: contributes w * (u_i - u_i) = 0
+#ifdef IBIS_EXPERIMENT_COALESCED_SIDES   // timing experiment only (wrong addresses, coalesced stores)
+        G.rec[j] = f < 0 ? -1 : ((long)(c / 32) * 32 * 6 * MAXF + (long)j * 6 * 32 + (c % 32) * 2);
+#else
+        G.rec[j] = f < 0 ? -1 : (long)f * frec<S>::stride + side * 6;
+#endif
+        G.other[j] = side ? -6 : 6;
+        G.ghost[j] = f >= 0 && nb >= g.n_cells;
+    }
+#pragma unroll
+    for (int v = 0; v < 5; v++) {
+        G.ui[v] = M::ldg(A.rc.val[v], c);
+        if (DIM == 2 && v == 4) continue;                      // vz: no gradient in 2-D
+#pragma unroll
+        for (int j = 0; j < NF; j++) G.un[v][j] = M::ldg(A.rc.val[v], G.nbr[j]);
+    }
+}
+
+// one variable of one cell: gradient, limiter, extrapolation to the NF interfaces -> r[j]
+template <int DIM, int NF, int WSTRIDE, typename S>
+IBIS_HD void var_to_faces(const S& ui, const S* un, const CellTables<WSTRIDE>& T, double eps, bool limit, S* r) {
+    S gx = S(0.0), gy = S(0.0), gz = S(0.0), umin = ui, umax = ui;
+#pragma unroll
+    for (int j = 0; j < NF; j++) {
+        const S diff_u = un[j] - ui;                           // gradient.h:110-113
+        gx += T.W(j, 0) * diff_u;
+        gy += T.W(j, 1) * diff_u;
+        gz += ((DIM == 3) ? T.W(j, 2) : 0.0) * diff_u;
+        umin = min_(umin, un[j]);                              // limiter.cpp:37-38
+        umax = max_(umax, un[j]);
+    }
+    S delta[NF];
+#pragma unroll
+    for (int j = 0; j < NF; j++) delta[j] = gx * T.D(j, 0) + gy * T.D(j, 1) + gz * T.D(j, 2);
+    const S phi = limit ? bj_phi<NF>(delta, ui, umin, umax, eps) : S(1.0);
+#pragma unroll
+    for (int j = 0; j < NF; j++) r[j] = ui + phi * delta[j];   // linear_interpolate, convective_flux.cpp:243-255
+}
+
+template <int DIM, int NF, int WSTRIDE, typename S>
+IBIS_HD void grad_sides_compute(const FvArgs<S>& A, const CellGather<NF, S>& G, const CellTables<WSTRIDE>& T) {
+    typedef mem<S> M;
+    const bool limit = A.limiter_on != 0;
+    S r0[NF], r1[NF];
+    var_to_faces<DIM, NF>(G.ui[0], G.un[0], T, A.eps, limit, r0);
+    var_to_faces<DIM, NF>(G.ui[1], G.un[1], T, A.eps, limit, r1);
+    S Tj[NF];
+#pragma unroll
+    for (int j = 0; j < NF; j++) {
+        S rho = r0[j], p = S(0.0), e = S(0.0);
+        Tj[j] = S(0.0);
+        if (A.thermo == THERMO_RHO_P) p = r1[j];
+        else if (A.thermo == THERMO_RHO_T) Tj[j] = r1[j];
+        else e = r1[j];
+        thermo_close(A.thermo, A.gas, rho, p, Tj[j], e);
+        if (G.rec[j] >= 0) M::store2(A.sides, G.rec[j], rho, p);
+    }
+    var_to_faces<DIM, NF>(G.ui[2], G.un[2], T, A.eps, limit, r0);
+#pragma unroll
+    for (int j = 0; j < NF; j++)
+#ifdef IBIS_EXPERIMENT_COALESCED_SIDES
+        if (G.rec[j] >= 0) M::store2(A.sides, G.rec[j] + 64, Tj[j], r0[j]);
+#else
+        if (G.rec[j] >= 0) M::store2(A.sides, G.rec[j] + 2, Tj[j], r0[j]);
+#endif
+    var_to_faces<DIM, NF>(G.ui[3], G.un[3], T, A.eps, limit, r0);
+    if (DIM == 3) {
+        var_to_faces<DIM, NF>(G.ui[4], G.un[4], T, A.eps, limit, r1);
+    } else {
+        // 2-D: vz has no gradient (convective_flux.cpp:206-208) and a unit limiter: value copied
+#pragma unroll
+        for (int j = 0; j < NF; j++) r1[j] = G.ui[4];
+    }
+#pragma unroll
+    for (int j = 0; j < NF; j++)
+#ifdef IBIS_EXPERIMENT_COALESCED_SIDES
+        if (G.rec[j] >= 0) M::store2(A.sides, G.rec[j] + 128, r0[j], r1[j]);
+#else
+        if (G.rec[j] >= 0) M::store2(A.sides, G.rec[j] + 4, r0[j], r1[j]);
+#endif
+    // the far side of a boundary interface is the ghost cell itself: zero gradient, unit limiter
+    // (convective_flux.cpp:281-300), i.e. its values, closed thermodynamically like any other side
+#pragma unroll
+    for (int j = 0; j < NF; j++) {
+        if (!G.ghost[j]) continue;
+        const int nb = G.nbr[j];
+        S rho = M::load(A.rc.val[0], nb), p = S(0.0), Tg = S(0.0), e = S(0.0);
+        const S th2 = M::load(A.rc.val[1], nb);
+        if (A.thermo == THERMO_RHO_P) p = th2;
+        else if (A.thermo == THERMO_RHO_T) Tg = th2;
+        else e = th2;
+        thermo_close(A.thermo, A.gas, rho, p, Tg, e);
+        const long ro = G.rec[j] + G.other[j];
+        M::store2(A.sides, ro, rho, p);
+        M::store2(A.sides, ro + 2, Tg, M::load(A.rc.val[2], nb));
+        M::store2(A.sides, ro + 4, M::load(A.rc.val[3], nb), M::load(A.rc.val[4], nb));
+    }
+}
+
+// host emulation / reference form: one call per cell straight from the global tables
+template <int DIM, int NF, typename S>
+IBIS_HD void grad_sides_body(const FvArgs<S>& A, int c) {
+    CellGather<NF, S> G;
+    grad_sides_gather<DIM, NF>(A, c, G);
+    CellTables<0> T;
+    T.w = A.g.cf_w;
+    T.d = A.g.cf_d;
+    T.stride_rt = A.g.cstride;
+    T.idx = c;
+    grad_sides_compute<DIM, NF, 0>(A, G, T);
+}
+
+// static part of the interface records (setup): the frame and area of interface f
+template <typename S>
+IBIS_HD void frec_geom_body(const GridDev& g, S* sides, int f) {
+    double* q = reinterpret_cast<double*>(sides + (long)f * frec<S>::stride + 12);
+    const long fs_ = g.fstride;
+    for (int d = 0; d < 3; d++) {
+        q[d] = g.f_n[d * fs_ + f];
+        q[3 + d] = g.f_t1[d * fs_ + f];
+        q[6 + d] = g.f_t2[d * fs_ + f];
+    }
+    q[9] = g.f_area[f];
+}
+
+// pass F', one interface: rec = its record (shared memory on the device, the global array in the
+// host emulation); out[k * ks], k = 0..4 <- flux in the global frame, k = 5 <- area.  out may
+// alias the left side of rec: everything is read before anything is written.
+template <int DIM, int FLUX, typename S>
+IBIS_HD void flux_from_record(const FvArgs<S>& A, const S* rec, S* out, long ks) {
+    typedef mem<S> M;
+    Side<S> L, R_;
+    M::ld2(rec, 0, L.rho, L.p);
+    M::ld2(rec, 2, L.T, L.u);
+    M::ld2(rec, 4, L.v, L.w);
+    M::ld2(rec, 6, R_.rho, R_.p);
+    M::ld2(rec, 8, R_.T, R_.u);
+    M::ld2(rec, 10, R_.v, R_.w);
+    L.e = S(0.0);
+    R_.e = S(0.0);
+    const double* gm = reinterpret_cast<const double*>(rec + 12);
+    double nx, ny, nz, t1x, t1y, t1z, t2x, t2y, t2z, area;
+    mem<double>::ld2(gm, 0, nx, ny);
+    mem<double>::ld2(gm, 2, nz, t1x);
+    mem<double>::ld2(gm, 4, t1y, t1z);
+    mem<double>::ld2(gm, 6, t2x, t2y);
+    mem<double>::ld2(gm, 8, t2z, area);
+    {
+        const S x = L.u * nx + L.v * ny + L.w * nz;           // util/vector3.cpp:142-153
+        const S y = L.u * t1x + L.v * t1y + L.w * t1z;
+        const S z = L.u * t2x + L.v * t2y + L.w * t2z;
+        L.u = x; L.v = y; L.w = z;
+    }
+    {
+        const S x = R_.u * nx + R_.v * ny + R_.w * nz;
+        const S y = R_.u * t1x + R_.v * t1y + R_.w * t1z;
+        const S z = R_.u * t2x + R_.v * t2y + R_.w * t2z;
+        R_.u = x; R_.v = y; R_.w = z;
+    }
+    Flux5<S> F = flux_calc<FLUX>(L, R_, A.gas, A.delta);
+    const S px = F.mx, py = F.my;
+    const S pz = (DIM == 3) ? F.mz : S(0.0);
+    out[0 * ks] = F.mass;                                     // convective_flux.cpp:148-164
+    out[1 * ks] = px * nx + py * t1x + pz * t2x;
+    out[2 * ks] = px * ny + py * t1y + pz * t2y;
+    out[3 * ks] = px * nz + py * t1z + pz * t2z;
+    out[4 * ks] = F.energy;
+    out[5 * ks] = S(area);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -10,6 +10,7 @@
 // served by L1/L2.  Built with --fmad=false: arithmetic is bit-for-bit the reference's.
 #include <cuda_runtime.h>
 
+#include "async_copy.h"
 #include "context.h"
 
 // tuning knobs (compile-time; tools/build_variants.sh builds alternatives for sweeps)
@@ -24,6 +25,19 @@
 #endif
 #ifndef IBIS_F_MINB
 #define IBIS_F_MINB 2        // min resident blocks per SM of pass F (register cap)
+#endif
+
+#ifndef IBIS_GS_BLOCK
+#define IBIS_GS_BLOCK 128    // threads per block of pass G' (gradients + limiters + interface sides)
+#endif
+#ifndef IBIS_GS_MINB
+#define IBIS_GS_MINB 4
+#endif
+#ifndef IBIS_F2_THREADS
+#define IBIS_F2_THREADS 256  // threads per block of pass F' (>= tile size)
+#endif
+#ifndef IBIS_F2_MINB
+#define IBIS_F2_MINB 2
 #endif
 
 namespace ib {
@@ -110,7 +124,94 @@ __global__ void __launch_bounds__(IBIS_F_MAXT, IBIS_F_MINB) k_residual_tile(cons
     const int n = tile_num_slots(A.g, tile);
     for (int s = threadIdx.x; s < n; s += blockDim.x) tile_flux_body<DIM, FLUX>(A, tile, s, st);
     __syncthreads();
-    if (has_cell) tile_cell_body<DIM>(A, c, st);
+    if (has_cell) tile_cell_body<DIM>(A, c, st, 1, A.g.tile_cap);
+}
+
+// pass G' of the sides path: one thread per cell with a face list (owned + inner halo ring).
+// The block's slice of the static tables (WLS weights, face offsets: 36 KB for hexes) arrives in
+// shared memory by bulk async copies (TMA) while the threads issue their neighbour gathers, so the
+// only registers tied up while waiting on HBM are the gathered values themselves.
+template <int DIM, int NF, typename S>
+__global__ void __launch_bounds__(IBIS_GS_BLOCK, IBIS_GS_MINB) k_grad_sides(const FvArgs<S> A) {
+    constexpr int B = IBIS_GS_BLOCK;
+    constexpr int NT = NF * 3;                                  // arrays per table
+    __shared__ __align__(128) double tab[2 * NT * B];
+    __shared__ uint64_t bar;
+    const int c0 = blockIdx.x * B;
+    const int c = c0 + threadIdx.x;
+    if (threadIdx.x == 0) {
+        ac::mbar_init(&bar, 1);
+        ac::fence_barrier_init();
+        ac::mbar_arrive_expect_tx(&bar, 2 * NT * B * (uint32_t)sizeof(double));
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * NT) {
+        const int a = threadIdx.x % NT;
+        const double* src = (threadIdx.x < NT ? A.g.cf_w : A.g.cf_d) + (long)a * A.g.cstride + c0;
+        ac::bulk_g2s(tab + threadIdx.x * B, src, B * (uint32_t)sizeof(double), &bar);
+    }
+    CellGather<NF, S> G;
+    const bool active = c < A.g.n_grad;
+    if (active) grad_sides_gather<DIM, NF>(A, c, G);
+    ac::mbar_wait(&bar, 0);
+    if (active) {
+        CellTables<B> T;
+        T.w = tab;
+        T.d = tab + NT * B;
+        T.stride_rt = B;
+        T.idx = threadIdx.x;
+        grad_sides_compute<DIM, NF, B>(A, G, T);
+    }
+}
+
+template <typename S>
+__global__ void __launch_bounds__(256) k_frec_geom(const GridDev g, S* sides) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f < g.n_faces) frec_geom_body(g, sides, f);
+}
+
+// pass F' of the sides path: blockDim.x >= A.g.tile; dynamic shared memory = tile_cap records.
+// The records of the tile's home interfaces are one contiguous range: one bulk async copy (TMA);
+// the foreign ones (homed in an earlier tile) are gathered with 16-byte cp.async.  Each flux
+// overwrites the left side of its own record; then one thread per cell sums its faces.
+template <int DIM, int FLUX, typename S>
+__global__ void __launch_bounds__(IBIS_F2_THREADS, IBIS_F2_MINB) k_flux_tile(const FvArgs<S> A) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t bar;
+    S* st = reinterpret_cast<S*>(smem_raw);
+    constexpr int RS = frec<S>::stride, RB = frec<S>::bytes;
+    const GridDev& g = A.g;
+    const int tile = blockIdx.x;
+    const int h0 = g.home0[tile], nh = g.home0[tile + 1] - h0;
+    const int fo = g.foreign_off[tile], n = nh + (g.foreign_off[tile + 1] - fo);
+    if (threadIdx.x == 0) {
+        ac::mbar_init(&bar, 1);
+        ac::fence_barrier_init();
+        if (nh > 0) {
+            ac::mbar_arrive_expect_tx(&bar, (uint32_t)nh * RB);
+            ac::bulk_g2s(st, A.sides + (long)h0 * RS, (uint32_t)nh * RB, &bar);
+        }
+    }
+    for (int s = nh + threadIdx.x; s < n; s += blockDim.x) {
+        const int f = g.foreign[fo + (s - nh)];
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(A.sides + (long)f * RS);
+        unsigned char* dst = reinterpret_cast<unsigned char*>(st + (long)s * RS);
+#pragma unroll
+        for (int q = 0; q < RB / 16; q++) ac::cp_async_16(dst + q * 16, src + q * 16);
+    }
+    const int c = tile * g.tile + threadIdx.x;
+    const bool has_cell = threadIdx.x < g.tile && c < g.n_owned;
+    CellFaces CF;
+    if (has_cell) tile_cell_load(g, c, CF);
+    ac::cp_async_wait_all();
+    __syncthreads();                       // barrier initialised; everybody's cp.async data landed
+    if (nh > 0) ac::mbar_wait(&bar, 0);
+    for (int s = threadIdx.x; s < n; s += blockDim.x) {
+        S* rec = st + (long)s * RS;
+        flux_from_record<DIM, FLUX>(A, rec, rec, 1);
+    }
+    __syncthreads();
+    if (has_cell) tile_cell_sum<DIM>(A, c, CF, st, RS, 1);
 }
 
 template <int DIM, int FLUX, bool O2, typename S>
@@ -300,6 +401,62 @@ void launch_residual(ibis_b200_ctx* c, const FvArgs<S>& A) {
 }
 template void launch_residual<double>(ibis_b200_ctx*, const FvArgs<double>&);
 template void launch_residual<dual>(ibis_b200_ctx*, const FvArgs<dual>&);
+
+template <int DIM, typename S>
+static void launch_grad_sides_nf(ibis_b200_ctx* c, const FvArgs<S>& A) {
+    const int nb = nblocks(A.g.n_grad, IBIS_GS_BLOCK);
+    switch (A.g.max_faces) {
+        case 6: k_grad_sides<DIM, 6, S><<<nb, IBIS_GS_BLOCK, 0, c->stream>>>(A); break;
+        case 5: k_grad_sides<DIM, 5, S><<<nb, IBIS_GS_BLOCK, 0, c->stream>>>(A); break;
+        case 4: k_grad_sides<DIM, 4, S><<<nb, IBIS_GS_BLOCK, 0, c->stream>>>(A); break;
+        default: k_grad_sides<DIM, 3, S><<<nb, IBIS_GS_BLOCK, 0, c->stream>>>(A); break;
+    }
+}
+
+template <typename S>
+void launch_grad_sides(ibis_b200_ctx* c, const FvArgs<S>& A) {
+    if (A.g.n_grad == 0) return;
+    prof_begin(c, 0);
+    if (A.g.dim == 3) launch_grad_sides_nf<3, S>(c, A);
+    else launch_grad_sides_nf<2, S>(c, A);
+    prof_end(c, 0);
+    CUDA_CHECK_LAUNCH(c);
+}
+template void launch_grad_sides<double>(ibis_b200_ctx*, const FvArgs<double>&);
+template void launch_grad_sides<dual>(ibis_b200_ctx*, const FvArgs<dual>&);
+
+template <int DIM, typename S>
+static void launch_flux_tile_dim(ibis_b200_ctx* c, const FvArgs<S>& A, int bs, size_t smem) {
+    switch (c->cfg.flux_calculator) {
+        case FLUX_HANEL: launch_one(c, k_flux_tile<DIM, FLUX_HANEL, S>, A.g.n_tiles, bs, smem, A); break;
+        case FLUX_AUSMDV: launch_one(c, k_flux_tile<DIM, FLUX_AUSMDV, S>, A.g.n_tiles, bs, smem, A); break;
+        case FLUX_LDFSS2: launch_one(c, k_flux_tile<DIM, FLUX_LDFSS2, S>, A.g.n_tiles, bs, smem, A); break;
+        default: launch_one(c, k_flux_tile<DIM, FLUX_RUSANOV, S>, A.g.n_tiles, bs, smem, A); break;
+    }
+}
+
+template <typename S>
+void launch_flux_tile(ibis_b200_ctx* c, const FvArgs<S>& A) {
+    if (A.g.n_tiles == 0) return;
+    const size_t smem = (size_t)A.g.tile_cap * frec<S>::bytes;
+    const int bs = A.g.tile > IBIS_F2_THREADS ? A.g.tile : IBIS_F2_THREADS;
+    prof_begin(c, 1);
+    if (A.g.dim == 3) launch_flux_tile_dim<3, S>(c, A, bs, smem);
+    else launch_flux_tile_dim<2, S>(c, A, bs, smem);
+    prof_end(c, 1);
+    CUDA_CHECK_LAUNCH(c);
+}
+template void launch_flux_tile<double>(ibis_b200_ctx*, const FvArgs<double>&);
+template void launch_flux_tile<dual>(ibis_b200_ctx*, const FvArgs<dual>&);
+
+template <typename S>
+void launch_frec_geom(ibis_b200_ctx* c, S* sides) {
+    if (c->g.n_faces == 0) return;
+    k_frec_geom<S><<<nblocks(c->g.n_faces, 256), 256, 0, c->stream>>>(c->g, sides);
+    CUDA_CHECK_LAUNCH(c);
+}
+template void launch_frec_geom<double>(ibis_b200_ctx*, double*);
+template void launch_frec_geom<dual>(ibis_b200_ctx*, dual*);
 
 template <typename S>
 void launch_face_flux(ibis_b200_ctx* c, const FvArgs<S>& A) {

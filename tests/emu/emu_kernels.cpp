@@ -113,8 +113,8 @@ void launch_residual(ibis_b200_ctx* c, const FvArgs<S>& A) {
             EMU_FLUX_CALL(TILE_RECON)
 #undef TILE_RECON
             for (int cell = c0; cell < c1; cell++) {
-                if (g.dim == 3) tile_cell_body<3>(A, cell, st.data());
-                else tile_cell_body<2>(A, cell, st.data());
+                if (g.dim == 3) tile_cell_body<3>(A, cell, st.data(), 1, g.tile_cap);
+                else tile_cell_body<2>(A, cell, st.data(), 1, g.tile_cap);
             }
         }
     }
@@ -122,6 +122,59 @@ void launch_residual(ibis_b200_ctx* c, const FvArgs<S>& A) {
 }
 template void launch_residual<double>(ibis_b200_ctx*, const FvArgs<double>&);
 template void launch_residual<dual>(ibis_b200_ctx*, const FvArgs<dual>&);
+
+template <typename S>
+void launch_grad_sides(ibis_b200_ctx* c, const FvArgs<S>& A) {
+#pragma omp parallel for
+    for (int i = 0; i < A.g.n_grad; i++) {
+#define GS(D)                                                        \
+    switch (A.g.max_faces) {                                         \
+        case 6: grad_sides_body<D, 6>(A, i); break;                  \
+        case 5: grad_sides_body<D, 5>(A, i); break;                  \
+        case 4: grad_sides_body<D, 4>(A, i); break;                  \
+        default: grad_sides_body<D, 3>(A, i); break;                 \
+    }
+        if (A.g.dim == 3) { GS(3) } else { GS(2) }
+#undef GS
+    }
+    c->launches++;
+}
+template void launch_grad_sides<double>(ibis_b200_ctx*, const FvArgs<double>&);
+template void launch_grad_sides<dual>(ibis_b200_ctx*, const FvArgs<dual>&);
+
+template <typename S>
+void launch_frec_geom(ibis_b200_ctx* c, S* sides) {
+    for (int f = 0; f < c->g.n_faces; f++) frec_geom_body(c->g, sides, f);
+    c->launches++;
+}
+template void launch_frec_geom<double>(ibis_b200_ctx*, double*);
+template void launch_frec_geom<dual>(ibis_b200_ctx*, dual*);
+
+template <typename S>
+void launch_flux_tile(ibis_b200_ctx* c, const FvArgs<S>& A) {
+    const GridDev& g = A.g;
+#pragma omp parallel
+    {
+        std::vector<S> st((size_t)6 * g.tile_cap);
+#pragma omp for
+        for (int t = 0; t < g.n_tiles; t++) {
+            const int c0 = t * g.tile, c1 = std::min(c0 + g.tile, g.n_owned);
+            const int n = tile_num_slots(g, t);
+#define TILE_FLUX(D, F, O)                                                                       \
+    for (int s = 0; s < n; s++)                                                                  \
+        flux_from_record<D, F>(A, A.sides + (long)tile_face_of_slot(g, t, s) * frec<S>::stride, st.data() + s, g.tile_cap);
+            EMU_FLUX_CALL(TILE_FLUX)
+#undef TILE_FLUX
+            for (int cell = c0; cell < c1; cell++) {
+                if (g.dim == 3) tile_cell_body<3>(A, cell, st.data(), 1, g.tile_cap);
+                else tile_cell_body<2>(A, cell, st.data(), 1, g.tile_cap);
+            }
+        }
+    }
+    c->launches++;
+}
+template void launch_flux_tile<double>(ibis_b200_ctx*, const FvArgs<double>&);
+template void launch_flux_tile<dual>(ibis_b200_ctx*, const FvArgs<dual>&);
 
 template <typename S>
 void launch_face_flux(ibis_b200_ctx* c, const FvArgs<S>& A) {

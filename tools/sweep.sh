@@ -1,10 +1,19 @@
 #!/bin/bash
-# tools/sweep.sh N tag...: bench.py --n N for each library variant (and the default library), one line each
-N=${1:-160}; shift
-for tag in default "$@"; do
-  if [ "$tag" = default ]; then unset IBIS_B200_LIB; else export IBIS_B200_LIB=ibis_b200/lib/variants/$tag/libibis_b200.so; fi
-  python bench.py --steps 4 --warmup 3 --n $N --no-cpu 2> gpurun_out/sweep_$tag.err | python -c "
-import json,sys
-d=json.loads(sys.stdin.read()); r=d['roofline']
-print('%-14s n=$N value %.3e  F %.3f ms (%.3f)  G %.3f ms  eval frac %.3f  step %.2f ms' % ('$tag', d['value'], r['avg_launch_ms'], r['frac'], r['pass_G']['avg_launch_ms'], r['evaluation']['frac'], d['ms_per_step']))" || tail -3 gpurun_out/sweep_$tag.err
+# tools/sweep.sh N "tag[:ENV=VAL,...]" ... : bench.py (no CPU arm) for each built variant library
+# (tools/build_variants.sh; tag "default" = ibis_b200/lib) and environment setting; prints one line
+# per run: pass G / pass F launch times, evaluation roofline fraction, evals/s.  Run under gpurun.
+N=$1; shift
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+for spec in "$@"; do
+  tag="${spec%%:*}"; envs=""; [[ "$spec" == *:* ]] && envs="${spec#*:}"
+  lib="ibis_b200/lib/variants/$tag/libibis_b200.so"; [ "$tag" = default ] && lib="ibis_b200/lib/libibis_b200.so"
+  out="gpurun_out/sweep_${tag}_$(echo "$envs" | tr ',=' '__').json"
+  env IBIS_B200_LIB=$lib $(echo "$envs" | tr ',' ' ') python bench.py --n $N --steps 4 --warmup 3 --no-cpu > "$out" 2> "$out.err" || { echo "$spec FAILED"; tail -3 "$out.err"; continue; }
+  python - "$out" "$spec" <<'PY'
+import json, sys
+d = json.load(open(sys.argv[1])); r = d["roofline"]
+print(f"{sys.argv[2]:40s} G {r['pass_G']['avg_launch_ms']:7.3f} ms  F {r['avg_launch_ms']:7.3f} ms  eval {100 * r['evaluation']['frac']:5.1f} %  "
+      f"value {d['value'] / 1e9:6.3f} G/s  step {d['ms_per_step']:7.2f} ms  e2e {d['e2e']['value'] / 1e9:5.2f} G/s")
+PY
 done
