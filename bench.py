@@ -13,7 +13,6 @@ east/north/top, perturbed initial field (ii).  One step = one RungeKutta::take_s
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -36,39 +35,52 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock and clock-event (throttle) reasons sampled through NVML from a thread of this
+    process every 10 ms DURING the timed region (nvidia-smi -lms starts too slowly for a region
+    of a few hundred milliseconds)."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index=0):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.sm, self.mask, self.stop_flag, self.thread, self.max_mhz = index, [], 0, False, None, None
+        self.power = []
 
     def start(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nv = pynvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:                                          # noqa: BLE001
+            self.err = str(e)
+            return
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+    def _run(self):
+        nv = self.nv
+        reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.mask |= int(reasons(self.h))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+            except Exception:                                           # noqa: BLE001
+                pass
+            time.sleep(0.01)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        self.t.join(timeout=2)
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) >= 6 and r[2 + i] == "Active" for r in self.rows)]
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        if not self.thread:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + getattr(self, "err", "?")],
+                    "samples": 0}
+        self.stop_flag = True
+        self.thread.join(timeout=2)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": [n for bit, n in self.REASONS.items() if self.mask & bit], "samples": len(self.sm),
+                "power_w_max": max(self.power) if self.power else None}
 
 
 def box_config():
@@ -88,12 +100,13 @@ def box_grid_host(n):
 
 def box_grid_fast(n, rank=0, world=1):
     """The same box (bit-identical arrays, tests/test_box_grid.py) from the closed-form C++
-    generator; with world > 1 the global box is n x n x (n * world) with lengths (1, 1, world)
-    and this rank owns the z-slab [rank * n, (rank + 1) * n) plus its two-ring halo."""
+    generator.  With world > 1 the SAME n^3 box is decomposed by cells into z-slabs (strong
+    scaling, BASELINE.json configs[4]): this rank owns the planes [n*rank/world, n*(rank+1)/world)
+    and carries its two-ring halo and exchange lists."""
     from ibis_b200.boxgrid import BoxGrid
     if world == 1:
         return BoxGrid(n)
-    return BoxGrid(n, n, n * world, lengths=(1.0, 1.0, float(world)), slab=(rank * n, (rank + 1) * n))
+    return BoxGrid(n, n, n, slab=(n * rank // world, n * (rank + 1) // world))
 
 
 def cpu_reference_rate(n_cpu, min_seconds=10.0):
@@ -131,7 +144,7 @@ def run_reference(args):
     n_cells = args.n_cpu ** 3
     line = {"impl": "reference", "metric": "fp64 cell-residual evals/sec", "value": cb["value"],
             "unit": "cell-residual evals/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 3.0 * n_cells / cb["value"] * 1e3, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": 3.0 * n_cells / cb["value"] * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"box {args.n_cpu}^3 hex (bounded sample of the box workload), ausmdv, order 2, "
                                    "barth_jespersen, rho_u, inviscid"},
@@ -166,10 +179,8 @@ def run_gpu(args):
     ctx = Context(g, config, device=local)
     if world > 1:
         import torch.distributed as dist
-        ids = [ctx.nccl_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ids, src=0)
-        ctx.comm_init(ids[0], rank, world)
-        ctx.halo_setup([rank + d for d in g.peer_dir], g.send_offsets, g.send_cells, g.recv_offsets, g.recv_cells)
+        halo_mode = ctx.connect(dist, rank, world, [rank + d for d in g.peer_dir], g.send_offsets, g.send_cells,
+                                g.recv_offsets, g.recv_cells, p2p=os.environ.get("IBIS_B200_HALO", "p2p") != "nccl")
     n_owned = int(g.n_owned)
     fs, cq = ctx.fs_create(), ctx.cq_create()
     ctx.fs_upload(fs, prim)
@@ -204,6 +215,7 @@ def run_gpu(args):
     ctx.sync()
     torch.cuda.synchronize()
     ms_total = e0.elapsed_time(e1)
+    ms_local = ms_total
     launches = ctx.launch_count() - l0
     prof_ms, prof_n = ctx.profile_read()
     ctx.profile_enable(False)
@@ -233,7 +245,7 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_e2e = float(t.item())
 
-    n_cells_total = n_owned * world
+    n_cells_total = n ** 3
     ms_per_step = ms_total / args.steps
     value = n_cells_total * 3.0 * args.steps / (ms_total * 1e-3)
     peak, peak_kind = measured_peak()
@@ -243,14 +255,15 @@ def run_gpu(args):
     line = {
         "metric": "fp64 cell-residual evals/sec", "value": value, "unit": "cell-residual evals/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"box {n}^3 = {n_owned} hex cells per GPU in unstructured form "
+        "config": {"workload": f"box {n}^3 = {n ** 3} hex cells in unstructured form "
                                f"(BASELINE.json configs[4]{'' if n == 400 else ', reduced size'}), ausmdv, order 2, "
                                "barth_jespersen, rho_u, inviscid, ssp-rk3 (3 residual evaluations per step), "
-                               "perturbed field; working set " + f"{n_owned * 1030 / 1e9:.1f} GB per evaluation, "
-                               "larger than L2" if n_owned * 1030 > 2 * 126e6 else f"box {n}^3 (L2 resident)",
-                   "cells_per_gpu": n_owned, "parallelism": f"dd{world} (z-slabs, two-ring halo)" if world > 1 else "dd1",
+                               "perturbed field; working set " + f"{n_owned * 1030 / 1e9:.1f} GB per GPU and evaluation, "
+                               + ("larger than L2" if n_owned * 1030 > 2 * 126e6 else "L2 RESIDENT (not a valid bench size)"),
+                   "cells_total": n ** 3, "cells_per_gpu": n_owned,
+                   "parallelism": f"dd{world} (cells decomposed into z-slabs, two-ring halo, NCCL)" if world > 1 else "dd1",
                    "fmad": False, "grid_build_s": round(t_grid, 2), "setup_s": round(t_setup, 2),
                    "bad_cells": bad},
         "gpu_launches": int(launches),
@@ -264,11 +277,19 @@ def run_gpu(args):
                                 "algorithmic_bytes_per_cell": ALG_BYTES_G},
                      "evaluation": {"achieved": ALG_BYTES_EVAL * n_owned / (tF + tG) / 1e9,
                                     "frac": ALG_BYTES_EVAL * n_owned / (tF + tG) / 1e9 / peak,
-                                    "algorithmic_bytes_per_cell": ALG_BYTES_EVAL}},
+                                    "algorithmic_bytes_per_cell": ALG_BYTES_EVAL},
+                     "halo_exchange_ms": (prof_ms[2] / max(int(prof_n[2]), 1)) if world > 1 else None,
+                     "halo_mode": halo_mode if world > 1 else None},
         "e2e": {"value": n_cells_total * 3.0 / t_e2e, "unit": "cell-residual evals/s",
                 "h2d_bytes_per_step": int(prim.nbytes), "d2h_bytes_per_step": int(prim.nbytes),
                 "note": "per step: fs_upload from pinned host memory, prim_to_cons, rk_step, fs_download"},
     }
+    if world > 1:
+        mine = {"rank": rank, "cells": n_owned, "step_ms": ms_local / args.steps, "pass_F_ms": tF * 1e3, "pass_G_ms": tG * 1e3,
+                "halo_exchange_ms": prof_ms[2] / max(int(prof_n[2]), 1)}
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine)
+        line["per_rank"] = per_rank
     if rank == 0:
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_reference_rate(args.n_cpu)
@@ -281,10 +302,11 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ibis_b200")
-    ap.add_argument("--n", type=int, default=int(os.environ.get("IBIS_BENCH_N", "128")))
+    ap.add_argument("--n", "--edge", dest="n", type=int, default=int(os.environ.get("IBIS_BENCH_N", "400")),
+                    help="edge of the global hex box (400 -> the 64 M-cell grid of BASELINE.json)")
     ap.add_argument("--n-cpu", type=int, default=64)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -204,7 +204,9 @@ int compute_dudt_impl(ibis_b200_ctx* c, Buffer* fs, Buffer* dudt, bool allow_rec
     int rc = ensure_fv_temporaries<S>(c);
     if (rc) return rc;
     FvArgs<S> A = make_args<S>(c, fs, dudt, allow_reconstruction);
+    prof_begin(c, 2);
     rc = comm::halo_exchange<S>(c, A.fs);
+    prof_end(c, 2);
     if (rc) return rc;
     launch_bc(c, A, IBIS_B200_PHASE_PRE_RECONSTRUCTION);
     if (sizeof(S) == sizeof(double)) c->last_fs = (int)(fs - c->bufs.data());
@@ -574,7 +576,7 @@ int ibis_b200_sizes(const ibis_b200_ctx* c, int32_t* dim, int64_t* n_cells, int6
 }
 int64_t ibis_b200_launch_count(const ibis_b200_ctx* c) { return c->launches; }
 int ibis_b200_profile_enable(ibis_b200_ctx* c, int on) { c->prof_on = on != 0; return 0; }
-int ibis_b200_profile_read(ibis_b200_ctx* c, double ms[2], int64_t count[2]) { return prof_read(c, ms, count); }
+int ibis_b200_profile_read(ibis_b200_ctx* c, double ms[4], int64_t count[4]) { return prof_read(c, ms, count); }
 void* ibis_b200_stream(ibis_b200_ctx* c) { return (void*)c->stream; }
 
 // ---- buffers ----
@@ -1021,5 +1023,11 @@ int ibis_b200_comm_init(ibis_b200_ctx* c, const void* id, int rank, int n_ranks)
     return comm::init(c, id, rank, n_ranks);
 }
 int ibis_b200_nccl_unique_id(void* out) { return comm::unique_id(out); }
+int ibis_b200_halo_p2p_export(ibis_b200_ctx* c, void* handle64, int64_t* n_recv) { return comm::p2p_export(c, handle64, n_recv); }
+int ibis_b200_halo_p2p_import(ibis_b200_ctx* c, int peer_index, const void* handle64, int64_t peer_n_recv,
+                              int64_t my_offset_in_peer, int my_slot_in_peer) {
+    return comm::p2p_import(c, peer_index, handle64, peer_n_recv, my_offset_in_peer, my_slot_in_peer);
+}
+int ibis_b200_halo_p2p_enable(ibis_b200_ctx* c, int on) { return comm::p2p_enable(c, on); }
 
 }  // extern "C"

@@ -105,6 +105,10 @@ int destroy(ibis_b200_ctx* c) {
     if (h.d_recv_cells) cudaFree(h.d_recv_cells);
     if (h.d_send_buf) cudaFree(h.d_send_buf);
     if (h.d_recv_buf) cudaFree(h.d_recv_buf);
+    for (unsigned char* p : h.peer_base)
+        if (p) cudaIpcCloseMemHandle(p);
+    if (h.d_ipc) cudaFree(h.d_ipc);
+    if (h.d_counters) cudaFree(h.d_counters);
     h = Halo();
     return 0;
 }
@@ -141,10 +145,91 @@ int halo_setup(ibis_b200_ctx* c, int n_peers, const int32_t* peer_ranks, const i
     return 0;
 }
 
+constexpr size_t FLAG_BYTES = 256;     // flags region of the exported allocation (<= 32 peers)
+
+int p2p_export(ibis_b200_ctx* c, void* handle64, int64_t* n_recv) {
+    Halo& h = c->halo;
+    if (h.n_peers > (int)(FLAG_BYTES / 8)) return comm_fail(c, "too many peers for the peer-memory exchange");
+    if (!h.d_ipc) {
+        h.area_bytes = (size_t)std::max<int64_t>(h.n_recv, 1) * 7 * 16;
+        cudaSetDevice(c->device);
+        if (cudaMalloc(&h.d_ipc, FLAG_BYTES + 2 * h.area_bytes) != cudaSuccess ||
+            cudaMalloc(&h.d_counters, sizeof(unsigned) * std::max(h.n_peers, 1)) != cudaSuccess)
+            return comm_fail(c, "out of device memory (peer-memory halo area)");
+        cudaMemsetAsync(h.d_ipc, 0, FLAG_BYTES, c->stream);
+        cudaMemsetAsync(h.d_counters, 0, sizeof(unsigned) * std::max(h.n_peers, 1), c->stream);
+        cudaStreamSynchronize(c->stream);
+        h.peer_base.assign(h.n_peers, nullptr);
+        h.peer_n_recv.assign(h.n_peers, 0);
+        h.peer_my_off.assign(h.n_peers, 0);
+        h.peer_my_slot.assign(h.n_peers, 0);
+    }
+    cudaIpcMemHandle_t mh;
+    cudaError_t e = cudaIpcGetMemHandle(&mh, h.d_ipc);
+    if (e != cudaSuccess) return comm_fail(c, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e));
+    static_assert(sizeof(mh) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(handle64, &mh, 64);
+    if (n_recv) *n_recv = h.n_recv;
+    return 0;
+}
+
+int p2p_import(ibis_b200_ctx* c, int p, const void* handle64, int64_t peer_n_recv, int64_t my_off, int my_slot) {
+    Halo& h = c->halo;
+    if (!h.d_ipc) return comm_fail(c, "halo_p2p_import before halo_p2p_export");
+    if (p < 0 || p >= h.n_peers || my_slot < 0 || my_slot >= (int)(FLAG_BYTES / 8))
+        return comm_fail(c, "halo_p2p_import: bad peer index");
+    cudaIpcMemHandle_t mh;
+    memcpy(&mh, handle64, 64);
+    void* base = nullptr;
+    cudaSetDevice(c->device);
+    cudaError_t e = cudaIpcOpenMemHandle(&base, mh, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return comm_fail(c, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+    h.peer_base[p] = static_cast<unsigned char*>(base);
+    h.peer_n_recv[p] = peer_n_recv;
+    h.peer_my_off[p] = my_off;
+    h.peer_my_slot[p] = my_slot;
+    return 0;
+}
+
+int p2p_enable(ibis_b200_ctx* c, int on) {
+    Halo& h = c->halo;
+    if (on)
+        for (int p = 0; p < h.n_peers; p++)
+            if (!h.peer_base.size() || !h.peer_base[p]) return comm_fail(c, "halo_p2p_enable: a peer is not imported");
+    h.p2p = on != 0;
+    return 0;
+}
+
+// The exchange without NCCL: every rank stores its boundary cells straight into its peers' receive
+// areas (remote stores over NVLink from k_halo_push) and then waits, on the device, for its own
+// flags (k_halo_pull).  Two receive areas alternate: a peer can only start exchange k + 2 after
+// it has consumed my data of exchange k + 1, which I sent after my own pull of exchange k.
+template <typename S>
+static int halo_exchange_p2p(ibis_b200_ctx* c, S* const* fs) {
+    Halo& h = c->halo;
+    h.iter++;
+    const int parity = (int)(h.iter & 1);
+    for (int p = 0; p < h.n_peers; p++) {
+        const int64_t so = h.send_off[p], sn = h.send_off[p + 1] - so;
+        unsigned char* peer_area = h.peer_base[p] + FLAG_BYTES + (size_t)parity * ((size_t)std::max<int64_t>(h.peer_n_recv[p], 1) * 7 * 16);
+        S* remote = reinterpret_cast<S*>(peer_area) + h.peer_my_off[p] * 7;
+        unsigned long long* rflag = reinterpret_cast<unsigned long long*>(h.peer_base[p]) + h.peer_my_slot[p];
+        launch_halo_push<S>(c, fs, h.d_send_cells + so, sn, remote, rflag, h.d_counters + p, h.iter);
+    }
+    for (int p = 0; p < h.n_peers; p++) {
+        const int64_t ro = h.recv_off[p], rn = h.recv_off[p + 1] - ro;
+        const S* area = reinterpret_cast<const S*>(h.d_ipc + FLAG_BYTES + (size_t)parity * h.area_bytes) + ro * 7;
+        launch_halo_pull<S>(c, fs, h.d_recv_cells + ro, rn, area,
+                            reinterpret_cast<const unsigned long long*>(h.d_ipc) + p, h.iter);
+    }
+    return c->last_error.empty() ? 0 : IBIS_B200_ECUDA;
+}
+
 template <typename S>
 int halo_exchange(ibis_b200_ctx* c, S* const* fs) {
     Halo& h = c->halo;
     if (h.n_peers == 0 || c->n_ranks <= 1) return 0;
+    if (h.p2p) return halo_exchange_p2p<S>(c, fs);
     if (!c->nccl_comm) return comm_fail(c, "halo exchange before comm_init");
     Nccl& n = nccl();
     S* sbuf = reinterpret_cast<S*>(h.d_send_buf);

@@ -33,6 +33,19 @@ struct Halo {
     double* d_send_buf = nullptr;              // packed [peer][var][cell], real or dual
     double* d_recv_buf = nullptr;
     int64_t n_send = 0, n_recv = 0;
+    // peer-memory exchange over NVLink (comm.cu): this rank exports ONE allocation
+    //   [flags: one uint64 per peer, padded to 256 B][receive area, parity 0][receive area, parity 1]
+    // and maps the peers' allocations; a receive area holds n_recv cells x 7 rows of dual size,
+    // peer segment p at recv_off[p], stored [row][cell of the segment]
+    bool p2p = false;
+    unsigned char* d_ipc = nullptr;
+    size_t area_bytes = 0;                     // one parity
+    std::vector<unsigned char*> peer_base;     // the peers' allocations as mapped here
+    std::vector<int64_t> peer_n_recv;          // the peer's n_recv (locates its parity-1 area)
+    std::vector<int64_t> peer_my_off;          // offset (cells) of my segment in the peer's receive order
+    std::vector<int> peer_my_slot;             // my index in the peer's peer list (its flag for me)
+    unsigned* d_counters = nullptr;            // last-block counters, one per peer
+    unsigned long long iter = 0;               // exchanges done (same on every rank)
 };
 
 }  // namespace ib
@@ -94,8 +107,8 @@ struct ibis_b200_ctx {
     // order of the reference's parallel_reduce with one OpenMP thread (tests of ill-conditioned
     // Krylov solves); the default is the two-stage tree reduction
     bool ordered_dot = false;
-    std::vector<void*> prof_ev[2];       // event pairs (start, stop, start, stop, ...) per kind
-    size_t prof_used[2] = {0, 0};
+    std::vector<void*> prof_ev[4];       // event pairs (start, stop, start, stop, ...) per kind
+    size_t prof_used[4] = {0, 0, 0, 0};
 
     std::vector<ib::Buffer> bufs;        // handle = index (0 unused)
     ib::Halo halo;
@@ -173,9 +186,19 @@ template <typename S>
 void launch_halo_pack(ibis_b200_ctx* c, S* const* fs, const int* cells, int64_t n, S* buf);
 template <typename S>
 void launch_halo_unpack(ibis_b200_ctx* c, S* const* fs, const int* cells, int64_t n, const S* buf);
+// peer-memory exchange: gather n cells and store them, [row][cell], straight into the peer's receive
+// area (remote), then release-store `iter` to the peer's flag from the last block to finish
+template <typename S>
+void launch_halo_push(ibis_b200_ctx* c, S* const* fs, const int* cells, int64_t n, S* remote,
+                      unsigned long long* remote_flag, unsigned* counter, unsigned long long iter);
+// wait (acquire) until the local flag reaches `iter`, then scatter the received segment
+template <typename S>
+void launch_halo_pull(ibis_b200_ctx* c, S* const* fs, const int* cells, int64_t n, const S* area,
+                      const unsigned long long* flag, unsigned long long iter);
 
 int reduction_blocks(int64_t n);
-// event bracket around a launch when profiling is on (kind 0 = pass G, 1 = pass F)
+// event bracket around a launch when profiling is on (kind 0 = pass G, 1 = pass F, 2 = halo
+// exchange, 3 = everything else of an rk_step: stage updates, conversions, dt)
 void prof_begin(ibis_b200_ctx* c, int kind);
 void prof_end(ibis_b200_ctx* c, int kind);
 int prof_read(ibis_b200_ctx* c, double* ms, int64_t* count);

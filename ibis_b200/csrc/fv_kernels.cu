@@ -71,7 +71,7 @@ void prof_end(ibis_b200_ctx* c, int kind) {
 }
 int prof_read(ibis_b200_ctx* c, double* ms, int64_t* count) {
     cudaStreamSynchronize(c->stream);
-    for (int k = 0; k < 2; k++) {
+    for (int k = 0; k < 4; k++) {
         double t = 0.0;
         for (size_t i = 0; i + 1 < c->prof_used[k]; i += 2) {
             float e = 0.f;

@@ -287,6 +287,59 @@ __global__ void __launch_bounds__(256) k_halo_unpack(Comps7<S> fs, const int* ce
     for (int q = 0; q < 7; q++) mem<S>::store(fs.p[q], cidx, mem<S>::load(buf, i * 7 + q));
 }
 
+// ---- peer-memory halo exchange (NVLink P2P, no NCCL on the data path) ----
+// push: one thread per sent cell gathers its 7 rows and stores them, coalesced along the cell
+// index, into the PEER's receive area; every block fences its remote stores at system scope and the
+// last block to finish publishes the exchange number to the peer's flag (release).
+template <typename S>
+__global__ void __launch_bounds__(256) k_halo_push(Comps7<S> fs, const int* cells, long n, S* remote,
+                                                   unsigned long long* remote_flag, unsigned* counter,
+                                                   unsigned long long iter) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const int cidx = cells[i];
+#pragma unroll
+        for (int q = 0; q < 7; q++) mem<S>::store(remote, q * n + i, mem<S>::load(fs.p[q], cidx));
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned done = atomicAdd(counter, 1u);
+        if (done == gridDim.x - 1) {
+            *counter = 0u;                                   // ready for the next exchange
+            __threadfence_system();
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(remote_flag), "l"(iter) : "memory");
+        }
+    }
+}
+
+// pull: wait until the peer has published this exchange (acquire), then scatter the segment; the
+// area is read past L1 (ld.global.cg): it was written by another GPU
+template <typename S>
+__global__ void __launch_bounds__(256) k_halo_pull(Comps7<S> fs, const int* cells, long n, const S* area,
+                                                   const unsigned long long* flag, unsigned long long iter) {
+    if (threadIdx.x == 0) {
+        unsigned long long seen;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(flag) : "memory");
+        } while (seen < iter);
+    }
+    __syncthreads();
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int cidx = cells[i];
+#pragma unroll
+    for (int q = 0; q < 7; q++) {
+        const double* src = reinterpret_cast<const double*>(area + (q * n + i));
+        if (sizeof(S) == sizeof(double)) {
+            reinterpret_cast<double*>(fs.p[q])[cidx] = __ldcg(src);
+        } else {
+            const double2 t = __ldcg(reinterpret_cast<const double2*>(src));
+            *reinterpret_cast<double2*>(fs.p[q] + cidx) = t;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------
@@ -472,5 +525,24 @@ void launch_halo_unpack(ibis_b200_ctx* c, S* const* fs, const int* cells, int64_
 }
 template void launch_halo_unpack<double>(ibis_b200_ctx*, double* const*, const int*, int64_t, const double*);
 template void launch_halo_unpack<dual>(ibis_b200_ctx*, dual* const*, const int*, int64_t, const dual*);
+
+template <typename S>
+void launch_halo_push(ibis_b200_ctx* c, S* const* fs, const int* cells, int64_t n, S* remote,
+                      unsigned long long* remote_flag, unsigned* counter, unsigned long long iter) {
+    // an empty segment still publishes the exchange number (one block, no cells)
+    k_halo_push<S><<<n > 0 ? nblocks(n, 256) : 1, 256, 0, c->stream>>>(c7(fs), cells, n, remote, remote_flag, counter, iter);
+    CUDA_CHECK_LAUNCH(c);
+}
+template void launch_halo_push<double>(ibis_b200_ctx*, double* const*, const int*, int64_t, double*, unsigned long long*, unsigned*, unsigned long long);
+template void launch_halo_push<dual>(ibis_b200_ctx*, dual* const*, const int*, int64_t, dual*, unsigned long long*, unsigned*, unsigned long long);
+
+template <typename S>
+void launch_halo_pull(ibis_b200_ctx* c, S* const* fs, const int* cells, int64_t n, const S* area,
+                      const unsigned long long* flag, unsigned long long iter) {
+    k_halo_pull<S><<<n > 0 ? nblocks(n, 256) : 1, 256, 0, c->stream>>>(c7(fs), cells, n, area, flag, iter);
+    CUDA_CHECK_LAUNCH(c);
+}
+template void launch_halo_pull<double>(ibis_b200_ctx*, double* const*, const int*, int64_t, const double*, const unsigned long long*, unsigned long long);
+template void launch_halo_pull<dual>(ibis_b200_ctx*, dual* const*, const int*, int64_t, const dual*, const unsigned long long*, unsigned long long);
 
 }  // namespace ib

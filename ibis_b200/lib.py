@@ -229,6 +229,8 @@ class Library:
             "ibis_b200_halo_setup": [vp, i, vp, vp, vp, vp, vp],
             "ibis_b200_profile_enable": [vp, i], "ibis_b200_profile_read": [vp, vp, vp],
             "ibis_b200_comm_init": [vp, vp, i, i], "ibis_b200_nccl_unique_id": [vp],
+            "ibis_b200_halo_p2p_export": [vp, vp, vp], "ibis_b200_halo_p2p_import": [vp, i, vp, i64, i64, i],
+            "ibis_b200_halo_p2p_enable": [vp, i],
         }
         for name, args in sig.items():
             f = getattr(L, name)
@@ -355,8 +357,8 @@ class Context:
         self._ck(self.lib.ibis_b200_profile_enable(self.h, int(on)), "profile_enable")
 
     def profile_read(self):
-        ms = np.zeros(2)
-        n = np.zeros(2, np.int64)
+        ms = np.zeros(4)
+        n = np.zeros(4, np.int64)
         self._ck(self.lib.ibis_b200_profile_read(self.h, _ptr(ms), _ptr(n)), "profile_read")
         return ms, n
 
@@ -438,6 +440,44 @@ class Context:
         ro, rc_ = _as(recv_offsets, np.int64), _as(recv_cells, np.int64)
         self._ck(self.lib.ibis_b200_halo_setup(self.h, len(pr), _ptr(pr), _ptr(so), _ptr(sc), _ptr(ro), _ptr(rc_)),
                  "halo_setup")
+
+    def halo_p2p_export(self):
+        """(64-byte CUDA IPC handle of this rank's receive allocation, its receive count)."""
+        buf = (C.c_char * 64)()
+        n = C.c_int64(0)
+        self._ck(self.lib.ibis_b200_halo_p2p_export(self.h, buf, C.byref(n)), "halo_p2p_export")
+        return bytes(buf), int(n.value)
+
+    def halo_p2p_import(self, peer_index, handle, peer_n_recv, my_offset_in_peer, my_slot_in_peer):
+        buf = (C.c_char * 64).from_buffer_copy(handle)
+        self._ck(self.lib.ibis_b200_halo_p2p_import(self.h, int(peer_index), buf, int(peer_n_recv),
+                                                    int(my_offset_in_peer), int(my_slot_in_peer)), "halo_p2p_import")
+
+    def halo_p2p_enable(self, on=True):
+        self._ck(self.lib.ibis_b200_halo_p2p_enable(self.h, int(on)), "halo_p2p_enable")
+
+    def connect(self, dist, rank, world, peer_ranks, send_offsets, send_cells, recv_offsets, recv_cells, p2p=True):
+        """The host plumbing of one rank of a decomposed run over torch.distributed: NCCL
+        communicator for the scalar reductions, exchange lists, and (p2p) the CUDA IPC handles of
+        the peer-memory halo exchange handed round with all_gather_object."""
+        ids = [self.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        self.comm_init(ids[0], rank, world)
+        peer_ranks = [int(r) for r in peer_ranks]
+        self.halo_setup(peer_ranks, send_offsets, send_cells, recv_offsets, recv_cells)
+        if not p2p:
+            return "nccl"
+        handle, n_recv = self.halo_p2p_export()
+        mine = (handle, n_recv, peer_ranks, [int(o) for o in recv_offsets])
+        everyone = [None] * world
+        dist.all_gather_object(everyone, mine)
+        for p, q in enumerate(peer_ranks):
+            q_handle, q_n_recv, q_peers, q_recv_off = everyone[q]
+            slot = q_peers.index(rank)
+            self.halo_p2p_import(p, q_handle, q_n_recv, q_recv_off[slot], slot)
+        dist.barrier()
+        self.halo_p2p_enable(True)
+        return "p2p"
 
     # JFNK
     def jfnk_set_dual(self, cq, vec, cq_tmp):

@@ -130,12 +130,13 @@ int64_t ibis_b200_launch_count(const ibis_b200_ctx* ctx);
 /* the CUDA stream all kernels are launched on, as a cudaStream_t cast to void* */
 void* ibis_b200_stream(ibis_b200_ctx* ctx);
 
-/* Per-kernel device timing for bench.py's roofline: when enabled, pass G (k_grad_limit) and
- * pass F (k_residual) launches are bracketed by CUDA events on the context's stream.
- * profile_read synchronises and returns the accumulated milliseconds and launch counts
- * since the last read: ms[0]/count[0] = pass G, ms[1]/count[1] = pass F. */
+/* Per-kernel device timing for bench.py's roofline: when enabled, pass G (gradients + limiters)
+ * and pass F (reconstruction + flux + surface integral) launches and the halo exchange are
+ * bracketed by CUDA events on the context's stream.  profile_read synchronises and returns the
+ * accumulated milliseconds and counts since the last read: [0] = pass G, [1] = pass F,
+ * [2] = halo exchange (pack, ncclSend/ncclRecv, unpack), [3] = reserved. */
 int ibis_b200_profile_enable(ibis_b200_ctx* ctx, int on);
-int ibis_b200_profile_read(ibis_b200_ctx* ctx, double ms[2], int64_t count[2]);
+int ibis_b200_profile_read(ibis_b200_ctx* ctx, double ms[4], int64_t count[4]);
 
 /* ---- buffers ------------------------------------------------------------------------- */
 /* FlowStates<T>(num_total_cells) (gas/flow_state.h:62) */
@@ -236,6 +237,18 @@ int ibis_b200_halo_setup(ibis_b200_ctx*, int n_peers, const int32_t* peer_ranks,
  * for the MIN / SUM reductions of estimate_dt, l2_norms, dot, norm2, count_bad_cells. */
 int ibis_b200_comm_init(ibis_b200_ctx*, const void* nccl_unique_id, int rank, int n_ranks);
 int ibis_b200_nccl_unique_id(void* out_128_bytes);
+/* Peer-memory halo exchange (one process per GPU, NVLink / NVSwitch): instead of ncclSend/ncclRecv the
+ * boundary cells are stored by a kernel of the sending rank straight into the receiving rank's
+ * memory, with device-side release / acquire flags -- no NCCL call and no host synchronisation on
+ * the data path.  After halo_setup every rank exports a 64-byte CUDA IPC handle of its receive
+ * allocation (and its total receive count); the host plumbing (torch.distributed / MPI) hands each
+ * rank, per peer p of its halo_setup list: that peer's handle and receive count, the offset (in
+ * cells) of this rank's segment in the peer's receive order, and this rank's index in the peer's
+ * peer list.  halo_p2p_enable(ctx, 1) then switches the exchange over (0: back to NCCL). */
+int ibis_b200_halo_p2p_export(ibis_b200_ctx*, void* out_handle_64_bytes, int64_t* n_recv_cells);
+int ibis_b200_halo_p2p_import(ibis_b200_ctx*, int peer_index, const void* handle_64_bytes,
+                              int64_t peer_n_recv_cells, int64_t my_offset_in_peer, int my_slot_in_peer);
+int ibis_b200_halo_p2p_enable(ibis_b200_ctx*, int on);
 
 #ifdef __cplusplus
 }

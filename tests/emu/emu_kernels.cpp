@@ -21,7 +21,7 @@ namespace ib {
 int reduction_blocks(int64_t) { return 1; }
 void prof_begin(ibis_b200_ctx*, int) {}
 void prof_end(ibis_b200_ctx*, int) {}
-int prof_read(ibis_b200_ctx*, double* ms, int64_t* n) { ms[0] = ms[1] = 0; n[0] = n[1] = 0; return 0; }
+int prof_read(ibis_b200_ctx*, double* ms, int64_t* n) { for (int k = 0; k < 4; k++) { ms[k] = 0; n[k] = 0; } return 0; }
 
 template <typename S>
 void launch_bc(ibis_b200_ctx* c, const FvArgs<S>& A, int phase) {
@@ -429,6 +429,9 @@ int unique_id(void*) { return IBIS_B200_ECOMM; }
 int allreduce(ibis_b200_ctx*, double*, int, int) { return 0; }
 int halo_setup(ibis_b200_ctx*, int, const int32_t*, const int64_t*, const int64_t*, const int64_t*, const int64_t*) { return 0; }
 template <typename S> int halo_exchange(ibis_b200_ctx*, S* const*) { return 0; }
+int p2p_export(ibis_b200_ctx*, void*, int64_t*) { return IBIS_B200_ECOMM; }
+int p2p_import(ibis_b200_ctx*, int, const void*, int64_t, int64_t, int) { return IBIS_B200_ECOMM; }
+int p2p_enable(ibis_b200_ctx*, int) { return IBIS_B200_ECOMM; }
 template int halo_exchange<double>(ibis_b200_ctx*, double* const*);
 template int halo_exchange<dual>(ibis_b200_ctx*, dual* const*);
 }  // namespace comm
