@@ -22,8 +22,21 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
 
-ALG_BYTES_G, ALG_BYTES_F = 392, 638       # pass G, pass F per cell
-ALG_BYTES_EVAL = ALG_BYTES_G + ALG_BYTES_F
+# algorithmic bytes per cell of one residual evaluation = 1030 (pass G 392 +
+# pass F 638).  The default (sides) path splits the work differently: k_grad_sides does pass G AND
+# the MUSCL extrapolation + thermodynamic closure of pass F (its state / gradient / limiter /
+# centroid / face-centre items: 224 B), k_flux_tile the rest of pass F (face frames 240, face and
+# cell-face ids 54, volume 8, residual 40, face centres already counted: 414 B... see DESIGN.md section 3).
+ALG_BYTES_EVAL = 1030
+ALG_BYTES_SPLIT = {"sides": (616, 414), "gather": (392, 638)}
+KERNEL_NAMES = {"sides": ("k_grad_sides (gradients + limiters + MUSCL sides)", "k_flux_tile (flux + surface integral)"),
+                "gather": ("k_grad_limit (gradients + limiters)", "k_residual_tile (reconstruct + flux + surface integral)")}
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch and cell from the committed `ncu --set full`
+# capture of the same kernels (profiles/r01_summary.md), bytes per cell; scaled by the cell count
+TRAFFIC_NCU_PER_CELL = {"sides": {"G": 662.6, "F": 604.7}, "gather": {"G": 382.0, "F": 786.0}}
+TRAFFIC_NCU = {}
 
 
 def measured_peak():
@@ -251,7 +264,12 @@ def run_gpu(args):
     peak, peak_kind = measured_peak()
     tF = prof_ms[1] / max(int(prof_n[1]), 1) * 1e-3
     tG = prof_ms[0] / max(int(prof_n[0]), 1) * 1e-3
-    achieved_F = ALG_BYTES_F * n_owned / tF / 1e9
+    path = "gather" if os.environ.get("IBIS_B200_SIDES", "1") == "0" else "sides"
+    bytes_G, bytes_F = ALG_BYTES_SPLIT[path]
+    name_G, name_F = KERNEL_NAMES[path]
+    ach_G, ach_F = bytes_G * n_owned / tG / 1e9, bytes_F * n_owned / tF / 1e9
+    dom = "G" if tG >= tF else "F"          # the dominant kernel = the one with the longer launches
+    TRAFFIC_NCU[path] = {k: v * n_owned for k, v in TRAFFIC_NCU_PER_CELL[path].items()}
     line = {
         "metric": "fp64 cell-residual evals/sec", "value": value, "unit": "cell-residual evals/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
@@ -268,13 +286,17 @@ def run_gpu(args):
                    "bad_cells": bad},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "k_residual (pass F: reconstruct+flux+integral)",
-                     "achieved": achieved_F, "peak": peak, "unit": "GB/s", "frac": achieved_F / peak,
-                     "traffic": None, "peak_kind": peak_kind,
-                     "algorithmic_bytes_per_cell": ALG_BYTES_F, "avg_launch_ms": tF * 1e3,
-                     "pass_G": {"kernel": "k_grad_limit", "avg_launch_ms": tG * 1e3,
-                                "achieved": ALG_BYTES_G * n_owned / tG / 1e9 if tG > 0 else None,
-                                "algorithmic_bytes_per_cell": ALG_BYTES_G},
+        "roofline": {"bound": "hbm", "kernel": name_G if dom == "G" else name_F,
+                     "achieved": ach_G if dom == "G" else ach_F, "peak": peak, "unit": "GB/s",
+                     "frac": (ach_G if dom == "G" else ach_F) / peak,
+                     "traffic": TRAFFIC_NCU.get(path, {}).get(dom), "peak_kind": peak_kind,
+                     "algorithmic_bytes_per_cell": bytes_G if dom == "G" else bytes_F,
+                     "avg_launch_ms": (tG if dom == "G" else tF) * 1e3,
+                     "path": path,
+                     "pass_G": {"kernel": name_G, "avg_launch_ms": tG * 1e3, "achieved": ach_G, "frac": ach_G / peak,
+                                "algorithmic_bytes_per_cell": bytes_G},
+                     "pass_F": {"kernel": name_F, "avg_launch_ms": tF * 1e3, "achieved": ach_F, "frac": ach_F / peak,
+                                "algorithmic_bytes_per_cell": bytes_F},
                      "evaluation": {"achieved": ALG_BYTES_EVAL * n_owned / (tF + tG) / 1e9,
                                     "frac": ALG_BYTES_EVAL * n_owned / (tF + tG) / 1e9 / peak,
                                     "algorithmic_bytes_per_cell": ALG_BYTES_EVAL},

@@ -121,12 +121,14 @@ FvArgs<S> make_args(ibis_b200_ctx* c, Buffer* fs, Buffer* dudt, bool allow_recon
         A.grad = reinterpret_cast<S*>(c->grad_r);
         A.lim = reinterpret_cast<S*>(c->lim_r);
         A.flux = reinterpret_cast<S*>(c->flux_r);
-        A.sides = reinterpret_cast<S*>(c->sides_r);
+        A.sideL = reinterpret_cast<S*>(c->sideL_r);
+        A.sideR = reinterpret_cast<S*>(c->sideR_r);
     } else {
         A.grad = reinterpret_cast<S*>(c->grad_d);
         A.lim = reinterpret_cast<S*>(c->lim_d);
         A.flux = reinterpret_cast<S*>(c->flux_d);
-        A.sides = reinterpret_cast<S*>(c->sides_d);
+        A.sideL = reinterpret_cast<S*>(c->sideL_d);
+        A.sideR = reinterpret_cast<S*>(c->sideR_d);
     }
     {   // the five reconstructed variables of pass F with their gradient / limiter arrays
         const int src[5] = {F_RHO, (c->cfg.thermo_interpolator == THERMO_RHO_P) ? F_P
@@ -169,11 +171,12 @@ template <typename S>
 int ensure_fv_temporaries(ibis_b200_ctx* c, bool want_grad = false) {
     const bool need_grad = want_grad || c->cfg.viscous || (c->cfg.reconstruction_order > 1 && !sides_path(c));
     if (sides_path(c)) {
-        S** sides = (sizeof(S) == 8) ? reinterpret_cast<S**>(&c->sides_r) : reinterpret_cast<S**>(&c->sides_d);
-        if (!*sides) {
-            int rc = dev_alloc_zero<S>(c, (int64_t)frec<S>::stride * std::max<int64_t>(c->n_faces, 1), sides);
-            if (rc) return fail(c, rc, "out of device memory (interface records)");
-            launch_frec_geom<S>(c, *sides);
+        S** sl = (sizeof(S) == 8) ? reinterpret_cast<S**>(&c->sideL_r) : reinterpret_cast<S**>(&c->sideL_d);
+        S** sr = (sizeof(S) == 8) ? reinterpret_cast<S**>(&c->sideR_r) : reinterpret_cast<S**>(&c->sideR_d);
+        if (!*sl) {
+            int rc = dev_alloc_zero<S>(c, (int64_t)6 * std::max<int64_t>(c->n_faces, 1), sl);
+            if (!rc) rc = dev_alloc_zero<S>(c, (int64_t)6 * std::max<int64_t>(c->n_faces, 1), sr);
+            if (rc) return fail(c, rc, "out of device memory (interface sides)");
         }
     }
     S** grad = (sizeof(S) == 8) ? reinterpret_cast<S**>(&c->grad_r) : reinterpret_cast<S**>(&c->grad_d);
@@ -260,6 +263,16 @@ int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd_ref, con
         int rrc = renumber_grid(gd_ref, morton, R, &err);
         if (rrc) return fail(nullptr, rrc, err ? err : "renumbering failed");
     }
+    // tiles and the tile-owned interface numbering (layout.h)
+    TileLayout TL;
+    {
+        int T = 128;
+        if (const char* e = getenv("IBIS_B200_TILE")) T = atoi(e);
+        if (T != 64 && T != 128 && T != 256) T = 128;
+        const char* err = nullptr;
+        int rrc = regroup_faces(R, T, TL, &err);
+        if (rrc) return fail(nullptr, rrc, err ? err : "interface regrouping failed");
+    }
     const ibis_b200_grid_desc* gd = &R.desc;
     if (gd->dim != 2 && gd->dim != 3) return fail(nullptr, IBIS_B200_EINVAL, "dim must be 2 or 3");
     if (cfg->thermo_interpolator == IBIS_B200_THERMO_P_T)
@@ -279,12 +292,14 @@ int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd_ref, con
     int rc = gpu::set_device(device);
     if (rc != 0) { delete c; return fail(nullptr, IBIS_B200_ECUDA, std::string("cudaSetDevice: ") + gpu::error_string(rc)); }
     gpu::get_device(&c->device);
+    c->n_sm = gpu::sm_count(c->device);
     rc = gpu::stream_create(&c->stream);
     if (rc != 0) { delete c; return fail(nullptr, IBIS_B200_ECUDA, std::string("cudaStreamCreate: ") + gpu::error_string(rc)); }
 
     c->cfg = *cfg;
     if (const char* e = getenv("IBIS_B200_ORDERED_DOT")) c->ordered_dot = e[0] == '1';
     if (const char* e = getenv("IBIS_B200_SIDES")) c->use_sides = e[0] != '0';
+    if (const char* e = getenv("IBIS_B200_RK_UNFUSED")) c->rk_unfused = e[0] == '1';
     c->bc_actions.assign(cfg->bc_actions, cfg->bc_actions + cfg->n_bc_actions);
     c->cfg.bc_actions = nullptr;
     c->dim = gd->dim;
@@ -400,6 +415,20 @@ int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd_ref, con
     g.cz = g.cx + 2 * cs;
     UP(fl, di, f_left) UP(fr, di, f_right) UP(fa, dd, f_area)
     UP(fn, dd, f_n) UP(ft1, dd, f_t1) UP(ft2, dd, f_t2) UP(fc, dd, f_c)
+    {
+        std::vector<double> fgeom((size_t)10 * std::max<int64_t>(gd->n_faces, 1), 0.0);
+#pragma omp parallel for schedule(static)
+        for (int64_t f = 0; f < gd->n_faces; f++) {
+            double* q = &fgeom[(size_t)10 * f];
+            for (int d = 0; d < 3; d++) {
+                q[d] = gd->face_norm[3 * f + d];
+                q[3 + d] = gd->face_tan1[3 * f + d];
+                q[6 + d] = gd->face_tan2[3 * f + d];
+            }
+            q[9] = gd->face_area[f];
+        }
+        UP(fgeom, dd, f_geom)
+    }
     UP(bf_face, di, bf_face) UP(bf_tag, di, bf_tag)
     UP(acts, da, act) UP(act_off, di, act_off)
     if (morton) {
@@ -407,57 +436,79 @@ int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd_ref, con
         if (rc) { ibis_b200_destroy(c); return fail(nullptr, rc, "grid upload failed"); }
     }
 #undef UP
-    // ---- tiles of the tiled residual kernel (fv_bodies.h: GridDev::tile...) ----
+    // ---- tiles (layout.h): slot / staging tables of the tiled kernels ----
     {
-        int T = 128;
-        if (const char* e = getenv("IBIS_B200_TILE")) T = atoi(e);
-        if (T != 64 && T != 128 && T != 256) T = 128;
-        const int64_t n_owned = c->n_owned;
-        const int n_tiles = (int)((n_owned + T - 1) / T);
-        std::vector<int> home0(n_tiles + 1, 0), foreign_off(n_tiles + 1, 0);
-        for (int b = 0; b <= n_tiles; b++) home0[b] = (int)R.cell_first_face[std::min<int64_t>((int64_t)b * T, n_owned)];
-        std::vector<unsigned short> cf_slot((size_t)MAXF * cs, 0xFFFF);
-#pragma omp parallel for schedule(static)
-        for (int b = 0; b < n_tiles; b++) {
+        const int T = TL.T;
+        const int nt = TL.nt_all, n_tiles = TL.nt_owned;
+        // flux slots of a tile: its home interfaces [0, nh), then the interfaces of its entries
+        std::vector<int> foreign_off(nt + 1, 0);
+        for (int b = 0; b < nt; b++) {
             int nf = 0;
-            const int64_t c0 = (int64_t)b * T, c1 = std::min<int64_t>(c0 + T, n_owned);
-            for (int64_t i = c0; i < c1; i++)
-                for (int j = 0; j < max_faces; j++) {
-                    const int f = cf_face[(size_t)j * cs + i];
-                    if (f >= 0 && f < home0[b]) nf++;
-                }
-            foreign_off[b + 1] = nf;
+            for (int e = TL.ent_off[b]; e < TL.ent_off[b + 1]; e++) nf += TL.entries[e].count;
+            foreign_off[b + 1] = foreign_off[b] + nf;
         }
-        for (int b = 0; b < n_tiles; b++) foreign_off[b + 1] += foreign_off[b];
-        std::vector<int> foreign(std::max(foreign_off[n_tiles], 1), 0);
-        int cap = 1;
-        bool too_many = false;
-#pragma omp parallel for schedule(static) reduction(max : cap) reduction(|| : too_many)
-        for (int b = 0; b < n_tiles; b++) {
-            const int nh = home0[b + 1] - home0[b];
+        std::vector<int> foreign(std::max(foreign_off[nt], 1), 0);
+#pragma omp parallel for schedule(static)
+        for (int b = 0; b < nt; b++) {
             int k = foreign_off[b];
-            const int64_t c0 = (int64_t)b * T, c1 = std::min<int64_t>(c0 + T, n_owned);
-            for (int64_t i = c0; i < c1; i++)
+            for (int e = TL.ent_off[b]; e < TL.ent_off[b + 1]; e++)
+                for (int q = 0; q < TL.entries[e].count; q++) foreign[k++] = TL.entries[e].f_start + q;
+        }
+        // per cell face: flux slot in the cell's tile, and the staging index of the cell's own side
+        std::vector<unsigned short> cf_slot((size_t)MAXF * cs, 0xFFFF), cf_stage((size_t)MAXF * cs, 0xFFFF);
+        bool bad_table = false;
+#pragma omp parallel for schedule(static) reduction(|| : bad_table)
+        for (int b = 0; b < nt; b++) {
+            const int h0 = TL.h0[b], nh = TL.h0[b + 1] - h0, nR = TL.nR[b];
+            const int n_own_l = TL.n_own_left(b);
+            for (int64_t i = TL.c0[b]; i < TL.c0[b + 1]; i++)
                 for (int j = 0; j < max_faces; j++) {
                     const int f = cf_face[(size_t)j * cs + i];
                     if (f < 0) continue;
-                    int slot;
-                    if (f < home0[b]) {
-                        slot = nh + (k - foreign_off[b]);
-                        foreign[k++] = f;
+                    const bool is_left = cf_out[(size_t)j * cs + i] > 0;
+                    int slot, stage;
+                    if (TL.home_tile[f] == b) {
+                        slot = f - h0;
+                        stage = is_left ? slot - nR : n_own_l + slot;
+                        if (stage < 0) bad_table = true;
                     } else {
-                        slot = f - home0[b];
+                        slot = TL.slot_other[f];
+                        stage = -1;
+                        for (int e = TL.ent_off[b]; e < TL.ent_off[b + 1]; e++) {
+                            const TileEntry& te = TL.entries[e];
+                            if (f >= te.f_start && f < te.f_start + te.count) stage = te.stage_start + (f - te.f_start);
+                        }
+                        if (slot < 0 || stage < 0) bad_table = true;
                     }
-                    if (slot >= 0xFFFF) too_many = true;
+                    if (slot >= 0xFFFF || stage >= 0xFFFF) bad_table = true;
                     cf_slot[(size_t)j * cs + i] = (unsigned short)slot;
+                    cf_stage[(size_t)j * cs + i] = (unsigned short)stage;
                 }
-            cap = std::max(cap, nh + (foreign_off[b + 1] - foreign_off[b]));
         }
-        if (too_many || cap >= 0x7FFF || (size_t)cap * frec<dual>::bytes > 220 * 1024) {
+        const int cap = TL.cap_slots;
+        if (bad_table || cap >= 0x7FFF || (size_t)cap * frec<dual>::bytes > 220 * 1024 ||
+            (size_t)TL.cap_stage * 6 * sizeof(dual) > 150 * 1024) {
             ibis_b200_destroy(c);
             return fail(nullptr, IBIS_B200_EINVAL, "tile has too many interfaces for shared memory");
         }
-        // sides of the tile's interfaces that belong to cells outside the tile
+        // tile descriptors for the kernels: {c0, nc, h0, nh, nR, n0, ent_off, n_ent, n_own_l, n_slots, -, -}
+        std::vector<int> tile_info((size_t)TILE_INFO * std::max(nt, 1), 0);
+        for (int b = 0; b < nt; b++) {
+            int* q = &tile_info[(size_t)TILE_INFO * b];
+            q[0] = TL.c0[b]; q[1] = TL.c0[b + 1] - TL.c0[b]; q[2] = TL.h0[b]; q[3] = TL.h0[b + 1] - TL.h0[b];
+            q[4] = TL.nR[b]; q[5] = TL.n0[b]; q[6] = TL.ent_off[b]; q[7] = TL.ent_off[b + 1] - TL.ent_off[b];
+            q[8] = TL.n_own_left(b);
+            q[9] = q[3];
+            for (int e = TL.ent_off[b]; e < TL.ent_off[b + 1]; e++) q[9] += TL.entries[e].count;
+        }
+        std::vector<int> tile_ent((size_t)5 * std::max<size_t>(TL.entries.size(), 1), 0);
+        for (size_t e = 0; e < TL.entries.size(); e++) {
+            int* q = &tile_ent[5 * e];
+            q[0] = TL.entries[e].f_start; q[1] = TL.entries[e].count; q[2] = TL.entries[e].section;
+            q[3] = TL.entries[e].slot_start; q[4] = TL.entries[e].stage_start;
+        }
+        std::vector<int> home0(TL.h0.begin(), TL.h0.end());
+        // sides of the (owned) tiles' interfaces that belong to cells outside the tile: gather path
         std::vector<int> out_off(n_tiles + 1, 0);
         auto face_of_slot = [&](int b, int slot) {
             const int nh = home0[b + 1] - home0[b];
@@ -465,7 +516,7 @@ int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd_ref, con
         };
 #pragma omp parallel for schedule(static)
         for (int b = 0; b < n_tiles; b++) {
-            const int64_t c0 = (int64_t)b * T, c1 = std::min<int64_t>(c0 + T, n_owned);
+            const int64_t c0 = TL.c0[b], c1 = TL.c0[b + 1];
             const int ns = (home0[b + 1] - home0[b]) + (foreign_off[b + 1] - foreign_off[b]);
             int n = 0;
             for (int sl = 0; sl < ns; sl++) {
@@ -488,7 +539,7 @@ int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd_ref, con
         };
 #pragma omp parallel for schedule(static)
         for (int b = 0; b < n_tiles; b++) {
-            const int64_t c0 = (int64_t)b * T, c1 = std::min<int64_t>(c0 + T, n_owned);
+            const int64_t c0 = TL.c0[b], c1 = TL.c0[b + 1];
             const int ns = (home0[b + 1] - home0[b]) + (foreign_off[b + 1] - foreign_off[b]);
             int k = out_off[b];
             for (int sl = 0; sl < ns; sl++) {
@@ -499,13 +550,16 @@ int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd_ref, con
         }
         g.tile = T;
         g.n_tiles = n_tiles;
+        g.n_tiles_all = nt;
         g.tile_cap = cap;
+        g.stage_cap = TL.cap_stage;
         unsigned short* du16 = nullptr;
 #define UP2(vec, ptr, field)                                                        \
     rc = upload_vec(c, vec, &ptr);                                                  \
     if (rc) { ibis_b200_destroy(c); return fail(nullptr, rc, "grid upload failed"); } \
     g.field = ptr;
         UP2(home0, di, home0) UP2(foreign_off, di, foreign_off) UP2(foreign, di, foreign) UP2(cf_slot, du16, cf_slot)
+        UP2(cf_stage, du16, cf_stage) UP2(tile_info, di, tile_info) UP2(tile_ent, di, tile_ent)
         UP2(out_off, di, out_off) UP2(out_slot, du16, out_slot) UP2(out_cell, di, out_cell) UP2(out_d, dd, out_d)
         g.n_out = n_out;
 #undef UP2
@@ -860,35 +914,59 @@ int ibis_b200_rk_step(ibis_b200_ctx* c, int fs, int cq, int n_stages, const doub
     double* d_dt = c->d_scalars + SC_DT;
     launch_rk_dt(c, c->d_scalars + SC_DT_STABLE, cfl, dt_prev, t_remaining, d_dt);
     int row = 0;    // a(i, j) = a[row(i) + j], row(i) = i(i-1)/2 for i = 1..stages-1
+    const bool fused = n_stages <= RK_MAX_TERMS && !c->rk_unfused;
+    double *uq[7], *fq[7], *ftq[7];
+    comp_ptrs<double>(U, uq);
+    comp_ptrs<double>(F, fq);
     for (int i = 1; i < n_stages; i++) {
         Buffer* ktmp = &c->bufs[c->rk_ktmp];
         Buffer* ftmp = &c->bufs[c->rk_fstmp];
-        rc = apply_dt(c, U, ktmp, &c->bufs[c->rk_k[0]], 0.0, d_dt, a[row + 0]);       // :155
-        if (rc) return rc;
-        for (int j = 1; j < i; j++) {
-            if (a[row + j] < 1e-14) continue;                                          // :166
-            rc = apply_dt(c, ktmp, ktmp, &c->bufs[c->rk_k[j]], 0.0, d_dt, a[row + j]); // :169
+        comp_ptrs<double>(ftmp, ftq);
+        if (fused) {
+            // k_tmp = U + dt a(i,0) k_0 [+ dt a(i,j) k_j ...] and flow_tmp = primitives(k_tmp), :155-177,
+            // in one pass; k_tmp itself stays in registers
+            RkTerms<double> T;
+            T.n = 0;
+            for (int j = 0; j < i; j++) {
+                if (j >= 1 && a[row + j] < 1e-14) continue;                            // :166
+                double* kq[7];
+                comp_ptrs<double>(&c->bufs[c->rk_k[j]], kq);
+                for (int q = 0; q < 5; q++) T.k[T.n][q] = kq[q];
+                T.scale[T.n++] = a[row + j];
+            }
+            launch_rk_update<double>(c, uq, T, d_dt, nullptr, ftq, c->n_total);
+        } else {
+            rc = apply_dt(c, U, ktmp, &c->bufs[c->rk_k[0]], 0.0, d_dt, a[row + 0]);       // :155
             if (rc) return rc;
-        }
-        {
-            double *q[7], *p[7];
+            for (int j = 1; j < i; j++) {
+                if (a[row + j] < 1e-14) continue;                                          // :166
+                rc = apply_dt(c, ktmp, ktmp, &c->bufs[c->rk_k[j]], 0.0, d_dt, a[row + j]); // :169
+                if (rc) return rc;
+            }
+            double* q[7];
             comp_ptrs<double>(ktmp, q);
-            comp_ptrs<double>(ftmp, p);
-            launch_cons_to_prim<double>(c, q, p, c->n_total);                          // :177
+            launch_cons_to_prim<double>(c, q, ftq, c->n_total);                          // :177
         }
         rc = compute_dudt_impl<double>(c, ftmp, &c->bufs[c->rk_k[i]], true);          // :181
         if (rc) return rc;
         row += i;
     }
-    for (int i = 0; i < n_stages; i++) {
-        rc = apply_dt(c, U, U, &c->bufs[c->rk_k[i]], 0.0, d_dt, b[i]);                // :185-186
-        if (rc) return rc;
-    }
-    {
-        double *q[7], *p[7];
-        comp_ptrs<double>(U, q);
-        comp_ptrs<double>(F, p);
-        launch_cons_to_prim<double>(c, q, p, c->n_total);                              // :193
+    if (fused) {
+        RkTerms<double> T;                                                             // :185-193
+        T.n = n_stages;
+        for (int i = 0; i < n_stages; i++) {
+            double* kq[7];
+            comp_ptrs<double>(&c->bufs[c->rk_k[i]], kq);
+            for (int q = 0; q < 5; q++) T.k[i][q] = kq[q];
+            T.scale[i] = b[i];
+        }
+        launch_rk_update<double>(c, uq, T, d_dt, uq, fq, c->n_total);
+    } else {
+        for (int i = 0; i < n_stages; i++) {
+            rc = apply_dt(c, U, U, &c->bufs[c->rk_k[i]], 0.0, d_dt, b[i]);                // :185-186
+            if (rc) return rc;
+        }
+        launch_cons_to_prim<double>(c, uq, fq, c->n_total);                              // :193
     }
     double out[2];
     rc = fetch_scalars(c, SC_DT_STABLE, 2, out);

@@ -40,6 +40,10 @@ inline int d2d(void* dst, const void* src, size_t bytes, stream_t s) {
 }
 inline const char* error_string(int e) { return cudaGetErrorString((cudaError_t)e); }
 inline int last_error() { return (int)cudaGetLastError(); }
+inline int sm_count(int dev) {
+    int n = 0;
+    return cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0 ? n : 148;
+}
 #else
 typedef void* stream_t;
 inline int set_device(int) { return 0; }
@@ -57,6 +61,7 @@ inline int d2h(void* h, const void* d, size_t bytes, stream_t) { memcpy(h, d, by
 inline int d2d(void* dst, const void* src, size_t bytes, stream_t) { memmove(dst, src, bytes); return 0; }
 inline const char* error_string(int) { return "host emulation error"; }
 inline int last_error() { return 0; }
+inline int sm_count(int) { return 1; }
 #endif
 
 }  // namespace gpu

@@ -9,6 +9,7 @@
 
 #include "backend.h"
 #include "fv_bodies.h"
+#include "solver_bodies.h"
 #include "ibis_b200.h"
 
 namespace ib {
@@ -52,6 +53,7 @@ struct Halo {
 
 struct ibis_b200_ctx {
     int device = 0;
+    int n_sm = 148;                      // multiprocessors of the device (persistent grids)
     ib::gpu::stream_t stream = nullptr;
     std::string last_error;
     int64_t launches = 0;
@@ -80,9 +82,11 @@ struct ibis_b200_ctx {
     double* face_T = nullptr;
     double* face_rho = nullptr;
     // interface-side records of the sides path (fv_bodies.h), real and dual
-    double* sides_r = nullptr;
-    ib::dual* sides_d = nullptr;
-    bool use_sides = false;              // IBIS_B200_SIDES=1: second order through the interface-record path
+    double* sideL_r = nullptr;
+    double* sideR_r = nullptr;
+    ib::dual* sideL_d = nullptr;
+    ib::dual* sideR_d = nullptr;
+    bool use_sides = true;               // IBIS_B200_SIDES=0: second order through the gather path (grad + limiter arrays)
     int last_fs = 0;                     // FlowStates handle of the last real evaluation (debug_gradients)
 
     // reductions
@@ -99,6 +103,7 @@ struct ibis_b200_ctx {
     std::vector<int> rk_k;            // handle of stage i (all equal when the stages alias)
     std::vector<int> rk_k_own;        // the buffers actually allocated
     bool rk_alias_stages = true;      // the reference's k_ stages share one array
+    bool rk_unfused = false;          // IBIS_B200_RK_UNFUSED=1: one kernel per apply_time_derivative / conversion
     int rk_ktmp = 0, rk_fstmp = 0;
 
     // optional per-kernel event timing (ibis_b200_profile_*)
@@ -132,8 +137,6 @@ void launch_grad_sides(ibis_b200_ctx* c, const FvArgs<S>& A);      // sides path
 template <typename S>
 void launch_flux_tile(ibis_b200_ctx* c, const FvArgs<S>& A);       // sides path, pass F'
 template <typename S>
-void launch_frec_geom(ibis_b200_ctx* c, S* sides);                 // static part of the interface records
-template <typename S>
 void launch_face_flux(ibis_b200_ctx* c, const FvArgs<S>& A);       // general path
 template <typename S>
 void launch_face_viscous(ibis_b200_ctx* c, const FvArgs<S>& A);
@@ -150,6 +153,9 @@ void launch_prim_to_cons(ibis_b200_ctx* c, S* const* cq, S* const* fs, int64_t n
 template <typename S>
 void launch_apply_dt(ibis_b200_ctx* c, S* const* u0, S* const* u1, S* const* k, double dt,
                      const double* d_dt, double scale, int64_t n);
+template <typename S>
+void launch_rk_update(ibis_b200_ctx* c, S* const* u_in, const RkTerms<S>& T, const double* d_dt, S* const* u_out,
+                      S* const* fs, int64_t n);     // fused stage / final update + cons_to_prim (u_out may be null)
 template <typename S>
 void launch_l2_norms(ibis_b200_ctx* c, S* const* cq, int64_t n, double* d_out6);
 template <typename S>

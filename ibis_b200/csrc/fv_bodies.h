@@ -12,15 +12,14 @@
 namespace ib {
 
 constexpr int MAXF = 6;       // faces per cell: hex 6, wedge/pyramid 5, tet/quad 4, tri 3
-// One record per interface in the sides array: [left rho p T vx vy vz | right ... | nx ny nz t1x t1y
-// t1z t2x t2y t2z area]: 12 scalars of type S written by pass G' every evaluation + the static
-// frame as 10 doubles, contiguous so that pass F' fetches an interface with one bulk copy
-// (176 bytes for double, 272 for dual; both multiples of 16).
+// The interface-side arrays of the sides path: sideL[f][6], sideR[f][6] (rho p T vx vy vz of the left
+// / right state, written by pass G' every evaluation) and the static frame f_geom[f][10] (nx ny nz
+// t1x t1y t1z t2x t2y t2z area).  Bytes of one interface in shared memory: 12 S + 10 doubles.
 template <typename S>
 struct frec {
     static constexpr int bytes = 12 * (int)sizeof(S) + 80;
-    static constexpr int stride = bytes / (int)sizeof(S);       // in units of S: 22 / 17
 };
+constexpr int TILE_INFO = 12;  // ints per tile descriptor (GridDev::tile_info)
 constexpr int NVARS = 6;      // gradient slots: rho, thermo-2, vx, vy, vz, T(viscous)
 enum { V_RHO = 0, V_TH2 = 1, V_VX = 2, V_VY = 3, V_VZ = 4, V_TVISC = 5 };
 enum { F_RHO = 0, F_P = 1, F_T = 2, F_E = 3, F_VX = 4, F_VY = 5, F_VZ = 6 };
@@ -60,6 +59,7 @@ struct GridDev {
     const double* f_t1;
     const double* f_t2;
     const double* f_c;          // centres
+    const double* f_geom;       // sides path: [face*10 + k] nx ny nz t1x t1y t1z t2x t2y t2z area
     // boundary faces in (tag alphabetical, marker order)
     const int* bf_face;
     const int* bf_tag;
@@ -74,6 +74,14 @@ struct GridDev {
     // tile-local flux slot of every cell face: home slot = face - home0[b], foreign slot =
     // n_home + position in the foreign list; 0xFFFF past the cell's last face.
     int tile, n_tiles, tile_cap;
+    // tiles of the sides path (layout.h): n_tiles owned tiles, then the tiles of the inner halo ring;
+    // tile_info[12 b ..] = {c0, nc, h0, nh, nR, n0, ent_off, n_ent, n_own_l, n_slots, -, -}, tile_ent[5 e ..] = {f_start, count,
+    // section, slot_start, stage_start}; cf_stage = staging index of the cell's own side of each
+    // of its interfaces (pass G'); stage_cap = largest staging buffer of a tile (sides)
+    int n_tiles_all, stage_cap;
+    const int* tile_info;
+    const int* tile_ent;
+    const unsigned short* cf_stage;
     const int* home0;
     const int* foreign_off;
     const int* foreign;
@@ -116,7 +124,8 @@ struct FvArgs {
     S* grad;           // [(var*3 + comp)*cstride + cell]
     S* lim;            // [var*cstride + cell]
     S* flux;           // general path: [comp*fstride + face]
-    S* sides;          // sides path: [(face*2 + side)*6 + k], k = rho p T vx vy vz, side 0 = left
+    S* sideL;          // sides path: [face*6 + k], k = rho p T vx vy vz of the left state
+    S* sideR;          //             ... of the right state
     double* face_T;    // face_fs of the viscous path (finite_volume.h:128), real parts
     double* face_rho;
     Recon<S> rc;
@@ -924,7 +933,7 @@ IBIS_HD void tile_cell_body(const FvArgs<S>& A, int c, const S* st, long ss, lon
 //            gas_model.h:91-117), written as one 48-byte record (rho p T vx vy vz) per interface
 //            side.  The limiter's delta_2 = grad . (x_f - x_c) IS the reconstruction increment, so
 //            it is evaluated once.  Gradients and limiters never go to HBM.
-//   pass F'  flux_from_record + tile_cell_sum   one thread per interface of a tile: rotate,
+//   pass F'  flux_from_sides + tile_cell_sum   one thread per interface of a tile: rotate,
 //            flux calculator, rotate back, staged in shared memory; then one thread per cell:
 //            flux_surface_integral (finite_volume.cpp:221-256).  No gathers of cell data at all.
 // Same per-face arithmetic and in-cell summation order as the reference, hence the same bits.
@@ -964,18 +973,17 @@ IBIS_HD double bj_phi(const double* delta, const double& ui, const double& umin,
 }
 
 // The static per cell-face tables (WLS weights cf_w, offsets cf_d) as the kernel sees them:
-// element (j, k) of cell `idx` is base[(j*3 + k) * stride + idx].  On the device the block's slice
-// of both tables is staged in shared memory by bulk async copies (stride = block size, idx =
-// threadIdx.x); the host emulation points at the global tables (stride = cstride, idx = cell).
+// element (j, k) of cell `idx` is base[(j*3 + k) * stride + idx].  On the device the tile's slice
+// of both tables is staged in shared memory by bulk async copies (stride = tile size, idx = cell
+// within the tile); the host emulation points at the global tables (stride = cstride, idx = cell).
 template <int WSTRIDE>
 struct CellTables {
     const double* w;
     const double* d;
     long stride_rt;
     int idx;
-    IBIS_HD long stride() const { return WSTRIDE > 0 ? WSTRIDE : stride_rt; }
     // staged tables are re-read from shared memory at every use (volatile): keeping all 36
-    // entries in registers across the five variables is what made the kernel spill
+    // entries in registers across the variables is what made the first version spill
     IBIS_HD double W(int j, int k) const {
         if (WSTRIDE > 0) return *static_cast<const volatile double*>(w + (j * 3 + k) * WSTRIDE + idx);
         return w[(j * 3 + k) * stride_rt + idx];
@@ -986,41 +994,38 @@ struct CellTables {
     }
 };
 
-// everything pass G' gathers for one cell, issued before the tables are waited for
-template <int NF, typename S>
-struct CellGather {
+// Pass G' splits a cell between two threads: half 0 does rho and the second thermodynamic variable
+// (and closes the state: rho p T), half 1 the velocity components.  NVH = variables of the half.
+// What a half gathers, issued before the staged tables are waited for:
+template <int NF, int NVH, typename S>
+struct HalfGather {
     int nbr[NF];
-    long rec[NF];                 // record of this cell's side of interface j, -1 if the slot is absent
-    int other[NF];                // offset from rec[j] to the record of the far side
-    bool ghost[NF];
-    S ui[5], un[5][NF];
+    int stage[NF];                // staging index of this cell's side of interface j, -1 if absent
+    bool left[NF];                // this cell is the left cell of interface j
+    S ui[NVH], un[NVH][NF];
 };
 
-template <int DIM, int NF, typename S>
-IBIS_HD void grad_sides_gather(const FvArgs<S>& A, int c, CellGather<NF, S>& G) {
+template <int DIM, int NF, int HALF, typename S>
+IBIS_HD void grad_sides_gather(const FvArgs<S>& A, int c, HalfGather<NF, HALF == 0 ? 2 : 3, S>& G) {
     typedef mem<S> M;
     const GridDev& g = A.g;
     const long cs = g.cstride;
 #pragma unroll
     for (int j = 0; j < NF; j++) {
-        const int f = g.cf_face[j * cs + c];
+        const int st = g.cf_stage[j * cs + c];
         const int nb = g.cf_nbr[j * cs + c];
-        const int side = g.cf_out[j * cs + c] > 0 ? 0 : 1;     // outsign +1: this cell is the left cell
-        G.nbr[j] = f < 0 ? c : nb;                             // absent slot: contributes w * (u_i - u_i) = 0
-#ifdef IBIS_EXPERIMENT_COALESCED_SIDES   // timing experiment only (wrong addresses, coalesced stores)
-        G.rec[j] = f < 0 ? -1 : ((long)(c / 32) * 32 * 6 * MAXF + (long)j * 6 * 32 + (c % 32) * 2);
-#else
-        G.rec[j] = f < 0 ? -1 : (long)f * frec<S>::stride + side * 6;
-#endif
-        G.other[j] = side ? -6 : 6;
-        G.ghost[j] = f >= 0 && nb >= g.n_cells;
+        G.left[j] = g.cf_out[j * cs + c] > 0;                  // outsign +1: this cell is the left cell
+        G.stage[j] = st == 0xFFFF ? -1 : st;
+        G.nbr[j] = st == 0xFFFF ? c : nb;                      // absent slot: contributes w * (u_i - u_i) = 0
     }
+    constexpr int NVH = HALF == 0 ? 2 : 3;
 #pragma unroll
-    for (int v = 0; v < 5; v++) {
-        G.ui[v] = M::ldg(A.rc.val[v], c);
-        if (DIM == 2 && v == 4) continue;                      // vz: no gradient in 2-D
+    for (int v = 0; v < NVH; v++) {
+        const S* src = A.rc.val[HALF == 0 ? v : 2 + v];
+        G.ui[v] = M::ldg(src, c);
+        if (DIM == 2 && HALF == 1 && v == 2) continue;         // vz: no gradient in 2-D
 #pragma unroll
-        for (int j = 0; j < NF; j++) G.un[v][j] = M::ldg(A.rc.val[v], G.nbr[j]);
+        for (int j = 0; j < NF; j++) G.un[v][j] = M::ldg(src, G.nbr[j]);
     }
 }
 
@@ -1045,108 +1050,138 @@ IBIS_HD void var_to_faces(const S& ui, const S* un, const CellTables<WSTRIDE>& T
     for (int j = 0; j < NF; j++) r[j] = ui + phi * delta[j];   // linear_interpolate, convective_flux.cpp:243-255
 }
 
-template <int DIM, int NF, int WSTRIDE, typename S>
-IBIS_HD void grad_sides_compute(const FvArgs<S>& A, const CellGather<NF, S>& G, const CellTables<WSTRIDE>& T) {
+// stg: the tile's staging buffer of side states, [index * 6 + k]; nR / n_own_l: see layout.h (the far
+// side of a boundary interface sits at a fixed distance from the near side in the staging buffer)
+template <int DIM, int NF, int HALF, int WSTRIDE, typename S>
+IBIS_HD void grad_sides_compute(const FvArgs<S>& A, const HalfGather<NF, HALF == 0 ? 2 : 3, S>& G,
+                                const CellTables<WSTRIDE>& T, int nR, int n_own_l, S* stg) {
     typedef mem<S> M;
     const bool limit = A.limiter_on != 0;
     S r0[NF], r1[NF];
-    var_to_faces<DIM, NF>(G.ui[0], G.un[0], T, A.eps, limit, r0);
-    var_to_faces<DIM, NF>(G.ui[1], G.un[1], T, A.eps, limit, r1);
-    S Tj[NF];
+    if (HALF == 0) {
+        var_to_faces<DIM, NF>(G.ui[0], G.un[0], T, A.eps, limit, r0);
+        var_to_faces<DIM, NF>(G.ui[1], G.un[1], T, A.eps, limit, r1);
 #pragma unroll
-    for (int j = 0; j < NF; j++) {
-        S rho = r0[j], p = S(0.0), e = S(0.0);
-        Tj[j] = S(0.0);
-        if (A.thermo == THERMO_RHO_P) p = r1[j];
-        else if (A.thermo == THERMO_RHO_T) Tj[j] = r1[j];
-        else e = r1[j];
-        thermo_close(A.thermo, A.gas, rho, p, Tj[j], e);
-        if (G.rec[j] >= 0) M::store2(A.sides, G.rec[j], rho, p);
-    }
-    var_to_faces<DIM, NF>(G.ui[2], G.un[2], T, A.eps, limit, r0);
-#pragma unroll
-    for (int j = 0; j < NF; j++)
-#ifdef IBIS_EXPERIMENT_COALESCED_SIDES
-        if (G.rec[j] >= 0) M::store2(A.sides, G.rec[j] + 64, Tj[j], r0[j]);
-#else
-        if (G.rec[j] >= 0) M::store2(A.sides, G.rec[j] + 2, Tj[j], r0[j]);
-#endif
-    var_to_faces<DIM, NF>(G.ui[3], G.un[3], T, A.eps, limit, r0);
-    if (DIM == 3) {
-        var_to_faces<DIM, NF>(G.ui[4], G.un[4], T, A.eps, limit, r1);
+        for (int j = 0; j < NF; j++) {
+            S rho = r0[j], p = S(0.0), Tj = S(0.0), e = S(0.0);
+            if (A.thermo == THERMO_RHO_P) p = r1[j];
+            else if (A.thermo == THERMO_RHO_T) Tj = r1[j];
+            else e = r1[j];
+            thermo_close(A.thermo, A.gas, rho, p, Tj, e);
+            if (G.stage[j] >= 0) {
+                S* q = stg + (long)G.stage[j] * 6;
+                q[0] = rho;
+                q[1] = p;
+                q[2] = Tj;
+            }
+        }
     } else {
-        // 2-D: vz has no gradient (convective_flux.cpp:206-208) and a unit limiter: value copied
+        S r2[NF];
+        var_to_faces<DIM, NF>(G.ui[0], G.un[0], T, A.eps, limit, r0);
+        var_to_faces<DIM, NF>(G.ui[1], G.un[1], T, A.eps, limit, r1);
+        if (DIM == 3) {
+            var_to_faces<DIM, NF>(G.ui[2], G.un[2], T, A.eps, limit, r2);
+        } else {
+            // 2-D: vz has no gradient (convective_flux.cpp:206-208) and a unit limiter: value copied
 #pragma unroll
-        for (int j = 0; j < NF; j++) r1[j] = G.ui[4];
+            for (int j = 0; j < NF; j++) r2[j] = G.ui[2];
+        }
+#pragma unroll
+        for (int j = 0; j < NF; j++)
+            if (G.stage[j] >= 0) {
+                S* q = stg + (long)G.stage[j] * 6;
+                q[3] = r0[j];
+                q[4] = r1[j];
+                q[5] = r2[j];
+            }
     }
-#pragma unroll
-    for (int j = 0; j < NF; j++)
-#ifdef IBIS_EXPERIMENT_COALESCED_SIDES
-        if (G.rec[j] >= 0) M::store2(A.sides, G.rec[j] + 128, r0[j], r1[j]);
-#else
-        if (G.rec[j] >= 0) M::store2(A.sides, G.rec[j] + 4, r0[j], r1[j]);
-#endif
     // the far side of a boundary interface is the ghost cell itself: zero gradient, unit limiter
     // (convective_flux.cpp:281-300), i.e. its values, closed thermodynamically like any other side
 #pragma unroll
     for (int j = 0; j < NF; j++) {
-        if (!G.ghost[j]) continue;
+        if (G.stage[j] < 0 || G.nbr[j] < A.g.n_cells) continue;
         const int nb = G.nbr[j];
-        S rho = M::load(A.rc.val[0], nb), p = S(0.0), Tg = S(0.0), e = S(0.0);
-        const S th2 = M::load(A.rc.val[1], nb);
-        if (A.thermo == THERMO_RHO_P) p = th2;
-        else if (A.thermo == THERMO_RHO_T) Tg = th2;
-        else e = th2;
-        thermo_close(A.thermo, A.gas, rho, p, Tg, e);
-        const long ro = G.rec[j] + G.other[j];
-        M::store2(A.sides, ro, rho, p);
-        M::store2(A.sides, ro + 2, Tg, M::load(A.rc.val[2], nb));
-        M::store2(A.sides, ro + 4, M::load(A.rc.val[3], nb), M::load(A.rc.val[4], nb));
+        const int far_idx = G.left[j] ? n_own_l + G.stage[j] + nR : G.stage[j] - n_own_l - nR;
+        S* q = stg + (long)far_idx * 6;
+        if (HALF == 0) {
+            S rho = M::load(A.rc.val[0], nb), p = S(0.0), Tg = S(0.0), e = S(0.0);
+            const S th2 = M::load(A.rc.val[1], nb);
+            if (A.thermo == THERMO_RHO_P) p = th2;
+            else if (A.thermo == THERMO_RHO_T) Tg = th2;
+            else e = th2;
+            thermo_close(A.thermo, A.gas, rho, p, Tg, e);
+            q[0] = rho;
+            q[1] = p;
+            q[2] = Tg;
+        } else {
+            q[3] = M::load(A.rc.val[2], nb);
+            q[4] = M::load(A.rc.val[3], nb);
+            q[5] = M::load(A.rc.val[4], nb);
+        }
     }
 }
 
-// host emulation / reference form: one call per cell straight from the global tables
-template <int DIM, int NF, typename S>
-IBIS_HD void grad_sides_body(const FvArgs<S>& A, int c) {
-    CellGather<NF, S> G;
-    grad_sides_gather<DIM, NF>(A, c, G);
+// host emulation form: one call per (cell, half) straight from the global tables
+template <int DIM, int NF, int HALF, typename S>
+IBIS_HD void grad_sides_body(const FvArgs<S>& A, int c, int nR, int n_own_l, S* stg) {
+    HalfGather<NF, HALF == 0 ? 2 : 3, S> G;
+    grad_sides_gather<DIM, NF, HALF>(A, c, G);
     CellTables<0> T;
     T.w = A.g.cf_w;
     T.d = A.g.cf_d;
     T.stride_rt = A.g.cstride;
     T.idx = c;
-    grad_sides_compute<DIM, NF, 0>(A, G, T);
+    grad_sides_compute<DIM, NF, HALF, 0>(A, G, T, nR, n_own_l, stg);
 }
 
-// static part of the interface records (setup): the frame and area of interface f
-template <typename S>
-IBIS_HD void frec_geom_body(const GridDev& g, S* sides, int f) {
-    double* q = reinterpret_cast<double*>(sides + (long)f * frec<S>::stride + 12);
-    const long fs_ = g.fstride;
-    for (int d = 0; d < 3; d++) {
-        q[d] = g.f_n[d * fs_ + f];
-        q[3 + d] = g.f_t1[d * fs_ + f];
-        q[6 + d] = g.f_t2[d * fs_ + f];
+// The bulk transfers of a tile (layout.h).  Transfer q of tile b moves `count` interfaces starting
+// at interface f0; in the staging buffer of pass G' they start at `stage`, in the flux slots of pass F'
+// at `slot`.  Stores (pass G'): q = 0 home left range, 1 home right range, 2 + e entry e.
+struct TileXfer {
+    int f0, count, stage, slot;
+    bool left;                    // stores: which array the tile's own sides go to
+};
+IBIS_HD int tile_n_own_left(const GridDev& g, int b) { return g.tile_info[TILE_INFO * b + 8]; }
+IBIS_HD TileXfer tile_store_xfer(const GridDev& g, int b, int q, int n_own_l) {
+    const int* ti = g.tile_info + TILE_INFO * b;
+    TileXfer x;
+    if (q == 0) { x.f0 = ti[2] + ti[4]; x.count = ti[3] - ti[4]; x.stage = 0; x.slot = ti[4]; x.left = true; }
+    else if (q == 1) { x.f0 = ti[2]; x.count = ti[4] + ti[5]; x.stage = n_own_l; x.slot = 0; x.left = false; }
+    else {
+        const int* te = g.tile_ent + 5 * (ti[6] + q - 2);
+        x.f0 = te[0]; x.count = te[1]; x.stage = te[4]; x.slot = te[3]; x.left = te[2] == 0;
     }
-    q[9] = g.f_area[f];
+    return x;
+}
+// loads (pass F'): q = 0 the home range, 1 + e entry e; each moves left sides, right sides and frames
+IBIS_HD TileXfer tile_load_xfer(const GridDev& g, int b, int q) {
+    const int* ti = g.tile_info + TILE_INFO * b;
+    TileXfer x;
+    x.stage = 0;
+    x.left = true;
+    if (q == 0) { x.f0 = ti[2]; x.count = ti[3]; x.slot = 0; }
+    else {
+        const int* te = g.tile_ent + 5 * (ti[6] + q - 1);
+        x.f0 = te[0]; x.count = te[1]; x.slot = te[3];
+    }
+    return x;
 }
 
-// pass F', one interface: rec = its record (shared memory on the device, the global array in the
-// host emulation); out[k * ks], k = 0..4 <- flux in the global frame, k = 5 <- area.  out may
-// alias the left side of rec: everything is read before anything is written.
+// pass F', one interface: L, R = its side states, gm = its frame (shared memory on the device,
+// the global arrays in the host emulation); out[k * ks], k = 0..4 <- flux in the global frame,
+// k = 5 <- area.  out may alias L: everything is read before anything is written.
 template <int DIM, int FLUX, typename S>
-IBIS_HD void flux_from_record(const FvArgs<S>& A, const S* rec, S* out, long ks) {
+IBIS_HD void flux_from_sides(const FvArgs<S>& A, const S* Ls, const S* Rs, const double* gm, S* out, long ks) {
     typedef mem<S> M;
     Side<S> L, R_;
-    M::ld2(rec, 0, L.rho, L.p);
-    M::ld2(rec, 2, L.T, L.u);
-    M::ld2(rec, 4, L.v, L.w);
-    M::ld2(rec, 6, R_.rho, R_.p);
-    M::ld2(rec, 8, R_.T, R_.u);
-    M::ld2(rec, 10, R_.v, R_.w);
+    M::ld2(Ls, 0, L.rho, L.p);
+    M::ld2(Ls, 2, L.T, L.u);
+    M::ld2(Ls, 4, L.v, L.w);
+    M::ld2(Rs, 0, R_.rho, R_.p);
+    M::ld2(Rs, 2, R_.T, R_.u);
+    M::ld2(Rs, 4, R_.v, R_.w);
     L.e = S(0.0);
     R_.e = S(0.0);
-    const double* gm = reinterpret_cast<const double*>(rec + 12);
     double nx, ny, nz, t1x, t1y, t1z, t2x, t2y, t2z, area;
     mem<double>::ld2(gm, 0, nx, ny);
     mem<double>::ld2(gm, 2, nz, t1x);

@@ -27,17 +27,26 @@
 #define IBIS_F_MINB 2        // min resident blocks per SM of pass F (register cap)
 #endif
 
-#ifndef IBIS_GS_BLOCK
-#define IBIS_GS_BLOCK 128    // threads per block of pass G' (gradients + limiters + interface sides)
-#endif
 #ifndef IBIS_GS_MINB
-#define IBIS_GS_MINB 4
+#define IBIS_GS_MINB 2       // min resident blocks per SM of pass G'
+#endif
+#ifndef IBIS_GS_TPC
+#define IBIS_GS_TPC 2        // threads per cell of pass G' (1 | 2)
+#endif
+#ifndef IBIS_GS_STAGE
+#define IBIS_GS_STAGE 1      // stage the static cell tables in shared memory by TMA
+#endif
+#ifndef IBIS_COPY_TMA
+#define IBIS_COPY_TMA 1      // 1: tile transfers as TMA bulk copies; 0: 16-byte cp.async / st.global by all threads
+#endif
+#ifndef IBIS_F2_PERSIST
+#define IBIS_F2_PERSIST 0    // 1: persistent blocks with a two-stage TMA pipeline; 0: one block per tile
 #endif
 #ifndef IBIS_F2_THREADS
 #define IBIS_F2_THREADS 256  // threads per block of pass F' (>= tile size)
 #endif
 #ifndef IBIS_F2_MINB
-#define IBIS_F2_MINB 2
+#define IBIS_F2_MINB 2       // resident blocks per SM of pass F'
 #endif
 
 namespace ib {
@@ -127,92 +136,254 @@ __global__ void __launch_bounds__(IBIS_F_MAXT, IBIS_F_MINB) k_residual_tile(cons
     if (has_cell) tile_cell_body<DIM>(A, c, st, 1, A.g.tile_cap);
 }
 
-// pass G' of the sides path: one thread per cell with a face list (owned + inner halo ring).
-// The block's slice of the static tables (WLS weights, face offsets: 36 KB for hexes) arrives in
-// shared memory by bulk async copies (TMA) while the threads issue their neighbour gathers, so the
-// only registers tied up while waiting on HBM are the gathered values themselves.
-template <int DIM, int NF, typename S>
-__global__ void __launch_bounds__(IBIS_GS_BLOCK, IBIS_GS_MINB) k_grad_sides(const FvArgs<S> A) {
-    constexpr int B = IBIS_GS_BLOCK;
+// block-cooperative copies of a contiguous range (bytes: multiple of 16, both ends 16-byte aligned)
+__device__ __forceinline__ void coop_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes) {
+    for (uint32_t o = threadIdx.x * 16u; o < bytes; o += blockDim.x * 16u)
+        ac::cp_async_16(static_cast<unsigned char*>(dst_smem) + o, static_cast<const unsigned char*>(src_gmem) + o);
+}
+__device__ __forceinline__ void coop_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+    for (uint32_t o = threadIdx.x * 16u; o < bytes; o += blockDim.x * 16u)
+        *reinterpret_cast<double2*>(static_cast<unsigned char*>(dst_gmem) + o) =
+            *reinterpret_cast<const double2*>(static_cast<const unsigned char*>(src_smem) + o);
+}
+
+// pass G' of the sides path: one block per tile (owned tiles, then the tiles of the inner halo
+// ring), TPC threads per cell (fv_bodies.h: grad_sides_*; TPC = 2: half 0 = thermodynamic variables,
+// half 1 = velocity).  Data movement of a block:
+//   in   (STAGE) the tile's slice of the static tables (WLS weights, face offsets; 36 KB for 128
+//        hexes): bulk async copies (TMA) into shared memory, in flight while the threads gather;
+//   out  the side states of the tile go to a staging buffer in shared memory and leave as a handful
+//        of bulk async stores (TMA): the tile-owned interface numbering (layout.h) makes the sides a
+//        tile produces contiguous ranges of the global side arrays.
+template <int DIM, int NF, int TS, int TPC, bool STAGE, typename S>
+__global__ void __launch_bounds__(TPC * TS, IBIS_GS_MINB) k_grad_sides(const FvArgs<S> A) {
     constexpr int NT = NF * 3;                                  // arrays per table
-    __shared__ __align__(128) double tab[2 * NT * B];
-    __shared__ uint64_t bar;
-    const int c0 = blockIdx.x * B;
-    const int c = c0 + threadIdx.x;
-    if (threadIdx.x == 0) {
-        ac::mbar_init(&bar, 1);
-        ac::fence_barrier_init();
-        ac::mbar_arrive_expect_tx(&bar, 2 * NT * B * (uint32_t)sizeof(double));
-    }
-    __syncthreads();
-    if (threadIdx.x < 2 * NT) {
-        const int a = threadIdx.x % NT;
-        const double* src = (threadIdx.x < NT ? A.g.cf_w : A.g.cf_d) + (long)a * A.g.cstride + c0;
-        ac::bulk_g2s(tab + threadIdx.x * B, src, B * (uint32_t)sizeof(double), &bar);
-    }
-    CellGather<NF, S> G;
-    const bool active = c < A.g.n_grad;
-    if (active) grad_sides_gather<DIM, NF>(A, c, G);
-    ac::mbar_wait(&bar, 0);
-    if (active) {
-        CellTables<B> T;
-        T.w = tab;
-        T.d = tab + NT * B;
-        T.stride_rt = B;
-        T.idx = threadIdx.x;
-        grad_sides_compute<DIM, NF, B>(A, G, T);
-    }
-}
-
-template <typename S>
-__global__ void __launch_bounds__(256) k_frec_geom(const GridDev g, S* sides) {
-    const int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f < g.n_faces) frec_geom_body(g, sides, f);
-}
-
-// pass F' of the sides path: blockDim.x >= A.g.tile; dynamic shared memory = tile_cap records.
-// The records of the tile's home interfaces are one contiguous range: one bulk async copy (TMA);
-// the foreign ones (homed in an earlier tile) are gathered with 16-byte cp.async.  Each flux
-// overwrites the left side of its own record; then one thread per cell sums its faces.
-template <int DIM, int FLUX, typename S>
-__global__ void __launch_bounds__(IBIS_F2_THREADS, IBIS_F2_MINB) k_flux_tile(const FvArgs<S> A) {
+    constexpr int WS = STAGE ? TS : 0;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bar;
-    S* st = reinterpret_cast<S*>(smem_raw);
-    constexpr int RS = frec<S>::stride, RB = frec<S>::bytes;
+    double* tab = reinterpret_cast<double*>(smem_raw);          // [2 * NT][TS] when STAGE
+    S* stg = reinterpret_cast<S*>(smem_raw + (STAGE ? (size_t)2 * NT * TS * sizeof(double) : 0));
     const GridDev& g = A.g;
     const int tile = blockIdx.x;
-    const int h0 = g.home0[tile], nh = g.home0[tile + 1] - h0;
-    const int fo = g.foreign_off[tile], n = nh + (g.foreign_off[tile + 1] - fo);
+    const int* ti = g.tile_info + TILE_INFO * tile;
+    const int c0 = ti[0], nc = ti[1], nR = ti[4], n_ent = ti[7], n_own_l = ti[8];
+    const int lane_cell = threadIdx.x % TS, half = threadIdx.x / TS;
+    const int c = c0 + lane_cell;
+    const bool bulk_in = IBIS_COPY_TMA && STAGE && (c0 & 1) == 0;   // 16-byte aligned table slices
+    const bool async_in = !IBIS_COPY_TMA && STAGE && (c0 & 1) == 0;
+    if (STAGE) {
+        if (async_in) {
+            for (int arr = 0; arr < 2 * NT; arr++) {
+                const int a = arr % NT;
+                coop_g2s(tab + arr * TS, (arr < NT ? g.cf_w : g.cf_d) + (long)a * g.cstride + c0, TS * (uint32_t)sizeof(double));
+            }
+        } else if (bulk_in) {
+            if (threadIdx.x == 0) {
+                ac::mbar_init(&bar, 2 * NT);
+                ac::fence_barrier_init();
+            }
+            __syncthreads();
+            if (threadIdx.x < 2 * NT) {
+                const int a = threadIdx.x % NT;
+                const double* src = (threadIdx.x < NT ? g.cf_w : g.cf_d) + (long)a * g.cstride + c0;
+                ac::mbar_arrive_expect_tx(&bar, TS * (uint32_t)sizeof(double));
+                ac::bulk_g2s(tab + threadIdx.x * TS, src, TS * (uint32_t)sizeof(double), &bar);
+            }
+        } else {
+            for (int q = threadIdx.x; q < 2 * NT * TS; q += blockDim.x) {
+                const int arr = q / TS, t = q % TS, a = arr % NT;
+                tab[q] = (arr < NT ? g.cf_w : g.cf_d)[(long)a * g.cstride + c0 + t];
+            }
+            __syncthreads();
+        }
+    }
+    const bool active = lane_cell < nc;
+    CellTables<WS> T;
+    T.w = STAGE ? tab : g.cf_w;
+    T.d = STAGE ? tab + NT * TS : g.cf_d;
+    T.stride_rt = STAGE ? TS : g.cstride;
+    T.idx = STAGE ? lane_cell : c;
+    if (TPC == 1) {
+        HalfGather<NF, 2, S> G0;
+        HalfGather<NF, 3, S> G1;
+        if (active) {
+            grad_sides_gather<DIM, NF, 0>(A, c, G0);
+            grad_sides_gather<DIM, NF, 1>(A, c, G1);
+        }
+        if (bulk_in) ac::mbar_wait(&bar, 0);
+        if (async_in) { ac::cp_async_wait_all(); __syncthreads(); }
+        if (active) {
+            grad_sides_compute<DIM, NF, 0, WS>(A, G0, T, nR, n_own_l, stg);
+            grad_sides_compute<DIM, NF, 1, WS>(A, G1, T, nR, n_own_l, stg);
+        }
+    } else if (half == 0) {
+        HalfGather<NF, 2, S> G;
+        if (active) grad_sides_gather<DIM, NF, 0>(A, c, G);
+        if (bulk_in) ac::mbar_wait(&bar, 0);
+        if (async_in) { ac::cp_async_wait_all(); __syncthreads(); }
+        if (active) grad_sides_compute<DIM, NF, 0, WS>(A, G, T, nR, n_own_l, stg);
+    } else {
+        HalfGather<NF, 3, S> G;
+        if (active) grad_sides_gather<DIM, NF, 1>(A, c, G);
+        if (bulk_in) ac::mbar_wait(&bar, 0);
+        if (async_in) { ac::cp_async_wait_all(); __syncthreads(); }
+        if (active) grad_sides_compute<DIM, NF, 1, WS>(A, G, T, nR, n_own_l, stg);
+    }
+#if IBIS_COPY_TMA
+    ac::fence_proxy_async();                                    // staging writes -> visible to the TMA unit
+    __syncthreads();
+    if (threadIdx.x < 2 + n_ent) {
+        const TileXfer x = tile_store_xfer(g, tile, threadIdx.x, n_own_l);
+        if (x.count > 0) {
+            S* dst = (x.left ? A.sideL : A.sideR) + (long)x.f0 * 6;
+            ac::bulk_s2g(dst, stg + (long)x.stage * 6, (uint32_t)x.count * 6 * (uint32_t)sizeof(S));
+        }
+        ac::bulk_commit_wait_read();                            // shared memory must outlive the reads
+    }
+#else
+    __syncthreads();
+    for (int q = 0; q < 2 + n_ent; q++) {
+        const TileXfer x = tile_store_xfer(g, tile, q, n_own_l);
+        S* dst = (x.left ? A.sideL : A.sideR) + (long)x.f0 * 6;
+        coop_s2g(dst, stg + (long)x.stage * 6, (uint32_t)x.count * 6 * (uint32_t)sizeof(S));
+    }
+#endif
+}
+
+// pass F' of the sides path: PERSISTENT blocks (one or two per SM) walk the owned tiles with a
+// two-stage shared-memory pipeline: while the block computes the fluxes of tile k from stage k & 1,
+// the TMA unit fills the other stage with tile k + gridDim.x -- left states, right states and frames
+// of its interfaces, all as bulk async copies of contiguous ranges (layout.h).  Each flux
+// overwrites the left state of its own interface; then one thread per cell sums its faces
+// (owner computes, no atomics).  The compute phases never wait on HBM.
+template <typename S>
+__device__ __forceinline__ void flux_tile_issue(const FvArgs<S>& A, int tile, S* stL, S* stR, double* stG,
+                                                uint64_t* bar) {
+    // called by warp 0: lane 0 arms the barrier with the byte count, lanes issue the copies
+    const GridDev& g = A.g;
+    const int* ti = g.tile_info + TILE_INFO * tile;
+    const int nh = ti[3], n_ent = ti[7], n_slots = ti[9];
+    if (threadIdx.x == 0) ac::mbar_arrive_expect_tx(bar, (uint32_t)n_slots * (uint32_t)frec<S>::bytes);
+    __syncwarp();
+    const int n_x = 1 + n_ent;
+    for (int q = threadIdx.x; q < 3 * n_x; q += 32) {
+        const TileXfer x = tile_load_xfer(g, tile, q / 3);
+        if (x.count <= 0) continue;
+        const int which = q % 3;
+        const uint32_t bytes = (uint32_t)x.count * (which == 2 ? 80u : 6u * (uint32_t)sizeof(S));
+        if (which == 0) ac::bulk_g2s(stL + (long)x.slot * 6, A.sideL + (long)x.f0 * 6, bytes, bar);
+        else if (which == 1) ac::bulk_g2s(stR + (long)x.slot * 6, A.sideR + (long)x.f0 * 6, bytes, bar);
+        else ac::bulk_g2s(stG + (long)x.slot * 10, g.f_geom + (long)x.f0 * 10, bytes, bar);
+    }
+    (void)nh;
+}
+
+#if IBIS_F2_PERSIST
+template <int DIM, int FLUX, typename S>
+__global__ void __launch_bounds__(IBIS_F2_THREADS, IBIS_F2_MINB) k_flux_tile(const FvArgs<S> A, const int n_stages) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t bar[2];
+    const GridDev& g = A.g;
+    const int cap = g.tile_cap;
+    const size_t stage_bytes = (size_t)cap * frec<S>::bytes;
+    if (threadIdx.x == 0) {
+        ac::mbar_init(&bar[0], 1);
+        ac::mbar_init(&bar[1], 1);
+        ac::fence_barrier_init();
+    }
+    __syncthreads();
+    auto stage_L = [&](int st) { return reinterpret_cast<S*>(smem_raw + (size_t)st * stage_bytes); };
+    auto stage_R = [&](int st) { return stage_L(st) + (size_t)cap * 6; };
+    auto stage_G = [&](int st) { return reinterpret_cast<double*>(stage_R(st) + (size_t)cap * 6); };
+    if (n_stages == 2 && threadIdx.x < 32 && (int)blockIdx.x < g.n_tiles)
+        flux_tile_issue<S>(A, blockIdx.x, stage_L(0), stage_R(0), stage_G(0), &bar[0]);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, it++) {
+        const int st = n_stages == 2 ? (it & 1) : 0;
+        const int next = tile + gridDim.x;
+        // two stages: the other stage was last read in iteration it - 1, which ended with
+        // __syncthreads; one stage (tiles too large for two): fetch this tile now
+        if (n_stages == 2) {
+            if (threadIdx.x < 32 && next < g.n_tiles)
+                flux_tile_issue<S>(A, next, stage_L(st ^ 1), stage_R(st ^ 1), stage_G(st ^ 1), &bar[st ^ 1]);
+        } else if (threadIdx.x < 32) {
+            flux_tile_issue<S>(A, tile, stage_L(0), stage_R(0), stage_G(0), &bar[0]);
+        }
+        const int* ti = g.tile_info + TILE_INFO * tile;
+        const int c0 = ti[0], nc = ti[1], n = ti[9];
+        const int c = c0 + threadIdx.x;
+        const bool has_cell = threadIdx.x < nc;
+        CellFaces CF;
+        if (has_cell) tile_cell_load(g, c, CF);
+        S* stL = stage_L(st);
+        S* stR = stage_R(st);
+        double* stG = stage_G(st);
+        ac::mbar_wait(&bar[st], (uint32_t)(n_stages == 2 ? ((it >> 1) & 1) : (it & 1)));
+        for (int s = threadIdx.x; s < n; s += blockDim.x)
+            flux_from_sides<DIM, FLUX>(A, stL + (long)s * 6, stR + (long)s * 6, stG + (long)s * 10, stL + (long)s * 6, 1);
+        __syncthreads();
+        if (has_cell) tile_cell_sum<DIM>(A, c, CF, stL, 6, 1);
+        ac::fence_proxy_async();           // generic accesses of this stage before the TMA refills it
+        __syncthreads();
+    }
+}
+#else
+// one block per owned tile, one pipeline stage: several resident blocks per SM overlap each other's
+// fetches (measured faster than the persistent two-stage form at the shared-memory footprint of
+// 128-cell tiles, profiles/r01_summary.md)
+// the same transfers with 16-byte cp.async issued by every thread of the block
+template <typename S>
+__device__ __forceinline__ void flux_tile_issue_coop(const FvArgs<S>& A, int tile, S* stL, S* stR, double* stG) {
+    const GridDev& g = A.g;
+    const int n_x = 1 + g.tile_info[TILE_INFO * tile + 7];
+    for (int q = 0; q < n_x; q++) {
+        const TileXfer x = tile_load_xfer(g, tile, q);
+        coop_g2s(stL + (long)x.slot * 6, A.sideL + (long)x.f0 * 6, (uint32_t)x.count * 6u * (uint32_t)sizeof(S));
+        coop_g2s(stR + (long)x.slot * 6, A.sideR + (long)x.f0 * 6, (uint32_t)x.count * 6u * (uint32_t)sizeof(S));
+        coop_g2s(stG + (long)x.slot * 10, g.f_geom + (long)x.f0 * 10, (uint32_t)x.count * 80u);
+    }
+}
+
+template <int DIM, int FLUX, typename S>
+__global__ void __launch_bounds__(IBIS_F2_THREADS, IBIS_F2_MINB) k_flux_tile(const FvArgs<S> A, const int n_stages) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t bar;
+    const GridDev& g = A.g;
+    const int cap = g.tile_cap;
+    S* stL = reinterpret_cast<S*>(smem_raw);
+    S* stR = stL + (size_t)cap * 6;
+    double* stG = reinterpret_cast<double*>(stR + (size_t)cap * 6);
+    const int tile = blockIdx.x;
+#if IBIS_COPY_TMA
     if (threadIdx.x == 0) {
         ac::mbar_init(&bar, 1);
         ac::fence_barrier_init();
-        if (nh > 0) {
-            ac::mbar_arrive_expect_tx(&bar, (uint32_t)nh * RB);
-            ac::bulk_g2s(st, A.sides + (long)h0 * RS, (uint32_t)nh * RB, &bar);
-        }
-    }
-    for (int s = nh + threadIdx.x; s < n; s += blockDim.x) {
-        const int f = g.foreign[fo + (s - nh)];
-        const unsigned char* src = reinterpret_cast<const unsigned char*>(A.sides + (long)f * RS);
-        unsigned char* dst = reinterpret_cast<unsigned char*>(st + (long)s * RS);
-#pragma unroll
-        for (int q = 0; q < RB / 16; q++) ac::cp_async_16(dst + q * 16, src + q * 16);
-    }
-    const int c = tile * g.tile + threadIdx.x;
-    const bool has_cell = threadIdx.x < g.tile && c < g.n_owned;
-    CellFaces CF;
-    if (has_cell) tile_cell_load(g, c, CF);
-    ac::cp_async_wait_all();
-    __syncthreads();                       // barrier initialised; everybody's cp.async data landed
-    if (nh > 0) ac::mbar_wait(&bar, 0);
-    for (int s = threadIdx.x; s < n; s += blockDim.x) {
-        S* rec = st + (long)s * RS;
-        flux_from_record<DIM, FLUX>(A, rec, rec, 1);
     }
     __syncthreads();
-    if (has_cell) tile_cell_sum<DIM>(A, c, CF, st, RS, 1);
+    if (threadIdx.x < 32) flux_tile_issue<S>(A, tile, stL, stR, stG, &bar);
+#else
+    flux_tile_issue_coop<S>(A, tile, stL, stR, stG);
+#endif
+    const int* ti = g.tile_info + TILE_INFO * tile;
+    const int c0 = ti[0], nc = ti[1], n = ti[9];
+    const int c = c0 + threadIdx.x;
+    const bool has_cell = threadIdx.x < nc;
+    CellFaces CF;
+    if (has_cell) tile_cell_load(g, c, CF);
+#if IBIS_COPY_TMA
+    ac::mbar_wait(&bar, 0);
+#else
+    ac::cp_async_wait_all();
+    __syncthreads();
+    (void)bar;
+#endif
+    for (int s = threadIdx.x; s < n; s += blockDim.x)
+        flux_from_sides<DIM, FLUX>(A, stL + (long)s * 6, stR + (long)s * 6, stG + (long)s * 10, stL + (long)s * 6, 1);
+    __syncthreads();
+    if (has_cell) tile_cell_sum<DIM>(A, c, CF, stL, 6, 1);
+    (void)n_stages;
 }
+#endif
 
 template <int DIM, int FLUX, bool O2, typename S>
 __global__ void __launch_bounds__(128) k_face_flux(const FvArgs<S> A) {
@@ -402,23 +573,42 @@ void launch_residual(ibis_b200_ctx* c, const FvArgs<S>& A) {
 template void launch_residual<double>(ibis_b200_ctx*, const FvArgs<double>&);
 template void launch_residual<dual>(ibis_b200_ctx*, const FvArgs<dual>&);
 
-template <int DIM, typename S>
-static void launch_grad_sides_nf(ibis_b200_ctx* c, const FvArgs<S>& A) {
-    const int nb = nblocks(A.g.n_grad, IBIS_GS_BLOCK);
-    switch (A.g.max_faces) {
-        case 6: k_grad_sides<DIM, 6, S><<<nb, IBIS_GS_BLOCK, 0, c->stream>>>(A); break;
-        case 5: k_grad_sides<DIM, 5, S><<<nb, IBIS_GS_BLOCK, 0, c->stream>>>(A); break;
-        case 4: k_grad_sides<DIM, 4, S><<<nb, IBIS_GS_BLOCK, 0, c->stream>>>(A); break;
-        default: k_grad_sides<DIM, 3, S><<<nb, IBIS_GS_BLOCK, 0, c->stream>>>(A); break;
+template <typename K, typename S, typename... Extra>
+static void launch_tiles(ibis_b200_ctx* c, K kernel, int grid, int bs, size_t smem, const FvArgs<S>& A, Extra... extra) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess && c->last_error.empty())
+        c->last_error = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e);
+    kernel<<<grid, bs, smem, c->stream>>>(A, extra...);
+}
+
+template <int DIM, int TS, typename S>
+static void launch_grad_sides_ts(ibis_b200_ctx* c, const FvArgs<S>& A) {
+    constexpr int TPC = IBIS_GS_TPC;
+    constexpr bool STAGE = IBIS_GS_STAGE != 0;
+    const int nf = A.g.max_faces < 3 ? 3 : A.g.max_faces;
+    const size_t smem = (STAGE ? (size_t)2 * nf * 3 * TS * sizeof(double) : 0) + (size_t)A.g.stage_cap * 6 * sizeof(S);
+    const int grid = A.g.n_tiles_all;
+    switch (nf) {
+        case 6: launch_tiles(c, k_grad_sides<DIM, 6, TS, TPC, STAGE, S>, grid, TPC * TS, smem, A); break;
+        case 5: launch_tiles(c, k_grad_sides<DIM, 5, TS, TPC, STAGE, S>, grid, TPC * TS, smem, A); break;
+        case 4: launch_tiles(c, k_grad_sides<DIM, 4, TS, TPC, STAGE, S>, grid, TPC * TS, smem, A); break;
+        default: launch_tiles(c, k_grad_sides<DIM, 3, TS, TPC, STAGE, S>, grid, TPC * TS, smem, A); break;
     }
 }
 
 template <typename S>
 void launch_grad_sides(ibis_b200_ctx* c, const FvArgs<S>& A) {
-    if (A.g.n_grad == 0) return;
+    if (A.g.n_tiles_all == 0) return;
     prof_begin(c, 0);
-    if (A.g.dim == 3) launch_grad_sides_nf<3, S>(c, A);
-    else launch_grad_sides_nf<2, S>(c, A);
+    if (A.g.dim == 3) {
+        if (A.g.tile == 64) launch_grad_sides_ts<3, 64, S>(c, A);
+        else if (A.g.tile == 128) launch_grad_sides_ts<3, 128, S>(c, A);
+        else launch_grad_sides_ts<3, 256, S>(c, A);
+    } else {
+        if (A.g.tile == 64) launch_grad_sides_ts<2, 64, S>(c, A);
+        else if (A.g.tile == 128) launch_grad_sides_ts<2, 128, S>(c, A);
+        else launch_grad_sides_ts<2, 256, S>(c, A);
+    }
     prof_end(c, 0);
     CUDA_CHECK_LAUNCH(c);
 }
@@ -426,37 +616,41 @@ template void launch_grad_sides<double>(ibis_b200_ctx*, const FvArgs<double>&);
 template void launch_grad_sides<dual>(ibis_b200_ctx*, const FvArgs<dual>&);
 
 template <int DIM, typename S>
-static void launch_flux_tile_dim(ibis_b200_ctx* c, const FvArgs<S>& A, int bs, size_t smem) {
+static void launch_flux_tile_dim(ibis_b200_ctx* c, const FvArgs<S>& A, int grid, int bs, size_t smem, int n_stages) {
     switch (c->cfg.flux_calculator) {
-        case FLUX_HANEL: launch_one(c, k_flux_tile<DIM, FLUX_HANEL, S>, A.g.n_tiles, bs, smem, A); break;
-        case FLUX_AUSMDV: launch_one(c, k_flux_tile<DIM, FLUX_AUSMDV, S>, A.g.n_tiles, bs, smem, A); break;
-        case FLUX_LDFSS2: launch_one(c, k_flux_tile<DIM, FLUX_LDFSS2, S>, A.g.n_tiles, bs, smem, A); break;
-        default: launch_one(c, k_flux_tile<DIM, FLUX_RUSANOV, S>, A.g.n_tiles, bs, smem, A); break;
+        case FLUX_HANEL: launch_tiles(c, k_flux_tile<DIM, FLUX_HANEL, S>, grid, bs, smem, A, n_stages); break;
+        case FLUX_AUSMDV: launch_tiles(c, k_flux_tile<DIM, FLUX_AUSMDV, S>, grid, bs, smem, A, n_stages); break;
+        case FLUX_LDFSS2: launch_tiles(c, k_flux_tile<DIM, FLUX_LDFSS2, S>, grid, bs, smem, A, n_stages); break;
+        default: launch_tiles(c, k_flux_tile<DIM, FLUX_RUSANOV, S>, grid, bs, smem, A, n_stages); break;
     }
 }
 
 template <typename S>
 void launch_flux_tile(ibis_b200_ctx* c, const FvArgs<S>& A) {
     if (A.g.n_tiles == 0) return;
-    const size_t smem = (size_t)A.g.tile_cap * frec<S>::bytes;
+    const size_t stage = (size_t)A.g.tile_cap * frec<S>::bytes;
     const int bs = A.g.tile > IBIS_F2_THREADS ? A.g.tile : IBIS_F2_THREADS;
+#if IBIS_F2_PERSIST
+    // persistent blocks, two pipeline stages when they fit
+    const int n_stages = 2 * stage <= 226 * 1024 ? 2 : 1;
+    const size_t smem = n_stages * stage;
+    int per_sm = (int)((227 * 1024) / (smem + 1024));
+    per_sm = per_sm < 1 ? 1 : (per_sm > IBIS_F2_MINB ? IBIS_F2_MINB : per_sm);
+    int grid = c->n_sm * per_sm;
+    if (grid > A.g.n_tiles) grid = A.g.n_tiles;
+#else
+    const int n_stages = 1;
+    const size_t smem = stage;
+    const int grid = A.g.n_tiles;
+#endif
     prof_begin(c, 1);
-    if (A.g.dim == 3) launch_flux_tile_dim<3, S>(c, A, bs, smem);
-    else launch_flux_tile_dim<2, S>(c, A, bs, smem);
+    if (A.g.dim == 3) launch_flux_tile_dim<3, S>(c, A, grid, bs, smem, n_stages);
+    else launch_flux_tile_dim<2, S>(c, A, grid, bs, smem, n_stages);
     prof_end(c, 1);
     CUDA_CHECK_LAUNCH(c);
 }
 template void launch_flux_tile<double>(ibis_b200_ctx*, const FvArgs<double>&);
 template void launch_flux_tile<dual>(ibis_b200_ctx*, const FvArgs<dual>&);
-
-template <typename S>
-void launch_frec_geom(ibis_b200_ctx* c, S* sides) {
-    if (c->g.n_faces == 0) return;
-    k_frec_geom<S><<<nblocks(c->g.n_faces, 256), 256, 0, c->stream>>>(c->g, sides);
-    CUDA_CHECK_LAUNCH(c);
-}
-template void launch_frec_geom<double>(ibis_b200_ctx*, double*);
-template void launch_frec_geom<dual>(ibis_b200_ctx*, dual*);
 
 template <typename S>
 void launch_face_flux(ibis_b200_ctx* c, const FvArgs<S>& A) {

@@ -213,4 +213,176 @@ inline int renumber_grid(const ibis_b200_grid_desc* gd, bool morton, Renumbered&
     return 0;
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Tiles and the tile-owned interface numbering of the sides path.
+//
+// A tile is a run of at most T consecutive cells that does not straddle n_owned: tiles
+// [0, nt_owned) cover the owned cells, [nt_owned, nt_all) the inner halo ring (cells with a face
+// list).  Every interface is "homed" in the tile of the first cell (in cell order) that lists it.
+// Inside the home range of tile b the interfaces are ordered in three sections,
+//     [R-owned | both-owned | L-owned],
+//   both-owned: the other cell is in tile b too, or is a boundary ghost (tile b writes both sides),
+//   R-owned:    the other cell is elsewhere and tile b's cell is the RIGHT cell,
+//   L-owned:    the other cell is elsewhere and tile b's cell is the LEFT cell,
+// the outer two sorted by the tile of the other cell.  Consequences: the left sides tile b
+// produces are the contiguous range [h0 + nR, h0 + nh), its right sides [h0, h0 + nR + n0), and
+// the interfaces it shares with any one other tile are one contiguous range per orientation:
+// every transfer of interface data of a tile, in either direction, is a handful of bulk copies.
+// ---------------------------------------------------------------------------------------
+struct TileEntry {        // a range of interfaces of tile t that are homed in another tile
+    int f_start, count;
+    int section;          // 0: the home tile owns the RIGHT side (t owns the left), 2: the reverse
+    int slot_start;       // tile-local flux slot of the first interface (home slots come first)
+    int stage_start;      // index of t's own side of the first interface in t's staging buffer
+};
+struct TileLayout {
+    int T = 0, nt_owned = 0, nt_all = 0;
+    std::vector<int> c0;          // nt_all + 1: cells of tile b = [c0[b], c0[b+1])
+    std::vector<int> h0;          // nt_all + 1: home interfaces of tile b = [h0[b], h0[b+1])
+    std::vector<int> nR, n0;      // sizes of the first two sections
+    std::vector<int> ent_off;     // nt_all + 1 into entries
+    std::vector<TileEntry> entries;
+    std::vector<int> slot_other;  // per interface: its flux slot in the tile of the non-home cell, -1
+    std::vector<int> home_tile;   // per interface
+    int cap_slots = 1, cap_stage = 1;
+    // staging layout of tile b: left sides first: [home left range | entries of section 0 ...],
+    // then right sides: [home right range | entries of section 2 ...]
+    int n_own_left(int b) const {
+        int n = (h0[b + 1] - h0[b]) - nR[b];
+        for (int e = ent_off[b]; e < ent_off[b + 1]; e++)
+            if (entries[e].section == 0) n += entries[e].count;
+        return n;
+    }
+};
+
+inline int regroup_faces(Renumbered& R, int T, TileLayout& TL, const char** err) {
+    const ibis_b200_grid_desc& d = R.desc;
+    const int64_t n_cells = d.n_cells, n_faces = d.n_faces, n_grad = R.n_grad;
+    const int64_t n_owned = d.n_owned > 0 ? d.n_owned : n_cells;
+    TL.T = T;
+    TL.nt_owned = (int)((n_owned + T - 1) / T);
+    const int nt_halo = (int)((n_grad - n_owned + T - 1) / T);
+    TL.nt_all = TL.nt_owned + nt_halo;
+    const int nt = TL.nt_all;
+    TL.c0.assign(nt + 1, 0);
+    for (int b = 0; b <= TL.nt_owned; b++) TL.c0[b] = (int)std::min<int64_t>((int64_t)b * T, n_owned);
+    for (int b = 0; b <= nt_halo; b++) TL.c0[TL.nt_owned + b] = (int)std::min<int64_t>(n_owned + (int64_t)b * T, n_grad);
+    auto tile_of = [&](int64_t c) -> int {
+        if (c < n_owned) return (int)(c / T);
+        return TL.nt_owned + (int)((c - n_owned) / T);
+    };
+    const int BIG = 0x7fffffff;
+    // home tile, section and sort key of every interface
+    std::vector<uint64_t> key(n_faces);
+    std::vector<int> home(n_faces, BIG), other_tile(n_faces, BIG), section(n_faces, 1);
+#pragma omp parallel for schedule(static)
+    for (int64_t f = 0; f < n_faces; f++) {
+        const int64_t l = R.face_left[f], r = R.face_right[f];
+        const bool lv = l >= 0 && l < n_grad, rv = r >= 0 && r < n_grad;
+        int hm = BIG, sec = 1, ot = BIG;
+        if (lv || rv) {
+            const bool home_is_left = lv && (!rv || l < r);
+            const int64_t hc = home_is_left ? l : r, oc = home_is_left ? r : l;
+            hm = tile_of(hc);
+            const bool o_list = oc >= 0 && oc < n_grad;
+            if (oc >= n_cells || (o_list && tile_of(oc) == hm)) {
+                sec = 1;                                   // ghost, or both cells in the home tile
+            } else {
+                sec = home_is_left ? 2 : 0;
+                ot = o_list ? tile_of(oc) : BIG - 1;       // outer halo ring: nobody produces that side
+            }
+        }
+        home[f] = hm;
+        section[f] = sec;
+        other_tile[f] = ot;
+    }
+    std::vector<int> order(n_faces);
+    for (int64_t f = 0; f < n_faces; f++) {
+        order[f] = (int)f;
+        const uint64_t hm = (uint64_t)std::min(home[f], 0xFFFFFF), ot = section[f] == 1 ? 0 : (uint64_t)std::min(other_tile[f], 0xFFFFFF);
+        key[f] = hm << 34 | (uint64_t)section[f] << 32 | ot;
+    }
+    radix_sort_by_key(key, order);                         // stable: ties keep the discovery order
+    std::vector<int64_t> fnew(n_faces);
+    for (int64_t k = 0; k < n_faces; k++) fnew[order[k]] = k;
+    // permute the interface arrays and everything that names an interface
+    {
+        std::vector<int64_t> fl(n_faces), fr(n_faces);
+        std::vector<double> fa(n_faces), fn(3 * n_faces), ft1(3 * n_faces), ft2(3 * n_faces), fc(3 * n_faces);
+#pragma omp parallel for schedule(static)
+        for (int64_t k = 0; k < n_faces; k++) {
+            const int64_t f = order[k];
+            fl[k] = R.face_left[f];
+            fr[k] = R.face_right[f];
+            fa[k] = R.f_area[f];
+            for (int q = 0; q < 3; q++) {
+                fn[3 * k + q] = R.f_norm[3 * f + q];
+                ft1[3 * k + q] = R.f_t1[3 * f + q];
+                ft2[3 * k + q] = R.f_t2[3 * f + q];
+                fc[3 * k + q] = R.f_c[3 * f + q];
+            }
+        }
+        R.face_left.swap(fl); R.face_right.swap(fr); R.f_area.swap(fa); R.f_norm.swap(fn);
+        R.f_t1.swap(ft1); R.f_t2.swap(ft2); R.f_c.swap(fc);
+    }
+#pragma omp parallel for schedule(static)
+    for (int64_t q = 0; q < (int64_t)R.cf_ids.size(); q++) R.cf_ids[q] = fnew[R.cf_ids[q]];
+    for (auto& f : R.tag_faces) f = fnew[f];
+    R.desc.face_left = R.face_left.data(); R.desc.face_right = R.face_right.data();
+    R.desc.face_area = R.f_area.data(); R.desc.face_norm = R.f_norm.data();
+    R.desc.face_tan1 = R.f_t1.data(); R.desc.face_tan2 = R.f_t2.data(); R.desc.face_centre = R.f_c.data();
+    R.desc.cell_face_ids = R.cf_ids.data(); R.desc.tag_faces = R.tag_faces.data();
+
+    // per-tile section sizes, home ranges, entries
+    TL.h0.assign(nt + 1, 0); TL.nR.assign(nt, 0); TL.n0.assign(nt, 0);
+    TL.home_tile.assign(n_faces, BIG);
+    std::vector<int> cnt(nt + 1, 0);
+    for (int64_t k = 0; k < n_faces; k++) {
+        const int f = order[k];
+        TL.home_tile[k] = home[f];
+        if (home[f] == BIG) continue;
+        cnt[home[f]]++;
+        if (section[f] == 0) TL.nR[home[f]]++;
+        if (section[f] == 1) TL.n0[home[f]]++;
+    }
+    for (int b = 0; b < nt; b++) TL.h0[b + 1] = TL.h0[b] + cnt[b];
+    // entries: maximal runs of equal (home, section != 1, other tile) in the new order
+    std::vector<std::vector<TileEntry>> per_tile(nt);
+    for (int64_t k = 0; k < n_faces;) {
+        const int f = order[k];
+        if (home[f] == BIG || section[f] == 1 || other_tile[f] >= nt) { k++; continue; }
+        int64_t e = k + 1;
+        while (e < n_faces && home[order[e]] == home[f] && section[order[e]] == section[f] &&
+               other_tile[order[e]] == other_tile[f]) e++;
+        TileEntry te;
+        te.f_start = (int)k; te.count = (int)(e - k); te.section = section[f]; te.slot_start = 0; te.stage_start = 0;
+        per_tile[other_tile[f]].push_back(te);
+        k = e;
+    }
+    TL.ent_off.assign(nt + 1, 0);
+    TL.slot_other.assign(n_faces, -1);
+    for (int b = 0; b < nt; b++) {
+        const int nh = TL.h0[b + 1] - TL.h0[b];
+        int slot = nh;
+        int stage_l = nh - TL.nR[b];                       // after the home left range
+        int n_own_l = stage_l;
+        for (auto& te : per_tile[b]) if (te.section == 0) n_own_l += te.count;
+        int stage_r = n_own_l + TL.nR[b] + TL.n0[b];       // after the home right range
+        for (auto& te : per_tile[b]) {
+            te.slot_start = slot;
+            for (int q = 0; q < te.count; q++) TL.slot_other[te.f_start + q] = slot + q;
+            slot += te.count;
+            if (te.section == 0) { te.stage_start = stage_l; stage_l += te.count; }
+            else { te.stage_start = stage_r; stage_r += te.count; }
+            TL.entries.push_back(te);
+        }
+        TL.ent_off[b + 1] = (int)TL.entries.size();
+        TL.cap_slots = std::max(TL.cap_slots, slot);
+        TL.cap_stage = std::max(TL.cap_stage, stage_r);
+    }
+    (void)err;
+    return 0;
+}
+
 }  // namespace ib

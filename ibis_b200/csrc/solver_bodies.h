@@ -9,14 +9,14 @@ namespace ib {
 // conserved_to_primatives (finite_volume/primative_conserved_conversion.cpp:5-23); runs
 // over ALL rows including ghosts (fs.gas.size()), where 0/0 gives NaN as in the reference.
 template <int DIM, typename S>
-IBIS_HD void cons_to_prim_body(S* const* cq, S* const* fs, const Gas<S>& gas, long i) {
+IBIS_HD void prim_from_cons_store(const S* q /* mass mx my mz energy */, S* const* fs, const Gas<S>& gas, long i) {
     typedef mem<S> M;
-    const S rho = M::load(cq[0], i);
-    const S vx = M::load(cq[1], i) / rho;
-    const S vy = M::load(cq[2], i) / rho;
-    const S vz = (DIM == 3) ? M::load(cq[3], i) / rho : S(0.0);
+    const S rho = q[0];
+    const S vx = q[1] / rho;
+    const S vy = q[2] / rho;
+    const S vz = (DIM == 3) ? q[3] / rho : S(0.0);
     const S ke = 0.5 * (vx * vx + vy * vy + vz * vz);
-    const S u = M::load(cq[4], i) / rho - ke;
+    const S u = q[4] / rho - ke;
     M::store(fs[F_RHO], i, rho);
     M::store(fs[F_VX], i, vx);
     M::store(fs[F_VY], i, vy);
@@ -25,6 +25,14 @@ IBIS_HD void cons_to_prim_body(S* const* cq, S* const* fs, const Gas<S>& gas, lo
     const S T = u / gas.Cv;                                   // update_thermo_from_rhou
     M::store(fs[F_T], i, T);
     M::store(fs[F_P], i, p_from_rhoT(rho, T, gas.R));
+}
+template <int DIM, typename S>
+IBIS_HD void cons_to_prim_body(S* const* cq, S* const* fs, const Gas<S>& gas, long i) {
+    typedef mem<S> M;
+    S q[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) q[k] = (DIM == 2 && k == 3) ? S(0.0) : M::load(cq[k], i);
+    prim_from_cons_store<DIM>(q, fs, gas, i);
 }
 
 // primatives_to_conserved (primative_conserved_conversion.cpp:32-50)
@@ -50,6 +58,43 @@ IBIS_HD void apply_dt_body(S* const* u0, S* const* u1, S* const* k, double dt, l
         if (DIM == 2 && q == 3) continue;
         M::store(u1[q], i, M::load(u0[q], i) + M::load(k[q], i) * dt);
     }
+}
+
+// One fused Runge-Kutta update of rk_step: the chain of apply_time_derivative calls of one stage
+// (runge_kutta.cpp:155-169) or of the final update (:185-186), U <- U + k_t * dt_t term after term
+// exactly as the separate kernels would round it, optionally stored (u_out), followed by the
+// conserved_to_primatives of the result (:177, :193) -- one pass over the cells instead of up to
+// five.  The intermediate conserved state of a stage (k_tmp_) is never needed in memory.
+constexpr int RK_MAX_TERMS = 8;
+template <typename S>
+struct RkTerms {
+    S* k[RK_MAX_TERMS][5];
+    double scale[RK_MAX_TERMS];
+    int n;
+};
+template <int DIM, typename S>
+IBIS_HD void rk_update_body(S* const* u_in, const RkTerms<S>& T, double dt, S* const* u_out, S* const* fs,
+                            const Gas<S>& gas, long i) {
+    typedef mem<S> M;
+    S q[5];
+#pragma unroll
+    for (int c = 0; c < 5; c++) q[c] = (DIM == 2 && c == 3) ? S(0.0) : M::load(u_in[c], i);
+    for (int t = 0; t < T.n; t++) {
+        const double dte = T.scale[t] * dt;
+#pragma unroll
+        for (int c = 0; c < 5; c++) {
+            if (DIM == 2 && c == 3) continue;
+            q[c] = q[c] + M::load(T.k[t][c], i) * dte;
+        }
+    }
+    if (u_out[0]) {
+#pragma unroll
+        for (int c = 0; c < 5; c++) {
+            if (DIM == 2 && c == 3) continue;
+            M::store(u_out[c], i, q[c]);
+        }
+    }
+    prim_from_cons_store<DIM>(q, fs, gas, i);
 }
 
 // L2_norms contributions (conserved_quantities.cpp:43-58), real parts:

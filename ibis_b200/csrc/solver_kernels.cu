@@ -57,6 +57,13 @@ __global__ void __launch_bounds__(256) k_apply_dt(Comps5<S> u0, Comps5<S> u1, Co
     if (i < n) apply_dt_body<DIM>(u0.p, u1.p, k.p, dte, i);
 }
 
+template <int DIM, typename S>
+__global__ void __launch_bounds__(256) k_rk_update(Comps5<S> u_in, RkTerms<S> T, const double* d_dt, Comps5<S> u_out,
+                                                    Comps7<S> fs, Gas<S> gas, long n) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) rk_update_body<DIM>(u_in.p, T, d_dt[0], u_out.p, fs.p, gas, i);
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -376,6 +383,17 @@ void launch_apply_dt(ibis_b200_ctx* c, S* const* u0, S* const* u1, S* const* k, 
 }
 template void launch_apply_dt<double>(ibis_b200_ctx*, double* const*, double* const*, double* const*, double, const double*, double, int64_t);
 template void launch_apply_dt<dual>(ibis_b200_ctx*, dual* const*, dual* const*, dual* const*, double, const double*, double, int64_t);
+
+template <typename S>
+void launch_rk_update(ibis_b200_ctx* c, S* const* u_in, const RkTerms<S>& T, const double* d_dt, S* const* u_out,
+                      S* const* fs, int64_t n) {
+    Comps5<S> uo;
+    for (int q = 0; q < 5; q++) uo.p[q] = u_out ? u_out[q] : nullptr;
+    if (c->dim == 3) k_rk_update<3, S><<<nblocks(n, 256), 256, 0, c->stream>>>(c5(u_in), T, d_dt, uo, c7(fs), gas_of<S>(c), n);
+    else k_rk_update<2, S><<<nblocks(n, 256), 256, 0, c->stream>>>(c5(u_in), T, d_dt, uo, c7(fs), gas_of<S>(c), n);
+    CUDA_CHECK_LAUNCH(c);
+}
+template void launch_rk_update<double>(ibis_b200_ctx*, double* const*, const RkTerms<double>&, const double*, double* const*, double* const*, int64_t);
 
 template <typename S>
 void launch_l2_norms(ibis_b200_ctx* c, S* const* cq, int64_t n, double* d_out6) {

@@ -123,51 +123,75 @@ void launch_residual(ibis_b200_ctx* c, const FvArgs<S>& A) {
 template void launch_residual<double>(ibis_b200_ctx*, const FvArgs<double>&);
 template void launch_residual<dual>(ibis_b200_ctx*, const FvArgs<dual>&);
 
+// pass G' tile by tile as the thread block runs it: both halves of every cell into the staging
+// buffer, then the tile's store transfers (the bulk stores of the device kernel) as memcpy
 template <typename S>
 void launch_grad_sides(ibis_b200_ctx* c, const FvArgs<S>& A) {
-#pragma omp parallel for
-    for (int i = 0; i < A.g.n_grad; i++) {
-#define GS(D)                                                        \
-    switch (A.g.max_faces) {                                         \
-        case 6: grad_sides_body<D, 6>(A, i); break;                  \
-        case 5: grad_sides_body<D, 5>(A, i); break;                  \
-        case 4: grad_sides_body<D, 4>(A, i); break;                  \
-        default: grad_sides_body<D, 3>(A, i); break;                 \
+    const GridDev& g = A.g;
+#pragma omp parallel
+    {
+        std::vector<S> stg((size_t)6 * std::max(g.stage_cap, 1));
+#pragma omp for
+        for (int t = 0; t < g.n_tiles_all; t++) {
+            const int* ti = g.tile_info + TILE_INFO * t;
+            const int nR = ti[4], n_own_l = tile_n_own_left(g, t);
+            for (int i = ti[0]; i < ti[0] + ti[1]; i++) {
+#define GS(D, NFV)                                                        \
+    grad_sides_body<D, NFV, 0>(A, i, nR, n_own_l, stg.data());            \
+    grad_sides_body<D, NFV, 1>(A, i, nR, n_own_l, stg.data());
+#define GS_NF(D)                                                          \
+    switch (g.max_faces) {                                                \
+        case 6: GS(D, 6) break;                                           \
+        case 5: GS(D, 5) break;                                           \
+        case 4: GS(D, 4) break;                                           \
+        default: GS(D, 3) break;                                          \
     }
-        if (A.g.dim == 3) { GS(3) } else { GS(2) }
+                if (g.dim == 3) { GS_NF(3) } else { GS_NF(2) }
+#undef GS_NF
 #undef GS
+            }
+            for (int q = 0; q < 2 + ti[7]; q++) {
+                const TileXfer x = tile_store_xfer(g, t, q, n_own_l);
+                S* dst = (x.left ? A.sideL : A.sideR) + (long)x.f0 * 6;
+                for (long k = 0; k < (long)x.count * 6; k++) dst[k] = stg[(size_t)x.stage * 6 + k];
+            }
+        }
     }
     c->launches++;
 }
 template void launch_grad_sides<double>(ibis_b200_ctx*, const FvArgs<double>&);
 template void launch_grad_sides<dual>(ibis_b200_ctx*, const FvArgs<dual>&);
 
-template <typename S>
-void launch_frec_geom(ibis_b200_ctx* c, S* sides) {
-    for (int f = 0; f < c->g.n_faces; f++) frec_geom_body(c->g, sides, f);
-    c->launches++;
-}
-template void launch_frec_geom<double>(ibis_b200_ctx*, double*);
-template void launch_frec_geom<dual>(ibis_b200_ctx*, dual*);
-
+// pass F' tile by tile: the tile's load transfers, the fluxes in place, the cell sums
 template <typename S>
 void launch_flux_tile(ibis_b200_ctx* c, const FvArgs<S>& A) {
     const GridDev& g = A.g;
 #pragma omp parallel
     {
-        std::vector<S> st((size_t)6 * g.tile_cap);
+        const size_t cap = std::max(g.tile_cap, 1);
+        std::vector<S> stL(6 * cap), stR(6 * cap);
+        std::vector<double> stG(10 * cap);
 #pragma omp for
         for (int t = 0; t < g.n_tiles; t++) {
-            const int c0 = t * g.tile, c1 = std::min(c0 + g.tile, g.n_owned);
-            const int n = tile_num_slots(g, t);
-#define TILE_FLUX(D, F, O)                                                                       \
-    for (int s = 0; s < n; s++)                                                                  \
-        flux_from_record<D, F>(A, A.sides + (long)tile_face_of_slot(g, t, s) * frec<S>::stride, st.data() + s, g.tile_cap);
+            const int* ti = g.tile_info + TILE_INFO * t;
+            int n = ti[3];
+            for (int q = 0; q < 1 + ti[7]; q++) {
+                const TileXfer x = tile_load_xfer(g, t, q);
+                for (long k = 0; k < (long)x.count * 6; k++) {
+                    stL[(size_t)x.slot * 6 + k] = A.sideL[(long)x.f0 * 6 + k];
+                    stR[(size_t)x.slot * 6 + k] = A.sideR[(long)x.f0 * 6 + k];
+                }
+                for (long k = 0; k < (long)x.count * 10; k++) stG[(size_t)x.slot * 10 + k] = g.f_geom[(long)x.f0 * 10 + k];
+                n = std::max(n, x.slot + x.count);
+            }
+#define TILE_FLUX(D, F, O)                                                                          \
+    for (int s = 0; s < n; s++)                                                                     \
+        flux_from_sides<D, F>(A, &stL[(size_t)s * 6], &stR[(size_t)s * 6], &stG[(size_t)s * 10], &stL[(size_t)s * 6], 1);
             EMU_FLUX_CALL(TILE_FLUX)
 #undef TILE_FLUX
-            for (int cell = c0; cell < c1; cell++) {
-                if (g.dim == 3) tile_cell_body<3>(A, cell, st.data(), 1, g.tile_cap);
-                else tile_cell_body<2>(A, cell, st.data(), 1, g.tile_cap);
+            for (int cell = ti[0]; cell < ti[0] + ti[1]; cell++) {
+                if (g.dim == 3) tile_cell_body<3>(A, cell, stL.data(), 6, 1);
+                else tile_cell_body<2>(A, cell, stL.data(), 6, 1);
             }
         }
     }
@@ -260,6 +284,20 @@ void launch_apply_dt(ibis_b200_ctx* c, S* const* u0, S* const* u1, S* const* k, 
 }
 template void launch_apply_dt<double>(ibis_b200_ctx*, double* const*, double* const*, double* const*, double, const double*, double, int64_t);
 template void launch_apply_dt<dual>(ibis_b200_ctx*, dual* const*, dual* const*, dual* const*, double, const double*, double, int64_t);
+
+template <typename S>
+void launch_rk_update(ibis_b200_ctx* c, S* const* u_in, const RkTerms<S>& T, const double* d_dt, S* const* u_out,
+                      S* const* fs, int64_t n) {
+    Gas<S> g = gas_of<S>(c);
+    S* none[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    S* const* uo = u_out ? u_out : none;
+    for (int64_t i = 0; i < n; i++) {
+        if (c->dim == 3) rk_update_body<3>(u_in, T, d_dt[0], uo, fs, g, i);
+        else rk_update_body<2>(u_in, T, d_dt[0], uo, fs, g, i);
+    }
+    c->launches++;
+}
+template void launch_rk_update<double>(ibis_b200_ctx*, double* const*, const RkTerms<double>&, const double*, double* const*, double* const*, int64_t);
 
 template <typename S>
 void launch_l2_norms(ibis_b200_ctx* c, S* const* cq, int64_t n, double* out) {
