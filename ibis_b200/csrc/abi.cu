@@ -500,6 +500,12 @@ int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd_ref, con
             q[8] = TL.n_own_left(b);
             q[9] = q[3];
             for (int e = TL.ent_off[b]; e < TL.ent_off[b + 1]; e++) q[9] += TL.entries[e].count;
+            if (q[7] <= TILE_INLINE_ENT)
+                for (int e = 0; e < q[7]; e++) {
+                    const TileEntry& te = TL.entries[TL.ent_off[b] + e];
+                    int* w = q + 12 + 5 * e;
+                    w[0] = te.f_start; w[1] = te.count; w[2] = te.section; w[3] = te.slot_start; w[4] = te.stage_start;
+                }
         }
         std::vector<int> tile_ent((size_t)5 * std::max<size_t>(TL.entries.size(), 1), 0);
         for (size_t e = 0; e < TL.entries.size(); e++) {

@@ -19,7 +19,8 @@ template <typename S>
 struct frec {
     static constexpr int bytes = 12 * (int)sizeof(S) + 80;
 };
-constexpr int TILE_INFO = 12;  // ints per tile descriptor (GridDev::tile_info)
+constexpr int TILE_INFO = 64;  // ints per tile descriptor (GridDev::tile_info): 12 header + 10 inline entries, 256 B
+constexpr int TILE_INLINE_ENT = 10;
 constexpr int NVARS = 6;      // gradient slots: rho, thermo-2, vx, vy, vz, T(viscous)
 enum { V_RHO = 0, V_TH2 = 1, V_VX = 2, V_VY = 3, V_VZ = 4, V_TVISC = 5 };
 enum { F_RHO = 0, F_P = 1, F_T = 2, F_E = 3, F_VX = 4, F_VY = 5, F_VZ = 6 };
@@ -75,7 +76,8 @@ struct GridDev {
     // n_home + position in the foreign list; 0xFFFF past the cell's last face.
     int tile, n_tiles, tile_cap;
     // tiles of the sides path (layout.h): n_tiles owned tiles, then the tiles of the inner halo ring;
-    // tile_info[12 b ..] = {c0, nc, h0, nh, nR, n0, ent_off, n_ent, n_own_l, n_slots, -, -}, tile_ent[5 e ..] = {f_start, count,
+    // tile_info[64 b ..] = {c0, nc, h0, nh, nR, n0, ent_off, n_ent, n_own_l, n_slots, -, -, then up to 10 entries
+    // inline (one 256-byte read gives a block everything it needs to issue its transfers)}, tile_ent[5 e ..] = {f_start, count,
     // section, slot_start, stage_start}; cf_stage = staging index of the cell's own side of each
     // of its interfaces (pass G'); stage_cap = largest staging buffer of a tile (sides)
     int n_tiles_all, stage_cap;
@@ -1142,13 +1144,25 @@ struct TileXfer {
     bool left;                    // stores: which array the tile's own sides go to
 };
 IBIS_HD int tile_n_own_left(const GridDev& g, int b) { return g.tile_info[TILE_INFO * b + 8]; }
+// entry e of the tile whose descriptor is ti: inline in the descriptor when there are few
+IBIS_HD const int* tile_entry(const GridDev& g, const int* ti, int e) {
+    return (ti[7] <= TILE_INLINE_ENT ? ti + 12 : g.tile_ent + 5 * ti[6]) + 5 * e;
+}
+// first cell and cell count of a tile without touching memory: owned tiles are runs of `tile`
+// cells from 0, the tiles of the inner halo ring runs from n_owned
+IBIS_HD void tile_cells(const GridDev& g, int b, int& c0, int& nc) {
+    const bool owned = b < g.n_tiles;
+    c0 = owned ? b * g.tile : g.n_owned + (b - g.n_tiles) * g.tile;
+    const int end = owned ? g.n_owned : g.n_grad;
+    nc = end - c0 < g.tile ? end - c0 : g.tile;
+}
 IBIS_HD TileXfer tile_store_xfer(const GridDev& g, int b, int q, int n_own_l) {
     const int* ti = g.tile_info + TILE_INFO * b;
     TileXfer x;
     if (q == 0) { x.f0 = ti[2] + ti[4]; x.count = ti[3] - ti[4]; x.stage = 0; x.slot = ti[4]; x.left = true; }
     else if (q == 1) { x.f0 = ti[2]; x.count = ti[4] + ti[5]; x.stage = n_own_l; x.slot = 0; x.left = false; }
     else {
-        const int* te = g.tile_ent + 5 * (ti[6] + q - 2);
+        const int* te = tile_entry(g, ti, q - 2);
         x.f0 = te[0]; x.count = te[1]; x.stage = te[4]; x.slot = te[3]; x.left = te[2] == 0;
     }
     return x;
@@ -1161,7 +1175,7 @@ IBIS_HD TileXfer tile_load_xfer(const GridDev& g, int b, int q) {
     x.left = true;
     if (q == 0) { x.f0 = ti[2]; x.count = ti[3]; x.slot = 0; }
     else {
-        const int* te = g.tile_ent + 5 * (ti[6] + q - 1);
+        const int* te = tile_entry(g, ti, q - 1);
         x.f0 = te[0]; x.count = te[1]; x.slot = te[3];
     }
     return x;
@@ -1231,8 +1245,10 @@ IBIS_HD double local_dt_body(const FvArgs<S>& A, int c) {
         if (j >= g.max_faces) break;
         const int f = g.cf_face[j * cs + c];
         if (f < 0) break;
-        const double area = g.f_area[f];
-        const double dot = vx * g.f_n[f] + vy * g.f_n[fs_ + f] + vz * g.f_n[2 * fs_ + f];
+        // the interface frame as one 80-byte record: normal and area in two sectors instead of four
+        const double* gm = g.f_geom + (long)f * 10;
+        const double area = gm[9];
+        const double dot = vx * gm[0] + vy * gm[1] + vz * gm[2];
         const double sig_vel = fabs(dot) + a;
         sr_c += sig_vel * area;
         if (A.viscous) {

@@ -166,7 +166,9 @@ __global__ void __launch_bounds__(TPC * TS, IBIS_GS_MINB) k_grad_sides(const FvA
     const GridDev& g = A.g;
     const int tile = blockIdx.x;
     const int* ti = g.tile_info + TILE_INFO * tile;
-    const int c0 = ti[0], nc = ti[1], nR = ti[4], n_ent = ti[7], n_own_l = ti[8];
+    int c0, nc;
+    tile_cells(g, tile, c0, nc);                               // no load on the way to the gathers
+    const int nR = ti[4], n_ent = ti[7], n_own_l = ti[8];
     const int lane_cell = threadIdx.x % TS, half = threadIdx.x / TS;
     const int c = c0 + lane_cell;
     const bool bulk_in = IBIS_COPY_TMA && STAGE && (c0 & 1) == 0;   // 16-byte aligned table slices
@@ -365,7 +367,9 @@ __global__ void __launch_bounds__(IBIS_F2_THREADS, IBIS_F2_MINB) k_flux_tile(con
     flux_tile_issue_coop<S>(A, tile, stL, stR, stG);
 #endif
     const int* ti = g.tile_info + TILE_INFO * tile;
-    const int c0 = ti[0], nc = ti[1], n = ti[9];
+    int c0, nc;
+    tile_cells(g, tile, c0, nc);
+    const int n = ti[9];
     const int c = c0 + threadIdx.x;
     const bool has_cell = threadIdx.x < nc;
     CellFaces CF;
