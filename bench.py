@@ -262,8 +262,10 @@ def run_gpu(args):
     ms_per_step = ms_total / args.steps
     value = n_cells_total * 3.0 * args.steps / (ms_total * 1e-3)
     peak, peak_kind = measured_peak()
-    tF = prof_ms[1] / max(int(prof_n[1]), 1) * 1e-3
-    tG = prof_ms[0] / max(int(prof_n[0]), 1) * 1e-3
+    # per evaluation: pass G' is two launches (early / late tiles) when the halo exchange is overlapped
+    n_eval = max(int(prof_n[1]), 1)
+    tF = prof_ms[1] / n_eval * 1e-3
+    tG = prof_ms[0] / n_eval * 1e-3
     path = "gather" if os.environ.get("IBIS_B200_SIDES", "1") == "0" else "sides"
     bytes_G, bytes_F = ALG_BYTES_SPLIT[path]
     name_G, name_F = KERNEL_NAMES[path]
@@ -308,7 +310,7 @@ def run_gpu(args):
     }
     if world > 1:
         mine = {"rank": rank, "cells": n_owned, "step_ms": ms_local / args.steps, "pass_F_ms": tF * 1e3, "pass_G_ms": tG * 1e3,
-                "halo_exchange_ms": prof_ms[2] / max(int(prof_n[2]), 1)}
+                "halo_wait_ms": prof_ms[2] / max(int(prof_n[2]), 1)}
         per_rank = [None] * world
         dist.all_gather_object(per_rank, mine)
         line["per_rank"] = per_rank

@@ -140,6 +140,7 @@ FvArgs<S> make_args(ibis_b200_ctx* c, Buffer* fs, Buffer* dudt, bool allow_recon
             A.rc.lim[v] = A.lim ? A.lim + (int64_t)v * c->cstride : nullptr;
         }
     }
+    A.dt_out = nullptr;
     A.face_T = c->face_T;
     A.face_rho = c->face_rho;
     A.gas.R = S(c->cfg.R);
@@ -202,19 +203,39 @@ int ensure_fv_temporaries(ibis_b200_ctx* c, bool want_grad = false) {
 }
 
 // FiniteVolume<T>::compute_dudt (finite_volume.cpp:57-96)
+// dt_bits: when not null and the evaluation takes the sides path, the minimum local time step of the
+// owned cells is left there (as the bit pattern of a double; the caller initialises it to +inf)
 template <typename S>
-int compute_dudt_impl(ibis_b200_ctx* c, Buffer* fs, Buffer* dudt, bool allow_reconstruction) {
+int compute_dudt_impl(ibis_b200_ctx* c, Buffer* fs, Buffer* dudt, bool allow_reconstruction, double* dt_bits = nullptr) {
     int rc = ensure_fv_temporaries<S>(c);
     if (rc) return rc;
     FvArgs<S> A = make_args<S>(c, fs, dudt, allow_reconstruction);
+    A.dt_out = reinterpret_cast<unsigned long long*>(dt_bits);
+    if (sizeof(S) == sizeof(double)) c->last_fs = (int)(fs - c->bufs.data());
+    if (A.order2 && sides_path(c) && comm::halo_split(c)) {
+        // overlap: this rank's boundary cells go out to the peers, the tiles that touch neither a halo
+        // cell nor a ghost run pass G' meanwhile, then the peers' data is awaited and scattered, the
+        // ghosts filled and the remaining tiles (incl. the inner halo ring) done
+        rc = comm::halo_exchange_begin<S>(c, A.fs);
+        if (rc) return rc;
+        launch_grad_sides(c, A, 1);
+        prof_begin(c, 2);
+        rc = comm::halo_exchange_end<S>(c, A.fs);
+        prof_end(c, 2);
+        if (rc) return rc;
+        launch_bc(c, A, IBIS_B200_PHASE_PRE_RECONSTRUCTION);
+        launch_grad_sides(c, A, 2);
+        launch_flux_tile(c, A);
+        if (!c->last_error.empty()) return IBIS_B200_ECUDA;
+        return 0;
+    }
     prof_begin(c, 2);
     rc = comm::halo_exchange<S>(c, A.fs);
     prof_end(c, 2);
     if (rc) return rc;
     launch_bc(c, A, IBIS_B200_PHASE_PRE_RECONSTRUCTION);
-    if (sizeof(S) == sizeof(double)) c->last_fs = (int)(fs - c->bufs.data());
     if (A.order2 && sides_path(c)) {
-        launch_grad_sides(c, A);
+        launch_grad_sides(c, A, 0);
         launch_flux_tile(c, A);
         if (!c->last_error.empty()) return IBIS_B200_ECUDA;
         return 0;
@@ -513,6 +534,21 @@ int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd_ref, con
             q[0] = TL.entries[e].f_start; q[1] = TL.entries[e].count; q[2] = TL.entries[e].section;
             q[3] = TL.entries[e].slot_start; q[4] = TL.entries[e].stage_start;
         }
+        // early tiles: owned tiles none of whose cells has a neighbour outside the owned range
+        std::vector<int> tiles_early, tiles_late;
+        for (int b = 0; b < nt; b++) {
+            bool early = b < n_tiles;
+            for (int64_t i = TL.c0[b]; early && i < TL.c0[b + 1]; i++)
+                for (int j = 0; j < max_faces; j++) {
+                    const int nb = cf_nbr[(size_t)j * cs + i];
+                    if (cf_face[(size_t)j * cs + i] >= 0 && nb >= c->n_owned) { early = false; break; }
+                }
+            (early ? tiles_early : tiles_late).push_back(b);
+        }
+        g.n_early = (int)tiles_early.size();
+        g.n_late = (int)tiles_late.size();
+        if (tiles_early.empty()) tiles_early.push_back(0);
+        if (tiles_late.empty()) tiles_late.push_back(0);
         std::vector<int> home0(TL.h0.begin(), TL.h0.end());
         // sides of the (owned) tiles' interfaces that belong to cells outside the tile: gather path
         std::vector<int> out_off(n_tiles + 1, 0);
@@ -566,6 +602,7 @@ int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd_ref, con
     g.field = ptr;
         UP2(home0, di, home0) UP2(foreign_off, di, foreign_off) UP2(foreign, di, foreign) UP2(cf_slot, du16, cf_slot)
         UP2(cf_stage, du16, cf_stage) UP2(tile_info, di, tile_info) UP2(tile_ent, di, tile_ent)
+        UP2(tiles_early, di, tiles_early) UP2(tiles_late, di, tiles_late)
         UP2(out_off, di, out_off) UP2(out_slot, du16, out_slot) UP2(out_cell, di, out_cell) UP2(out_d, dd, out_d)
         g.n_out = n_out;
 #undef UP2
@@ -913,9 +950,13 @@ int ibis_b200_rk_step(ibis_b200_ctx* c, int fs, int cq, int n_stages, const doub
     }
     F = get_buf(c, fs, BUF_FS);           // bufs may have been reallocated
     U = get_buf(c, cq, BUF_CQ);
-    int rc = compute_dudt_impl<double>(c, F, &c->bufs[c->rk_k[0]], true);             // :143
+    // the dt estimate (:147) reads the same FlowStates as the first evaluation (:143): on the sides
+    // path it rides along in pass F' (same frames, same cell-face order, min is exact)
+    const bool dt_fused = sides_path(c) && c->cfg.reconstruction_order == 2 && !c->rk_unfused;
+    if (dt_fused) launch_fill(c, c->d_scalars + SC_DT_STABLE, INFINITY, 1);
+    int rc = compute_dudt_impl<double>(c, F, &c->bufs[c->rk_k[0]], true, dt_fused ? c->d_scalars + SC_DT_STABLE : nullptr);
     if (rc) return rc;
-    rc = estimate_dt_device(c, F);                                                     // :147
+    rc = dt_fused ? comm::allreduce(c, c->d_scalars + SC_DT_STABLE, 1, comm::OP_MIN) : estimate_dt_device(c, F);
     if (rc) return rc;
     double* d_dt = c->d_scalars + SC_DT;
     launch_rk_dt(c, c->d_scalars + SC_DT_STABLE, cfl, dt_prev, t_remaining, d_dt);

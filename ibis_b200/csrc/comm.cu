@@ -205,7 +205,7 @@ int p2p_enable(ibis_b200_ctx* c, int on) {
 // flags (k_halo_pull).  Two receive areas alternate: a peer can only start exchange k + 2 after
 // it has consumed my data of exchange k + 1, which I sent after my own pull of exchange k.
 template <typename S>
-static int halo_exchange_p2p(ibis_b200_ctx* c, S* const* fs) {
+static int halo_push_p2p(ibis_b200_ctx* c, S* const* fs) {
     Halo& h = c->halo;
     h.iter++;
     const int parity = (int)(h.iter & 1);
@@ -216,6 +216,12 @@ static int halo_exchange_p2p(ibis_b200_ctx* c, S* const* fs) {
         unsigned long long* rflag = reinterpret_cast<unsigned long long*>(h.peer_base[p]) + h.peer_my_slot[p];
         launch_halo_push<S>(c, fs, h.d_send_cells + so, sn, remote, rflag, h.d_counters + p, h.iter);
     }
+    return c->last_error.empty() ? 0 : IBIS_B200_ECUDA;
+}
+template <typename S>
+static int halo_pull_p2p(ibis_b200_ctx* c, S* const* fs) {
+    Halo& h = c->halo;
+    const int parity = (int)(h.iter & 1);
     for (int p = 0; p < h.n_peers; p++) {
         const int64_t ro = h.recv_off[p], rn = h.recv_off[p + 1] - ro;
         const S* area = reinterpret_cast<const S*>(h.d_ipc + FLAG_BYTES + (size_t)parity * h.area_bytes) + ro * 7;
@@ -229,7 +235,10 @@ template <typename S>
 int halo_exchange(ibis_b200_ctx* c, S* const* fs) {
     Halo& h = c->halo;
     if (h.n_peers == 0 || c->n_ranks <= 1) return 0;
-    if (h.p2p) return halo_exchange_p2p<S>(c, fs);
+    if (h.p2p) {
+        int rc = halo_push_p2p<S>(c, fs);
+        return rc ? rc : halo_pull_p2p<S>(c, fs);
+    }
     if (!c->nccl_comm) return comm_fail(c, "halo exchange before comm_init");
     Nccl& n = nccl();
     S* sbuf = reinterpret_cast<S*>(h.d_send_buf);
@@ -251,6 +260,19 @@ int halo_exchange(ibis_b200_ctx* c, S* const* fs) {
     launch_halo_unpack<S>(c, fs, h.d_recv_cells, h.n_recv, rbuf);
     return c->last_error.empty() ? 0 : IBIS_B200_ECUDA;
 }
+bool halo_split(const ibis_b200_ctx* c) { return c->halo.p2p && c->halo.n_peers > 0 && c->n_ranks > 1; }
+template <typename S>
+int halo_exchange_begin(ibis_b200_ctx* c, S* const* fs) {
+    return halo_split(c) ? halo_push_p2p<S>(c, fs) : 0;
+}
+template <typename S>
+int halo_exchange_end(ibis_b200_ctx* c, S* const* fs) {
+    return halo_split(c) ? halo_pull_p2p<S>(c, fs) : halo_exchange<S>(c, fs);
+}
+template int halo_exchange_begin<double>(ibis_b200_ctx*, double* const*);
+template int halo_exchange_begin<dual>(ibis_b200_ctx*, dual* const*);
+template int halo_exchange_end<double>(ibis_b200_ctx*, double* const*);
+template int halo_exchange_end<dual>(ibis_b200_ctx*, dual* const*);
 template int halo_exchange<double>(ibis_b200_ctx*, double* const*);
 template int halo_exchange<dual>(ibis_b200_ctx*, dual* const*);
 

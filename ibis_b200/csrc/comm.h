@@ -22,6 +22,14 @@ int halo_setup(ibis_b200_ctx* c, int n_peers, const int32_t* peer_ranks, const i
                const int64_t* send_cells, const int64_t* recv_offsets, const int64_t* recv_cells);
 template <typename S>
 int halo_exchange(ibis_b200_ctx* c, S* const* fs);                   // no-op without peers
+// split form for overlap: begin = this rank's stores into its peers (returns at once), end = wait for
+// the peers' data and scatter it; halo_split() says whether the split form does anything useful (peer
+// memory enabled).  Between the two, kernels that touch no halo cell may run.
+template <typename S>
+int halo_exchange_begin(ibis_b200_ctx* c, S* const* fs);
+template <typename S>
+int halo_exchange_end(ibis_b200_ctx* c, S* const* fs);
+bool halo_split(const ibis_b200_ctx* c);
 // peer-memory (NVLink P2P) data path: export this rank's receive allocation, map a peer's, switch on
 int p2p_export(ibis_b200_ctx* c, void* handle64, int64_t* n_recv);
 int p2p_import(ibis_b200_ctx* c, int peer_index, const void* handle64, int64_t peer_n_recv,

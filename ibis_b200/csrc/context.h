@@ -133,7 +133,7 @@ void launch_grad_limit(ibis_b200_ctx* c, const FvArgs<S>& A, bool viscous_pass);
 template <typename S>
 void launch_residual(ibis_b200_ctx* c, const FvArgs<S>& A);        // fused inviscid path (order 1)
 template <typename S>
-void launch_grad_sides(ibis_b200_ctx* c, const FvArgs<S>& A);      // sides path, pass G'
+void launch_grad_sides(ibis_b200_ctx* c, const FvArgs<S>& A, int which);   // sides path, pass G' (0 all | 1 early | 2 late tiles)
 template <typename S>
 void launch_flux_tile(ibis_b200_ctx* c, const FvArgs<S>& A);       // sides path, pass F'
 template <typename S>

@@ -81,6 +81,11 @@ struct GridDev {
     // section, slot_start, stage_start}; cf_stage = staging index of the cell's own side of each
     // of its interfaces (pass G'); stage_cap = largest staging buffer of a tile (sides)
     int n_tiles_all, stage_cap;
+    // tiles of pass G' that touch no halo cell and no boundary ghost ("early": they can run while the
+    // halo exchange is in flight) and the rest ("late": after the exchange and the ghost fill)
+    int n_early, n_late;
+    const int* tiles_early;
+    const int* tiles_late;
     const int* tile_info;
     const int* tile_ent;
     const unsigned short* cf_stage;
@@ -128,6 +133,10 @@ struct FvArgs {
     S* flux;           // general path: [comp*fstride + face]
     S* sideL;          // sides path: [face*6 + k], k = rho p T vx vy vz of the left state
     S* sideR;          //             ... of the right state
+    // sides path: when not null, pass F' also takes the minimum over the owned cells of the local
+    // time step (estimate_dt fused into the first evaluation of a Runge-Kutta step): the bit
+    // pattern of a positive double orders like the double, so the reduction is an integer atomicMin
+    unsigned long long* dt_out;
     double* face_T;    // face_fs of the viscous path (finite_volume.h:128), real parts
     double* face_rho;
     Recon<S> rc;
@@ -920,6 +929,27 @@ IBIS_HD void tile_cell_sum(const FvArgs<S>& A, int c, const CellFaces& F, const 
     if (DIM == 3) M::store(A.dudt[3], c, d_mz / vol);
     M::store(A.dudt[4], c, d_e / vol);
 }
+// local time step of cell c (finite_volume.cpp:145-180, inviscid) from the staged interface frames
+// frames[slot * 10 + k]: the same frames, in the same cell-face order, as local_dt_body reads
+template <typename S>
+IBIS_HD double tile_cell_dt(const FvArgs<S>& A, int c, const CellFaces& F, const double* frames) {
+    typedef mem<S> M;
+    const double vx = re(M::load(A.fs[F_VX], c)), vy = re(M::load(A.fs[F_VY], c)), vz = re(M::load(A.fs[F_VZ], c));
+    const double a = speed_of_sound(re(M::load(A.fs[F_T], c)), re(A.gas.R), re(A.gas.gamma));
+    double sr_c = 0.0;
+    const double sr_v = 0.0;
+#pragma unroll
+    for (int j = 0; j < MAXF; j++) {
+        if (F.slot[j] == 0xFFFF) continue;
+        const double* gm = frames + (long)F.slot[j] * 10;
+        const double area = gm[9];
+        const double dot = vx * gm[0] + vy * gm[1] + vz * gm[2];
+        const double sig_vel = fabs(dot) + a;
+        sr_c += sig_vel * area;
+    }
+    return F.vol / (sr_c + A.signal_factor * sr_v);
+}
+
 template <int DIM, typename S>
 IBIS_HD void tile_cell_body(const FvArgs<S>& A, int c, const S* st, long ss, long ks) {
     CellFaces F;

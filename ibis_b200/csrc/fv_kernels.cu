@@ -136,6 +136,8 @@ __global__ void __launch_bounds__(IBIS_F_MAXT, IBIS_F_MINB) k_residual_tile(cons
     if (has_cell) tile_cell_body<DIM>(A, c, st, 1, A.g.tile_cap);
 }
 
+__device__ __forceinline__ double warp_min(double v);
+
 // block-cooperative copies of a contiguous range (bytes: multiple of 16, both ends 16-byte aligned)
 __device__ __forceinline__ void coop_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes) {
     for (uint32_t o = threadIdx.x * 16u; o < bytes; o += blockDim.x * 16u)
@@ -156,7 +158,7 @@ __device__ __forceinline__ void coop_s2g(void* dst_gmem, const void* src_smem, u
 //        of bulk async stores (TMA): the tile-owned interface numbering (layout.h) makes the sides a
 //        tile produces contiguous ranges of the global side arrays.
 template <int DIM, int NF, int TS, int TPC, bool STAGE, typename S>
-__global__ void __launch_bounds__(TPC * TS, IBIS_GS_MINB) k_grad_sides(const FvArgs<S> A) {
+__global__ void __launch_bounds__(TPC * TS, IBIS_GS_MINB) k_grad_sides(const FvArgs<S> A, const int* __restrict__ tile_list) {
     constexpr int NT = NF * 3;                                  // arrays per table
     constexpr int WS = STAGE ? TS : 0;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -164,7 +166,7 @@ __global__ void __launch_bounds__(TPC * TS, IBIS_GS_MINB) k_grad_sides(const FvA
     double* tab = reinterpret_cast<double*>(smem_raw);          // [2 * NT][TS] when STAGE
     S* stg = reinterpret_cast<S*>(smem_raw + (STAGE ? (size_t)2 * NT * TS * sizeof(double) : 0));
     const GridDev& g = A.g;
-    const int tile = blockIdx.x;
+    const int tile = tile_list ? tile_list[blockIdx.x] : blockIdx.x;
     const int* ti = g.tile_info + TILE_INFO * tile;
     int c0, nc;
     tile_cells(g, tile, c0, nc);                               // no load on the way to the gathers
@@ -385,6 +387,17 @@ __global__ void __launch_bounds__(IBIS_F2_THREADS, IBIS_F2_MINB) k_flux_tile(con
         flux_from_sides<DIM, FLUX>(A, stL + (long)s * 6, stR + (long)s * 6, stG + (long)s * 10, stL + (long)s * 6, 1);
     __syncthreads();
     if (has_cell) tile_cell_sum<DIM>(A, c, CF, stL, 6, 1);
+    if (A.dt_out) {                         // estimate_dt fused into this evaluation (uniform branch)
+        double d = has_cell ? tile_cell_dt<S>(A, c, CF, stG) : INFINITY;
+        d = warp_min(d);
+        __shared__ double dmin[32];
+        if ((threadIdx.x & 31) == 0) dmin[threadIdx.x >> 5] = d;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < (int)(blockDim.x >> 5); w++) d = dmin[w] < d ? dmin[w] : d;
+            if (d == d) atomicMin(A.dt_out, (unsigned long long)__double_as_longlong(d));
+        }
+    }
     (void)n_stages;
 }
 #endif
@@ -586,38 +599,40 @@ static void launch_tiles(ibis_b200_ctx* c, K kernel, int grid, int bs, size_t sm
 }
 
 template <int DIM, int TS, typename S>
-static void launch_grad_sides_ts(ibis_b200_ctx* c, const FvArgs<S>& A) {
+static void launch_grad_sides_ts(ibis_b200_ctx* c, const FvArgs<S>& A, const int* list, int grid) {
     constexpr int TPC = IBIS_GS_TPC;
     constexpr bool STAGE = IBIS_GS_STAGE != 0;
     const int nf = A.g.max_faces < 3 ? 3 : A.g.max_faces;
     const size_t smem = (STAGE ? (size_t)2 * nf * 3 * TS * sizeof(double) : 0) + (size_t)A.g.stage_cap * 6 * sizeof(S);
-    const int grid = A.g.n_tiles_all;
     switch (nf) {
-        case 6: launch_tiles(c, k_grad_sides<DIM, 6, TS, TPC, STAGE, S>, grid, TPC * TS, smem, A); break;
-        case 5: launch_tiles(c, k_grad_sides<DIM, 5, TS, TPC, STAGE, S>, grid, TPC * TS, smem, A); break;
-        case 4: launch_tiles(c, k_grad_sides<DIM, 4, TS, TPC, STAGE, S>, grid, TPC * TS, smem, A); break;
-        default: launch_tiles(c, k_grad_sides<DIM, 3, TS, TPC, STAGE, S>, grid, TPC * TS, smem, A); break;
+        case 6: launch_tiles(c, k_grad_sides<DIM, 6, TS, TPC, STAGE, S>, grid, TPC * TS, smem, A, list); break;
+        case 5: launch_tiles(c, k_grad_sides<DIM, 5, TS, TPC, STAGE, S>, grid, TPC * TS, smem, A, list); break;
+        case 4: launch_tiles(c, k_grad_sides<DIM, 4, TS, TPC, STAGE, S>, grid, TPC * TS, smem, A, list); break;
+        default: launch_tiles(c, k_grad_sides<DIM, 3, TS, TPC, STAGE, S>, grid, TPC * TS, smem, A, list); break;
     }
 }
 
+// which: 0 = every tile, 1 = the early tiles (no halo cell, no ghost among their neighbours), 2 = the late ones
 template <typename S>
-void launch_grad_sides(ibis_b200_ctx* c, const FvArgs<S>& A) {
-    if (A.g.n_tiles_all == 0) return;
+void launch_grad_sides(ibis_b200_ctx* c, const FvArgs<S>& A, int which) {
+    const int* list = which == 1 ? A.g.tiles_early : which == 2 ? A.g.tiles_late : nullptr;
+    const int grid = which == 1 ? A.g.n_early : which == 2 ? A.g.n_late : A.g.n_tiles_all;
+    if (grid == 0) return;
     prof_begin(c, 0);
     if (A.g.dim == 3) {
-        if (A.g.tile == 64) launch_grad_sides_ts<3, 64, S>(c, A);
-        else if (A.g.tile == 128) launch_grad_sides_ts<3, 128, S>(c, A);
-        else launch_grad_sides_ts<3, 256, S>(c, A);
+        if (A.g.tile == 64) launch_grad_sides_ts<3, 64, S>(c, A, list, grid);
+        else if (A.g.tile == 128) launch_grad_sides_ts<3, 128, S>(c, A, list, grid);
+        else launch_grad_sides_ts<3, 256, S>(c, A, list, grid);
     } else {
-        if (A.g.tile == 64) launch_grad_sides_ts<2, 64, S>(c, A);
-        else if (A.g.tile == 128) launch_grad_sides_ts<2, 128, S>(c, A);
-        else launch_grad_sides_ts<2, 256, S>(c, A);
+        if (A.g.tile == 64) launch_grad_sides_ts<2, 64, S>(c, A, list, grid);
+        else if (A.g.tile == 128) launch_grad_sides_ts<2, 128, S>(c, A, list, grid);
+        else launch_grad_sides_ts<2, 256, S>(c, A, list, grid);
     }
     prof_end(c, 0);
     CUDA_CHECK_LAUNCH(c);
 }
-template void launch_grad_sides<double>(ibis_b200_ctx*, const FvArgs<double>&);
-template void launch_grad_sides<dual>(ibis_b200_ctx*, const FvArgs<dual>&);
+template void launch_grad_sides<double>(ibis_b200_ctx*, const FvArgs<double>&, int);
+template void launch_grad_sides<dual>(ibis_b200_ctx*, const FvArgs<dual>&, int);
 
 template <int DIM, typename S>
 static void launch_flux_tile_dim(ibis_b200_ctx* c, const FvArgs<S>& A, int grid, int bs, size_t smem, int n_stages) {

@@ -126,13 +126,16 @@ template void launch_residual<dual>(ibis_b200_ctx*, const FvArgs<dual>&);
 // pass G' tile by tile as the thread block runs it: both halves of every cell into the staging
 // buffer, then the tile's store transfers (the bulk stores of the device kernel) as memcpy
 template <typename S>
-void launch_grad_sides(ibis_b200_ctx* c, const FvArgs<S>& A) {
+void launch_grad_sides(ibis_b200_ctx* c, const FvArgs<S>& A, int which) {
     const GridDev& g = A.g;
+    const int* list = which == 1 ? g.tiles_early : which == 2 ? g.tiles_late : nullptr;
+    const int n_list = which == 1 ? g.n_early : which == 2 ? g.n_late : g.n_tiles_all;
 #pragma omp parallel
     {
         std::vector<S> stg((size_t)6 * std::max(g.stage_cap, 1));
 #pragma omp for
-        for (int t = 0; t < g.n_tiles_all; t++) {
+        for (int k = 0; k < n_list; k++) {
+            const int t = list ? list[k] : k;
             const int* ti = g.tile_info + TILE_INFO * t;
             const int nR = ti[4], n_own_l = tile_n_own_left(g, t);
             for (int i = ti[0]; i < ti[0] + ti[1]; i++) {
@@ -159,8 +162,8 @@ void launch_grad_sides(ibis_b200_ctx* c, const FvArgs<S>& A) {
     }
     c->launches++;
 }
-template void launch_grad_sides<double>(ibis_b200_ctx*, const FvArgs<double>&);
-template void launch_grad_sides<dual>(ibis_b200_ctx*, const FvArgs<dual>&);
+template void launch_grad_sides<double>(ibis_b200_ctx*, const FvArgs<double>&, int);
+template void launch_grad_sides<dual>(ibis_b200_ctx*, const FvArgs<dual>&, int);
 
 // pass F' tile by tile: the tile's load transfers, the fluxes in place, the cell sums
 template <typename S>
@@ -192,6 +195,17 @@ void launch_flux_tile(ibis_b200_ctx* c, const FvArgs<S>& A) {
             for (int cell = ti[0]; cell < ti[0] + ti[1]; cell++) {
                 if (g.dim == 3) tile_cell_body<3>(A, cell, stL.data(), 6, 1);
                 else tile_cell_body<2>(A, cell, stL.data(), 6, 1);
+                if (A.dt_out) {
+                    CellFaces CF;
+                    tile_cell_load(g, cell, CF);
+                    const double d = tile_cell_dt<S>(A, cell, CF, stG.data());
+#pragma omp critical
+                    {
+                        double cur;
+                        memcpy(&cur, A.dt_out, 8);
+                        if (d < cur) memcpy(A.dt_out, &d, 8);
+                    }
+                }
             }
         }
     }
@@ -467,6 +481,13 @@ int unique_id(void*) { return IBIS_B200_ECOMM; }
 int allreduce(ibis_b200_ctx*, double*, int, int) { return 0; }
 int halo_setup(ibis_b200_ctx*, int, const int32_t*, const int64_t*, const int64_t*, const int64_t*, const int64_t*) { return 0; }
 template <typename S> int halo_exchange(ibis_b200_ctx*, S* const*) { return 0; }
+template <typename S> int halo_exchange_begin(ibis_b200_ctx*, S* const*) { return 0; }
+template <typename S> int halo_exchange_end(ibis_b200_ctx*, S* const*) { return 0; }
+template int halo_exchange_begin<double>(ibis_b200_ctx*, double* const*);
+template int halo_exchange_begin<dual>(ibis_b200_ctx*, dual* const*);
+template int halo_exchange_end<double>(ibis_b200_ctx*, double* const*);
+template int halo_exchange_end<dual>(ibis_b200_ctx*, dual* const*);
+bool halo_split(const ibis_b200_ctx*) { return true; }   // the emulation always takes the early / late order
 int p2p_export(ibis_b200_ctx*, void*, int64_t*) { return IBIS_B200_ECOMM; }
 int p2p_import(ibis_b200_ctx*, int, const void*, int64_t, int64_t, int) { return IBIS_B200_ECOMM; }
 int p2p_enable(ibis_b200_ctx*, int) { return IBIS_B200_ECOMM; }

@@ -45,3 +45,24 @@ def test_launch_counter_counts_kernels():
     ctx.compute_dudt(fs, dq)
     assert ctx.launch_count() - n0 == 3       # ghost fill, pass G, pass F
     ctx.close()
+
+
+@pytest.mark.gpu
+def test_decomposed_run_equals_whole_box_on_two_gpus():
+    """tools/mgpu_check.py under torchrun: two ranks, peer-memory halo exchange overlapped with the
+    interior tiles of pass G', bit-identical to the undecomposed run (skipped on a one-GPU box)."""
+    _require_cuda()
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for mode in ("p2p", "nccl"):
+        env = dict(os.environ, IBIS_B200_HALO=mode)
+        out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                              "--master-addr", "127.0.0.1", "--master-port", "29533",
+                              os.path.join(root, "tools", "mgpu_check.py"), "--edge", "32", "--steps", "2"],
+                             capture_output=True, text=True, timeout=600, env=env)
+        assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+        assert '"ok": true' in out.stdout
