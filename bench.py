@@ -239,18 +239,28 @@ def run_gpu(args):
         ms_total = float(t.item())
     bad = ctx.count_bad_cells(fs)
 
-    # end-to-end: host-resident state in pinned memory, uploaded and read back every step
-    pin_in = torch.from_numpy(prim).pin_memory()
+    # end-to-end: the flow state lives on the HOST, in pinned memory, as the reference's own
+    # native_binary snapshot (io/native.cpp: one f64 array per variable T, p, vx, vy, vz over the valid
+    # cells); every step reads the snapshot in (H2D + update_thermo_from_pT), converts, takes one
+    # RungeKutta::take_step and writes the new snapshot back out (D2H) through the C ABI
+    n_valid = int(g.n_cells)
+    snap = np.ascontiguousarray(prim[:n_valid, [2, 1, 4, 5, 6]].T)          # T p vx vy vz
+    pin_in = torch.from_numpy(snap).pin_memory()
     pin_out = torch.empty_like(pin_in).pin_memory()
+    row = n_valid * 8
+    in_ptrs = [pin_in.data_ptr() + q * row for q in range(5)]
+    out_ptrs = [pin_out.data_ptr() + q * row for q in range(5)]
     n_e2e = max(1, min(args.steps, 3))
-    ctx.fs_upload_ptr(fs, pin_in.data_ptr())
+    ctx.flow_read_native(fs, *in_ptrs)
     ctx.sync()
+    if world > 1:
+        dist.barrier()
     t0 = time.perf_counter()
     for _ in range(n_e2e):
-        ctx.fs_upload_ptr(fs, pin_in.data_ptr())
+        ctx.flow_read_native(fs, *in_ptrs)
         ctx.prim_to_cons(cq, fs)
         ctx.rk_step(fs, cq, tab["a"], tab["b"], 0.5, sys.float_info.max, 1.0)
-        ctx.fs_download_ptr(fs, pin_out.data_ptr())
+        ctx.flow_write_native(fs, out=out_ptrs)
     ctx.sync()
     t_e2e = (time.perf_counter() - t0) / n_e2e
     if world > 1:
@@ -305,8 +315,9 @@ def run_gpu(args):
                      "halo_exchange_ms": (prof_ms[2] / max(int(prof_n[2]), 1)) if world > 1 else None,
                      "halo_mode": halo_mode if world > 1 else None},
         "e2e": {"value": n_cells_total * 3.0 / t_e2e, "unit": "cell-residual evals/s",
-                "h2d_bytes_per_step": int(prim.nbytes), "d2h_bytes_per_step": int(prim.nbytes),
-                "note": "per step: fs_upload from pinned host memory, prim_to_cons, rk_step, fs_download"},
+                "h2d_bytes_per_step": int(snap.nbytes), "d2h_bytes_per_step": int(snap.nbytes),
+                "note": "per step and rank: flow_read_native (the reference's native_binary snapshot arrays T p vx vy vz "
+                        "from pinned host memory + update_thermo_from_pT), prim_to_cons, rk_step, flow_write_native"},
     }
     if world > 1:
         mine = {"rank": rank, "cells": n_owned, "step_ms": ms_local / args.steps, "pass_F_ms": tF * 1e3, "pass_G_ms": tG * 1e3,

@@ -759,6 +759,37 @@ int ibis_b200_fs_download(ibis_b200_ctx* c, int h, double* re_, double* du_) {
     if (!b) return fail(c, IBIS_B200_EHANDLE, "not a FlowStates handle");
     return download_rows(c, b, FS_MAP, 7, re_, du_);
 }
+int ibis_b200_flow_read_native(ibis_b200_ctx* c, int h, const double* T, const double* p, const double* vx,
+                               const double* vy, const double* vz) {
+    Buffer* b = get_buf(c, h, BUF_FS);
+    if (!b) return fail(c, IBIS_B200_EHANDLE, "not a FlowStates handle");
+    if (!T || !p || !vx || !vy || (c->dim == 3 && !vz)) return fail(c, IBIS_B200_EINVAL, "null host array");
+    const int64_t n = c->n_cells;
+    const int nv = vz ? 5 : 4;
+    int rc = ensure_stage(c, 5 * n);
+    if (rc) return rc;
+    const double* src[5] = {T, p, vx, vy, vz};
+    for (int q = 0; q < nv; q++) GPU_TRY(c, gpu::h2d(c->d_stage + q * n, src[q], n * sizeof(double), c->stream));
+    if (b->is_dual) { dual* f[7]; comp_ptrs<dual>(b, f); launch_flow_read<dual>(c, c->d_stage, n, vz != nullptr, f); }
+    else { double* f[7]; comp_ptrs<double>(b, f); launch_flow_read<double>(c, c->d_stage, n, vz != nullptr, f); }
+    GPU_TRY(c, gpu::stream_sync(c->stream));    // the host arrays may be pageable
+    return c->last_error.empty() ? 0 : IBIS_B200_ECUDA;
+}
+int ibis_b200_flow_write_native(ibis_b200_ctx* c, int h, double* T, double* p, double* vx, double* vy, double* vz) {
+    Buffer* b = get_buf(c, h, BUF_FS);
+    if (!b) return fail(c, IBIS_B200_EHANDLE, "not a FlowStates handle");
+    if (!T || !p || !vx || !vy || (c->dim == 3 && !vz)) return fail(c, IBIS_B200_EINVAL, "null host array");
+    const int64_t n = c->n_cells;
+    const int nv = vz ? 5 : 4;
+    int rc = ensure_stage(c, 5 * n);
+    if (rc) return rc;
+    if (b->is_dual) { dual* f[7]; comp_ptrs<dual>(b, f); launch_flow_write<dual>(c, f, c->d_stage, n, vz != nullptr); }
+    else { double* f[7]; comp_ptrs<double>(b, f); launch_flow_write<double>(c, f, c->d_stage, n, vz != nullptr); }
+    double* dst[5] = {T, p, vx, vy, vz};
+    for (int q = 0; q < nv; q++) GPU_TRY(c, gpu::d2h(dst[q], c->d_stage + q * n, n * sizeof(double), c->stream));
+    GPU_TRY(c, gpu::stream_sync(c->stream));
+    return c->last_error.empty() ? 0 : IBIS_B200_ECUDA;
+}
 int ibis_b200_cq_upload(ibis_b200_ctx* c, int h, const double* re_, const double* du_) {
     Buffer* b = get_buf(c, h, BUF_CQ);
     if (!b) return fail(c, IBIS_B200_EHANDLE, "not a ConservedQuantities handle");

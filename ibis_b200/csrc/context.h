@@ -169,6 +169,10 @@ void launch_pack_in(ibis_b200_ctx* c, const double* d_re, const double* d_du, S*
 template <typename S>
 void launch_pack_out(ibis_b200_ctx* c, S* const* comps, const int* comp_map, int ncomp_ref,
                      int64_t n, double* d_re, double* d_du);
+template <typename S>
+void launch_flow_read(ibis_b200_ctx* c, const double* stage, int64_t n, int has_vz, S* const* fs);
+template <typename S>
+void launch_flow_write(ibis_b200_ctx* c, S* const* fs, double* stage, int64_t n, int has_vz);
 void launch_gather_debug(ibis_b200_ctx* c, const double* src, int ncomp, int64_t n, double* out);
 // vectors
 void launch_dot(ibis_b200_ctx* c, const double* a, const double* b, int64_t n, double* d_out,

@@ -35,6 +35,31 @@ IBIS_HD void cons_to_prim_body(S* const* cq, S* const* fs, const Gas<S>& gas, lo
     prim_from_cons_store<DIM>(q, fs, gas, i);
 }
 
+// one cell of a native flow snapshot (io/native.cpp:280-336): T p vx vy vz in, thermodynamic
+// closure update_thermo_from_pT (gas_model.h:91-95); row i of the arrays is reference cell i
+template <typename S>
+IBIS_HD void flow_read_body(const double* T_, const double* p_, const double* vx, const double* vy, const double* vz,
+                            S* const* fs, const Gas<S>& gas, long i, long cell) {
+    typedef mem<S> M;
+    const S T = S(T_[i]), p = S(p_[i]);
+    M::store(fs[F_T], cell, T);
+    M::store(fs[F_P], cell, p);
+    M::store(fs[F_RHO], cell, rho_from_pT(p, T, gas.R));
+    M::store(fs[F_E], cell, gas.Cv * T);
+    M::store(fs[F_VX], cell, S(vx[i]));
+    M::store(fs[F_VY], cell, S(vy[i]));
+    M::store(fs[F_VZ], cell, vz ? S(vz[i]) : S(0.0));
+}
+template <typename S>
+IBIS_HD void flow_write_body(S* const* fs, double* T_, double* p_, double* vx, double* vy, double* vz, long i, long cell) {
+    typedef mem<S> M;
+    T_[i] = re(M::load(fs[F_T], cell));
+    p_[i] = re(M::load(fs[F_P], cell));
+    vx[i] = re(M::load(fs[F_VX], cell));
+    vy[i] = re(M::load(fs[F_VY], cell));
+    if (vz) vz[i] = re(M::load(fs[F_VZ], cell));
+}
+
 // primatives_to_conserved (primative_conserved_conversion.cpp:32-50)
 template <int DIM, typename S>
 IBIS_HD void prim_to_cons_body(S* const* cq, S* const* fs, long i) {

@@ -158,6 +158,22 @@ __global__ void __launch_bounds__(256) k_pack_in(const double* re_, const double
 }
 
 template <typename S>
+__global__ void __launch_bounds__(256) k_flow_read(const double* stage, long n, int has_vz, Comps7<S> fs, Gas<S> gas,
+                                                    const int* perm) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    flow_read_body<S>(stage, stage + n, stage + 2 * n, stage + 3 * n, has_vz ? stage + 4 * n : nullptr, fs.p, gas, i,
+                      perm ? perm[i] : i);
+}
+template <typename S>
+__global__ void __launch_bounds__(256) k_flow_write(Comps7<S> fs, double* stage, long n, int has_vz, const int* perm) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    flow_write_body<S>(fs.p, stage, stage + n, stage + 2 * n, stage + 3 * n, has_vz ? stage + 4 * n : nullptr, i,
+                       perm ? perm[i] : i);
+}
+
+template <typename S>
 __global__ void __launch_bounds__(256) k_pack_out(Comps7<S> comps, CompMap map, int ncomp_ref, long n,
                                                    double* re_, double* du_, const int* perm) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -437,6 +453,23 @@ void launch_pack_in(ibis_b200_ctx* c, const double* d_re, const double* d_du, S*
 }
 template void launch_pack_in<double>(ibis_b200_ctx*, const double*, const double*, double* const*, const int*, int, int64_t);
 template void launch_pack_in<dual>(ibis_b200_ctx*, const double*, const double*, dual* const*, const int*, int, int64_t);
+
+template <typename S>
+void launch_flow_read(ibis_b200_ctx* c, const double* stage, int64_t n, int has_vz, S* const* fs) {
+    if (n <= 0) return;
+    k_flow_read<S><<<nblocks(n, 256), 256, 0, c->stream>>>(stage, n, has_vz, c7(fs), gas_of<S>(c), c->d_ref2int);
+    CUDA_CHECK_LAUNCH(c);
+}
+template void launch_flow_read<double>(ibis_b200_ctx*, const double*, int64_t, int, double* const*);
+template void launch_flow_read<dual>(ibis_b200_ctx*, const double*, int64_t, int, dual* const*);
+template <typename S>
+void launch_flow_write(ibis_b200_ctx* c, S* const* fs, double* stage, int64_t n, int has_vz) {
+    if (n <= 0) return;
+    k_flow_write<S><<<nblocks(n, 256), 256, 0, c->stream>>>(c7(fs), stage, n, has_vz, c->d_ref2int);
+    CUDA_CHECK_LAUNCH(c);
+}
+template void launch_flow_write<double>(ibis_b200_ctx*, double* const*, double*, int64_t, int);
+template void launch_flow_write<dual>(ibis_b200_ctx*, dual* const*, double*, int64_t, int);
 
 template <typename S>
 void launch_pack_out(ibis_b200_ctx* c, S* const* comps, const int* comp_map, int ncomp_ref,

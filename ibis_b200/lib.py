@@ -231,6 +231,8 @@ class Library:
             "ibis_b200_comm_init": [vp, vp, i, i], "ibis_b200_nccl_unique_id": [vp],
             "ibis_b200_halo_p2p_export": [vp, vp, vp], "ibis_b200_halo_p2p_import": [vp, i, vp, i64, i64, i],
             "ibis_b200_halo_p2p_enable": [vp, i],
+            "ibis_b200_flow_read_native": [vp, i, vp, vp, vp, vp, vp],
+            "ibis_b200_flow_write_native": [vp, i, vp, vp, vp, vp, vp],
         }
         for name, args in sig.items():
             f = getattr(L, name)
@@ -343,6 +345,25 @@ class Context:
         a = np.zeros(int(n))
         self._ck(self.lib.ibis_b200_vec_download(self.h, h, _ptr(a)), "vec_download")
         return a
+
+    def flow_read_native(self, h, T, p, vx, vy, vz=None):
+        """The reference's native_binary snapshot arrays (one f64 array per variable over the valid
+        cells) -> FlowStates, with update_thermo_from_pT; arrays may be numpy arrays or raw pointers."""
+        keep = [x if isinstance(x, int) or x is None else _as(x, np.float64) for x in (T, p, vx, vy, vz)]
+        a = [C.c_void_p(x) if isinstance(x, int) else _ptr(x) for x in keep]
+        self._ck(self.lib.ibis_b200_flow_read_native(self.h, h, *a), "flow_read_native")
+
+    def flow_write_native(self, h, out=None):
+        """FlowStates -> (T, p, vx, vy[, vz]); `out` = five raw pointers to write through instead."""
+        if out is not None:
+            self._ck(self.lib.ibis_b200_flow_write_native(self.h, h, *[C.c_void_p(x) if x else None for x in out]),
+                     "flow_write_native")
+            return None
+        dim, n, _, _ = self.sizes()
+        arrs = [np.empty(n) for _ in range(5 if dim == 3 else 4)]
+        ptrs = [_ptr(x) for x in arrs] + ([None] if dim == 2 else [])
+        self._ck(self.lib.ibis_b200_flow_write_native(self.h, h, *ptrs), "flow_write_native")
+        return arrs
 
     def copy(self, dst, src):
         self._ck(self.lib.ibis_b200_copy(self.h, dst, src), "copy")

@@ -154,6 +154,15 @@ int ibis_b200_cq_upload(ibis_b200_ctx*, int cq, const double* cons_re, const dou
 int ibis_b200_cq_download(ibis_b200_ctx*, int cq, double* cons_re, double* cons_du);
 int ibis_b200_vec_upload(ibis_b200_ctx*, int vec, const double* x);
 int ibis_b200_vec_download(ibis_b200_ctx*, int vec, double* x);
+/* The reference's native_binary flow snapshot (io/native.cpp:200-339): one raw f64 array per variable,
+ * T, p, vx, vy[, vz], over the num_valid_cells in reference numbering (no ghost rows).
+ * flow_read_native = NativeBinaryInput::read followed by its update_thermo_from_pT loop
+ * (native.cpp:280-336: rho = p / (R T), e = Cv T; ghost rows untouched); flow_write_native =
+ * NativeBinaryOutput::write (native.cpp:200-262).  40 bytes per cell cross the bus instead of the 56
+ * bytes per row (ghosts included) of fs_upload / fs_download.  vz may be NULL in 2-D. */
+int ibis_b200_flow_read_native(ibis_b200_ctx*, int fs, const double* T, const double* p, const double* vx,
+                               const double* vy, const double* vz);
+int ibis_b200_flow_write_native(ibis_b200_ctx*, int fs, double* T, double* p, double* vx, double* vy, double* vz);
 int ibis_b200_copy(ibis_b200_ctx*, int dst, int src);          /* deep_copy, same kind */
 int ibis_b200_zero(ibis_b200_ctx*, int buf);
 

@@ -364,6 +364,28 @@ template void launch_pack_in<double>(ibis_b200_ctx*, const double*, const double
 template void launch_pack_in<dual>(ibis_b200_ctx*, const double*, const double*, dual* const*, const int*, int, int64_t);
 
 template <typename S>
+void launch_flow_read(ibis_b200_ctx* c, const double* stage, int64_t n, int has_vz, S* const* fs) {
+    Gas<S> g = gas_of<S>(c);
+    const int* perm = c->d_ref2int;
+    for (int64_t i = 0; i < n; i++)
+        flow_read_body<S>(stage, stage + n, stage + 2 * n, stage + 3 * n, has_vz ? stage + 4 * n : nullptr, fs, g, i,
+                          perm ? perm[i] : i);
+    c->launches++;
+}
+template void launch_flow_read<double>(ibis_b200_ctx*, const double*, int64_t, int, double* const*);
+template void launch_flow_read<dual>(ibis_b200_ctx*, const double*, int64_t, int, dual* const*);
+template <typename S>
+void launch_flow_write(ibis_b200_ctx* c, S* const* fs, double* stage, int64_t n, int has_vz) {
+    const int* perm = c->d_ref2int;
+    for (int64_t i = 0; i < n; i++)
+        flow_write_body<S>(fs, stage, stage + n, stage + 2 * n, stage + 3 * n, has_vz ? stage + 4 * n : nullptr, i,
+                           perm ? perm[i] : i);
+    c->launches++;
+}
+template void launch_flow_write<double>(ibis_b200_ctx*, double* const*, double*, int64_t, int);
+template void launch_flow_write<dual>(ibis_b200_ctx*, dual* const*, double*, int64_t, int);
+
+template <typename S>
 void launch_pack_out(ibis_b200_ctx* c, S* const* comps, const int* map, int ncomp_ref, int64_t n,
                      double* re_, double* du_) {
     const int* perm = c->d_ref2int;
