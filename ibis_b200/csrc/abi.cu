@@ -4,6 +4,7 @@
 // context's stream.
 #include <math.h>
 #include <stdio.h>
+#include <time.h>
 
 #include <algorithm>
 #include <new>
@@ -34,6 +35,20 @@ int fail(ibis_b200_ctx* c, int code, const std::string& msg) {
     } while (0)
 
 int64_t pad_to(int64_t n, int64_t m) { return (n + m - 1) / m * m; }
+
+// IBIS_B200_TIMING=1: wall time of the stages of ibis_b200_create on stderr
+struct StageTimer {
+    bool on;
+    double t0;
+    static double now() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
+    StageTimer() : on(getenv("IBIS_B200_TIMING") != nullptr), t0(now()) {}
+    void lap(const char* what) {
+        if (!on) return;
+        const double t = now();
+        fprintf(stderr, "[ibis_b200 create] %-28s %8.3f s\n", what, t - t0);
+        t0 = t;
+    }
+};
 
 template <typename T>
 int upload_vec(ibis_b200_ctx* c, const std::vector<T>& h, T** d) {
@@ -278,12 +293,14 @@ int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd_ref, con
     // internal renumbering (layout.h); IBIS_B200_RENUMBER=0 keeps the reference numbering
     const char* env_renumber = getenv("IBIS_B200_RENUMBER");
     const bool morton = !(env_renumber && env_renumber[0] == '0');
+    StageTimer timer;
     Renumbered R;
     {
         const char* err = nullptr;
         int rrc = renumber_grid(gd_ref, morton, R, &err);
         if (rrc) return fail(nullptr, rrc, err ? err : "renumbering failed");
     }
+    timer.lap("renumber_grid (Morton)");
     // tiles and the tile-owned interface numbering (layout.h)
     TileLayout TL;
     {
@@ -294,6 +311,7 @@ int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd_ref, con
         int rrc = regroup_faces(R, T, TL, &err);
         if (rrc) return fail(nullptr, rrc, err ? err : "interface regrouping failed");
     }
+    timer.lap("regroup_faces (tiles)");
     const ibis_b200_grid_desc* gd = &R.desc;
     if (gd->dim != 2 && gd->dim != 3) return fail(nullptr, IBIS_B200_EINVAL, "dim must be 2 or 3");
     if (cfg->thermo_interpolator == IBIS_B200_THERMO_P_T)
@@ -343,8 +361,10 @@ int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd_ref, con
     if (max_faces == 0) max_faces = 1;
     std::vector<int> cf_face((size_t)max_faces * cs, -1), cf_nbr((size_t)max_faces * cs, -1);
     std::vector<signed char> cf_out((size_t)MAXF * cs, 0);            // MAXF wide, see GridDev
-    int64_t n_grad = 0;
-    bool grad_prefix_open = true;
+    // cells with their full face list come first; halo cells of the outer layer carry none
+    // (renumber_grid has checked that they form a prefix)
+    const int64_t n_grad = R.n_grad;
+#pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < gd->n_cells; i++) {
         const int64_t o = gd->cell_face_offsets[i];
         const int nf = (int)(gd->cell_face_offsets[i + 1] - o);
@@ -353,18 +373,19 @@ int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd_ref, con
             cf_nbr[(size_t)j * cs + i] = (int)gd->cell_neighbours[o + j];
             cf_out[(size_t)j * cs + i] = (signed char)gd->cell_outsigns[o + j];
         }
-        // cells with their full face list come first; halo cells of the outer layer carry none
-        if (nf > 0 && grad_prefix_open) n_grad = i + 1; else if (nf == 0) grad_prefix_open = false;
     }
     std::vector<double> cxyz((size_t)3 * cs, 0.0), vol((size_t)cs, 1.0);
-    for (int64_t i = 0; i < n_total; i++)
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n_total; i++) {
         for (int d = 0; d < 3; d++) cxyz[(size_t)d * cs + i] = gd->cell_centroid[3 * i + d];
-    for (int64_t i = 0; i < gd->n_cells; i++) vol[i] = gd->cell_volume[i];
+        if (i < gd->n_cells) vol[i] = gd->cell_volume[i];
+    }
 
     // ---- faces SoA ----
     std::vector<int> fl(fs, 0), fr(fs, 0);
     std::vector<double> fa(fs, 0.0), fn((size_t)3 * fs, 0.0), ft1((size_t)3 * fs, 0.0), ft2((size_t)3 * fs, 0.0),
         fc((size_t)3 * fs, 0.0);
+#pragma omp parallel for schedule(static)
     for (int64_t f = 0; f < gd->n_faces; f++) {
         fl[f] = (int)gd->face_left[f];
         fr[f] = (int)gd->face_right[f];
@@ -457,6 +478,7 @@ int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd_ref, con
         if (rc) { ibis_b200_destroy(c); return fail(nullptr, rc, "grid upload failed"); }
     }
 #undef UP
+    timer.lap("SoA build + upload");
     // ---- tiles (layout.h): slot / staging tables of the tiled kernels ----
     {
         const int T = TL.T;
@@ -607,6 +629,7 @@ int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd_ref, con
         g.n_out = n_out;
 #undef UP2
     }
+    timer.lap("tile tables + upload");
     // WLS r-factors on the device (GridBlock::allocate_gradient_weights, grid.h:499-503)
     double* r = nullptr;
     rc = dev_alloc_zero<double>(c, 6 * cs, &r);
@@ -638,6 +661,7 @@ int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd_ref, con
         ibis_b200_destroy(c);
         return fail(nullptr, IBIS_B200_ECUDA, msg);
     }
+    timer.lap("device setup kernels");
     *out = c;
     return 0;
 }
