@@ -183,10 +183,15 @@ bool sides_path(const ibis_b200_ctx* c) {
     return c->use_sides && c->cfg.reconstruction_order == 2 && !c->cfg.viscous;
 }
 
+// dual-number evaluations (16-byte scalars: one tile per SM in the sides kernels) measured 10 % faster
+// through the gather path (profiles/r01_summary.md), so the sides path serves the real evaluations
+template <typename S>
+bool sides_path_for(const ibis_b200_ctx* c) { return sides_path(c) && sizeof(S) == sizeof(double); }
+
 template <typename S>
 int ensure_fv_temporaries(ibis_b200_ctx* c, bool want_grad = false) {
-    const bool need_grad = want_grad || c->cfg.viscous || (c->cfg.reconstruction_order > 1 && !sides_path(c));
-    if (sides_path(c)) {
+    const bool need_grad = want_grad || c->cfg.viscous || (c->cfg.reconstruction_order > 1 && !sides_path_for<S>(c));
+    if (sides_path_for<S>(c)) {
         S** sl = (sizeof(S) == 8) ? reinterpret_cast<S**>(&c->sideL_r) : reinterpret_cast<S**>(&c->sideL_d);
         S** sr = (sizeof(S) == 8) ? reinterpret_cast<S**>(&c->sideR_r) : reinterpret_cast<S**>(&c->sideR_d);
         if (!*sl) {
@@ -227,7 +232,7 @@ int compute_dudt_impl(ibis_b200_ctx* c, Buffer* fs, Buffer* dudt, bool allow_rec
     FvArgs<S> A = make_args<S>(c, fs, dudt, allow_reconstruction);
     A.dt_out = reinterpret_cast<unsigned long long*>(dt_bits);
     if (sizeof(S) == sizeof(double)) c->last_fs = (int)(fs - c->bufs.data());
-    if (A.order2 && sides_path(c) && comm::halo_split(c)) {
+    if (A.order2 && sides_path_for<S>(c) && comm::halo_split(c)) {
         // overlap: this rank's boundary cells go out to the peers, the tiles that touch neither a halo
         // cell nor a ghost run pass G' meanwhile, then the peers' data is awaited and scattered, the
         // ghosts filled and the remaining tiles (incl. the inner halo ring) done
@@ -249,7 +254,7 @@ int compute_dudt_impl(ibis_b200_ctx* c, Buffer* fs, Buffer* dudt, bool allow_rec
     prof_end(c, 2);
     if (rc) return rc;
     launch_bc(c, A, IBIS_B200_PHASE_PRE_RECONSTRUCTION);
-    if (A.order2 && sides_path(c)) {
+    if (A.order2 && sides_path_for<S>(c)) {
         launch_grad_sides(c, A, 0);
         launch_flux_tile(c, A);
         if (!c->last_error.empty()) return IBIS_B200_ECUDA;
