@@ -36,6 +36,9 @@
 #ifndef IBIS_GS_STAGE
 #define IBIS_GS_STAGE 1      // stage the static cell tables in shared memory by TMA
 #endif
+#ifndef IBIS_PREFETCH_AHEAD
+#define IBIS_PREFETCH_AHEAD 296   // a block asks the TMA unit to pull the data of the tile this many blocks ahead
+#endif                            // (2 resident blocks x 148 SMs: the tile that takes this block's place) into L2; 0 = off
 #ifndef IBIS_COPY_TMA
 #define IBIS_COPY_TMA 1      // 1: tile transfers as TMA bulk copies; 0: 16-byte cp.async / st.global by all threads
 #endif
@@ -201,6 +204,26 @@ __global__ void __launch_bounds__(TPC * TS, IBIS_GS_MINB) k_grad_sides(const FvA
             __syncthreads();
         }
     }
+    if (IBIS_PREFETCH_AHEAD > 0 && (int)blockIdx.x + IBIS_PREFETCH_AHEAD < (int)gridDim.x && threadIdx.x >= 64 &&
+        threadIdx.x < 64 + 2 * NT + 5 + 3 * NF) {
+        // warps 2.. : the data of the tile that will take this block's place, into L2
+        const int pt = tile_list ? tile_list[blockIdx.x + IBIS_PREFETCH_AHEAD] : (int)blockIdx.x + IBIS_PREFETCH_AHEAD;
+        int pc0, pnc;
+        tile_cells(g, pt, pc0, pnc);
+        const int q = threadIdx.x - 64;
+        if ((pc0 & 1) == 0) {
+            if (q < 2 * NT) {
+                ac::bulk_prefetch_l2((q < NT ? g.cf_w : g.cf_d) + (long)(q % NT) * g.cstride + pc0, TS * 8u);
+            } else if (q < 2 * NT + 5) {
+                ac::bulk_prefetch_l2(A.rc.val[q - 2 * NT] + pc0, TS * (uint32_t)sizeof(S));
+            } else {
+                const int r = q - 2 * NT - 5, j = r % NF, which = r / NF;
+                if (which == 0 && (pc0 & 3) == 0) ac::bulk_prefetch_l2(g.cf_nbr + (long)j * g.cstride + pc0, TS * 4u);
+                else if (which == 1 && (pc0 & 7) == 0) ac::bulk_prefetch_l2(g.cf_stage + (long)j * g.cstride + pc0, TS * 2u);
+                else if (which == 2 && (pc0 & 15) == 0) ac::bulk_prefetch_l2(g.cf_out + (long)j * g.cstride + pc0, TS * 1u);
+            }
+        }
+    }
     const bool active = lane_cell < nc;
     CellTables<WS> T;
     T.w = STAGE ? tab : g.cf_w;
@@ -335,6 +358,22 @@ __global__ void __launch_bounds__(IBIS_F2_THREADS, IBIS_F2_MINB) k_flux_tile(con
 // one block per owned tile, one pipeline stage: several resident blocks per SM overlap each other's
 // fetches (measured faster than the persistent two-stage form at the shared-memory footprint of
 // 128-cell tiles, profiles/r01_summary.md)
+// the transfers of another tile as L2 prefetches (called by one warp other than warp 0)
+template <typename S>
+__device__ __forceinline__ void flux_tile_prefetch(const FvArgs<S>& A, int tile) {
+    const GridDev& g = A.g;
+    const int n_x = 1 + g.tile_info[TILE_INFO * tile + 7];
+    for (int q = threadIdx.x & 31; q < 3 * n_x; q += 32) {
+        const TileXfer x = tile_load_xfer(g, tile, q / 3);
+        if (x.count <= 0) continue;
+        const int which = q % 3;
+        const uint32_t bytes = (uint32_t)x.count * (which == 2 ? 80u : 6u * (uint32_t)sizeof(S));
+        if (which == 0) ac::bulk_prefetch_l2(A.sideL + (long)x.f0 * 6, bytes);
+        else if (which == 1) ac::bulk_prefetch_l2(A.sideR + (long)x.f0 * 6, bytes);
+        else ac::bulk_prefetch_l2(g.f_geom + (long)x.f0 * 10, bytes);
+    }
+}
+
 // the same transfers with 16-byte cp.async issued by every thread of the block
 template <typename S>
 __device__ __forceinline__ void flux_tile_issue_coop(const FvArgs<S>& A, int tile, S* stL, S* stR, double* stG) {
@@ -365,6 +404,8 @@ __global__ void __launch_bounds__(IBIS_F2_THREADS, IBIS_F2_MINB) k_flux_tile(con
     }
     __syncthreads();
     if (threadIdx.x < 32) flux_tile_issue<S>(A, tile, stL, stR, stG, &bar);
+    else if (IBIS_PREFETCH_AHEAD > 0 && threadIdx.x >= 64 && threadIdx.x < 96 && tile + IBIS_PREFETCH_AHEAD < g.n_tiles)
+        flux_tile_prefetch<S>(A, tile + IBIS_PREFETCH_AHEAD);
 #else
     flux_tile_issue_coop<S>(A, tile, stL, stR, stG);
 #endif
