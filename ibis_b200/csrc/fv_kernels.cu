@@ -42,9 +42,6 @@
 #ifndef IBIS_COPY_TMA
 #define IBIS_COPY_TMA 1      // 1: tile transfers as TMA bulk copies; 0: 16-byte cp.async / st.global by all threads
 #endif
-#ifndef IBIS_F2_PERSIST
-#define IBIS_F2_PERSIST 0    // 1: persistent blocks with a two-stage TMA pipeline; 0: one block per tile
-#endif
 #ifndef IBIS_F2_THREADS
 #define IBIS_F2_THREADS 256  // threads per block of pass F' (>= tile size)
 #endif
@@ -277,19 +274,20 @@ __global__ void __launch_bounds__(TPC * TS, IBIS_GS_MINB) k_grad_sides(const FvA
 #endif
 }
 
-// pass F' of the sides path: PERSISTENT blocks (one or two per SM) walk the owned tiles with a
-// two-stage shared-memory pipeline: while the block computes the fluxes of tile k from stage k & 1,
-// the TMA unit fills the other stage with tile k + gridDim.x -- left states, right states and frames
-// of its interfaces, all as bulk async copies of contiguous ranges (layout.h).  Each flux
-// overwrites the left state of its own interface; then one thread per cell sums its faces
-// (owner computes, no atomics).  The compute phases never wait on HBM.
+// pass F' of the sides path: one block per owned tile.  Left states, right states and frames of the
+// tile's interfaces arrive as TMA bulk copies of contiguous ranges (layout.h) on one mbarrier (splitting
+// the fetch over two barriers so that the block starts on the first half measured 5 % slower).  Each flux
+// overwrites the left state of its own interface; then one thread per cell sums its faces (owner
+// computes, no atomics).  Several resident blocks per SM overlap each other's fetches; a persistent
+// two-stage pipeline (one 512-thread block per SM) measured SLOWER (profiles/r01_summary.md, r01g)
+// and was dropped.
 template <typename S>
 __device__ __forceinline__ void flux_tile_issue(const FvArgs<S>& A, int tile, S* stL, S* stR, double* stG,
                                                 uint64_t* bar) {
     // called by warp 0: lane 0 arms the barrier with the byte count, lanes issue the copies
     const GridDev& g = A.g;
     const int* ti = g.tile_info + TILE_INFO * tile;
-    const int nh = ti[3], n_ent = ti[7], n_slots = ti[9];
+    const int n_ent = ti[7], n_slots = ti[9];
     if (threadIdx.x == 0) ac::mbar_arrive_expect_tx(bar, (uint32_t)n_slots * (uint32_t)frec<S>::bytes);
     __syncwarp();
     const int n_x = 1 + n_ent;
@@ -302,62 +300,8 @@ __device__ __forceinline__ void flux_tile_issue(const FvArgs<S>& A, int tile, S*
         else if (which == 1) ac::bulk_g2s(stR + (long)x.slot * 6, A.sideR + (long)x.f0 * 6, bytes, bar);
         else ac::bulk_g2s(stG + (long)x.slot * 10, g.f_geom + (long)x.f0 * 10, bytes, bar);
     }
-    (void)nh;
 }
 
-#if IBIS_F2_PERSIST
-template <int DIM, int FLUX, typename S>
-__global__ void __launch_bounds__(IBIS_F2_THREADS, IBIS_F2_MINB) k_flux_tile(const FvArgs<S> A, const int n_stages) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ uint64_t bar[2];
-    const GridDev& g = A.g;
-    const int cap = g.tile_cap;
-    const size_t stage_bytes = (size_t)cap * frec<S>::bytes;
-    if (threadIdx.x == 0) {
-        ac::mbar_init(&bar[0], 1);
-        ac::mbar_init(&bar[1], 1);
-        ac::fence_barrier_init();
-    }
-    __syncthreads();
-    auto stage_L = [&](int st) { return reinterpret_cast<S*>(smem_raw + (size_t)st * stage_bytes); };
-    auto stage_R = [&](int st) { return stage_L(st) + (size_t)cap * 6; };
-    auto stage_G = [&](int st) { return reinterpret_cast<double*>(stage_R(st) + (size_t)cap * 6); };
-    if (n_stages == 2 && threadIdx.x < 32 && (int)blockIdx.x < g.n_tiles)
-        flux_tile_issue<S>(A, blockIdx.x, stage_L(0), stage_R(0), stage_G(0), &bar[0]);
-    int it = 0;
-    for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, it++) {
-        const int st = n_stages == 2 ? (it & 1) : 0;
-        const int next = tile + gridDim.x;
-        // two stages: the other stage was last read in iteration it - 1, which ended with
-        // __syncthreads; one stage (tiles too large for two): fetch this tile now
-        if (n_stages == 2) {
-            if (threadIdx.x < 32 && next < g.n_tiles)
-                flux_tile_issue<S>(A, next, stage_L(st ^ 1), stage_R(st ^ 1), stage_G(st ^ 1), &bar[st ^ 1]);
-        } else if (threadIdx.x < 32) {
-            flux_tile_issue<S>(A, tile, stage_L(0), stage_R(0), stage_G(0), &bar[0]);
-        }
-        const int* ti = g.tile_info + TILE_INFO * tile;
-        const int c0 = ti[0], nc = ti[1], n = ti[9];
-        const int c = c0 + threadIdx.x;
-        const bool has_cell = threadIdx.x < nc;
-        CellFaces CF;
-        if (has_cell) tile_cell_load(g, c, CF);
-        S* stL = stage_L(st);
-        S* stR = stage_R(st);
-        double* stG = stage_G(st);
-        ac::mbar_wait(&bar[st], (uint32_t)(n_stages == 2 ? ((it >> 1) & 1) : (it & 1)));
-        for (int s = threadIdx.x; s < n; s += blockDim.x)
-            flux_from_sides<DIM, FLUX>(A, stL + (long)s * 6, stR + (long)s * 6, stG + (long)s * 10, stL + (long)s * 6, 1);
-        __syncthreads();
-        if (has_cell) tile_cell_sum<DIM>(A, c, CF, stL, 6, 1);
-        ac::fence_proxy_async();           // generic accesses of this stage before the TMA refills it
-        __syncthreads();
-    }
-}
-#else
-// one block per owned tile, one pipeline stage: several resident blocks per SM overlap each other's
-// fetches (measured faster than the persistent two-stage form at the shared-memory footprint of
-// 128-cell tiles, profiles/r01_summary.md)
 // the transfers of another tile as L2 prefetches (called by one warp other than warp 0)
 template <typename S>
 __device__ __forceinline__ void flux_tile_prefetch(const FvArgs<S>& A, int tile) {
@@ -441,7 +385,6 @@ __global__ void __launch_bounds__(IBIS_F2_THREADS, IBIS_F2_MINB) k_flux_tile(con
     }
     (void)n_stages;
 }
-#endif
 
 template <int DIM, int FLUX, bool O2, typename S>
 __global__ void __launch_bounds__(128) k_face_flux(const FvArgs<S> A) {
@@ -690,19 +633,9 @@ void launch_flux_tile(ibis_b200_ctx* c, const FvArgs<S>& A) {
     if (A.g.n_tiles == 0) return;
     const size_t stage = (size_t)A.g.tile_cap * frec<S>::bytes;
     const int bs = A.g.tile > IBIS_F2_THREADS ? A.g.tile : IBIS_F2_THREADS;
-#if IBIS_F2_PERSIST
-    // persistent blocks, two pipeline stages when they fit
-    const int n_stages = 2 * stage <= 226 * 1024 ? 2 : 1;
-    const size_t smem = n_stages * stage;
-    int per_sm = (int)((227 * 1024) / (smem + 1024));
-    per_sm = per_sm < 1 ? 1 : (per_sm > IBIS_F2_MINB ? IBIS_F2_MINB : per_sm);
-    int grid = c->n_sm * per_sm;
-    if (grid > A.g.n_tiles) grid = A.g.n_tiles;
-#else
     const int n_stages = 1;
     const size_t smem = stage;
     const int grid = A.g.n_tiles;
-#endif
     prof_begin(c, 1);
     if (A.g.dim == 3) launch_flux_tile_dim<3, S>(c, A, grid, bs, smem, n_stages);
     else launch_flux_tile_dim<2, S>(c, A, grid, bs, smem, n_stages);
