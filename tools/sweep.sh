@@ -13,7 +13,7 @@ for spec in "$@"; do
   python - "$out" "$spec" <<'PY'
 import json, sys
 d = json.load(open(sys.argv[1])); r = d["roofline"]
-print(f"{sys.argv[2]:40s} G {r['pass_G']['avg_launch_ms']:7.3f} ms  F {r['avg_launch_ms']:7.3f} ms  eval {100 * r['evaluation']['frac']:5.1f} %  "
+print(f"{sys.argv[2]:40s} G {r['pass_G']['avg_launch_ms']:7.3f} ms  F {r.get('pass_F', r)['avg_launch_ms']:7.3f} ms  eval {100 * r['evaluation']['frac']:5.1f} %  "
       f"value {d['value'] / 1e9:6.3f} G/s  step {d['ms_per_step']:7.2f} ms  e2e {d['e2e']['value'] / 1e9:5.2f} G/s")
 PY
 done
