@@ -1013,9 +1013,10 @@ int ibis_b200_rk_step(ibis_b200_ctx* c, int fs, int cq, int n_stages, const doub
     // the dt estimate (:147) reads the same FlowStates as the first evaluation (:143): on the sides
     // path it rides along in pass F' (same frames, same cell-face order, min is exact)
     const bool dt_fused = sides_path(c) && c->cfg.reconstruction_order == 2 && !c->rk_unfused;
-    if (dt_fused) launch_fill(c, c->d_scalars + SC_DT_STABLE, INFINITY, 1);
+    if (dt_fused) launch_dt_reduce_init(c, c->d_scalars + SC_DT_STABLE);
     int rc = compute_dudt_impl<double>(c, F, &c->bufs[c->rk_k[0]], true, dt_fused ? c->d_scalars + SC_DT_STABLE : nullptr);
     if (rc) return rc;
+    if (dt_fused) launch_dt_reduce_finish(c, c->d_scalars + SC_DT_STABLE);
     rc = dt_fused ? comm::allreduce(c, c->d_scalars + SC_DT_STABLE, 1, comm::OP_MIN) : estimate_dt_device(c, F);
     if (rc) return rc;
     double* d_dt = c->d_scalars + SC_DT;

@@ -136,6 +136,9 @@ template <typename S>
 void launch_grad_sides(ibis_b200_ctx* c, const FvArgs<S>& A, int which);   // sides path, pass G' (0 all | 1 early | 2 late tiles)
 template <typename S>
 void launch_flux_tile(ibis_b200_ctx* c, const FvArgs<S>& A);       // sides path, pass F'
+// fused dt reduction in pass F': before the launch / after it (device: integer keys; emulation: doubles)
+void launch_dt_reduce_init(ibis_b200_ctx* c, double* p);
+void launch_dt_reduce_finish(ibis_b200_ctx* c, double* p);
 template <typename S>
 void launch_face_flux(ibis_b200_ctx* c, const FvArgs<S>& A);       // general path
 template <typename S>

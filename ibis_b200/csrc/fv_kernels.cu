@@ -380,7 +380,13 @@ __global__ void __launch_bounds__(IBIS_F2_THREADS, IBIS_F2_MINB) k_flux_tile(con
         __syncthreads();
         if (threadIdx.x == 0) {
             for (int w = 1; w < (int)(blockDim.x >> 5); w++) d = dmin[w] < d ? dmin[w] : d;
-            if (d == d) atomicMin(A.dt_out, (unsigned long long)__double_as_longlong(d));
+            // order-preserving key of a double (negative local time steps of inverted cells included: the
+            // reference's min picks them, finite_volume.cpp:180): flip all bits of negatives, the sign of
+            // the others; NaN never wins a `<` in the reference and is skipped here
+            if (d == d) {
+                const unsigned long long b = (unsigned long long)__double_as_longlong(d);
+                atomicMin(A.dt_out, b ^ ((b >> 63) ? ~0ull : 0x8000000000000000ull));
+            }
         }
     }
     (void)n_stages;
@@ -644,6 +650,21 @@ void launch_flux_tile(ibis_b200_ctx* c, const FvArgs<S>& A) {
 }
 template void launch_flux_tile<double>(ibis_b200_ctx*, const FvArgs<double>&);
 template void launch_flux_tile<dual>(ibis_b200_ctx*, const FvArgs<dual>&);
+
+// the fused dt reduction of pass F' works on order-preserving integer keys (see k_flux_tile)
+__global__ void k_dt_key_init(unsigned long long* p) { *p = 0x7ff0000000000000ull ^ 0x8000000000000000ull; }   // +inf
+__global__ void k_dt_key_decode(unsigned long long* p) {
+    const unsigned long long k = *p;
+    *p = k ^ ((k >> 63) ? 0x8000000000000000ull : ~0ull);
+}
+void launch_dt_reduce_init(ibis_b200_ctx* c, double* p) {
+    k_dt_key_init<<<1, 1, 0, c->stream>>>(reinterpret_cast<unsigned long long*>(p));
+    CUDA_CHECK_LAUNCH(c);
+}
+void launch_dt_reduce_finish(ibis_b200_ctx* c, double* p) {
+    k_dt_key_decode<<<1, 1, 0, c->stream>>>(reinterpret_cast<unsigned long long*>(p));
+    CUDA_CHECK_LAUNCH(c);
+}
 
 template <typename S>
 void launch_face_flux(ibis_b200_ctx* c, const FvArgs<S>& A) {

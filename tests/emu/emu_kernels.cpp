@@ -214,6 +214,9 @@ void launch_flux_tile(ibis_b200_ctx* c, const FvArgs<S>& A) {
 template void launch_flux_tile<double>(ibis_b200_ctx*, const FvArgs<double>&);
 template void launch_flux_tile<dual>(ibis_b200_ctx*, const FvArgs<dual>&);
 
+void launch_dt_reduce_init(ibis_b200_ctx* c, double* p) { *p = INFINITY; c->launches++; }
+void launch_dt_reduce_finish(ibis_b200_ctx* c, double*) { c->launches++; }
+
 template <typename S>
 void launch_face_flux(ibis_b200_ctx* c, const FvArgs<S>& A) {
 #pragma omp parallel for

@@ -199,3 +199,64 @@ def test_two_ranks_gloo():
 
 if __name__ == "__main__":
     sys.exit(pytest.main([__file__, "-x", "-q"]))
+
+
+# ---- general unstructured grids: recursive coordinate bisection (ibis_b200/partition.py) ----
+def _exchange_subs(ctxs, fss, subs):
+    states = [c.fs_download(f) for c, f in zip(ctxs, fss)]
+    for r, s in enumerate(subs):
+        for p, q in enumerate(s.peer_ranks):
+            o = subs[q]
+            qp = o.peer_ranks.index(r)
+            mine = s.recv_cells[s.recv_offsets[p]:s.recv_offsets[p + 1]]
+            theirs = o.send_cells[o.send_offsets[qp]:o.send_offsets[qp + 1]]
+            assert len(mine) == len(theirs)
+            states[r][mine] = states[q][theirs]
+    for c, f, st in zip(ctxs, fss, states):
+        c.fs_upload(f, st)
+
+
+@pytest.mark.parametrize("name,n_parts", [("mixed3d_walls", 3), ("naca_omesh", 4), ("tri2d", 2), ("box3d_ausmdv", 5),
+                                          ("quad2d_viscous", 3)])
+def test_rcb_partition_equals_whole_grid(name, n_parts):
+    from ibis_b200 import partition
+    lib = emu_lib()
+    mesh, config, g, prim = cases.build_case(name)
+    owner, subs = partition.decompose(g, n_parts)
+    counts = np.bincount(owner, minlength=n_parts)
+    assert counts.max() - counts.min() <= 1 and counts.sum() == g.n_cells
+
+    wctx = Context(g, config, lib_path=lib)
+    wfs, wdq = wctx.fs_create(), wctx.cq_create()
+    wctx.fs_upload(wfs, prim)
+    wctx.compute_dudt(wfs, wdq, True)
+    ref = wctx.cq_download(wdq)
+    ref_dt = wctx.estimate_dt(wfs)
+    ref_o1 = None
+    wctx.compute_dudt(wfs, wdq, False)
+    ref_o1 = wctx.cq_download(wdq)
+
+    ctxs = [Context(s, config, lib_path=lib) for s in subs]
+    fss, dqs = [], []
+    for s, c in zip(subs, ctxs):
+        loc = np.ascontiguousarray(prim[s.local_to_global])
+        loc[s.n_owned:s.n_cells] = -1.0e300                 # halo values arrive only through the exchange
+        f = c.fs_create()
+        c.fs_upload(f, loc)
+        fss.append(f)
+        dqs.append(c.cq_create())
+    _exchange_subs(ctxs, fss, subs)
+    dts, seen = [], 0
+    for s, c, f, dq in zip(subs, ctxs, fss, dqs):
+        own = s.local_to_global[:s.n_owned]
+        c.compute_dudt(f, dq, True)
+        d = c.cq_download(dq)
+        assert np.array_equal(d[:s.n_owned], ref[own]), f"{name}: owned residuals differ from the whole grid"
+        assert not d[s.n_owned:].any()
+        dts.append(c.estimate_dt(f))
+        c.compute_dudt(f, dq, False)
+        assert np.array_equal(c.cq_download(dq)[:s.n_owned], ref_o1[own]), f"{name}: first-order residuals differ"
+        seen += s.n_owned
+    assert seen == g.n_cells and min(dts) == ref_dt
+    for c in ctxs + [wctx]:
+        c.close()

@@ -24,6 +24,9 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--edge", dest="n", type=int, default=48)
     ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--case", default=None,
+                    help="a case of tests/cases.py (unstructured SU2 mesh) decomposed by recursive coordinate "
+                         "bisection (ibis_b200/partition.py) instead of the box in slabs")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -37,19 +40,30 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n = args.n
-    config = bench.box_config()
     tab = cfg.BUTCHER["ssp-rk3"]
-    whole = BoxGrid(n)
-    gprim = cases.perturbed_state(whole, 3)
-
-    slab = bench.box_grid_fast(n, rank, world)
-    ijk = np.clip(np.floor(slab.cell_centroid[:slab.n_cells] * n).astype(np.int64), 0, n - 1)
-    gid = ijk[:, 0] + n * (ijk[:, 1] + n * ijk[:, 2])
-    loc = np.ones((slab.n_total, 7))
-    loc[:slab.n_cells] = gprim[gid]
-    loc[slab.n_owned:slab.n_cells] = -1.0e300          # halo values must come through NCCL
+    if args.case:
+        from ibis_b200 import partition
+        mesh, config, whole, gprim = cases.build_case(args.case)
+        _, subs = partition.decompose(whole, world)
+        slab = subs[rank]
+        gid = slab.local_to_global[:slab.n_cells]
+        loc = np.ascontiguousarray(gprim[slab.local_to_global])
+        peers = slab.peer_ranks
+        n_global = whole.n_cells
+    else:
+        config = bench.box_config()
+        whole = BoxGrid(n)
+        gprim = cases.perturbed_state(whole, 3)
+        slab = bench.box_grid_fast(n, rank, world)
+        ijk = np.clip(np.floor(slab.cell_centroid[:slab.n_cells] * n).astype(np.int64), 0, n - 1)
+        gid = ijk[:, 0] + n * (ijk[:, 1] + n * ijk[:, 2])
+        loc = np.ones((slab.n_total, 7))
+        loc[:slab.n_cells] = gprim[gid]
+        peers = [rank + d for d in slab.peer_dir]
+        n_global = n ** 3
+    loc[slab.n_owned:slab.n_cells] = -1.0e300          # halo values must come through the exchange
     ctx = Context(slab, config, device=local)
-    mode = ctx.connect(dist, rank, world, [rank + d for d in slab.peer_dir], slab.send_offsets, slab.send_cells,
+    mode = ctx.connect(dist, rank, world, peers, slab.send_offsets, slab.send_cells,
                        slab.recv_offsets, slab.recv_cells, p2p=os.environ.get("IBIS_B200_HALO", "p2p") != "nccl")
     fs, cq = ctx.fs_create(), ctx.cq_create()
     ctx.fs_upload(fs, loc)
@@ -80,8 +94,8 @@ def main():
             seen += len(g_ids)
             ok &= d == wdts
             ok &= bool(np.allclose(nm, wnorms, rtol=1e-12))
-        ok &= mism == 0 and seen == n ** 3
-        print(json.dumps({"check": "decomposed == whole box", "n": n, "ranks": world, "halo": mode, "steps": args.steps,
+        ok &= mism == 0 and seen == n_global
+        print(json.dumps({"check": "decomposed == whole grid", "grid": args.case or f"box {n}^3", "ranks": world, "halo": mode, "steps": args.steps,
                           "cells_compared": seen, "cells_differing": mism, "dt_identical": bool(gathered[0][2] == wdts),
                           "l2_norms_decomposed": gathered[0][3], "l2_norms_whole": list(wnorms), "ok": bool(ok)}))
         wctx.close()
