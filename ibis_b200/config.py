@@ -83,6 +83,19 @@ def subsonic_outflow(pressure):
     return _bc([{"type": "subsonic_outflow", "pressure": pressure}])
 
 
+def boundary_layer_inflow(height, velocity_profile, temperature_profile, pressure):
+    # prep.py:549-557
+    return _bc([{"type": "boundary_layer_profile",
+                 "profile": {"height": list(height), "v": list(velocity_profile),
+                             "T": list(temperature_profile), "p": pressure}}])
+
+
+def constant_flux(fs):
+    # prep.py:609-617 (also exported there as bow_shock_fit)
+    return _bc([{"type": "flow_state_copy", "flow_state": dict(fs)}],
+               post=[{"type": "constant_flux", "flow_state": dict(fs)}])
+
+
 def runge_kutta(method="ssp-rk3", cfl=0.5, max_step=100, max_time=1.0, dt_init=-1.0,
                 print_frequency=1000, plot_frequency=-1, plot_every_n_steps=-1,
                 residual_frequency=-1, residuals_every_n_steps=-1):

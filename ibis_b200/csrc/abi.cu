@@ -177,10 +177,42 @@ FvArgs<S> make_args(ibis_b200_ctx* c, Buffer* fs, Buffer* dudt, bool allow_recon
     return A;
 }
 
+// CubicSpline::CubicSpline (util/cubic_spline.cpp:9-89): second derivatives of the natural spline through
+// (x_i, y_i) by the reference's assembly and Thomas sweep, operation for operation.  The result is indexed
+// by knot, n entries with y''_0 = y''_{n-1} = 0 (see spline_eval in fv_bodies.h for the reference's two
+// out-of-bounds entries).
+std::vector<double> spline_second_derivatives(const double* x, const double* y, int n) {
+    const int ne = n - 2;
+    std::vector<double> diag(ne, 0.0), upper(ne, 0.0), rhs(ne, 0.0), ydd(n, 0.0);
+    for (int i = 0; i <= ne; i++) {
+        const double dxi = x[i + 1] - x[i], dyi = y[i + 1] - y[i];
+        if (i != ne) {
+            diag[i] += dxi;
+            rhs[i] -= dyi / dxi;
+        }
+        if (i == 0) continue;
+        rhs[i - 1] += dyi / dxi;
+        diag[i - 1] += dxi;
+        upper[i - 1] += dxi;        // upper[ne - 1] is never read
+    }
+    for (int i = 0; i < ne; i++) {
+        rhs[i] *= 6;
+        diag[i] *= 2;
+    }
+    for (int i = 1; i < ne; i++) {
+        const double w = upper[i - 1] / diag[i - 1];
+        diag[i] = diag[i] - w * upper[i - 1];
+        rhs[i] = rhs[i] - w * rhs[i - 1];
+    }
+    ydd[n - 2] = rhs[ne - 1] / diag[ne - 1];
+    for (int i = ne - 2; i >= 0; i--) ydd[i + 1] = (rhs[i] - upper[i] * ydd[i + 2]) / diag[i];
+    return ydd;
+}
+
 // lazily allocated FiniteVolume temporaries for one scalar type
 // second-order inviscid evaluations go through the sides path (fv_bodies.h)
 bool sides_path(const ibis_b200_ctx* c) {
-    return c->use_sides && c->cfg.reconstruction_order == 2 && !c->cfg.viscous;
+    return c->use_sides && c->cfg.reconstruction_order == 2 && !c->cfg.viscous && !c->has_flux_actions;
 }
 
 // dual-number evaluations (16-byte scalars: one tile per SM in the sides kernels) measured 10 % faster
@@ -209,7 +241,7 @@ int ensure_fv_temporaries(ibis_b200_ctx* c, bool want_grad = false) {
         rc = dev_alloc_zero<S>(c, (int64_t)NVARS * c->cstride, lim);
         if (rc) return fail(c, rc, "out of device memory (limiters)");
     }
-    if (c->cfg.viscous && !*flux) {
+    if ((c->cfg.viscous || c->has_flux_actions) && !*flux) {
         int rc = dev_alloc_zero<S>(c, (int64_t)5 * c->fstride, flux);
         if (rc) return fail(c, rc, "out of device memory (face flux)");
     }
@@ -261,11 +293,15 @@ int compute_dudt_impl(ibis_b200_ctx* c, Buffer* fs, Buffer* dudt, bool allow_rec
         return 0;
     }
     if (A.order2) launch_grad_limit(c, A, false);
-    if (A.viscous) {
+    if (A.viscous || c->has_flux_actions) {
+        // the reference's own sequence over a stored face-flux array (finite_volume.cpp:62-81)
         launch_face_flux(c, A);
-        if (c->has_previscous) launch_bc(c, A, IBIS_B200_PHASE_PRE_VISCOUS_GRAD);
-        launch_grad_limit(c, A, true);
-        launch_face_viscous(c, A);
+        if (c->has_flux_actions) launch_bc(c, A, IBIS_B200_PHASE_POST_CONVECTIVE_FLUX);
+        if (A.viscous) {
+            if (c->has_previscous) launch_bc(c, A, IBIS_B200_PHASE_PRE_VISCOUS_GRAD);
+            launch_grad_limit(c, A, true);
+            launch_face_viscous(c, A);
+        }
         launch_integral(c, A);
     } else {
         launch_residual(c, A);
@@ -411,26 +447,52 @@ int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd_ref, con
             bf_tag[k] = t;
         }
     std::vector<BcAction> acts;
-    std::vector<int> act_off((size_t)2 * (gd->n_tags + 1), 0);
-    for (int phase = 0; phase < 2; phase++) {
+    std::vector<double> bc_tab;
+    std::vector<int> act_off((size_t)N_PHASES * (gd->n_tags + 1), 0);
+    for (int phase = 0; phase < N_PHASES; phase++) {
         for (int t = 0; t < gd->n_tags; t++) {
             act_off[(size_t)phase * (gd->n_tags + 1) + t] = (int)acts.size();
             for (const auto& a : c->bc_actions)
                 if (a.tag == t && a.phase == phase) {
-                    if (a.type < 0 || a.type > IBIS_B200_BC_SUBSONIC_OUTFLOW) {
+                    // the reference has one factory per kind (boundary.cpp:449-492): a ghost-cell action
+                    // in a flux list, or the reverse, is "Unknown ... action" there
+                    const bool flux_action = a.type == IBIS_B200_BC_CONSTANT_FLUX;
+                    if (a.type < 0 || a.type > IBIS_B200_BC_CONSTANT_FLUX ||
+                        flux_action != (phase == IBIS_B200_PHASE_POST_CONVECTIVE_FLUX)) {
                         ibis_b200_destroy(c);
-                        return fail(nullptr, IBIS_B200_EINVAL, "Unknown boundary action");
+                        return fail(nullptr, IBIS_B200_EINVAL, phase == IBIS_B200_PHASE_POST_CONVECTIVE_FLUX
+                                                                   ? "Unknown flux action" : "Unknown boundary action");
                     }
                     BcAction b;
                     b.type = a.type;
                     b.pad = 0;
                     for (int q = 0; q < 7; q++) b.params[q] = a.params[q];
+                    if (a.type == IBIS_B200_BC_BOUNDARY_LAYER_PROFILE) {
+                        const int64_t n = (int64_t)a.params[1], off = (int64_t)a.params[2];
+                        std::string why;
+                        if (n < 4) why = "Insufficient points for cubic spline";        // cubic_spline.cpp:12-14
+                        else if (!cfg->bc_tables || off < 0 || off + 3 * n > cfg->n_bc_tables)
+                            why = "boundary_layer_profile: table outside bc_tables";
+                        if (!why.empty()) {
+                            ibis_b200_destroy(c);
+                            return fail(nullptr, IBIS_B200_EINVAL, why.c_str());
+                        }
+                        const double* x = cfg->bc_tables + off;
+                        b.params[2] = (double)bc_tab.size();
+                        bc_tab.insert(bc_tab.end(), x, x + 3 * n);
+                        for (int q = 1; q <= 2; q++) {
+                            const std::vector<double> dd = spline_second_derivatives(x, x + q * n, (int)n);
+                            bc_tab.insert(bc_tab.end(), dd.begin(), dd.end());
+                        }
+                    }
                     acts.push_back(b);
-                    if (phase == 1) c->has_previscous = true;
+                    if (phase == IBIS_B200_PHASE_PRE_VISCOUS_GRAD) c->has_previscous = true;
+                    if (phase == IBIS_B200_PHASE_POST_CONVECTIVE_FLUX) c->has_flux_actions = true;
                 }
         }
         act_off[(size_t)phase * (gd->n_tags + 1) + gd->n_tags] = (int)acts.size();
     }
+    if (bc_tab.empty()) bc_tab.push_back(0.0);
     if (acts.empty()) acts.push_back(BcAction());
 
     c->ref2int = R.ref2int;
@@ -477,7 +539,7 @@ int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd_ref, con
         UP(fgeom, dd, f_geom)
     }
     UP(bf_face, di, bf_face) UP(bf_tag, di, bf_tag)
-    UP(acts, da, act) UP(act_off, di, act_off)
+    UP(acts, da, act) UP(act_off, di, act_off) UP(bc_tab, dd, bc_tab)
     if (morton) {
         rc = upload_vec(c, c->ref2int, &c->d_ref2int);
         if (rc) { ibis_b200_destroy(c); return fail(nullptr, rc, "grid upload failed"); }

@@ -65,6 +65,7 @@ struct ibis_b200_ctx {
     ibis_b200_config cfg;
     std::vector<ibis_b200_bc_action> bc_actions;
     bool has_previscous = false;
+    bool has_flux_actions = false;       // any constant_flux: evaluations go through the face-flux array
 
     // internal renumbering (layout.h): reference cell id -> internal id, nullptr = identity
     int* d_ref2int = nullptr;

@@ -25,7 +25,9 @@ constexpr int NVARS = 6;      // gradient slots: rho, thermo-2, vx, vy, vz, T(vi
 enum { V_RHO = 0, V_TH2 = 1, V_VX = 2, V_VY = 3, V_VZ = 4, V_TVISC = 5 };
 enum { F_RHO = 0, F_P = 1, F_T = 2, F_E = 3, F_VX = 4, F_VY = 5, F_VZ = 6 };
 enum { BC_FLOW_STATE_COPY = 0, BC_INTERNAL_COPY = 1, BC_REFLECT_NORMAL = 2, BC_VEL_REFLECT = 3,
-       BC_FIX_TEMPERATURE = 4, BC_SUBSONIC_INFLOW = 5, BC_SUBSONIC_OUTFLOW = 6 };
+       BC_FIX_TEMPERATURE = 4, BC_SUBSONIC_INFLOW = 5, BC_SUBSONIC_OUTFLOW = 6,
+       BC_BOUNDARY_LAYER_PROFILE = 7, BC_CONSTANT_FLUX = 8 };
+enum { PHASE_PRE_RECONSTRUCTION = 0, PHASE_PRE_VISCOUS_GRAD = 1, PHASE_POST_CONVECTIVE_FLUX = 2, N_PHASES = 3 };
 
 struct BcAction {
     int type;
@@ -68,6 +70,9 @@ struct GridDev {
     const BcAction* act;
     const int* act_off;
     int n_tags;
+    // spline tables of the boundary_layer_profile actions: for an action with params {p, n, off}
+    // bc_tab[off ..] = x[n] | v[n] | T[n] | v''[n] | T''[n]  (util/cubic_spline.cpp:9-89)
+    const double* bc_tab;
     // tiles of `tile` consecutive owned cells for the tiled residual kernel (pass F): the
     // interfaces first listed by a cell of tile b ("home" interfaces) are the contiguous range
     // [home0[b], home0[b+1]); the other interfaces of its cells ("foreign", homed in an earlier
@@ -149,6 +154,27 @@ struct FvArgs {
     int order2;        // reconstruction order 2 in effect for this evaluation
     int viscous;
 };
+
+// CubicSpline::eval (util/cubic_spline.h:14-45): x, y, y'' are n-point tables.  The reference's
+// constructor sizes y'' for the n - 2 interior knots but indexes it by knot (cubic_spline.cpp:46,
+// 80-83 and cubic_spline.h:33-40), so that its evaluations in the LAST TWO intervals read past the
+// end of the allocation; the tables here hold the n values those formulas address (natural
+// spline: y''_0 = y''_{n-1} = 0), which is what the reference computes wherever it is defined.
+IBIS_HD double spline_eval(const double* x_, const double* y_, const double* ydd_, int n, double x) {
+    if (x <= x_[0]) return y_[0];
+    if (x >= x_[n - 1]) return y_[n - 1];
+    int idx = 0;
+    for (int i = 0; i < n; i++)
+        if (x_[i] >= x) { idx = i - 1; break; }
+    const double dx_plus = x_[idx + 1] - x;
+    const double dx_minus = x - x_[idx];
+    const double delta_xi = x_[idx + 1] - x_[idx];
+    const double a = (ydd_[idx] * dx_plus * dx_plus * dx_plus + ydd_[idx + 1] * dx_minus * dx_minus * dx_minus) /
+                     (6 * delta_xi);
+    const double b = (y_[idx] / delta_xi - ydd_[idx] * delta_xi / 6) * dx_plus;
+    const double c = (y_[idx + 1] / delta_xi - ydd_[idx + 1] * delta_xi / 6) * dx_minus;
+    return a + b + c;
+}
 
 // ---------------------------------------------------------------------------------------
 // boundary conditions: one thread per boundary face applies its tag's action list in order
@@ -260,6 +286,38 @@ IBIS_HD void bc_body(const FvArgs<S>& A, int k, int phase) {
                 M::store(fs[F_VX], ghost, 2.0 * vx_face - vvx);
                 M::store(fs[F_VY], ghost, 2.0 * vy_face - vvy);
                 M::store(fs[F_VZ], ghost, 2.0 * vz_face - vvz);
+                break;
+            }
+            case BC_BOUNDARY_LAYER_PROFILE: {                // boundary.cpp:61-95
+                const int n = (int)act.params[1];
+                const double* tab = g.bc_tab + (long)act.params[2];
+                const double pos = g.cy[ghost];              // real_part of the ghost centroid's y
+                S p = S(act.params[0]);
+                S T = S(spline_eval(tab, tab + 2 * n, tab + 4 * n, n, pos));
+                M::store(fs[F_P], ghost, p);
+                M::store(fs[F_T], ghost, T);
+                M::store(fs[F_RHO], ghost, rho_from_pT(p, T, A.gas.R));       // update_thermo_from_pT
+                M::store(fs[F_E], ghost, A.gas.Cv * T);
+                M::store(fs[F_VX], ghost, S(spline_eval(tab, tab + n, tab + 3 * n, n, pos)));
+                M::store(fs[F_VY], ghost, S(0.0));
+                M::store(fs[F_VZ], ghost, S(0.0));
+                break;
+            }
+            case BC_CONSTANT_FLUX: {                         // boundary.cpp:405-444 (a FluxAction: phase 2)
+                const long fs_ = g.fstride;
+                S nx = S(g.f_n[f]), ny = S(g.f_n[g.fstride + f]), nz = S(g.f_n[2 * g.fstride + f]);
+                S rho = S(act.params[0]), p = S(act.params[1]), T = S(act.params[2]);
+                S vx = S(act.params[4]), vy = S(act.params[5]), vz = S(act.params[6]);
+                S u = A.gas.Cv * T;                          // gas_model.internal_energy (gas_model.h:164)
+                S rel_vx = vx - S(0.0), rel_vy = vy - S(0.0), rel_vz = vz - S(0.0);   // face_vel = 0: static grid
+                S mass_flux = rho * (rel_vx * nx + rel_vy * ny + rel_vz * nz);
+                M::store(A.flux, 0 * fs_ + f, mass_flux);
+                M::store(A.flux, 1 * fs_ + f, p * nx + vx * mass_flux);
+                M::store(A.flux, 2 * fs_ + f, p * ny + vy * mass_flux);
+                if (g.dim == 3) M::store(A.flux, 3 * fs_ + f, p * nz + vz * mass_flux);
+                // `vy * nx` is the reference's (boundary.cpp:441), kept for parity
+                M::store(A.flux, 4 * fs_ + f, mass_flux * (u + 0.5 * (vx * vx + vy * vy + vz * vz)) +
+                                                  p * (vx * nx + vy * nx + vz * nz));
                 break;
             }
         }

@@ -17,8 +17,9 @@ LIMITER = {"unlimited": 0, "barth_jespersen": 1}
 THERMO = {"rho_p": 0, "rho_T": 1, "rho_u": 2, "p_T": 3}
 BC = {"flow_state_copy": 0, "internal_copy": 1, "internal_copy_reflect_normal": 2,
       "internal_vel_copy_reflect": 3, "fix_temperature": 4, "subsonic_inflow": 5,
-      "subsonic_outflow": 6}
-PHASE = {"pre_reconstruction": 0, "pre_viscous_grad": 1}
+      "subsonic_outflow": 6, "boundary_layer_profile": 7}
+FLUX_ACTION = {"constant_flux": 8}          # build_flux_action (boundary.cpp:482-492)
+PHASE = {"pre_reconstruction": 0, "pre_viscous_grad": 1, "post_convective_flux": 2}
 
 
 class IbisB200Error(RuntimeError):
@@ -53,7 +54,8 @@ class Config(C.Structure):
                 ("viscous_signal_factor", C.c_double),
                 ("R", C.c_double), ("Cv", C.c_double), ("Cp", C.c_double), ("gamma", C.c_double),
                 ("mu0", C.c_double), ("T0", C.c_double), ("Ts", C.c_double), ("Pr", C.c_double),
-                ("bc_actions", C.POINTER(BcAction))]
+                ("bc_actions", C.POINTER(BcAction)),
+                ("n_bc_tables", C.c_int64), ("bc_tables", C.POINTER(C.c_double))]
 
 
 def _flow_state_params(fs):
@@ -98,32 +100,41 @@ def flatten_config(config, tags):
     cfgs.T0 = float(tp["viscosity"]["T_0"])
     cfgs.Ts = float(tp["viscosity"]["T_s"])
     cfgs.Pr = float(tp["thermal_conductivity"]["Pr"])
-    actions = []
+    actions, tables = [], []
     bnds = config["grid"]["boundaries"]
     for t, tag in enumerate(tags):
         b = bnds[tag]
-        if b.get("post_convective_flux"):
-            raise IbisB200Error("post_convective_flux actions (constant_flux) are not on the hot path")
-        for phase in ("pre_reconstruction", "pre_viscous_grad"):
+        for phase in ("pre_reconstruction", "post_convective_flux", "pre_viscous_grad"):
+            flux_phase = phase == "post_convective_flux"
             for act in b.get(phase, []):
-                if act["type"] not in BC:
-                    raise IbisB200Error("Unknown boundary action")
+                if act["type"] not in (FLUX_ACTION if flux_phase else BC):
+                    raise IbisB200Error("Unknown flux action" if flux_phase else "Unknown boundary action")
                 a = BcAction()
-                a.tag, a.phase, a.type = t, PHASE[phase], BC[act["type"]]
+                a.tag, a.phase, a.type = t, PHASE[phase], (FLUX_ACTION if flux_phase else BC)[act["type"]]
                 p = [0.0] * 8
-                if act["type"] in ("flow_state_copy", "subsonic_inflow"):
+                if act["type"] in ("flow_state_copy", "subsonic_inflow", "constant_flux"):
                     p = _flow_state_params(act["flow_state"])
                 elif act["type"] == "fix_temperature":
                     p[0] = float(act["temperature"])
                 elif act["type"] == "subsonic_outflow":
                     p[0] = float(act["pressure"])
+                elif act["type"] == "boundary_layer_profile":       # boundary.cpp:51-58
+                    prof = act["profile"]
+                    n = len(prof["height"])
+                    if len(prof["v"]) != n or len(prof["T"]) != n:
+                        raise IbisB200Error("Cubic spline has different number of x and y points")
+                    p[0], p[1], p[2] = float(prof["p"]), float(n), float(len(tables))
+                    tables += [float(v) for k in ("height", "v", "T") for v in prof[k]]
                 for i in range(8):
                     a.params[i] = p[i]
                 actions.append(a)
     arr = (BcAction * max(len(actions), 1))(*actions)
     cfgs.n_bc_actions = len(actions)
     cfgs.bc_actions = C.cast(arr, C.POINTER(BcAction))
-    cfgs._keepalive = arr
+    tab = (C.c_double * max(len(tables), 1))(*tables)
+    cfgs.n_bc_tables = len(tables)
+    cfgs.bc_tables = C.cast(tab, C.POINTER(C.c_double))
+    cfgs._keepalive = (arr, tab)
     return cfgs
 
 

@@ -47,18 +47,25 @@ enum { IBIS_B200_LIMITER_UNLIMITED = 0, IBIS_B200_LIMITER_BARTH_JESPERSEN = 1 };
  * upstream (convective_flux.cpp:53-55) and rejected with EINVAL */
 enum { IBIS_B200_THERMO_RHO_P = 0, IBIS_B200_THERMO_RHO_T = 1, IBIS_B200_THERMO_RHO_U = 2,
        IBIS_B200_THERMO_P_T = 3 };
-/* finite_volume/boundaries/boundary.cpp:449-479 (build_boundary_action) */
+/* finite_volume/boundaries/boundary.cpp:449-479 (build_boundary_action) and :482-492
+ * (build_flux_action: constant_flux, the one FluxAction) */
 enum { IBIS_B200_BC_FLOW_STATE_COPY = 0, IBIS_B200_BC_INTERNAL_COPY = 1,
        IBIS_B200_BC_INTERNAL_COPY_REFLECT_NORMAL = 2, IBIS_B200_BC_INTERNAL_VEL_COPY_REFLECT = 3,
        IBIS_B200_BC_FIX_TEMPERATURE = 4, IBIS_B200_BC_SUBSONIC_INFLOW = 5,
-       IBIS_B200_BC_SUBSONIC_OUTFLOW = 6 };
+       IBIS_B200_BC_SUBSONIC_OUTFLOW = 6, IBIS_B200_BC_BOUNDARY_LAYER_PROFILE = 7,
+       IBIS_B200_BC_CONSTANT_FLUX = 8 };
 /* which list of BoundaryCondition the action belongs to (boundary.cpp:495-515) */
-enum { IBIS_B200_PHASE_PRE_RECONSTRUCTION = 0, IBIS_B200_PHASE_PRE_VISCOUS_GRAD = 1 };
+enum { IBIS_B200_PHASE_PRE_RECONSTRUCTION = 0, IBIS_B200_PHASE_PRE_VISCOUS_GRAD = 1,
+       IBIS_B200_PHASE_POST_CONVECTIVE_FLUX = 2 };
 
-/* One GhostCellAction of one boundary tag, in the order the reference applies them
+/* One GhostCellAction / FluxAction of one boundary tag, in the order the reference applies them
  * (tags alphabetical: finite_volume.cpp:187-218; actions in list order: boundary.cpp:517-543).
- * params: flow_state_copy / subsonic_inflow = {rho,p,T,e,vx,vy,vz};
- *         fix_temperature = {Twall}; subsonic_outflow = {pressure}. */
+ * params: flow_state_copy / subsonic_inflow / constant_flux = {rho,p,T,e,vx,vy,vz};
+ *         fix_temperature = {Twall}; subsonic_outflow = {pressure};
+ *         boundary_layer_profile = {p, n_pts, offset}: the profile's "height", "v" and "T" lists
+ *         (boundary.cpp:51-58), n_pts doubles each, back to back at config->bc_tables + offset.
+ * constant_flux is only valid in phase POST_CONVECTIVE_FLUX and the ghost-cell actions only in the
+ * other two, like the reference's two factories. */
 typedef struct {
     int32_t tag;
     int32_t phase;
@@ -111,6 +118,8 @@ typedef struct {
     double R, Cv, Cp, gamma;          /* gas_model (gas/gas_model.h:58-62) */
     double mu0, T0, Ts, Pr;           /* transport_properties (gas/transport_properties.h:22-26,57-60) */
     const ibis_b200_bc_action* bc_actions;
+    int64_t n_bc_tables;              /* doubles at bc_tables (0 without boundary_layer_profile) */
+    const double* bc_tables;          /* borrowed during ibis_b200_create only */
 } ibis_b200_config;
 
 /* ---- context ------------------------------------------------------------------------- */

@@ -115,6 +115,46 @@ _add("naca_omesh", lambda: su2.naca0012_omesh(32, 12),
      lambda: {"wall": cfg.adiabatic_no_slip_wall(), "inflow": cfg.subsonic_inflow(FS2_SUB),
               "outflow": cfg.subsonic_outflow(101325.0)}, 0.2, flux_calculator="ausmdv", viscous=True)
 
+
+
+# the two remaining boundary actions: boundary_layer_profile (a cubic spline in
+# the ghost centroid's y) and constant_flux (the one FluxAction).  The profile knots keep every ghost
+# centroid out of the LAST TWO spline intervals, where the reference reads past the end of its y''
+# array (see spline_eval in ibis_b200/csrc/fv_bodies.h): below the first knot, inside, and above the
+# last knot are all exercised.
+def quad2_profile_bcs():
+    h = [0.08, 0.2, 0.3, 0.45, 0.6, 0.8, 1.1, 2.0, 3.0]                 # ghost y in (0, 1): clamp below 0.08
+    v = [0.0, 310.0, 520.0, 700.0, 840.0, 930.0, 990.0, 1000.0, 1000.0]
+    T = [500.0, 470.0, 430.0, 390.0, 350.0, 320.0, 305.0, 300.0, 300.0]
+    b = quad2_visc_bcs()
+    b["left"] = cfg.boundary_layer_inflow(h, v, T, 101325.0)
+    return b
+
+
+def box3_profile_flux_bcs():
+    # regular 6^3 box: ghost centroids at y = (j + 1/2)/6; 0.5833 is in [0.45, 0.6], none in the last two
+    # intervals [0.6, 0.65], [0.65, 0.7]; 0.75 and 0.9167 take the clamp above the last knot
+    h = [0.0, 0.1, 0.2, 0.3, 0.45, 0.6, 0.65, 0.7]
+    v = [0.0, 260.0, 480.0, 650.0, 820.0, 930.0, 950.0, 960.0]
+    T = [450.0, 430.0, 400.0, 370.0, 335.0, 310.0, 304.0, 300.0]
+    b = box3_bcs()
+    b["west"] = cfg.boundary_layer_inflow(h, v, T, 95000.0)
+    b["south"] = cfg.constant_flux(FS3)
+    b["bottom"] = cfg.slip_wall()
+    return b
+
+
+def quad2_flux_visc_bcs():
+    b = quad2_visc_bcs()
+    b["left"] = cfg.constant_flux(FS2)
+    b["top"] = cfg.constant_flux(cfg.flow_state(rho=0.9, T=350.0, vx=-300.0, vy=-450.0))
+    return b
+
+
+_add("quad2d_bl_profile", _quad, quad2_profile_bcs, 0.5, flux_calculator="ausmdv", viscous=True)
+_add("box3d_profile_cflux", lambda: su2.box_hex(6), box3_profile_flux_bcs, flux_calculator="ausmdv")
+_add("quad2d_cflux_viscous", _quad, quad2_flux_visc_bcs, 0.5, flux_calculator="hanel", viscous=True)
+
 VISCOUS_CASES = [k for k, v in CASES.items() if v[3].get("viscous")]
 
 

@@ -22,9 +22,17 @@ import refharness as rh  # noqa: E402
 
 
 def main():
+    pad = os.path.join(ROOT, "oracle", "_ref", "libpadmalloc.so")
+    if os.path.exists(pad) and "libpadmalloc" not in os.environ.get("LD_PRELOAD", ""):
+        # oracle/ref_build/padmalloc.c: the reference's CubicSpline constructor overruns two arrays
+        os.environ["LD_PRELOAD"] = pad
+        os.execv(sys.executable, [sys.executable] + sys.argv)
     tmp = "/tmp/ibis_golden"
     os.makedirs(tmp, exist_ok=True)
+    only = sys.argv[1:]                      # optional: regenerate just these cases
     for name in cases.CASES:
+        if only and name not in only:
+            continue
         mesh, config, g, prim = cases.build_case(name)
         path = os.path.join(tmp, name + ".su2")
         mesh.write(path)

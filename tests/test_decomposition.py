@@ -217,7 +217,8 @@ def _exchange_subs(ctxs, fss, subs):
 
 
 @pytest.mark.parametrize("name,n_parts", [("mixed3d_walls", 3), ("naca_omesh", 4), ("tri2d", 2), ("box3d_ausmdv", 5),
-                                          ("quad2d_viscous", 3)])
+                                          ("quad2d_viscous", 3), ("box3d_profile_cflux", 3),
+                                          ("quad2d_bl_profile", 2)])
 def test_rcb_partition_equals_whole_grid(name, n_parts):
     from ibis_b200 import partition
     lib = emu_lib()

@@ -72,7 +72,7 @@ def test_gmres_known_answer_on_device():
     ctx.close()
 
 
-@pytest.mark.parametrize("name", ["mixed3d_walls", "box3d_ausmdv", "naca_omesh"])
+@pytest.mark.parametrize("name", ["mixed3d_walls", "box3d_ausmdv", "naca_omesh", "box3d_profile_cflux"])
 def test_fused_rk_step_equals_kernel_by_kernel_step(name, monkeypatch):
     """ibis_b200_rk_step with its fused pieces (dt reduction riding in pass F', one update kernel per
     stage) against the same step made of one kernel per reference call, bit for bit -- including on
