@@ -34,6 +34,12 @@ int fail(ibis_b200_ctx* c, int code, const std::string& msg) {
             return fail(c, IBIS_B200_ECUDA, std::string(#expr) + ": " + gpu::error_string(e__)); \
     } while (0)
 
+}  // namespace
+namespace ib {
+int fail_global(int code, const char* msg) { return fail(nullptr, code, msg); }
+}  // namespace ib
+namespace {
+
 int64_t pad_to(int64_t n, int64_t m) { return (n + m - 1) / m * m; }
 
 // IBIS_B200_TIMING=1: wall time of the stages of ibis_b200_create on stderr

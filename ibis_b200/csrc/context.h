@@ -13,6 +13,8 @@
 #include "ibis_b200.h"
 
 namespace ib {
+// records msg as the thread's ibis_b200_last_error(NULL) and returns code (abi.cu)
+int fail_global(int code, const char* msg);
 
 enum BufKind { BUF_FREE = 0, BUF_FS = 1, BUF_CQ = 2, BUF_VEC = 3, BUF_BASIS = 4 };
 

@@ -46,6 +46,12 @@ class GridDesc(C.Structure):
                 ("tag_offsets", _i64p), ("tag_faces", _i64p), ("n_owned", C.c_int64)]
 
 
+class MeshDesc(C.Structure):
+    _fields_ = [("dim", C.c_int32), ("n_tags", C.c_int32), ("n_vertices", C.c_int64), ("n_cells", C.c_int64),
+                ("vertices", _dp), ("cell_types", _i32p), ("cell_vertices", _i64p),
+                ("marker_offsets", _i64p), ("marker_vertices", _i64p)]
+
+
 class Config(C.Structure):
     _fields_ = [("flux_calculator", C.c_int32), ("reconstruction_order", C.c_int32),
                 ("limiter", C.c_int32), ("thermo_interpolator", C.c_int32),
@@ -244,6 +250,7 @@ class Library:
             "ibis_b200_halo_p2p_enable": [vp, i],
             "ibis_b200_flow_read_native": [vp, i, vp, vp, vp, vp, vp],
             "ibis_b200_flow_write_native": [vp, i, vp, vp, vp, vp, vp],
+            "ibis_b200_grid_build": [C.POINTER(vp), C.POINTER(MeshDesc), i], "ibis_b200_grid_destroy": [vp],
         }
         for name, args in sig.items():
             f = getattr(L, name)
@@ -255,12 +262,65 @@ class Library:
         L.ibis_b200_launch_count.restype = C.c_int64
         L.ibis_b200_stream.argtypes = [vp]
         L.ibis_b200_stream.restype = vp
+        L.ibis_b200_grid_desc_of.argtypes = [vp]
+        L.ibis_b200_grid_desc_of.restype = C.POINTER(GridDesc)
+        for name in ("ibis_b200_grid_face_vertices", "ibis_b200_grid_tag_ghosts"):
+            getattr(L, name).argtypes = [vp]
+            getattr(L, name).restype = _i64p
 
-    EXPORTS = ["ibis_b200_last_error", "ibis_b200_launch_count", "ibis_b200_stream"]
+    EXPORTS = ["ibis_b200_last_error", "ibis_b200_launch_count", "ibis_b200_stream", "ibis_b200_grid_desc_of",
+               "ibis_b200_grid_face_vertices", "ibis_b200_grid_tag_ghosts"]
 
 
 def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def build_grid(mesh, boundary_tags=None, device=-1, lib_path=None):
+    """ibis_b200_grid_build: su2.Su2Mesh -> grid.Grid with the arrays of the reference GridBlock in the
+    reference's numbering (same result as the numpy mirror grid.build_grid, which the tests hold it to)."""
+    from .grid import Grid
+    L = Library.load(lib_path)
+    tags = sorted(mesh.markers.keys() if boundary_tags is None else boundary_tags)
+    mv = [_as(mesh.markers[t][1], np.int64) for t in tags]
+    offs = np.zeros(len(tags) + 1, np.int64)
+    offs[1:] = np.cumsum([len(a) for a in mv])
+    mverts = _as(np.concatenate(mv) if mv else np.zeros((0, 4)), np.int64)
+    pos, ctype, cverts = _as(mesh.vertices, np.float64), _as(mesh.cell_types, np.int32), _as(mesh.cell_vertices, np.int64)
+    md = MeshDesc(int(mesh.dim), len(tags), len(pos), len(ctype), pos.ctypes.data_as(_dp), ctype.ctypes.data_as(_i32p),
+                  cverts.ctypes.data_as(_i64p), offs.ctypes.data_as(_i64p), mverts.ctypes.data_as(_i64p))
+    h = C.c_void_p()
+    rc = L.lib.ibis_b200_grid_build(C.byref(h), C.byref(md), int(device))
+    if rc != 0:
+        raise IbisB200Error(f"ibis_b200_grid_build failed ({rc}): {L.lib.ibis_b200_last_error(None).decode()}")
+    try:
+        d = L.lib.ibis_b200_grid_desc_of(h).contents
+        nc, ng, nf = int(d.n_cells), int(d.n_ghost), int(d.n_faces)
+
+        def arr(ptr, shape):
+            n = int(np.prod(shape))
+            return np.ctypeslib.as_array(ptr, shape=(n,)).reshape(shape).copy() if n else np.zeros(shape, ptr._type_)
+
+        g = Grid()
+        g.dim, g.n_cells, g.n_ghost, g.n_faces, g.n_vertices = int(d.dim), nc, ng, nf, len(pos)
+        g.cell_face_offsets = arr(d.cell_face_offsets, (nc + 1,))
+        nr = int(g.cell_face_offsets[-1])
+        g.face_left, g.face_right = arr(d.face_left, (nf,)), arr(d.face_right, (nf,))
+        g.face_area = arr(d.face_area, (nf,))
+        for k in ("norm", "tan1", "tan2", "centre"):
+            setattr(g, "face_" + k, arr(getattr(d, "face_" + k), (nf, 3)))
+        g.cell_face_ids, g.cell_outsigns = arr(d.cell_face_ids, (nr,)), arr(d.cell_outsigns, (nr,))
+        g.cell_neighbours = arr(d.cell_neighbours, (nr,))
+        g.cell_volume, g.cell_centroid = arr(d.cell_volume, (nc,)), arr(d.cell_centroid, (nc + ng, 3))
+        g.face_vertices = arr(L.lib.ibis_b200_grid_face_vertices(h), (nf, 4))
+        g.face_nv = (g.face_vertices >= 0).sum(axis=1)
+        tf, tg = arr(d.tag_faces, (ng,)), arr(L.lib.ibis_b200_grid_tag_ghosts(h), (ng,))
+        for i, t in enumerate(tags):
+            g.tags[t] = dict(faces=tf[offs[i]:offs[i + 1]], ghosts=tg[offs[i]:offs[i + 1]])
+        g.cell_types = ctype
+        return g
+    finally:
+        L.lib.ibis_b200_grid_destroy(h)
 
 
 class Context:

@@ -122,6 +122,36 @@ typedef struct {
     const double* bc_tables;          /* borrowed during ibis_b200_create only */
 } ibis_b200_config;
 
+/* ---- grid build ---------------------------------------------
+ * replaces: GridIO::read_su2_grid's element tables + InterfaceLookup (string-hashed face
+ * de-duplication, grid/interface.cpp:38-80) + GridBlock<T>::init_grid_block and the geometry
+ * kernels it calls (grid/grid.h:89-167,186-213,364-433; interface.h:187-250; cell.h:236-303;
+ * geom.h:30-83).  Input: an SU2 mesh as plain arrays.  Output: the arrays of the reference
+ * GridBlock in the reference's numbering (faces in order of first discovery, ghosts appended per
+ * tag in alphabetical order) -- an ibis_b200_grid_desc that ibis_b200_create takes as is.
+ * Connectivity is one lexicographic sort on the host; every geometric quantity is computed by
+ * CUDA kernels on `device` with the reference's formulas (bit-identical arrays). */
+typedef struct {
+    int32_t dim;
+    int32_t n_tags;                   /* boundary markers, alphabetical by tag                   */
+    int64_t n_vertices;
+    int64_t n_cells;
+    const double* vertices;           /* n_vertices x 3 (z = 0 in 2-D)                           */
+    const int32_t* cell_types;        /* VTK code: 5 tri, 9 quad, 10 tetra, 12 hex, 13 wedge, 14 pyramid */
+    const int64_t* cell_vertices;     /* n_cells x 8, padded with -1, VTK vertex order           */
+    const int64_t* marker_offsets;    /* n_tags + 1, into the marker elements                    */
+    const int64_t* marker_vertices;   /* n_marker_elements x 4, padded with -1                   */
+} ibis_b200_mesh_desc;
+typedef struct ibis_b200_grid ibis_b200_grid;
+int ibis_b200_grid_build(ibis_b200_grid** grid, const ibis_b200_mesh_desc* mesh, int device);
+/* the built arrays; valid until ibis_b200_grid_destroy */
+const ibis_b200_grid_desc* ibis_b200_grid_desc_of(const ibis_b200_grid* grid);
+/* Interfaces::vertex_ids (grid/interface.h:331): n_faces x 4 padded with -1, orientation of the
+ * first discoverer; and the ghost cell of every boundary face, in tag_faces order */
+const int64_t* ibis_b200_grid_face_vertices(const ibis_b200_grid* grid);
+const int64_t* ibis_b200_grid_tag_ghosts(const ibis_b200_grid* grid);
+int ibis_b200_grid_destroy(ibis_b200_grid* grid);
+
 /* ---- context ------------------------------------------------------------------------- */
 /* replaces: GridBlock<T>(su2, config) + FiniteVolume<T>(grid, config) + IdealGas/
  * TransportProperties constructors (solvers/runge_kutta.cpp:21-80, simulation/simulation.h).
