@@ -36,6 +36,11 @@ def write_case(case_dir, mesh, config, snap, dim):
 
 
 def main():
+    pad = os.path.join(ROOT, "oracle", "_ref", "libpadmalloc.so")
+    if os.path.exists(pad) and "libpadmalloc" not in os.environ.get("LD_PRELOAD", ""):
+        # oracle/ref_build/padmalloc.c: the reference's CubicSpline constructor overruns two arrays
+        os.environ["LD_PRELOAD"] = pad
+        os.execv(sys.executable, [sys.executable] + sys.argv)
     names = sys.argv[1:] or list(sc.SOLVE_CASES)
     # ONE OpenMP thread: the reference's parallel_reduce then sums in index order, which makes the
     # fixtures independent of the machine they were generated on

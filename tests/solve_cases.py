@@ -120,6 +120,33 @@ SOLVE_CASES = {
                                                                         "tolerance": 1e-2,
                                                                         "max_preconditioner_iters": 60,
                                                                         "preconditioner_tolerance": 1e-1}))),
+    # examples/flat_plate/2D/truncated_plate: boundary-layer inflow profile (cubic splines in the ghost
+    # centroid's y), viscous, explicit.  Knots: the domain top (0.05) lies below the third-last knot, so no
+    # ghost centroid falls in the last two spline intervals (reference out-of-bounds reads)
+    "rk_plate_viscous_bl_inflow": (lambda: su2.flat_plate_2d(24, 16, height=0.05),
+                           {"inflow": cfg.boundary_layer_inflow(
+                               [0.0, 0.002, 0.004, 0.007, 0.011, 0.016, 0.03, 0.051, 0.06, 0.07],
+                               [0.0, 420.0, 760.0, 1050.0, 1250.0, 1350.0, 1388.0, 1390.0, 1390.0, 1390.0],
+                               [300.0, 480.0, 520.0, 470.0, 390.0, 330.0, 302.0, 300.0, 300.0, 300.0], 1.013e3),
+                            "outflow": cfg.supersonic_outflow(),
+                            "wall": cfg.fixed_temperature_no_slip_wall(300.0)},
+                           lambda g, d: _uniform(g, FS_PLATE, d),
+                           dict(flux_calculator="ausmdv", viscous=True,
+                                solver=cfg.runge_kutta(method="ssp-rk3", cfl=0.5, max_step=30, max_time=1.0))),
+    # constant_flux inflow (prep.py bow_shock_fit = constant_flux, here on a static grid), explicit
+    "rk_quad2d_cflux": (lambda: su2.box_quad(10, 8, jitter=0.15),
+                        dict(cases.quad2_bcs(), left=cfg.constant_flux(cases.FS2)),
+                        lambda g, d: _perturbed(g, d, 1.0),
+                        dict(flux_calculator="ausmdv",
+                             solver=cfg.runge_kutta(method="ssp-rk3", cfl=0.5, max_step=25, max_time=1.0))),
+    # ... and through the dual residual of the steady solver
+    "steady_quad2d_cflux": (lambda: su2.box_quad(8, 6, jitter=0.15),
+                            dict(cases.quad2_bcs(), left=cfg.constant_flux(cases.FS2)),
+                            lambda g, d: _perturbed(g, d, 1.0),
+                            dict(flux_calculator="hanel",
+                                 solver=cfg.steady_state(cfl=5.0, max_steps=8, tolerance=1e-12,
+                                                         linear_solver={"type": "gmres", "max_iters": 40,
+                                                                        "tol": 1e-3}))),
     # 3-D steady
     "steady_box3d": (lambda: su2.box_hex(4, 4, 3, jitter=0.1), cases.box3_wall_bcs(),
                      lambda g, d: _perturbed(g, d, 1.0),
