@@ -251,6 +251,7 @@ class Library:
             "ibis_b200_flow_read_native": [vp, i, vp, vp, vp, vp, vp],
             "ibis_b200_flow_write_native": [vp, i, vp, vp, vp, vp, vp],
             "ibis_b200_grid_build": [C.POINTER(vp), C.POINTER(MeshDesc), i], "ibis_b200_grid_destroy": [vp],
+            "ibis_b200_mesh_read_su2": [C.POINTER(vp), C.c_char_p], "ibis_b200_mesh_destroy": [vp],
         }
         for name, args in sig.items():
             f = getattr(L, name)
@@ -264,16 +265,49 @@ class Library:
         L.ibis_b200_stream.restype = vp
         L.ibis_b200_grid_desc_of.argtypes = [vp]
         L.ibis_b200_grid_desc_of.restype = C.POINTER(GridDesc)
+        L.ibis_b200_mesh_desc_of.argtypes = [vp]
+        L.ibis_b200_mesh_desc_of.restype = C.POINTER(MeshDesc)
+        L.ibis_b200_mesh_tag.argtypes = [vp, i]
+        L.ibis_b200_mesh_tag.restype = C.c_char_p
         for name in ("ibis_b200_grid_face_vertices", "ibis_b200_grid_tag_ghosts"):
             getattr(L, name).argtypes = [vp]
             getattr(L, name).restype = _i64p
 
     EXPORTS = ["ibis_b200_last_error", "ibis_b200_launch_count", "ibis_b200_stream", "ibis_b200_grid_desc_of",
-               "ibis_b200_grid_face_vertices", "ibis_b200_grid_tag_ghosts"]
+               "ibis_b200_grid_face_vertices", "ibis_b200_grid_tag_ghosts", "ibis_b200_mesh_desc_of", "ibis_b200_mesh_tag"]
 
 
 def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def read_su2(path, lib_path=None):
+    """ibis_b200_mesh_read_su2: SU2 text file -> su2.Su2Mesh (markers in alphabetical tag order)."""
+    from . import su2
+    L = Library.load(lib_path)
+    h = C.c_void_p()
+    rc = L.lib.ibis_b200_mesh_read_su2(C.byref(h), os.fsencode(path))
+    if rc != 0:
+        raise IbisB200Error(f"ibis_b200_mesh_read_su2 failed ({rc}): {L.lib.ibis_b200_last_error(None).decode()}")
+    try:
+        d = L.lib.ibis_b200_mesh_desc_of(h).contents
+        nv, nc, nt = int(d.n_vertices), int(d.n_cells), int(d.n_tags)
+
+        def arr(ptr, shape, dtype):
+            n = int(np.prod(shape))
+            return np.ctypeslib.as_array(ptr, shape=(n,)).reshape(shape).copy() if n else np.zeros(shape, dtype)
+
+        offs = arr(d.marker_offsets, (nt + 1,), np.int64)
+        mv = arr(d.marker_vertices, (int(offs[-1]), 4), np.int64)
+        line_tri_quad = np.array([0, 0, su2.LINE, su2.TRI, su2.QUAD], np.int32)
+        markers = {}
+        for k in range(nt):
+            v = mv[offs[k]:offs[k + 1]]
+            markers[L.lib.ibis_b200_mesh_tag(h, k).decode()] = (line_tri_quad[(v >= 0).sum(axis=1)], v)
+        return su2.Su2Mesh(int(d.dim), arr(d.vertices, (nv, 3), np.float64), arr(d.cell_types, (nc,), np.int32),
+                           arr(d.cell_vertices, (nc, 8), np.int64), markers)
+    finally:
+        L.lib.ibis_b200_mesh_destroy(h)
 
 
 def build_grid(mesh, boundary_tags=None, device=-1, lib_path=None):

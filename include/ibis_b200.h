@@ -142,6 +142,15 @@ typedef struct {
     const int64_t* marker_offsets;    /* n_tags + 1, into the marker elements                    */
     const int64_t* marker_vertices;   /* n_marker_elements x 4, padded with -1                   */
 } ibis_b200_mesh_desc;
+/* replaces GridIO::GridIO(file_name) + GridIO::read_su2_grid (grid/grid_io.cpp:100-268): an SU2 text
+ * file as a mesh description; tags alphabetical (GridIO keeps its markers in a std::map), a tag that
+ * appears twice has its elements appended, unknown lines ignored.  Host only. */
+typedef struct ibis_b200_mesh ibis_b200_mesh;
+int ibis_b200_mesh_read_su2(ibis_b200_mesh** mesh, const char* path);
+const ibis_b200_mesh_desc* ibis_b200_mesh_desc_of(const ibis_b200_mesh* mesh);
+const char* ibis_b200_mesh_tag(const ibis_b200_mesh* mesh, int i);        /* NULL past the last tag */
+int ibis_b200_mesh_destroy(ibis_b200_mesh* mesh);
+
 typedef struct ibis_b200_grid ibis_b200_grid;
 int ibis_b200_grid_build(ibis_b200_grid** grid, const ibis_b200_mesh_desc* mesh, int device);
 /* the built arrays; valid until ibis_b200_grid_destroy */

@@ -107,3 +107,57 @@ def test_native_grid_errors():
     hexes.dim = 2
     with pytest.raises(IbisB200Error, match="unsupported cell type"):              # 3-D cells in a 2-D grid
         libmod.build_grid(hexes, None, lib_path=L)
+
+
+# ---- ibis_b200_mesh_read_su2 (GridIO::read_su2_grid, grid/grid_io.cpp:218-268) ----
+@pytest.mark.parametrize("name", ["mixed3d_walls", "tri2d", "naca_omesh", "box3d_ausmdv"])
+def test_native_su2_reader_round_trip(name, tmp_path):
+    """the file the reference itself is given (Su2Mesh.write, 17 significant digits) read back natively:
+    same vertices bit for bit, same cells, same markers; then file -> grid equals the reference's GridBlock"""
+    L = emu_lib()
+    mesh, tags = _mesh_of(name)
+    path = str(tmp_path / "block_0000.su2")
+    mesh.write(path)
+    got = libmod.read_su2(path, lib_path=L)
+    assert got.dim == mesh.dim
+    assert np.array_equal(got.vertices, mesh.vertices)
+    assert np.array_equal(got.cell_types, mesh.cell_types) and np.array_equal(got.cell_vertices, mesh.cell_vertices)
+    assert list(got.markers) == sorted(mesh.markers)
+    for t in mesh.markers:
+        assert np.array_equal(got.markers[t][0], mesh.markers[t][0]) and np.array_equal(got.markers[t][1], mesh.markers[t][1])
+    ref = su2.Su2Mesh.read(path)
+    assert np.array_equal(ref.vertices, got.vertices) and np.array_equal(ref.cell_vertices, got.cell_vertices)
+    g = libmod.build_grid(got, tags, lib_path=L)
+    gold = parity.load_golden(name)
+    for k in ("face_left", "face_right", "face_area", "face_norm", "cell_volume", "cell_centroid", "cell_face_ids"):
+        assert np.array_equal(np.asarray(getattr(g, k)), gold["grid_" + k]), k
+
+
+def test_native_su2_reader_quirks(tmp_path):
+    """trailing indices after vertices / elements, unknown lines, a tag split over two MARKER_TAG blocks
+    (appended, grid_io.cpp:254-262), tags returned alphabetically; missing file and bad lines are errors"""
+    L = emu_lib()
+    path = str(tmp_path / "g.su2")
+    with open(path, "w") as f:
+        f.write("% comment the reader ignores\nNDIME= 2\nNPOIN= 6 \n"
+                "0 0 0\n 1.5 0 1\n3 0 2\n0 1e0 3\n1.5 1 4\n  3.0 1.0   5\n"
+                "NELEM= 2\n9 0 1 4 3 0\n9 1 2 5 4 1\n"
+                "NMARK= 4\nMARKER_TAG= wall\nMARKER_ELEMS= 1\n3 0 1\nMARKER_TAG= in\nMARKER_ELEMS= 1\n3 3 0\n"
+                "MARKER_TAG= wall\nMARKER_ELEMS= 3\n3 1 2\n3 4 3\n3 5 4\nMARKER_TAG= out\nMARKER_ELEMS= 1\n3 2 5\n")
+    m = libmod.read_su2(path, lib_path=L)
+    assert m.dim == 2 and list(m.markers) == ["in", "out", "wall"]
+    assert np.array_equal(m.vertices, [[0, 0, 0], [1.5, 0, 0], [3, 0, 0], [0, 1, 0], [1.5, 1, 0], [3, 1, 0]])
+    assert np.array_equal(m.cell_vertices[:, :4], [[0, 1, 4, 3], [1, 2, 5, 4]])
+    assert np.array_equal(m.markers["wall"][1][:, :2], [[0, 1], [1, 2], [4, 3], [5, 4]])
+    g = libmod.build_grid(m, None, lib_path=L)
+    assert g.n_faces == 7 and g.n_ghost == 6 and abs(g.cell_volume.sum() - 3.0) < 1e-15
+    with pytest.raises(IbisB200Error, match="Could not find"):
+        libmod.read_su2(str(tmp_path / "absent.su2"), lib_path=L)
+    with open(path, "w") as f:
+        f.write("NDIME= 2\nNPOIN= 2\n0 0\n1 0\nNELEM= 1\n11 0 1 2 3 4 5 6 7\n")
+    with pytest.raises(IbisB200Error, match="unsupported element"):
+        libmod.read_su2(path, lib_path=L)
+    with open(path, "w") as f:
+        f.write("NDIME= 3\nNPOIN= 5\n0 0 0\n1 0 0\n")
+    with pytest.raises(IbisB200Error, match="truncated NPOIN"):
+        libmod.read_su2(path, lib_path=L)
