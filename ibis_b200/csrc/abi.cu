@@ -1023,6 +1023,18 @@ int ibis_b200_l2_norms(ibis_b200_ctx* c, int cq, double out[6]) {
     return rc;
 }
 
+int ibis_b200_debug_dual_ops(ibis_b200_ctx* c, const double* in5, double* out44) {
+    if (!c || !in5 || !out44) return fail(c, IBIS_B200_EINVAL, "null argument");
+    int rc = ensure_stage(c, 64);
+    if (rc) return rc;
+    GPU_TRY(c, gpu::h2d(c->d_stage, in5, 5 * sizeof(double), c->stream));
+    GPU_TRY(c, gpu::stream_sync(c->stream));
+    launch_dual_kat(c, c->d_stage, c->d_stage + 8);
+    GPU_TRY(c, gpu::d2h(out44, c->d_stage + 8, 44 * sizeof(double), c->stream));
+    GPU_TRY(c, gpu::stream_sync(c->stream));
+    return c->last_error.empty() ? 0 : IBIS_B200_ECUDA;
+}
+
 int ibis_b200_debug_gradients(ibis_b200_ctx* c, int var, double* grad, double* limiter) {
     if (var < 0 || var >= NVARS) return fail(c, IBIS_B200_EINVAL, "no gradients available");
     if (sides_path(c)) {

@@ -180,6 +180,7 @@ void launch_flow_read(ibis_b200_ctx* c, const double* stage, int64_t n, int has_
 template <typename S>
 void launch_flow_write(ibis_b200_ctx* c, S* const* fs, double* stage, int64_t n, int has_vz);
 void launch_gather_debug(ibis_b200_ctx* c, const double* src, int ncomp, int64_t n, double* out);
+void launch_dual_kat(ibis_b200_ctx* c, const double* in, double* out);   // solver_bodies.h::dual_kat_body, one thread
 // vectors
 void launch_dot(ibis_b200_ctx* c, const double* a, const double* b, int64_t n, double* d_out,
                 int post);   // post: 0 none, 1 sqrt, 2 sqrt and also store 1/sqrt at d_out[1]

@@ -148,4 +148,36 @@ IBIS_HD bool bad_cell(const dual& T, const dual& rho) {
            isinf(rho.du);
 }
 
+// the operations the reference's own Dual tests exercise (util/dual.cpp:4-222), evaluated with the
+// operators of scalar.h: in = {x.re, x.du, y.re, y.du, r}, out = 22 (re, du) pairs
+IBIS_HD void dual_kat_body(const double* in, double* out) {
+    const dual x(in[0], in[1]), y(in[2], in[3]);
+    const double r = in[4];
+    dual t;
+    int k = 0;
+    auto put = [&](const dual& d) { out[2 * k] = d.re; out[2 * k + 1] = d.du; k++; };
+    put(x + y);
+    t = x; t += y; put(t);
+    put(x + r);
+    put(x - y);
+    t = x; t -= y; put(t);
+    put(x - r);
+    put(r - x);
+    put(x * y);
+    t = x; t *= y; put(t);
+    put(x * r);
+    t = x; t *= r; put(t);
+    put(r * x);
+    put(x / y);
+    t = x; t /= y; put(t);
+    put(x / r);
+    t = x; t /= r; put(t);
+    put(r / x);
+    put(sqrt_(x));
+    put(abs_(x));
+    put(abs_(x * x));
+    put(x * x + 2.0 * x);
+    put(x * x - sqrt_(x));
+}
+
 }  // namespace ib

@@ -484,6 +484,12 @@ void launch_pack_out(ibis_b200_ctx* c, S* const* comps, const int* comp_map, int
 template void launch_pack_out<double>(ibis_b200_ctx*, double* const*, const int*, int, int64_t, double*, double*);
 template void launch_pack_out<dual>(ibis_b200_ctx*, dual* const*, const int*, int, int64_t, double*, double*);
 
+__global__ void k_dual_kat(const double* in, double* out) { dual_kat_body(in, out); }
+void launch_dual_kat(ibis_b200_ctx* c, const double* in, double* out) {
+    k_dual_kat<<<1, 1, 0, c->stream>>>(in, out);
+    CUDA_CHECK_LAUNCH(c);
+}
+
 void launch_gather_debug(ibis_b200_ctx* c, const double* src, int ncomp, int64_t n, double* out) {
     k_gather_debug<<<nblocks(n, 256), 256, 0, c->stream>>>(src, c->cstride, ncomp, n, out, c->d_ref2int);
     CUDA_CHECK_LAUNCH(c);

@@ -231,7 +231,7 @@ class Library:
             "ibis_b200_cons_to_prim": [vp, i, i], "ibis_b200_prim_to_cons": [vp, i, i],
             "ibis_b200_apply_time_derivative": [vp, i, i, i, d],
             "ibis_b200_l2_norms": [vp, i, vp],
-            "ibis_b200_debug_gradients": [vp, i, vp, vp],
+            "ibis_b200_debug_gradients": [vp, i, vp, vp], "ibis_b200_debug_dual_ops": [vp, vp, vp],
             "ibis_b200_rk_step": [vp, i, i, i, vp, vp, d, d, d, C.POINTER(d), C.POINTER(d)],
             "ibis_b200_rk_residual_norms": [vp, vp], "ibis_b200_rk_distinct_stages": [vp, i],
             "ibis_b200_jfnk_set_dual": [vp, i, i, i],
@@ -533,6 +533,12 @@ class Context:
         l = np.zeros(self.n_cells)
         self._ck(self.lib.ibis_b200_debug_gradients(self.h, var, _ptr(g), _ptr(l)), "debug_gradients")
         return g, l
+
+    def debug_dual_ops(self, x, y, r):
+        """-> (22, 2) array of (re, du): see ibis_b200_debug_dual_ops in include/ibis_b200.h"""
+        a, out = _as([x[0], x[1], y[0], y[1], r], np.float64), np.zeros(44)
+        self._ck(self.lib.ibis_b200_debug_dual_ops(self.h, _ptr(a), _ptr(out)), "debug_dual_ops")
+        return out.reshape(22, 2)
 
     def rk_step(self, fs, cq, a_rows, b, cfl, dt_prev, t_remaining):
         a = np.array([x for row in a_rows for x in row], dtype=np.float64)

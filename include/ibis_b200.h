@@ -237,6 +237,11 @@ int ibis_b200_l2_norms(ibis_b200_ctx*, int cq, double out[6]);
  * grad [n_cells x 3] and limiter [n_cells] of variable var (0 rho, 1 thermo-2 (u|p|T),
  * 2 vx, 3 vy, 4 vz); either pointer may be NULL. */
 int ibis_b200_debug_gradients(ibis_b200_ctx*, int var, double* grad, double* limiter);
+/* the dual-number operators of the device code (Ibis::Dual, util/dual.h:75-314) on one pair of operands, so
+ * that the reference's own Dual tests (util/dual.cpp:4-222) can be replayed on the device:
+ * in = {x.re, x.du, y.re, y.du, r}; out = 22 (re, du) pairs: x+y, x+=y, x+r, x-y, x-=y, x-r, r-x, x*y, x*=y,
+ * x*r, x*=r, r*x, x/y, x/=y, x/r, x/=r, r/x, sqrt(x), abs(x), abs(x*x), x*x+2x, x*x-sqrt(x) */
+int ibis_b200_debug_dual_ops(ibis_b200_ctx*, const double* in5, double* out44);
 
 /* ---- fused explicit step (solvers/runge_kutta.cpp:131-203) --------------------------- */
 /* One RungeKutta::take_step with the tableau a (row i has i entries, i = 1..stages-1,

@@ -403,6 +403,11 @@ void launch_pack_out(ibis_b200_ctx* c, S* const* comps, const int* map, int ncom
 template void launch_pack_out<double>(ibis_b200_ctx*, double* const*, const int*, int, int64_t, double*, double*);
 template void launch_pack_out<dual>(ibis_b200_ctx*, dual* const*, const int*, int, int64_t, double*, double*);
 
+void launch_dual_kat(ibis_b200_ctx* c, const double* in, double* out) {
+    dual_kat_body(in, out);
+    c->launches++;
+}
+
 void launch_gather_debug(ibis_b200_ctx* c, const double* src, int ncomp, int64_t n, double* out) {
     const int* perm = c->d_ref2int;
     for (int64_t i = 0; i < n; i++)
