@@ -96,6 +96,11 @@ def constant_flux(fs):
                post=[{"type": "constant_flux", "flow_state": dict(fs)}])
 
 
+def rigid_body_translation(x=0.0, y=0.0, z=0.0):
+    # prep.py:309-328 (RigidBodyTranslation.as_dict)
+    return {"enabled": True, "type": "rigid_body_translation", "velocity": {"x": x, "y": y, "z": z}}
+
+
 def runge_kutta(method="ssp-rk3", cfl=0.5, max_step=100, max_time=1.0, dt_init=-1.0,
                 print_frequency=1000, plot_frequency=-1, plot_every_n_steps=-1,
                 residual_frequency=-1, residuals_every_n_steps=-1):
@@ -121,7 +126,7 @@ def steady_state(cfl=10.0, max_steps=50, tolerance=1e-10, linear_solver=None,
 
 def make_config(dim, boundaries, flux_calculator="hanel", reconstruction_order=2,
                 limiter="barth_jespersen", epsilon=1e-25, thermo_interpolator="rho_u",
-                viscous=False, signal_factor=4.0, solver=None, R=AIR_R, ldfss_delta=2.0):
+                viscous=False, signal_factor=4.0, solver=None, R=AIR_R, ldfss_delta=2.0, motion=None):
     fc = {"type": flux_calculator}
     if flux_calculator == "ldfss2":
         fc["delta"] = ldfss_delta
@@ -134,7 +139,7 @@ def make_config(dim, boundaries, flux_calculator="hanel", reconstruction_order=2
         "viscous_flux": {"enabled": bool(viscous), "signal_factor": signal_factor},
         "solver": solver if solver is not None else runge_kutta(),
         "grid": {"boundaries": copy.deepcopy(boundaries), "dimensions": dim,
-                 "motion": {"enabled": False}},
+                 "motion": copy.deepcopy(motion) if motion else {"enabled": False}},
         "gas_model": ideal_gas(R),
         "transport_properties": air_transport(),
         "io": {"flow_format": "native_binary"},

@@ -163,6 +163,7 @@ FvArgs<S> make_args(ibis_b200_ctx* c, Buffer* fs, Buffer* dudt, bool allow_recon
     }
     A.dt_out = nullptr;
     A.face_T = c->face_T;
+    A.face_vel = nullptr;              // set by the moving-grid evaluation only
     A.face_rho = c->face_rho;
     A.gas.R = S(c->cfg.R);
     A.gas.Cv = S(c->cfg.Cv);
@@ -227,7 +228,7 @@ template <typename S>
 bool sides_path_for(const ibis_b200_ctx* c) { return sides_path(c) && sizeof(S) == sizeof(double); }
 
 template <typename S>
-int ensure_fv_temporaries(ibis_b200_ctx* c, bool want_grad = false) {
+int ensure_fv_temporaries(ibis_b200_ctx* c, bool want_grad = false, bool want_flux = false) {
     const bool need_grad = want_grad || c->cfg.viscous || (c->cfg.reconstruction_order > 1 && !sides_path_for<S>(c));
     if (sides_path_for<S>(c)) {
         S** sl = (sizeof(S) == 8) ? reinterpret_cast<S**>(&c->sideL_r) : reinterpret_cast<S**>(&c->sideL_d);
@@ -247,7 +248,7 @@ int ensure_fv_temporaries(ibis_b200_ctx* c, bool want_grad = false) {
         rc = dev_alloc_zero<S>(c, (int64_t)NVARS * c->cstride, lim);
         if (rc) return fail(c, rc, "out of device memory (limiters)");
     }
-    if ((c->cfg.viscous || c->has_flux_actions) && !*flux) {
+    if ((c->cfg.viscous || c->has_flux_actions || want_flux) && !*flux) {
         int rc = dev_alloc_zero<S>(c, (int64_t)5 * c->fstride, flux);
         if (rc) return fail(c, rc, "out of device memory (face flux)");
     }
@@ -263,12 +264,39 @@ int ensure_fv_temporaries(ibis_b200_ctx* c, bool want_grad = false) {
 // FiniteVolume<T>::compute_dudt (finite_volume.cpp:57-96)
 // dt_bits: when not null and the evaluation takes the sides path, the minimum local time step of the
 // owned cells is left there (as the bit pattern of a double; the caller initialises it to +inf)
+// cq != nullptr: the moving-grid overload (finite_volume.cpp:57-85) -- interface velocities from the vertex
+// velocities last set, interface-relative fluxes through the stored face-flux array, GCL term with cq
 template <typename S>
-int compute_dudt_impl(ibis_b200_ctx* c, Buffer* fs, Buffer* dudt, bool allow_reconstruction, double* dt_bits = nullptr) {
-    int rc = ensure_fv_temporaries<S>(c);
+int compute_dudt_impl(ibis_b200_ctx* c, Buffer* fs, Buffer* dudt, bool allow_reconstruction, double* dt_bits = nullptr,
+                      Buffer* cq = nullptr) {
+    const bool moving = cq != nullptr;
+    int rc = ensure_fv_temporaries<S>(c, moving && c->cfg.reconstruction_order > 1, moving);
     if (rc) return rc;
     FvArgs<S> A = make_args<S>(c, fs, dudt, allow_reconstruction);
     A.dt_out = reinterpret_cast<unsigned long long*>(dt_bits);
+    if (moving) {
+        prof_begin(c, 2);
+        rc = comm::halo_exchange<S>(c, A.fs);
+        prof_end(c, 2);
+        if (rc) return rc;
+        launch_bc(c, A, IBIS_B200_PHASE_PRE_RECONSTRUCTION);
+        launch_face_vel(c, c->d_fverts, c->d_vertex_vel, c->d_face_vel);      // grid.compute_grid_motion (grid.h:562-565)
+        A.face_vel = c->d_face_vel;
+        if (A.order2) launch_grad_limit(c, A, false);
+        launch_face_flux_moving(c, A);
+        if (c->has_flux_actions) launch_bc(c, A, IBIS_B200_PHASE_POST_CONVECTIVE_FLUX);
+        if (A.viscous) {
+            if (c->has_previscous) launch_bc(c, A, IBIS_B200_PHASE_PRE_VISCOUS_GRAD);
+            launch_grad_limit(c, A, true);
+            launch_face_viscous(c, A);
+        }
+        launch_integral(c, A);
+        S* q[7];
+        comp_ptrs<S>(cq, q);
+        launch_gcl(c, A, q);
+        if (!c->last_error.empty()) return IBIS_B200_ECUDA;
+        return 0;
+    }
     if (sizeof(S) == sizeof(double)) c->last_fs = (int)(fs - c->bufs.data());
     if (A.order2 && sides_path_for<S>(c) && comm::halo_split(c)) {
         // overlap: this rank's boundary cells go out to the peers, the tiles that touch neither a halo
@@ -502,6 +530,7 @@ int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd_ref, con
     if (acts.empty()) acts.push_back(BcAction());
 
     c->ref2int = R.ref2int;
+    c->face_ref2int.swap(R.face_ref2int);
     GridDev& g = c->g;
     g.dim = gd->dim;
     g.n_owned = (int)c->n_owned;
@@ -1021,6 +1050,63 @@ int ibis_b200_l2_norms(ibis_b200_ctx* c, int cq, double out[6]) {
     rc = fetch_scalars(c, SC_L2, 6, out);
     for (int i = 0; i < 6; i++) out[i] = sqrt(out[i]);
     return rc;
+}
+
+int ibis_b200_set_face_vertices(ibis_b200_ctx* c, const int64_t* face_vertices, int64_t n_vertices) {
+    if (!c || !face_vertices || n_vertices <= 0) return fail(c, IBIS_B200_EINVAL, "null argument");
+    if (n_vertices >= (int64_t)1 << 31) return fail(c, IBIS_B200_EINVAL, "too many vertices for 32-bit ids");
+    std::vector<int> fv((size_t)4 * c->fstride, -1);
+    bool bad = false;
+#pragma omp parallel for schedule(static) reduction(|| : bad)
+    for (int64_t f = 0; f < c->n_faces; f++) {
+        const int64_t g = c->face_ref2int[f];
+        for (int k = 0; k < 4; k++) {
+            const int64_t v = face_vertices[4 * f + k];
+            if (v >= n_vertices || (k < 2 && v < 0)) bad = true;
+            fv[(size_t)k * c->fstride + g] = v < 0 ? -1 : (int)v;
+        }
+    }
+    if (bad) return fail(c, IBIS_B200_EINVAL, "interface refers to a vertex outside the vertex list");
+    if (c->d_fverts) return fail(c, IBIS_B200_EINVAL, "face vertices already set");
+    int rc = upload_vec(c, fv, &c->d_fverts);
+    if (!rc) rc = dev_alloc_zero<double>(c, 3 * n_vertices, &c->d_vertex_vel);
+    if (!rc) rc = dev_alloc_zero<double>(c, 3 * c->fstride, &c->d_face_vel);
+    if (rc) return fail(c, rc, "out of device memory (moving grid)");
+    c->n_vertices = n_vertices;
+    return 0;
+}
+
+int ibis_b200_set_vertex_velocities(ibis_b200_ctx* c, const double* vertex_vel) {
+    if (!c || !vertex_vel) return fail(c, IBIS_B200_EINVAL, "null argument");
+    if (!c->d_fverts) return fail(c, IBIS_B200_EINVAL, "ibis_b200_set_face_vertices has not been called");
+    GPU_TRY(c, gpu::h2d(c->d_vertex_vel, vertex_vel, (size_t)3 * c->n_vertices * sizeof(double), c->stream));
+    GPU_TRY(c, gpu::stream_sync(c->stream));      // vertex_vel is the caller's
+    c->have_vertex_vel = true;
+    return 0;
+}
+
+int ibis_b200_compute_dudt_moving(ibis_b200_ctx* c, int fs, int cq, int dudt, int allow_reconstruction) {
+    if (!c) return IBIS_B200_EINVAL;
+    if (!c->have_vertex_vel) return fail(c, IBIS_B200_EINVAL, "no vertex velocities: the grid is not moving");
+    if (c->n_ranks > 1) return fail(c, IBIS_B200_EINVAL, "moving grids are single-block");
+    Buffer* F = get_buf(c, fs, BUF_FS);
+    Buffer* Q = get_buf(c, cq, BUF_CQ);
+    Buffer* D = get_buf(c, dudt, BUF_CQ);
+    if (!F || !Q || !D) return fail(c, IBIS_B200_EHANDLE, "compute_dudt_moving: bad handle");
+    if (F->is_dual != D->is_dual || F->is_dual != Q->is_dual)
+        return fail(c, IBIS_B200_EINVAL, "compute_dudt_moving: real/dual mismatch");
+    return F->is_dual ? compute_dudt_impl<dual>(c, F, D, allow_reconstruction != 0, nullptr, Q)
+                      : compute_dudt_impl<double>(c, F, D, allow_reconstruction != 0, nullptr, Q);
+}
+
+int ibis_b200_debug_face_velocities(ibis_b200_ctx* c, double* face_vel) {
+    if (!c || !face_vel || !c->d_face_vel) return fail(c, IBIS_B200_EINVAL, "no interface velocities");
+    std::vector<double> h((size_t)3 * c->fstride);
+    GPU_TRY(c, gpu::d2h(h.data(), c->d_face_vel, h.size() * sizeof(double), c->stream));
+    GPU_TRY(c, gpu::stream_sync(c->stream));
+    for (int64_t f = 0; f < c->n_faces; f++)
+        for (int k = 0; k < 3; k++) face_vel[3 * f + k] = h[(size_t)k * c->fstride + c->face_ref2int[f]];
+    return 0;
 }
 
 int ibis_b200_debug_dual_ops(ibis_b200_ctx* c, const double* in5, double* out44) {

@@ -67,7 +67,14 @@ struct ibis_b200_ctx {
     ibis_b200_config cfg;
     std::vector<ibis_b200_bc_action> bc_actions;
     bool has_previscous = false;
-    bool has_flux_actions = false;       // any constant_flux: evaluations go through the face-flux array
+    bool has_flux_actions = false;
+    // moving grid (ibis_b200_set_face_vertices / _set_vertex_velocities / _compute_dudt_moving)
+    std::vector<int> face_ref2int;       // reference interface id -> internal id
+    int* d_fverts = nullptr;             // [4][fstride] vertex ids of every interface, internal numbering, -1 padded
+    int64_t n_vertices = 0;
+    double* d_vertex_vel = nullptr;      // n_vertices x 3
+    double* d_face_vel = nullptr;        // [3][fstride]
+    bool have_vertex_vel = false;       // any constant_flux: evaluations go through the face-flux array
 
     // internal renumbering (layout.h): reference cell id -> internal id, nullptr = identity
     int* d_ref2int = nullptr;
@@ -144,6 +151,11 @@ void launch_dt_reduce_init(ibis_b200_ctx* c, double* p);
 void launch_dt_reduce_finish(ibis_b200_ctx* c, double* p);
 template <typename S>
 void launch_face_flux(ibis_b200_ctx* c, const FvArgs<S>& A);       // general path
+template <typename S>
+void launch_face_flux_moving(ibis_b200_ctx* c, const FvArgs<S>& A);   // moving grid: relative to A.face_vel
+void launch_face_vel(ibis_b200_ctx* c, const int* fverts, const double* vvel, double* face_vel);   // compute_face_vel
+template <typename S>
+void launch_gcl(ibis_b200_ctx* c, const FvArgs<S>& A, S* const* cq);   // geometric conservation law
 template <typename S>
 void launch_face_viscous(ibis_b200_ctx* c, const FvArgs<S>& A);
 template <typename S>

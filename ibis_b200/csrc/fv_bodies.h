@@ -143,6 +143,10 @@ struct FvArgs {
     // pattern of a positive double orders like the double, so the reduction is an integer atomicMin
     unsigned long long* dt_out;
     double* face_T;    // face_fs of the viscous path (finite_volume.h:128), real parts
+    // moving grid (GridBlock::face_vel, grid.h:599,638): [3][fstride], nullptr on a static grid.  Written by
+    // face_vel_body, replaced by its local-frame round trip in the flux kernel as in the reference
+    // (convective_flux.cpp:114-116,166-176), then read by constant_flux and the GCL term
+    double* face_vel;
     double* face_rho;
     Recon<S> rc;
     Gas<S> gas;
@@ -309,7 +313,9 @@ IBIS_HD void bc_body(const FvArgs<S>& A, int k, int phase) {
                 S rho = S(act.params[0]), p = S(act.params[1]), T = S(act.params[2]);
                 S vx = S(act.params[4]), vy = S(act.params[5]), vz = S(act.params[6]);
                 S u = A.gas.Cv * T;                          // gas_model.internal_energy (gas_model.h:164)
-                S rel_vx = vx - S(0.0), rel_vy = vy - S(0.0), rel_vz = vz - S(0.0);   // face_vel = 0: static grid
+                const double* fv = A.face_vel;                                  // nullptr: static grid
+                S rel_vx = vx - (fv ? fv[f] : 0.0), rel_vy = vy - (fv ? fv[fs_ + f] : 0.0),
+                  rel_vz = vz - (fv ? fv[2 * fs_ + f] : 0.0);
                 S mass_flux = rho * (rel_vx * nx + rel_vy * ny + rel_vz * nz);
                 M::store(A.flux, 0 * fs_ + f, mass_flux);
                 M::store(A.flux, 1 * fs_ + f, p * nx + vx * mass_flux);
@@ -604,7 +610,10 @@ IBIS_HD Side<S> reconstruct_side(const FvArgs<S>& A, int f, int cell) {
 // convective flux of one interface in the GLOBAL frame: reconstruct, rotate
 // (util/vector3.cpp:142-153), flux calculator, rotate back (convective_flux.cpp:148-164).
 // The face frame (n, t1, t2) enters as plain doubles (zero dual part in the reference).
-template <int DIM, int FLUX, bool O2, typename S>
+// MOVING (grid.moving(), convective_flux.cpp:105-140,166-176): the interface velocity is subtracted from
+// both sides, rotated into the face frame, the flux is corrected from the moving frame back to the
+// inertial one, and the velocity is rotated back (and stored: that round trip is what the GCL sees).
+template <int DIM, int FLUX, bool O2, typename S, bool MOVING = false>
 IBIS_HD Flux5<S> face_convective_flux(const FvArgs<S>& A, int f) {
     const GridDev& g = A.g;
     const long fs_ = g.fstride;
@@ -613,6 +622,15 @@ IBIS_HD Flux5<S> face_convective_flux(const FvArgs<S>& A, int f) {
     const double nx = g.f_n[f], ny = g.f_n[fs_ + f], nz = g.f_n[2 * fs_ + f];
     const double t1x = g.f_t1[f], t1y = g.f_t1[fs_ + f], t1z = g.f_t1[2 * fs_ + f];
     const double t2x = g.f_t2[f], t2y = g.f_t2[fs_ + f], t2z = g.f_t2[2 * fs_ + f];
+    double lx = 0.0, ly = 0.0, lz = 0.0;       // interface velocity in the face frame
+    if (MOVING) {
+        const double vx = A.face_vel[f], vy = A.face_vel[fs_ + f], vz = A.face_vel[2 * fs_ + f];
+        L.u = L.u - vx; L.v = L.v - vy; L.w = L.w - vz;
+        R_.u = R_.u - vx; R_.v = R_.v - vy; R_.w = R_.w - vz;
+        lx = vx * nx + vy * ny + vz * nz;
+        ly = vx * t1x + vy * t1y + vz * t1z;
+        lz = vx * t2x + vy * t2y + vz * t2z;
+    }
     {
         const S x = L.u * nx + L.v * ny + L.w * nz;
         const S y = L.u * t1x + L.v * t1y + L.w * t1z;
@@ -626,6 +644,17 @@ IBIS_HD Flux5<S> face_convective_flux(const FvArgs<S>& A, int f) {
         R_.u = x; R_.v = y; R_.w = z;
     }
     Flux5<S> F = flux_calc<FLUX>(L, R_, A.gas, A.delta);
+    if (MOVING) {
+        const double v_sqr = lx * lx + ly * ly + lz * lz;
+        F.energy += 0.5 * F.mass * v_sqr + F.mx * lx + F.my * ly;
+        if (DIM == 3) F.energy += F.mz * lz;
+        F.mx += lx * F.mass;
+        F.my += ly * F.mass;
+        if (DIM == 3) F.mz += lz * F.mass;
+        A.face_vel[f] = lx * nx + ly * t1x + lz * t2x;
+        A.face_vel[fs_ + f] = lx * ny + ly * t1y + lz * t2y;
+        A.face_vel[2 * fs_ + f] = lx * nz + ly * t1z + lz * t2z;
+    }
     const S px = F.mx, py = F.my;
     const S pz = (DIM == 3) ? F.mz : S(0.0);
     F.mx = px * nx + py * t1x + pz * t2x;
@@ -729,11 +758,11 @@ IBIS_HD void face_viscous_flux(const FvArgs<S>& A, int f, Flux5<S>& F) {
 // ---------------------------------------------------------------------------------------
 // general path, interface kernels: write / update the face flux array
 // ---------------------------------------------------------------------------------------
-template <int DIM, int FLUX, bool O2, typename S>
+template <int DIM, int FLUX, bool O2, typename S, bool MOVING = false>
 IBIS_HD void face_flux_body(const FvArgs<S>& A, int f) {
     typedef mem<S> M;
     const long fs_ = A.g.fstride;
-    Flux5<S> F = face_convective_flux<DIM, FLUX, O2>(A, f);
+    Flux5<S> F = face_convective_flux<DIM, FLUX, O2, S, MOVING>(A, f);
     M::store(A.flux, 0 * fs_ + f, F.mass);
     M::store(A.flux, 1 * fs_ + f, F.mx);
     M::store(A.flux, 2 * fs_ + f, F.my);
@@ -756,6 +785,46 @@ IBIS_HD void face_viscous_body(const FvArgs<S>& A, int f) {
     M::store(A.flux, 2 * fs_ + f, F.my);
     if (DIM == 3) M::store(A.flux, 3 * fs_ + f, F.mz);
     M::store(A.flux, 4 * fs_ + f, F.energy);
+}
+
+// GridBlock::compute_face_vel (grid.h:571-592): average of the vertex velocities of the interface, summed in
+// the interface's vertex order.  fverts = [4][fstride] vertex ids, -1 past the last; vvel = n_vertices x 3.
+IBIS_HD void face_vel_body(const GridDev& g, const int* fverts, const double* vvel, double* face_vel, int f) {
+    double vx = 0.0, vy = 0.0, vz = 0.0;
+    int nv = 0;
+    for (int k = 0; k < 4; k++) {
+        const int v = fverts[k * g.fstride + f];
+        if (v < 0) break;
+        vx += vvel[3 * (long)v];
+        vy += vvel[3 * (long)v + 1];
+        vz += vvel[3 * (long)v + 2];
+        nv++;
+    }
+    face_vel[f] = vx / (double)nv;
+    face_vel[g.fstride + f] = vy / (double)nv;
+    face_vel[2 * g.fstride + f] = vz / (double)nv;
+}
+
+// FiniteVolume::apply_geometric_conservation_law (finite_volume.cpp:99-128): dudt -= U dV/dt / V
+template <int DIM, typename S>
+IBIS_HD void gcl_body(const FvArgs<S>& A, S* const* cq, int c) {
+    typedef mem<S> M;
+    const GridDev& g = A.g;
+    const long cs = g.cstride, fs_ = g.fstride;
+    S dVdt = S(0.0);
+    for (int j = 0; j < MAXF; j++) {
+        if (j >= g.max_faces) break;
+        const int f = g.cf_face[j * cs + c];
+        if (f < 0) break;
+        const double area = g.f_area[f] * (double)g.cf_out[j * cs + c];
+        const double vx = A.face_vel[f], vy = A.face_vel[fs_ + f], vz = A.face_vel[2 * fs_ + f];
+        dVdt += (vx * g.f_n[f] + vy * g.f_n[fs_ + f] + vz * g.f_n[2 * fs_ + f]) * area;
+    }
+    const S V = S(g.volume[c]);
+    for (int k = 0; k < 5; k++) {
+        if (k == 3 && DIM != 3) continue;
+        M::store(A.dudt[k], c, M::load(A.dudt[k], c) - M::load(cq[k], c) * dVdt / V);
+    }
 }
 
 // flux_surface_integral from the stored face fluxes (finite_volume.cpp:221-256)

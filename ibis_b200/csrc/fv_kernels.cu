@@ -398,6 +398,26 @@ __global__ void __launch_bounds__(128) k_face_flux(const FvArgs<S> A) {
     if (f < A.g.n_faces) face_flux_body<DIM, FLUX, O2>(A, f);
 }
 
+// moving grid: interface-velocity-relative flux (convective_flux.cpp:105-140,166-176)
+template <int DIM, int FLUX, bool O2, typename S>
+__global__ void __launch_bounds__(128) k_face_flux_moving(const FvArgs<S> A) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f < A.g.n_faces) face_flux_body<DIM, FLUX, O2, S, true>(A, f);
+}
+
+__global__ void __launch_bounds__(256) k_face_vel(const GridDev g, const int* fverts, const double* vvel, double* face_vel) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f < g.n_faces) face_vel_body(g, fverts, vvel, face_vel, f);
+}
+
+template <typename S>
+struct CqPtrs { S* p[5]; };
+template <int DIM, typename S>
+__global__ void __launch_bounds__(256) k_gcl(const FvArgs<S> A, const CqPtrs<S> cq) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < A.g.n_owned) gcl_body<DIM>(A, cq.p, c);
+}
+
 template <int DIM, typename S>
 __global__ void __launch_bounds__(128) k_face_viscous(const FvArgs<S> A) {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
@@ -678,6 +698,39 @@ void launch_face_flux(ibis_b200_ctx* c, const FvArgs<S>& A) {
 }
 template void launch_face_flux<double>(ibis_b200_ctx*, const FvArgs<double>&);
 template void launch_face_flux<dual>(ibis_b200_ctx*, const FvArgs<dual>&);
+
+template <typename S>
+void launch_face_flux_moving(ibis_b200_ctx* c, const FvArgs<S>& A) {
+    if (A.g.n_faces == 0) return;
+    if (A.g.dim == 3) {
+        DISPATCH_FLUX_O2(k_face_flux_moving, 3, nblocks(A.g.n_faces, 128), 128, 0)
+    } else {
+        DISPATCH_FLUX_O2(k_face_flux_moving, 2, nblocks(A.g.n_faces, 128), 128, 0)
+    }
+    CUDA_CHECK_LAUNCH(c);
+}
+template void launch_face_flux_moving<double>(ibis_b200_ctx*, const FvArgs<double>&);
+template void launch_face_flux_moving<dual>(ibis_b200_ctx*, const FvArgs<dual>&);
+
+void launch_face_vel(ibis_b200_ctx* c, const int* fverts, const double* vvel, double* face_vel) {
+    if (c->g.n_faces == 0) return;
+    k_face_vel<<<nblocks(c->g.n_faces, 256), 256, 0, c->stream>>>(c->g, fverts, vvel, face_vel);
+    CUDA_CHECK_LAUNCH(c);
+}
+
+template <typename S>
+void launch_gcl(ibis_b200_ctx* c, const FvArgs<S>& A, S* const* cq) {
+    if (A.g.n_owned == 0) return;
+    CqPtrs<S> q;
+    for (int k = 0; k < 5; k++) q.p[k] = cq[k];
+    if (A.g.dim == 3)
+        k_gcl<3, S><<<nblocks(A.g.n_owned, 256), 256, 0, c->stream>>>(A, q);
+    else
+        k_gcl<2, S><<<nblocks(A.g.n_owned, 256), 256, 0, c->stream>>>(A, q);
+    CUDA_CHECK_LAUNCH(c);
+}
+template void launch_gcl<double>(ibis_b200_ctx*, const FvArgs<double>&, double* const*);
+template void launch_gcl<dual>(ibis_b200_ctx*, const FvArgs<dual>&, dual* const*);
 
 template <typename S>
 void launch_face_viscous(ibis_b200_ctx* c, const FvArgs<S>& A) {

@@ -25,6 +25,7 @@ namespace ib {
 struct Renumbered {
     ibis_b200_grid_desc desc;                 // same content as the input, new numbering
     std::vector<int> ref2int, int2ref;        // cells incl. ghosts
+    std::vector<int> face_ref2int;            // reference interface id -> internal id (both renumberings composed)
     std::vector<int64_t> face_left, face_right, cf_ids, cf_nbr, tag_faces;
     std::vector<int32_t> cf_out;
     std::vector<int64_t> cf_off;
@@ -155,6 +156,9 @@ inline int renumber_grid(const ibis_b200_grid_desc* gd, bool morton, Renumbered&
     R.cell_first_face[n_grad] = counter;
     for (int64_t f = 0; f < n_faces; f++)
         if (fnew[f] < 0) fnew[f] = counter++;       // interfaces no cell lists (not expected)
+    R.face_ref2int.resize(n_faces);
+#pragma omp parallel for schedule(static)
+    for (int64_t f = 0; f < n_faces; f++) R.face_ref2int[f] = (int)fnew[f];
 
     // ---- permuted copies ----
     const int64_t n_cf = R.cf_off[n_cells];
@@ -329,6 +333,8 @@ inline int regroup_faces(Renumbered& R, int T, TileLayout& TL, const char** err)
 #pragma omp parallel for schedule(static)
     for (int64_t q = 0; q < (int64_t)R.cf_ids.size(); q++) R.cf_ids[q] = fnew[R.cf_ids[q]];
     for (auto& f : R.tag_faces) f = fnew[f];
+#pragma omp parallel for schedule(static)
+    for (int64_t f = 0; f < n_faces; f++) R.face_ref2int[f] = (int)fnew[R.face_ref2int[f]];
     R.desc.face_left = R.face_left.data(); R.desc.face_right = R.face_right.data();
     R.desc.face_area = R.f_area.data(); R.desc.face_norm = R.f_norm.data();
     R.desc.face_tan1 = R.f_t1.data(); R.desc.face_tan2 = R.f_t2.data(); R.desc.face_centre = R.f_c.data();

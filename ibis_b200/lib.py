@@ -232,6 +232,8 @@ class Library:
             "ibis_b200_apply_time_derivative": [vp, i, i, i, d],
             "ibis_b200_l2_norms": [vp, i, vp],
             "ibis_b200_debug_gradients": [vp, i, vp, vp], "ibis_b200_debug_dual_ops": [vp, vp, vp],
+            "ibis_b200_set_face_vertices": [vp, vp, i64], "ibis_b200_set_vertex_velocities": [vp, vp],
+            "ibis_b200_compute_dudt_moving": [vp, i, i, i, i], "ibis_b200_debug_face_velocities": [vp, vp],
             "ibis_b200_rk_step": [vp, i, i, i, vp, vp, d, d, d, C.POINTER(d), C.POINTER(d)],
             "ibis_b200_rk_residual_norms": [vp, vp], "ibis_b200_rk_distinct_stages": [vp, i],
             "ibis_b200_jfnk_set_dual": [vp, i, i, i],
@@ -533,6 +535,24 @@ class Context:
         l = np.zeros(self.n_cells)
         self._ck(self.lib.ibis_b200_debug_gradients(self.h, var, _ptr(g), _ptr(l)), "debug_gradients")
         return g, l
+
+    # moving grid
+    def set_face_vertices(self, face_vertices, n_vertices):
+        a = _as(face_vertices, np.int64)
+        self._ck(self.lib.ibis_b200_set_face_vertices(self.h, _ptr(a), int(n_vertices)), "set_face_vertices")
+
+    def set_vertex_velocities(self, vertex_vel):
+        a = _as(vertex_vel, np.float64)
+        self._ck(self.lib.ibis_b200_set_vertex_velocities(self.h, _ptr(a)), "set_vertex_velocities")
+
+    def compute_dudt_moving(self, fs, cq, dudt, allow_reconstruction=True):
+        self._ck(self.lib.ibis_b200_compute_dudt_moving(self.h, fs, cq, dudt, int(allow_reconstruction)),
+                 "compute_dudt_moving")
+
+    def debug_face_velocities(self):
+        out = np.zeros((self.n_faces, 3))
+        self._ck(self.lib.ibis_b200_debug_face_velocities(self.h, _ptr(out)), "debug_face_velocities")
+        return out
 
     def debug_dual_ops(self, x, y, r):
         """-> (22, 2) array of (re, du): see ibis_b200_debug_dual_ops in include/ibis_b200.h"""

@@ -233,6 +233,23 @@ int ibis_b200_apply_time_derivative(ibis_b200_ctx*, int u0, int u1, int dudt, do
 /* ConservedQuantities<T>::L2_norms (conserved_quantities.cpp:41-69):
  * out = {global, mass, momentum_x, momentum_y, momentum_z, energy} */
 int ibis_b200_l2_norms(ibis_b200_ctx*, int cq, double out[6]);
+/* ---- moving grid: the residual terms (first part) -----------------
+ * compute_dudt(flow_state, vertex_vel, cq, grid, dudt, ...) of a grid with motion enabled
+ * (finite_volume.cpp:57-85): interface velocities = average of the vertex velocities
+ * (GridBlock::compute_face_vel, grid/grid.h:571-592), fluxes relative to the moving interface with the
+ * correction back to the inertial frame (convective_flux.cpp:105-140,166-176), constant_flux relative
+ * to the interface (boundary.cpp:420-426), and the geometric-conservation-law term -U dV/dt / V
+ * (finite_volume.cpp:99-128).  The vertex velocities are what the reference's GridMotionDriver
+ * produces (rigid_body_translation.cpp:14-27: one constant vector; shock fitting is not built); moving
+ * the vertices and recomputing the geometry between stages is not built yet either.
+ * face_vertices: Interfaces::vertex_ids (grid/interface.h:331) = ibis_b200_grid_face_vertices, n_faces x 4
+ * padded with -1, set once; vertex_vel: n_vertices x 3, copied at the call. */
+int ibis_b200_set_face_vertices(ibis_b200_ctx*, const int64_t* face_vertices, int64_t n_vertices);
+int ibis_b200_set_vertex_velocities(ibis_b200_ctx*, const double* vertex_vel);
+int ibis_b200_compute_dudt_moving(ibis_b200_ctx*, int fs, int cq, int dudt, int allow_reconstruction);
+/* GridBlock::face_vel() after the last moving evaluation (n_faces x 3, reference numbering) */
+int ibis_b200_debug_face_velocities(ibis_b200_ctx*, double* face_vel);
+
 /* intermediates of the last real evaluation, for bisecting parity (reference numbering):
  * grad [n_cells x 3] and limiter [n_cells] of variable var (0 rho, 1 thermo-2 (u|p|T),
  * 2 vx, 3 vy, 4 vz); either pointer may be NULL. */

@@ -17,6 +17,7 @@
 
 #include <finite_volume/conserved_quantities.h>
 #include <finite_volume/finite_volume.h>
+#include <finite_volume/grid_motion_driver.h>
 #include <finite_volume/primative_conserved_conversion.h>
 #include <gas/flow_state.h>
 #include <gas/transport_properties.h>
@@ -57,6 +58,8 @@ struct CaseBase {
 
 template <typename T>
 struct Case : CaseBase {
+    using scalar = T;
+    bool motion_set = false;
     json config;
     GridBlock<T> grid;
     FiniteVolume<T> fv;
@@ -273,6 +276,38 @@ int ref_compute_dudt(void* h, double* prim_re, double* prim_du, double* dudt_re,
                 if (dudt_re) dudt_re[i * nc + k] = re(c.dudt(i, k));
                 if (dudt_du) dudt_du[i * nc + k] = du(c.dudt(i, k));
             }
+        return rc;
+    });
+}
+
+// The moving-grid overload FiniteVolume<T>::compute_dudt(fs, vertex_vel, cq, grid, dudt, ...)
+// (finite_volume.cpp:57-85) with the motion driver of config.grid.motion, as RungeKutta wires it
+// (runge_kutta.cpp:58-66,121-129); cq = primatives_to_conserved(fs).  face_vel (n_faces x 3) receives
+// GridBlock::face_vel() as the evaluation leaves it.
+int ref_compute_dudt_moving(void* h, double* prim_re, double* prim_du, double* dudt_re,
+                            double* dudt_du, int allow_reconstruction, double* face_vel) {
+    return dispatch(h, [&](auto& c) {
+        using T = typename std::decay_t<decltype(c)>::scalar;
+        if (!c.grid.moving()) return -1;
+        if (!c.motion_set) {
+            auto driver = build_grid_motion_driver<T>(c.grid, c.config.at("grid").at("motion"));
+            c.grid.set_motion_driver(driver);
+            c.motion_set = true;
+        }
+        c.load_prim(prim_re, prim_du);
+        primatives_to_conserved(c.cq, c.fs, c.gm);
+        Vector3s<T> vertex_vel(c.grid.num_vertices());
+        int rc = (int)c.fv.compute_dudt(c.fs, vertex_vel, c.cq, c.grid, c.dudt, c.gm, c.tp,
+                                        allow_reconstruction != 0);
+        c.store_prim(prim_re, prim_du);
+        size_t n = c.grid.num_cells();
+        size_t nc = c.dudt.n_conserved();
+        for (size_t i = 0; i < n; i++)
+            for (size_t k = 0; k < nc; k++) {
+                if (dudt_re) dudt_re[i * nc + k] = re(c.dudt(i, k));
+                if (dudt_du) dudt_du[i * nc + k] = du(c.dudt(i, k));
+            }
+        copy_vec3(c.grid.face_vel(), c.grid.num_interfaces(), face_vel);
         return rc;
     });
 }

@@ -66,6 +66,9 @@ class RefLib:
         L.ref_grid_wls_r.argtypes = [C.c_void_p, _dp]
         L.ref_compute_dudt.restype = C.c_int
         L.ref_compute_dudt.argtypes = [C.c_void_p] + [C.c_void_p] * 4 + [C.c_int]
+        if hasattr(L, "ref_compute_dudt_moving"):
+            L.ref_compute_dudt_moving.restype = C.c_int
+            L.ref_compute_dudt_moving.argtypes = [C.c_void_p] + [C.c_void_p] * 4 + [C.c_int, C.c_void_p]
         L.ref_time_dudt.restype = C.c_double
         L.ref_time_dudt.argtypes = [C.c_void_p, _dp, C.c_int, C.c_int]
         L.ref_intermediates.argtypes = [C.c_void_p] + [C.c_void_p] * 15
@@ -171,6 +174,24 @@ class RefCase:
             return dr, pr, dd, pd
         self.lib.ref_compute_dudt(self.h, _ptr(pr), None, _ptr(dr), None, int(allow_reconstruction))
         return dr, pr
+
+    def compute_dudt_moving(self, prim, prim_dual=None, allow_reconstruction=True):
+        """the moving-grid overload (config.grid.motion enabled). Returns (dudt, prim_after, face_vel) or, dual,
+        (dudt, prim_after, dudt_du, prim_du, face_vel)."""
+        pr = np.array(prim, dtype=np.float64, order="C").reshape(self.n_total, 7)
+        dr = np.zeros((self.n_cells, self.n_cons))
+        fv = np.zeros((self.n_faces, 3))
+        if self.dual:
+            pd = (np.zeros_like(pr) if prim_dual is None
+                  else np.array(prim_dual, dtype=np.float64, order="C").reshape(self.n_total, 7))
+            dd = np.zeros_like(dr)
+            rc = self.lib.ref_compute_dudt_moving(self.h, _ptr(pr), _ptr(pd), _ptr(dr), _ptr(dd),
+                                                  int(allow_reconstruction), _ptr(fv))
+            assert rc == 0, "the reference grid is not moving"
+            return dr, pr, dd, pd, fv
+        rc = self.lib.ref_compute_dudt_moving(self.h, _ptr(pr), None, _ptr(dr), None, int(allow_reconstruction), _ptr(fv))
+        assert rc == 0, "the reference grid is not moving"
+        return dr, pr, fv
 
     def time_dudt(self, prim, nrep, allow_reconstruction=True):
         pr = np.array(prim, dtype=np.float64, order="C").reshape(self.n_total, 7)

@@ -155,6 +155,33 @@ _add("quad2d_bl_profile", _quad, quad2_profile_bcs, 0.5, flux_calculator="ausmdv
 _add("box3d_profile_cflux", lambda: su2.box_hex(6), box3_profile_flux_bcs, flux_calculator="ausmdv")
 _add("quad2d_cflux_viscous", _quad, quad2_flux_visc_bcs, 0.5, flux_calculator="hanel", viscous=True)
 
+# moving-grid residuals (first part): a case of CASES + a rigid-body translation
+# of the grid (finite_volume/rigid_body_translation.cpp) -> fixtures tests/golden/moving_<name>.npz
+MOVING_CASES = {
+    "box3d_ausmdv": (120.0, -75.0, 40.0),
+    "box3d_rusanov": (-310.0, 20.0, 55.0),
+    "quad2d_hanel": (-200.0, 90.0, 0.0),
+    "quad2d_ldfss2": (75.0, 130.0, 0.0),
+    "mixed3d_walls": (50.0, 60.0, -70.0),          # triangular faces: (v + v + v) / 3 is not always v
+    "tet3d": (33.0, -21.0, 12.0),
+    "quad2d_cflux_viscous": (150.0, -30.0, 0.0),   # constant_flux relative to the moving interface, viscous
+    "box3d_profile_cflux": (-40.0, 25.0, 10.0),
+}
+
+
+def build_moving_case(name):
+    """-> (mesh, config with grid.motion enabled, Grid, prim, vertex velocities (n_vertices, 3))"""
+    mesh_f, bcs_f, mach, kw = CASES[name]
+    mesh = mesh_f()
+    bcs = bcs_f()
+    vel = MOVING_CASES[name]
+    config = cfg.make_config(mesh.dim, bcs, motion=cfg.rigid_body_translation(*vel), **kw)
+    g = gridmod.build_grid(mesh, list(bcs.keys()))
+    prim = perturbed_state(g, mesh.dim, mach)
+    vvel = np.tile(np.array(vel, dtype=np.float64), (len(mesh.vertices), 1))
+    return mesh, config, g, prim, vvel
+
+
 VISCOUS_CASES = [k for k, v in CASES.items() if v[3].get("viscous")]
 
 

@@ -231,6 +231,34 @@ template void launch_face_flux<double>(ibis_b200_ctx*, const FvArgs<double>&);
 template void launch_face_flux<dual>(ibis_b200_ctx*, const FvArgs<dual>&);
 
 template <typename S>
+void launch_face_flux_moving(ibis_b200_ctx* c, const FvArgs<S>& A) {
+#pragma omp parallel for
+    for (int i = 0; i < A.g.n_faces; i++) {
+#define FACE_FLUX(D, F, O) face_flux_body<D, F, O, S, true>(A, i);
+        EMU_FLUX_CALL(FACE_FLUX)
+#undef FACE_FLUX
+    }
+    c->launches++;
+}
+template void launch_face_flux_moving<double>(ibis_b200_ctx*, const FvArgs<double>&);
+template void launch_face_flux_moving<dual>(ibis_b200_ctx*, const FvArgs<dual>&);
+
+void launch_face_vel(ibis_b200_ctx* c, const int* fverts, const double* vvel, double* face_vel) {
+    for (int f = 0; f < c->g.n_faces; f++) face_vel_body(c->g, fverts, vvel, face_vel, f);
+    c->launches++;
+}
+
+template <typename S>
+void launch_gcl(ibis_b200_ctx* c, const FvArgs<S>& A, S* const* cq) {
+    for (int i = 0; i < A.g.n_owned; i++) {
+        if (A.g.dim == 3) gcl_body<3>(A, cq, i); else gcl_body<2>(A, cq, i);
+    }
+    c->launches++;
+}
+template void launch_gcl<double>(ibis_b200_ctx*, const FvArgs<double>&, double* const*);
+template void launch_gcl<dual>(ibis_b200_ctx*, const FvArgs<dual>&, dual* const*);
+
+template <typename S>
 void launch_face_viscous(ibis_b200_ctx* c, const FvArgs<S>& A) {
     for (int f = 0; f < A.g.n_faces; f++) {
         if (A.g.dim == 3) face_viscous_body<3>(A, f); else face_viscous_body<2>(A, f);
