@@ -270,6 +270,8 @@ template <typename S>
 int compute_dudt_impl(ibis_b200_ctx* c, Buffer* fs, Buffer* dudt, bool allow_reconstruction, double* dt_bits = nullptr,
                       Buffer* cq = nullptr) {
     const bool moving = cq != nullptr;
+    if (!moving && c->geometry_moved)
+        return fail(c, IBIS_B200_EINVAL, "the vertices have moved: only ibis_b200_compute_dudt_moving is valid on this context");
     int rc = ensure_fv_temporaries<S>(c, moving && c->cfg.reconstruction_order > 1, moving);
     if (rc) return rc;
     FvArgs<S> A = make_args<S>(c, fs, dudt, allow_reconstruction);
@@ -1082,6 +1084,78 @@ int ibis_b200_set_vertex_velocities(ibis_b200_ctx* c, const double* vertex_vel) 
     GPU_TRY(c, gpu::h2d(c->d_vertex_vel, vertex_vel, (size_t)3 * c->n_vertices * sizeof(double), c->stream));
     GPU_TRY(c, gpu::stream_sync(c->stream));      // vertex_vel is the caller's
     c->have_vertex_vel = true;
+    return 0;
+}
+
+int ibis_b200_set_cell_vertices(ibis_b200_ctx* c, const int32_t* cell_types, const int64_t* cell_vertices) {
+    if (!c || !cell_types || !cell_vertices) return fail(c, IBIS_B200_EINVAL, "null argument");
+    if (!c->d_fverts) return fail(c, IBIS_B200_EINVAL, "ibis_b200_set_face_vertices has not been called");
+    if (c->d_cverts) return fail(c, IBIS_B200_EINVAL, "cell vertices already set");
+    std::vector<int> cv((size_t)8 * c->cstride, -1), ct((size_t)c->cstride, 0);
+    bool bad = false;
+#pragma omp parallel for schedule(static) reduction(|| : bad)
+    for (int64_t o = 0; o < c->n_cells; o++) {
+        const int64_t i = c->ref2int.empty() ? o : c->ref2int[o];
+        const int nv = gb_num_vertices(cell_types[o]);
+        if (nv == 0) bad = true;
+        ct[i] = cell_types[o];
+        for (int k = 0; k < nv; k++) {
+            const int64_t v = cell_vertices[8 * o + k];
+            if (v < 0 || v >= c->n_vertices) bad = true;
+            cv[(size_t)k * c->cstride + i] = (int)v;
+        }
+    }
+    if (bad) return fail(c, IBIS_B200_EINVAL, "cell refers to a vertex outside the vertex list, or unsupported cell type");
+    int rc = upload_vec(c, cv, &c->d_cverts);
+    if (!rc) rc = upload_vec(c, ct, &c->d_ctype);
+    if (!rc) rc = dev_alloc_zero<double>(c, 3 * c->n_vertices, &c->d_vertex_pos);
+    if (rc) return fail(c, rc, "out of device memory (moving grid)");
+    return 0;
+}
+
+// GridBlock::compute_geometric_data (grid.h:169-178) from the vertex positions on the device
+static int recompute_geometry(ibis_b200_ctx* c) {
+    GeomUpdate U;
+    U.fverts = c->d_fverts;
+    U.cverts = c->d_cverts;
+    U.ctype = c->d_ctype;
+    U.pos = c->d_vertex_pos;
+    U.f_c = const_cast<double*>(c->g.f_c);
+    U.f_area = const_cast<double*>(c->g.f_area);
+    U.f_geom = const_cast<double*>(c->g.f_geom);
+    U.cxyz = const_cast<double*>(c->g.cx);
+    U.volume = const_cast<double*>(c->g.volume);
+    launch_geom_update(c, U);
+    launch_wls_r(c, const_cast<double*>(c->g.wls_r));                                  // compute_gradient_weights
+    launch_cell_static(c, const_cast<double*>(c->g.cf_w), const_cast<double*>(c->g.cf_d));
+    c->geometry_moved = true;
+    return c->last_error.empty() ? 0 : IBIS_B200_ECUDA;
+}
+
+int ibis_b200_set_vertex_positions(ibis_b200_ctx* c, const double* positions) {
+    if (!c || !positions) return fail(c, IBIS_B200_EINVAL, "null argument");
+    if (!c->d_cverts) return fail(c, IBIS_B200_EINVAL, "ibis_b200_set_cell_vertices has not been called");
+    GPU_TRY(c, gpu::h2d(c->d_vertex_pos, positions, (size_t)3 * c->n_vertices * sizeof(double), c->stream));
+    GPU_TRY(c, gpu::stream_sync(c->stream));
+    const bool first = !c->have_vertex_pos;
+    c->have_vertex_pos = true;
+    // the first call hands over the positions the grid was built from: nothing to recompute
+    return first ? 0 : recompute_geometry(c);
+}
+
+int ibis_b200_move_vertices(ibis_b200_ctx* c, double scale, int recompute) {
+    if (!c) return IBIS_B200_EINVAL;
+    if (!c->have_vertex_pos || !c->have_vertex_vel)
+        return fail(c, IBIS_B200_EINVAL, "move_vertices needs vertex positions and velocities");
+    launch_move_vertices(c, c->d_vertex_pos, c->d_vertex_vel, scale, 3 * c->n_vertices);
+    c->geometry_moved = true;
+    return recompute ? recompute_geometry(c) : (c->last_error.empty() ? 0 : IBIS_B200_ECUDA);
+}
+
+int ibis_b200_get_vertex_positions(ibis_b200_ctx* c, double* positions) {
+    if (!c || !positions || !c->have_vertex_pos) return fail(c, IBIS_B200_EINVAL, "no vertex positions");
+    GPU_TRY(c, gpu::d2h(positions, c->d_vertex_pos, (size_t)3 * c->n_vertices * sizeof(double), c->stream));
+    GPU_TRY(c, gpu::stream_sync(c->stream));
     return 0;
 }
 

@@ -74,7 +74,12 @@ struct ibis_b200_ctx {
     int64_t n_vertices = 0;
     double* d_vertex_vel = nullptr;      // n_vertices x 3
     double* d_face_vel = nullptr;        // [3][fstride]
-    bool have_vertex_vel = false;       // any constant_flux: evaluations go through the face-flux array
+    bool have_vertex_vel = false;
+    int* d_cverts = nullptr;             // [8][cstride] vertex ids of every valid cell (internal numbering)
+    int* d_ctype = nullptr;
+    double* d_vertex_pos = nullptr;      // n_vertices x 3
+    bool have_vertex_pos = false;
+    bool geometry_moved = false;         // the fused static paths hold tables of the ORIGINAL geometry       // any constant_flux: evaluations go through the face-flux array
 
     // internal renumbering (layout.h): reference cell id -> internal id, nullptr = identity
     int* d_ref2int = nullptr;
@@ -154,6 +159,8 @@ void launch_face_flux(ibis_b200_ctx* c, const FvArgs<S>& A);       // general pa
 template <typename S>
 void launch_face_flux_moving(ibis_b200_ctx* c, const FvArgs<S>& A);   // moving grid: relative to A.face_vel
 void launch_face_vel(ibis_b200_ctx* c, const int* fverts, const double* vvel, double* face_vel);   // compute_face_vel
+void launch_geom_update(ibis_b200_ctx* c, const GeomUpdate& U);       // compute_geometric_data after a vertex move
+void launch_move_vertices(ibis_b200_ctx* c, double* pos, const double* vel, double scale, int64_t n3);
 template <typename S>
 void launch_gcl(ibis_b200_ctx* c, const FvArgs<S>& A, S* const* cq);   // geometric conservation law
 template <typename S>

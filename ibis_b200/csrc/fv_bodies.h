@@ -7,6 +7,7 @@
 
 #include <stdint.h>
 
+#include "grid_bodies.h"
 #include "physics.h"
 
 namespace ib {
@@ -785,6 +786,91 @@ IBIS_HD void face_viscous_body(const FvArgs<S>& A, int f) {
     M::store(A.flux, 2 * fs_ + f, F.my);
     if (DIM == 3) M::store(A.flux, 3 * fs_ + f, F.mz);
     M::store(A.flux, 4 * fs_ + f, F.energy);
+}
+
+// ---------------------------------------------------------------------------------------
+// moving grid: GridBlock::compute_geometric_data (grid.h:169-178) on the device-resident layout after the
+// vertices moved -- interface centres and areas, cell centroids and volumes, ghost-cell centres (the
+// reference does not recompute the interface orientations there); the WLS tables follow through
+// wls_r_body / cell_static_body.  Same formulas as grid_bodies.h (the initial build).
+// ---------------------------------------------------------------------------------------
+struct GeomUpdate {
+    const int* fverts;     // [4][fstride] vertex ids of every interface, -1 padded
+    const int* cverts;     // [8][cstride] vertex ids of every valid cell, VTK order
+    const int* ctype;      // VTK code of every valid cell
+    const double* pos;     // n_vertices x 3
+    double* f_c;           // the GridDev arrays, writable
+    double* f_area;
+    double* f_geom;
+    double* cxyz;          // cx | cy | cz
+    double* volume;
+};
+
+IBIS_HD void geom_face_body(const GridDev& g, const GeomUpdate& U, int f) {
+    long v[4];
+    int nv = 0;
+    for (int k = 0; k < 4; k++) {
+        v[k] = U.fverts[k * g.fstride + f];
+        if (v[k] >= 0) nv = k + 1;
+    }
+    for (int d = 0; d < 3; d++) {
+        double acc = 0.0;
+        for (int k = 0; k < nv; k++) acc += U.pos[3 * v[k] + d];
+        U.f_c[d * g.fstride + f] = acc / (double)nv;
+    }
+    double area;
+    if (nv == 2) {
+        const double d0 = U.pos[3 * v[1]] - U.pos[3 * v[0]], d1 = U.pos[3 * v[1] + 1] - U.pos[3 * v[0] + 1],
+                     d2 = U.pos[3 * v[1] + 2] - U.pos[3 * v[0] + 2];
+        area = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+    } else if (nv == 3) {
+        area = gb_tri_area(U.pos, v[0], v[1], v[2]);
+    } else {
+        area = gb_tri_area(U.pos, v[0], v[1], v[2]) + gb_tri_area(U.pos, v[0], v[2], v[3]);
+    }
+    U.f_area[f] = area;
+    U.f_geom[(long)f * 10 + 9] = area;
+}
+
+IBIS_HD void geom_centroid_body(const GridDev& g, const GeomUpdate& U, int c) {
+    const int nv = gb_num_vertices(U.ctype[c]);
+    for (int d = 0; d < 3; d++) {
+        double acc = 0.0;
+        for (int k = 0; k < nv; k++) acc += U.pos[3 * (long)U.cverts[k * g.cstride + c] + d];
+        U.cxyz[d * g.cstride + c] = acc / (double)nv;
+    }
+}
+
+IBIS_HD void geom_volume_body(const GridDev& g, const GeomUpdate& U, int c) {
+    const long cs = g.cstride, fs_ = g.fstride;
+    if (g.dim == 2) {
+        const long a = U.cverts[c], b = U.cverts[cs + c], d = U.cverts[2 * cs + c];
+        U.volume[c] = U.ctype[c] == VTK_TRI ? gb_tri_area(U.pos, a, b, d)
+                                           : gb_tri_area(U.pos, a, b, d) + gb_tri_area(U.pos, a, d, (long)U.cverts[3 * cs + c]);
+        return;
+    }
+    double acc = 0.0;
+    for (int j = 0; j < g.max_faces; j++) {
+        const int f = g.cf_face[j * cs + c];
+        if (f < 0) break;
+        const double out = (double)g.cf_out[j * cs + c];
+        const double dotv = U.f_c[f] * out * g.f_n[f] + U.f_c[fs_ + f] * out * g.f_n[fs_ + f] +
+                            U.f_c[2 * fs_ + f] * out * g.f_n[2 * fs_ + f];
+        acc = acc + dotv * U.f_area[f];
+    }
+    U.volume[c] = acc / 3.0;
+}
+
+IBIS_HD void geom_ghost_body(const GridDev& g, const GeomUpdate& U, int k) {
+    const int f = g.bf_face[k];
+    const int l = g.f_left[f], r = g.f_right[f];
+    int valid, ghost;
+    if (l < g.n_cells) { valid = l; ghost = r; } else { valid = r; ghost = l; }
+    for (int d = 0; d < 3; d++) {
+        const double fc = U.f_c[d * g.fstride + f];
+        const double dxyz = fc - U.cxyz[d * g.cstride + valid];
+        U.cxyz[d * g.cstride + ghost] = fc + dxyz;
+    }
 }
 
 // GridBlock::compute_face_vel (grid.h:571-592): average of the vertex velocities of the interface, summed in

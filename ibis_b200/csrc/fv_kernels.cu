@@ -410,6 +410,22 @@ __global__ void __launch_bounds__(256) k_face_vel(const GridDev g, const int* fv
     if (f < g.n_faces) face_vel_body(g, fverts, vvel, face_vel, f);
 }
 
+// GridBlock::compute_geometric_data after a vertex move (grid.h:169-178): 0 interfaces, 1 centroids,
+// 2 volumes, 3 ghost-cell centres
+template <int OP>
+__global__ void __launch_bounds__(256) k_geom_update(const GridDev g, const GeomUpdate U, const int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (OP == 0) geom_face_body(g, U, i);
+    else if (OP == 1) geom_centroid_body(g, U, i);
+    else if (OP == 2) geom_volume_body(g, U, i);
+    else geom_ghost_body(g, U, i);
+}
+__global__ void __launch_bounds__(256) k_move_vertices(double* pos, const double* vel, const double scale, const long n3) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n3) pos[i] = pos[i] + vel[i] * scale;          // add_scaled_vector (util/vector3.cpp:39-47)
+}
+
 template <typename S>
 struct CqPtrs { S* p[5]; };
 template <int DIM, typename S>
@@ -711,6 +727,20 @@ void launch_face_flux_moving(ibis_b200_ctx* c, const FvArgs<S>& A) {
 }
 template void launch_face_flux_moving<double>(ibis_b200_ctx*, const FvArgs<double>&);
 template void launch_face_flux_moving<dual>(ibis_b200_ctx*, const FvArgs<dual>&);
+
+void launch_geom_update(ibis_b200_ctx* c, const GeomUpdate& U) {
+    const GridDev& g = c->g;
+    if (g.n_faces) k_geom_update<0><<<nblocks(g.n_faces, 256), 256, 0, c->stream>>>(g, U, g.n_faces);
+    if (g.n_cells) k_geom_update<1><<<nblocks(g.n_cells, 256), 256, 0, c->stream>>>(g, U, g.n_cells);
+    if (g.n_cells) k_geom_update<2><<<nblocks(g.n_cells, 256), 256, 0, c->stream>>>(g, U, g.n_cells);
+    if (g.n_bfaces) k_geom_update<3><<<nblocks(g.n_bfaces, 256), 256, 0, c->stream>>>(g, U, g.n_bfaces);
+    CUDA_CHECK_LAUNCH(c);
+}
+void launch_move_vertices(ibis_b200_ctx* c, double* pos, const double* vel, double scale, int64_t n3) {
+    if (n3 == 0) return;
+    k_move_vertices<<<nblocks(n3, 256), 256, 0, c->stream>>>(pos, vel, scale, (long)n3);
+    CUDA_CHECK_LAUNCH(c);
+}
 
 void launch_face_vel(ibis_b200_ctx* c, const int* fverts, const double* vvel, double* face_vel) {
     if (c->g.n_faces == 0) return;

@@ -29,7 +29,7 @@ class RkConfig(C.Structure):
                 ("dt_init", C.c_double), ("print_frequency", C.c_int32),
                 ("plot_every_n_steps", C.c_int32), ("plot_frequency", C.c_double),
                 ("residuals_every_n_steps", C.c_int32), ("distinct_stages", C.c_int32),
-                ("residual_frequency", C.c_double)]
+                ("residual_frequency", C.c_double), ("moving_grid", C.c_int32), ("reserved", C.c_int32)]
 
 
 class LinearSolverConfig(C.Structure):
@@ -170,6 +170,9 @@ def solve(ctx, config, prim0, fused_step=True, on_plot=None, on_residuals=None, 
         cfg.plot_frequency = float(sc["plot_frequency"])
         cfg.residuals_every_n_steps = int(sc["residuals_every_n_steps"])
         cfg.residual_frequency = float(sc["residual_frequency"])
+        cfg.moving_grid = int(bool(config["grid"].get("motion", {}).get("enabled", False)))
+        if cfg.moving_grid:
+            cfg.fused_step = 0
         rc = H.lib.ibis_b200_host_run_rk(ctx.h, C.byref(cfg), prim0.ctypes.data, out.ctypes.data,
                                          C.byref(rep), C.byref(obs))
     elif sc["name"] == "steady_state":

@@ -434,7 +434,8 @@ RungeKutta::RungeKutta(ibis_b200_ctx* ctx, const ibis_b200_rk_config& c, const d
     if (c.n_stages < 1 || !c.b) throw std::runtime_error("RungeKutta: bad butcher tableau");
     tableau_ = ButcherTableau(c.n_stages, c.a, c.b);
     cfl_ = make_cfl_schedule(c.cfl);
-    fused_ = c.fused_step != 0;
+    moving_grid_ = c.moving_grid != 0;                                                 // :58
+    fused_ = c.fused_step != 0 && !moving_grid_;
     max_time_ = c.max_time;
     max_step_ = (size_t)c.max_step;
     dt_init_ = c.dt_init;
@@ -475,7 +476,7 @@ int RungeKutta::initialise() {
     ABI(ibis_b200_fs_upload(ctx_, flow_, prim0_, nullptr));                            // io_.read :87
     ABI(ibis_b200_prim_to_cons(ctx_, conserved_quantities_, flow_));                   // :89
     dt_ = (dt_init_ > 0) ? dt_init_ : std::numeric_limits<double>::max();              // :90
-    if (!fused_) function_eval_(flow_, 0);                                             // :93
+    if (!fused_) function_eval_(flow_, conserved_quantities_, 0);                      // :93
     if (residuals_every_n_steps_ > 0 || residual_frequency_ > 0) {
         if (fused_) {
             // the fused step owns its k_[0]; evaluate the initial residual into a scratch buffer
@@ -504,8 +505,9 @@ void RungeKutta::estimate_dt() {                                                
         dt_ = std::min(dt_, plot_frequency_ - time_since_last_plot_);
 }
 
-void RungeKutta::function_eval_(int fs, size_t index) {                                // :121-129
-    ABI(ibis_b200_compute_dudt(ctx_, fs, k_[index], 1));
+void RungeKutta::function_eval_(int fs, int cq, size_t index) {                        // :121-129
+    if (moving_grid_) ABI(ibis_b200_compute_dudt_moving(ctx_, fs, cq, k_[index], 1));
+    else ABI(ibis_b200_compute_dudt(ctx_, fs, k_[index], 1));
 }
 
 int RungeKutta::take_step(size_t step) {
@@ -523,22 +525,32 @@ int RungeKutta::take_step(size_t step) {
         dt_ = dt;
         stable_dt_ = dts;
     } else {
-        function_eval_(flow_, 0);                                                      // :143
+        // Moving grid: `init_vertex_pos_ = grid_.vertices().positions()` (:136) copies a view HANDLE, so
+        // init_vertex_pos_ IS the grid's position array, and vertex_vel_ (:64-65) is one array in every stage
+        // slot: each add_scaled_vector below (:158,172,189) therefore displaces the grid's own vertices in
+        // place, cumulatively.  Reproduced as such: one move per reference call.
+        function_eval_(flow_, conserved_quantities_, 0);                               // :143
         estimate_dt();                                                                 // :147
         for (size_t i = 1; i < tableau_.num_stages(); i++) {
             ABI(ibis_b200_apply_time_derivative(ctx_, conserved_quantities_, k_tmp_, k_[0],
                                                 tableau_.a(i, 0) * dt_));              // :155
+            if (moving_grid_) ABI(ibis_b200_move_vertices(ctx_, tableau_.a(i, 0) * dt_, 0));   // :157-160
             for (size_t j = 1; j < i; j++) {
                 if (tableau_.a(i, j) < 1e-14) continue;                                // :166
                 ABI(ibis_b200_apply_time_derivative(ctx_, k_tmp_, k_tmp_, k_[j], tableau_.a(i, j) * dt_));
+                if (moving_grid_) ABI(ibis_b200_move_vertices(ctx_, tableau_.a(i, j) * dt_, 0));   // :170-173
             }
             ABI(ibis_b200_cons_to_prim(ctx_, k_tmp_, flow_tmp_));                      // :177
-            function_eval_(flow_tmp_, i);                                              // :181
+            if (moving_grid_) ABI(ibis_b200_move_vertices(ctx_, 0.0, 1));              // compute_geometric_data :178-180
+            function_eval_(flow_tmp_, k_tmp_, i);                                      // :181
         }
-        for (size_t i = 0; i < tableau_.num_stages(); i++)                             // :185-186
+        for (size_t i = 0; i < tableau_.num_stages(); i++) {                           // :185-191
             ABI(ibis_b200_apply_time_derivative(ctx_, conserved_quantities_, conserved_quantities_, k_[i],
                                                 tableau_.b(i) * dt_));
+            if (moving_grid_) ABI(ibis_b200_move_vertices(ctx_, tableau_.b(i) * dt_, 0));
+        }
         ABI(ibis_b200_cons_to_prim(ctx_, conserved_quantities_, flow_));               // :193
+        if (moving_grid_) ABI(ibis_b200_move_vertices(ctx_, 0.0, 1));                  // set_vertex_positions :194-196
     }
     t_ += dt_;
     time_since_last_plot_ += dt_;

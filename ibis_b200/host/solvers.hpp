@@ -276,6 +276,7 @@ private:
     ButcherTableau tableau_;
     std::unique_ptr<CflSchedule> cfl_;
     bool fused_;
+    bool moving_grid_ = false;
     double t_ = 0.0, dt_ = 0.0, stable_dt_ = 0.0, max_time_, dt_init_;
     size_t max_step_;
     unsigned int print_frequency_;
@@ -284,7 +285,7 @@ private:
     double time_since_last_plot_ = 0.0, time_since_last_residual_ = 0.0;
     int64_t last_bad_ = 0;
     void estimate_dt();
-    void function_eval_(int fs, size_t index);
+    void function_eval_(int fs, int cq, size_t index);
 };
 
 // ---- solvers/steady_state.h: SteadyState ------------------------------------------------

@@ -233,7 +233,9 @@ class Library:
             "ibis_b200_l2_norms": [vp, i, vp],
             "ibis_b200_debug_gradients": [vp, i, vp, vp], "ibis_b200_debug_dual_ops": [vp, vp, vp],
             "ibis_b200_set_face_vertices": [vp, vp, i64], "ibis_b200_set_vertex_velocities": [vp, vp],
-            "ibis_b200_compute_dudt_moving": [vp, i, i, i, i], "ibis_b200_debug_face_velocities": [vp, vp],
+            "ibis_b200_compute_dudt_moving": [vp, i, i, i, i],
+            "ibis_b200_set_cell_vertices": [vp, vp, vp], "ibis_b200_set_vertex_positions": [vp, vp],
+            "ibis_b200_move_vertices": [vp, d, i], "ibis_b200_get_vertex_positions": [vp, vp], "ibis_b200_debug_face_velocities": [vp, vp],
             "ibis_b200_rk_step": [vp, i, i, i, vp, vp, d, d, d, C.POINTER(d), C.POINTER(d)],
             "ibis_b200_rk_residual_norms": [vp, vp], "ibis_b200_rk_distinct_stages": [vp, i],
             "ibis_b200_jfnk_set_dual": [vp, i, i, i],
@@ -544,6 +546,23 @@ class Context:
     def set_vertex_velocities(self, vertex_vel):
         a = _as(vertex_vel, np.float64)
         self._ck(self.lib.ibis_b200_set_vertex_velocities(self.h, _ptr(a)), "set_vertex_velocities")
+
+    def set_cell_vertices(self, cell_types, cell_vertices):
+        t, v = _as(cell_types, np.int32), _as(cell_vertices, np.int64)
+        self._ck(self.lib.ibis_b200_set_cell_vertices(self.h, _ptr(t), _ptr(v)), "set_cell_vertices")
+
+    def set_vertex_positions(self, positions):
+        a = _as(positions, np.float64)
+        self._n_vertices = len(a)
+        self._ck(self.lib.ibis_b200_set_vertex_positions(self.h, _ptr(a)), "set_vertex_positions")
+
+    def move_vertices(self, scale, recompute_geometry=True):
+        self._ck(self.lib.ibis_b200_move_vertices(self.h, float(scale), int(recompute_geometry)), "move_vertices")
+
+    def get_vertex_positions(self):
+        out = np.zeros((self._n_vertices, 3))
+        self._ck(self.lib.ibis_b200_get_vertex_positions(self.h, _ptr(out)), "get_vertex_positions")
+        return out
 
     def compute_dudt_moving(self, fs, cq, dudt, allow_reconstruction=True):
         self._ck(self.lib.ibis_b200_compute_dudt_moving(self.h, fs, cq, dudt, int(allow_reconstruction)),

@@ -247,6 +247,19 @@ int ibis_b200_l2_norms(ibis_b200_ctx*, int cq, double out[6]);
 int ibis_b200_set_face_vertices(ibis_b200_ctx*, const int64_t* face_vertices, int64_t n_vertices);
 int ibis_b200_set_vertex_velocities(ibis_b200_ctx*, const double* vertex_vel);
 int ibis_b200_compute_dudt_moving(ibis_b200_ctx*, int fs, int cq, int dudt, int allow_reconstruction);
+/* Moving the vertices (solvers/runge_kutta.cpp:136,157-195): cell_types / cell_vertices as in
+ * ibis_b200_mesh_desc, set once after the face vertices; set_vertex_positions hands the positions over (the
+ * first call: the positions the grid was built from; later calls recompute the geometry); move_vertices does
+ * positions += scale * vertex_vel on the device (add_scaled_vector, util/vector3.cpp:39-47) and then, when
+ * recompute_geometry is set (several moves may precede one recomputation, runge_kutta.cpp:157-180), what
+ * GridBlock::compute_geometric_data does (grid/grid.h:169-178): interface centres and areas, cell centroids and
+ * volumes, ghost-cell centres, WLS weights -- not the interface orientations, as in the reference.
+ * Once the vertices have moved the context serves ibis_b200_compute_dudt_moving only (the fused static
+ * kernels keep tables of the original geometry). */
+int ibis_b200_set_cell_vertices(ibis_b200_ctx*, const int32_t* cell_types, const int64_t* cell_vertices);
+int ibis_b200_set_vertex_positions(ibis_b200_ctx*, const double* positions);
+int ibis_b200_move_vertices(ibis_b200_ctx*, double scale, int recompute_geometry);
+int ibis_b200_get_vertex_positions(ibis_b200_ctx*, double* positions);
 /* GridBlock::face_vel() after the last moving evaluation (n_faces x 3, reference numbering) */
 int ibis_b200_debug_face_velocities(ibis_b200_ctx*, double* face_vel);
 

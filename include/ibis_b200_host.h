@@ -47,6 +47,10 @@ typedef struct {
     int32_t distinct_stages;   /* 0 (default): k_[i] alias one array like the reference
                                   (runge_kutta.cpp:49-50, see ibis_b200_rk_distinct_stages) */
     double residual_frequency;
+    int32_t moving_grid;       /* grid.motion.enabled (runge_kutta.cpp:58-70): the context must hold face / cell
+                                  vertices, vertex positions and the motion driver's vertex velocities (rigid body
+                                  translation: one constant vector); forces the unfused call sequence */
+    int32_t reserved;
 } ibis_b200_rk_config;
 
 /* linear_algebra/gmres.cpp:305-318 (make_linear_solver) */

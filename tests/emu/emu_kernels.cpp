@@ -243,6 +243,19 @@ void launch_face_flux_moving(ibis_b200_ctx* c, const FvArgs<S>& A) {
 template void launch_face_flux_moving<double>(ibis_b200_ctx*, const FvArgs<double>&);
 template void launch_face_flux_moving<dual>(ibis_b200_ctx*, const FvArgs<dual>&);
 
+void launch_geom_update(ibis_b200_ctx* c, const GeomUpdate& U) {
+    const GridDev& g = c->g;
+    for (int i = 0; i < g.n_faces; i++) geom_face_body(g, U, i);
+    for (int i = 0; i < g.n_cells; i++) geom_centroid_body(g, U, i);
+    for (int i = 0; i < g.n_cells; i++) geom_volume_body(g, U, i);
+    for (int i = 0; i < g.n_bfaces; i++) geom_ghost_body(g, U, i);
+    c->launches += 4;
+}
+void launch_move_vertices(ibis_b200_ctx* c, double* pos, const double* vel, double scale, int64_t n3) {
+    for (int64_t i = 0; i < n3; i++) pos[i] = pos[i] + vel[i] * scale;
+    c->launches++;
+}
+
 void launch_face_vel(ibis_b200_ctx* c, const int* fverts, const double* vvel, double* face_vel) {
     for (int f = 0; f < c->g.n_faces; f++) face_vel_body(c->g, fverts, vvel, face_vel, f);
     c->launches++;

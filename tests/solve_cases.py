@@ -147,6 +147,16 @@ SOLVE_CASES = {
                                  solver=cfg.steady_state(cfl=5.0, max_steps=8, tolerance=1e-12,
                                                          linear_solver={"type": "gmres", "max_iters": 40,
                                                                         "tol": 1e-3}))),
+    # moving grids: rigid_body_translation driver, vertices displaced and the geometry recomputed every stage
+    # (runge_kutta.cpp:136,157-196)
+    "rk_quad2d_moving": (lambda: su2.box_quad(10, 8, jitter=0.15), cases.quad2_bcs(),
+                         lambda g, d: _perturbed(g, d, 1.0),
+                         dict(flux_calculator="ausmdv", motion=cfg.rigid_body_translation(150.0, -60.0, 0.0),
+                              solver=cfg.runge_kutta(method="ssp-rk3", cfl=0.5, max_step=20, max_time=1.0))),
+    "rk_box3d_moving": (lambda: su2.box_hex(5, 4, 4, jitter=0.2), cases.box3_bcs(),
+                        lambda g, d: _perturbed(g, d, 1.0),
+                        dict(flux_calculator="hanel", motion=cfg.rigid_body_translation(-80.0, 40.0, 25.0),
+                             solver=cfg.runge_kutta(method="midpoint", cfl=0.4, max_step=15, max_time=1.0))),
     # 3-D steady
     "steady_box3d": (lambda: su2.box_hex(4, 4, 3, jitter=0.1), cases.box3_wall_bcs(),
                      lambda g, d: _perturbed(g, d, 1.0),

@@ -21,6 +21,15 @@ def run_solve_case(name, lib_path=None, host_lib=None, fused_step=True, exact=No
     mesh, config, g, prim0, snap = sc.build_solve_case(name)
     gold = dict(np.load(os.path.join(GOLDEN, "solve_" + name + ".npz")))
     ctx = Context(g, config, lib_path=lib_path)
+    motion = config["grid"].get("motion", {})
+    if motion.get("enabled"):
+        # what RungeKutta's constructor wires for a moving grid (runge_kutta.cpp:58-70); the rigid-body driver
+        # hands every vertex the same velocity (rigid_body_translation.cpp:14-27)
+        v = motion["velocity"]
+        ctx.set_face_vertices(g.face_vertices, len(mesh.vertices))
+        ctx.set_cell_vertices(mesh.cell_types, mesh.cell_vertices)
+        ctx.set_vertex_positions(mesh.vertices)
+        ctx.set_vertex_velocities(np.tile([v["x"], v["y"], v["z"]], (len(mesh.vertices), 1)))
     try:
         out, rep = host.solve(ctx, config, prim0, fused_step=fused_step, host_lib=host_lib)
     finally:
