@@ -1,8 +1,9 @@
 """Shared parity cases: mesh + boundary conditions + configuration + seeded input state.
 
 Used by tests/golden/make_golden.py (which runs the real reference on them), by the CPU
-tests (oracle restatement and host emulation against the golden vectors) and by the GPU
-parity tests (CUDA path through the C ABI against the golden vectors and the oracle)."""
+tests (host emulation of the kernel bodies + the C-ABI layer against the golden vectors) and by
+the GPU parity tests (CUDA path through the C ABI against the golden vectors and, when it
+travelled to the box, against the compiled reference oracle/_ref itself)."""
 import numpy as np
 
 from ibis_b200 import config as cfg
