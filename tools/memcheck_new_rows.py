@@ -15,7 +15,27 @@ import parity  # noqa: E402
 from ibis_b200 import lib as libmod  # noqa: E402
 
 
+def hot():
+    """--hot: the headline kernels instead (k_bc, k_grad_sides, k_flux_tile, k_rk_update, reductions; dual gather path)"""
+    from ibis_b200 import config as cfg
+    parity.run_case("box3d_ausmdv")
+    mesh, config, g, prim = cases.build_case("box3d_regular")
+    ctx = libmod.Context(g, config)
+    fs, cq = ctx.fs_create(), ctx.cq_create()
+    ctx.fs_upload(fs, prim)
+    ctx.prim_to_cons(cq, fs)
+    tab = cfg.BUTCHER["ssp-rk3"]
+    dt = sys.float_info.max
+    for _ in range(2):
+        dt, _ = ctx.rk_step(fs, cq, tab["a"], tab["b"], 0.5, dt, 1.0)
+    assert ctx.count_bad_cells(fs) == 0
+    ctx.close()
+    print("memcheck walk (hot path) ok")
+
+
 def main():
+    if "--hot" in sys.argv:
+        return hot()
     for name in ("box3d_profile_cflux", "quad2d_cflux_viscous"):
         parity.run_case(name)
     for name in ("mixed3d_walls", "quad2d_cflux_viscous"):
