@@ -161,3 +161,33 @@ def test_native_su2_reader_quirks(tmp_path):
         f.write("NDIME= 3\nNPOIN= 5\n0 0 0\n1 0 0\n")
     with pytest.raises(IbisB200Error, match="truncated NPOIN"):
         libmod.read_su2(path, lib_path=L)
+
+
+def test_empty_and_single_cell_grids():
+    """edge sizes (host harness; not yet run on a GPU): an empty mesh builds, creates a context and evaluates
+    (nothing); one triangle closed by slip walls has three ghosts, area 1/2, and no mass flux through its walls"""
+    from ibis_b200 import config as cfg
+    L = emu_lib()
+    empty = su2.Su2Mesh(2, np.zeros((0, 3)), np.zeros(0, np.int32), np.zeros((0, 8), np.int64), {})
+    g = libmod.build_grid(empty, [], lib_path=L)
+    assert (g.n_cells, g.n_faces, g.n_ghost) == (0, 0, 0)
+    ctx = Context(g, cfg.make_config(2, {}), lib_path=L)
+    fs, dq = ctx.fs_create(), ctx.cq_create()
+    ctx.compute_dudt(fs, dq, True)
+    assert ctx.count_bad_cells(fs) == 0 and ctx.cq_download(dq).shape == (0, 4)
+    ctx.close()
+    tri = su2.Su2Mesh(2, np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0.0]]), np.array([su2.TRI], np.int32),
+                      np.array([[0, 1, 2, -1, -1, -1, -1, -1]]),
+                      {"w": (np.array([su2.LINE] * 3, np.int32), np.array([[0, 1, -1, -1], [1, 2, -1, -1], [2, 0, -1, -1]]))})
+    g = libmod.build_grid(tri, None, lib_path=L)
+    assert (g.n_cells, g.n_faces, g.n_ghost) == (1, 3, 3) and g.cell_volume[0] == 0.5
+    assert np.array_equal(np.sort(g.cell_neighbours), [1, 2, 3])
+    ctx = Context(g, cfg.make_config(2, {"w": cfg.slip_wall()}, flux_calculator="ausmdv"), lib_path=L)
+    fs, dq = ctx.fs_create(), ctx.cq_create()
+    ctx.fs_upload(fs, cases.uniform_state(g, 2, cases.FS2))
+    for allow in (True, False):
+        ctx.compute_dudt(fs, dq, allow)
+        d = ctx.cq_download(dq)[0]
+        assert abs(d[0]) < 1e-9 * 1.225 * 1000.0 / 0.5 and np.isfinite(d).all()
+    assert ctx.estimate_dt(fs) > 0
+    ctx.close()
