@@ -59,7 +59,7 @@ namespace ib {
         (c)->launches++;                                                                 \
     } while (0)
 
-static inline int nblocks(int64_t n, int bs) { return (int)((n + bs - 1) / bs); }
+static inline int nblocks(int64_t n, int bs) { return n > 0 ? (int)((n + bs - 1) / bs) : 1; }   // an empty grid launches one idle block
 
 void prof_begin(ibis_b200_ctx* c, int kind) {
     if (!c->prof_on) return;

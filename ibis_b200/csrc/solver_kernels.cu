@@ -18,7 +18,7 @@ namespace ib {
         (c)->launches++;                                                                 \
     } while (0)
 
-static inline int nblocks(int64_t n, int bs) { return (int)((n + bs - 1) / bs); }
+static inline int nblocks(int64_t n, int bs) { return n > 0 ? (int)((n + bs - 1) / bs) : 1; }   // an empty grid launches one idle block
 
 // grid for reductions: a fixed multiple of the 148 SMs, grid-stride loops
 int reduction_blocks(int64_t n) {
