@@ -1,0 +1,358 @@
+"""oracle/restatement.py -- TEST INFRASTRUCTURE, not product code.
+
+A plain-numpy restatement of the reference's inviscid residual, FiniteVolume<real>::compute_dudt
+(/root/reference/src/finite_volume/finite_volume/finite_volume.cpp:57-96), written from the reference's
+sources function by function (each block cites the file:line it follows) and independent of the product's
+kernel bodies.  It exists next to the compiled reference (oracle/_ref, the primary oracle) for two reasons:
+it travels as source, and it is a second, independently written statement of the same arithmetic.
+
+Pinned: tests/test_oracle_restatement.py holds it BIT FOR BIT to the golden vectors the compiled reference
+produced (tests/golden/*.npz: residual, ghost fill, every gradient and limiter) on every inviscid case of
+tests/cases.py it covers -- hexes, mixed cells, tets, quads, triangles; ausmdv / hanel / rusanov; limited and
+unlimited; rho_u / rho_p / rho_T; first and second order.  Every operation below is an individually rounded
+IEEE operation in the reference's association order (numpy does not contract to FMA), which is why equality is
+exact.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import this module.
+
+Covered: ghost-cell actions flow_state_copy, internal_copy, internal_copy_reflect_normal; WLS gradients;
+Barth-Jespersen / unlimited; MUSCL reconstruction with the three working thermo interpolators; the ausmdv,
+hanel and rusanov flux calculators; the surface integral.  Not covered (use oracle/_ref): viscous terms, ldfss2,
+subsonic / profile boundary actions, dual numbers.
+"""
+import numpy as np
+
+R_AIR = 287.0
+
+
+def _min(a, b):
+    """Ibis::min -> Kokkos::min(a, b) = (b < a) ? b : a   (util/real.h:15-65)"""
+    return np.where(b < a, b, a)
+
+
+def _max(a, b):
+    """Kokkos::max(a, b) = (a < b) ? b : a"""
+    return np.where(a < b, b, a)
+
+
+class _Ragged:
+    """cell -> (faces, neighbours, outsigns) in cell-face order, as padded (n_cells, max_faces) tables + mask"""
+
+    def __init__(self, g):
+        off = np.asarray(g.cell_face_offsets, np.int64)
+        n = len(off) - 1
+        cnt = np.diff(off)
+        self.maxf = int(cnt.max()) if n else 0
+        slot = np.arange(self.maxf)[None, :]
+        self.mask = slot < cnt[:, None]
+        idx = np.where(self.mask, off[:-1, None] + slot, 0)
+        self.face = np.where(self.mask, np.asarray(g.cell_face_ids, np.int64)[idx], 0)
+        self.nbr = np.where(self.mask, np.asarray(g.cell_neighbours, np.int64)[idx], 0)
+        self.out = np.where(self.mask, np.asarray(g.cell_outsigns, np.int64)[idx], 0)
+
+
+def apply_pre_reconstruction(g, config, prim):
+    """finite_volume.cpp:187-199: tags in alphabetical order, actions in list order (boundary.cpp:517-543)"""
+    fs = prim
+    n = g.n_cells
+    left, right = np.asarray(g.face_left), np.asarray(g.face_right)
+    for tag in sorted(g.tags):
+        faces = np.asarray(g.tags[tag]["faces"], np.int64)
+        l, r = left[faces], right[faces]
+        ghost = np.where(l < n, r, l)
+        valid = np.where(l < n, l, r)
+        for act in config["grid"]["boundaries"][tag]["pre_reconstruction"]:
+            kind = act["type"]
+            if kind == "flow_state_copy":                        # boundary.cpp:15-45
+                s = act["flow_state"]
+                fs[ghost] = [s["rho"], s["p"], s["T"], s["energy"], s["vx"], s["vy"], s["vz"]]
+            elif kind == "internal_copy":                        # boundary.cpp:100-136
+                fs[ghost] = fs[valid]
+            elif kind == "internal_copy_reflect_normal":         # boundary.cpp:139-206
+                fs[ghost, :4] = fs[valid, :4]
+                x, y, z = fs[valid, 4], fs[valid, 5], fs[valid, 6]
+                nrm, t1, t2 = g.face_norm[faces], g.face_tan1[faces], g.face_tan2[faces]
+                xs = -(x * nrm[:, 0] + y * nrm[:, 1] + z * nrm[:, 2])
+                ys = x * t1[:, 0] + y * t1[:, 1] + z * t1[:, 2]
+                zs = x * t2[:, 0] + y * t2[:, 1] + z * t2[:, 2]
+                fs[ghost, 4] = xs * nrm[:, 0] + ys * t1[:, 0] + zs * t2[:, 0]
+                fs[ghost, 5] = xs * nrm[:, 1] + ys * t1[:, 1] + zs * t2[:, 1]
+                fs[ghost, 6] = xs * nrm[:, 2] + ys * t1[:, 2] + zs * t2[:, 2]
+            else:
+                raise NotImplementedError(f"boundary action {kind}: use the compiled reference (oracle/_ref)")
+    return fs
+
+
+def wls_r(g, rag):
+    """WLSGradient::compute_weights (grid/gradient.h:119-162) -> r11 r12 r22 r13 r23 r33"""
+    n = g.n_cells
+    c = np.asarray(g.cell_centroid)
+    s = [np.zeros(n) for _ in range(6)]
+    for j in range(rag.maxf):
+        m, nb = rag.mask[:, j], rag.nbr[:, j]
+        dx, dy, dz = c[nb, 0] - c[:n, 0], c[nb, 1] - c[:n, 1], c[nb, 2] - c[:n, 2]
+        for k, t in enumerate((dx * dx, dx * dy, dx * dz, dy * dy, dy * dz, dz * dz)):
+            s[k] = np.where(m, s[k] + t, s[k])
+    sxx, sxy, sxz, syy, syz, szz = s
+    with np.errstate(all="ignore"):
+        r11 = np.sqrt(sxx)
+        r12 = 1.0 / r11 * sxy
+        r22 = np.sqrt(syy - r12 * r12)
+        r13 = 1.0 / r11 * sxz
+        r23 = 1.0 / r22 * (syz - r12 / r11 * sxz)
+        r33 = np.sqrt(szz - (r13 * r13 + r23 * r23))
+    if g.dim == 2:                                               # gradient.h:156-160: only stored in 3-D
+        r13, r23, r33 = np.zeros(n), np.zeros(n), np.zeros(n)
+    return r11, r12, r22, r13, r23, r33
+
+
+def wls_gradient(g, rag, r, values):
+    """WLSGradient::compute_gradients (grid/gradient.h:66-116)"""
+    n = g.n_cells
+    c = np.asarray(g.cell_centroid)
+    r11, r12, r22, r13, r23, r33 = r
+    gx, gy, gz = np.zeros(n), np.zeros(n), np.zeros(n)
+    with np.errstate(all="ignore"):
+        beta = (r12 * r23 - r13 * r23) / (r11 * r22)
+        for j in range(rag.maxf):
+            m, nb = rag.mask[:, j], rag.nbr[:, j]
+            diff_u = values[nb] - values[:n]
+            dx, dy, dz = c[nb, 0] - c[:n, 0], c[nb, 1] - c[:n, 1], c[nb, 2] - c[:n, 2]
+            alpha_1 = dx / (r11 * r11)
+            alpha_2 = 1.0 / (r22 * r22) * (dy - r12 / r11 * dx)
+            alpha_3 = np.zeros(n)
+            if g.dim == 3:
+                alpha_3 = 1.0 / (r33 * r33) * (dz - r23 / r22 * dy + beta * dx)
+            w_1 = alpha_1 - r12 / r11 * alpha_2 + beta * alpha_3
+            w_2 = alpha_2 - r23 / r22 * alpha_3
+            w_3 = alpha_3
+            gx = np.where(m, gx + w_1 * diff_u, gx)
+            gy = np.where(m, gy + w_2 * diff_u, gy)
+            gz = np.where(m, gz + w_3 * diff_u, gz)
+    return np.stack([gx, gy, gz], axis=1)
+
+
+def barth_jespersen(g, rag, values, grad, epsilon):
+    """BarthJespersen::calculate_limiters (finite_volume/limiter.cpp:24-63)"""
+    n = g.n_cells
+    ui = values[:n]
+    umin, umax = ui.copy(), ui.copy()
+    for j in range(rag.maxf):
+        m, un = rag.mask[:, j], values[rag.nbr[:, j]]
+        umin = np.where(m, _min(umin, un), umin)
+        umax = np.where(m, _max(umax, un), umax)
+    phi = np.ones(n)
+    c, fc = np.asarray(g.cell_centroid), np.asarray(g.face_centre)
+    with np.errstate(all="ignore"):
+        for j in range(rag.maxf):
+            m, f = rag.mask[:, j], rag.face[:, j]
+            dx, dy, dz = fc[f, 0] - c[:n, 0], fc[f, 1] - c[:n, 1], fc[f, 2] - c[:n, 2]
+            d2 = grad[:, 0] * dx + grad[:, 1] * dy + grad[:, 2] * dz
+            sign = (d2 > 0).astype(np.int64) - (d2 < 0).astype(np.int64)
+            d2 = sign * (np.abs(d2) + epsilon)
+            pos = _min(phi, (umax - ui) / d2)
+            neg = _min(phi, (umin - ui) / d2)
+            phi = np.where(m & (sign > 0), pos, np.where(m & (sign < 0), neg, phi))
+    return phi
+
+
+def _thermo_close(kind, rho, th2, R, Cv):
+    """update_thermo_from_rhop / rhou / rhoT on the interface states (gas/gas_model.h:91-117) -> p, T, e"""
+    if kind == "rho_p":
+        p = th2
+        T = p / (rho * R)
+        return p, T, Cv * T
+    if kind == "rho_u":
+        e = th2
+        T = e / Cv
+        return rho * R * T, T, e
+    if kind == "rho_T":
+        T = th2
+        return rho * R * T, T, Cv * T
+    raise NotImplementedError("thermo_interpolator p_T is broken upstream (convective_flux.cpp:53-55)")
+
+
+def reconstruct(g, config, fs, rag, want):
+    """copy_reconstruct (convective_flux.cpp:212-240) or linear_reconstruct (:258-420) -> left, right states
+    (rho p T e vx vy vz per interface) and the gradients / limiters by name"""
+    n = g.n_cells
+    cf = config["convective_flux"]
+    gm = config["gas_model"]
+    left, right = np.asarray(g.face_left), np.asarray(g.face_right)
+    if not want:
+        return fs[left].copy(), fs[right].copy(), {}
+    kind = cf["thermo_interpolator"]
+    col2, name2 = {"rho_p": (1, "p"), "rho_u": (3, "u"), "rho_T": (2, "T")}[kind]
+    r = wls_r(g, rag)
+    # compute_convective_gradient (:181-209): thermo pair, then vx, vy and (3-D only) vz
+    var_cols = [("rho", 0), (name2, col2), ("vx", 4), ("vy", 5), ("vz", 6)]
+    inter = {}
+    grads, lims = {}, {}
+    limited = cf["limiter"]["type"] == "barth_jespersen"
+    for name, col in var_cols:
+        if name == "vz" and g.dim == 2:
+            grads[name] = np.zeros((n, 3))                       # never computed in 2-D: the Views stay zero
+        else:
+            grads[name] = wls_gradient(g, rag, r, fs[:, col])
+        inter["grad_" + name] = grads[name]
+        if limited:                                              # compute_limiters (:423-462)
+            lims[name] = barth_jespersen(g, rag, fs[:, col], grads[name], float(cf["limiter"].get("epsilon", 1e-25)))
+            inter["lim_" + name] = lims[name]
+    c, fc = np.asarray(g.cell_centroid), np.asarray(g.face_centre)
+    sides = []
+    for cell in (left, right):
+        valid = cell < n
+        safe = np.where(valid, cell, 0)
+        dx, dy, dz = fc[:, 0] - c[cell, 0], fc[:, 1] - c[cell, 1], fc[:, 2] - c[cell, 2]
+
+        def interp(name, col):                                   # linear_interpolate (:243-255)
+            gr = np.where(valid[:, None], grads[name][safe], 0.0)
+            lim = np.where(valid, lims[name][safe], 1.0) if limited else np.ones(len(cell))
+            return fs[cell, col] + lim * (gr[:, 0] * dx + gr[:, 1] * dy + gr[:, 2] * dz)
+
+        rho = interp("rho", 0)
+        th2 = interp(name2, col2)
+        p, T, e = _thermo_close(kind, rho, th2, float(gm["R"]), float(gm["Cv"]))
+        sides.append(np.stack([rho, p, T, e, interp("vx", 4), interp("vy", 5), interp("vz", 6)], axis=1))
+    return sides[0], sides[1], inter
+
+
+def _to_local(v, nrm, t1, t2):
+    """transform_to_local_frame (util/vector3.cpp:142-153)"""
+    x = v[:, 0] * nrm[:, 0] + v[:, 1] * nrm[:, 1] + v[:, 2] * nrm[:, 2]
+    y = v[:, 0] * t1[:, 0] + v[:, 1] * t1[:, 1] + v[:, 2] * t1[:, 2]
+    z = v[:, 0] * t2[:, 0] + v[:, 1] * t2[:, 1] + v[:, 2] * t2[:, 2]
+    return x, y, z
+
+
+def _unpack(s, vel, gm):
+    rho, p, T = s[:, 0], s[:, 1], s[:, 2]
+    u, v, w = vel
+    e = float(gm["Cv"]) * T                                      # gm.internal_energy (gas_model.h:164-170)
+    a = np.sqrt(float(gm["gamma"]) * float(gm["R"]) * T)         # speed_of_sound_ (gas_model.h:27-31)
+    ke = 0.5 * (u * u + v * v + w * w)
+    return rho, p, u, v, w, e, a, ke
+
+
+def flux_ausmdv(L, R_, vl, vr, gm, three_d):
+    """Ausmdv::compute_flux (flux_calculators/ausmdv.cpp:8-132) -> mass, mx, my, mz, energy"""
+    rL, pL, uL, vL, wL, eL, aL, keL = _unpack(L, vl, gm)
+    rR, pR, uR, vR, wR, eR, aR, keR = _unpack(R_, vr, gm)
+    pLrL, pRrR = pL / rL, pR / rR
+    HL, HR = eL + pLrL + keL, eR + pRrR + keR
+    alphaL = 2.0 * pLrL / (pLrL + pRrR)
+    alphaR = 2.0 * pRrR / (pLrL + pRrR)
+    am = _max(aL, aR)
+    ML, MR = uL / am, uR / am
+    duL = 0.5 * (uL + np.abs(uL))
+    subL = np.abs(ML) <= 1.0
+    pLplus = np.where(subL, pL * (ML + 1.0) * (ML + 1.0) * (2.0 - ML) * 0.25, pL * duL / uL)
+    uLplus = np.where(subL, alphaL * ((uL + am) * (uL + am) / (4.0 * am) - duL) + duL, duL)
+    duR = 0.5 * (uR - np.abs(uR))
+    subR = np.abs(MR) <= 1.0
+    pRminus = np.where(subR, pR * (MR - 1.0) * (MR - 1.0) * (2.0 + MR) * 0.25, pR * duR / uR)
+    uRminus = np.where(subR, alphaR * (-(uR - am) * (uR - am) / (4.0 * am) - duR) + duR, duR)
+    ru_half = uLplus * rL + uRminus * rR
+    p_half = pLplus + pRminus
+    dp = pL - pR
+    dp = 10.0 * np.abs(dp) / _min(pL, pR)
+    s = 0.5 * _min(np.ones_like(dp), dp)
+    ru2_AUSMV = uLplus * rL * uL + uRminus * rR * uR
+    ru2_AUSMD = 0.5 * (ru_half * (uL + uR) - np.abs(ru_half) * (uR - uL))
+    ru2_half = (0.5 + s) * ru2_AUSMV + (0.5 - s) * ru2_AUSMD
+    fromL = ru_half >= 0.0
+    mass = ru_half.copy()
+    mx = ru2_half + p_half
+    my = np.where(fromL, ru_half * vL, ru_half * vR)
+    mz = np.where(fromL, ru_half * wL, ru_half * wR)
+    en = np.where(fromL, ru_half * HL, ru_half * HR)
+    caseA = ((uL - aL) < 0.0) & ((uR - aR) > 0.0)
+    caseB = ((uL + aL) < 0.0) & ((uR + aR) > 0.0)
+    d_ua = np.zeros_like(mass)
+    d_ua = np.where(caseA & ~caseB, 0.125 * ((uR - aR) - (uL - aL)), d_ua)
+    d_ua = np.where(caseB & ~caseA, 0.125 * ((uR + aR) - (uL + aL)), d_ua)
+    fix = d_ua != 0.0
+    mass = np.where(fix, mass - d_ua * (rR - rL), mass)
+    mx = np.where(fix, mx - d_ua * (rR * uR - rL * uL), mx)
+    my = np.where(fix, my - d_ua * (rR * vR - rL * vL), my)
+    mz = np.where(fix, mz - d_ua * (rR * wR - rL * wL), mz)
+    en = np.where(fix, en - d_ua * (rR * HR - rL * HL), en)
+    return mass, mx, my, (mz if three_d else np.zeros_like(mz)), en
+
+
+def flux_hanel(L, R_, vl, vr, gm, three_d):
+    """Hanel::compute_flux (flux_calculators/hanel.cpp:7-65)"""
+    rL, pL, uL, vL, wL, eL, aL, keL = _unpack(L, vl, gm)
+    rR, pR, uR, vR, wR, eR, aR, keR = _unpack(R_, vr, gm)
+    HL, HR = eL + pL / rL + keL, eR + pR / rR + keR
+    subL = np.abs(uL) <= aL
+    uLplus = np.where(subL, 1.0 / (4.0 * aL) * (uL + aL) * (uL + aL), 0.5 * (uL + np.abs(uL)))
+    pLplus = np.where(subL, pL * uLplus * (1.0 / aL * (2.0 - uL / aL)), pL * uLplus * (1.0 / uL))
+    subR = np.abs(uR) <= aR
+    uRminus = np.where(subR, -1.0 / (4.0 * aR) * (uR - aR) * (uR - aR), 0.5 * (uR - np.abs(uR)))
+    pRminus = np.where(subR, pR * uRminus * (1.0 / aR * (-2.0 - uR / aR)), pR * uRminus * (1.0 / uR))
+    p_half = pLplus + pRminus
+    mass = uLplus * rL + uRminus * rR
+    mx = uLplus * rL * uL + uRminus * rR * uR + p_half
+    my = uLplus * rL * vL + uRminus * rR * vR
+    mz = uLplus * rL * wL + uRminus * rR * wR
+    en = uLplus * rL * HL + uRminus * rR * HR
+    return mass, mx, my, (mz if three_d else np.zeros_like(mz)), en
+
+
+def flux_rusanov(L, R_, vl, vr, gm, three_d):
+    """Rusanov::compute_flux (flux_calculators/rusanov.cpp:8-53)"""
+    rL, pL, uL, vL, wL, eL, aL, keL = _unpack(L, vl, gm)
+    rR, pR, uR, vR, wR, eR, aR, keR = _unpack(R_, vr, gm)
+    ruL, ruR = rL * uL, rR * uR
+    HL, HR = eL + pL / rL + keL, eR + pR / rR + keR
+    S = _max(np.abs(uL - aL), np.abs(uR - aR))
+    S = _max(S, np.abs(uL + aL))
+    S = _max(S, np.abs(uR + aR))
+    mass = 0.5 * (ruL + ruR) - 0.5 * S * (rR - rL)
+    mx = 0.5 * (ruL * uL + pL + ruR * uR + pR) - 0.5 * S * (rR * uR - rL * uL)
+    my = 0.5 * (ruL * vL + ruR * vR) - 0.5 * S * (rR * vR - rL * vL)
+    mz = 0.5 * (ruL * wL + ruR * wR) - 0.5 * S * (rR * wR - rL * wL)
+    en = 0.5 * (ruL * HL + ruR * HR) - 0.5 * S * (rR * HR - rL * HL)
+    return mass, mx, my, (mz if three_d else np.zeros_like(mz)), en
+
+
+FLUX = {"ausmdv": flux_ausmdv, "hanel": flux_hanel, "rusanov": flux_rusanov}
+
+
+def compute_dudt(g, config, prim, allow_reconstruction=True):
+    """FiniteVolume<real>::compute_dudt (finite_volume.cpp:57-96), inviscid, static grid.
+    prim: (n_cells + n_ghost, 7) rho p T e vx vy vz.  -> dudt (n_cells, dim + 2), prim after the ghost fill,
+    dict of intermediates (grad_* (n_cells, 3), lim_* (n_cells,))."""
+    if config["viscous_flux"]["enabled"]:
+        raise NotImplementedError("viscous terms: use the compiled reference (oracle/_ref)")
+    cf = config["convective_flux"]
+    if cf["flux_calculator"]["type"] not in FLUX:
+        raise NotImplementedError("flux calculator " + cf["flux_calculator"]["type"])
+    for b in config["grid"]["boundaries"].values():
+        if b.get("post_convective_flux"):
+            raise NotImplementedError("flux actions: use the compiled reference (oracle/_ref)")
+    fs = apply_pre_reconstruction(g, config, np.array(prim, dtype=np.float64))
+    rag = _Ragged(g)
+    order2 = allow_reconstruction and int(cf["reconstruction_order"]) == 2
+    with np.errstate(all="ignore"):
+        L, R_, inter = reconstruct(g, config, fs, rag, order2)
+        nrm, t1, t2 = np.asarray(g.face_norm), np.asarray(g.face_tan1), np.asarray(g.face_tan2)
+        vl, vr = _to_local(L[:, 4:7], nrm, t1, t2), _to_local(R_[:, 4:7], nrm, t1, t2)        # convective_flux.cpp:110-113
+        three_d = g.dim == 3
+        mass, px, py, pz, en = FLUX[cf["flux_calculator"]["type"]](L, R_, vl, vr, config["gas_model"], three_d)
+        # flux::transform_to_global (convective_flux.cpp:148-164)
+        mx = px * nrm[:, 0] + py * t1[:, 0] + pz * t2[:, 0]
+        my = px * nrm[:, 1] + py * t1[:, 1] + pz * t2[:, 1]
+        mz = px * nrm[:, 2] + py * t1[:, 2] + pz * t2[:, 2]
+        comps = [mass, mx, my] + ([mz] if three_d else []) + [en]
+        # flux_surface_integral (finite_volume.cpp:221-256): in cell-face order
+        n = g.n_cells
+        acc = [np.zeros(n) for _ in comps]
+        area_all = np.asarray(g.face_area)
+        for j in range(rag.maxf):
+            m, f = rag.mask[:, j], rag.face[:, j]
+            area = -area_all[f] * rag.out[:, j]
+            for k, comp in enumerate(comps):
+                acc[k] = np.where(m, acc[k] + comp[f] * area, acc[k])
+        vol = np.asarray(g.cell_volume)
+        dudt = np.stack([a / vol for a in acc], axis=1)
+    return dudt, fs, inter
