@@ -8,15 +8,15 @@ it travels as source, and it is a second, independently written statement of the
 
 Pinned: tests/test_oracle_restatement.py holds it BIT FOR BIT to the golden vectors the compiled reference
 produced (tests/golden/*.npz: residual, ghost fill, every gradient and limiter) on every inviscid case of
-tests/cases.py it covers -- hexes, mixed cells, tets, quads, triangles; ausmdv / hanel / rusanov; limited and
-unlimited; rho_u / rho_p / rho_T; first and second order.  Every operation below is an individually rounded
+tests/cases.py it covers -- hexes, mixed cells, tets, quads, triangles; ausmdv / hanel / rusanov / ldfss2; limited
+and unlimited; rho_u / rho_p / rho_T; supersonic and subsonic boundaries; first and second order.  Every operation below is an individually rounded
 IEEE operation in the reference's association order (numpy does not contract to FMA), which is why equality is
 exact.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import this module.
 
-Covered: ghost-cell actions flow_state_copy, internal_copy, internal_copy_reflect_normal; WLS gradients;
-Barth-Jespersen / unlimited; MUSCL reconstruction with the three working thermo interpolators; the ausmdv,
-hanel and rusanov flux calculators; the surface integral.  Not covered (use oracle/_ref): viscous terms, ldfss2,
-subsonic / profile boundary actions, dual numbers.
+Covered: ghost-cell actions flow_state_copy, internal_copy, internal_copy_reflect_normal, subsonic_inflow,
+subsonic_outflow; WLS gradients; Barth-Jespersen / unlimited; MUSCL reconstruction with the three working thermo
+interpolators; the ausmdv, hanel, rusanov and ldfss2 flux calculators; the surface integral.  Not covered (use
+oracle/_ref): viscous terms, the profile / flux boundary actions, moving grids, dual numbers.
 """
 import numpy as np
 
@@ -76,6 +76,33 @@ def apply_pre_reconstruction(g, config, prim):
                 fs[ghost, 4] = xs * nrm[:, 0] + ys * t1[:, 0] + zs * t2[:, 0]
                 fs[ghost, 5] = xs * nrm[:, 1] + ys * t1[:, 1] + zs * t2[:, 1]
                 fs[ghost, 6] = xs * nrm[:, 2] + ys * t1[:, 2] + zs * t2[:, 2]
+            elif kind in ("subsonic_inflow", "subsonic_outflow"):  # boundary.cpp:279-342, 345-400
+                gm = config["gas_model"]
+                nrm = g.face_norm[faces]
+                nx, ny, nz = nrm[:, 0], nrm[:, 1], nrm[:, 2]
+                a = np.sqrt(float(gm["gamma"]) * float(gm["R"]) * fs[valid, 2])
+                rho_ref, p_v = fs[valid, 0], fs[valid, 1]
+                vx, vy, vz = fs[valid, 4], fs[valid, 5], fs[valid, 6]
+                if kind == "subsonic_inflow":
+                    s = act["flow_state"]
+                    vel_correct = nx * (s["vx"] - vx) + ny * (s["vy"] - vy) + nz * (s["vz"] - vz)
+                    p_in = s["p"]
+                    p_face = 0.5 * (p_in + p_v - rho_ref * a * vel_correct)
+                    rho_face = s["rho"] + (p_face - p_in) / a / a
+                    vx_face = s["vx"] - nx * (p_in - p_face) / (rho_ref * a)
+                    vy_face = s["vy"] - ny * (p_in - p_face) / (rho_ref * a)
+                    vz_face = s["vz"] - nz * (p_in - p_face) / (rho_ref * a)
+                else:
+                    p_face = float(act["pressure"])
+                    rho_face = rho_ref + (p_face - p_v) / a / a
+                    vx_face = vx + nx * (p_v - p_face) / (rho_ref * a)
+                    vy_face = vy + ny * (p_v - p_face) / (rho_ref * a)
+                    vz_face = vz + nz * (p_v - p_face) / (rho_ref * a)
+                pg = 2.0 * p_face - p_v
+                rg = 2.0 * rho_face - rho_ref
+                Tg = pg / (rg * float(gm["R"]))                  # update_thermo_from_rhop (gas_model.h:105-110)
+                fs[ghost, 1], fs[ghost, 0], fs[ghost, 2], fs[ghost, 3] = pg, rg, Tg, float(gm["Cv"]) * Tg
+                fs[ghost, 4], fs[ghost, 5], fs[ghost, 6] = 2.0 * vx_face - vx, 2.0 * vy_face - vy, 2.0 * vz_face - vz
             else:
                 raise NotImplementedError(f"boundary action {kind}: use the compiled reference (oracle/_ref)")
     return fs
@@ -315,7 +342,40 @@ def flux_rusanov(L, R_, vl, vr, gm, three_d):
     return mass, mx, my, (mz if three_d else np.zeros_like(mz)), en
 
 
-FLUX = {"ausmdv": flux_ausmdv, "hanel": flux_hanel, "rusanov": flux_rusanov}
+def flux_ldfss2(L, R_, vl, vr, gm, three_d, delta=2.0):
+    """Ldfss2::compute_flux (flux_calculators/ldfss2.cpp:9-90)"""
+    rL, pL, uL, vL, wL, eL, aL, keL = _unpack(L, vl, gm)
+    rR, pR, uR, vR, wR, eR, aR, keR = _unpack(R_, vr, gm)
+    HL, HR = eL + pL / rL + keL, eR + pR / rR + keR
+    am = 0.5 * (aL + aR)
+    ML, MR = uL / am, uR / am
+    MpL = 0.25 * (ML + 1.0) * (ML + 1.0)
+    MmR = -0.25 * (MR - 1.0) * (MR - 1.0)
+    alphaL = 0.5 * (1.0 + np.copysign(1.0, ML))
+    alphaR = 0.5 * (1.0 - np.copysign(1.0, MR))
+    zero = np.zeros_like(ML)
+    betaL = -_max(zero, 1.0 - np.floor(np.abs(ML)))
+    betaR = -_max(zero, 1.0 - np.floor(np.abs(MR)))
+    PL = 0.25 * (ML + 1.0) * (ML + 1.0) * (2.0 - ML)
+    PR = 0.25 * (MR - 1.0) * (MR - 1.0) * (2.0 + MR)
+    DL = alphaL * (1.0 + betaL) - betaL * PL
+    DR = alphaR * (1.0 + betaR) - betaR * PR
+    Mhalf = 0.25 * betaL * betaR * np.power(np.sqrt(0.5 * (ML * ML + MR * MR)) - 1.0, 2.0)
+    MhalfL = Mhalf * (1.0 - ((pL - pR) / (pL + pR) + delta * (np.abs(pL - pR) / pL)))
+    MhalfR = Mhalf * (1.0 + ((pL - pR) / (pL + pR) - delta * (np.abs(pL - pR) / pR)))
+    CL = alphaL * (1.0 + betaL) * ML - betaL * MpL - MhalfL
+    CR = alphaR * (1.0 + betaR) * MR - betaR * MmR + MhalfR
+    mass = am * rL * CL + am * rR * CR
+    ru2_half = am * rL * CL * uL + am * rR * CR * uR
+    p_half = DL * pL + DR * pR
+    mx = ru2_half + p_half
+    my = am * rL * CL * vL + am * rR * CR * vR
+    mz = am * rL * CL * wL + am * rR * CR * wR
+    en = am * rL * CL * HL + am * rR * CR * HR
+    return mass, mx, my, (mz if three_d else np.zeros_like(mz)), en
+
+
+FLUX = {"ausmdv": flux_ausmdv, "hanel": flux_hanel, "rusanov": flux_rusanov, "ldfss2": flux_ldfss2}
 
 
 def compute_dudt(g, config, prim, allow_reconstruction=True):
@@ -338,7 +398,9 @@ def compute_dudt(g, config, prim, allow_reconstruction=True):
         nrm, t1, t2 = np.asarray(g.face_norm), np.asarray(g.face_tan1), np.asarray(g.face_tan2)
         vl, vr = _to_local(L[:, 4:7], nrm, t1, t2), _to_local(R_[:, 4:7], nrm, t1, t2)        # convective_flux.cpp:110-113
         three_d = g.dim == 3
-        mass, px, py, pz, en = FLUX[cf["flux_calculator"]["type"]](L, R_, vl, vr, config["gas_model"], three_d)
+        fc = cf["flux_calculator"]
+        extra = {"delta": float(fc.get("delta", 2.0))} if fc["type"] == "ldfss2" else {}
+        mass, px, py, pz, en = FLUX[fc["type"]](L, R_, vl, vr, config["gas_model"], three_d, **extra)
         # flux::transform_to_global (convective_flux.cpp:148-164)
         mx = px * nrm[:, 0] + py * t1[:, 0] + pz * t2[:, 0]
         my = px * nrm[:, 1] + py * t1[:, 1] + pz * t2[:, 1]

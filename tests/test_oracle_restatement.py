@@ -17,13 +17,15 @@ import restatement  # noqa: E402
 
 COVERED = sorted(n for n, (_, bcs_f, _, kw) in cases.CASES.items()
                  if not kw.get("viscous") and kw.get("flux_calculator", "hanel") in restatement.FLUX
-                 and all(a["type"] in ("flow_state_copy", "internal_copy", "internal_copy_reflect_normal")
+                 and all(a["type"] in ("flow_state_copy", "internal_copy", "internal_copy_reflect_normal",
+                                       "subsonic_inflow", "subsonic_outflow")
                          for b in bcs_f().values() for a in b["pre_reconstruction"])
                  and not any(b["post_convective_flux"] for b in bcs_f().values()))
 
 
 def test_coverage_is_what_the_header_says():
-    assert len(COVERED) >= 14 and {"box3d_ausmdv", "box3d_hanel", "box3d_rusanov", "quad2d_ausmdv", "mixed3d_walls",
+    assert len(COVERED) >= 19 and {"box3d_ausmdv", "box3d_hanel", "box3d_rusanov", "box3d_ldfss2", "quad2d_ldfss2",
+                                    "quad2d_subsonic_bcs", "quad2d_ausmdv", "mixed3d_walls",
                                     "tet3d", "tri2d", "wedge2d", "box3d_rho_p", "box3d_rho_T", "box3d_unlimited",
                                     "box3d_order1"} <= set(COVERED)
 
