@@ -14,9 +14,10 @@ IEEE operation in the reference's association order (numpy does not contract to 
 exact.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import this module.
 
 Covered: ghost-cell actions flow_state_copy, internal_copy, internal_copy_reflect_normal, subsonic_inflow,
-subsonic_outflow; WLS gradients; Barth-Jespersen / unlimited; MUSCL reconstruction with the three working thermo
+subsonic_outflow, boundary_layer_profile (with CubicSpline); the constant_flux flux action; estimate_dt,
+count_bad_cells, L2 norms, primitive <-> conserved; WLS gradients; Barth-Jespersen / unlimited; MUSCL reconstruction with the three working thermo
 interpolators; the ausmdv, hanel, rusanov and ldfss2 flux calculators; the surface integral.  Not covered (use
-oracle/_ref): viscous terms, the profile / flux boundary actions, moving grids, dual numbers.
+oracle/_ref): viscous terms, moving grids, dual numbers.
 """
 import numpy as np
 
@@ -49,6 +50,57 @@ class _Ragged:
         self.out = np.where(self.mask, np.asarray(g.cell_outsigns, np.int64)[idx], 0)
 
 
+class CubicSpline:
+    """util/cubic_spline.cpp:9-89 (constructor: assembly + Thomas sweep for the interior second derivatives) and
+    util/cubic_spline.h:14-45 (eval).  The reference stores y'' in an array of n - 2 entries but indexes it by
+    knot, i.e. it reads past the end in the last two intervals; here y'' holds the n values those formulas
+    address (natural spline) -- identical wherever the reference is defined."""
+
+    def __init__(self, x, y):
+        x, y = [float(v) for v in x], [float(v) for v in y]
+        n = len(x)
+        if n < 4:
+            raise ValueError("Insufficient points for cubic spline")
+        if len(y) != n:
+            raise ValueError("Cubic spline has different number of x and y points")
+        ne = n - 2
+        diag, upper, rhs = [0.0] * ne, [0.0] * ne, [0.0] * ne
+        for i in range(ne + 1):
+            dxi, dyi = x[i + 1] - x[i], y[i + 1] - y[i]
+            if i != ne:
+                diag[i] += dxi
+                rhs[i] -= dyi / dxi
+            if i == 0:
+                continue
+            rhs[i - 1] += dyi / dxi
+            diag[i - 1] += dxi
+            upper[i - 1] += dxi
+        rhs = [v * 6 for v in rhs]
+        diag = [v * 2 for v in diag]
+        for i in range(1, ne):
+            w = upper[i - 1] / diag[i - 1]
+            diag[i] = diag[i] - w * upper[i - 1]
+            rhs[i] = rhs[i] - w * rhs[i - 1]
+        ydd = [0.0] * n
+        ydd[n - 2] = rhs[ne - 1] / diag[ne - 1]
+        for i in range(ne - 2, -1, -1):
+            ydd[i + 1] = (rhs[i] - upper[i] * ydd[i + 2]) / diag[i]
+        self.x, self.y, self.ydd = x, y, ydd
+
+    def eval(self, q):
+        x, y, ydd = self.x, self.y, self.ydd
+        if q <= x[0]:
+            return y[0]
+        if q >= x[-1]:
+            return y[-1]
+        idx = next(i for i in range(len(x)) if x[i] >= q) - 1
+        dx_plus, dx_minus, delta = x[idx + 1] - q, q - x[idx], x[idx + 1] - x[idx]
+        a = (ydd[idx] * dx_plus * dx_plus * dx_plus + ydd[idx + 1] * dx_minus * dx_minus * dx_minus) / (6 * delta)
+        b = (y[idx] / delta - ydd[idx] * delta / 6) * dx_plus
+        c = (y[idx + 1] / delta - ydd[idx + 1] * delta / 6) * dx_minus
+        return a + b + c
+
+
 def apply_pre_reconstruction(g, config, prim):
     """finite_volume.cpp:187-199: tags in alphabetical order, actions in list order (boundary.cpp:517-543)"""
     fs = prim
@@ -76,6 +128,18 @@ def apply_pre_reconstruction(g, config, prim):
                 fs[ghost, 4] = xs * nrm[:, 0] + ys * t1[:, 0] + zs * t2[:, 0]
                 fs[ghost, 5] = xs * nrm[:, 1] + ys * t1[:, 1] + zs * t2[:, 1]
                 fs[ghost, 6] = xs * nrm[:, 2] + ys * t1[:, 2] + zs * t2[:, 2]
+            elif kind == "boundary_layer_profile":               # boundary.cpp:51-95
+                prof = act["profile"]
+                gm = config["gas_model"]
+                vs, Ts = CubicSpline(prof["height"], prof["v"]), CubicSpline(prof["height"], prof["T"])
+                pos = np.asarray(g.cell_centroid)[ghost, 1]
+                T = np.array([Ts.eval(float(q)) for q in pos])
+                p = float(prof["p"])
+                fs[ghost, 1], fs[ghost, 2] = p, T
+                fs[ghost, 0] = p / (float(gm["R"]) * T)          # update_thermo_from_pT (gas_model.h:91-96)
+                fs[ghost, 3] = float(gm["Cv"]) * T
+                fs[ghost, 4] = [vs.eval(float(q)) for q in pos]
+                fs[ghost, 5], fs[ghost, 6] = 0.0, 0.0
             elif kind in ("subsonic_inflow", "subsonic_outflow"):  # boundary.cpp:279-342, 345-400
                 gm = config["gas_model"]
                 nrm = g.face_norm[faces]
@@ -387,9 +451,6 @@ def compute_dudt(g, config, prim, allow_reconstruction=True):
     cf = config["convective_flux"]
     if cf["flux_calculator"]["type"] not in FLUX:
         raise NotImplementedError("flux calculator " + cf["flux_calculator"]["type"])
-    for b in config["grid"]["boundaries"].values():
-        if b.get("post_convective_flux"):
-            raise NotImplementedError("flux actions: use the compiled reference (oracle/_ref)")
     fs = apply_pre_reconstruction(g, config, np.array(prim, dtype=np.float64))
     rag = _Ragged(g)
     order2 = allow_reconstruction and int(cf["reconstruction_order"]) == 2
@@ -405,6 +466,23 @@ def compute_dudt(g, config, prim, allow_reconstruction=True):
         mx = px * nrm[:, 0] + py * t1[:, 0] + pz * t2[:, 0]
         my = px * nrm[:, 1] + py * t1[:, 1] + pz * t2[:, 1]
         mz = px * nrm[:, 2] + py * t1[:, 2] + pz * t2[:, 2]
+        # apply_post_convective_flux_bc (finite_volume.cpp:201-210): ConstantFlux::apply (boundary.cpp:405-444) on a
+        # static grid, its `vy * n.x` in the energy flux included
+        for tag in sorted(g.tags):
+            for act in config["grid"]["boundaries"][tag].get("post_convective_flux", []):
+                if act["type"] != "constant_flux":
+                    raise NotImplementedError("flux action " + act["type"])
+                s_, gm = act["flow_state"], config["gas_model"]
+                f = np.asarray(g.tags[tag]["faces"], np.int64)
+                nx, ny, nz = nrm[f, 0], nrm[f, 1], nrm[f, 2]
+                u_ = float(gm["Cv"]) * s_["T"]
+                mf = s_["rho"] * ((s_["vx"] - 0.0) * nx + (s_["vy"] - 0.0) * ny + (s_["vz"] - 0.0) * nz)
+                mass[f] = mf
+                mx[f] = s_["p"] * nx + s_["vx"] * mf
+                my[f] = s_["p"] * ny + s_["vy"] * mf
+                mz[f] = s_["p"] * nz + s_["vz"] * mf
+                en[f] = mf * (u_ + 0.5 * (s_["vx"] * s_["vx"] + s_["vy"] * s_["vy"] + s_["vz"] * s_["vz"])) + \
+                    s_["p"] * (s_["vx"] * nx + s_["vy"] * nx + s_["vz"] * nz)
         comps = [mass, mx, my] + ([mz] if three_d else []) + [en]
         # flux_surface_integral (finite_volume.cpp:221-256): in cell-face order
         n = g.n_cells
@@ -418,3 +496,70 @@ def compute_dudt(g, config, prim, allow_reconstruction=True):
         vol = np.asarray(g.cell_volume)
         dudt = np.stack([a / vol for a in acc], axis=1)
     return dudt, fs, inter
+
+
+def estimate_dt(g, config, fs):
+    """FiniteVolume::estimate_dt (finite_volume.cpp:131-184), inviscid: min over the valid cells of
+    V / sum_f (|v.n| + a) A, summed in cell-face order"""
+    n = g.n_cells
+    gm = config["gas_model"]
+    rag = _Ragged(g)
+    nrm, area = np.asarray(g.face_norm), np.asarray(g.face_area)
+    vx, vy, vz = fs[:n, 4], fs[:n, 5], fs[:n, 6]
+    a = np.sqrt(float(gm["gamma"]) * float(gm["R"]) * fs[:n, 2])
+    sr = np.zeros(n)
+    with np.errstate(all="ignore"):
+        for j in range(rag.maxf):
+            m, f = rag.mask[:, j], rag.face[:, j]
+            dot = vx * nrm[f, 0] + vy * nrm[f, 1] + vz * nrm[f, 2]
+            sr = np.where(m, sr + (np.abs(dot) + a) * area[f], sr)
+        local = np.asarray(g.cell_volume) / (sr + float(config["viscous_flux"]["signal_factor"]) * 0.0)
+    dt = np.inf                                                  # Kokkos::Min identity; min(a, b) = (b < a) ? b : a
+    for v in local:
+        dt = v if v < dt else dt
+    return float(dt)
+
+
+def count_bad_cells(g, fs):
+    """FiniteVolume::count_bad_cells (finite_volume.cpp:258-270)"""
+    n = g.n_cells
+    T, rho = fs[:n, 2], fs[:n, 0]
+    return int(((T < 0.0) | (rho < 0.0) | np.isnan(rho) | np.isinf(rho)).sum())
+
+
+def primatives_to_conserved(fs, dim):
+    """primative_conserved_conversion.cpp:34-57 -> (n, dim + 2) mass, momentum, energy"""
+    rho, e, vx, vy, vz = fs[:, 0], fs[:, 3], fs[:, 4], fs[:, 5], fs[:, 6]
+    ke = 0.5 * (vx * vx + vy * vy + vz * vz)
+    cols = [rho, rho * vx, rho * vy] + ([rho * vz] if dim == 3 else []) + [rho * (ke + e)]
+    return np.stack(cols, axis=1)
+
+
+def conserved_to_primatives(cq, dim, gm):
+    """primative_conserved_conversion.cpp:5-26 with update_thermo_from_rhou -> (n, 7) rho p T e vx vy vz"""
+    with np.errstate(all="ignore"):
+        rho = cq[:, 0]
+        vx, vy = cq[:, 1] / rho, cq[:, 2] / rho
+        vz = cq[:, 3] / rho if dim == 3 else np.zeros_like(rho)
+        ke = 0.5 * (vx * vx + vy * vy + vz * vz)
+        u = cq[:, -1] / rho - ke
+        T = u / float(gm["Cv"])
+        p = rho * float(gm["R"]) * T
+    return np.stack([rho, p, T, u, vx, vy, vz], axis=1)
+
+
+def l2_norms(dudt, dim):
+    """ConservedQuantities::L2_norms (conserved_quantities.cpp:41-69) over the rows given, summed in index order
+    (one OpenMP thread): global, mass, momentum x y z, energy"""
+    acc = np.zeros(6)
+    for row in dudt:
+        m, mx, my = row[0], row[1], row[2]
+        mz = row[3] if dim == 3 else 0.0
+        en = row[-1]
+        acc[1] += m * m
+        acc[2] += mx * mx
+        acc[3] += my * my
+        acc[4] += mz * mz
+        acc[5] += en * en
+        acc[0] += m * m + mx * mx + my * my + mz * mz + en * en
+    return np.sqrt(acc)
