@@ -1,23 +1,24 @@
 """oracle/restatement.py -- TEST INFRASTRUCTURE, not product code.
 
-A plain-numpy restatement of the reference's inviscid residual, FiniteVolume<real>::compute_dudt
+A plain-numpy restatement of the reference's residual, FiniteVolume<real>::compute_dudt
 (/root/reference/src/finite_volume/finite_volume/finite_volume.cpp:57-96), written from the reference's
 sources function by function (each block cites the file:line it follows) and independent of the product's
 kernel bodies.  It exists next to the compiled reference (oracle/_ref, the primary oracle) for two reasons:
 it travels as source, and it is a second, independently written statement of the same arithmetic.
 
 Pinned: tests/test_oracle_restatement.py holds it BIT FOR BIT to the golden vectors the compiled reference
-produced (tests/golden/*.npz: residual, ghost fill, every gradient and limiter) on every inviscid case of
-tests/cases.py it covers -- hexes, mixed cells, tets, quads, triangles; ausmdv / hanel / rusanov / ldfss2; limited
+produced (tests/golden/*.npz: residual, ghost fill, every gradient and limiter, dt, conversions) on all 26 cases of
+tests/cases.py -- inviscid and viscous; hexes, mixed cells, tets, quads, triangles; ausmdv / hanel / rusanov / ldfss2; limited
 and unlimited; rho_u / rho_p / rho_T; supersonic and subsonic boundaries; first and second order.  Every operation below is an individually rounded
 IEEE operation in the reference's association order (numpy does not contract to FMA), which is why equality is
 exact.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import this module.
 
 Covered: ghost-cell actions flow_state_copy, internal_copy, internal_copy_reflect_normal, subsonic_inflow,
 subsonic_outflow, boundary_layer_profile (with CubicSpline); the constant_flux flux action; estimate_dt,
-count_bad_cells, L2 norms, primitive <-> conserved; WLS gradients; Barth-Jespersen / unlimited; MUSCL reconstruction with the three working thermo
+count_bad_cells, L2 norms, primitive <-> conserved; the viscous flux (pre_viscous_grad actions, Hasselbacher
+face gradients, Sutherland / constant-Prandtl transport) and the viscous time-step term; WLS gradients; Barth-Jespersen / unlimited; MUSCL reconstruction with the three working thermo
 interpolators; the ausmdv, hanel, rusanov and ldfss2 flux calculators; the surface integral.  Not covered (use
-oracle/_ref): viscous terms, moving grids, dual numbers.
+oracle/_ref): moving grids, dual numbers.
 """
 import numpy as np
 
@@ -101,8 +102,9 @@ class CubicSpline:
         return a + b + c
 
 
-def apply_pre_reconstruction(g, config, prim):
-    """finite_volume.cpp:187-199: tags in alphabetical order, actions in list order (boundary.cpp:517-543)"""
+def apply_pre_reconstruction(g, config, prim, phase="pre_reconstruction"):
+    """finite_volume.cpp:187-218: tags in alphabetical order, actions in list order (boundary.cpp:517-543);
+    phase = "pre_reconstruction" or "pre_viscous_grad"""
     fs = prim
     n = g.n_cells
     left, right = np.asarray(g.face_left), np.asarray(g.face_right)
@@ -111,7 +113,7 @@ def apply_pre_reconstruction(g, config, prim):
         l, r = left[faces], right[faces]
         ghost = np.where(l < n, r, l)
         valid = np.where(l < n, l, r)
-        for act in config["grid"]["boundaries"][tag]["pre_reconstruction"]:
+        for act in config["grid"]["boundaries"][tag][phase]:
             kind = act["type"]
             if kind == "flow_state_copy":                        # boundary.cpp:15-45
                 s = act["flow_state"]
@@ -128,6 +130,10 @@ def apply_pre_reconstruction(g, config, prim):
                 fs[ghost, 4] = xs * nrm[:, 0] + ys * t1[:, 0] + zs * t2[:, 0]
                 fs[ghost, 5] = xs * nrm[:, 1] + ys * t1[:, 1] + zs * t2[:, 1]
                 fs[ghost, 6] = xs * nrm[:, 2] + ys * t1[:, 2] + zs * t2[:, 2]
+            elif kind == "internal_vel_copy_reflect":            # boundary.cpp:209-240
+                fs[ghost, 4], fs[ghost, 5], fs[ghost, 6] = -fs[valid, 4], -fs[valid, 5], -fs[valid, 6]
+            elif kind == "fix_temperature":                      # boundary.cpp:243-276
+                fs[ghost, 2] = 2.0 * float(act["temperature"]) - fs[valid, 2]
             elif kind == "boundary_layer_profile":               # boundary.cpp:51-95
                 prof = act["profile"]
                 gm = config["gas_model"]
@@ -443,11 +449,9 @@ FLUX = {"ausmdv": flux_ausmdv, "hanel": flux_hanel, "rusanov": flux_rusanov, "ld
 
 
 def compute_dudt(g, config, prim, allow_reconstruction=True):
-    """FiniteVolume<real>::compute_dudt (finite_volume.cpp:57-96), inviscid, static grid.
+    """FiniteVolume<real>::compute_dudt (finite_volume.cpp:57-96), static grid.
     prim: (n_cells + n_ghost, 7) rho p T e vx vy vz.  -> dudt (n_cells, dim + 2), prim after the ghost fill,
     dict of intermediates (grad_* (n_cells, 3), lim_* (n_cells,))."""
-    if config["viscous_flux"]["enabled"]:
-        raise NotImplementedError("viscous terms: use the compiled reference (oracle/_ref)")
     cf = config["convective_flux"]
     if cf["flux_calculator"]["type"] not in FLUX:
         raise NotImplementedError("flux calculator " + cf["flux_calculator"]["type"])
@@ -483,6 +487,14 @@ def compute_dudt(g, config, prim, allow_reconstruction=True):
                 mz[f] = s_["p"] * nz + s_["vz"] * mf
                 en[f] = mf * (u_ + 0.5 * (s_["vx"] * s_["vx"] + s_["vy"] * s_["vy"] + s_["vz"] * s_["vz"])) + \
                     s_["p"] * (s_["vx"] * nx + s_["vy"] * nx + s_["vz"] * nz)
+        if config["viscous_flux"]["enabled"]:                    # finite_volume.cpp:73-77
+            fs = apply_pre_reconstruction(g, config, fs, "pre_viscous_grad")
+            by_name = {"mx": mx, "my": my, "mz": mz, "en": en}
+            vgrads, face_fs = viscous_flux(g, config, fs, rag, by_name)
+            # cell_grad_ is shared: the viscous gradients overwrite the convective ones (finite_volume.h:116-141)
+            for name, gr in vgrads.items():
+                inter["grad_" + name] = gr
+            inter["face_fs"] = face_fs
         comps = [mass, mx, my] + ([mz] if three_d else []) + [en]
         # flux_surface_integral (finite_volume.cpp:221-256): in cell-face order
         n = g.n_cells
@@ -498,7 +510,68 @@ def compute_dudt(g, config, prim, allow_reconstruction=True):
     return dudt, fs, inter
 
 
-def estimate_dt(g, config, fs):
+def _viscosity(T, tp):
+    """ViscosityModel::viscosity (gas/transport_properties.h:29-42): Sutherland"""
+    v = tp["viscosity"]
+    mu0, T0, Ts = float(v["mu_0"]), float(v["T_0"]), float(v["T_s"])
+    return mu0 * np.power(T / T0, 3.0 / 2.0) * (T0 + Ts) / (T + Ts)
+
+
+def viscous_flux(g, config, fs, rag, comps_by_name):
+    """ViscousFlux::compute_viscous_flux (finite_volume/viscous_flux.cpp:122-184) with
+    compute_viscous_properties_at_faces (:83-107) and the Hasselbacher average (:37-80): subtracts the viscous
+    flux in place; -> (viscous cell gradients by name, face_fs T and rho for estimate_dt)"""
+    n = g.n_cells
+    gm, tp = config["gas_model"], config["transport_properties"]
+    r = wls_r(g, rag)
+    grads = {name: wls_gradient(g, rag, r, fs[:, col]) for name, col in (("T", 2), ("vx", 4), ("vy", 5), ("vz", 6))}
+    left, right = np.asarray(g.face_left), np.asarray(g.face_right)
+    lv, rv = left < n, right < n
+    both = lv & rv
+    interior = np.where(lv, left, right)
+    ls, rs = np.where(both, left, 0), np.where(both, right, 0)
+    c, nrm = np.asarray(g.cell_centroid), np.asarray(g.face_norm)
+    ex, ey, ez = c[right, 0] - c[left, 0], c[right, 1] - c[left, 1], c[right, 2] - c[left, 2]
+    len_e = np.sqrt(ex * ex + ey * ey + ez * ez)
+    ehx, ehy, ehz = ex / len_e, ey / len_e, ez / len_e
+    nx, ny, nz = nrm[:, 0], nrm[:, 1], nrm[:, 2]
+    ehat_dot_n = ehx * nx + ehy * ny + ehz * nz
+    face_grad = {}
+    for name, col in (("vx", 4), ("vy", 5), ("vz", 6), ("T", 2)):
+        gr = grads[name]
+        ax, ay, az = 0.5 * (gr[ls, 0] + gr[rs, 0]), 0.5 * (gr[ls, 1] + gr[rs, 1]), 0.5 * (gr[ls, 2] + gr[rs, 2])
+        corr = (ax * ehx + ay * ehy + az * ehz) - (fs[right, col] - fs[left, col]) / len_e
+        hx, hy, hz = ax - corr * nx / ehat_dot_n, ay - corr * ny / ehat_dot_n, az - corr * nz / ehat_dot_n
+        gi = gr[np.where(both, 0, interior)]
+        face_grad[name] = (np.where(both, hx, gi[:, 0]), np.where(both, hy, gi[:, 1]), np.where(both, hz, gi[:, 2]))
+    # average_flow_states_pT + update_thermo_from_pT (gas/flow_state.h:89-91, gas_state.h:108-113)
+    p = 0.5 * (fs[left, 1] + fs[right, 1])
+    T = 0.5 * (fs[left, 2] + fs[right, 2])
+    rho = p / (float(gm["R"]) * T)
+    vx, vy, vz = (0.5 * (fs[left, k] + fs[right, k]) for k in (4, 5, 6))
+    mu = _viscosity(T, tp)
+    k = float(gm["Cp"]) * mu / float(tp["thermal_conductivity"]["Pr"])
+    lam = -2.0 / 3.0 * mu
+    gvx, gvy, gvz, gT = face_grad["vx"], face_grad["vy"], face_grad["vz"], face_grad["T"]
+    bulk = lam * (gvx[0] + gvy[1] + gvz[2])
+    tau_xx = 2.0 * mu * gvx[0] + bulk
+    tau_yy = 2.0 * mu * gvy[1] + bulk
+    tau_zz = 2.0 * mu * gvz[2] + bulk
+    tau_xy = mu * (gvx[1] + gvy[0])
+    tau_xz = mu * (gvx[2] + gvz[0])
+    tau_yz = mu * (gvy[2] + gvz[1])
+    theta_x = vx * tau_xx + vy * tau_xy + vz * tau_xz + k * gT[0]
+    theta_y = vx * tau_xy + vy * tau_yy + vz * tau_yz + k * gT[1]
+    theta_z = vx * tau_xz + vy * tau_yz + vz * tau_zz + k * gT[2]
+    comps_by_name["mx"] -= nx * tau_xx + ny * tau_xy + nz * tau_xz
+    comps_by_name["my"] -= nx * tau_xy + ny * tau_yy + nz * tau_yz
+    if g.dim == 3:
+        comps_by_name["mz"] -= nx * tau_xz + ny * tau_yz + nz * tau_zz
+    comps_by_name["en"] -= nx * theta_x + ny * theta_y + nz * theta_z
+    return grads, (T, rho)
+
+
+def estimate_dt(g, config, fs, face_fs=None):
     """FiniteVolume::estimate_dt (finite_volume.cpp:131-184), inviscid: min over the valid cells of
     V / sum_f (|v.n| + a) A, summed in cell-face order"""
     n = g.n_cells
@@ -507,13 +580,24 @@ def estimate_dt(g, config, fs):
     nrm, area = np.asarray(g.face_norm), np.asarray(g.face_area)
     vx, vy, vz = fs[:n, 4], fs[:n, 5], fs[:n, 6]
     a = np.sqrt(float(gm["gamma"]) * float(gm["R"]) * fs[:n, 2])
-    sr = np.zeros(n)
+    sr, sr_v = np.zeros(n), np.zeros(n)
+    vol = np.asarray(g.cell_volume)
+    viscous = bool(config["viscous_flux"]["enabled"])
+    if viscous and face_fs is None:
+        raise ValueError("viscous estimate_dt reads the face states of the last viscous flux evaluation")
     with np.errstate(all="ignore"):
         for j in range(rag.maxf):
             m, f = rag.mask[:, j], rag.face[:, j]
             dot = vx * nrm[f, 0] + vy * nrm[f, 1] + vz * nrm[f, 2]
             sr = np.where(m, sr + (np.abs(dot) + a) * area[f], sr)
-        local = np.asarray(g.cell_volume) / (sr + float(config["viscous_flux"]["signal_factor"]) * 0.0)
+            if viscous:                                          # finite_volume.cpp:166-174
+                Tf, rhof = face_fs[0][f], face_fs[1][f]
+                mu = _viscosity(Tf, config["transport_properties"])
+                k = float(gm["Cp"]) * mu / float(config["transport_properties"]["thermal_conductivity"]["Pr"])
+                Pr = mu * float(gm["Cp"]) / k
+                tmp = (float(gm["gamma"]) / rhof) * (mu / Pr) * area[f] * area[f]
+                sr_v = np.where(m, sr_v + tmp / vol, sr_v)
+        local = vol / (sr + float(config["viscous_flux"]["signal_factor"]) * sr_v)
     dt = np.inf                                                  # Kokkos::Min identity; min(a, b) = (b < a) ? b : a
     for v in local:
         dt = v if v < dt else dt
