@@ -7,18 +7,21 @@ kernel bodies.  It exists next to the compiled reference (oracle/_ref, the prima
 it travels as source, and it is a second, independently written statement of the same arithmetic.
 
 Pinned: tests/test_oracle_restatement.py holds it BIT FOR BIT to the golden vectors the compiled reference
-produced (tests/golden/*.npz: residual, ghost fill, every gradient and limiter, dt, conversions) on all 26 cases of
-tests/cases.py -- inviscid and viscous; hexes, mixed cells, tets, quads, triangles; ausmdv / hanel / rusanov / ldfss2; limited
-and unlimited; rho_u / rho_p / rho_T; supersonic and subsonic boundaries; first and second order.  Every operation below is an individually rounded
-IEEE operation in the reference's association order (numpy does not contract to FMA), which is why equality is
-exact.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import this module.
+produced (tests/golden/*.npz: residual, ghost fill, every gradient and limiter, dt, conversions; and
+moving_*.npz) on all 26 static and 8 moving-grid cases of tests/cases.py -- inviscid and viscous; hexes, mixed
+cells, tets, quads, triangles; ausmdv / hanel / rusanov / ldfss2; limited and unlimited; rho_u / rho_p / rho_T;
+supersonic, subsonic, wall, profile and constant-flux boundaries; first and second order.  Every operation
+below is an individually rounded IEEE operation in the reference's association order (numpy does not contract
+to FMA; pow is glibc's on both sides), which is why equality is exact.
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import this module.
 
-Covered: ghost-cell actions flow_state_copy, internal_copy, internal_copy_reflect_normal, subsonic_inflow,
-subsonic_outflow, boundary_layer_profile (with CubicSpline); the constant_flux flux action; estimate_dt,
-count_bad_cells, L2 norms, primitive <-> conserved; the viscous flux (pre_viscous_grad actions, Hasselbacher
-face gradients, Sutherland / constant-Prandtl transport) and the viscous time-step term; WLS gradients; Barth-Jespersen / unlimited; MUSCL reconstruction with the three working thermo
-interpolators; the ausmdv, hanel, rusanov and ldfss2 flux calculators; the surface integral.  Not covered (use
-oracle/_ref): moving grids, dual numbers.
+Covered: all eight ghost-cell actions (boundary_layer_profile with CubicSpline) and the constant_flux flux
+action; WLS r-factors and gradients; Barth-Jespersen / unlimited; MUSCL reconstruction with the three working
+thermo interpolators; the four flux calculators; the viscous flux (pre_viscous_grad actions, Hasselbacher face
+gradients, Sutherland / constant-Prandtl transport); the surface integral; the moving-grid terms (interface
+velocities, relative fluxes, geometric conservation law); estimate_dt with its viscous term, count_bad_cells,
+L2 norms, primitive <-> conserved.  Not covered (use oracle/_ref): vertex motion / geometry recomputation, the
+solvers, dual numbers.
 """
 import numpy as np
 
@@ -448,8 +451,11 @@ def flux_ldfss2(L, R_, vl, vr, gm, three_d, delta=2.0):
 FLUX = {"ausmdv": flux_ausmdv, "hanel": flux_hanel, "rusanov": flux_rusanov, "ldfss2": flux_ldfss2}
 
 
-def compute_dudt(g, config, prim, allow_reconstruction=True):
-    """FiniteVolume<real>::compute_dudt (finite_volume.cpp:57-96), static grid.
+def compute_dudt(g, config, prim, allow_reconstruction=True, vertex_vel=None, cq=None):
+    """FiniteVolume<real>::compute_dudt (finite_volume.cpp:57-96).  With vertex_vel (n_vertices, 3) and cq
+    (conserved quantities of prim) it is the moving-grid overload: interface velocities (grid.h:571-592),
+    interface-relative fluxes with the inertial-frame correction (convective_flux.cpp:105-140,166-176) and the
+    geometric conservation law (finite_volume.cpp:99-128); inter["face_vel"] is GridBlock::face_vel() afterwards.
     prim: (n_cells + n_ghost, 7) rho p T e vx vy vz.  -> dudt (n_cells, dim + 2), prim after the ghost fill,
     dict of intermediates (grad_* (n_cells, 3), lim_* (n_cells,))."""
     cf = config["convective_flux"]
@@ -461,11 +467,39 @@ def compute_dudt(g, config, prim, allow_reconstruction=True):
     with np.errstate(all="ignore"):
         L, R_, inter = reconstruct(g, config, fs, rag, order2)
         nrm, t1, t2 = np.asarray(g.face_norm), np.asarray(g.face_tan1), np.asarray(g.face_tan2)
+        moving = vertex_vel is not None
+        face_vel = np.zeros((g.n_faces, 3))
+        if moving:                                               # GridBlock::compute_face_vel (grid.h:571-592)
+            fv_ids, nv = np.asarray(g.face_vertices), np.asarray(g.face_nv)
+            acc = np.zeros((g.n_faces, 3))
+            for k in range(4):
+                mk = (nv > k)[:, None]
+                acc = np.where(mk, acc + vertex_vel[np.maximum(fv_ids[:, k], 0)], acc)
+            face_vel = acc / nv[:, None].astype(np.float64)
+            L, R_ = L.copy(), R_.copy()
+            L[:, 4:7] = L[:, 4:7] - face_vel                     # subtract (convective_flux.cpp:105-108)
+            R_[:, 4:7] = R_[:, 4:7] - face_vel
         vl, vr = _to_local(L[:, 4:7], nrm, t1, t2), _to_local(R_[:, 4:7], nrm, t1, t2)        # convective_flux.cpp:110-113
+        if moving:
+            lx, ly, lz = _to_local(face_vel, nrm, t1, t2)        # :114-117
         three_d = g.dim == 3
         fc = cf["flux_calculator"]
         extra = {"delta": float(fc.get("delta", 2.0))} if fc["type"] == "ldfss2" else {}
         mass, px, py, pz, en = FLUX[fc["type"]](L, R_, vl, vr, config["gas_model"], three_d, **extra)
+        if moving:                                               # flux::grid_motion (convective_flux.cpp:123-141)
+            v_sqr = lx * lx + ly * ly + lz * lz
+            en = en + (0.5 * mass * v_sqr + px * lx + py * ly)
+            if three_d:
+                en = en + pz * lz
+            px = px + lx * mass
+            py = py + ly * mass
+            if three_d:
+                pz = pz + lz * mass
+            # the interface velocity goes back to the global frame through the same rotation (:166-176)
+            face_vel = np.stack([lx * nrm[:, 0] + ly * t1[:, 0] + lz * t2[:, 0],
+                                 lx * nrm[:, 1] + ly * t1[:, 1] + lz * t2[:, 1],
+                                 lx * nrm[:, 2] + ly * t1[:, 2] + lz * t2[:, 2]], axis=1)
+            inter["face_vel"] = face_vel
         # flux::transform_to_global (convective_flux.cpp:148-164)
         mx = px * nrm[:, 0] + py * t1[:, 0] + pz * t2[:, 0]
         my = px * nrm[:, 1] + py * t1[:, 1] + pz * t2[:, 1]
@@ -480,7 +514,8 @@ def compute_dudt(g, config, prim, allow_reconstruction=True):
                 f = np.asarray(g.tags[tag]["faces"], np.int64)
                 nx, ny, nz = nrm[f, 0], nrm[f, 1], nrm[f, 2]
                 u_ = float(gm["Cv"]) * s_["T"]
-                mf = s_["rho"] * ((s_["vx"] - 0.0) * nx + (s_["vy"] - 0.0) * ny + (s_["vz"] - 0.0) * nz)
+                mf = s_["rho"] * ((s_["vx"] - face_vel[f, 0]) * nx + (s_["vy"] - face_vel[f, 1]) * ny +
+                                  (s_["vz"] - face_vel[f, 2]) * nz)
                 mass[f] = mf
                 mx[f] = s_["p"] * nx + s_["vx"] * mf
                 my[f] = s_["p"] * ny + s_["vy"] * mf
@@ -507,6 +542,14 @@ def compute_dudt(g, config, prim, allow_reconstruction=True):
                 acc[k] = np.where(m, acc[k] + comp[f] * area, acc[k])
         vol = np.asarray(g.cell_volume)
         dudt = np.stack([a / vol for a in acc], axis=1)
+        if moving:                                               # apply_geometric_conservation_law (finite_volume.cpp:99-128)
+            dVdt = np.zeros(n)
+            for j in range(rag.maxf):
+                m, f = rag.mask[:, j], rag.face[:, j]
+                area = area_all[f] * rag.out[:, j]
+                dVdt = np.where(m, dVdt + (face_vel[f, 0] * nrm[f, 0] + face_vel[f, 1] * nrm[f, 1] +
+                                           face_vel[f, 2] * nrm[f, 2]) * area, dVdt)
+            dudt = dudt - cq[:n] * dVdt[:, None] / vol[:, None]
     return dudt, fs, inter
 
 

@@ -42,6 +42,19 @@ def test_restatement_equals_compiled_reference(name):
                 assert any(k.startswith("grad_") for k in inter)
 
 
+@pytest.mark.parametrize("name", sorted(cases.MOVING_CASES))
+def test_restatement_moving_grid_equals_compiled_reference(name):
+    """the moving-grid overload (rigid_body_translation driver) against tests/golden/moving_*.npz"""
+    mesh, config, g, prim, vvel = cases.build_moving_case(name)
+    gold = dict(np.load(os.path.join(parity.GOLDEN, "moving_" + name + ".npz")))
+    cq = restatement.primatives_to_conserved(prim, mesh.dim)
+    for allow, sfx in ((True, ""), (False, "_o1")):
+        dudt, fs, inter = restatement.compute_dudt(g, config, prim, allow, vertex_vel=vvel, cq=cq)
+        parity.assert_close(dudt, gold["dudt" + sfx], 1.0, f"{name}: moving dudt{sfx}", True)
+        parity.assert_close(fs, gold["prim_out" + sfx], 1.0, f"{name}: ghost fill{sfx}", True)
+        parity.assert_close(inter["face_vel"], gold["face_vel" + sfx], 1.0, f"{name}: face_vel{sfx}", True)
+
+
 def test_restatement_cubic_spline_reference_kats():
     """util/cubic_spline.cpp:91-160"""
     s = restatement.CubicSpline([1.0, 2.0, 3.0, 4.0, 8.0], [4.0, 6.0, 8.0, 10.0, 18.0])
