@@ -20,8 +20,9 @@ action; WLS r-factors and gradients; Barth-Jespersen / unlimited; MUSCL reconstr
 thermo interpolators; the four flux calculators; the viscous flux (pre_viscous_grad actions, Hasselbacher face
 gradients, Sutherland / constant-Prandtl transport); the surface integral; the moving-grid terms (interface
 velocities, relative fluxes, geometric conservation law); estimate_dt with its viscous term, count_bad_cells,
-L2 norms, primitive <-> conserved.  Not covered (use oracle/_ref): vertex motion / geometry recomputation, the
-solvers, dual numbers.
+L2 norms, primitive <-> conserved; and the explicit solver (Solver::solve + RungeKutta on a static grid), held to
+the final snapshots of the reference's own runs (tests/golden/solve_rk_*.npz).  Not covered (use oracle/_ref):
+vertex motion / geometry recomputation, the steady solver, dual numbers.
 """
 import numpy as np
 
@@ -690,3 +691,72 @@ def l2_norms(dudt, dim):
         acc[5] += en * en
         acc[0] += m * m + mx * mx + my * my + mz * mz + en * en
     return np.sqrt(acc)
+
+
+def _cfl(schedule, t):
+    """ConstantSchedule / LinearSchedule::eval (solvers/cfl.cpp:11-40)"""
+    if schedule["type"] == "constant":
+        return float(schedule["value"])
+    if schedule["type"] == "linear_interpolate":
+        times, cfls = schedule["times"], schedule["cfls"]
+        if t <= times[0]:
+            return cfls[0]
+        if t >= times[-1]:
+            return cfls[-1]
+        for i in range(len(times)):
+            if times[i] <= t < times[i + 1]:
+                frac = (t - times[i]) / (times[i + 1] - times[i])
+                return cfls[i] + frac * (cfls[i + 1] - cfls[i])
+    raise NotImplementedError("cfl schedule " + schedule["type"])
+
+
+def runge_kutta(g, config, prim0):
+    """Solver::solve (solvers/solver.cpp:18-64) driving RungeKutta::initialise / estimate_dt / take_step / stop_now
+    (solvers/runge_kutta.cpp:82-119,131-203,258-262) on a static grid, time-based plotting off.  The stage arrays
+    k_[i] are ONE array in the reference (runge_kutta.cpp:49-50 copies one view handle into every slot), so
+    every k_[j] below is the most recent evaluation.  -> (final primitive state, t, steps taken)"""
+    import sys
+    sc, gm, dim = config["solver"], config["gas_model"], g.dim
+    a_rows, b = sc["butcher_tableau"]["a"], sc["butcher_tableau"]["b"]
+    n_stages = len(b)
+    a = lambda i, j: float(a_rows[i - 1][j])                                        # noqa: E731
+    flow = np.array(prim0, dtype=np.float64)
+    cq = primatives_to_conserved(flow, dim)
+    dt = float(sc["dt_init"]) if sc["dt_init"] > 0 else sys.float_info.max
+    t, max_time, max_step = 0.0, float(sc["max_time"]), int(sc["max_step"])
+    viscous = bool(config["viscous_flux"]["enabled"])
+
+    def evaluate(fs):
+        """function_eval_: dudt over all rows (ghost rows stay zero), the ghost-filled state, face_fs"""
+        d, fs_out, inter = compute_dudt(g, config, fs, True)
+        full = np.zeros((len(fs), dim + 2))
+        full[:g.n_cells] = d
+        return full, fs_out, inter.get("face_fs")
+
+    k, flow, face_fs = evaluate(flow)                                               # initialise(): :93
+    steps = 0
+    for step in range(max_step):
+        k, flow, face_fs = evaluate(flow)                                           # take_step: :143
+        stable = estimate_dt(g, config, flow, face_fs if viscous else None)        # :108-119
+        dt_startup = min(_cfl(sc["cfl"], t) * stable, 1.5 * dt)
+        dt = min(dt_startup, max_time - t)
+        for i in range(1, n_stages):
+            k_tmp = cq + k * (a(i, 0) * dt)                                         # :155
+            for j in range(1, i):
+                if a(i, j) < 1e-14:
+                    continue
+                k_tmp = k_tmp + k * (a(i, j) * dt)                                  # :169
+            with np.errstate(all="ignore"):
+                flow_tmp = conserved_to_primatives(k_tmp, dim, gm)                  # :177
+            k, _, face_fs = evaluate(flow_tmp)                                      # :181 (flow_tmp's ghosts are its own)
+        for i in range(n_stages):
+            cq = cq + k * (float(b[i]) * dt)                                        # :185-186
+        with np.errstate(all="ignore"):
+            flow = conserved_to_primatives(cq, dim, gm)                             # :193
+        t += dt
+        steps += 1
+        if count_bad_cells(g, flow) > 0:                                            # solver.cpp:38-43
+            break
+        if step >= max_step - 1 or t >= max_time:                                   # stop_now
+            break
+    return flow, t, steps
