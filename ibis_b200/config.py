@@ -137,7 +137,7 @@ def make_config(dim, boundaries, flux_calculator="hanel", reconstruction_order=2
         "convective_flux": {"flux_calculator": fc, "reconstruction_order": reconstruction_order,
                             "limiter": lim, "thermo_interpolator": thermo_interpolator},
         "viscous_flux": {"enabled": bool(viscous), "signal_factor": signal_factor},
-        "solver": solver if solver is not None else runge_kutta(),
+        "solver": copy.deepcopy(solver) if solver is not None else runge_kutta(),
         "grid": {"boundaries": copy.deepcopy(boundaries), "dimensions": dim,
                  "motion": copy.deepcopy(motion) if motion else {"enabled": False}},
         "gas_model": ideal_gas(R),
