@@ -47,4 +47,14 @@ def test_product_has_no_cpu_fallback():
             with open(os.path.join(dirpath, fn)) as f:
                 text = f.read()
             assert "import refharness" not in text and "from oracle" not in text and "libibis_ref" not in text, fn
+            assert "import restatement" not in text, fn
             assert "ibis_b200_emu" not in text or fn in ("abi.cu", "backend.h"), fn
+
+
+@pytest.mark.parametrize("header", ["ibis_b200.h", "ibis_b200_host.h"])
+def test_headers_are_plain_c(header):
+    """the boundary is a C ABI: the headers compile as C99 (no C++ types, no torch types in any signature)"""
+    import subprocess
+    r = subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-x", "c", "-fsyntax-only", "-I", ROOT, "-"],
+                       input=f'#include "include/{header}"\n', text=True, capture_output=True)
+    assert r.returncode == 0, r.stderr
