@@ -129,3 +129,26 @@ def test_product_equals_restatement_on_seeded_input(build, seed):
         assert np.array_equal(ctx.cq_download(dq)[:g.n_cells], want)
         assert np.array_equal(ctx.fs_download(fs), ghosts)
     ctx.close()
+
+
+@pytest.mark.parametrize("name,allow", [("box3d_unlimited", True), ("box3d_hanel", False), ("quad2d_rusanov", False)])
+def test_dual_residual_is_the_derivative_of_the_restated_residual(name, allow):
+    """ties the dual-number path (the exact Jacobian-vector product of the steady solver) to the restatement, which
+    has no dual numbers: dual part of R(u + eps v) == central difference of the restated real residual along v.
+    Smooth configurations only (unlimited second order, first order): a limiter is not differentiable."""
+    from emu_util import emu_lib
+    from ibis_b200.lib import Context
+    mesh, config, g, prim = cases.build_case(name)
+    v = cases.dual_seed(prim)
+    ctx = Context(g, config, lib_path=emu_lib())
+    fsd, dqd = ctx.fs_create(True), ctx.cq_create(True)
+    ctx.fs_upload(fsd, prim, v)
+    ctx.compute_dudt(fsd, dqd, allow)
+    _, du = ctx.cq_download(dqd, dual=True)
+    ctx.close()
+    h = 1e-4                                     # v is ~1e-3 of the state: the step is 1e-7 relative
+    plus = restatement.compute_dudt(g, config, prim + h * v, allow)[0]
+    minus = restatement.compute_dudt(g, config, prim - h * v, allow)[0]
+    fd = (plus - minus) / (2.0 * h)
+    scale = np.abs(du[:g.n_cells]).max(axis=0)
+    assert (np.abs(du[:g.n_cells] - fd) <= 2e-5 * scale).all(), np.abs(du[:g.n_cells] - fd).max(axis=0) / scale
