@@ -20,22 +20,29 @@ action; WLS r-factors and gradients; Barth-Jespersen / unlimited; MUSCL reconstr
 thermo interpolators; the four flux calculators; the viscous flux (pre_viscous_grad actions, Hasselbacher face
 gradients, Sutherland / constant-Prandtl transport); the surface integral; the moving-grid terms (interface
 velocities, relative fluxes, geometric conservation law); estimate_dt with its viscous term, count_bad_cells,
-L2 norms, primitive <-> conserved; and the explicit solver (Solver::solve + RungeKutta on a static grid), held to
+L2 norms, primitive <-> conserved -- all of it on dual numbers too (oracle/dualnum.py: one exact Jacobian-vector
+product direction of the steady solver); and the explicit solver (Solver::solve + RungeKutta on a static grid), held to
 the final snapshots of the reference's own runs (tests/golden/solve_rk_*.npz).  Not covered (use oracle/_ref):
-vertex motion / geometry recomputation, the steady solver, dual numbers.
+vertex motion / geometry recomputation, the steady solver.
 """
 import numpy as np
+
+from dualnum import Dual, as_T, dmax, dmin
 
 R_AIR = 287.0
 
 
 def _min(a, b):
-    """Ibis::min -> Kokkos::min(a, b) = (b < a) ? b : a   (util/real.h:15-65)"""
+    """Ibis::min -> Kokkos::min(a, b) = (b < a) ? b : a for doubles (util/real.h:15-65); dual.h:284-298 for duals"""
+    if isinstance(a, Dual) or isinstance(b, Dual):
+        return dmin(a, b)
     return np.where(b < a, b, a)
 
 
 def _max(a, b):
-    """Kokkos::max(a, b) = (a < b) ? b : a"""
+    """Kokkos::max(a, b) = (a < b) ? b : a for doubles; dual.h:269-282 for duals"""
+    if isinstance(a, Dual) or isinstance(b, Dual):
+        return dmax(a, b)
     return np.where(a < b, b, a)
 
 
@@ -263,7 +270,7 @@ def _thermo_close(kind, rho, th2, R, Cv):
         return p, T, Cv * T
     if kind == "rho_u":
         e = th2
-        T = e / Cv
+        T = e / as_T(Cv, e)                                      # temp_from_energy(u, Cv_): Cv_ is a T
         return rho * R * T, T, e
     if kind == "rho_T":
         T = th2
@@ -462,7 +469,7 @@ def compute_dudt(g, config, prim, allow_reconstruction=True, vertex_vel=None, cq
     cf = config["convective_flux"]
     if cf["flux_calculator"]["type"] not in FLUX:
         raise NotImplementedError("flux calculator " + cf["flux_calculator"]["type"])
-    fs = apply_pre_reconstruction(g, config, np.array(prim, dtype=np.float64))
+    fs = apply_pre_reconstruction(g, config, prim.copy() if isinstance(prim, Dual) else np.array(prim, dtype=np.float64))
     rag = _Ragged(g)
     order2 = allow_reconstruction and int(cf["reconstruction_order"]) == 2
     with np.errstate(all="ignore"):
@@ -542,7 +549,7 @@ def compute_dudt(g, config, prim, allow_reconstruction=True, vertex_vel=None, cq
             for k, comp in enumerate(comps):
                 acc[k] = np.where(m, acc[k] + comp[f] * area, acc[k])
         vol = np.asarray(g.cell_volume)
-        dudt = np.stack([a / vol for a in acc], axis=1)
+        dudt = np.stack([a / as_T(vol, a) for a in acc], axis=1)
         if moving:                                               # apply_geometric_conservation_law (finite_volume.cpp:99-128)
             dVdt = np.zeros(n)
             for j in range(rag.maxf):
@@ -550,7 +557,7 @@ def compute_dudt(g, config, prim, allow_reconstruction=True, vertex_vel=None, cq
                 area = area_all[f] * rag.out[:, j]
                 dVdt = np.where(m, dVdt + (face_vel[f, 0] * nrm[f, 0] + face_vel[f, 1] * nrm[f, 1] +
                                            face_vel[f, 2] * nrm[f, 2]) * area, dVdt)
-            dudt = dudt - cq[:n] * dVdt[:, None] / vol[:, None]
+            dudt = dudt - cq[:n] * dVdt[:, None] / as_T(vol[:, None], dudt)
     return dudt, fs, inter
 
 
@@ -558,7 +565,7 @@ def _viscosity(T, tp):
     """ViscosityModel::viscosity (gas/transport_properties.h:29-42): Sutherland"""
     v = tp["viscosity"]
     mu0, T0, Ts = float(v["mu_0"]), float(v["T_0"]), float(v["T_s"])
-    return mu0 * np.power(T / T0, 3.0 / 2.0) * (T0 + Ts) / (T + Ts)
+    return mu0 * np.power(T / as_T(T0, T), 3.0 / 2.0) * (T0 + Ts) / (T + Ts)
 
 
 def viscous_flux(g, config, fs, rag, comps_by_name):
@@ -584,8 +591,9 @@ def viscous_flux(g, config, fs, rag, comps_by_name):
     for name, col in (("vx", 4), ("vy", 5), ("vz", 6), ("T", 2)):
         gr = grads[name]
         ax, ay, az = 0.5 * (gr[ls, 0] + gr[rs, 0]), 0.5 * (gr[ls, 1] + gr[rs, 1]), 0.5 * (gr[ls, 2] + gr[rs, 2])
-        corr = (ax * ehx + ay * ehy + az * ehz) - (fs[right, col] - fs[left, col]) / len_e
-        hx, hy, hz = ax - corr * nx / ehat_dot_n, ay - corr * ny / ehat_dot_n, az - corr * nz / ehat_dot_n
+        corr = (ax * ehx + ay * ehy + az * ehz) - (fs[right, col] - fs[left, col]) / as_T(len_e, ax)
+        den = as_T(ehat_dot_n, ax)
+        hx, hy, hz = ax - corr * nx / den, ay - corr * ny / den, az - corr * nz / den
         gi = gr[np.where(both, 0, interior)]
         face_grad[name] = (np.where(both, hx, gi[:, 0]), np.where(both, hy, gi[:, 1]), np.where(both, hz, gi[:, 2]))
     # average_flow_states_pT + update_thermo_from_pT (gas/flow_state.h:89-91, gas_state.h:108-113)
@@ -594,7 +602,7 @@ def viscous_flux(g, config, fs, rag, comps_by_name):
     rho = p / (float(gm["R"]) * T)
     vx, vy, vz = (0.5 * (fs[left, k] + fs[right, k]) for k in (4, 5, 6))
     mu = _viscosity(T, tp)
-    k = float(gm["Cp"]) * mu / float(tp["thermal_conductivity"]["Pr"])
+    k = float(gm["Cp"]) * mu / as_T(float(tp["thermal_conductivity"]["Pr"]), mu)
     lam = -2.0 / 3.0 * mu
     gvx, gvy, gvz, gT = face_grad["vx"], face_grad["vy"], face_grad["vz"], face_grad["T"]
     bulk = lam * (gvx[0] + gvy[1] + gvz[2])
@@ -671,7 +679,7 @@ def conserved_to_primatives(cq, dim, gm):
         vz = cq[:, 3] / rho if dim == 3 else np.zeros_like(rho)
         ke = 0.5 * (vx * vx + vy * vy + vz * vz)
         u = cq[:, -1] / rho - ke
-        T = u / float(gm["Cv"])
+        T = u / as_T(float(gm["Cv"]), u)
         p = rho * float(gm["R"]) * T
     return np.stack([rho, p, T, u, vx, vy, vz], axis=1)
 
