@@ -21,9 +21,9 @@ thermo interpolators; the four flux calculators; the viscous flux (pre_viscous_g
 gradients, Sutherland / constant-Prandtl transport); the surface integral; the moving-grid terms (interface
 velocities, relative fluxes, geometric conservation law); estimate_dt with its viscous term, count_bad_cells,
 L2 norms, primitive <-> conserved -- all of it on dual numbers too (oracle/dualnum.py: one exact Jacobian-vector
-product direction of the steady solver); and the explicit solver (Solver::solve + RungeKutta on a static grid), held to
-the final snapshots of the reference's own runs (tests/golden/solve_rk_*.npz).  Not covered (use oracle/_ref):
-vertex motion / geometry recomputation, the steady solver.
+product direction of the steady solver); and the solvers: Solver::solve + RungeKutta on a static grid (bit for bit) and SteadyState / Jfnk /
+Gmres with dual-number matrix-vector products (1e-9), held to the final snapshots of the reference's own runs
+(tests/golden/solve_*.npz).  Not covered (use oracle/_ref): vertex motion / geometry recomputation, FGMRES.
 """
 import numpy as np
 
@@ -768,3 +768,154 @@ def runge_kutta(g, config, prim0):
         if step >= max_step - 1 or t >= max_time:                                   # stop_now
             break
     return flow, t, steps
+
+
+def _seqsum(a):
+    """Kokkos::parallel_reduce(Sum) with one thread: index order"""
+    return float(np.cumsum(a)[-1]) if len(a) else 0.0
+
+
+def gmres(matvec, rhs, x0, max_iters, tol):
+    """Gmres::solve (linear_algebra/gmres.cpp:119-182) with compute_r0_ (:11-20) and
+    apply_rotations_to_hessenberg_ (:22-74: full (j+2)^2 matrix products on the host, kept as such); dot / norm2
+    summed in index order.  -> (x, success, n_iters, relative residual)"""
+    m = max_iters
+    Q0, Q1, Om = np.eye(m + 1), np.eye(m + 1), np.eye(m + 1)
+    H0, H1 = np.zeros((m + 1, m + 1)), np.zeros((m + 1, m + 1))
+    g0, g1 = np.zeros(m + 1), np.zeros(m + 1)
+    x = np.array(x0, dtype=np.float64)
+    r0 = rhs - matvec(x)
+    beta = np.sqrt(_seqsum(r0 * r0))
+    if beta < tol:
+        return x, True, 0, beta
+    g0[0] = beta
+    v = r0 * (1.0 / beta)
+    V = [v.copy()]
+    success, n_iters, rel = False, 0, beta
+
+    def gemm(A, B):                                              # dense_linear_algebra.h:262-279
+        out = np.zeros((A.shape[0], B.shape[1]))
+        for r in range(A.shape[0]):
+            for c in range(B.shape[1]):
+                dot = 0.0
+                for i in range(A.shape[1]):
+                    dot += A[r, i] * B[i, c]
+                out[r, c] = dot
+        return out
+
+    def gemv(A, xv):                                             # :244-260
+        out = np.zeros(A.shape[0])
+        for r in range(A.shape[0]):
+            dot = 0.0
+            for c in range(A.shape[1]):
+                dot += A[r, c] * xv[c]
+            out[r] = dot
+        return out
+
+    for j in range(m):
+        w = matvec(v)
+        for i in range(j + 1):
+            H0[i, j] = _seqsum(w * V[i])
+            w = w + V[i] * (-H0[i, j])
+        H0[j + 1, j] = np.sqrt(_seqsum(w * w))
+        v = w * (1.0 / H0[j + 1, j])
+        V.append(v.copy())
+        if j != 0:
+            H0[:j + 1, j] = gemv(Q0[:j + 1, :j + 1], H0[:j + 1, j].copy())
+        Om[...] = np.eye(m + 1)
+        denom = np.sqrt(H0[j, j] * H0[j, j] + H0[j + 1, j] * H0[j + 1, j])
+        si, ci = H0[j + 1, j] / denom, H0[j, j] / denom
+        Om[j, j], Om[j, j + 1], Om[j + 1, j], Om[j + 1, j + 1] = ci, si, -si, ci
+        k = j + 2
+        H1[:k, :k] = gemm(Om[:k, :k], H0[:k, :k])
+        g1[:k] = gemv(Om[:k, :k], g0[:k])
+        Q1[:k, :k] = Om[:k, :k] if j == 0 else gemm(Om[:k, :k], Q0[:k, :k])
+        g0[:k] = g1[:k]
+        Q0[:k, :k] = Q1[:k, :k]
+        H0[:k, :k] = H1[:k, :k]
+        residual = abs(g0[j + 1])
+        rel, n_iters = residual / beta, j + 1
+        if residual < tol * beta:
+            success = True
+            break
+    nv = n_iters
+    ym = np.zeros(nv)                                            # upper_triangular_solve (:280-297)
+    ym[nv - 1] = g0[nv - 1] / H0[nv - 1, nv - 1]
+    for i in range(nv - 2, -1, -1):
+        s = g0[i]
+        for jj in range(i + 1, nv):
+            s -= H0[i, jj] * ym[jj]
+        ym[i] = s / H0[i, i]
+    w = np.zeros_like(x)
+    for c in range(nv):                                          # gemv(V, ym, w): row-wise, columns in order
+        w = w + V[c] * ym[c]
+    return x + w * 1.0, success, n_iters, rel
+
+
+def steady_state(g, config, prim0):
+    """Solver::solve driving SteadyState::take_step -> Jfnk::step (solvers/steady_state.cpp:47-170,222-300,
+    solvers/jfnk.cpp:25-93) with the unpreconditioned Gmres: the matrix-vector product is one dual-number residual
+    evaluation.  -> (final primitive state (real), steps taken, relative global residual)"""
+    sc = config["solver"]
+    ls = sc["linear_solver"]
+    if ls["type"] != "gmres":
+        raise NotImplementedError("linear solver " + ls["type"])
+    gm, dim = config["gas_model"], g.dim
+    n, nc = g.n_cells, g.dim + 2
+    viscous = bool(config["viscous_flux"]["enabled"])
+    fs = Dual(np.array(prim0, dtype=np.float64))
+    cq = primatives_to_conserved(fs, dim)
+
+    def residual(fs_in):
+        d, fs_out, inter = compute_dudt(g, config, fs_in, True)
+        ff = inter.get("face_fs")
+        return d, fs_out, (None if ff is None else (ff[0].re, ff[1].re))
+
+    def norms_of(d):
+        return l2_norms(d.re, dim)
+
+    res, fs, face_fs = residual(fs)                              # Jfnk::initialise: eval_rhs
+    rhs = res.re.reshape(-1).copy()
+    norms = norms_of(res)
+    init = norms.copy()
+    cflc = sc["cfl"]
+    prev_cfl, prev_res = float(cflc.get("start_cfl", 0.0)), 1.0
+    steps = 0
+    for step in range(int(sc["max_steps"])):
+        stable = estimate_dt(g, config, fs.re, face_fs if viscous else None)
+        if cflc["type"] == "residual_based":                     # ResidualBasedCfl::eval (cfl.cpp:57-70)
+            t = norms[0] / init[0]
+            if t > float(cflc["growth_threshold"]):
+                prev_res, cfl = t, prev_cfl
+            else:
+                new = prev_cfl * np.power(prev_res / t, float(cflc["power"]))
+                new = float(cflc["max_cfl"]) if float(cflc["max_cfl"]) < new else new          # Ibis::min(new, max_cfl)
+                new = new if float(cflc["start_cfl"]) < new else float(cflc["start_cfl"])      # Ibis::max(start_cfl, new)
+                prev_res, prev_cfl, cfl = t, new, new
+        else:
+            cfl = _cfl(cflc, float(step))
+        dt_star = cfl * stable
+
+        def matvec(vec):                                         # SteadyStateLinearisation::matrix_vector_product
+            cq_tmp = Dual(np.zeros(cq.re.shape))
+            cq_tmp.re[:n] = cq.re[:n]
+            cq_tmp.du[:n] = vec.reshape(n, nc)
+            with np.errstate(all="ignore"):
+                fs_tmp = conserved_to_primatives(cq_tmp, dim, gm)
+            d = compute_dudt(g, config, fs_tmp, True)[0]
+            return 1 / dt_star * vec - d.du.reshape(-1)
+
+        dU, ok, iters, rel = gmres(matvec, rhs, np.zeros(n * nc), int(ls["max_iters"]), float(ls["tol"]))
+        cq.re[:n] += dU.reshape(n, nc)                           # Jfnk::apply_update_
+        cq.du[:n] = 0.0
+        with np.errstate(all="ignore"):
+            fs = conserved_to_primatives(cq, dim, gm)
+        res, fs, face_fs = residual(fs)
+        rhs = res.re.reshape(-1).copy()
+        norms = norms_of(res)
+        steps += 1
+        if count_bad_cells(g, fs.re) > 0:
+            break
+        if step >= int(sc["max_steps"]) - 1 or norms[0] / init[0] < float(sc["tolerance"]):
+            break
+    return fs.re, steps, norms[0] / init[0]

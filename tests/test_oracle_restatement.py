@@ -185,3 +185,21 @@ def test_restatement_moving_grid_on_dual_numbers(name):
         d, _, _ = restatement.compute_dudt(g, config, dprim, allow, vertex_vel=vvel, cq=cq)
         parity.assert_close(d.re, gold["dual_dudt_re" + sfx], S, f"{name}: moving dual re{sfx}", exact)
         parity.assert_close(d.du, gold["dual_dudt_du" + sfx], 1e-3 * S, f"{name}: moving dual du{sfx}", exact)
+
+
+@pytest.mark.parametrize("name", ["steady_quad2d", "steady_quad2d_cflux", "steady_box3d", "steady_wedge2d"])
+def test_restatement_steady_solver_equals_reference_snapshot(name):
+    """JFNK + GMRES restated (dual-number matrix-vector products, Arnoldi, the reference's Givens bookkeeping)
+    against the final snapshot of the reference's own steady run, north-star tolerance 1e-9"""
+    import solve_cases as sc
+    mesh, config, g, prim0, snap = sc.build_solve_case(name)
+    gold = dict(np.load(os.path.join(parity.GOLDEN, "solve_" + name + ".npz")))
+    flow, steps, rel = restatement.steady_state(g, config, prim0)
+    n = g.n_cells
+    assert steps - 1 == int(float(gold["final_time"]))
+    vscale = np.sqrt(flow[:n, 4] ** 2 + flow[:n, 5] ** 2 + flow[:n, 6] ** 2).max()
+    for k, col in (("T", 2), ("p", 1), ("vx", 4), ("vy", 5), ("vz", 6)):
+        if "final_" + k in gold:
+            b = gold["final_" + k]
+            scale = vscale if k.startswith("v") else np.abs(b).max()
+            assert np.abs(flow[:n, col] - b).max() <= 1e-9 * scale, (name, k, np.abs(flow[:n, col] - b).max() / scale)
