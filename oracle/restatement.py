@@ -22,8 +22,8 @@ gradients, Sutherland / constant-Prandtl transport); the surface integral; the m
 velocities, relative fluxes, geometric conservation law); estimate_dt with its viscous term, count_bad_cells,
 L2 norms, primitive <-> conserved -- all of it on dual numbers too (oracle/dualnum.py: one exact Jacobian-vector
 product direction of the steady solver); and the solvers: Solver::solve + RungeKutta on a static grid (bit for bit) and SteadyState / Jfnk /
-Gmres with dual-number matrix-vector products (1e-9), held to the final snapshots of the reference's own runs
-(tests/golden/solve_*.npz).  Not covered (use oracle/_ref): vertex motion / geometry recomputation, FGMRES.
+Gmres / FGmres with dual-number matrix-vector products (1e-9), held to the final snapshots of the reference's own runs
+(tests/golden/solve_*.npz).  Not covered (use oracle/_ref): vertex motion / geometry recomputation.
 """
 import numpy as np
 
@@ -775,11 +775,13 @@ def _seqsum(a):
     return float(np.cumsum(a)[-1]) if len(a) else 0.0
 
 
-def gmres(matvec, rhs, x0, max_iters, tol):
+def gmres(matvec, rhs, x0, max_iters, tol, precond=None):
     """Gmres::solve (linear_algebra/gmres.cpp:119-182) with compute_r0_ (:11-20) and
     apply_rotations_to_hessenberg_ (:22-74: full (j+2)^2 matrix products on the host, kept as such); dot / norm2
-    summed in index order.  -> (x, success, n_iters, relative residual)"""
-    m = max_iters
+    summed in index order.  With precond (v -> z, an inner Gmres on the preconditioner system) it is
+    FGmres::solve (:234-303): w = A z_j, and the update is built from the z_j.
+    -> (x, success, n_iters, relative residual)"""
+    m = min(max_iters, len(rhs))
     Q0, Q1, Om = np.eye(m + 1), np.eye(m + 1), np.eye(m + 1)
     H0, H1 = np.zeros((m + 1, m + 1)), np.zeros((m + 1, m + 1))
     g0, g1 = np.zeros(m + 1), np.zeros(m + 1)
@@ -791,6 +793,7 @@ def gmres(matvec, rhs, x0, max_iters, tol):
     g0[0] = beta
     v = r0 * (1.0 / beta)
     V = [v.copy()]
+    Z = []
     success, n_iters, rel = False, 0, beta
 
     def gemm(A, B):                                              # dense_linear_algebra.h:262-279
@@ -813,7 +816,12 @@ def gmres(matvec, rhs, x0, max_iters, tol):
         return out
 
     for j in range(m):
-        w = matvec(v)
+        if precond is not None:
+            z = precond(v)
+            Z.append(z.copy())
+            w = matvec(z)
+        else:
+            w = matvec(v)
         for i in range(j + 1):
             H0[i, j] = _seqsum(w * V[i])
             w = w + V[i] * (-H0[i, j])
@@ -847,8 +855,9 @@ def gmres(matvec, rhs, x0, max_iters, tol):
             s -= H0[i, jj] * ym[jj]
         ym[i] = s / H0[i, i]
     w = np.zeros_like(x)
-    for c in range(nv):                                          # gemv(V, ym, w): row-wise, columns in order
-        w = w + V[c] * ym[c]
+    basis = V if precond is None else Z
+    for c in range(nv):                                          # gemv(V | Z, ym, w): row-wise, columns in order
+        w = w + basis[c] * ym[c]
     return x + w * 1.0, success, n_iters, rel
 
 
@@ -858,7 +867,7 @@ def steady_state(g, config, prim0):
     evaluation.  -> (final primitive state (real), steps taken, relative global residual)"""
     sc = config["solver"]
     ls = sc["linear_solver"]
-    if ls["type"] != "gmres":
+    if ls["type"] not in ("gmres", "fgmres"):
         raise NotImplementedError("linear solver " + ls["type"])
     gm, dim = config["gas_model"], g.dim
     n, nc = g.n_cells, g.dim + 2
@@ -896,16 +905,25 @@ def steady_state(g, config, prim0):
             cfl = _cfl(cflc, float(step))
         dt_star = cfl * stable
 
-        def matvec(vec):                                         # SteadyStateLinearisation::matrix_vector_product
+        def matvec(vec, allow=True):                             # SteadyStateLinearisation::matrix_vector_product
             cq_tmp = Dual(np.zeros(cq.re.shape))
             cq_tmp.re[:n] = cq.re[:n]
             cq_tmp.du[:n] = vec.reshape(n, nc)
             with np.errstate(all="ignore"):
                 fs_tmp = conserved_to_primatives(cq_tmp, dim, gm)
-            d = compute_dudt(g, config, fs_tmp, True)[0]
+            d = compute_dudt(g, config, fs_tmp, allow)[0]
             return 1 / dt_star * vec - d.du.reshape(-1)
 
-        dU, ok, iters, rel = gmres(matvec, rhs, np.zeros(n * nc), int(ls["max_iters"]), float(ls["tol"]))
+        if ls["type"] == "fgmres":
+            # the preconditioner is the same linearisation without reconstruction (steady_state.cpp:47-50), solved
+            # by an inner Gmres from a zero guess (gmres.cpp:258-262)
+            def precond(v):
+                return gmres(lambda x: matvec(x, False), v, np.zeros(n * nc), int(ls["max_preconditioner_iters"]),
+                             float(ls["preconditioner_tolerance"]))[0]
+            dU, ok, iters, rel = gmres(matvec, rhs, np.zeros(n * nc), int(ls["max_iters"]), float(ls["tolerance"]),
+                                       precond)
+        else:
+            dU, ok, iters, rel = gmres(matvec, rhs, np.zeros(n * nc), int(ls["max_iters"]), float(ls["tol"]))
         cq.re[:n] += dU.reshape(n, nc)                           # Jfnk::apply_update_
         cq.du[:n] = 0.0
         with np.errstate(all="ignore"):

@@ -187,7 +187,8 @@ def test_restatement_moving_grid_on_dual_numbers(name):
         parity.assert_close(d.du, gold["dual_dudt_du" + sfx], 1e-3 * S, f"{name}: moving dual du{sfx}", exact)
 
 
-@pytest.mark.parametrize("name", ["steady_quad2d", "steady_quad2d_cflux", "steady_box3d", "steady_wedge2d"])
+@pytest.mark.parametrize("name", ["steady_quad2d", "steady_quad2d_cflux", "steady_box3d", "steady_wedge2d",
+                                  "steady_plate_fgmres"])
 def test_restatement_steady_solver_equals_reference_snapshot(name):
     """JFNK + GMRES restated (dual-number matrix-vector products, Arnoldi, the reference's Givens bookkeeping)
     against the final snapshot of the reference's own steady run, north-star tolerance 1e-9"""
