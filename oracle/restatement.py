@@ -23,7 +23,7 @@ velocities, relative fluxes, geometric conservation law); estimate_dt with its v
 L2 norms, primitive <-> conserved -- all of it on dual numbers too (oracle/dualnum.py: one exact Jacobian-vector
 product direction of the steady solver); and the solvers: Solver::solve + RungeKutta on a static grid (bit for bit) and SteadyState / Jfnk /
 Gmres / FGmres with dual-number matrix-vector products (1e-9), held to the final snapshots of the reference's own runs
-(tests/golden/solve_*.npz).  Not covered (use oracle/_ref): vertex motion / geometry recomputation.
+(tests/golden/solve_*.npz), moving grids with the geometry recomputed every stage included.
 """
 import numpy as np
 
@@ -718,11 +718,72 @@ def _cfl(schedule, t):
     raise NotImplementedError("cfl schedule " + schedule["type"])
 
 
-def runge_kutta(g, config, prim0):
+def _area_of_triangle(pos, a, b, c):
+    """Ibis::area_of_triangle (grid/geom.h:30-45)"""
+    ab, ac = pos[b] - pos[a], pos[c] - pos[a]
+    cx = ab[:, 1] * ac[:, 2] - ab[:, 2] * ac[:, 1]
+    cy = ab[:, 2] * ac[:, 0] - ab[:, 0] * ac[:, 2]
+    cz = ab[:, 0] * ac[:, 1] - ab[:, 1] * ac[:, 0]
+    return 0.5 * np.sqrt(cx * cx + cy * cy + cz * cz)
+
+
+def compute_geometric_data(g, mesh, pos):
+    """GridBlock::compute_geometric_data (grid/grid.h:169-178) after the vertices moved to pos: interface centres
+    (interface.h:304-327) and areas (:257-302), cell centroids (cell.h:236-254) and volumes (cell.h:263-303,
+    geom.h:67-83), ghost-cell centres (grid.h:364-403).  The interface orientations are NOT recomputed, as in
+    the reference; the WLS r-factors follow from the centroids (they are recomputed on every evaluation here).
+    Rewrites the arrays of g in place."""
+    n = g.n_cells
+    fv, nv = np.asarray(g.face_vertices), np.asarray(g.face_nv)
+    acc = np.zeros((g.n_faces, 3))
+    for k in range(4):
+        acc = np.where((nv > k)[:, None], acc + pos[np.maximum(fv[:, k], 0)], acc)
+    g.face_centre = acc / nv[:, None].astype(np.float64)
+    v0, v1, v2, v3 = (np.maximum(fv[:, k], 0) for k in range(4))
+    d = pos[v1] - pos[v0]
+    line = np.sqrt(d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1] + d[:, 2] * d[:, 2])
+    tri = _area_of_triangle(pos, v0, v1, v2)
+    quad = _area_of_triangle(pos, v0, v1, v2) + _area_of_triangle(pos, v0, v2, v3)
+    g.face_area = np.where(nv == 2, line, np.where(nv == 3, tri, quad))
+    ct, cv = np.asarray(mesh.cell_types), np.asarray(mesh.cell_vertices)
+    ncv = (cv >= 0).sum(axis=1)
+    acc = np.zeros((n, 3))
+    for k in range(8):
+        acc = np.where((ncv > k)[:, None], acc + pos[np.maximum(cv[:, k], 0)], acc)
+    cen = np.array(g.cell_centroid)
+    cen[:n] = acc / ncv[:, None].astype(np.float64)
+    rag = _Ragged(g)
+    if g.dim == 2:
+        a, b, c, dd = (np.maximum(cv[:, k], 0) for k in range(4))
+        g.cell_volume = np.where(ct == 5, _area_of_triangle(pos, a, b, c),
+                                 _area_of_triangle(pos, a, b, c) + _area_of_triangle(pos, a, c, dd))
+    else:
+        vol = np.zeros(n)
+        fc, fn = g.face_centre, np.asarray(g.face_norm)
+        for j in range(rag.maxf):
+            m, f, out = rag.mask[:, j], rag.face[:, j], rag.out[:, j]
+            dot = fc[f, 0] * out * fn[f, 0] + fc[f, 1] * out * fn[f, 1] + fc[f, 2] * out * fn[f, 2]
+            vol = np.where(m, vol + dot * g.face_area[f], vol)
+        g.cell_volume = vol / 3.0
+    left, right = np.asarray(g.face_left), np.asarray(g.face_right)
+    for tag in sorted(g.tags):
+        f = np.asarray(g.tags[tag]["faces"], np.int64)
+        l, r = left[f], right[f]
+        valid, ghost = np.where(l < n, l, r), np.where(l < n, r, l)
+        dxyz = g.face_centre[f] - cen[valid]
+        cen[ghost] = g.face_centre[f] + dxyz
+    g.cell_centroid = cen
+
+
+def runge_kutta(g, config, prim0, mesh=None):
     """Solver::solve (solvers/solver.cpp:18-64) driving RungeKutta::initialise / estimate_dt / take_step / stop_now
-    (solvers/runge_kutta.cpp:82-119,131-203,258-262) on a static grid, time-based plotting off.  The stage arrays
-    k_[i] are ONE array in the reference (runge_kutta.cpp:49-50 copies one view handle into every slot), so
-    every k_[j] below is the most recent evaluation.  -> (final primitive state, t, steps taken)"""
+    (solvers/runge_kutta.cpp:82-119,131-203,258-262), time-based plotting off.  The stage arrays k_[i] are ONE
+    array in the reference (runge_kutta.cpp:49-50 copies one view handle into every slot), so every k_[j] below is
+    the most recent evaluation.  With grid.motion enabled (mesh = the su2.Su2Mesh of g; rigid_body_translation
+    driver) the vertices move: `init_vertex_pos_ = grid_.vertices().positions()` (:136) copies a view HANDLE and
+    vertex_vel_ is one array in every stage slot (:64-65), so every add_scaled_vector (:158,172,189) displaces
+    the grid's own vertices cumulatively, and the geometry is recomputed before every later stage and at the end
+    of the step (:178-180,194-196).  g is modified in place then.  -> (final primitive state, t, steps taken)"""
     import sys
     sc, gm, dim = config["solver"], config["gas_model"], g.dim
     a_rows, b = sc["butcher_tableau"]["a"], sc["butcher_tableau"]["b"]
@@ -733,34 +794,55 @@ def runge_kutta(g, config, prim0):
     dt = float(sc["dt_init"]) if sc["dt_init"] > 0 else sys.float_info.max
     t, max_time, max_step = 0.0, float(sc["max_time"]), int(sc["max_step"])
     viscous = bool(config["viscous_flux"]["enabled"])
+    motion = config["grid"].get("motion", {})
+    moving = bool(motion.get("enabled"))
+    if moving:
+        if motion["type"] != "rigid_body_translation":
+            raise NotImplementedError("grid motion driver " + motion["type"])
+        pos = np.array(mesh.vertices, dtype=np.float64)
+        vv = motion["velocity"]
+        vertex_vel = np.tile([float(vv["x"]), float(vv["y"]), float(vv["z"])], (len(pos), 1))
 
-    def evaluate(fs):
+    def evaluate(fs, cq_of_fs=None):
         """function_eval_: dudt over all rows (ghost rows stay zero), the ghost-filled state, face_fs"""
-        d, fs_out, inter = compute_dudt(g, config, fs, True)
+        if moving:
+            d, fs_out, inter = compute_dudt(g, config, fs, True, vertex_vel=vertex_vel, cq=cq_of_fs)
+        else:
+            d, fs_out, inter = compute_dudt(g, config, fs, True)
         full = np.zeros((len(fs), dim + 2))
         full[:g.n_cells] = d
         return full, fs_out, inter.get("face_fs")
 
-    k, flow, face_fs = evaluate(flow)                                               # initialise(): :93
+    k, flow, face_fs = evaluate(flow, cq)                                           # initialise(): :93
     steps = 0
     for step in range(max_step):
-        k, flow, face_fs = evaluate(flow)                                           # take_step: :143
+        k, flow, face_fs = evaluate(flow, cq)                                       # take_step: :143
         stable = estimate_dt(g, config, flow, face_fs if viscous else None)        # :108-119
         dt_startup = min(_cfl(sc["cfl"], t) * stable, 1.5 * dt)
         dt = min(dt_startup, max_time - t)
         for i in range(1, n_stages):
             k_tmp = cq + k * (a(i, 0) * dt)                                         # :155
+            if moving:
+                pos = pos + vertex_vel * (a(i, 0) * dt)                             # :157-160
             for j in range(1, i):
                 if a(i, j) < 1e-14:
                     continue
                 k_tmp = k_tmp + k * (a(i, j) * dt)                                  # :169
+                if moving:
+                    pos = pos + vertex_vel * (a(i, j) * dt)                         # :170-173
             with np.errstate(all="ignore"):
                 flow_tmp = conserved_to_primatives(k_tmp, dim, gm)                  # :177
-            k, _, face_fs = evaluate(flow_tmp)                                      # :181 (flow_tmp's ghosts are its own)
+            if moving:
+                compute_geometric_data(g, mesh, pos)                                # :178-180
+            k, _, face_fs = evaluate(flow_tmp, k_tmp)                               # :181 (flow_tmp's ghosts are its own)
         for i in range(n_stages):
             cq = cq + k * (float(b[i]) * dt)                                        # :185-186
+            if moving:
+                pos = pos + vertex_vel * (float(b[i]) * dt)                         # :188-190
         with np.errstate(all="ignore"):
             flow = conserved_to_primatives(cq, dim, gm)                             # :193
+        if moving:
+            compute_geometric_data(g, mesh, pos)                                    # :194-196
         t += dt
         steps += 1
         if count_bad_cells(g, flow) > 0:                                            # solver.cpp:38-43

@@ -55,14 +55,15 @@ def test_restatement_moving_grid_equals_compiled_reference(name):
         parity.assert_close(inter["face_vel"], gold["face_vel" + sfx], 1.0, f"{name}: face_vel{sfx}", True)
 
 
-@pytest.mark.parametrize("name", ["rk_wedge2d", "rk_box3d", "rk_quad2d_cflux", "rk_ffs2d", "rk_plate2d_viscous"])
+@pytest.mark.parametrize("name", ["rk_wedge2d", "rk_box3d", "rk_quad2d_cflux", "rk_ffs2d", "rk_plate2d_viscous",
+                                  "rk_quad2d_moving", "rk_box3d_moving"])
 def test_restatement_runge_kutta_equals_reference_snapshot(name):
     """the explicit solver restated (Solver::solve + RungeKutta, aliased stage arrays included) against the final
     snapshot of the reference's own run (tests/golden/solve_*.npz): bit for bit"""
     import solve_cases as sc
     mesh, config, g, prim0, snap = sc.build_solve_case(name)
     gold = dict(np.load(os.path.join(parity.GOLDEN, "solve_" + name + ".npz")))
-    flow, t, steps = restatement.runge_kutta(g, config, prim0)
+    flow, t, steps = restatement.runge_kutta(g, config, prim0, mesh)
     n = g.n_cells
     assert t == float(gold["final_time"])
     for k, col in (("T", 2), ("p", 1), ("vx", 4), ("vy", 5), ("vz", 6)):
