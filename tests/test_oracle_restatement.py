@@ -205,3 +205,60 @@ def test_restatement_steady_solver_equals_reference_snapshot(name):
             b = gold["final_" + k]
             scale = vscale if k.startswith("v") else np.abs(b).max()
             assert np.abs(flow[:n, col] - b).max() <= 1e-9 * scale, (name, k, np.abs(flow[:n, col] - b).max() / scale)
+
+
+_SWEEP = [
+    # mesh factory, dim, bcs factory, make_config kwargs, mach scale
+    (lambda s: su2_mod().box_hex(7, 6, 5, jitter=0.3, seed=s), 3, cases.box3_wall_bcs, dict(flux_calculator="hanel", limiter="unlimited"), 0.4),
+    (lambda s: su2_mod().box_hex(6, 7, 5, jitter=0.3, seed=s), 3, cases.box3_bcs, dict(flux_calculator="ldfss2", thermo_interpolator="rho_p"), 1.0),
+    (lambda s: su2_mod().box_hex(5, 5, 6, jitter=0.2, seed=s), 3, cases.box3_visc_bcs, dict(flux_calculator="rusanov", viscous=True, thermo_interpolator="rho_T"), 0.5),
+    (lambda s: su2_mod().mixed_3d(5), 3, cases.box3_wall_bcs, dict(flux_calculator="ausmdv", thermo_interpolator="rho_T"), 0.6),
+    (lambda s: su2_mod().box_tet(5), 3, cases.box3_bcs, dict(flux_calculator="rusanov"), 1.0),
+    (lambda s: su2_mod().box_quad(14, 11, jitter=0.3, seed=s, triangulate=True), 2, cases.quad2_sub_bcs, dict(flux_calculator="ausmdv"), 0.2),
+    (lambda s: su2_mod().box_quad(13, 9, jitter=0.3, seed=s), 2, cases.quad2_visc_bcs, dict(flux_calculator="ldfss2", viscous=True), 0.5),
+    (lambda s: su2_mod().box_quad(11, 12, jitter=0.25, seed=s), 2, cases.quad2_flux_visc_bcs, dict(flux_calculator="ausmdv", viscous=True, limiter="unlimited"), 0.5),
+]
+
+
+def su2_mod():
+    from ibis_b200 import su2
+    return su2
+
+
+@pytest.mark.parametrize("combo", range(len(_SWEEP)))
+@pytest.mark.parametrize("seed", [3, 11])
+def test_host_harness_equals_restatement_sweep(combo, seed):
+    """configurations and inputs no fixture stores (seeded jitter, seeded state; flux calculator x interpolator x
+    limiter x boundary mixes, viscous ones included): the product's kernel bodies through the C ABI (host harness)
+    against the restatement -- real residual, ghost fill, and the dual residual's real and dual parts; bit for bit
+    where inviscid, 1e-12 where Sutherland's pow enters"""
+    from dualnum import Dual
+    from emu_util import emu_lib
+    from ibis_b200 import config as cfg
+    from ibis_b200 import grid as gridmod
+    from ibis_b200.lib import Context
+    mesh_f, dim, bcs_f, kw, mach = _SWEEP[combo]
+    mesh = mesh_f(seed)
+    bcs = bcs_f()
+    config = cfg.make_config(dim, bcs, **kw)
+    g = gridmod.build_grid(mesh, list(bcs.keys()))
+    prim = cases.perturbed_state(g, dim, mach, seed=seed)
+    pdu = cases.dual_seed(prim, seed=seed + 1)
+    exact = not kw.get("viscous")
+    S = parity.flux_scale(g, prim, dim)
+    ctx = Context(g, config, lib_path=emu_lib())
+    fs, dq, fsd, dqd = ctx.fs_create(), ctx.cq_create(), ctx.fs_create(True), ctx.cq_create(True)
+    for allow in (True, False):
+        ctx.fs_upload(fs, prim)
+        ctx.compute_dudt(fs, dq, allow)
+        want, ghosts, _ = restatement.compute_dudt(g, config, prim, allow)
+        parity.assert_close(ctx.cq_download(dq)[:g.n_cells], want, S, f"combo {combo}: dudt (allow={allow})", exact)
+        parity.assert_close(ctx.fs_download(fs), ghosts, 1.0, f"combo {combo}: ghost fill", True)
+        ctx.fs_upload(fsd, prim, pdu)
+        ctx.compute_dudt(fsd, dqd, allow)
+        dr, dd = ctx.cq_download(dqd, dual=True)
+        wd = restatement.compute_dudt(g, config, Dual(prim, pdu), allow)[0]
+        parity.assert_close(dr[:g.n_cells], wd.re, S, f"combo {combo}: dual re (allow={allow})", exact)
+        parity.assert_close(dd[:g.n_cells], wd.du, 1e-3 * S, f"combo {combo}: dual du (allow={allow})",
+                            exact and kw["flux_calculator"] != "ldfss2")
+    ctx.close()
