@@ -12,7 +12,8 @@ import pytest
 import cases
 import parity
 
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import restatement  # noqa: E402
 
 COVERED = sorted(cases.CASES)             # every case of tests/cases.py
@@ -314,3 +315,50 @@ def test_host_solver_equals_restated_solver_sweep(combo):
     assert nsteps == steps or (combo == 1 and nsteps == 6 and rep["status"] == 1 and t < 0.0)
     a, b = out[:n], want[:n]
     assert ((a == b) | (np.isnan(a) & np.isnan(b))).all()
+
+
+@pytest.mark.parametrize("combo", [0, 1])
+def test_host_steady_solver_equals_restated_steady_solver(combo):
+    """JFNK / GMRES of the C++ host solver (host harness, dot products in index order) against the restated steady
+    solver on runs no fixture stores: 1e-9 of the field scale"""
+    import subprocess
+    import sys
+    code = r'''
+import sys
+sys.path[:0] = [%r, %r, %r]
+import numpy as np
+import cases, restatement, solve_cases as sc
+from emu_util import emu_host_lib, emu_lib
+from ibis_b200 import config as cfg, grid as gridmod, host, su2
+from ibis_b200.lib import Context
+combo = %d
+if combo == 0:
+    mesh, bcs, dim = su2.box_quad(9, 7, jitter=0.2, seed=4), cases.quad2_bcs(), 2
+    kw = dict(flux_calculator="ausmdv", solver=cfg.steady_state(cfl=4.0, max_steps=6, tolerance=1e-12,
+              linear_solver={"type": "gmres", "max_iters": 35, "tol": 1e-3}))
+else:
+    mesh, bcs, dim = su2.box_hex(4, 3, 4, jitter=0.15, seed=6), cases.box3_wall_bcs(), 3
+    kw = dict(flux_calculator="rusanov", thermo_interpolator="rho_p",
+              solver=cfg.steady_state(cfl={"type": "residual_based", "growth_threshold": 0.9, "power": 1.0, "start_cfl": 1.0,
+                                           "max_cfl": 50.0}, max_steps=5, tolerance=1e-12,
+                                      linear_solver={"type": "gmres", "max_iters": 30, "tol": 1e-3}))
+config = cfg.make_config(dim, bcs, **kw)
+g = gridmod.build_grid(mesh, list(bcs.keys()))
+full = cases.perturbed_state(g, dim, 1.0, seed=77 + combo)
+n = g.n_cells
+prim0 = sc.snapshot_state(g, full[:n, 2], full[:n, 1], full[:n, 4], full[:n, 5], full[:n, 6])
+ctx = Context(g, config, lib_path=emu_lib())
+out, rep = host.solve(ctx, config, prim0, host_lib=emu_host_lib())
+ctx.close()
+want, steps, rel = restatement.steady_state(g, config, prim0)
+assert rep["steps"] == steps, (rep["steps"], steps)
+vs = np.sqrt((want[:n, 4:7] ** 2).sum(axis=1)).max()
+for col in (1, 2, 4, 5, 6):
+    scale = vs if col >= 4 else np.abs(want[:n, col]).max()
+    err = np.abs(out[:n, col] - want[:n, col]).max() / scale
+    assert err <= 1e-9, (col, err)
+print("STEADY_SWEEP_OK", steps)
+''' % (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle"), combo)
+    env = dict(os.environ, IBIS_B200_ORDERED_DOT="1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "STEADY_SWEEP_OK" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
