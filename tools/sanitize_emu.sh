@@ -1,7 +1,7 @@
 #!/bin/bash
 # tools/sanitize_emu.sh -- host-side memory / UB check of the C-ABI layer (abi.cu, layout.h, grid_build.cu,
 # mesh_io.cu) and of every kernel body: builds the host-emulation harness with AddressSanitizer +
-# UndefinedBehaviorSanitizer and runs the CPU parity tests on it.  Last run (round 1): 97 tests, no report.
+# UndefinedBehaviorSanitizer and runs the CPU parity tests on it.  Last run (end of round 1): no report.
 set -e
 ROOT=$(cd "$(dirname "$0")/.." && pwd)
 OUT=${OUT:-/tmp/ibis_b200_asan}
@@ -18,10 +18,10 @@ emu_util.emu_lib = lambda: "$OUT/libibis_b200_emu.so"
 import pytest
 if __name__ == "__main__":
     t = "$ROOT/tests/"
-    sys.exit(pytest.main(["-x", "-q", "-p", "no:cacheprovider", "-m", "not gpu", "-k", "not gloo"] +
+    sys.exit(pytest.main(["-x", "-q", "-p", "no:cacheprovider", "-m", "not gpu", "-k", "not gloo and not host_solver and not host_steady"] +
                          [t + f for f in ("test_emu_parity.py", "test_boundary_actions.py", "test_grid_build.py",
                                           "test_moving_grid.py", "test_reference_kats.py", "test_decomposition.py",
-                                          "test_flow_io.py")]))
+                                          "test_flow_io.py", "test_oracle_restatement.py", "test_properties.py")]))
 PY
 ASAN=$(/usr/bin/g++ -print-file-name=libasan.so)
 UBSAN=$(/usr/bin/g++ -print-file-name=libubsan.so)
