@@ -6,6 +6,8 @@
 #include <stdio.h>
 #include <time.h>
 
+#include <string.h>
+
 #include <algorithm>
 #include <new>
 #include <string>
@@ -381,9 +383,9 @@ int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd_ref, con
     // tiles and the tile-owned interface numbering (layout.h)
     TileLayout TL;
     {
-        int T = 128;
+        int T = 64;
         if (const char* e = getenv("IBIS_B200_TILE")) T = atoi(e);
-        if (T != 64 && T != 128 && T != 256) T = 128;
+        if (T != 64 && T != 128) T = 64;
         const char* err = nullptr;
         int rrc = regroup_faces(R, T, TL, &err);
         if (rrc) return fail(nullptr, rrc, err ? err : "interface regrouping failed");
@@ -426,7 +428,7 @@ int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd_ref, con
     c->n_ghost = gd->n_ghost;
     c->n_total = n_total;
     c->n_faces = gd->n_faces;
-    c->cstride = pad_to(std::max<int64_t>(n_total, 1), 256);   // whole blocks of pass G' stay in bounds
+    c->cstride = pad_to(std::max<int64_t>(n_total, 1) + 256, 256);   // whole-tile bulk copies that start at any cell stay in bounds
     c->fstride = pad_to(std::max<int64_t>(gd->n_faces, 1), 32);
     const int64_t cs = c->cstride, fs = c->fstride;
 
@@ -731,6 +733,111 @@ int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd_ref, con
         UP2(tiles_early, di, tiles_early) UP2(tiles_late, di, tiles_late)
         UP2(out_off, di, out_off) UP2(out_slot, du16, out_slot) UP2(out_cell, di, out_cell) UP2(out_d, dd, out_d)
         g.n_out = n_out;
+        // ---- packed per-tile records of the pipelined sides path (fv_pipe.cu; layout in fv_bodies.h::GridDev) ----
+        g.t_wd = nullptr; g.t_grec = nullptr; g.t_frec = nullptr; g.f_frame6 = nullptr;
+        g.grec_stride = g.frec_stride = g.halo_cap = 0;
+        g.pipe_nf = max_faces < 3 ? 3 : max_faces;
+        // the kernels recompute the interface normal as cross(t1, t2), the reference's own formula
+        // (grid/interface.h:250): arrays that do not satisfy it bit for bit keep to the gather path
+        bool normals_exact = true;
+#pragma omp parallel for schedule(static) reduction(&& : normals_exact)
+        for (int64_t f = 0; f < gd->n_faces; f++) {
+            const double* a = gd->face_tan1 + 3 * f;
+            const double* b = gd->face_tan2 + 3 * f;
+            const double n[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+            if (memcmp(n, gd->face_norm + 3 * f, sizeof n) != 0) normals_exact = false;
+        }
+        if (!normals_exact) c->use_sides = false;
+        if (sides_path(c)) {
+            const int NFr = g.pipe_nf;
+            // neighbours of a tile's cells outside the tile: sorted, without duplicates
+            std::vector<int> halo_off(nt + 1, 0);
+            std::vector<std::vector<int>> halos(nt);
+#pragma omp parallel for schedule(dynamic, 64)
+            for (int b = 0; b < nt; b++) {
+                const int64_t c0 = TL.c0[b], c1 = TL.c0[b + 1];
+                std::vector<int>& h = halos[b];
+                for (int64_t i = c0; i < c1; i++)
+                    for (int j = 0; j < max_faces; j++) {
+                        if (cf_face[(size_t)j * cs + i] < 0) continue;
+                        const int nb = cf_nbr[(size_t)j * cs + i];
+                        if (nb < c0 || nb >= c1) h.push_back(nb);
+                    }
+                std::sort(h.begin(), h.end());
+                h.erase(std::unique(h.begin(), h.end()), h.end());
+            }
+            int halo_cap = 4;
+            for (int b = 0; b < nt; b++) halo_cap = std::max<int>(halo_cap, (int)halos[b].size());
+            halo_cap = (int)pad_to(halo_cap, 4);
+            if (T + halo_cap > NBR_LOCAL_MASK) { ibis_b200_destroy(c); return fail(nullptr, IBIS_B200_EINVAL, "tile halo too large"); }
+            g.halo_cap = halo_cap;
+            g.grec_stride = (int)pad_to(grec_bytes(NFr, T, halo_cap), 128);
+            g.frec_stride = (int)pad_to(frec_bytes(T), 128);
+            std::vector<unsigned char> grec((size_t)g.grec_stride * std::max(nt, 1), 0);
+#pragma omp parallel for schedule(dynamic, 64)
+            for (int b = 0; b < nt; b++) {
+                unsigned char* rec = &grec[(size_t)g.grec_stride * b];
+                unsigned short* nbr = reinterpret_cast<unsigned short*>(rec);
+                unsigned short* stg = nbr + (size_t)NFr * T;
+                int* hdr = reinterpret_cast<int*>(stg + (size_t)NFr * T);
+                int* info = hdr + 4;
+                int* hl = info + TILE_INFO;
+                const int64_t c0 = TL.c0[b], c1 = TL.c0[b + 1];
+                const std::vector<int>& h = halos[b];
+                for (int i = 0; i < T; i++)
+                    for (int j = 0; j < NFr; j++) {
+                        const int64_t cell = c0 + i;
+                        unsigned short e = (unsigned short)i, st = 0xFFFF;
+                        if (cell < c1 && j < max_faces) st = cf_stage[(size_t)j * cs + cell];
+                        if (st != 0xFFFF) {
+                            const int nb = cf_nbr[(size_t)j * cs + cell];
+                            int local;
+                            if (nb >= c0 && nb < c1) local = (int)(nb - c0);
+                            else local = T + (int)(std::lower_bound(h.begin(), h.end(), nb) - h.begin());
+                            e = (unsigned short)local;
+                            if (cf_out[(size_t)j * cs + cell] > 0) e |= NBR_LEFT_BIT;
+                            if (nb >= gd->n_cells) e |= NBR_GHOST_BIT;
+                        }
+                        nbr[(size_t)j * T + i] = e;
+                        stg[(size_t)j * T + i] = st;
+                    }
+                hdr[0] = (int)h.size(); hdr[1] = TL.nR[b]; hdr[2] = TL.n_own_left(b); hdr[3] = 0;
+                memcpy(info, &tile_info[(size_t)TILE_INFO * b], sizeof(int) * TILE_INFO);
+                for (size_t k = 0; k < h.size(); k++) hl[k] = h[k];
+                for (int k = (int)h.size(); k < halo_cap; k++) hl[k] = h.empty() ? (int)c0 : h[0];   // padding: any valid cell
+            }
+            std::vector<std::vector<int>>().swap(halos);
+            std::vector<unsigned char> frec((size_t)g.frec_stride * std::max(n_tiles, 1), 0);
+#pragma omp parallel for schedule(static)
+            for (int b = 0; b < n_tiles; b++) {
+                unsigned char* rec = &frec[(size_t)g.frec_stride * b];
+                double* rv = reinterpret_cast<double*>(rec);
+                double* sa = rv + T;
+                unsigned short* sl = reinterpret_cast<unsigned short*>(sa + (size_t)MAXF * T);
+                const int64_t c0 = TL.c0[b], c1 = TL.c0[b + 1];
+                for (int i = 0; i < T; i++) {
+                    const int64_t cell = c0 + i;
+                    rv[i] = cell < c1 ? vol[cell] : 1.0;
+                    for (int j = 0; j < MAXF; j++) {
+                        unsigned short s = 0xFFFF;
+                        double a = 0.0;
+                        if (cell < c1 && j < max_faces && cf_face[(size_t)j * cs + cell] >= 0) {
+                            s = cf_slot[(size_t)j * cs + cell];
+                            a = -fa[cf_face[(size_t)j * cs + cell]] * (double)cf_out[(size_t)j * cs + cell];
+                        }
+                        sl[(size_t)j * T + i] = s;
+                        sa[(size_t)j * T + i] = a;
+                    }
+                }
+            }
+            unsigned char* du8 = nullptr;
+            rc = upload_vec(c, grec, &du8);
+            if (rc) { ibis_b200_destroy(c); return fail(nullptr, rc, "grid upload failed"); }
+            g.t_grec = du8;
+            rc = upload_vec(c, frec, &du8);
+            if (rc) { ibis_b200_destroy(c); return fail(nullptr, rc, "grid upload failed"); }
+            g.t_frec = du8;
+        }
 #undef UP2
     }
     timer.lap("tile tables + upload");
@@ -747,6 +854,16 @@ int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd_ref, con
     g.cf_d = cfd;
     launch_wls_r(c, r);
     launch_cell_static(c, cfw, cfd);
+    if (g.t_grec) {
+        // the tile-major copies the pipelined kernels fetch with one bulk copy per tile
+        double *twd = nullptr, *fr6 = nullptr;
+        rc = dev_alloc_zero<double>(c, (int64_t)std::max(g.n_tiles_all, 1) * 2 * g.pipe_nf * 3 * g.tile, &twd);
+        if (!rc) rc = dev_alloc_zero<double>(c, (int64_t)6 * std::max<int64_t>(gd->n_faces, 1), &fr6);
+        if (rc) { ibis_b200_destroy(c); return fail(nullptr, rc, "out of device memory"); }
+        g.t_wd = twd;
+        g.f_frame6 = fr6;
+        launch_pack_pipe_tables(c, twd, fr6);
+    }
 
     // reductions
     c->n_red_blocks = 148 * 8;

@@ -143,6 +143,7 @@ template <typename S>
 void launch_bc(ibis_b200_ctx* c, const FvArgs<S>& A, int phase);
 void launch_wls_r(ibis_b200_ctx* c, double* r_out);
 void launch_cell_static(ibis_b200_ctx* c, double* w_out, double* d_out);   // cf_w, cf_d (after wls_r)
+void launch_pack_pipe_tables(ibis_b200_ctx* c, double* t_wd, double* f_frame6);   // tile-major cf_w / cf_d, t1 t2 frames
 template <typename S>
 void launch_grad_limit(ibis_b200_ctx* c, const FvArgs<S>& A, bool viscous_pass);
 template <typename S>

@@ -14,11 +14,11 @@ namespace ib {
 
 constexpr int MAXF = 6;       // faces per cell: hex 6, wedge/pyramid 5, tet/quad 4, tri 3
 // The interface-side arrays of the sides path: sideL[f][6], sideR[f][6] (rho p T vx vy vz of the left
-// / right state, written by pass G' every evaluation) and the static frame f_geom[f][10] (nx ny nz
-// t1x t1y t1z t2x t2y t2z area).  Bytes of one interface in shared memory: 12 S + 10 doubles.
+// / right state, written by pass G' every evaluation) and the static frame f_frame6[f][6] (t1x t1y t1z
+// t2x t2y t2z).  Bytes of one interface in shared memory: 12 S + 6 doubles.
 template <typename S>
 struct frec {
-    static constexpr int bytes = 12 * (int)sizeof(S) + 80;
+    static constexpr int bytes = 12 * (int)sizeof(S) + 48;
 };
 constexpr int TILE_INFO = 64;  // ints per tile descriptor (GridDev::tile_info): 12 header + 10 inline entries, 256 B
 constexpr int TILE_INLINE_ENT = 10;
@@ -107,6 +107,22 @@ struct GridDev {
     const int* out_cell;
     const double* out_d;
     long n_out;
+    // pipelined sides path (fv_pipe.cu): per-tile packed records, each fetched by ONE bulk copy.
+    //   t_wd     [tile][2 * pipe_nf * 3][tile]  WLS weights, then face offsets, of the tile's cells
+    //   t_grec   [tile], grec_stride bytes: u16 nbr[pipe_nf][tile] (tile-local index of the neighbour: < tile an own
+    //            cell, >= tile entry (index - tile) of the halo list; bit 14: this cell is the LEFT cell of the
+    //            interface, bit 15: the neighbour is a boundary ghost; an absent slot points at the cell itself) |
+    //            u16 stage[pipe_nf][tile] (cf_stage) | int hdr[4] = {n_halo, nR, n_own_l, -} | int tile_info[64] |
+    //            int halo[halo_cap] (cell ids of the neighbours outside the tile, no duplicates)
+    //   t_frec   [owned tile], frec_stride bytes: double vol[tile] | double sarea[6][tile] (-area * outsign, 0 for an
+    //            absent slot) | u16 slot[6][tile] (cf_slot)
+    //   f_frame6 [face * 6] t1x t1y t1z t2x t2y t2z: the normal is cross(t1, t2) as in the reference
+    //            (grid/interface.h:250, util/vector3.h:153-160) and is recomputed, bit for bit, in the kernels
+    const double* t_wd;
+    const unsigned char* t_grec;
+    const unsigned char* t_frec;
+    const double* f_frame6;
+    int grec_stride, frec_stride, halo_cap, pipe_nf;
     // NOTE cf_slot, cf_out and cf_d are always MAXF slots wide (absent slots: 0xFFFF / 0 / 0) so
     // that the tiled kernel can load all slots unconditionally; cf_face, cf_nbr, cf_w are
     // max_faces wide.
@@ -1142,27 +1158,6 @@ IBIS_HD void tile_cell_sum(const FvArgs<S>& A, int c, const CellFaces& F, const 
     if (DIM == 3) M::store(A.dudt[3], c, d_mz / vol);
     M::store(A.dudt[4], c, d_e / vol);
 }
-// local time step of cell c (finite_volume.cpp:145-180, inviscid) from the staged interface frames
-// frames[slot * 10 + k]: the same frames, in the same cell-face order, as local_dt_body reads
-template <typename S>
-IBIS_HD double tile_cell_dt(const FvArgs<S>& A, int c, const CellFaces& F, const double* frames) {
-    typedef mem<S> M;
-    const double vx = re(M::load(A.fs[F_VX], c)), vy = re(M::load(A.fs[F_VY], c)), vz = re(M::load(A.fs[F_VZ], c));
-    const double a = speed_of_sound(re(M::load(A.fs[F_T], c)), re(A.gas.R), re(A.gas.gamma));
-    double sr_c = 0.0;
-    const double sr_v = 0.0;
-#pragma unroll
-    for (int j = 0; j < MAXF; j++) {
-        if (F.slot[j] == 0xFFFF) continue;
-        const double* gm = frames + (long)F.slot[j] * 10;
-        const double area = gm[9];
-        const double dot = vx * gm[0] + vy * gm[1] + vz * gm[2];
-        const double sig_vel = fabs(dot) + a;
-        sr_c += sig_vel * area;
-    }
-    return F.vol / (sr_c + A.signal_factor * sr_v);
-}
-
 template <int DIM, typename S>
 IBIS_HD void tile_cell_body(const FvArgs<S>& A, int c, const S* st, long ss, long ks) {
     CellFaces F;
@@ -1239,44 +1234,10 @@ struct CellTables {
     }
 };
 
-// Pass G' splits a cell between two threads: half 0 does rho and the second thermodynamic variable
-// (and closes the state: rho p T), half 1 the velocity components.  NVH = variables of the half.
-// What a half gathers, issued before the staged tables are waited for:
-template <int NF, int NVH, typename S>
-struct HalfGather {
-    int nbr[NF];
-    int stage[NF];                // staging index of this cell's side of interface j, -1 if absent
-    bool left[NF];                // this cell is the left cell of interface j
-    S ui[NVH], un[NVH][NF];
-};
-
-template <int DIM, int NF, int HALF, typename S>
-IBIS_HD void grad_sides_gather(const FvArgs<S>& A, int c, HalfGather<NF, HALF == 0 ? 2 : 3, S>& G) {
-    typedef mem<S> M;
-    const GridDev& g = A.g;
-    const long cs = g.cstride;
-#pragma unroll
-    for (int j = 0; j < NF; j++) {
-        const int st = g.cf_stage[j * cs + c];
-        const int nb = g.cf_nbr[j * cs + c];
-        G.left[j] = g.cf_out[j * cs + c] > 0;                  // outsign +1: this cell is the left cell
-        G.stage[j] = st == 0xFFFF ? -1 : st;
-        G.nbr[j] = st == 0xFFFF ? c : nb;                      // absent slot: contributes w * (u_i - u_i) = 0
-    }
-    constexpr int NVH = HALF == 0 ? 2 : 3;
-#pragma unroll
-    for (int v = 0; v < NVH; v++) {
-        const S* src = A.rc.val[HALF == 0 ? v : 2 + v];
-        G.ui[v] = M::ldg(src, c);
-        if (DIM == 2 && HALF == 1 && v == 2) continue;         // vz: no gradient in 2-D
-#pragma unroll
-        for (int j = 0; j < NF; j++) G.un[v][j] = M::ldg(src, G.nbr[j]);
-    }
-}
-
 // one variable of one cell: gradient, limiter, extrapolation to the NF interfaces -> r[j]
-template <int DIM, int NF, int WSTRIDE, typename S>
-IBIS_HD void var_to_faces(const S& ui, const S* un, const CellTables<WSTRIDE>& T, double eps, bool limit, S* r) {
+// (TT: the static tables of the cell, W(j, k) WLS weights and D(j, k) face offsets)
+template <int DIM, int NF, typename TT, typename S>
+IBIS_HD void var_to_faces(const S& ui, const S* un, const TT& T, double eps, bool limit, S* r) {
     S gx = S(0.0), gy = S(0.0), gz = S(0.0), umin = ui, umax = ui;
 #pragma unroll
     for (int j = 0; j < NF; j++) {
@@ -1295,88 +1256,101 @@ IBIS_HD void var_to_faces(const S& ui, const S* un, const CellTables<WSTRIDE>& T
     for (int j = 0; j < NF; j++) r[j] = ui + phi * delta[j];   // linear_interpolate, convective_flux.cpp:243-255
 }
 
-// stg: the tile's staging buffer of side states, [index * 6 + k]; nR / n_own_l: see layout.h (the far
-// side of a boundary interface sits at a fixed distance from the near side in the staging buffer)
-template <int DIM, int NF, int HALF, int WSTRIDE, typename S>
-IBIS_HD void grad_sides_compute(const FvArgs<S>& A, const HalfGather<NF, HALF == 0 ? 2 : 3, S>& G,
-                                const CellTables<WSTRIDE>& T, int nR, int n_own_l, S* stg) {
-    typedef mem<S> M;
-    const bool limit = A.limiter_on != 0;
-    S r0[NF], r1[NF];
-    if (HALF == 0) {
-        var_to_faces<DIM, NF>(G.ui[0], G.un[0], T, A.eps, limit, r0);
-        var_to_faces<DIM, NF>(G.ui[1], G.un[1], T, A.eps, limit, r1);
-#pragma unroll
-        for (int j = 0; j < NF; j++) {
-            S rho = r0[j], p = S(0.0), Tj = S(0.0), e = S(0.0);
-            if (A.thermo == THERMO_RHO_P) p = r1[j];
-            else if (A.thermo == THERMO_RHO_T) Tj = r1[j];
-            else e = r1[j];
-            thermo_close(A.thermo, A.gas, rho, p, Tj, e);
-            if (G.stage[j] >= 0) {
-                S* q = stg + (long)G.stage[j] * 6;
-                q[0] = rho;
-                q[1] = p;
-                q[2] = Tj;
-            }
-        }
-    } else {
-        S r2[NF];
-        var_to_faces<DIM, NF>(G.ui[0], G.un[0], T, A.eps, limit, r0);
-        var_to_faces<DIM, NF>(G.ui[1], G.un[1], T, A.eps, limit, r1);
-        if (DIM == 3) {
-            var_to_faces<DIM, NF>(G.ui[2], G.un[2], T, A.eps, limit, r2);
-        } else {
-            // 2-D: vz has no gradient (convective_flux.cpp:206-208) and a unit limiter: value copied
-#pragma unroll
-            for (int j = 0; j < NF; j++) r2[j] = G.ui[2];
-        }
-#pragma unroll
-        for (int j = 0; j < NF; j++)
-            if (G.stage[j] >= 0) {
-                S* q = stg + (long)G.stage[j] * 6;
-                q[3] = r0[j];
-                q[4] = r1[j];
-                q[5] = r2[j];
-            }
-    }
-    // the far side of a boundary interface is the ghost cell itself: zero gradient, unit limiter
-    // (convective_flux.cpp:281-300), i.e. its values, closed thermodynamically like any other side
-#pragma unroll
-    for (int j = 0; j < NF; j++) {
-        if (G.stage[j] < 0 || G.nbr[j] < A.g.n_cells) continue;
-        const int nb = G.nbr[j];
-        const int far_idx = G.left[j] ? n_own_l + G.stage[j] + nR : G.stage[j] - n_own_l - nR;
-        S* q = stg + (long)far_idx * 6;
-        if (HALF == 0) {
-            S rho = M::load(A.rc.val[0], nb), p = S(0.0), Tg = S(0.0), e = S(0.0);
-            const S th2 = M::load(A.rc.val[1], nb);
-            if (A.thermo == THERMO_RHO_P) p = th2;
-            else if (A.thermo == THERMO_RHO_T) Tg = th2;
-            else e = th2;
-            thermo_close(A.thermo, A.gas, rho, p, Tg, e);
-            q[0] = rho;
-            q[1] = p;
-            q[2] = Tg;
-        } else {
-            q[3] = M::load(A.rc.val[2], nb);
-            q[4] = M::load(A.rc.val[3], nb);
-            q[5] = M::load(A.rc.val[4], nb);
-        }
-    }
+// ---- pass G' on the packed per-tile records (GridDev::t_wd / t_grec) ----
+// entry of the tile-local neighbour table
+constexpr int NBR_LOCAL_MASK = 0x3FFF, NBR_LEFT_BIT = 0x4000, NBR_GHOST_BIT = 0x8000;
+// a view of one tile's record in memory (global memory in the host emulation, shared memory on the device)
+struct GRec {
+    const unsigned short* nbr;     // [nf][T]
+    const unsigned short* stage;   // [nf][T]
+    const int* hdr;                // n_halo, nR, n_own_l, -
+    const int* info;               // the tile descriptor (tile_info), 64 ints
+    const int* halo;               // [halo_cap]
+};
+IBIS_HD GRec grec_view(const unsigned char* rec, int nf, int T) {
+    GRec R;
+    R.nbr = reinterpret_cast<const unsigned short*>(rec);
+    R.stage = R.nbr + (size_t)nf * T;
+    R.hdr = reinterpret_cast<const int*>(R.stage + (size_t)nf * T);
+    R.info = R.hdr + 4;
+    R.halo = R.info + TILE_INFO;
+    return R;
+}
+IBIS_HD int grec_bytes(int nf, int T, int halo_cap) { return 4 * nf * T + 16 + 4 * TILE_INFO + 4 * halo_cap; }
+
+// the thermodynamic pair (rho, second variable) extrapolated to one interface -> rho p T of the side record
+template <typename S>
+IBIS_HD void side_close_store(int thermo, const Gas<S>& gas, S rho, const S& th2, S* q) {
+    S p = S(0.0), Tj = S(0.0), e = S(0.0);
+    if (thermo == THERMO_RHO_P) p = th2;
+    else if (thermo == THERMO_RHO_T) Tj = th2;
+    else e = th2;
+    thermo_close(thermo, gas, rho, p, Tj, e);
+    q[0] = rho;
+    q[1] = p;
+    q[2] = Tj;
+}
+// staging index of the far side of a boundary interface (the ghost cell's own values): the far side
+// sits at a fixed distance from the near side in the tile's staging buffer (layout.h)
+IBIS_HD int far_stage_index(bool left, int stage, int nR, int n_own_l) {
+    return left ? n_own_l + stage + nR : stage - n_own_l - nR;
 }
 
-// host emulation form: one call per (cell, half) straight from the global tables
-template <int DIM, int NF, int HALF, typename S>
-IBIS_HD void grad_sides_body(const FvArgs<S>& A, int c, int nR, int n_own_l, S* stg) {
-    HalfGather<NF, HALF == 0 ? 2 : 3, S> G;
-    grad_sides_gather<DIM, NF, HALF>(A, c, G);
-    CellTables<0> T;
-    T.w = A.g.cf_w;
-    T.d = A.g.cf_d;
-    T.stride_rt = A.g.cstride;
-    T.idx = c;
-    grad_sides_compute<DIM, NF, HALF, 0>(A, G, T, nR, n_own_l, stg);
+// all five variables of tile-local cell i, one after the other: the host emulation of pass G' (the device kernel
+// gives every (cell, variable) its own thread, fv_pipe.cu, with the same calls).  sv = the tile's state values
+// [5][svs]: own cells at [0, T), halo-list entries from T on.  wd = the tile's slice of t_wd.
+template <int DIM, int NF, typename S>
+IBIS_HD void pipe_grad_cell(const FvArgs<S>& A, const double* wd, const GRec& R, int T, int i, const S* sv, int svs, S* stg) {
+    const bool limit = A.limiter_on != 0;
+    CellTables<0> Tb;
+    Tb.w = wd;
+    Tb.d = wd + (size_t)NF * 3 * T;
+    Tb.stride_rt = T;
+    Tb.idx = i;
+    const int nR = R.hdr[1], n_own_l = R.hdr[2];
+    int nl[NF], st[NF];
+    bool left[NF], ghost[NF];
+#pragma unroll
+    for (int j = 0; j < NF; j++) {
+        const int e = R.nbr[j * T + i];
+        nl[j] = e & NBR_LOCAL_MASK;
+        left[j] = (e & NBR_LEFT_BIT) != 0;
+        ghost[j] = (e & NBR_GHOST_BIT) != 0;
+        st[j] = R.stage[j * T + i];
+    }
+    S r[5][NF];
+#pragma unroll
+    for (int v = 0; v < 5; v++) {
+        const S ui = sv[v * svs + i];
+        if (DIM == 2 && v == 4) {
+            // 2-D: vz has no gradient (convective_flux.cpp:206-208) and a unit limiter: value copied
+#pragma unroll
+            for (int j = 0; j < NF; j++) r[v][j] = ui;
+            continue;
+        }
+        S un[NF];
+#pragma unroll
+        for (int j = 0; j < NF; j++) un[j] = sv[v * svs + nl[j]];
+        var_to_faces<DIM, NF>(ui, un, Tb, A.eps, limit, r[v]);
+    }
+#pragma unroll
+    for (int j = 0; j < NF; j++) {
+        if (st[j] == 0xFFFF) continue;
+        S* q = stg + (long)st[j] * 6;
+        side_close_store(A.thermo, A.gas, r[0][j], r[1][j], q);
+        q[3] = r[2][j];
+        q[4] = r[3][j];
+        q[5] = r[4][j];
+        if (ghost[j]) {
+            // the far side of a boundary interface is the ghost cell itself: zero gradient, unit limiter
+            // (convective_flux.cpp:281-300), i.e. its values, closed thermodynamically like any other side
+            S* f = stg + (long)far_stage_index(left[j], st[j], nR, n_own_l) * 6;
+            side_close_store(A.thermo, A.gas, sv[0 * svs + nl[j]], sv[1 * svs + nl[j]], f);
+            f[3] = sv[2 * svs + nl[j]];
+            f[4] = sv[3 * svs + nl[j]];
+            f[5] = sv[4 * svs + nl[j]];
+        }
+    }
 }
 
 // The bulk transfers of a tile (layout.h).  Transfer q of tile b moves `count` interfaces starting
@@ -1424,11 +1398,17 @@ IBIS_HD TileXfer tile_load_xfer(const GridDev& g, int b, int q) {
     return x;
 }
 
-// pass F', one interface: L, R = its side states, gm = its frame (shared memory on the device,
-// the global arrays in the host emulation); out[k * ks], k = 0..4 <- flux in the global frame,
-// k = 5 <- area.  out may alias L: everything is read before anything is written.
+// pass F', one interface: Ls, Rs = its side states, fr = its frame t1 t2 (shared memory on the device, the
+// global arrays in the host emulation); out[0..4] <- flux in the global frame.  out may alias Ls: everything is
+// read before anything is written.  The normal is cross(t1, t2) as the reference computes it
+// (grid/interface.h:250, util/vector3.h:153-160).
+IBIS_HD void frame_normal(const double* fr, double& nx, double& ny, double& nz) {
+    nx = fr[1] * fr[5] - fr[2] * fr[4];
+    ny = fr[2] * fr[3] - fr[0] * fr[5];
+    nz = fr[0] * fr[4] - fr[1] * fr[3];
+}
 template <int DIM, int FLUX, typename S>
-IBIS_HD void flux_from_sides(const FvArgs<S>& A, const S* Ls, const S* Rs, const double* gm, S* out, long ks) {
+IBIS_HD void flux_from_sides6(const FvArgs<S>& A, const S* Ls, const S* Rs, const double* fr, S* out) {
     typedef mem<S> M;
     Side<S> L, R_;
     M::ld2(Ls, 0, L.rho, L.p);
@@ -1439,12 +1419,13 @@ IBIS_HD void flux_from_sides(const FvArgs<S>& A, const S* Ls, const S* Rs, const
     M::ld2(Rs, 4, R_.v, R_.w);
     L.e = S(0.0);
     R_.e = S(0.0);
-    double nx, ny, nz, t1x, t1y, t1z, t2x, t2y, t2z, area;
-    mem<double>::ld2(gm, 0, nx, ny);
-    mem<double>::ld2(gm, 2, nz, t1x);
-    mem<double>::ld2(gm, 4, t1y, t1z);
-    mem<double>::ld2(gm, 6, t2x, t2y);
-    mem<double>::ld2(gm, 8, t2z, area);
+    double t1x, t1y, t1z, t2x, t2y, t2z;
+    mem<double>::ld2(fr, 0, t1x, t1y);
+    mem<double>::ld2(fr, 2, t1z, t2x);
+    mem<double>::ld2(fr, 4, t2y, t2z);
+    const double nx = t1y * t2z - t1z * t2y;
+    const double ny = t1z * t2x - t1x * t2z;
+    const double nz = t1x * t2y - t1y * t2x;
     {
         const S x = L.u * nx + L.v * ny + L.w * nz;           // util/vector3.cpp:142-153
         const S y = L.u * t1x + L.v * t1y + L.w * t1z;
@@ -1460,12 +1441,72 @@ IBIS_HD void flux_from_sides(const FvArgs<S>& A, const S* Ls, const S* Rs, const
     Flux5<S> F = flux_calc<FLUX>(L, R_, A.gas, A.delta);
     const S px = F.mx, py = F.my;
     const S pz = (DIM == 3) ? F.mz : S(0.0);
-    out[0 * ks] = F.mass;                                     // convective_flux.cpp:148-164
-    out[1 * ks] = px * nx + py * t1x + pz * t2x;
-    out[2 * ks] = px * ny + py * t1y + pz * t2y;
-    out[3 * ks] = px * nz + py * t1z + pz * t2z;
-    out[4 * ks] = F.energy;
-    out[5 * ks] = S(area);
+    out[0] = F.mass;                                          // convective_flux.cpp:148-164
+    out[1] = px * nx + py * t1x + pz * t2x;
+    out[2] = px * ny + py * t1y + pz * t2y;
+    out[3] = px * nz + py * t1z + pz * t2z;
+    out[4] = F.energy;
+}
+
+// the per-tile cell record of pass F' (GridDev::t_frec)
+struct FRec {
+    const double* vol;             // [T]
+    const double* sarea;           // [6][T]  -area * outsign of the cell's face j
+    const unsigned short* slot;    // [6][T]  flux slot of the cell's face j in the tile, 0xFFFF past the last face
+};
+IBIS_HD FRec frec_view(const unsigned char* rec, int T) {
+    FRec R;
+    R.vol = reinterpret_cast<const double*>(rec);
+    R.sarea = R.vol + T;
+    R.slot = reinterpret_cast<const unsigned short*>(R.sarea + (size_t)MAXF * T);
+    return R;
+}
+IBIS_HD int frec_bytes(int T) { return T * (8 + 8 * MAXF + 2 * MAXF); }
+
+// flux_surface_integral of tile-local cell i (global cell c) from the staged fluxes st[slot * 6 + k]
+// (finite_volume.cpp:221-256): same products, same order over the cell's faces as tile_cell_sum
+template <int DIM, typename S>
+IBIS_HD void pipe_cell_sum(const FvArgs<S>& A, int c, int i, int T, const FRec& R, const S* st) {
+    typedef mem<S> M;
+    S d_mass = S(0.0), d_mx = S(0.0), d_my = S(0.0), d_mz = S(0.0), d_e = S(0.0);
+#pragma unroll
+    for (int j = 0; j < MAXF; j++) {
+        const int sl = R.slot[j * T + i];
+        if (sl == 0xFFFF) continue;
+        const S* q = st + (long)sl * 6;
+        const double area = R.sarea[j * T + i];
+        d_mass += q[0] * area;
+        d_mx += q[1] * area;
+        d_my += q[2] * area;
+        if (DIM == 3) d_mz += q[3] * area;
+        d_e += q[4] * area;
+    }
+    const S vol = S(R.vol[i]);
+    M::store(A.dudt[0], c, d_mass / vol);
+    M::store(A.dudt[1], c, d_mx / vol);
+    M::store(A.dudt[2], c, d_my / vol);
+    if (DIM == 3) M::store(A.dudt[3], c, d_mz / vol);
+    M::store(A.dudt[4], c, d_e / vol);
+}
+// local time step of the cell (finite_volume.cpp:145-180, inviscid) from the tile's frames[slot * 6 + k]:
+// the same normals and areas, in the same cell-face order, as local_dt_body reads
+IBIS_HD double pipe_cell_dt(double vx, double vy, double vz, double Tc, double gas_R, double gamma, double signal_factor,
+                            int i, int T, const FRec& R, const double* frames) {
+    const double a = speed_of_sound(Tc, gas_R, gamma);
+    double sr_c = 0.0;
+    const double sr_v = 0.0;
+#pragma unroll
+    for (int j = 0; j < MAXF; j++) {
+        const int sl = R.slot[j * T + i];
+        if (sl == 0xFFFF) continue;
+        double nx, ny, nz;
+        frame_normal(frames + (long)sl * 6, nx, ny, nz);
+        const double area = fabs(R.sarea[j * T + i]);
+        const double dot = vx * nx + vy * ny + vz * nz;
+        const double sig_vel = fabs(dot) + a;
+        sr_c += sig_vel * area;
+    }
+    return R.vol[i] / (sr_c + signal_factor * sr_v);
 }
 
 // ---------------------------------------------------------------------------------------

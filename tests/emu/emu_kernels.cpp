@@ -123,40 +123,67 @@ void launch_residual(ibis_b200_ctx* c, const FvArgs<S>& A) {
 template void launch_residual<double>(ibis_b200_ctx*, const FvArgs<double>&);
 template void launch_residual<dual>(ibis_b200_ctx*, const FvArgs<dual>&);
 
-// pass G' tile by tile as the thread block runs it: both halves of every cell into the staging
-// buffer, then the tile's store transfers (the bulk stores of the device kernel) as memcpy
+// tile-major copies of the static tables, as the device pack kernels write them (fv_pipe.cu)
+void launch_pack_pipe_tables(ibis_b200_ctx* c, double* t_wd, double* fr6) {
+    const GridDev& g = c->g;
+    const int T = g.tile, NT = g.pipe_nf * 3;
+    for (int cell = 0; cell < g.n_grad; cell++) {
+        const bool owned = cell < g.n_owned;
+        const int tile = owned ? cell / T : g.n_tiles + (cell - g.n_owned) / T;
+        const int i = owned ? cell % T : (cell - g.n_owned) % T;
+        double* dst = t_wd + (size_t)tile * 2 * NT * T + i;
+        for (int r = 0; r < NT; r++) {
+            dst[(size_t)r * T] = r < g.max_faces * 3 ? g.cf_w[(size_t)r * g.cstride + cell] : 0.0;
+            dst[(size_t)(NT + r) * T] = g.cf_d[(size_t)r * g.cstride + cell];
+        }
+    }
+    for (int f = 0; f < g.n_faces; f++)
+        for (int k = 0; k < 3; k++) {
+            fr6[(size_t)f * 6 + k] = g.f_t1[(size_t)k * g.fstride + f];
+            fr6[(size_t)f * 6 + 3 + k] = g.f_t2[(size_t)k * g.fstride + f];
+        }
+    c->launches++;
+}
+
+// pass G' tile by tile, on the packed per-tile records the device kernel stages: the state of the tile's own
+// cells and of its halo list, every cell's five variables into the staging buffer, then the tile's store
+// transfers (the bulk stores of the device kernel) as memcpy
 template <typename S>
 void launch_grad_sides(ibis_b200_ctx* c, const FvArgs<S>& A, int which) {
     const GridDev& g = A.g;
     const int* list = which == 1 ? g.tiles_early : which == 2 ? g.tiles_late : nullptr;
     const int n_list = which == 1 ? g.n_early : which == 2 ? g.n_late : g.n_tiles_all;
+    const int T = g.tile, NF = g.pipe_nf, svs = T + g.halo_cap;
 #pragma omp parallel
     {
-        std::vector<S> stg((size_t)6 * std::max(g.stage_cap, 1));
+        std::vector<S> stg((size_t)6 * std::max(g.stage_cap, 1)), sv((size_t)5 * svs);
 #pragma omp for
         for (int k = 0; k < n_list; k++) {
             const int t = list ? list[k] : k;
-            const int* ti = g.tile_info + TILE_INFO * t;
-            const int nR = ti[4], n_own_l = tile_n_own_left(g, t);
-            for (int i = ti[0]; i < ti[0] + ti[1]; i++) {
-#define GS(D, NFV)                                                        \
-    grad_sides_body<D, NFV, 0>(A, i, nR, n_own_l, stg.data());            \
-    grad_sides_body<D, NFV, 1>(A, i, nR, n_own_l, stg.data());
-#define GS_NF(D)                                                          \
-    switch (g.max_faces) {                                                \
-        case 6: GS(D, 6) break;                                           \
-        case 5: GS(D, 5) break;                                           \
-        case 4: GS(D, 4) break;                                           \
-        default: GS(D, 3) break;                                          \
+            const GRec R = grec_view(g.t_grec + (size_t)t * g.grec_stride, NF, T);
+            const double* wd = g.t_wd + (size_t)t * 2 * NF * 3 * T;
+            int c0, nc;
+            tile_cells(g, t, c0, nc);
+            for (int v = 0; v < 5; v++) {
+                for (int i = 0; i < nc; i++) sv[(size_t)v * svs + i] = A.rc.val[v][c0 + i];
+                for (int h = 0; h < R.hdr[0]; h++) sv[(size_t)v * svs + T + h] = A.rc.val[v][R.halo[h]];
+            }
+            for (int i = 0; i < nc; i++) {
+#define GS_NF(D)                                                                              \
+    switch (NF) {                                                                             \
+        case 6: pipe_grad_cell<D, 6>(A, wd, R, T, i, sv.data(), svs, stg.data()); break;      \
+        case 5: pipe_grad_cell<D, 5>(A, wd, R, T, i, sv.data(), svs, stg.data()); break;      \
+        case 4: pipe_grad_cell<D, 4>(A, wd, R, T, i, sv.data(), svs, stg.data()); break;      \
+        default: pipe_grad_cell<D, 3>(A, wd, R, T, i, sv.data(), svs, stg.data()); break;     \
     }
                 if (g.dim == 3) { GS_NF(3) } else { GS_NF(2) }
 #undef GS_NF
-#undef GS
             }
-            for (int q = 0; q < 2 + ti[7]; q++) {
+            const int n_own_l = R.hdr[2];
+            for (int q = 0; q < 2 + R.info[7]; q++) {
                 const TileXfer x = tile_store_xfer(g, t, q, n_own_l);
                 S* dst = (x.left ? A.sideL : A.sideR) + (long)x.f0 * 6;
-                for (long k = 0; k < (long)x.count * 6; k++) dst[k] = stg[(size_t)x.stage * 6 + k];
+                for (long e = 0; e < (long)x.count * 6; e++) dst[e] = stg[(size_t)x.stage * 6 + e];
             }
         }
     }
@@ -165,15 +192,16 @@ void launch_grad_sides(ibis_b200_ctx* c, const FvArgs<S>& A, int which) {
 template void launch_grad_sides<double>(ibis_b200_ctx*, const FvArgs<double>&, int);
 template void launch_grad_sides<dual>(ibis_b200_ctx*, const FvArgs<dual>&, int);
 
-// pass F' tile by tile: the tile's load transfers, the fluxes in place, the cell sums
+// pass F' tile by tile: the tile's load transfers, the fluxes in place, the cell sums from the tile's cell record
 template <typename S>
 void launch_flux_tile(ibis_b200_ctx* c, const FvArgs<S>& A) {
     const GridDev& g = A.g;
+    const int T = g.tile;
 #pragma omp parallel
     {
         const size_t cap = std::max(g.tile_cap, 1);
         std::vector<S> stL(6 * cap), stR(6 * cap);
-        std::vector<double> stG(10 * cap);
+        std::vector<double> stF(6 * cap);
 #pragma omp for
         for (int t = 0; t < g.n_tiles; t++) {
             const int* ti = g.tile_info + TILE_INFO * t;
@@ -183,22 +211,26 @@ void launch_flux_tile(ibis_b200_ctx* c, const FvArgs<S>& A) {
                 for (long k = 0; k < (long)x.count * 6; k++) {
                     stL[(size_t)x.slot * 6 + k] = A.sideL[(long)x.f0 * 6 + k];
                     stR[(size_t)x.slot * 6 + k] = A.sideR[(long)x.f0 * 6 + k];
+                    stF[(size_t)x.slot * 6 + k] = g.f_frame6[(long)x.f0 * 6 + k];
                 }
-                for (long k = 0; k < (long)x.count * 10; k++) stG[(size_t)x.slot * 10 + k] = g.f_geom[(long)x.f0 * 10 + k];
                 n = std::max(n, x.slot + x.count);
             }
 #define TILE_FLUX(D, F, O)                                                                          \
     for (int s = 0; s < n; s++)                                                                     \
-        flux_from_sides<D, F>(A, &stL[(size_t)s * 6], &stR[(size_t)s * 6], &stG[(size_t)s * 10], &stL[(size_t)s * 6], 1);
+        flux_from_sides6<D, F>(A, &stL[(size_t)s * 6], &stR[(size_t)s * 6], &stF[(size_t)s * 6], &stL[(size_t)s * 6]);
             EMU_FLUX_CALL(TILE_FLUX)
 #undef TILE_FLUX
-            for (int cell = ti[0]; cell < ti[0] + ti[1]; cell++) {
-                if (g.dim == 3) tile_cell_body<3>(A, cell, stL.data(), 6, 1);
-                else tile_cell_body<2>(A, cell, stL.data(), 6, 1);
+            const FRec Rc = frec_view(g.t_frec + (size_t)t * g.frec_stride, T);
+            int c0, nc;
+            tile_cells(g, t, c0, nc);
+            for (int i = 0; i < nc; i++) {
+                const int cell = c0 + i;
+                if (g.dim == 3) pipe_cell_sum<3>(A, cell, i, T, Rc, stL.data());
+                else pipe_cell_sum<2>(A, cell, i, T, Rc, stL.data());
                 if (A.dt_out) {
-                    CellFaces CF;
-                    tile_cell_load(g, cell, CF);
-                    const double d = tile_cell_dt<S>(A, cell, CF, stG.data());
+                    const double d = pipe_cell_dt(re(A.fs[F_VX][cell]), re(A.fs[F_VY][cell]), re(A.fs[F_VZ][cell]),
+                                                  re(A.fs[F_T][cell]), re(A.gas.R), re(A.gas.gamma), A.signal_factor, i, T,
+                                                  Rc, stF.data());
 #pragma omp critical
                     {
                         double cur;
