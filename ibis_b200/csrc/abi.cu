@@ -164,6 +164,7 @@ FvArgs<S> make_args(ibis_b200_ctx* c, Buffer* fs, Buffer* dudt, bool allow_recon
         }
     }
     A.dt_out = nullptr;
+    A.pipe_dbg = c->d_pipe_dbg;
     A.face_T = c->face_T;
     A.face_vel = nullptr;              // set by the moving-grid evaluation only
     A.face_rho = c->face_rho;
@@ -348,9 +349,25 @@ int compute_dudt_impl(ibis_b200_ctx* c, Buffer* fs, Buffer* dudt, bool allow_rec
     return 0;
 }
 
+// after a synchronise: did a pipelined kernel give up on a stage barrier (fv_pipe.cu::pipe_wait)?
+int check_pipe_stall(ibis_b200_ctx* c) {
+    if (!c->h_pipe_dbg || c->h_pipe_dbg[0] == 0) return 0;
+    const unsigned int* d = c->h_pipe_dbg;
+    char msg[256];
+    snprintf(msg, sizeof msg, "pipelined kernel stalled and was aborted: barrier kind %u, block %u, warp %u, local tile %u, parity %u",
+             d[1], d[2], d[3], d[4], d[5]);
+    return fail(c, IBIS_B200_ECUDA, msg);
+}
+int sync_checked(ibis_b200_ctx* c) {
+    if (c->d_pipe_dbg) GPU_TRY(c, gpu::d2h(c->h_pipe_dbg, c->d_pipe_dbg, 8 * sizeof(unsigned int), c->stream));
+    GPU_TRY(c, gpu::stream_sync(c->stream));
+    return check_pipe_stall(c);
+}
+
 int fetch_scalars(ibis_b200_ctx* c, int first, int count, double* out) {
     GPU_TRY(c, gpu::d2h(c->h_scalars + first, c->d_scalars + first, count * sizeof(double), c->stream));
-    GPU_TRY(c, gpu::stream_sync(c->stream));
+    int rc = sync_checked(c);
+    if (rc) return rc;
     for (int i = 0; i < count; i++) out[i] = c->h_scalars[first + i];
     return 0;
 }
@@ -841,6 +858,10 @@ int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd_ref, con
 #undef UP2
     }
     timer.lap("tile tables + upload");
+    if (timer.on)
+        fprintf(stderr, "[ibis_b200 create] tile %d, tiles %d (+%d halo ring), slots/tile <= %d, staged sides/tile <= %d, halo list <= %d, "
+                        "records %d + %d B/tile\n", c->g.tile, c->g.n_tiles, c->g.n_tiles_all - c->g.n_tiles, c->g.tile_cap,
+                c->g.stage_cap, c->g.halo_cap, c->g.grec_stride, c->g.frec_stride);
     // WLS r-factors on the device (GridBlock::allocate_gradient_weights, grid.h:499-503)
     double* r = nullptr;
     rc = dev_alloc_zero<double>(c, 6 * cs, &r);
@@ -876,6 +897,13 @@ int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd_ref, con
         return fail(nullptr, IBIS_B200_ENOMEM, "pinned allocation failed");
     }
     c->h_scalars = static_cast<double*>(hp);
+    rc = dev_alloc_zero<unsigned int>(c, 8, &c->d_pipe_dbg);
+    if (rc || gpu::host_malloc(&hp, 8 * sizeof(unsigned int)) != 0) {
+        ibis_b200_destroy(c);
+        return fail(nullptr, IBIS_B200_ENOMEM, "allocation failed");
+    }
+    c->h_pipe_dbg = static_cast<unsigned int*>(hp);
+    memset(c->h_pipe_dbg, 0, 8 * sizeof(unsigned int));
     rc = gpu::stream_sync(c->stream);
     if (rc != 0 || !c->last_error.empty()) {
         std::string msg = c->last_error.empty() ? gpu::error_string(rc) : c->last_error;
@@ -897,13 +925,15 @@ int ibis_b200_destroy(ibis_b200_ctx* c) {
     for (void* p : c->owned_allocs) gpu::dev_free(p);
     if (c->d_stage) gpu::dev_free(c->d_stage);
     if (c->h_scalars) gpu::host_free(c->h_scalars);
+    if (c->h_pipe_dbg) gpu::host_free(c->h_pipe_dbg);
     if (c->stream) gpu::stream_destroy(c->stream);
     delete c;
     return 0;
 }
 
 int ibis_b200_sync(ibis_b200_ctx* c) {
-    GPU_TRY(c, gpu::stream_sync(c->stream));
+    int rc_ = sync_checked(c);
+    if (rc_) return rc_;
     if (!c->last_error.empty()) return IBIS_B200_ECUDA;
     return 0;
 }

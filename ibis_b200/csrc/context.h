@@ -109,6 +109,8 @@ struct ibis_b200_ctx {
     double* d_scalars = nullptr;         // results of final reductions (64 doubles)
     double* h_scalars = nullptr;         // pinned mirror
     int n_red_blocks = 0;
+    unsigned int* d_pipe_dbg = nullptr;  // abort flag + stall record of the pipelined kernels (FvArgs::pipe_dbg), 8 words
+    unsigned int* h_pipe_dbg = nullptr;  // pinned mirror
 
     // I/O staging (reference AoS <-> internal SoA)
     double* d_stage = nullptr;

@@ -159,6 +159,9 @@ struct FvArgs {
     // time step (estimate_dt fused into the first evaluation of a Runge-Kutta step): the bit
     // pattern of a positive double orders like the double, so the reduction is an integer atomicMin
     unsigned long long* dt_out;
+    // pipelined kernels: word 0 != 0 aborts every wait loop (set by the first warp whose wait on a stage barrier
+    // exceeds the time limit, with a record of which barrier in words 1..7); read by the host after a synchronise
+    unsigned int* pipe_dbg;
     double* face_T;    // face_fs of the viscous path (finite_volume.h:128), real parts
     // moving grid (GridBlock::face_vel, grid.h:599,638): [3][fstride], nullptr on a static grid.  Written by
     // face_vel_body, replaced by its local-frame round trip in the flux kernel as in the reference

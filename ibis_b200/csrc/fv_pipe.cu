@@ -48,6 +48,33 @@ namespace ib {
 constexpr int PIPE_MAX_STAGES = 8;
 constexpr size_t PIPE_SMEM_BUDGET = 227 * 1024 - 1024;   // dynamic shared memory of one block (static barriers aside)
 
+// Bounded wait on a stage barrier.  Returns false -- for the whole warp -- when the pipeline has been aborted:
+// by this warp, after PIPE_TIMEOUT_CLOCKS in this one wait (it records which barrier in dbg[1..5]), or by another.
+// Every caller leaves the kernel on false, so a protocol error or a lost peer surfaces as an error at the next
+// synchronise (abi.cu::check_pipe_stall) instead of a hung stream.
+enum { PW_FULL = 1, PW_EMPTY = 2, PW_REC = 3, PW_SFREE = 4 };
+constexpr long long PIPE_TIMEOUT_CLOCKS = 6000000000ll;          // about 3 s
+__device__ __forceinline__ bool pipe_wait(uint64_t* bar, uint32_t parity, unsigned int* dbg, int kind, int k) {
+    bool ok = ac::mbar_try_wait(bar, parity);
+    if (!ok) {
+        const long long t0 = clock64();
+        for (int it = 1;; it++) {
+            if (ac::mbar_try_wait(bar, parity)) { ok = true; break; }
+            if ((it & 63) == 0) {
+                if (*reinterpret_cast<volatile unsigned int*>(dbg) != 0u) break;
+                if (clock64() - t0 > PIPE_TIMEOUT_CLOCKS) {
+                    if (atomicCAS(dbg, 0u, 1u) == 0u) {
+                        dbg[1] = (unsigned)kind; dbg[2] = blockIdx.x; dbg[3] = threadIdx.x >> 5; dbg[4] = (unsigned)k; dbg[5] = parity;
+                        __threadfence();
+                    }
+                    break;
+                }
+            }
+        }
+    }
+    return __all_sync(0xffffffffu, ok);
+}
+
 __device__ __forceinline__ double warp_min_d(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -134,7 +161,7 @@ __global__ void __launch_bounds__(32 * (IBIS_PIPE_F_WARPS + 1), 1) k_flux_pipe(c
             const int* ti = g.tile_info + (size_t)TILE_INFO * t;
             const int n_ent = __ldg(ti + 7), n_slots = __ldg(ti + 9);
             if (t + (int)gridDim.x < g.n_tiles) ac::prefetch_l2(ti + (size_t)TILE_INFO * gridDim.x);
-            if (k >= nst) ac::mbar_wait(&empty[s], ((k / nst) - 1) & 1);
+            if (k >= nst && !pipe_wait(&empty[s], ((k / nst) - 1) & 1, A.pipe_dbg, PW_EMPTY, k)) return;
             int c0, nc;
             tile_cells(g, t, c0, nc);
             unsigned char* st = smem + (size_t)s * stage_bytes;
@@ -175,7 +202,7 @@ __global__ void __launch_bounds__(32 * (IBIS_PIPE_F_WARPS + 1), 1) k_flux_pipe(c
     int k = 0;
     for (int t = blockIdx.x; t < g.n_tiles; t += gridDim.x, k++) {
         const int s = k % nst;
-        ac::mbar_wait(&full[s], (k / nst) & 1);
+        if (!pipe_wait(&full[s], (k / nst) & 1, A.pipe_dbg, PW_FULL, k)) return;
         unsigned char* st = smem + (size_t)s * stage_bytes;
         S* stL = reinterpret_cast<S*>(st);
         const S* stR = reinterpret_cast<const S*>(st + offR);
@@ -398,7 +425,7 @@ __global__ void __launch_bounds__(32 * (IBIS_PIPE_G_WARPS + 1), 1)
                 const int s = k % nsi;
                 const int idx = (int)blockIdx.x + k * (int)gridDim.x;
                 const int t = tile_list ? __ldg(tile_list + idx) : idx;
-                if (k >= nsi) ac::mbar_wait(&empty[s], ((k / nsi) - 1) & 1);
+                if (k >= nsi && !pipe_wait(&empty[s], ((k / nsi) - 1) & 1, A.pipe_dbg, 16 + PW_EMPTY, k)) return;
                 unsigned char* st = smem + (size_t)s * in_bytes;
                 if (lane == 0) {
                     next_task[s] = 0;
@@ -416,7 +443,7 @@ __global__ void __launch_bounds__(32 * (IBIS_PIPE_G_WARPS + 1), 1)
             }
             if (k >= la) {
                 const int kk = k - la, s = kk % nsi;
-                ac::mbar_wait(&rec_full[s], (kk / nsi) & 1);
+                if (!pipe_wait(&rec_full[s], (kk / nsi) & 1, A.pipe_dbg, 16 + PW_REC, kk)) return;
                 unsigned char* st = smem + (size_t)s * in_bytes;
                 const GRec R = grec_view(st + WD_BYTES, NF, T);
                 S* sv = reinterpret_cast<S*>(st + WD_BYTES + g.grec_stride);
@@ -448,21 +475,28 @@ __global__ void __launch_bounds__(32 * (IBIS_PIPE_G_WARPS + 1), 1)
     constexpr int N_THERMO = T / 16, NV = DIM == 3 ? 3 : 2, N_TASKS = N_THERMO + NV * (T / 32);
     for (int k = 0; k < n_my; k++) {
         const int s = k % nsi, o = k % nso;
-        ac::mbar_wait(&rec_full[s], (k / nsi) & 1);
-        ac::mbar_wait(&full[s], (k / nsi) & 1);
-        if (k >= nso) ac::mbar_wait(&sfree[o], ((k / nso) - 1) & 1);
+        if (!pipe_wait(&rec_full[s], (k / nsi) & 1, A.pipe_dbg, 16 + PW_REC, k)) return;
+        if (!pipe_wait(&full[s], (k / nsi) & 1, A.pipe_dbg, 16 + PW_FULL, k)) return;
         unsigned char* st = smem + (size_t)s * in_bytes;
         const double* wd = reinterpret_cast<const double*>(st);
         const GRec R = grec_view(st + WD_BYTES, NF, T);
         const S* sv = reinterpret_cast<const S*>(st + WD_BYTES + g.grec_stride);
         S* stg = reinterpret_cast<S*>(out_base + (size_t)o * out_bytes);
         const int nc = meta[s][1];
-        bool last = false;
+        bool last = false, out_free = k < nso;
         for (;;) {
             int j = 0;
             if (lane == 0) j = atomicAdd(&next_task[s], 1);
             j = __shfl_sync(0xffffffffu, j, 0);
             if (j >= N_TASKS) break;
+            // The staging buffer is free once the stores of the tile nso tiles back have read it.  Only a warp that
+            // HOLDS a task of this tile may wait for that: the tile cannot complete without it, so the barrier is at
+            // most one phase ahead and the parity test is unambiguous (a warp without a task could arrive here after
+            // this tile's own stores, with no later tile left to flip the parity back: the tail of the sequence).
+            if (!out_free) {
+                if (!pipe_wait(&sfree[o], ((k / nso) - 1) & 1, A.pipe_dbg, 16 + PW_SFREE, k)) return;
+                out_free = true;
+            }
             if (j < N_THERMO) {
                 grad_task_thermo<DIM, NF, T, S>(A, wd, R, sv, svs, stg, j, nc, lane);
             } else {
