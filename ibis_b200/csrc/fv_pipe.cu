@@ -48,31 +48,72 @@ namespace ib {
 constexpr int PIPE_MAX_STAGES = 8;
 constexpr size_t PIPE_SMEM_BUDGET = 227 * 1024 - 1024;   // dynamic shared memory of one block (static barriers aside)
 
-// Bounded wait on a stage barrier.  Returns false -- for the whole warp -- when the pipeline has been aborted:
-// by this warp, after PIPE_TIMEOUT_CLOCKS in this one wait (it records which barrier in dbg[1..5]), or by another.
-// Every caller leaves the kernel on false, so a protocol error or a lost peer surfaces as an error at the next
-// synchronise (abi.cu::check_pipe_stall) instead of a hung stream.
-enum { PW_FULL = 1, PW_EMPTY = 2, PW_REC = 3, PW_SFREE = 4 };
+// Bounded waits.  Both return false -- for the whole warp -- when the pipeline has been aborted: by this warp,
+// after PIPE_TIMEOUT_CLOCKS in this one wait (it records which wait in dbg[1..5]), or by another.  Every caller
+// leaves the kernel on false, so a protocol error surfaces as an error at the next synchronise
+// (abi.cu::check_pipe_stall) instead of a hung stream.
+enum { PW_FULL = 1, PW_EMPTY = 2, PW_REC = 3, PW_OUT = 4, PW_STAGE = 5, PW_DONE = 6 };
 constexpr long long PIPE_TIMEOUT_CLOCKS = 6000000000ll;          // about 3 s
+__device__ __forceinline__ bool pipe_timed_out(long long t0, unsigned int* dbg, int kind, int k, unsigned aux) {
+    if (*reinterpret_cast<volatile unsigned int*>(dbg) != 0u) return true;
+    if (clock64() - t0 > PIPE_TIMEOUT_CLOCKS) {
+        if (atomicCAS(dbg, 0u, 1u) == 0u) {
+            dbg[1] = (unsigned)kind; dbg[2] = blockIdx.x; dbg[3] = threadIdx.x >> 5; dbg[4] = (unsigned)k; dbg[5] = aux;
+            __threadfence();
+        }
+        return true;
+    }
+    return false;
+}
+// the phase of an mbarrier (the hardware suspends the warp inside try_wait)
 __device__ __forceinline__ bool pipe_wait(uint64_t* bar, uint32_t parity, unsigned int* dbg, int kind, int k) {
     bool ok = ac::mbar_try_wait(bar, parity);
     if (!ok) {
         const long long t0 = clock64();
         for (int it = 1;; it++) {
             if (ac::mbar_try_wait(bar, parity)) { ok = true; break; }
-            if ((it & 63) == 0) {
-                if (*reinterpret_cast<volatile unsigned int*>(dbg) != 0u) break;
-                if (clock64() - t0 > PIPE_TIMEOUT_CLOCKS) {
-                    if (atomicCAS(dbg, 0u, 1u) == 0u) {
-                        dbg[1] = (unsigned)kind; dbg[2] = blockIdx.x; dbg[3] = threadIdx.x >> 5; dbg[4] = (unsigned)k; dbg[5] = parity;
-                        __threadfence();
-                    }
-                    break;
-                }
-            }
+            if ((it & 15) == 0 && pipe_timed_out(t0, dbg, kind, k, parity)) break;
         }
     }
     return __all_sync(0xffffffffu, ok);
+}
+// a monotone counter in shared memory reaching `target` (no parity, hence no aliasing when a warp is late)
+__device__ __forceinline__ bool pipe_spin_ge(const int* p, int target, unsigned int* dbg, int kind, int k) {
+    const volatile int* vp = p;
+    bool ok = *vp >= target;
+    if (!ok) {
+        const long long t0 = clock64();
+        for (int it = 1;; it++) {
+            __nanosleep(64);
+            if (*vp >= target) { ok = true; break; }
+            if ((it & 63) == 0 && pipe_timed_out(t0, dbg, kind, k, (unsigned)target)) break;
+        }
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    __threadfence_block();
+    return ok;
+}
+// next item of the block's ordered work queue
+__device__ __forceinline__ int pipe_next_item(int* head, int lane) {
+    int i = 0;
+    if (lane == 0) i = atomicAdd(head, 1);
+    return __shfl_sync(0xffffffffu, i, 0);
+}
+
+// a 64-int tile descriptor held by a warp: lane l has ints l and 32 + l
+struct TileDesc {
+    int d0, d1;
+};
+__device__ __forceinline__ TileDesc td_load(const int* ti, int lane) {
+    TileDesc d;
+    d.d0 = __ldg(ti + lane);
+    d.d1 = __ldg(ti + 32 + lane);
+    return d;
+}
+// int idx of the descriptor (converged call; idx may differ between the lanes)
+__device__ __forceinline__ int td_get(const TileDesc& d, int idx) {
+    const int a = __shfl_sync(0xffffffffu, d.d0, idx & 31), b = __shfl_sync(0xffffffffu, d.d1, idx & 31);
+    return idx < 32 ? a : b;
 }
 
 __device__ __forceinline__ double warp_min_d(double v) {
@@ -130,11 +171,17 @@ __host__ __device__ inline size_t flux_stage_bytes(int cap, int frec_stride, int
     return (b + 127) / 128 * 128;
 }
 
+// Work items of a block, handed out in this order by one counter: for its m-th tile the NCH = ceil(cap / 32) flux
+// chunks (32 interfaces each), then the T / 32 cell parts of tile m - 1 (one lane per cell sums its faces; queued
+// behind the NEXT tile's chunks so that the fluxes they need are normally complete when a warp gets there).  A warp
+// holding an item of tile k waits for stage_tile[s] >= k (the loader has re-designated the stage) before it tests
+// the stage barrier's parity: the stage cannot be recycled while an item of its tile is outstanding, so the barrier is
+// then exactly at the awaited phase or one behind, never two.
 template <int DIM, int FLUX, typename S>
 __global__ void __launch_bounds__(32 * (IBIS_PIPE_F_WARPS + 1), 1) k_flux_pipe(const FvArgs<S> A, const int nst) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t full[PIPE_MAX_STAGES], empty[PIPE_MAX_STAGES];
-    __shared__ int next_chunk[PIPE_MAX_STAGES], done_chunk[PIPE_MAX_STAGES], meta[PIPE_MAX_STAGES][4];
+    __shared__ int stage_tile[PIPE_MAX_STAGES], done_items[PIPE_MAX_STAGES], meta[PIPE_MAX_STAGES][4], q_head;
     const GridDev& g = A.g;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ncw = (int)(blockDim.x >> 5) - 1;
@@ -146,21 +193,24 @@ __global__ void __launch_bounds__(32 * (IBIS_PIPE_F_WARPS + 1), 1) k_flux_pipe(c
     if (threadIdx.x == 0) {
         for (int s = 0; s < nst; s++) {
             ac::mbar_init(&full[s], 1);
-            ac::mbar_init(&empty[s], ncw);
-            next_chunk[s] = 0;
-            done_chunk[s] = 0;
+            ac::mbar_init(&empty[s], 1);
+            stage_tile[s] = -1;
+            done_items[s] = 0;
         }
+        q_head = 0;
         ac::fence_barrier_init();
     }
     __syncthreads();
+    const int n_my = (int)blockIdx.x < g.n_tiles ? (g.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     if (warp == ncw) {
-        // ---- loader ----
-        int k = 0;
-        for (int t = blockIdx.x; t < g.n_tiles; t += gridDim.x, k++) {
-            const int s = k % nst;
-            const int* ti = g.tile_info + (size_t)TILE_INFO * t;
-            const int n_ent = __ldg(ti + 7), n_slots = __ldg(ti + 9);
-            if (t + (int)gridDim.x < g.n_tiles) ac::prefetch_l2(ti + (size_t)TILE_INFO * gridDim.x);
+        // ---- loader: the descriptor of the next tile is in registers before this tile's stage is waited for ----
+        TileDesc cur = td_load(g.tile_info + (size_t)TILE_INFO * blockIdx.x, lane);
+        for (int k = 0; k < n_my; k++) {
+            const int t = (int)blockIdx.x + k * (int)gridDim.x, s = k % nst;
+            const bool more = k + 1 < n_my;
+            const TileDesc nxt = more ? td_load(g.tile_info + (size_t)TILE_INFO * (t + gridDim.x), lane) : cur;
+            const int h0 = td_get(cur, 2), nh = td_get(cur, 3), ent_off = td_get(cur, 6), n_ent = td_get(cur, 7),
+                      n_slots = td_get(cur, 9);
             if (k >= nst && !pipe_wait(&empty[s], ((k / nst) - 1) & 1, A.pipe_dbg, PW_EMPTY, k)) return;
             int c0, nc;
             tile_cells(g, t, c0, nc);
@@ -169,25 +219,33 @@ __global__ void __launch_bounds__(32 * (IBIS_PIPE_F_WARPS + 1), 1) k_flux_pipe(c
             S* stR = reinterpret_cast<S*>(st + offR);
             double* stF = reinterpret_cast<double*>(st + offF);
             if (lane == 0) {
-                next_chunk[s] = 0;
-                done_chunk[s] = 0;
                 meta[s][0] = n_slots;
                 meta[s][1] = nc;
                 meta[s][2] = c0;
+                __threadfence_block();
+                *reinterpret_cast<volatile int*>(&stage_tile[s]) = k;
                 const uint32_t bytes = (uint32_t)n_slots * (uint32_t)frec<S>::bytes + (uint32_t)g.frec_stride +
                                        (with_dt ? 4u * (uint32_t)T * (uint32_t)sizeof(S) : 0u);
                 ac::mbar_arrive_expect_tx(&full[s], bytes);
             }
             __syncwarp();
-            const int n_x = 1 + n_ent;
-            for (int q = lane; q < 3 * n_x; q += 32) {
-                const TileXfer x = tile_load_xfer(g, t, q / 3);
-                if (x.count <= 0) continue;
-                const int which = q % 3;
-                const uint32_t bytes = (uint32_t)x.count * (which == 2 ? 48u : 6u * (uint32_t)sizeof(S));
-                if (which == 0) ac::bulk_g2s(stL + (long)x.slot * 6, A.sideL + (long)x.f0 * 6, bytes, &full[s]);
-                else if (which == 1) ac::bulk_g2s(stR + (long)x.slot * 6, A.sideR + (long)x.f0 * 6, bytes, &full[s]);
-                else ac::bulk_g2s(stF + (long)x.slot * 6, g.f_frame6 + (long)x.f0 * 6, bytes, &full[s]);
+            const int n_q = 3 * (1 + n_ent);
+            const bool inl = n_ent <= TILE_INLINE_ENT;
+            for (int q0 = 0; q0 < n_q; q0 += 32) {
+                const int q = q0 + lane, e = q / 3 - 1, which = q % 3;
+                int idx = 12 + 5 * (e < 0 ? 0 : e);
+                idx = idx > 59 ? 59 : idx;
+                int f0 = td_get(cur, idx), count = td_get(cur, idx + 1), slot = td_get(cur, idx + 3);
+                if (!inl && e >= 0 && q < n_q) {
+                    const int* te = g.tile_ent + 5 * (size_t)(ent_off + e);
+                    f0 = __ldg(te); count = __ldg(te + 1); slot = __ldg(te + 3);
+                }
+                if (e < 0) { f0 = h0; count = nh; slot = 0; }
+                if (q >= n_q || count <= 0) continue;
+                const uint32_t bytes = (uint32_t)count * (which == 2 ? 48u : 6u * (uint32_t)sizeof(S));
+                if (which == 0) ac::bulk_g2s(stL + (long)slot * 6, A.sideL + (long)f0 * 6, bytes, &full[s]);
+                else if (which == 1) ac::bulk_g2s(stR + (long)slot * 6, A.sideR + (long)f0 * 6, bytes, &full[s]);
+                else ac::bulk_g2s(stF + (long)slot * 6, g.f_frame6 + (long)f0 * 6, bytes, &full[s]);
             }
             if (lane == 31) ac::bulk_g2s(st + offRec, g.t_frec + (size_t)t * g.frec_stride, (uint32_t)g.frec_stride, &full[s]);
             if (with_dt && lane >= 27 && lane < 31) {
@@ -195,65 +253,70 @@ __global__ void __launch_bounds__(32 * (IBIS_PIPE_F_WARPS + 1), 1) k_flux_pipe(c
                 const S* src = A.fs[v < 3 ? F_VX + v : F_T] + c0;
                 ac::bulk_g2s(st + offDt + (size_t)v * T * sizeof(S), src, (uint32_t)T * (uint32_t)sizeof(S), &full[s]);
             }
+            cur = nxt;
         }
         return;
     }
     // ---- consumers ----
-    int k = 0;
-    for (int t = blockIdx.x; t < g.n_tiles; t += gridDim.x, k++) {
+    const int NCH = (cap + 31) >> 5, NCL = (T + 31) >> 5, P = NCH + NCL;
+    const int total = (n_my + 1) * P;
+    for (;;) {
+        const int item = pipe_next_item(&q_head, lane);
+        if (item >= total) break;
+        const int m = item / P, r = item % P;
+        const bool is_flux = r < NCH;
+        const int k = is_flux ? m : m - 1;
+        if (k < 0 || k >= n_my) continue;
         const int s = k % nst;
+        if (!pipe_spin_ge(&stage_tile[s], k, A.pipe_dbg, PW_STAGE, k)) return;
         if (!pipe_wait(&full[s], (k / nst) & 1, A.pipe_dbg, PW_FULL, k)) return;
         unsigned char* st = smem + (size_t)s * stage_bytes;
         S* stL = reinterpret_cast<S*>(st);
-        const S* stR = reinterpret_cast<const S*>(st + offR);
         const double* stF = reinterpret_cast<const double*>(st + offF);
-        const int n_slots = meta[s][0], nc = meta[s][1], c0 = meta[s][2];
-        const int nchunks = n_slots > 0 ? (n_slots + 31) >> 5 : 1;
-        bool last = false;
-        for (;;) {
-            int j = 0;
-            if (lane == 0) j = atomicAdd(&next_chunk[s], 1);
-            j = __shfl_sync(0xffffffffu, j, 0);
-            if (j >= nchunks) break;
-            const int slot = j * 32 + lane;
-            if (slot < n_slots)
+        if (is_flux) {
+            const S* stR = reinterpret_cast<const S*>(st + offR);
+            const int slot = r * 32 + lane;
+            if (slot < meta[s][0])
                 flux_from_sides6<DIM, FLUX>(A, stL + (long)slot * 6, stR + (long)slot * 6, stF + (long)slot * 6, stL + (long)slot * 6);
+            ac::fence_proxy_async();        // the flux written over the left side precedes the next bulk copy into the stage
             __syncwarp();
-            int d = 0;
             if (lane == 0) {
                 __threadfence_block();
-                d = atomicAdd(&done_chunk[s], 1);
+                atomicAdd(&done_items[s], 1);
             }
-            d = __shfl_sync(0xffffffffu, d, 0);
-            if (d == nchunks - 1) { last = true; break; }
-        }
-        if (last) {
-            // every flux of the tile is in shared memory: one lane per cell sums its faces
-            __threadfence_block();
+        } else {
+            // every flux of the tile must be in shared memory
+            if (!pipe_spin_ge(&done_items[s], NCH, A.pipe_dbg, PW_DONE, k)) return;
+            const int nc = meta[s][1], c0 = meta[s][2];
             const FRec Rc = frec_view(st + offRec, T);
-            const S* dtx = reinterpret_cast<const S*>(st + offDt);
-            for (int i0 = 0; i0 < nc; i0 += 32) {
-                const int i = i0 + lane;
-                if (i < nc) pipe_cell_sum<DIM>(A, c0 + i, i, T, Rc, stL);
-                if (with_dt) {                  // estimate_dt fused into this evaluation (uniform branch)
-                    double dl = INFINITY;
-                    if (i < nc)
-                        dl = pipe_cell_dt(re(dtx[i]), re(dtx[T + i]), re(dtx[2 * T + i]), re(dtx[3 * T + i]), re(A.gas.R),
-                                          re(A.gas.gamma), A.signal_factor, i, T, Rc, stF);
-                    dl = warp_min_d(dl);
-                    // order-preserving key of a double (negative local time steps of inverted cells included: the
-                    // reference's min picks them, finite_volume.cpp:180): flip all bits of negatives, the sign of
-                    // the others; NaN never wins a `<` in the reference and is skipped here
-                    if (lane == 0 && dl == dl) {
-                        const unsigned long long b = (unsigned long long)__double_as_longlong(dl);
-                        atomicMin(A.dt_out, b ^ ((b >> 63) ? ~0ull : 0x8000000000000000ull));
-                    }
+            const int i = (r - NCH) * 32 + lane;
+            if (i < nc) pipe_cell_sum<DIM>(A, c0 + i, i, T, Rc, stL);
+            if (with_dt) {                      // estimate_dt fused into this evaluation (uniform branch)
+                const S* dtx = reinterpret_cast<const S*>(st + offDt);
+                double dl = INFINITY;
+                if (i < nc)
+                    dl = pipe_cell_dt(re(dtx[i]), re(dtx[T + i]), re(dtx[2 * T + i]), re(dtx[3 * T + i]), re(A.gas.R),
+                                      re(A.gas.gamma), A.signal_factor, i, T, Rc, stF);
+                dl = warp_min_d(dl);
+                // order-preserving key of a double (negative local time steps of inverted cells included: the
+                // reference's min picks them, finite_volume.cpp:180): flip all bits of negatives, the sign of
+                // the others; NaN never wins a `<` in the reference and is skipped here
+                if (lane == 0 && dl == dl) {
+                    const unsigned long long b = (unsigned long long)__double_as_longlong(dl);
+                    atomicMin(A.dt_out, b ^ ((b >> 63) ? ~0ull : 0x8000000000000000ull));
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_block();
+                if (atomicAdd(&done_items[s], 1) == P - 1) {
+                    // the tile's last item: the stage goes back to the loader
+                    done_items[s] = 0;
+                    __threadfence_block();
+                    ac::mbar_arrive(&empty[s]);
                 }
             }
         }
-        ac::fence_proxy_async();        // the fluxes written over the left sides precede the next bulk copy into the stage
-        __syncwarp();
-        if (lane == 0) ac::mbar_arrive(&empty[s]);
     }
 }
 
@@ -280,13 +343,21 @@ __host__ __device__ inline size_t grad_out_bytes(int stage_cap) {
     return ((size_t)stage_cap * 6 * sizeof(S) + 127) / 128 * 128;
 }
 
-// 16 cells x (rho, second thermodynamic variable): lanes 0-15 extrapolate rho, lanes 16-31 the other variable,
-// of the same 16 cells; the pair of lanes of a cell then closes the thermodynamic state of half of the faces each
+// One work item of pass G': 32 (cell, variable) pairs of a tile.
+//   items [0, T / 16):  16 cells x (rho, second thermodynamic variable) -- lanes 0-15 extrapolate rho, lanes 16-31
+//                       the other variable, of the same 16 cells; the two lanes of a cell then close the
+//                       thermodynamic state (gas_model.h:91-117) of half of the cell's faces each;
+//   the others:         32 cells x one velocity component (vx, vy[, vz]).
+// One code path computes the gradient, the limiter and the extrapolation of the lane's variable (var_to_faces);
+// only the epilogue differs.
 template <int DIM, int NF, int T, typename S>
-__device__ __forceinline__ void grad_task_thermo(const FvArgs<S>& A, const double* wd, const GRec& R, const S* sv,
-                                                 const int svs, S* stg, const int chunk16, const int nc, const int lane) {
-    const int var = lane >> 4;
-    const int i = chunk16 * 16 + (lane & 15);
+__device__ __forceinline__ void grad_task(const FvArgs<S>& A, const double* wd, const GRec& R, const S* sv, const int svs,
+                                          S* stg, const int task, const int nc, const int lane) {
+    constexpr int N_THERMO = T / 16;
+    const bool thermo = task < N_THERMO;
+    const int q = task - N_THERMO;
+    const int var = thermo ? (lane >> 4) : 2 + q / (T / 32);
+    const int i = thermo ? task * 16 + (lane & 15) : (q % (T / 32)) * 32 + lane;
     const bool active = i < nc;
     const bool limit = A.limiter_on != 0;
     TileTables<NF, T> Tb;
@@ -299,80 +370,59 @@ __device__ __forceinline__ void grad_task_thermo(const FvArgs<S>& A, const doubl
         st[j] = R.stage[j * T + i];
     }
     const S ui = sv[var * svs + i];
-    S un[NF], r[NF], o[NF];
+    S un[NF], r[NF];
 #pragma unroll
     for (int j = 0; j < NF; j++) un[j] = sv[var * svs + (fl[j] & NBR_LOCAL_MASK)];
     var_to_faces<DIM, NF>(ui, un, Tb, A.eps, limit, r);
-#pragma unroll
-    for (int j = 0; j < NF; j++) o[j] = shfl_xor_s(r[j], 16);
-    constexpr int H = (NF + 1) / 2;
-#pragma unroll
-    for (int jj = 0; jj < H; jj++) {
-        const int j0 = jj, j1 = H + jj;
-        S rho_j, th_j;
-        int st_j;
-        if (j1 < NF) {
-            rho_j = var ? o[j1] : r[j0];
-            th_j = var ? r[j1] : o[j0];
-            st_j = var ? st[j1] : st[j0];
-        } else {
-            rho_j = r[j0];
-            th_j = o[j0];
-            st_j = var ? 0xFFFF : st[j0];
-        }
-        if (active && st_j != 0xFFFF) side_close_store(A.thermo, A.gas, rho_j, th_j, stg + (long)st_j * 6);
-    }
-    // the far side of a boundary interface is the ghost cell itself: zero gradient, unit limiter
-    // (convective_flux.cpp:281-300), i.e. its values, closed thermodynamically like any other side
     const int nR = R.hdr[1], n_own_l = R.hdr[2];
+    if (thermo) {
+        S o[NF];
 #pragma unroll
-    for (int j = 0; j < NF; j++) {
-        const bool gh = active && st[j] != 0xFFFF && (fl[j] & NBR_GHOST_BIT);
-        if (__any_sync(0xffffffffu, gh)) {
-            const S uo = shfl_xor_s(un[j], 16);
-            if (gh && var == 0) {
-                const int far_idx = far_stage_index((fl[j] & NBR_LEFT_BIT) != 0, st[j], nR, n_own_l);
-                side_close_store(A.thermo, A.gas, un[j], uo, stg + (long)far_idx * 6);
+        for (int j = 0; j < NF; j++) o[j] = shfl_xor_s(r[j], 16);
+        constexpr int H = (NF + 1) / 2;
+#pragma unroll
+        for (int jj = 0; jj < H; jj++) {
+            const int j0 = jj, j1 = H + jj;
+            S rho_j, th_j;
+            int st_j;
+            if (j1 < NF) {
+                rho_j = var ? o[j1] : r[j0];
+                th_j = var ? r[j1] : o[j0];
+                st_j = var ? st[j1] : st[j0];
+            } else {
+                rho_j = r[j0];
+                th_j = o[j0];
+                st_j = var ? 0xFFFF : st[j0];
+            }
+            if (active && st_j != 0xFFFF) side_close_store(A.thermo, A.gas, rho_j, th_j, stg + (long)st_j * 6);
+        }
+        // the far side of a boundary interface is the ghost cell itself: zero gradient, unit limiter
+        // (convective_flux.cpp:281-300), i.e. its values, closed thermodynamically like any other side
+#pragma unroll
+        for (int j = 0; j < NF; j++) {
+            const bool gh = active && st[j] != 0xFFFF && (fl[j] & NBR_GHOST_BIT);
+            if (__any_sync(0xffffffffu, gh)) {
+                const S uo = shfl_xor_s(un[j], 16);
+                if (gh && var == 0) {
+                    const int far_idx = far_stage_index((fl[j] & NBR_LEFT_BIT) != 0, st[j], nR, n_own_l);
+                    side_close_store(A.thermo, A.gas, un[j], uo, stg + (long)far_idx * 6);
+                }
             }
         }
-    }
-}
-
-// 32 cells x one velocity component v = 2, 3, 4 (vx, vy, vz)
-template <int DIM, int NF, int T, typename S>
-__device__ __forceinline__ void grad_task_velocity(const FvArgs<S>& A, const double* wd, const GRec& R, const S* sv,
-                                                   const int svs, S* stg, const int v, const int chunk32, const int nc,
-                                                   const int lane) {
-    const int i = chunk32 * 32 + lane;
-    if (i >= nc) return;
-    const bool limit = A.limiter_on != 0;
-    TileTables<NF, T> Tb;
-    Tb.w = wd;
-    Tb.idx = i;
-    int fl[NF], st[NF];
+    } else if (active) {
+        const int kq = 3 + (var - 2);
 #pragma unroll
-    for (int j = 0; j < NF; j++) {
-        fl[j] = R.nbr[j * T + i];
-        st[j] = R.stage[j * T + i];
-    }
-    const S ui = sv[v * svs + i];
-    S un[NF], r[NF];
-#pragma unroll
-    for (int j = 0; j < NF; j++) un[j] = sv[v * svs + (fl[j] & NBR_LOCAL_MASK)];
-    var_to_faces<DIM, NF>(ui, un, Tb, A.eps, limit, r);
-    const int nR = R.hdr[1], n_own_l = R.hdr[2];
-    const int k = 3 + (v - 2);
-#pragma unroll
-    for (int j = 0; j < NF; j++) {
-        if (st[j] == 0xFFFF) continue;
-        S* q = stg + (long)st[j] * 6;
-        q[k] = r[j];
-        // 2-D: vz has no gradient (convective_flux.cpp:206-208) and a unit limiter: the vy thread copies the value
-        if (DIM == 2 && v == 3) q[5] = sv[4 * svs + i];
-        if (fl[j] & NBR_GHOST_BIT) {
-            S* f = stg + (long)far_stage_index((fl[j] & NBR_LEFT_BIT) != 0, st[j], nR, n_own_l) * 6;
-            f[k] = un[j];
-            if (DIM == 2 && v == 3) f[5] = sv[4 * svs + (fl[j] & NBR_LOCAL_MASK)];
+        for (int j = 0; j < NF; j++) {
+            if (st[j] == 0xFFFF) continue;
+            S* qd = stg + (long)st[j] * 6;
+            qd[kq] = r[j];
+            // 2-D: vz has no gradient (convective_flux.cpp:206-208) and a unit limiter: the vy lane copies the value
+            if (DIM == 2 && var == 3) qd[5] = sv[4 * svs + i];
+            if (fl[j] & NBR_GHOST_BIT) {
+                S* f = stg + (long)far_stage_index((fl[j] & NBR_LEFT_BIT) != 0, st[j], nR, n_own_l) * 6;
+                f[kq] = un[j];
+                if (DIM == 2 && var == 3) f[5] = sv[4 * svs + (fl[j] & NBR_LOCAL_MASK)];
+            }
         }
     }
 }
@@ -390,12 +440,17 @@ __device__ __forceinline__ TileXfer tile_store_xfer_ti(const GridDev& g, const i
     return x;
 }
 
+// Work items of a block, in queue order: the N_TASKS (cell, variable) items of its m-th tile, then the STORE item of
+// tile m - 1 (the tile's side records leave the staging buffer as a handful of bulk stores; queued behind the next
+// tile's items so that the records are normally complete when a warp gets there).  Input stages recycle through
+// mbarriers guarded by stage_tile (see k_flux_pipe); the staging buffers through the monotone counter out_done.
 template <int DIM, int NF, int T, typename S>
 __global__ void __launch_bounds__(32 * (IBIS_PIPE_G_WARPS + 1), 1)
     k_grad_pipe(const FvArgs<S> A, const int* __restrict__ tile_list, const int n_list, const int nsi, const int nso) {
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ uint64_t rec_full[PIPE_MAX_STAGES], full[PIPE_MAX_STAGES], empty[PIPE_MAX_STAGES], sfree[PIPE_MAX_STAGES];
-    __shared__ int next_task[PIPE_MAX_STAGES], done_task[PIPE_MAX_STAGES], meta[PIPE_MAX_STAGES][4];
+    __shared__ uint64_t rec_full[PIPE_MAX_STAGES], full[PIPE_MAX_STAGES], empty[PIPE_MAX_STAGES];
+    __shared__ int stage_tile[PIPE_MAX_STAGES], done_tasks[PIPE_MAX_STAGES], out_done[PIPE_MAX_STAGES],
+        meta[PIPE_MAX_STAGES][4], q_head;
     const GridDev& g = A.g;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ncw = (int)(blockDim.x >> 5) - 1;
@@ -408,11 +463,12 @@ __global__ void __launch_bounds__(32 * (IBIS_PIPE_G_WARPS + 1), 1)
         for (int s = 0; s < nsi; s++) {
             ac::mbar_init(&rec_full[s], 1);
             ac::mbar_init(&full[s], 33);          // the loader's arrive.expect_tx + one cp.async arrival per lane
-            ac::mbar_init(&empty[s], ncw);
-            next_task[s] = 0;
-            done_task[s] = 0;
+            ac::mbar_init(&empty[s], 1);
+            stage_tile[s] = -1;
+            done_tasks[s] = 0;
         }
-        for (int o = 0; o < nso; o++) ac::mbar_init(&sfree[o], 1);
+        for (int o = 0; o < nso; o++) out_done[o] = -1;
+        q_head = 0;
         ac::fence_barrier_init();
     }
     __syncthreads();
@@ -428,13 +484,13 @@ __global__ void __launch_bounds__(32 * (IBIS_PIPE_G_WARPS + 1), 1)
                 if (k >= nsi && !pipe_wait(&empty[s], ((k / nsi) - 1) & 1, A.pipe_dbg, 16 + PW_EMPTY, k)) return;
                 unsigned char* st = smem + (size_t)s * in_bytes;
                 if (lane == 0) {
-                    next_task[s] = 0;
-                    done_task[s] = 0;
                     int c0, nc;
                     tile_cells(g, t, c0, nc);
                     meta[s][0] = t;
                     meta[s][1] = nc;
                     meta[s][2] = c0;
+                    __threadfence_block();
+                    *reinterpret_cast<volatile int*>(&stage_tile[s]) = k;
                     ac::mbar_arrive_expect_tx(&rec_full[s], (uint32_t)WD_BYTES + (uint32_t)g.grec_stride);
                     ac::bulk_g2s(st, g.t_wd + (size_t)t * (WD_BYTES / 8), (uint32_t)WD_BYTES, &rec_full[s]);
                     ac::bulk_g2s(st + WD_BYTES, g.t_grec + (size_t)t * g.grec_stride, (uint32_t)g.grec_stride, &rec_full[s]);
@@ -472,50 +528,37 @@ __global__ void __launch_bounds__(32 * (IBIS_PIPE_G_WARPS + 1), 1)
         return;
     }
     // ---- consumers ----
-    constexpr int N_THERMO = T / 16, NV = DIM == 3 ? 3 : 2, N_TASKS = N_THERMO + NV * (T / 32);
-    for (int k = 0; k < n_my; k++) {
+    constexpr int N_THERMO = T / 16, NV = DIM == 3 ? 3 : 2, N_TASKS = N_THERMO + NV * (T / 32), P = N_TASKS + 1;
+    const int total = (n_my + 1) * P;
+    for (;;) {
+        const int item = pipe_next_item(&q_head, lane);
+        if (item >= total) break;
+        const int m = item / P, r = item % P;
+        const bool is_task = r < N_TASKS;
+        const int k = is_task ? m : m - 1;
+        if (k < 0 || k >= n_my) continue;
         const int s = k % nsi, o = k % nso;
+        if (!pipe_spin_ge(&stage_tile[s], k, A.pipe_dbg, 16 + PW_STAGE, k)) return;
         if (!pipe_wait(&rec_full[s], (k / nsi) & 1, A.pipe_dbg, 16 + PW_REC, k)) return;
-        if (!pipe_wait(&full[s], (k / nsi) & 1, A.pipe_dbg, 16 + PW_FULL, k)) return;
         unsigned char* st = smem + (size_t)s * in_bytes;
-        const double* wd = reinterpret_cast<const double*>(st);
         const GRec R = grec_view(st + WD_BYTES, NF, T);
-        const S* sv = reinterpret_cast<const S*>(st + WD_BYTES + g.grec_stride);
         S* stg = reinterpret_cast<S*>(out_base + (size_t)o * out_bytes);
-        const int nc = meta[s][1];
-        bool last = false, out_free = k < nso;
-        for (;;) {
-            int j = 0;
-            if (lane == 0) j = atomicAdd(&next_task[s], 1);
-            j = __shfl_sync(0xffffffffu, j, 0);
-            if (j >= N_TASKS) break;
-            // The staging buffer is free once the stores of the tile nso tiles back have read it.  Only a warp that
-            // HOLDS a task of this tile may wait for that: the tile cannot complete without it, so the barrier is at
-            // most one phase ahead and the parity test is unambiguous (a warp without a task could arrive here after
-            // this tile's own stores, with no later tile left to flip the parity back: the tail of the sequence).
-            if (!out_free) {
-                if (!pipe_wait(&sfree[o], ((k / nso) - 1) & 1, A.pipe_dbg, 16 + PW_SFREE, k)) return;
-                out_free = true;
-            }
-            if (j < N_THERMO) {
-                grad_task_thermo<DIM, NF, T, S>(A, wd, R, sv, svs, stg, j, nc, lane);
-            } else {
-                const int q = j - N_THERMO;
-                grad_task_velocity<DIM, NF, T, S>(A, wd, R, sv, svs, stg, 2 + q / (T / 32), q % (T / 32), nc, lane);
-            }
+        if (is_task) {
+            if (!pipe_wait(&full[s], (k / nsi) & 1, A.pipe_dbg, 16 + PW_FULL, k)) return;
+            // the staging buffer is free once the stores of the tile nso tiles back have read it
+            if (k >= nso && !pipe_spin_ge(&out_done[o], k - nso, A.pipe_dbg, 16 + PW_OUT, k)) return;
+            const double* wd = reinterpret_cast<const double*>(st);
+            const S* sv = reinterpret_cast<const S*>(st + WD_BYTES + g.grec_stride);
+            grad_task<DIM, NF, T, S>(A, wd, R, sv, svs, stg, r, meta[s][1], lane);
             ac::fence_proxy_async();                       // the staging writes -> visible to the TMA unit
             __syncwarp();
-            int d = 0;
             if (lane == 0) {
                 __threadfence_block();
-                d = atomicAdd(&done_task[s], 1);
+                atomicAdd(&done_tasks[s], 1);
             }
-            d = __shfl_sync(0xffffffffu, d, 0);
-            if (d == N_TASKS - 1) { last = true; break; }
-        }
-        if (last) {
+        } else {
             // the tile's side records are complete in the staging buffer: they leave as a handful of bulk stores
-            __threadfence_block();
+            if (!pipe_spin_ge(&done_tasks[s], N_TASKS, A.pipe_dbg, 16 + PW_DONE, k)) return;
             ac::fence_proxy_async();
             const int n_ent = R.info[7], n_own_l = R.hdr[2];
             for (int q = lane; q < 2 + n_ent; q += 32) {
@@ -525,12 +568,19 @@ __global__ void __launch_bounds__(32 * (IBIS_PIPE_G_WARPS + 1), 1)
                     ac::bulk_s2g(dst, stg + (long)x.stage * 6, (uint32_t)x.count * 6 * (uint32_t)sizeof(S));
                 }
             }
+            __syncwarp();
+            if (lane == 0) {                               // the input stage goes back to the loader
+                done_tasks[s] = 0;
+                __threadfence_block();
+                ac::mbar_arrive(&empty[s]);
+            }
             ac::bulk_commit_wait_read();                   // the staging buffer may be written again after this
             __syncwarp();
-            if (lane == 0) ac::mbar_arrive(&sfree[o]);
+            if (lane == 0) {
+                __threadfence_block();
+                *reinterpret_cast<volatile int*>(&out_done[o]) = k;
+            }
         }
-        __syncwarp();
-        if (lane == 0) ac::mbar_arrive(&empty[s]);
     }
 }
 
