@@ -144,14 +144,12 @@ FvArgs<S> make_args(ibis_b200_ctx* c, Buffer* fs, Buffer* dudt, bool allow_recon
         A.grad = reinterpret_cast<S*>(c->grad_r);
         A.lim = reinterpret_cast<S*>(c->lim_r);
         A.flux = reinterpret_cast<S*>(c->flux_r);
-        A.sideL = reinterpret_cast<S*>(c->sideL_r);
-        A.sideR = reinterpret_cast<S*>(c->sideR_r);
+        A.sidesP = reinterpret_cast<S*>(c->sidesP_r);
     } else {
         A.grad = reinterpret_cast<S*>(c->grad_d);
         A.lim = reinterpret_cast<S*>(c->lim_d);
         A.flux = reinterpret_cast<S*>(c->flux_d);
-        A.sideL = reinterpret_cast<S*>(c->sideL_d);
-        A.sideR = reinterpret_cast<S*>(c->sideR_d);
+        A.sidesP = reinterpret_cast<S*>(c->sidesP_d);
     }
     {   // the five reconstructed variables of pass F with their gradient / limiter arrays
         const int src[5] = {F_RHO, (c->cfg.thermo_interpolator == THERMO_RHO_P) ? F_P
@@ -234,11 +232,9 @@ template <typename S>
 int ensure_fv_temporaries(ibis_b200_ctx* c, bool want_grad = false, bool want_flux = false) {
     const bool need_grad = want_grad || c->cfg.viscous || (c->cfg.reconstruction_order > 1 && !sides_path_for<S>(c));
     if (sides_path_for<S>(c)) {
-        S** sl = (sizeof(S) == 8) ? reinterpret_cast<S**>(&c->sideL_r) : reinterpret_cast<S**>(&c->sideL_d);
-        S** sr = (sizeof(S) == 8) ? reinterpret_cast<S**>(&c->sideR_r) : reinterpret_cast<S**>(&c->sideR_d);
-        if (!*sl) {
-            int rc = dev_alloc_zero<S>(c, (int64_t)6 * std::max<int64_t>(c->n_faces, 1), sl);
-            if (!rc) rc = dev_alloc_zero<S>(c, (int64_t)6 * std::max<int64_t>(c->n_faces, 1), sr);
+        S** sp = (sizeof(S) == 8) ? reinterpret_cast<S**>(&c->sidesP_r) : reinterpret_cast<S**>(&c->sidesP_d);
+        if (!*sp) {
+            int rc = dev_alloc_zero<S>(c, (int64_t)6 * std::max<int64_t>(c->p_total, 1), sp);
             if (rc) return fail(c, rc, "out of device memory (interface sides)");
         }
     }
@@ -751,8 +747,8 @@ int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd_ref, con
         UP2(out_off, di, out_off) UP2(out_slot, du16, out_slot) UP2(out_cell, di, out_cell) UP2(out_d, dd, out_d)
         g.n_out = n_out;
         // ---- packed per-tile records of the pipelined sides path (fv_pipe.cu; layout in fv_bodies.h::GridDev) ----
-        g.t_wd = nullptr; g.t_grec = nullptr; g.t_frec = nullptr; g.f_frame6 = nullptr;
-        g.grec_stride = g.frec_stride = g.halo_cap = 0;
+        g.t_wd = nullptr; g.t_grec = nullptr; g.t_freca = nullptr; g.t_frec = nullptr; g.t_pinfo = nullptr;
+        g.grec_stride = g.freca_stride = g.frec_stride = g.halo_cap = g.push_cap = g.p_cap = 0;
         g.pipe_nf = max_faces < 3 ? 3 : max_faces;
         // the kernels recompute the interface normal as cross(t1, t2), the reference's own formula
         // (grid/interface.h:250): arrays that do not satisfy it bit for bit keep to the gather path
@@ -765,30 +761,126 @@ int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd_ref, con
             if (memcmp(n, gd->face_norm + 3 * f, sizeof n) != 0) normals_exact = false;
         }
         if (!normals_exact) c->use_sides = false;
+        c->p_total = 0;
         if (sides_path(c)) {
             const int NFr = g.pipe_nf;
-            // neighbours of a tile's cells outside the tile: sorted, without duplicates
-            std::vector<int> halo_off(nt + 1, 0);
+            const int capp = (int)pad_to(cap, 4);
+            g.tile_cap = capp;
+            auto tile_of_cell = [&](int64_t cell) -> int {
+                if (cell < c->n_owned) return (int)(cell / T);
+                if (cell < n_grad) return n_tiles + (int)((cell - c->n_owned) / T);
+                return -1;
+            };
+            auto slot_in_cell = [&](int64_t cell, int f) -> int {
+                for (int j = 0; j < max_faces; j++)
+                    if (cf_face[(size_t)j * cs + cell] == f) return j;
+                return -1;
+            };
+            // neighbours of a tile's cells outside the tile (sorted, without duplicates) and the size of the tile's
+            // staging image (its cells' sides + the ghost sides of its boundary interfaces)
             std::vector<std::vector<int>> halos(nt);
+            std::vector<int> n_stage(nt, 0);
 #pragma omp parallel for schedule(dynamic, 64)
             for (int b = 0; b < nt; b++) {
                 const int64_t c0 = TL.c0[b], c1 = TL.c0[b + 1];
+                const int nR = TL.nR[b], n_own_l = TL.n_own_left(b);
                 std::vector<int>& h = halos[b];
+                int ns = 0;
                 for (int64_t i = c0; i < c1; i++)
                     for (int j = 0; j < max_faces; j++) {
                         if (cf_face[(size_t)j * cs + i] < 0) continue;
                         const int nb = cf_nbr[(size_t)j * cs + i];
                         if (nb < c0 || nb >= c1) h.push_back(nb);
+                        const int st = cf_stage[(size_t)j * cs + i];
+                        ns = std::max(ns, st + 1);
+                        if (nb >= gd->n_cells) ns = std::max(ns, far_stage_index(cf_out[(size_t)j * cs + i] > 0, st, nR, n_own_l) + 1);
                     }
                 std::sort(h.begin(), h.end());
                 h.erase(std::unique(h.begin(), h.end()), h.end());
+                n_stage[b] = ns;
             }
             int halo_cap = 4;
             for (int b = 0; b < nt; b++) halo_cap = std::max<int>(halo_cap, (int)halos[b].size());
             halo_cap = (int)pad_to(halo_cap, 4);
             if (T + halo_cap > NBR_LOCAL_MASK) { ibis_b200_destroy(c); return fail(nullptr, IBIS_B200_EINVAL, "tile halo too large"); }
             g.halo_cap = halo_cap;
-            g.grec_stride = (int)pad_to(grec_bytes(NFr, T, halo_cap), 128);
+            // the loader of pass G' keeps a tile's halo ids in registers (fv_pipe.cu::PIPE_HALO_REGS): grids whose
+            // tiles scatter further than that keep to the gather path
+            if (halo_cap > 256) c->use_sides = false;
+          if (c->use_sides) {
+
+            // side-state arrays of the owned tiles: where both sides of every flux slot live, who pushes what where
+            struct Foreign { int a, a_stage, slot, right; };
+            struct Push { int src, count, dst; };
+            std::vector<std::vector<Foreign>> foreign_of(n_tiles);
+            std::vector<int> lidx((size_t)capp * std::max(n_tiles, 1), 0), ridx((size_t)capp * std::max(n_tiles, 1), 0);
+            bool bad_sides = false;
+#pragma omp parallel for schedule(dynamic, 64) reduction(|| : bad_sides)
+            for (int b = 0; b < n_tiles; b++) {
+                const int nR = TL.nR[b], n_own_l = TL.n_own_left(b);
+                const int ns = (home0[b + 1] - home0[b]) + (foreign_off[b + 1] - foreign_off[b]);
+                std::vector<Foreign>& F = foreign_of[b];
+                for (int sl = 0; sl < ns; sl++) {
+                    const int f = face_of_slot(b, sl);
+                    const int64_t cl[2] = {fl[f], fr[f]};
+                    for (int side = 0; side < 2; side++) {
+                        const int64_t cell = cl[side], other = cl[1 - side];
+                        int idx = -1;
+                        if (cell >= gd->n_cells) {                          // ghost: the far side the tile itself stages
+                            const int j = slot_in_cell(other, f);
+                            if (j < 0 || tile_of_cell(other) != b) { bad_sides = true; continue; }
+                            idx = far_stage_index(cf_out[(size_t)j * cs + other] > 0, cf_stage[(size_t)j * cs + other], nR, n_own_l);
+                        } else if (tile_of_cell(cell) == b) {
+                            const int j = slot_in_cell(cell, f);
+                            if (j < 0) { bad_sides = true; continue; }
+                            idx = cf_stage[(size_t)j * cs + cell];
+                        } else {
+                            const int a = tile_of_cell(cell);
+                            const int j = a >= 0 ? slot_in_cell(cell, f) : -1;
+                            if (j < 0) { bad_sides = true; continue; }
+                            F.push_back({a, (int)cf_stage[(size_t)j * cs + cell], sl, side});
+                        }
+                        (side == 0 ? lidx : ridx)[(size_t)capp * b + sl] = idx;
+                    }
+                }
+                std::sort(F.begin(), F.end(), [](const Foreign& x, const Foreign& y) {
+                    return x.a != y.a ? x.a < y.a : x.a_stage != y.a_stage ? x.a_stage < y.a_stage : x.slot < y.slot;
+                });
+                for (size_t q = 0; q < F.size(); q++)
+                    (F[q].right ? ridx : lidx)[(size_t)capp * b + F[q].slot] = n_stage[b] + (int)q;
+            }
+            if (bad_sides) { ibis_b200_destroy(c); return fail(nullptr, IBIS_B200_EINVAL, "inconsistent tile tables"); }
+            std::vector<int> pinfo((size_t)2 * std::max(n_tiles, 1), 0);
+            int64_t ptotal = 0;
+            int p_cap = 4;
+            for (int b = 0; b < n_tiles; b++) {
+                const int np = n_stage[b] + (int)foreign_of[b].size();
+                if (ptotal + np >= ((int64_t)1 << 31)) { ibis_b200_destroy(c); return fail(nullptr, IBIS_B200_EINVAL, "too many side records for 32-bit ids"); }
+                pinfo[2 * b] = (int)ptotal;
+                pinfo[2 * b + 1] = np;
+                ptotal += np;
+                p_cap = std::max(p_cap, np);
+            }
+            c->p_total = ptotal;
+            g.p_cap = p_cap;
+            if (p_cap >= 0xFFFF) { ibis_b200_destroy(c); return fail(nullptr, IBIS_B200_EINVAL, "tile has too many side records"); }
+            std::vector<std::vector<Push>> pushes(nt);
+            for (int b = 0; b < n_tiles; b++) pushes[b].push_back({0, n_stage[b], pinfo[2 * b]});          // the staging image itself
+            for (int b = 0; b < n_tiles; b++) {
+                const std::vector<Foreign>& F = foreign_of[b];
+                for (size_t q = 0; q < F.size();) {
+                    size_t e = q + 1;
+                    while (e < F.size() && F[e].a == F[q].a && F[e].a_stage == F[q].a_stage + (int)(e - q)) e++;
+                    pushes[F[q].a].push_back({F[q].a_stage, (int)(e - q), pinfo[2 * b] + n_stage[b] + (int)q});
+                    q = e;
+                }
+            }
+            std::vector<std::vector<Foreign>>().swap(foreign_of);
+            int push_cap = 1;
+            for (int b = 0; b < nt; b++) push_cap = std::max<int>(push_cap, (int)pushes[b].size());
+            g.push_cap = push_cap;
+            g.grec_stride = (int)pad_to(grec_bytes(NFr, T, halo_cap, push_cap), 128);
+            g.freca_stride = (int)pad_to(freca_bytes(capp), 128);
             g.frec_stride = (int)pad_to(frec_bytes(T), 128);
             std::vector<unsigned char> grec((size_t)g.grec_stride * std::max(nt, 1), 0);
 #pragma omp parallel for schedule(dynamic, 64)
@@ -797,8 +889,8 @@ int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd_ref, con
                 unsigned short* nbr = reinterpret_cast<unsigned short*>(rec);
                 unsigned short* stg = nbr + (size_t)NFr * T;
                 int* hdr = reinterpret_cast<int*>(stg + (size_t)NFr * T);
-                int* info = hdr + 4;
-                int* hl = info + TILE_INFO;
+                int* pu = hdr + 4;
+                int* hl = pu + 3 * (size_t)push_cap;
                 const int64_t c0 = TL.c0[b], c1 = TL.c0[b + 1];
                 const std::vector<int>& h = halos[b];
                 for (int i = 0; i < T; i++)
@@ -818,15 +910,33 @@ int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd_ref, con
                         nbr[(size_t)j * T + i] = e;
                         stg[(size_t)j * T + i] = st;
                     }
-                hdr[0] = (int)h.size(); hdr[1] = TL.nR[b]; hdr[2] = TL.n_own_left(b); hdr[3] = 0;
-                memcpy(info, &tile_info[(size_t)TILE_INFO * b], sizeof(int) * TILE_INFO);
+                hdr[0] = (int)h.size(); hdr[1] = TL.nR[b]; hdr[2] = TL.n_own_left(b); hdr[3] = (int)pushes[b].size();
+                for (size_t k = 0; k < pushes[b].size(); k++) {
+                    pu[3 * k] = pushes[b][k].src; pu[3 * k + 1] = pushes[b][k].count; pu[3 * k + 2] = pushes[b][k].dst;
+                }
                 for (size_t k = 0; k < h.size(); k++) hl[k] = h[k];
                 for (int k = (int)h.size(); k < halo_cap; k++) hl[k] = h.empty() ? (int)c0 : h[0];   // padding: any valid cell
             }
             std::vector<std::vector<int>>().swap(halos);
+            std::vector<std::vector<Push>>().swap(pushes);
+            std::vector<unsigned char> freca((size_t)g.freca_stride * std::max(n_tiles, 1), 0);
             std::vector<unsigned char> frec((size_t)g.frec_stride * std::max(n_tiles, 1), 0);
 #pragma omp parallel for schedule(static)
             for (int b = 0; b < n_tiles; b++) {
+                unsigned char* ra = &freca[(size_t)g.freca_stride * b];
+                unsigned short* li = reinterpret_cast<unsigned short*>(ra);
+                unsigned short* ri = li + capp;
+                double* fr6 = reinterpret_cast<double*>(ri + capp);
+                const int ns = (home0[b + 1] - home0[b]) + (foreign_off[b + 1] - foreign_off[b]);
+                for (int sl = 0; sl < ns; sl++) {
+                    li[sl] = (unsigned short)lidx[(size_t)capp * b + sl];
+                    ri[sl] = (unsigned short)ridx[(size_t)capp * b + sl];
+                    const int f = face_of_slot(b, sl);
+                    for (int d = 0; d < 3; d++) {
+                        fr6[(size_t)sl * 6 + d] = gd->face_tan1[3 * (size_t)f + d];
+                        fr6[(size_t)sl * 6 + 3 + d] = gd->face_tan2[3 * (size_t)f + d];
+                    }
+                }
                 unsigned char* rec = &frec[(size_t)g.frec_stride * b];
                 double* rv = reinterpret_cast<double*>(rec);
                 double* sa = rv + T;
@@ -836,13 +946,13 @@ int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd_ref, con
                     const int64_t cell = c0 + i;
                     rv[i] = cell < c1 ? vol[cell] : 1.0;
                     for (int j = 0; j < MAXF; j++) {
-                        unsigned short s = 0xFFFF;
+                        unsigned short sv = 0xFFFF;
                         double a = 0.0;
                         if (cell < c1 && j < max_faces && cf_face[(size_t)j * cs + cell] >= 0) {
-                            s = cf_slot[(size_t)j * cs + cell];
+                            sv = cf_slot[(size_t)j * cs + cell];
                             a = -fa[cf_face[(size_t)j * cs + cell]] * (double)cf_out[(size_t)j * cs + cell];
                         }
-                        sl[(size_t)j * T + i] = s;
+                        sl[(size_t)j * T + i] = sv;
                         sa[(size_t)j * T + i] = a;
                     }
                 }
@@ -851,17 +961,25 @@ int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd_ref, con
             rc = upload_vec(c, grec, &du8);
             if (rc) { ibis_b200_destroy(c); return fail(nullptr, rc, "grid upload failed"); }
             g.t_grec = du8;
+            rc = upload_vec(c, freca, &du8);
+            if (rc) { ibis_b200_destroy(c); return fail(nullptr, rc, "grid upload failed"); }
+            g.t_freca = du8;
             rc = upload_vec(c, frec, &du8);
             if (rc) { ibis_b200_destroy(c); return fail(nullptr, rc, "grid upload failed"); }
             g.t_frec = du8;
+            rc = upload_vec(c, pinfo, &di);
+            if (rc) { ibis_b200_destroy(c); return fail(nullptr, rc, "grid upload failed"); }
+            g.t_pinfo = di;
+          }
         }
 #undef UP2
     }
     timer.lap("tile tables + upload");
     if (timer.on)
-        fprintf(stderr, "[ibis_b200 create] tile %d, tiles %d (+%d halo ring), slots/tile <= %d, staged sides/tile <= %d, halo list <= %d, "
-                        "records %d + %d B/tile\n", c->g.tile, c->g.n_tiles, c->g.n_tiles_all - c->g.n_tiles, c->g.tile_cap,
-                c->g.stage_cap, c->g.halo_cap, c->g.grec_stride, c->g.frec_stride);
+        fprintf(stderr, "[ibis_b200 create] tile %d, tiles %d (+%d halo ring), slots/tile <= %d, staged sides/tile <= %d, side records/tile <= %d "
+                        "(%lld in all), halo list <= %d, pushes/tile <= %d, records %d + %d + %d B/tile\n", c->g.tile, c->g.n_tiles,
+                c->g.n_tiles_all - c->g.n_tiles, c->g.tile_cap, c->g.stage_cap, c->g.p_cap, (long long)c->p_total, c->g.halo_cap,
+                c->g.push_cap, c->g.grec_stride, c->g.freca_stride, c->g.frec_stride);
     // WLS r-factors on the device (GridBlock::allocate_gradient_weights, grid.h:499-503)
     double* r = nullptr;
     rc = dev_alloc_zero<double>(c, 6 * cs, &r);
@@ -876,14 +994,12 @@ int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd_ref, con
     launch_wls_r(c, r);
     launch_cell_static(c, cfw, cfd);
     if (g.t_grec) {
-        // the tile-major copies the pipelined kernels fetch with one bulk copy per tile
-        double *twd = nullptr, *fr6 = nullptr;
+        // the tile-major copy of the WLS tables the pipelined kernel fetches with one bulk copy per tile
+        double* twd = nullptr;
         rc = dev_alloc_zero<double>(c, (int64_t)std::max(g.n_tiles_all, 1) * 2 * g.pipe_nf * 3 * g.tile, &twd);
-        if (!rc) rc = dev_alloc_zero<double>(c, (int64_t)6 * std::max<int64_t>(gd->n_faces, 1), &fr6);
         if (rc) { ibis_b200_destroy(c); return fail(nullptr, rc, "out of device memory"); }
         g.t_wd = twd;
-        g.f_frame6 = fr6;
-        launch_pack_pipe_tables(c, twd, fr6);
+        launch_pack_pipe_tables(c, twd);
     }
 
     // reductions

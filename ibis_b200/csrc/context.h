@@ -97,10 +97,9 @@ struct ibis_b200_ctx {
     double* face_T = nullptr;
     double* face_rho = nullptr;
     // interface-side records of the sides path (fv_bodies.h), real and dual
-    double* sideL_r = nullptr;
-    double* sideR_r = nullptr;
-    ib::dual* sideL_d = nullptr;
-    ib::dual* sideR_d = nullptr;
+    double* sidesP_r = nullptr;
+    ib::dual* sidesP_d = nullptr;
+    int64_t p_total = 0;                 // records in a side-state array (all owned tiles)
     bool use_sides = true;               // IBIS_B200_SIDES=0: second order through the gather path (grad + limiter arrays)
     int last_fs = 0;                     // FlowStates handle of the last real evaluation (debug_gradients)
 
@@ -145,7 +144,7 @@ template <typename S>
 void launch_bc(ibis_b200_ctx* c, const FvArgs<S>& A, int phase);
 void launch_wls_r(ibis_b200_ctx* c, double* r_out);
 void launch_cell_static(ibis_b200_ctx* c, double* w_out, double* d_out);   // cf_w, cf_d (after wls_r)
-void launch_pack_pipe_tables(ibis_b200_ctx* c, double* t_wd, double* f_frame6);   // tile-major cf_w / cf_d, t1 t2 frames
+void launch_pack_pipe_tables(ibis_b200_ctx* c, double* t_wd);   // tile-major cf_w / cf_d
 template <typename S>
 void launch_grad_limit(ibis_b200_ctx* c, const FvArgs<S>& A, bool viscous_pass);
 template <typename S>

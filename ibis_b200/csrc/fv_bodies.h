@@ -13,9 +13,9 @@
 namespace ib {
 
 constexpr int MAXF = 6;       // faces per cell: hex 6, wedge/pyramid 5, tet/quad 4, tri 3
-// The interface-side arrays of the sides path: sideL[f][6], sideR[f][6] (rho p T vx vy vz of the left
-// / right state, written by pass G' every evaluation) and the static frame f_frame6[f][6] (t1x t1y t1z
-// t2x t2y t2z).  Bytes of one interface in shared memory: 12 S + 6 doubles.
+// The side states of the sides path: one record (rho p T vx vy vz) per interface side, written by pass G' every
+// evaluation into per-tile arrays; the static frame of an interface is t1 t2 (6 doubles).  Bytes of one interface
+// slot in shared memory: 2 side records + 6 doubles.
 template <typename S>
 struct frec {
     static constexpr int bytes = 12 * (int)sizeof(S) + 48;
@@ -107,22 +107,32 @@ struct GridDev {
     const int* out_cell;
     const double* out_d;
     long n_out;
-    // pipelined sides path (fv_pipe.cu): per-tile packed records, each fetched by ONE bulk copy.
+    // pipelined sides path (fv_pipe.cu): per-tile packed records, each fetched by ONE bulk copy, and per-tile
+    // side-state arrays that pass G' fills and pass F' fetches with ONE bulk copy.
     //   t_wd     [tile][2 * pipe_nf * 3][tile]  WLS weights, then face offsets, of the tile's cells
     //   t_grec   [tile], grec_stride bytes: u16 nbr[pipe_nf][tile] (tile-local index of the neighbour: < tile an own
     //            cell, >= tile entry (index - tile) of the halo list; bit 14: this cell is the LEFT cell of the
     //            interface, bit 15: the neighbour is a boundary ghost; an absent slot points at the cell itself) |
-    //            u16 stage[pipe_nf][tile] (cf_stage) | int hdr[4] = {n_halo, nR, n_own_l, -} | int tile_info[64] |
+    //            u16 stage[pipe_nf][tile] (cf_stage) | int hdr[4] = {n_halo, nR, n_own_l, n_push} |
+    //            int push[push_cap][3] = {first staged record, count, destination record in the side-state array}:
+    //            where the records pass G' has staged for the tile go (the whole staging image into the tile's own
+    //            array, then the runs a neighbouring tile needs into THAT tile's array) |
     //            int halo[halo_cap] (cell ids of the neighbours outside the tile, no duplicates)
+    //   side-state array of owned tile b: records [t_pinfo[2b], + t_pinfo[2b+1]) of FvArgs::sidesP, 6 S each:
+    //            first the tile's own staging image (its cells' sides in the staging order of layout.h, the ghost
+    //            sides of its boundary interfaces included), then the sides its neighbours push
+    //   t_freca  [owned tile], freca_stride bytes: u16 lidx[tile_cap] | u16 ridx[tile_cap] (record, in the tile's
+    //            side-state array, of the left / right state of the interface in flux slot s) |
+    //            double frame[tile_cap][6] (t1 t2 of that interface: the normal is cross(t1, t2) as in the reference,
+    //            grid/interface.h:250, util/vector3.h:153-160, recomputed bit for bit in the kernels)
     //   t_frec   [owned tile], frec_stride bytes: double vol[tile] | double sarea[6][tile] (-area * outsign, 0 for an
     //            absent slot) | u16 slot[6][tile] (cf_slot)
-    //   f_frame6 [face * 6] t1x t1y t1z t2x t2y t2z: the normal is cross(t1, t2) as in the reference
-    //            (grid/interface.h:250, util/vector3.h:153-160) and is recomputed, bit for bit, in the kernels
     const double* t_wd;
     const unsigned char* t_grec;
+    const unsigned char* t_freca;
     const unsigned char* t_frec;
-    const double* f_frame6;
-    int grec_stride, frec_stride, halo_cap, pipe_nf;
+    const int* t_pinfo;
+    int grec_stride, freca_stride, frec_stride, halo_cap, push_cap, p_cap, pipe_nf;
     // NOTE cf_slot, cf_out and cf_d are always MAXF slots wide (absent slots: 0xFFFF / 0 / 0) so
     // that the tiled kernel can load all slots unconditionally; cf_face, cf_nbr, cf_w are
     // max_faces wide.
@@ -153,8 +163,7 @@ struct FvArgs {
     S* grad;           // [(var*3 + comp)*cstride + cell]
     S* lim;            // [var*cstride + cell]
     S* flux;           // general path: [comp*fstride + face]
-    S* sideL;          // sides path: [face*6 + k], k = rho p T vx vy vz of the left state
-    S* sideR;          //             ... of the right state
+    S* sidesP;         // sides path: the per-tile side-state arrays (GridDev::t_pinfo), 6 S per record: rho p T vx vy vz
     // sides path: when not null, pass F' also takes the minimum over the owned cells of the local
     // time step (estimate_dt fused into the first evaluation of a Runge-Kutta step): the bit
     // pattern of a positive double orders like the double, so the reduction is an integer atomicMin
@@ -486,8 +495,8 @@ IBIS_HD void bj_limiters(const GridDev& g, int c, double eps, const double* ui, 
 #pragma unroll
     for (int v = 0; v < NV; v++) {
         double p = 1.0;
-        if (dmax[v] > 0.0) p = min_(p, (umax[v] - ui[v]) / (dmax[v] + eps));
-        if (dmin[v] < 0.0) p = min_(p, (umin[v] - ui[v]) / -(-dmin[v] + eps));
+        if (dmax[v] > 0.0) p = min_(p, div_z(umax[v] - ui[v], dmax[v] + eps));
+        if (dmin[v] < 0.0) p = min_(p, div_z(umin[v] - ui[v], -(-dmin[v] + eps)));
         phi[v] = p;
     }
 }
@@ -1210,8 +1219,8 @@ IBIS_HD double bj_phi(const double* delta, const double& ui, const double& umin,
         dmin = delta[j] < dmin ? delta[j] : dmin;
     }
     double p = 1.0;
-    if (dmax > 0.0) p = min_(p, (umax - ui) / (dmax + eps));
-    if (dmin < 0.0) p = min_(p, (umin - ui) / -(-dmin + eps));
+    if (dmax > 0.0) p = min_(p, div_z(umax - ui, dmax + eps));
+    if (dmin < 0.0) p = min_(p, div_z(umin - ui, -(-dmin + eps)));
     return p;
 }
 
@@ -1266,20 +1275,20 @@ constexpr int NBR_LOCAL_MASK = 0x3FFF, NBR_LEFT_BIT = 0x4000, NBR_GHOST_BIT = 0x
 struct GRec {
     const unsigned short* nbr;     // [nf][T]
     const unsigned short* stage;   // [nf][T]
-    const int* hdr;                // n_halo, nR, n_own_l, -
-    const int* info;               // the tile descriptor (tile_info), 64 ints
+    const int* hdr;                // n_halo, nR, n_own_l, n_push
+    const int* push;               // [push_cap][3]
     const int* halo;               // [halo_cap]
 };
-IBIS_HD GRec grec_view(const unsigned char* rec, int nf, int T) {
+IBIS_HD GRec grec_view(const unsigned char* rec, int nf, int T, int push_cap) {
     GRec R;
     R.nbr = reinterpret_cast<const unsigned short*>(rec);
     R.stage = R.nbr + (size_t)nf * T;
     R.hdr = reinterpret_cast<const int*>(R.stage + (size_t)nf * T);
-    R.info = R.hdr + 4;
-    R.halo = R.info + TILE_INFO;
+    R.push = R.hdr + 4;
+    R.halo = R.push + 3 * (size_t)push_cap;
     return R;
 }
-IBIS_HD int grec_bytes(int nf, int T, int halo_cap) { return 4 * nf * T + 16 + 4 * TILE_INFO + 4 * halo_cap; }
+IBIS_HD int grec_bytes(int nf, int T, int halo_cap, int push_cap) { return 4 * nf * T + 16 + 12 * push_cap + 4 * halo_cap; }
 
 // the thermodynamic pair (rho, second variable) extrapolated to one interface -> rho p T of the side record
 template <typename S>
@@ -1410,22 +1419,31 @@ IBIS_HD void frame_normal(const double* fr, double& nx, double& ny, double& nz) 
     ny = fr[2] * fr[3] - fr[0] * fr[5];
     nz = fr[0] * fr[4] - fr[1] * fr[3];
 }
-template <int DIM, int FLUX, typename S>
-IBIS_HD void flux_from_sides6(const FvArgs<S>& A, const S* Ls, const S* Rs, const double* fr, S* out) {
-    typedef mem<S> M;
-    Side<S> L, R_;
-    M::ld2(Ls, 0, L.rho, L.p);
-    M::ld2(Ls, 2, L.T, L.u);
-    M::ld2(Ls, 4, L.v, L.w);
-    M::ld2(Rs, 0, R_.rho, R_.p);
-    M::ld2(Rs, 2, R_.T, R_.u);
-    M::ld2(Rs, 4, R_.v, R_.w);
-    L.e = S(0.0);
-    R_.e = S(0.0);
+// the operands of one interface: side states and frame, as loaded from the stage
+template <typename S>
+struct FluxOperands {
+    Side<S> L, R;
     double t1x, t1y, t1z, t2x, t2y, t2z;
-    mem<double>::ld2(fr, 0, t1x, t1y);
-    mem<double>::ld2(fr, 2, t1z, t2x);
-    mem<double>::ld2(fr, 4, t2y, t2z);
+};
+template <typename S>
+IBIS_HD void flux_load_operands(const S* Ls, const S* Rs, const double* fr, FluxOperands<S>& O) {
+    typedef mem<S> M;
+    M::ld2(Ls, 0, O.L.rho, O.L.p);
+    M::ld2(Ls, 2, O.L.T, O.L.u);
+    M::ld2(Ls, 4, O.L.v, O.L.w);
+    M::ld2(Rs, 0, O.R.rho, O.R.p);
+    M::ld2(Rs, 2, O.R.T, O.R.u);
+    M::ld2(Rs, 4, O.R.v, O.R.w);
+    O.L.e = S(0.0);
+    O.R.e = S(0.0);
+    mem<double>::ld2(fr, 0, O.t1x, O.t1y);
+    mem<double>::ld2(fr, 2, O.t1z, O.t2x);
+    mem<double>::ld2(fr, 4, O.t2y, O.t2z);
+}
+template <int DIM, int FLUX, typename S>
+IBIS_HD void flux_from_operands(const FvArgs<S>& A, const FluxOperands<S>& O, S* out) {
+    Side<S> L = O.L, R_ = O.R;
+    const double t1x = O.t1x, t1y = O.t1y, t1z = O.t1z, t2x = O.t2x, t2y = O.t2y, t2z = O.t2z;
     const double nx = t1y * t2z - t1z * t2y;
     const double ny = t1z * t2x - t1x * t2z;
     const double nz = t1x * t2y - t1y * t2x;
@@ -1450,6 +1468,27 @@ IBIS_HD void flux_from_sides6(const FvArgs<S>& A, const S* Ls, const S* Rs, cons
     out[3] = px * nz + py * t1z + pz * t2z;
     out[4] = F.energy;
 }
+template <int DIM, int FLUX, typename S>
+IBIS_HD void flux_from_sides6(const FvArgs<S>& A, const S* Ls, const S* Rs, const double* fr, S* out) {
+    FluxOperands<S> O;
+    flux_load_operands(Ls, Rs, fr, O);
+    flux_from_operands<DIM, FLUX>(A, O, out);
+}
+
+// the per-tile interface record of pass F' (GridDev::t_freca)
+struct FRecA {
+    const unsigned short* lidx;    // [cap]
+    const unsigned short* ridx;    // [cap]
+    const double* frame;           // [cap][6]
+};
+IBIS_HD FRecA freca_view(const unsigned char* rec, int cap) {
+    FRecA R;
+    R.lidx = reinterpret_cast<const unsigned short*>(rec);
+    R.ridx = R.lidx + cap;
+    R.frame = reinterpret_cast<const double*>(R.ridx + cap);
+    return R;
+}
+IBIS_HD int freca_bytes(int cap) { return 4 * cap + 48 * cap; }
 
 // the per-tile cell record of pass F' (GridDev::t_frec)
 struct FRec {
@@ -1466,9 +1505,9 @@ IBIS_HD FRec frec_view(const unsigned char* rec, int T) {
 }
 IBIS_HD int frec_bytes(int T) { return T * (8 + 8 * MAXF + 2 * MAXF); }
 
-// flux_surface_integral of tile-local cell i (global cell c) from the staged fluxes st[slot * 6 + k]
+// flux_surface_integral of tile-local cell i (global cell c) from the staged fluxes st[slot * QS + k]
 // (finite_volume.cpp:221-256): same products, same order over the cell's faces as tile_cell_sum
-template <int DIM, typename S>
+template <int DIM, int QS = 6, typename S>
 IBIS_HD void pipe_cell_sum(const FvArgs<S>& A, int c, int i, int T, const FRec& R, const S* st) {
     typedef mem<S> M;
     S d_mass = S(0.0), d_mx = S(0.0), d_my = S(0.0), d_mz = S(0.0), d_e = S(0.0);
@@ -1476,7 +1515,7 @@ IBIS_HD void pipe_cell_sum(const FvArgs<S>& A, int c, int i, int T, const FRec& 
     for (int j = 0; j < MAXF; j++) {
         const int sl = R.slot[j * T + i];
         if (sl == 0xFFFF) continue;
-        const S* q = st + (long)sl * 6;
+        const S* q = st + (long)sl * QS;
         const double area = R.sarea[j * T + i];
         d_mass += q[0] * area;
         d_mx += q[1] * area;
@@ -1550,5 +1589,8 @@ IBIS_HD double local_dt_body(const FvArgs<S>& A, int c) {
     }
     return volume / (sr_c + A.signal_factor * sr_v);
 }
+
+// the same with `frames` = the tile's frames in GLOBAL memory (t_freca; pass F' has released its staged copy by the
+// time the cells sum their faces): identical code, the loads go through L2
 
 }  // namespace ib

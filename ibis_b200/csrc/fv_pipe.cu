@@ -7,16 +7,19 @@
 //   k_flux_pipe  pass F': rotate, flux calculator, rotate back (convective_flux.cpp:148-164) and
 //                flux_surface_integral (finite_volume.cpp:221-256), owner computes, no atomics on the residual
 //
-// Both have the same anatomy.  ONE loader warp walks the block's tiles and keeps a ring of shared-memory
-// stages full: every static table of a tile is a packed per-tile record (GridDev::t_wd, t_grec, t_frec) or a
-// contiguous interface range (tile-owned interface numbering, layout.h), so a stage is filled by a handful of
-// TMA bulk copies (cp.async.bulk, SASS UBLKCP) completing on an mbarrier; the only gathered data -- the state of
-// the neighbour cells outside the tile -- is fetched by the loader's lanes with cp.async into the same stage and
-// reported to the same mbarrier.  The CONSUMER warps never touch global memory on the input side: they wait on the
-// stage's mbarrier, take work items (32 interfaces, or 32 (cell, variable) pairs) off a per-stage counter, and the
-// warp that finishes a tile's last item does the tile's epilogue (cell sums / bulk store of the side records).
-// No block-wide barrier after start-up; warps of one block are at different tiles at the same time, which is what
-// hides the latency of the fp64 dependency chains and of the loads.
+// Both have the same anatomy.  ONE loader warp walks the block's tiles and keeps a ring of shared-memory stages
+// full.  Everything a tile needs is a packed per-tile record or a per-tile array (GridDev::t_wd, t_grec, t_freca,
+// t_frec, the side-state arrays), so a stage is filled by two to seven TMA bulk copies (cp.async.bulk, SASS UBLKCP)
+// completing on an mbarrier -- the loader issues its bulk copies one lane at a time, so their NUMBER per tile is what
+// bounds it; the only gathered data (the state of the neighbour cells outside the tile, pass G') is fetched by the
+// loader's lanes with cp.async into the same stage and reported to the same mbarrier.  The loader also asks the TMA
+// unit to pull the data of the tile a few iterations ahead into L2 (cp.async.bulk.prefetch.L2), so that a stage waits
+// for an L2 round trip, not a DRAM one.  The CONSUMER warps never touch global memory on the input side: they take
+// work items (32 interfaces, or 32 (cell, variable) pairs) off the block's ordered queue, wait for the item's stage,
+// and the warp that completes a tile's last item hands the stage back (and, pass G', sends the tile's side records
+// off: the staging image into the tile's own side-state array, the runs a neighbouring tile needs into that
+// tile's array -- pass F' then reads ONE contiguous array per tile).  No block-wide barrier after start-up; warps of
+// one block are at different tiles at the same time, which is what hides the latency of the fp64 dependency chains.
 //
 // Arithmetic: the same per-value expression trees as the reference (and as the host emulation in tests/emu runs
 // them through fv_bodies.h::pipe_grad_cell / flux_from_sides6 / pipe_cell_sum), hence the same bits.
@@ -26,13 +29,19 @@
 #include "context.h"
 
 #ifndef IBIS_PIPE_F_WARPS
-#define IBIS_PIPE_F_WARPS 19      // consumer warps of pass F'
+#define IBIS_PIPE_F_WARPS 18      // consumer warps of pass F'
+#endif
+#ifndef IBIS_PIPE_F_LOADERS
+#define IBIS_PIPE_F_LOADERS 2     // loader warps of pass F' (loader w takes the block's tiles w, w + NL, ...)
 #endif
 #ifndef IBIS_PIPE_G_WARPS
-#define IBIS_PIPE_G_WARPS 19      // consumer warps of pass G'
+#define IBIS_PIPE_G_WARPS 17      // consumer warps of pass G'
 #endif
-#ifndef IBIS_PIPE_LOOKAHEAD
-#define IBIS_PIPE_LOOKAHEAD 2     // pass G': the static record is requested this many tiles ahead of the gather
+#ifndef IBIS_PIPE_G_LOADERS
+#define IBIS_PIPE_G_LOADERS 3     // loader warps of pass G'
+#endif
+#ifndef IBIS_PIPE_PREFETCH
+#define IBIS_PIPE_PREFETCH 6      // a loader pulls a tile's data into L2 this many tiles (a multiple of its stride) ahead
 #endif
 
 namespace ib {
@@ -46,6 +55,7 @@ namespace ib {
     } while (0)
 
 constexpr int PIPE_MAX_STAGES = 8;
+constexpr int PIPE_HALO_REGS = 8;                        // halo ids a loader lane keeps in registers (halo list <= 256)
 constexpr size_t PIPE_SMEM_BUDGET = 227 * 1024 - 1024;   // dynamic shared memory of one block (static barriers aside)
 
 // Bounded waits.  Both return false -- for the whole warp -- when the pipeline has been aborted: by this warp,
@@ -65,14 +75,23 @@ __device__ __forceinline__ bool pipe_timed_out(long long t0, unsigned int* dbg, 
     }
     return false;
 }
-// the phase of an mbarrier (the hardware suspends the warp inside try_wait)
+// Waits poll with a growing sleep instead of suspending on the barrier: a stage barrier sees some forty events per
+// phase (one per bulk copy), and an event-driven sleep wakes every waiting warp at each of them -- measured, that
+// cost more issue slots than the work itself.
+__device__ __forceinline__ unsigned pipe_backoff(unsigned ns) {
+    __nanosleep(ns);
+    return ns < 512u ? ns * 2u : ns;
+}
+// the phase of an mbarrier
 __device__ __forceinline__ bool pipe_wait(uint64_t* bar, uint32_t parity, unsigned int* dbg, int kind, int k) {
-    bool ok = ac::mbar_try_wait(bar, parity);
+    bool ok = ac::mbar_test_wait(bar, parity);
     if (!ok) {
         const long long t0 = clock64();
+        unsigned ns = 64u;
         for (int it = 1;; it++) {
-            if (ac::mbar_try_wait(bar, parity)) { ok = true; break; }
-            if ((it & 15) == 0 && pipe_timed_out(t0, dbg, kind, k, parity)) break;
+            ns = pipe_backoff(ns);
+            if (ac::mbar_test_wait(bar, parity)) { ok = true; break; }
+            if ((it & 63) == 0 && pipe_timed_out(t0, dbg, kind, k, parity)) break;
         }
     }
     return __all_sync(0xffffffffu, ok);
@@ -83,8 +102,9 @@ __device__ __forceinline__ bool pipe_spin_ge(const int* p, int target, unsigned 
     bool ok = *vp >= target;
     if (!ok) {
         const long long t0 = clock64();
+        unsigned ns = 64u;
         for (int it = 1;; it++) {
-            __nanosleep(64);
+            ns = pipe_backoff(ns);
             if (*vp >= target) { ok = true; break; }
             if ((it & 63) == 0 && pipe_timed_out(t0, dbg, kind, k, (unsigned)target)) break;
         }
@@ -93,6 +113,20 @@ __device__ __forceinline__ bool pipe_spin_ge(const int* p, int target, unsigned 
     __threadfence_block();
     return ok;
 }
+// the same for a single thread (the loaders run on one lane)
+__device__ __forceinline__ bool pipe_spin_ge_1(const int* p, int target, unsigned int* dbg, int kind, int k) {
+    const volatile int* vp = p;
+    if (*vp < target) {
+        const long long t0 = clock64();
+        unsigned ns = 64u;
+        for (int it = 1; *vp < target; it++) {
+            ns = pipe_backoff(ns);
+            if ((it & 63) == 0 && pipe_timed_out(t0, dbg, kind, k, (unsigned)target)) return false;
+        }
+    }
+    __threadfence_block();
+    return true;
+}
 // next item of the block's ordered work queue
 __device__ __forceinline__ int pipe_next_item(int* head, int lane) {
     int i = 0;
@@ -100,21 +134,9 @@ __device__ __forceinline__ int pipe_next_item(int* head, int lane) {
     return __shfl_sync(0xffffffffu, i, 0);
 }
 
-// a 64-int tile descriptor held by a warp: lane l has ints l and 32 + l
-struct TileDesc {
-    int d0, d1;
-};
-__device__ __forceinline__ TileDesc td_load(const int* ti, int lane) {
-    TileDesc d;
-    d.d0 = __ldg(ti + lane);
-    d.d1 = __ldg(ti + 32 + lane);
-    return d;
-}
-// int idx of the descriptor (converged call; idx may differ between the lanes)
-__device__ __forceinline__ int td_get(const TileDesc& d, int idx) {
-    const int a = __shfl_sync(0xffffffffu, d.d0, idx & 31), b = __shfl_sync(0xffffffffu, d.d1, idx & 31);
-    return idx < 32 ? a : b;
-}
+// n / d for the small n of the work queue, d given as m = ceil(2^32 / d) (exact while n * d < 2^32)
+__host__ __device__ inline unsigned pipe_magic(int d) { return (unsigned)((0x100000000ull + (unsigned)d - 1) / (unsigned)d); }
+__device__ __forceinline__ int pipe_div(int n, unsigned m) { return (int)__umulhi((unsigned)n, m); }
 
 __device__ __forceinline__ double warp_min_d(double v) {
 #pragma unroll
@@ -130,7 +152,7 @@ __device__ __forceinline__ dual shfl_xor_s(const dual& v, int m) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// setup: tile-major copies of the static tables
+// setup: tile-major copy of the static WLS tables
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_pack_wd(const GridDev g, double* t_wd) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -145,158 +167,198 @@ __global__ void __launch_bounds__(256) k_pack_wd(const GridDev g, double* t_wd) 
         dst[(size_t)(NT + r) * T] = g.cf_d[(size_t)r * g.cstride + c];
     }
 }
-__global__ void __launch_bounds__(256) k_pack_frame6(const GridDev g, double* fr6) {
-    const int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= g.n_faces) return;
-    for (int k = 0; k < 3; k++) {
-        fr6[(size_t)f * 6 + k] = g.f_t1[(size_t)k * g.fstride + f];
-        fr6[(size_t)f * 6 + 3 + k] = g.f_t2[(size_t)k * g.fstride + f];
-    }
-}
-void launch_pack_pipe_tables(ibis_b200_ctx* c, double* t_wd, double* f_frame6) {
+void launch_pack_pipe_tables(ibis_b200_ctx* c, double* t_wd) {
     const GridDev& g = c->g;
     if (g.n_grad > 0) k_pack_wd<<<(g.n_grad + 255) / 256, 256, 0, c->stream>>>(g, t_wd);
-    if (g.n_faces > 0) k_pack_frame6<<<(g.n_faces + 255) / 256, 256, 0, c->stream>>>(g, f_frame6);
     CUDA_CHECK_LAUNCH(c);
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // pass F'
 // ---------------------------------------------------------------------------------------------------------
-// stage = [left sides cap x 6 S | right sides cap x 6 S | frames cap x 6 double | cell record frec_stride |
-//          (dt fused into this evaluation) vx vy vz T of the tile's cells, 4 x T S]
+// Two rings in shared memory:
+//   input stage  [the tile's side-state array p_cap x 6 S | its interface record freca_stride]: the operands of the
+//                tile's interfaces.  A flux item moves its 32 interfaces' operands into registers first, and the
+//                stage goes back to the loader as soon as every item of the tile has done so -- it is occupied for
+//                a load and a few hundred cycles, not for the flux computation;
+//   flux buffer  [fluxes cap x 5 S | cell record frec_stride | (dt fused) vx vy vz T of the tile's cells, 4 x T S]:
+//                lives until the tile's cells have summed their faces.
+// Shared memory holds what is IN FLIGHT from L2 plus the small per-tile results, instead of every operand for the
+// whole time a tile is being worked on.
 template <typename S>
-__host__ __device__ inline size_t flux_stage_bytes(int cap, int frec_stride, int T, bool with_dt) {
-    size_t b = (size_t)cap * frec<S>::bytes + (size_t)frec_stride + (with_dt ? (size_t)4 * T * sizeof(S) : 0);
+__host__ __device__ inline size_t flux_in_bytes(int p_cap, int freca_stride) {
+    return ((size_t)p_cap * 6 * sizeof(S) + 127) / 128 * 128 + (size_t)freca_stride;
+}
+template <typename S>
+__host__ __device__ inline size_t flux_fb_bytes(int cap, int frec_stride, int T, bool with_dt) {
+    size_t b = (size_t)cap * 5 * sizeof(S) + (size_t)frec_stride + (with_dt ? (size_t)4 * T * sizeof(S) : 0);
     return (b + 127) / 128 * 128;
 }
 
 // Work items of a block, handed out in this order by one counter: for its m-th tile the NCH = ceil(cap / 32) flux
 // chunks (32 interfaces each), then the T / 32 cell parts of tile m - 1 (one lane per cell sums its faces; queued
 // behind the NEXT tile's chunks so that the fluxes they need are normally complete when a warp gets there).  A warp
-// holding an item of tile k waits for stage_tile[s] >= k (the loader has re-designated the stage) before it tests
-// the stage barrier's parity: the stage cannot be recycled while an item of its tile is outstanding, so the barrier is
-// then exactly at the awaited phase or one behind, never two.
+// holding an item of tile k first waits for stage_tile[s] >= k / fb_tile[o] >= k (the loader has re-designated the
+// stage / buffer) and only then tests the barrier's parity: neither can be recycled while an item of its tile is
+// outstanding, so the barrier is then exactly at the awaited phase or one behind, never two.
 template <int DIM, int FLUX, typename S>
-__global__ void __launch_bounds__(32 * (IBIS_PIPE_F_WARPS + 1), 1) k_flux_pipe(const FvArgs<S> A, const int nst) {
+__global__ void __launch_bounds__(32 * (IBIS_PIPE_F_WARPS + IBIS_PIPE_F_LOADERS), 1) k_flux_pipe(const FvArgs<S> A, const int nsi, const int nfb) {
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ uint64_t full[PIPE_MAX_STAGES], empty[PIPE_MAX_STAGES];
-    __shared__ int stage_tile[PIPE_MAX_STAGES], done_items[PIPE_MAX_STAGES], meta[PIPE_MAX_STAGES][4], q_head;
+    __shared__ uint64_t full_in[PIPE_MAX_STAGES], rec_full[PIPE_MAX_STAGES];
+    __shared__ int stage_tile[PIPE_MAX_STAGES], stage_free[PIPE_MAX_STAGES], reads_done[PIPE_MAX_STAGES], n_slots_of[PIPE_MAX_STAGES];
+    __shared__ int fb_tile[PIPE_MAX_STAGES], fb_done[PIPE_MAX_STAGES], done_items[PIPE_MAX_STAGES], meta[PIPE_MAX_STAGES][4];
+    __shared__ int q_head;
     const GridDev& g = A.g;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ncw = (int)(blockDim.x >> 5) - 1;
+    const int ncw = (int)(blockDim.x >> 5) - IBIS_PIPE_F_LOADERS;
     const int cap = g.tile_cap, T = g.tile;
     const bool with_dt = A.dt_out != nullptr;
-    const size_t stage_bytes = flux_stage_bytes<S>(cap, g.frec_stride, T, with_dt);
-    const size_t offR = (size_t)cap * 6 * sizeof(S), offF = 2 * offR, offRec = offF + (size_t)cap * 48,
-                 offDt = offRec + (size_t)g.frec_stride;
+    const size_t in_bytes = flux_in_bytes<S>(g.p_cap, g.freca_stride), fb_bytes = flux_fb_bytes<S>(cap, g.frec_stride, T, with_dt);
+    const size_t offA = in_bytes - (size_t)g.freca_stride;                 // interface record inside the input stage
+    const size_t offRec = (size_t)cap * 5 * sizeof(S), offDt = offRec + (size_t)g.frec_stride;
+    unsigned char* fb_base = smem + (size_t)nsi * in_bytes;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < nst; s++) {
-            ac::mbar_init(&full[s], 1);
-            ac::mbar_init(&empty[s], 1);
+        for (int s = 0; s < nsi; s++) {
+            ac::mbar_init(&full_in[s], 1);
             stage_tile[s] = -1;
-            done_items[s] = 0;
+            stage_free[s] = -1;
+            reads_done[s] = 0;
+        }
+        for (int o = 0; o < nfb; o++) {
+            ac::mbar_init(&rec_full[o], 1);
+            fb_tile[o] = -1;
+            fb_done[o] = -1;
+            done_items[o] = 0;
         }
         q_head = 0;
         ac::fence_barrier_init();
     }
     __syncthreads();
     const int n_my = (int)blockIdx.x < g.n_tiles ? (g.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-    if (warp == ncw) {
-        // ---- loader: the descriptor of the next tile is in registers before this tile's stage is waited for ----
-        TileDesc cur = td_load(g.tile_info + (size_t)TILE_INFO * blockIdx.x, lane);
-        for (int k = 0; k < n_my; k++) {
-            const int t = (int)blockIdx.x + k * (int)gridDim.x, s = k % nst;
-            const bool more = k + 1 < n_my;
-            const TileDesc nxt = more ? td_load(g.tile_info + (size_t)TILE_INFO * (t + gridDim.x), lane) : cur;
-            const int h0 = td_get(cur, 2), nh = td_get(cur, 3), ent_off = td_get(cur, 6), n_ent = td_get(cur, 7),
-                      n_slots = td_get(cur, 9);
-            if (k >= nst && !pipe_wait(&empty[s], ((k / nst) - 1) & 1, A.pipe_dbg, PW_EMPTY, k)) return;
+    if (warp >= ncw) {
+        // ---- loaders: loader w takes the block's tiles w, w + NL, ...  Per tile three bulk copies (side-state
+        // array, interface record, cell record; + 4 rows with the fused dt), issued by lane 0, and the same ranges of a
+        // later tile of its own as L2 prefetches ----
+        if (lane != 0) return;
+        const int step = (int)gridDim.x, w = warp - ncw;
+        constexpr int NL = IBIS_PIPE_F_LOADERS, PF = (IBIS_PIPE_PREFETCH + NL - 1) / NL * NL;
+        // {first record, record count} of the tile's side-state array and its slot count, fetched one tile ahead
+        int pi0 = 0, pi1 = 0, pi2 = 0;
+        if (w < n_my) {
+            const size_t t = (size_t)blockIdx.x + (size_t)w * step;
+            pi0 = __ldg(g.t_pinfo + 2 * t);
+            pi1 = __ldg(g.t_pinfo + 2 * t + 1);
+            pi2 = __ldg(g.tile_info + (size_t)TILE_INFO * t + 9);
+        }
+        for (int k = w; k < n_my; k += NL) {
+            const int t = (int)blockIdx.x + k * step, s = k % nsi, o = k % nfb;
+            if (k + PF < n_my) {                              // L2 prefetch of a later tile of this loader
+                const size_t tp = (size_t)t + (size_t)PF * step;
+                const int q0 = __ldg(g.t_pinfo + 2 * tp), q1 = __ldg(g.t_pinfo + 2 * tp + 1);
+                ac::bulk_prefetch_l2(A.sidesP + (size_t)q0 * 6, (uint32_t)q1 * 6u * (uint32_t)sizeof(S));
+                ac::bulk_prefetch_l2(g.t_freca + tp * g.freca_stride, (uint32_t)g.freca_stride);
+                ac::bulk_prefetch_l2(g.t_frec + tp * g.frec_stride, (uint32_t)g.frec_stride);
+                if (with_dt) {
+                    int c0p, ncp;
+                    tile_cells(g, (int)tp, c0p, ncp);
+                    for (int v = 0; v < 4; v++) ac::bulk_prefetch_l2(A.fs[v < 3 ? F_VX + v : F_T] + c0p, (uint32_t)T * (uint32_t)sizeof(S));
+                }
+            }
+            int nx0 = 0, nx1 = 0, nx2 = 0;                    // this loader's next tile, in flight during the waits
+            if (k + NL < n_my) {
+                const size_t tn = (size_t)t + (size_t)NL * step;
+                nx0 = __ldg(g.t_pinfo + 2 * tn);
+                nx1 = __ldg(g.t_pinfo + 2 * tn + 1);
+                nx2 = __ldg(g.tile_info + (size_t)TILE_INFO * tn + 9);
+            }
+            if (k >= nsi && !pipe_spin_ge_1(&stage_free[s], k - nsi, A.pipe_dbg, PW_EMPTY, k)) return;
+            if (k >= nfb && !pipe_spin_ge_1(&fb_done[o], k - nfb, A.pipe_dbg, PW_OUT, k)) return;
             int c0, nc;
             tile_cells(g, t, c0, nc);
-            unsigned char* st = smem + (size_t)s * stage_bytes;
-            S* stL = reinterpret_cast<S*>(st);
-            S* stR = reinterpret_cast<S*>(st + offR);
-            double* stF = reinterpret_cast<double*>(st + offF);
-            if (lane == 0) {
-                meta[s][0] = n_slots;
-                meta[s][1] = nc;
-                meta[s][2] = c0;
-                __threadfence_block();
-                *reinterpret_cast<volatile int*>(&stage_tile[s]) = k;
-                const uint32_t bytes = (uint32_t)n_slots * (uint32_t)frec<S>::bytes + (uint32_t)g.frec_stride +
-                                       (with_dt ? 4u * (uint32_t)T * (uint32_t)sizeof(S) : 0u);
-                ac::mbar_arrive_expect_tx(&full[s], bytes);
-            }
-            __syncwarp();
-            const int n_q = 3 * (1 + n_ent);
-            const bool inl = n_ent <= TILE_INLINE_ENT;
-            for (int q0 = 0; q0 < n_q; q0 += 32) {
-                const int q = q0 + lane, e = q / 3 - 1, which = q % 3;
-                int idx = 12 + 5 * (e < 0 ? 0 : e);
-                idx = idx > 59 ? 59 : idx;
-                int f0 = td_get(cur, idx), count = td_get(cur, idx + 1), slot = td_get(cur, idx + 3);
-                if (!inl && e >= 0 && q < n_q) {
-                    const int* te = g.tile_ent + 5 * (size_t)(ent_off + e);
-                    f0 = __ldg(te); count = __ldg(te + 1); slot = __ldg(te + 3);
-                }
-                if (e < 0) { f0 = h0; count = nh; slot = 0; }
-                if (q >= n_q || count <= 0) continue;
-                const uint32_t bytes = (uint32_t)count * (which == 2 ? 48u : 6u * (uint32_t)sizeof(S));
-                if (which == 0) ac::bulk_g2s(stL + (long)slot * 6, A.sideL + (long)f0 * 6, bytes, &full[s]);
-                else if (which == 1) ac::bulk_g2s(stR + (long)slot * 6, A.sideR + (long)f0 * 6, bytes, &full[s]);
-                else ac::bulk_g2s(stF + (long)slot * 6, g.f_frame6 + (long)f0 * 6, bytes, &full[s]);
-            }
-            if (lane == 31) ac::bulk_g2s(st + offRec, g.t_frec + (size_t)t * g.frec_stride, (uint32_t)g.frec_stride, &full[s]);
-            if (with_dt && lane >= 27 && lane < 31) {
-                const int v = lane - 27;
-                const S* src = A.fs[v < 3 ? F_VX + v : F_T] + c0;
-                ac::bulk_g2s(st + offDt + (size_t)v * T * sizeof(S), src, (uint32_t)T * (uint32_t)sizeof(S), &full[s]);
-            }
-            cur = nxt;
+            unsigned char* st = smem + (size_t)s * in_bytes;
+            unsigned char* fb = fb_base + (size_t)o * fb_bytes;
+            n_slots_of[s] = pi2;
+            meta[o][0] = nc;
+            meta[o][1] = c0;
+            meta[o][2] = t;
+            __threadfence_block();
+            *reinterpret_cast<volatile int*>(&fb_tile[o]) = k;
+            *reinterpret_cast<volatile int*>(&stage_tile[s]) = k;
+            const uint32_t pbytes = (uint32_t)pi1 * 6u * (uint32_t)sizeof(S);
+            ac::mbar_arrive_expect_tx(&full_in[s], pbytes + (uint32_t)g.freca_stride);
+            ac::mbar_arrive_expect_tx(&rec_full[o], (uint32_t)g.frec_stride + (with_dt ? 4u * (uint32_t)T * (uint32_t)sizeof(S) : 0u));
+            ac::bulk_g2s(st, A.sidesP + (size_t)pi0 * 6, pbytes, &full_in[s]);
+            ac::bulk_g2s(st + offA, g.t_freca + (size_t)t * g.freca_stride, (uint32_t)g.freca_stride, &full_in[s]);
+            ac::bulk_g2s(fb + offRec, g.t_frec + (size_t)t * g.frec_stride, (uint32_t)g.frec_stride, &rec_full[o]);
+            if (with_dt)
+                for (int v = 0; v < 4; v++)
+                    ac::bulk_g2s(fb + offDt + (size_t)v * T * sizeof(S), A.fs[v < 3 ? F_VX + v : F_T] + c0,
+                                 (uint32_t)T * (uint32_t)sizeof(S), &rec_full[o]);
+            pi0 = nx0;
+            pi1 = nx1;
+            pi2 = nx2;
         }
         return;
     }
     // ---- consumers ----
     const int NCH = (cap + 31) >> 5, NCL = (T + 31) >> 5, P = NCH + NCL;
     const int total = (n_my + 1) * P;
+    const unsigned mP = pipe_magic(P), mI = pipe_magic(nsi), mO = pipe_magic(nfb);
     for (;;) {
         const int item = pipe_next_item(&q_head, lane);
         if (item >= total) break;
-        const int m = item / P, r = item % P;
+        const int m = pipe_div(item, mP), r = item - m * P;
         const bool is_flux = r < NCH;
         const int k = is_flux ? m : m - 1;
         if (k < 0 || k >= n_my) continue;
-        const int s = k % nst;
-        if (!pipe_spin_ge(&stage_tile[s], k, A.pipe_dbg, PW_STAGE, k)) return;
-        if (!pipe_wait(&full[s], (k / nst) & 1, A.pipe_dbg, PW_FULL, k)) return;
-        unsigned char* st = smem + (size_t)s * stage_bytes;
-        S* stL = reinterpret_cast<S*>(st);
-        const double* stF = reinterpret_cast<const double*>(st + offF);
+        const int ui = pipe_div(k, mI), uo = pipe_div(k, mO);         // use counts of the stage and of the buffer
+        const int s = k - ui * nsi, o = k - uo * nfb;
+        unsigned char* fb = fb_base + (size_t)o * fb_bytes;
+        S* flux = reinterpret_cast<S*>(fb);
         if (is_flux) {
-            const S* stR = reinterpret_cast<const S*>(st + offR);
+            if (!pipe_spin_ge(&stage_tile[s], k, A.pipe_dbg, PW_STAGE, k)) return;
+            if (!pipe_wait(&full_in[s], ui & 1, A.pipe_dbg, PW_FULL, k)) return;
+            const unsigned char* st = smem + (size_t)s * in_bytes;
+            const S* Pt = reinterpret_cast<const S*>(st);
+            const FRecA Ra = freca_view(st + offA, cap);
             const int slot = r * 32 + lane;
-            if (slot < meta[s][0])
-                flux_from_sides6<DIM, FLUX>(A, stL + (long)slot * 6, stR + (long)slot * 6, stF + (long)slot * 6, stL + (long)slot * 6);
-            ac::fence_proxy_async();        // the flux written over the left side precedes the next bulk copy into the stage
+            const bool active = slot < n_slots_of[s];
+            FluxOperands<S> O;
+            if (active) flux_load_operands(Pt + (long)Ra.lidx[slot] * 6, Pt + (long)Ra.ridx[slot] * 6, Ra.frame + (long)slot * 6, O);
+            // the operands are in registers: once every chunk of the tile has said so the stage is the loader's again
             __syncwarp();
             if (lane == 0) {
                 __threadfence_block();
-                atomicAdd(&done_items[s], 1);
+                if (atomicAdd(&reads_done[s], 1) == NCH - 1) {
+                    reads_done[s] = 0;
+                    __threadfence_block();
+                    *reinterpret_cast<volatile int*>(&stage_free[s]) = k;
+                }
+            }
+            if (active) flux_from_operands<DIM, FLUX>(A, O, flux + (long)slot * 5);
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_block();
+                atomicAdd(&done_items[o], 1);
             }
         } else {
-            // every flux of the tile must be in shared memory
-            if (!pipe_spin_ge(&done_items[s], NCH, A.pipe_dbg, PW_DONE, k)) return;
-            const int nc = meta[s][1], c0 = meta[s][2];
-            const FRec Rc = frec_view(st + offRec, T);
+            if (!pipe_spin_ge(&fb_tile[o], k, A.pipe_dbg, PW_STAGE, k)) return;
+            if (!pipe_wait(&rec_full[o], uo & 1, A.pipe_dbg, PW_REC, k)) return;
+            // every flux of the tile must be in the buffer
+            if (!pipe_spin_ge(&done_items[o], NCH, A.pipe_dbg, PW_DONE, k)) return;
+            const int nc = meta[o][0], c0 = meta[o][1], t = meta[o][2];
+            const FRec Rc = frec_view(fb + offRec, T);
             const int i = (r - NCH) * 32 + lane;
-            if (i < nc) pipe_cell_sum<DIM>(A, c0 + i, i, T, Rc, stL);
+            if (i < nc) pipe_cell_sum<DIM, 5>(A, c0 + i, i, T, Rc, flux);
             if (with_dt) {                      // estimate_dt fused into this evaluation (uniform branch)
-                const S* dtx = reinterpret_cast<const S*>(st + offDt);
+                // the staged frames have left shared memory with the input stage: the tile's interface record in
+                // global memory serves (L2: this block fetched it a few microseconds ago)
+                const S* dtx = reinterpret_cast<const S*>(fb + offDt);
+                const double* frames = freca_view(g.t_freca + (size_t)t * g.freca_stride, cap).frame;
                 double dl = INFINITY;
                 if (i < nc)
                     dl = pipe_cell_dt(re(dtx[i]), re(dtx[T + i]), re(dtx[2 * T + i]), re(dtx[3 * T + i]), re(A.gas.R),
-                                      re(A.gas.gamma), A.signal_factor, i, T, Rc, stF);
+                                      re(A.gas.gamma), A.signal_factor, i, T, Rc, frames);
                 dl = warp_min_d(dl);
                 // order-preserving key of a double (negative local time steps of inverted cells included: the
                 // reference's min picks them, finite_volume.cpp:180): flip all bits of negatives, the sign of
@@ -306,14 +368,15 @@ __global__ void __launch_bounds__(32 * (IBIS_PIPE_F_WARPS + 1), 1) k_flux_pipe(c
                     atomicMin(A.dt_out, b ^ ((b >> 63) ? ~0ull : 0x8000000000000000ull));
                 }
             }
+            ac::fence_proxy_async();            // reads of the cell record precede the next bulk copy into the buffer
             __syncwarp();
             if (lane == 0) {
                 __threadfence_block();
-                if (atomicAdd(&done_items[s], 1) == P - 1) {
-                    // the tile's last item: the stage goes back to the loader
-                    done_items[s] = 0;
+                if (atomicAdd(&done_items[o], 1) == P - 1) {
+                    // the tile's last item: the buffer goes back to the loader
+                    done_items[o] = 0;
                     __threadfence_block();
-                    ac::mbar_arrive(&empty[s]);
+                    *reinterpret_cast<volatile int*>(&fb_done[o]) = k;
                 }
             }
         }
@@ -427,33 +490,20 @@ __device__ __forceinline__ void grad_task(const FvArgs<S>& A, const double* wd, 
     }
 }
 
-// store transfer q of a tile from its descriptor ti (a copy in shared memory): q = 0 home left range, 1 home right
-// range, 2 + e entry e (fv_bodies.h::tile_store_xfer reads the descriptor from global memory)
-__device__ __forceinline__ TileXfer tile_store_xfer_ti(const GridDev& g, const int* ti, int q, int n_own_l) {
-    TileXfer x;
-    if (q == 0) { x.f0 = ti[2] + ti[4]; x.count = ti[3] - ti[4]; x.stage = 0; x.slot = ti[4]; x.left = true; }
-    else if (q == 1) { x.f0 = ti[2]; x.count = ti[4] + ti[5]; x.stage = n_own_l; x.slot = 0; x.left = false; }
-    else {
-        const int* te = tile_entry(g, ti, q - 2);
-        x.f0 = te[0]; x.count = te[1]; x.stage = te[4]; x.slot = te[3]; x.left = te[2] == 0;
-    }
-    return x;
-}
-
-// Work items of a block, in queue order: the N_TASKS (cell, variable) items of its m-th tile, then the STORE item of
-// tile m - 1 (the tile's side records leave the staging buffer as a handful of bulk stores; queued behind the next
-// tile's items so that the records are normally complete when a warp gets there).  Input stages recycle through
-// mbarriers guarded by stage_tile (see k_flux_pipe); the staging buffers through the monotone counter out_done.
+// Work items of a block, in queue order: the N_TASKS (cell, variable) items of its tiles.  The warp that completes a
+// tile's last item sends the tile's side records off (the push list of the tile's record: bulk stores out of the
+// staging buffer) and hands the input stage back.  Input stages recycle through an mbarrier guarded by stage_tile
+// (see k_flux_pipe), the staging buffers through the monotone counter out_done.
 template <int DIM, int NF, int T, typename S>
-__global__ void __launch_bounds__(32 * (IBIS_PIPE_G_WARPS + 1), 1)
+__global__ void __launch_bounds__(32 * (IBIS_PIPE_G_WARPS + IBIS_PIPE_G_LOADERS), 1)
     k_grad_pipe(const FvArgs<S> A, const int* __restrict__ tile_list, const int n_list, const int nsi, const int nso) {
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ uint64_t rec_full[PIPE_MAX_STAGES], full[PIPE_MAX_STAGES], empty[PIPE_MAX_STAGES];
-    __shared__ int stage_tile[PIPE_MAX_STAGES], done_tasks[PIPE_MAX_STAGES], out_done[PIPE_MAX_STAGES],
-        meta[PIPE_MAX_STAGES][4], q_head;
+    __shared__ uint64_t full[PIPE_MAX_STAGES];
+    __shared__ int stage_tile[PIPE_MAX_STAGES], stage_free[PIPE_MAX_STAGES], done_tasks[PIPE_MAX_STAGES], out_done[PIPE_MAX_STAGES],
+        nc_of[PIPE_MAX_STAGES], q_head;
     const GridDev& g = A.g;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ncw = (int)(blockDim.x >> 5) - 1;
+    const int ncw = (int)(blockDim.x >> 5) - IBIS_PIPE_G_LOADERS;
     const int svs = T + g.halo_cap;
     constexpr int WD_BYTES = 2 * NF * 3 * T * 8;
     const size_t in_bytes = grad_stage_bytes<S>(NF, T, g.grec_stride, g.halo_cap);
@@ -461,10 +511,9 @@ __global__ void __launch_bounds__(32 * (IBIS_PIPE_G_WARPS + 1), 1)
     unsigned char* out_base = smem + (size_t)nsi * in_bytes;
     if (threadIdx.x == 0) {
         for (int s = 0; s < nsi; s++) {
-            ac::mbar_init(&rec_full[s], 1);
             ac::mbar_init(&full[s], 33);          // the loader's arrive.expect_tx + one cp.async arrival per lane
-            ac::mbar_init(&empty[s], 1);
             stage_tile[s] = -1;
+            stage_free[s] = -1;
             done_tasks[s] = 0;
         }
         for (int o = 0; o < nso; o++) out_done[o] = -1;
@@ -473,115 +522,147 @@ __global__ void __launch_bounds__(32 * (IBIS_PIPE_G_WARPS + 1), 1)
     }
     __syncthreads();
     const int n_my = (int)blockIdx.x < n_list ? (n_list - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-    if (warp == ncw) {
-        // ---- loader: records IBIS_PIPE_LOOKAHEAD tiles ahead of the state gather ----
-        const int la = IBIS_PIPE_LOOKAHEAD < nsi ? IBIS_PIPE_LOOKAHEAD : nsi - 1;
-        for (int k = 0; k < n_my + la; k++) {
-            if (k < n_my) {
-                const int s = k % nsi;
-                const int idx = (int)blockIdx.x + k * (int)gridDim.x;
-                const int t = tile_list ? __ldg(tile_list + idx) : idx;
-                if (k >= nsi && !pipe_wait(&empty[s], ((k / nsi) - 1) & 1, A.pipe_dbg, 16 + PW_EMPTY, k)) return;
-                unsigned char* st = smem + (size_t)s * in_bytes;
-                if (lane == 0) {
-                    int c0, nc;
-                    tile_cells(g, t, c0, nc);
-                    meta[s][0] = t;
-                    meta[s][1] = nc;
-                    meta[s][2] = c0;
-                    __threadfence_block();
-                    *reinterpret_cast<volatile int*>(&stage_tile[s]) = k;
-                    ac::mbar_arrive_expect_tx(&rec_full[s], (uint32_t)WD_BYTES + (uint32_t)g.grec_stride);
-                    ac::bulk_g2s(st, g.t_wd + (size_t)t * (WD_BYTES / 8), (uint32_t)WD_BYTES, &rec_full[s]);
-                    ac::bulk_g2s(st + WD_BYTES, g.t_grec + (size_t)t * g.grec_stride, (uint32_t)g.grec_stride, &rec_full[s]);
-                }
-                __syncwarp();
-            }
-            if (k >= la) {
-                const int kk = k - la, s = kk % nsi;
-                if (!pipe_wait(&rec_full[s], (kk / nsi) & 1, A.pipe_dbg, 16 + PW_REC, kk)) return;
-                unsigned char* st = smem + (size_t)s * in_bytes;
-                const GRec R = grec_view(st + WD_BYTES, NF, T);
-                S* sv = reinterpret_cast<S*>(st + WD_BYTES + g.grec_stride);
-                const int c0 = meta[s][2];
-                const int n_halo = R.hdr[0];
-                // own cells: contiguous rows (bulk copies when 16-byte aligned), halo list: gathered
-                const bool bulk_own = ((size_t)c0 * sizeof(S)) % 16 == 0;
-                if (lane == 0) ac::mbar_arrive_expect_tx(&full[s], bulk_own ? 5u * (uint32_t)T * (uint32_t)sizeof(S) : 0u);
-                __syncwarp();
-                if (bulk_own) {
-                    if (lane < 5) ac::bulk_g2s(sv + (size_t)lane * svs, A.rc.val[lane] + c0, (uint32_t)T * (uint32_t)sizeof(S), &full[s]);
-                } else {
-                    for (int q = lane; q < 5 * T; q += 32) {
-                        const int v = q / T, i = q % T;
-                        ac::cp_async_small<(int)sizeof(S)>(sv + (size_t)v * svs + i, A.rc.val[v] + c0 + i);
-                    }
-                }
-                for (int h = lane; h < n_halo; h += 32) {
-                    const int id = R.halo[h];
+    if (warp >= ncw) {
+        // ---- loaders: loader w takes the block's tiles w, w + NL, ...  Per tile the WLS slice, the record and five
+        // state rows as bulk copies, the halo list's state as cp.async gathers; the halo ids of the loader's NEXT tile
+        // are read from global memory (L2: prefetched) one tile ahead, so that the gathers of a tile are issued in the
+        // same breath as its bulk copies.  One warp issues a tile's ~25 dependent instructions per lane in about a
+        // microsecond: several loaders keep the stages full ----
+        const int step = (int)gridDim.x, w = warp - ncw;
+        constexpr int NL = IBIS_PIPE_G_LOADERS, PF = (IBIS_PIPE_PREFETCH + NL - 1) / NL * NL;
+        const int hoff = 4 * NF * T + 16 + 12 * g.push_cap;                   // halo list inside the record
+        auto tile_at = [&](int k) { const int idx = (int)blockIdx.x + k * step; return tile_list ? __ldg(tile_list + idx) : idx; };
+        int ids[PIPE_HALO_REGS], n_halo = 0, ids_n[PIPE_HALO_REGS], n_halo_n = 0;
+        auto fetch_ids = [&](int t, int* out, int& nh) {
+            const unsigned char* rec = g.t_grec + (size_t)t * g.grec_stride;
+            nh = __ldg(reinterpret_cast<const int*>(rec + 4 * NF * T));
+            const int* hl = reinterpret_cast<const int*>(rec + hoff);
 #pragma unroll
-                    for (int v = 0; v < 5; v++) ac::cp_async_small<(int)sizeof(S)>(sv + (size_t)v * svs + T + h, A.rc.val[v] + id);
-                }
-                ac::cp_async_mbar_arrive_noinc(&full[s]);
+            for (int q = 0; q < PIPE_HALO_REGS; q++) out[q] = (lane + 32 * q < g.halo_cap) ? __ldg(hl + lane + 32 * q) : 0;
+        };
+        if (w < n_my) fetch_ids(tile_at(w), ids, n_halo);
+        for (int k = w; k < n_my; k += NL) {
+            const int t = tile_at(k), s = k % nsi;
+            if (k + PF < n_my && lane < 7) {                  // L2 prefetch of a later tile of this loader
+                const int tp = tile_at(k + PF);
+                int c0p, ncp;
+                tile_cells(g, tp, c0p, ncp);
+                if (lane == 0) ac::bulk_prefetch_l2(g.t_wd + (size_t)tp * (WD_BYTES / 8), (uint32_t)WD_BYTES);
+                else if (lane == 1) ac::bulk_prefetch_l2(g.t_grec + (size_t)tp * g.grec_stride, (uint32_t)g.grec_stride);
+                else if (((size_t)c0p * sizeof(S)) % 16 == 0) ac::bulk_prefetch_l2(A.rc.val[lane - 2] + c0p, (uint32_t)T * (uint32_t)sizeof(S));
             }
+            if (k + NL < n_my) fetch_ids(tile_at(k + NL), ids_n, n_halo_n);   // in flight during the wait below
+            if (k >= nsi && !pipe_spin_ge(&stage_free[s], k - nsi, A.pipe_dbg, 16 + PW_EMPTY, k)) return;
+            unsigned char* st = smem + (size_t)s * in_bytes;
+            S* sv = reinterpret_cast<S*>(st + WD_BYTES + g.grec_stride);
+            int c0, nc;
+            tile_cells(g, t, c0, nc);
+            // own cells: contiguous rows (bulk copies when 16-byte aligned), halo list: gathered
+            const bool bulk_own = ((size_t)c0 * sizeof(S)) % 16 == 0;
+            if (lane == 0) {
+                nc_of[s] = nc;
+                __threadfence_block();
+                *reinterpret_cast<volatile int*>(&stage_tile[s]) = k;
+                ac::mbar_arrive_expect_tx(&full[s], (uint32_t)WD_BYTES + (uint32_t)g.grec_stride +
+                                                        (bulk_own ? 5u * (uint32_t)T * (uint32_t)sizeof(S) : 0u));
+                ac::bulk_g2s(st, g.t_wd + (size_t)t * (WD_BYTES / 8), (uint32_t)WD_BYTES, &full[s]);
+                ac::bulk_g2s(st + WD_BYTES, g.t_grec + (size_t)t * g.grec_stride, (uint32_t)g.grec_stride, &full[s]);
+                if (bulk_own)
+                    for (int v = 0; v < 5; v++)
+                        ac::bulk_g2s(sv + (size_t)v * svs, A.rc.val[v] + c0, (uint32_t)T * (uint32_t)sizeof(S), &full[s]);
+            }
+            __syncwarp();
+            if (!bulk_own)
+                for (int q = lane; q < 5 * T; q += 32) {
+                    const int v = q / T, i = q % T;
+                    ac::cp_async_small<(int)sizeof(S)>(sv + (size_t)v * svs + i, A.rc.val[v] + c0 + i);
+                }
+#pragma unroll
+            for (int q = 0; q < PIPE_HALO_REGS; q++) {
+                const int h = lane + 32 * q;
+                if (h < n_halo) {
+#pragma unroll
+                    for (int v = 0; v < 5; v++) ac::cp_async_small<(int)sizeof(S)>(sv + (size_t)v * svs + T + h, A.rc.val[v] + ids[q]);
+                }
+            }
+            ac::cp_async_mbar_arrive_noinc(&full[s]);
+#pragma unroll
+            for (int q = 0; q < PIPE_HALO_REGS; q++) ids[q] = ids_n[q];
+            n_halo = n_halo_n;
         }
         return;
     }
     // ---- consumers ----
-    constexpr int N_THERMO = T / 16, NV = DIM == 3 ? 3 : 2, N_TASKS = N_THERMO + NV * (T / 32), P = N_TASKS + 1;
-    const int total = (n_my + 1) * P;
+    constexpr int N_THERMO = T / 16, NV = DIM == 3 ? 3 : 2, N_TASKS = N_THERMO + NV * (T / 32);
+    const int total = n_my * N_TASKS;
+    const unsigned mT = pipe_magic(N_TASKS), mI = pipe_magic(nsi), mO = pipe_magic(nso);
+    // the bulk stores this warp issued for tile pend_k out of staging buffer pend_o and has not yet seen drained
+    int pend_o = -1, pend_k = 0;
+    auto flush_pending = [&]() {
+        if (pend_o < 0) return;
+        ac::bulk_commit_wait_read();                       // the staging buffer may be written again after this
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence_block();
+            *reinterpret_cast<volatile int*>(&out_done[pend_o]) = pend_k;
+        }
+        pend_o = -1;
+    };
     for (;;) {
         const int item = pipe_next_item(&q_head, lane);
         if (item >= total) break;
-        const int m = item / P, r = item % P;
-        const bool is_task = r < N_TASKS;
-        const int k = is_task ? m : m - 1;
-        if (k < 0 || k >= n_my) continue;
-        const int s = k % nsi, o = k % nso;
+        const int k = pipe_div(item, mT), r = item - k * N_TASKS;
+        const int ui = pipe_div(k, mI);
+        const int s = k - ui * nsi, o = k - pipe_div(k, mO) * nso;
+        const bool had_pending = pend_o >= 0;
         if (!pipe_spin_ge(&stage_tile[s], k, A.pipe_dbg, 16 + PW_STAGE, k)) return;
-        if (!pipe_wait(&rec_full[s], (k / nsi) & 1, A.pipe_dbg, 16 + PW_REC, k)) return;
+        if (!pipe_wait(&full[s], ui & 1, A.pipe_dbg, 16 + PW_FULL, k)) return;
+        // the staging buffer is free once the stores of the tile nso tiles back have read it (never wait for
+        // another warp's publication while sitting on one's own)
+        if (k >= nso) {
+            flush_pending();
+            if (!pipe_spin_ge(&out_done[o], k - nso, A.pipe_dbg, 16 + PW_OUT, k)) return;
+        }
         unsigned char* st = smem + (size_t)s * in_bytes;
-        const GRec R = grec_view(st + WD_BYTES, NF, T);
+        const GRec R = grec_view(st + WD_BYTES, NF, T, g.push_cap);
         S* stg = reinterpret_cast<S*>(out_base + (size_t)o * out_bytes);
-        if (is_task) {
-            if (!pipe_wait(&full[s], (k / nsi) & 1, A.pipe_dbg, 16 + PW_FULL, k)) return;
-            // the staging buffer is free once the stores of the tile nso tiles back have read it
-            if (k >= nso && !pipe_spin_ge(&out_done[o], k - nso, A.pipe_dbg, 16 + PW_OUT, k)) return;
-            const double* wd = reinterpret_cast<const double*>(st);
-            const S* sv = reinterpret_cast<const S*>(st + WD_BYTES + g.grec_stride);
-            grad_task<DIM, NF, T, S>(A, wd, R, sv, svs, stg, r, meta[s][1], lane);
-            ac::fence_proxy_async();                       // the staging writes -> visible to the TMA unit
+        const double* wd = reinterpret_cast<const double*>(st);
+        const S* sv = reinterpret_cast<const S*>(st + WD_BYTES + g.grec_stride);
+        grad_task<DIM, NF, T, S>(A, wd, R, sv, svs, stg, r, nc_of[s], lane);
+        ac::fence_proxy_async();                           // the staging writes -> visible to the TMA unit
+        __syncwarp();
+        int d = 0;
+        if (lane == 0) {
+            __threadfence_block();
+            d = atomicAdd(&done_tasks[s], 1);
+        }
+        d = __shfl_sync(0xffffffffu, d, 0);
+        if (d == N_TASKS - 1) {
+            // the tile's last item: its side records are complete in the staging buffer and leave as a handful of
+            // bulk stores; the input stage goes back to the loader at once, the staging buffer when this warp has
+            // seen the stores drained -- one item later, so that it does not sit and wait for them
+            __threadfence_block();
+            flush_pending();
+            ac::fence_proxy_async();
+            const int n_push = R.hdr[3];
+            for (int q = lane; q < n_push; q += 32) {
+                const int src = R.push[3 * q], count = R.push[3 * q + 1], dst = R.push[3 * q + 2];
+                if (count > 0) ac::bulk_s2g(A.sidesP + (size_t)dst * 6, stg + (long)src * 6, (uint32_t)count * 6 * (uint32_t)sizeof(S));
+            }
+            ac::bulk_commit();
             __syncwarp();
             if (lane == 0) {
-                __threadfence_block();
-                atomicAdd(&done_tasks[s], 1);
-            }
-        } else {
-            // the tile's side records are complete in the staging buffer: they leave as a handful of bulk stores
-            if (!pipe_spin_ge(&done_tasks[s], N_TASKS, A.pipe_dbg, 16 + PW_DONE, k)) return;
-            ac::fence_proxy_async();
-            const int n_ent = R.info[7], n_own_l = R.hdr[2];
-            for (int q = lane; q < 2 + n_ent; q += 32) {
-                const TileXfer x = tile_store_xfer_ti(g, R.info, q, n_own_l);
-                if (x.count > 0) {
-                    S* dst = (x.left ? A.sideL : A.sideR) + (long)x.f0 * 6;
-                    ac::bulk_s2g(dst, stg + (long)x.stage * 6, (uint32_t)x.count * 6 * (uint32_t)sizeof(S));
-                }
-            }
-            __syncwarp();
-            if (lane == 0) {                               // the input stage goes back to the loader
                 done_tasks[s] = 0;
                 __threadfence_block();
-                ac::mbar_arrive(&empty[s]);
+                *reinterpret_cast<volatile int*>(&stage_free[s]) = k;
             }
-            ac::bulk_commit_wait_read();                   // the staging buffer may be written again after this
-            __syncwarp();
-            if (lane == 0) {
-                __threadfence_block();
-                *reinterpret_cast<volatile int*>(&out_done[o]) = k;
-            }
+            pend_o = o;
+            pend_k = k;
+        } else if (had_pending) {
+            flush_pending();
         }
     }
+    flush_pending();
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -600,23 +681,20 @@ static bool set_smem(ibis_b200_ctx* c, K kernel, size_t smem) {
 template <int DIM, int NF, int T, typename S>
 static void launch_grad_pipe_t(ibis_b200_ctx* c, const FvArgs<S>& A, const int* list, int n_list) {
     const size_t in_b = grad_stage_bytes<S>(NF, T, A.g.grec_stride, A.g.halo_cap), out_b = grad_out_bytes<S>(A.g.stage_cap);
-    // stages: as many as fit, inputs : outputs about 3 : 2
-    int nsi = 2, nso = 1;
-    for (;;) {
-        const bool grow_in = nsi < PIPE_MAX_STAGES && 2 * nsi <= 3 * nso + 2;
-        const size_t next = (size_t)(nsi + (grow_in ? 1 : 0)) * in_b + (size_t)(nso + (grow_in ? 0 : 1)) * out_b;
-        if (next > PIPE_SMEM_BUDGET || (!grow_in && nso >= PIPE_MAX_STAGES)) break;
-        if (grow_in) nsi++; else nso++;
-    }
-    const size_t smem = (size_t)nsi * in_b + (size_t)nso * out_b;
-    if (smem > PIPE_SMEM_BUDGET) {
+    // staging buffers: four when they fit (items + drain of a tile overlap the next tiles'), the rest input stages
+    int nso = 4;
+    while (nso > 1 && (size_t)nso * out_b + 2 * in_b > PIPE_SMEM_BUDGET) nso--;
+    int nsi = (size_t)nso * out_b < PIPE_SMEM_BUDGET ? (int)((PIPE_SMEM_BUDGET - (size_t)nso * out_b) / in_b) : 0;
+    if (nsi > PIPE_MAX_STAGES) nsi = PIPE_MAX_STAGES;
+    if (nsi < 2 || A.g.halo_cap > 32 * PIPE_HALO_REGS) {
         if (c->last_error.empty()) c->last_error = "pass G': a tile does not fit shared memory";
         return;
     }
+    const size_t smem = (size_t)nsi * in_b + (size_t)nso * out_b;
     auto kernel = k_grad_pipe<DIM, NF, T, S>;
     if (!set_smem(c, kernel, smem)) return;
     const int grid = n_list < c->n_sm ? n_list : c->n_sm;
-    kernel<<<grid, 32 * (IBIS_PIPE_G_WARPS + 1), smem, c->stream>>>(A, list, n_list, nsi, nso);
+    kernel<<<grid, 32 * (IBIS_PIPE_G_WARPS + IBIS_PIPE_G_LOADERS), smem, c->stream>>>(A, list, n_list, nsi, nso);
 }
 
 template <int DIM, int T, typename S>
@@ -651,17 +729,29 @@ template void launch_grad_sides<dual>(ibis_b200_ctx*, const FvArgs<dual>&, int);
 
 template <int DIM, int FLUX, typename S>
 static void launch_flux_pipe_k(ibis_b200_ctx* c, const FvArgs<S>& A) {
-    const size_t stage = flux_stage_bytes<S>(A.g.tile_cap, A.g.frec_stride, A.g.tile, A.dt_out != nullptr);
-    int nst = (int)(PIPE_SMEM_BUDGET / stage);
-    if (nst > PIPE_MAX_STAGES) nst = PIPE_MAX_STAGES;
-    if (nst < 2) {
+    const size_t in_b = flux_in_bytes<S>(A.g.p_cap, A.g.freca_stride);
+    const size_t fb_b = flux_fb_bytes<S>(A.g.tile_cap, A.g.frec_stride, A.g.tile, A.dt_out != nullptr);
+    // three input stages cover the load latency; the rest of shared memory holds flux buffers
+    int nsi = 3;
+    int nfb = PIPE_SMEM_BUDGET > (size_t)nsi * in_b ? (int)((PIPE_SMEM_BUDGET - (size_t)nsi * in_b) / fb_b) : 0;
+    if (nfb < 3) {
+        nsi = 2;
+        nfb = PIPE_SMEM_BUDGET > (size_t)nsi * in_b ? (int)((PIPE_SMEM_BUDGET - (size_t)nsi * in_b) / fb_b) : 0;
+    }
+    if (nfb > PIPE_MAX_STAGES) {
+        nfb = PIPE_MAX_STAGES;
+        const int more = (int)((PIPE_SMEM_BUDGET - (size_t)nfb * fb_b) / in_b);
+        nsi = more > PIPE_MAX_STAGES ? PIPE_MAX_STAGES : more;
+    }
+    if (nfb < 2) {
         if (c->last_error.empty()) c->last_error = "pass F': a tile does not fit shared memory";
         return;
     }
+    const size_t smem = (size_t)nsi * in_b + (size_t)nfb * fb_b;
     auto kernel = k_flux_pipe<DIM, FLUX, S>;
-    if (!set_smem(c, kernel, (size_t)nst * stage)) return;
+    if (!set_smem(c, kernel, smem)) return;
     const int grid = A.g.n_tiles < c->n_sm ? A.g.n_tiles : c->n_sm;
-    kernel<<<grid, 32 * (IBIS_PIPE_F_WARPS + 1), (size_t)nst * stage, c->stream>>>(A, nst);
+    kernel<<<grid, 32 * (IBIS_PIPE_F_WARPS + IBIS_PIPE_F_LOADERS), smem, c->stream>>>(A, nsi, nfb);
 }
 template <int DIM, typename S>
 static void launch_flux_pipe_dim(ibis_b200_ctx* c, const FvArgs<S>& A) {

@@ -139,7 +139,7 @@ IBIS_HD Flux5<S> flux_ausmdv(const Side<S>& L, const Side<S>& R_, const Gas<S>& 
         pLplus = pL * (ML + 1.0) * (ML + 1.0) * (2.0 - ML) * 0.25;
         uLplus = alphaL * ((uL + am) * (uL + am) / (4.0 * am) - duL) + duL;
     } else {
-        pLplus = pL * duL / uL;
+        pLplus = div_z(pL * duL, uL);
         uLplus = duL;
     }
     S pRminus, uRminus;
@@ -148,7 +148,7 @@ IBIS_HD Flux5<S> flux_ausmdv(const Side<S>& L, const Side<S>& R_, const Gas<S>& 
         pRminus = pR * (MR - 1.0) * (MR - 1.0) * (2.0 + MR) * 0.25;
         uRminus = alphaR * (-(uR - am) * (uR - am) / (4.0 * am) - duR) + duR;
     } else {
-        pRminus = pR * duR / uR;
+        pRminus = div_z(pR * duR, uR);
         uRminus = duR;
     }
     S ru_half = uLplus * rL + uRminus * rR;
@@ -156,7 +156,7 @@ IBIS_HD Flux5<S> flux_ausmdv(const Side<S>& L, const Side<S>& R_, const Gas<S>& 
 
     S dp = pL - pR;
     const S K_SWITCH = 10.0;
-    dp = K_SWITCH * abs_(dp) / min_(pL, pR);
+    dp = div_z(K_SWITCH * abs_(dp), min_(pL, pR));
     S s = 0.5 * min_(1.0, dp);
     S ru2_AUSMV = uLplus * rL * uL + uRminus * rR * uR;
     S ru2_AUSMD = 0.5 * (ru_half * (uL + uR) - abs_(ru_half) * (uR - uL));
@@ -232,8 +232,8 @@ IBIS_HD Flux5<S> flux_ldfss2(const Side<S>& L, const Side<S>& R_, const Gas<S>& 
 
     S Mhalf = 0.25 * betaL * betaR * pow2_((sqrt_(0.5 * (ML * ML + MR * MR)) - 1.0));
 
-    S MhalfL = Mhalf * (1.0 - ((pL - pR) / (pL + pR) + delta * (abs_(pL - pR) / pL)));
-    S MhalfR = Mhalf * (1.0 + ((pL - pR) / (pL + pR) - delta * (abs_(pL - pR) / pR)));
+    S MhalfL = Mhalf * (1.0 - (div_z(pL - pR, pL + pR) + delta * div_z(abs_(pL - pR), pL)));
+    S MhalfR = Mhalf * (1.0 + (div_z(pL - pR, pL + pR) - delta * div_z(abs_(pL - pR), pR)));
 
     S CL = alphaL * (1.0 + betaL) * ML - betaL * MpL - MhalfL;
     S CR = alphaR * (1.0 + betaR) * MR - betaR * MmR + MhalfR;

@@ -123,8 +123,8 @@ void launch_residual(ibis_b200_ctx* c, const FvArgs<S>& A) {
 template void launch_residual<double>(ibis_b200_ctx*, const FvArgs<double>&);
 template void launch_residual<dual>(ibis_b200_ctx*, const FvArgs<dual>&);
 
-// tile-major copies of the static tables, as the device pack kernels write them (fv_pipe.cu)
-void launch_pack_pipe_tables(ibis_b200_ctx* c, double* t_wd, double* fr6) {
+// tile-major copy of the WLS tables, as the device pack kernel writes it (fv_pipe.cu)
+void launch_pack_pipe_tables(ibis_b200_ctx* c, double* t_wd) {
     const GridDev& g = c->g;
     const int T = g.tile, NT = g.pipe_nf * 3;
     for (int cell = 0; cell < g.n_grad; cell++) {
@@ -137,17 +137,12 @@ void launch_pack_pipe_tables(ibis_b200_ctx* c, double* t_wd, double* fr6) {
             dst[(size_t)(NT + r) * T] = g.cf_d[(size_t)r * g.cstride + cell];
         }
     }
-    for (int f = 0; f < g.n_faces; f++)
-        for (int k = 0; k < 3; k++) {
-            fr6[(size_t)f * 6 + k] = g.f_t1[(size_t)k * g.fstride + f];
-            fr6[(size_t)f * 6 + 3 + k] = g.f_t2[(size_t)k * g.fstride + f];
-        }
     c->launches++;
 }
 
 // pass G' tile by tile, on the packed per-tile records the device kernel stages: the state of the tile's own
-// cells and of its halo list, every cell's five variables into the staging buffer, then the tile's store
-// transfers (the bulk stores of the device kernel) as memcpy
+// cells and of its halo list, every cell's five variables into the staging buffer, then the tile's push list (the
+// bulk stores of the device kernel) as memcpy
 template <typename S>
 void launch_grad_sides(ibis_b200_ctx* c, const FvArgs<S>& A, int which) {
     const GridDev& g = A.g;
@@ -160,7 +155,7 @@ void launch_grad_sides(ibis_b200_ctx* c, const FvArgs<S>& A, int which) {
 #pragma omp for
         for (int k = 0; k < n_list; k++) {
             const int t = list ? list[k] : k;
-            const GRec R = grec_view(g.t_grec + (size_t)t * g.grec_stride, NF, T);
+            const GRec R = grec_view(g.t_grec + (size_t)t * g.grec_stride, NF, T, g.push_cap);
             const double* wd = g.t_wd + (size_t)t * 2 * NF * 3 * T;
             int c0, nc;
             tile_cells(g, t, c0, nc);
@@ -179,11 +174,10 @@ void launch_grad_sides(ibis_b200_ctx* c, const FvArgs<S>& A, int which) {
                 if (g.dim == 3) { GS_NF(3) } else { GS_NF(2) }
 #undef GS_NF
             }
-            const int n_own_l = R.hdr[2];
-            for (int q = 0; q < 2 + R.info[7]; q++) {
-                const TileXfer x = tile_store_xfer(g, t, q, n_own_l);
-                S* dst = (x.left ? A.sideL : A.sideR) + (long)x.f0 * 6;
-                for (long e = 0; e < (long)x.count * 6; e++) dst[e] = stg[(size_t)x.stage * 6 + e];
+            for (int q = 0; q < R.hdr[3]; q++) {
+                const int src = R.push[3 * q], count = R.push[3 * q + 1];
+                S* dst = A.sidesP + (long)R.push[3 * q + 2] * 6;
+                for (long e = 0; e < (long)count * 6; e++) dst[e] = stg[(size_t)src * 6 + e];
             }
         }
     }
@@ -192,32 +186,23 @@ void launch_grad_sides(ibis_b200_ctx* c, const FvArgs<S>& A, int which) {
 template void launch_grad_sides<double>(ibis_b200_ctx*, const FvArgs<double>&, int);
 template void launch_grad_sides<dual>(ibis_b200_ctx*, const FvArgs<dual>&, int);
 
-// pass F' tile by tile: the tile's load transfers, the fluxes in place, the cell sums from the tile's cell record
+// pass F' tile by tile: the tile's side-state array and interface record, the fluxes, the cell sums from the
+// tile's cell record
 template <typename S>
 void launch_flux_tile(ibis_b200_ctx* c, const FvArgs<S>& A) {
     const GridDev& g = A.g;
-    const int T = g.tile;
+    const int T = g.tile, cap = g.tile_cap;
 #pragma omp parallel
     {
-        const size_t cap = std::max(g.tile_cap, 1);
-        std::vector<S> stL(6 * cap), stR(6 * cap);
-        std::vector<double> stF(6 * cap);
+        std::vector<S> flux((size_t)5 * std::max(cap, 1));
 #pragma omp for
         for (int t = 0; t < g.n_tiles; t++) {
-            const int* ti = g.tile_info + TILE_INFO * t;
-            int n = ti[3];
-            for (int q = 0; q < 1 + ti[7]; q++) {
-                const TileXfer x = tile_load_xfer(g, t, q);
-                for (long k = 0; k < (long)x.count * 6; k++) {
-                    stL[(size_t)x.slot * 6 + k] = A.sideL[(long)x.f0 * 6 + k];
-                    stR[(size_t)x.slot * 6 + k] = A.sideR[(long)x.f0 * 6 + k];
-                    stF[(size_t)x.slot * 6 + k] = g.f_frame6[(long)x.f0 * 6 + k];
-                }
-                n = std::max(n, x.slot + x.count);
-            }
+            const int n = g.tile_info[TILE_INFO * t + 9];
+            const S* P = A.sidesP + (long)g.t_pinfo[2 * t] * 6;
+            const FRecA Ra = freca_view(g.t_freca + (size_t)t * g.freca_stride, cap);
 #define TILE_FLUX(D, F, O)                                                                          \
     for (int s = 0; s < n; s++)                                                                     \
-        flux_from_sides6<D, F>(A, &stL[(size_t)s * 6], &stR[(size_t)s * 6], &stF[(size_t)s * 6], &stL[(size_t)s * 6]);
+        flux_from_sides6<D, F>(A, P + (long)Ra.lidx[s] * 6, P + (long)Ra.ridx[s] * 6, Ra.frame + (long)s * 6, &flux[(size_t)s * 5]);
             EMU_FLUX_CALL(TILE_FLUX)
 #undef TILE_FLUX
             const FRec Rc = frec_view(g.t_frec + (size_t)t * g.frec_stride, T);
@@ -225,12 +210,12 @@ void launch_flux_tile(ibis_b200_ctx* c, const FvArgs<S>& A) {
             tile_cells(g, t, c0, nc);
             for (int i = 0; i < nc; i++) {
                 const int cell = c0 + i;
-                if (g.dim == 3) pipe_cell_sum<3>(A, cell, i, T, Rc, stL.data());
-                else pipe_cell_sum<2>(A, cell, i, T, Rc, stL.data());
+                if (g.dim == 3) pipe_cell_sum<3, 5>(A, cell, i, T, Rc, flux.data());
+                else pipe_cell_sum<2, 5>(A, cell, i, T, Rc, flux.data());
                 if (A.dt_out) {
                     const double d = pipe_cell_dt(re(A.fs[F_VX][cell]), re(A.fs[F_VY][cell]), re(A.fs[F_VZ][cell]),
                                                   re(A.fs[F_T][cell]), re(A.gas.R), re(A.gas.gamma), A.signal_factor, i, T,
-                                                  Rc, stF.data());
+                                                  Rc, Ra.frame);
 #pragma omp critical
                     {
                         double cur;
