@@ -202,7 +202,7 @@ __host__ __device__ inline size_t flux_fb_bytes(int cap, int frec_stride, int T,
 // stage / buffer) and only then tests the barrier's parity: neither can be recycled while an item of its tile is
 // outstanding, so the barrier is then exactly at the awaited phase or one behind, never two.
 template <int DIM, int FLUX, typename S>
-__global__ void __launch_bounds__(32 * (IBIS_PIPE_F_WARPS + IBIS_PIPE_F_LOADERS), 1) k_flux_pipe(const FvArgs<S> A, const int nsi, const int nfb) {
+__global__ void __launch_bounds__(32 * (IBIS_PIPE_F_WARPS + IBIS_PIPE_F_LOADERS), 1) k_flux_pipe(const FvArgs<S> A, const int nsi, const int nfb, const int pf) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t full_in[PIPE_MAX_STAGES], rec_full[PIPE_MAX_STAGES];
     __shared__ int stage_tile[PIPE_MAX_STAGES], stage_free[PIPE_MAX_STAGES], reads_done[PIPE_MAX_STAGES], n_slots_of[PIPE_MAX_STAGES];
@@ -213,10 +213,10 @@ __global__ void __launch_bounds__(32 * (IBIS_PIPE_F_WARPS + IBIS_PIPE_F_LOADERS)
     const int ncw = (int)(blockDim.x >> 5) - IBIS_PIPE_F_LOADERS;
     const int cap = g.tile_cap, T = g.tile;
     const bool with_dt = A.dt_out != nullptr;
-    const size_t in_bytes = flux_in_bytes<S>(g.p_cap, g.freca_stride), fb_bytes = flux_fb_bytes<S>(cap, g.frec_stride, T, with_dt);
-    const size_t offA = in_bytes - (size_t)g.freca_stride;                 // interface record inside the input stage
-    const size_t offRec = (size_t)cap * 5 * sizeof(S), offDt = offRec + (size_t)g.frec_stride;
-    unsigned char* fb_base = smem + (size_t)nsi * in_bytes;
+    const unsigned in_bytes = (unsigned)flux_in_bytes<S>(g.p_cap, g.freca_stride), fb_bytes = (unsigned)flux_fb_bytes<S>(cap, g.frec_stride, T, with_dt);
+    const unsigned offA = in_bytes - (unsigned)g.freca_stride;             // interface record inside the input stage
+    const unsigned offRec = (unsigned)cap * 5u * (unsigned)sizeof(S), offDt = offRec + (unsigned)g.frec_stride;
+    unsigned char* fb_base = smem + (unsigned)nsi * in_bytes;
     if (threadIdx.x == 0) {
         for (int s = 0; s < nsi; s++) {
             ac::mbar_init(&full_in[s], 1);
@@ -241,7 +241,8 @@ __global__ void __launch_bounds__(32 * (IBIS_PIPE_F_WARPS + IBIS_PIPE_F_LOADERS)
         // later tile of its own as L2 prefetches ----
         if (lane != 0) return;
         const int step = (int)gridDim.x, w = warp - ncw;
-        constexpr int NL = IBIS_PIPE_F_LOADERS, PF = (IBIS_PIPE_PREFETCH + NL - 1) / NL * NL;
+        constexpr int NL = IBIS_PIPE_F_LOADERS;
+        const int PF = (pf + NL - 1) / NL * NL;
         // {first record, record count} of the tile's side-state array and its slot count, fetched one tile ahead
         int pi0 = 0, pi1 = 0, pi2 = 0;
         if (w < n_my) {
@@ -252,7 +253,7 @@ __global__ void __launch_bounds__(32 * (IBIS_PIPE_F_WARPS + IBIS_PIPE_F_LOADERS)
         }
         for (int k = w; k < n_my; k += NL) {
             const int t = (int)blockIdx.x + k * step, s = k % nsi, o = k % nfb;
-            if (k + PF < n_my) {                              // L2 prefetch of a later tile of this loader
+            if (PF > 0 && k + PF < n_my) {                    // L2 prefetch of a later tile of this loader
                 const size_t tp = (size_t)t + (size_t)PF * step;
                 const int q0 = __ldg(g.t_pinfo + 2 * tp), q1 = __ldg(g.t_pinfo + 2 * tp + 1);
                 ac::bulk_prefetch_l2(A.sidesP + (size_t)q0 * 6, (uint32_t)q1 * 6u * (uint32_t)sizeof(S));
@@ -275,8 +276,8 @@ __global__ void __launch_bounds__(32 * (IBIS_PIPE_F_WARPS + IBIS_PIPE_F_LOADERS)
             if (k >= nfb && !pipe_spin_ge_1(&fb_done[o], k - nfb, A.pipe_dbg, PW_OUT, k)) return;
             int c0, nc;
             tile_cells(g, t, c0, nc);
-            unsigned char* st = smem + (size_t)s * in_bytes;
-            unsigned char* fb = fb_base + (size_t)o * fb_bytes;
+            unsigned char* st = smem + (unsigned)s * in_bytes;
+            unsigned char* fb = fb_base + (unsigned)o * fb_bytes;
             n_slots_of[s] = pi2;
             meta[o][0] = nc;
             meta[o][1] = c0;
@@ -292,7 +293,7 @@ __global__ void __launch_bounds__(32 * (IBIS_PIPE_F_WARPS + IBIS_PIPE_F_LOADERS)
             ac::bulk_g2s(fb + offRec, g.t_frec + (size_t)t * g.frec_stride, (uint32_t)g.frec_stride, &rec_full[o]);
             if (with_dt)
                 for (int v = 0; v < 4; v++)
-                    ac::bulk_g2s(fb + offDt + (size_t)v * T * sizeof(S), A.fs[v < 3 ? F_VX + v : F_T] + c0,
+                    ac::bulk_g2s(fb + offDt + (unsigned)v * (unsigned)T * (unsigned)sizeof(S), A.fs[v < 3 ? F_VX + v : F_T] + c0,
                                  (uint32_t)T * (uint32_t)sizeof(S), &rec_full[o]);
             pi0 = nx0;
             pi1 = nx1;
@@ -304,21 +305,22 @@ __global__ void __launch_bounds__(32 * (IBIS_PIPE_F_WARPS + IBIS_PIPE_F_LOADERS)
     const int NCH = (cap + 31) >> 5, NCL = (T + 31) >> 5, P = NCH + NCL;
     const int total = (n_my + 1) * P;
     const unsigned mP = pipe_magic(P), mI = pipe_magic(nsi), mO = pipe_magic(nfb);
-    for (;;) {
-        const int item = pipe_next_item(&q_head, lane);
-        if (item >= total) break;
+    // the next item is claimed while the current one is worked on (the claim -- a shared-memory atomic and a
+    // shuffle -- is a few hundred cycles of latency that nothing else in the item can hide)
+    for (int item = pipe_next_item(&q_head, lane), next; item < total; item = next) {
+        next = pipe_next_item(&q_head, lane);
         const int m = pipe_div(item, mP), r = item - m * P;
         const bool is_flux = r < NCH;
         const int k = is_flux ? m : m - 1;
         if (k < 0 || k >= n_my) continue;
         const int ui = pipe_div(k, mI), uo = pipe_div(k, mO);         // use counts of the stage and of the buffer
         const int s = k - ui * nsi, o = k - uo * nfb;
-        unsigned char* fb = fb_base + (size_t)o * fb_bytes;
+        unsigned char* fb = fb_base + (unsigned)o * fb_bytes;
         S* flux = reinterpret_cast<S*>(fb);
         if (is_flux) {
             if (!pipe_spin_ge(&stage_tile[s], k, A.pipe_dbg, PW_STAGE, k)) return;
             if (!pipe_wait(&full_in[s], ui & 1, A.pipe_dbg, PW_FULL, k)) return;
-            const unsigned char* st = smem + (size_t)s * in_bytes;
+            const unsigned char* st = smem + (unsigned)s * in_bytes;
             const S* Pt = reinterpret_cast<const S*>(st);
             const FRecA Ra = freca_view(st + offA, cap);
             const int slot = r * 32 + lane;
@@ -406,22 +408,17 @@ __host__ __device__ inline size_t grad_out_bytes(int stage_cap) {
     return ((size_t)stage_cap * 6 * sizeof(S) + 127) / 128 * 128;
 }
 
-// One work item of pass G': 32 (cell, variable) pairs of a tile.
-//   items [0, T / 16):  16 cells x (rho, second thermodynamic variable) -- lanes 0-15 extrapolate rho, lanes 16-31
-//                       the other variable, of the same 16 cells; the two lanes of a cell then close the
-//                       thermodynamic state (gas_model.h:91-117) of half of the cell's faces each;
-//   the others:         32 cells x one velocity component (vx, vy[, vz]).
-// One code path computes the gradient, the limiter and the extrapolation of the lane's variable (var_to_faces);
-// only the epilogue differs.
+// One work item of pass G': 32 cells of a tile x one half of the variables, one cell per lane.
+//   half 0: rho and the second thermodynamic variable, one after the other, then the thermodynamic closure
+//           (gas_model.h:91-117) of every face -> rho p T of the cell's side records;
+//   half 1: the velocity components, one after the other -> vx vy vz of the side records.
+// The cell's neighbour / staging indices are read once per item and serve all its variables.
 template <int DIM, int NF, int T, typename S>
 __device__ __forceinline__ void grad_task(const FvArgs<S>& A, const double* wd, const GRec& R, const S* sv, const int svs,
                                           S* stg, const int task, const int nc, const int lane) {
-    constexpr int N_THERMO = T / 16;
-    const bool thermo = task < N_THERMO;
-    const int q = task - N_THERMO;
-    const int var = thermo ? (lane >> 4) : 2 + q / (T / 32);
-    const int i = thermo ? task * 16 + (lane & 15) : (q % (T / 32)) * 32 + lane;
-    const bool active = i < nc;
+    const int half = task & 1;
+    const int i = (task >> 1) * 32 + lane;
+    if (i >= nc) return;
     const bool limit = A.limiter_on != 0;
     TileTables<NF, T> Tb;
     Tb.w = wd;
@@ -432,71 +429,74 @@ __device__ __forceinline__ void grad_task(const FvArgs<S>& A, const double* wd, 
         fl[j] = R.nbr[j * T + i];
         st[j] = R.stage[j * T + i];
     }
-    const S ui = sv[var * svs + i];
-    S un[NF], r[NF];
-#pragma unroll
-    for (int j = 0; j < NF; j++) un[j] = sv[var * svs + (fl[j] & NBR_LOCAL_MASK)];
-    var_to_faces<DIM, NF>(ui, un, Tb, A.eps, limit, r);
     const int nR = R.hdr[1], n_own_l = R.hdr[2];
-    if (thermo) {
-        S o[NF];
+    if (half == 0) {
+        {
+            // rho: parked in its place in the side records while the second variable is worked out
+            const S ui = sv[i];
+            S un[NF], r0[NF];
 #pragma unroll
-        for (int j = 0; j < NF; j++) o[j] = shfl_xor_s(r[j], 16);
-        constexpr int H = (NF + 1) / 2;
+            for (int j = 0; j < NF; j++) un[j] = sv[fl[j] & NBR_LOCAL_MASK];
+            var_to_faces<DIM, NF>(ui, un, Tb, A.eps, limit, r0);
 #pragma unroll
-        for (int jj = 0; jj < H; jj++) {
-            const int j0 = jj, j1 = H + jj;
-            S rho_j, th_j;
-            int st_j;
-            if (j1 < NF) {
-                rho_j = var ? o[j1] : r[j0];
-                th_j = var ? r[j1] : o[j0];
-                st_j = var ? st[j1] : st[j0];
-            } else {
-                rho_j = r[j0];
-                th_j = o[j0];
-                st_j = var ? 0xFFFF : st[j0];
-            }
-            if (active && st_j != 0xFFFF) side_close_store(A.thermo, A.gas, rho_j, th_j, stg + (long)st_j * 6);
+            for (int j = 0; j < NF; j++)
+                if (st[j] != 0xFFFF) stg[(long)st[j] * 6] = r0[j];
         }
-        // the far side of a boundary interface is the ghost cell itself: zero gradient, unit limiter
-        // (convective_flux.cpp:281-300), i.e. its values, closed thermodynamically like any other side
+        const S ui = sv[svs + i];
+        S un[NF], r1[NF];
 #pragma unroll
-        for (int j = 0; j < NF; j++) {
-            const bool gh = active && st[j] != 0xFFFF && (fl[j] & NBR_GHOST_BIT);
-            if (__any_sync(0xffffffffu, gh)) {
-                const S uo = shfl_xor_s(un[j], 16);
-                if (gh && var == 0) {
-                    const int far_idx = far_stage_index((fl[j] & NBR_LEFT_BIT) != 0, st[j], nR, n_own_l);
-                    side_close_store(A.thermo, A.gas, un[j], uo, stg + (long)far_idx * 6);
-                }
-            }
-        }
-    } else if (active) {
-        const int kq = 3 + (var - 2);
+        for (int j = 0; j < NF; j++) un[j] = sv[svs + (fl[j] & NBR_LOCAL_MASK)];
+        var_to_faces<DIM, NF>(ui, un, Tb, A.eps, limit, r1);
 #pragma unroll
         for (int j = 0; j < NF; j++) {
             if (st[j] == 0xFFFF) continue;
-            S* qd = stg + (long)st[j] * 6;
-            qd[kq] = r[j];
-            // 2-D: vz has no gradient (convective_flux.cpp:206-208) and a unit limiter: the vy lane copies the value
-            if (DIM == 2 && var == 3) qd[5] = sv[4 * svs + i];
-            if (fl[j] & NBR_GHOST_BIT) {
-                S* f = stg + (long)far_stage_index((fl[j] & NBR_LEFT_BIT) != 0, st[j], nR, n_own_l) * 6;
-                f[kq] = un[j];
-                if (DIM == 2 && var == 3) f[5] = sv[4 * svs + (fl[j] & NBR_LOCAL_MASK)];
+            S* q = stg + (long)st[j] * 6;
+            side_close_store(A.thermo, A.gas, q[0], r1[j], q);
+            // the far side of a boundary interface is the ghost cell itself: zero gradient, unit limiter
+            // (convective_flux.cpp:281-300), i.e. its values, closed thermodynamically like any other side
+            if (fl[j] & NBR_GHOST_BIT)
+                side_close_store(A.thermo, A.gas, sv[fl[j] & NBR_LOCAL_MASK], un[j],
+                                 stg + (long)far_stage_index((fl[j] & NBR_LEFT_BIT) != 0, st[j], nR, n_own_l) * 6);
+        }
+    } else {
+        constexpr int NV = DIM == 3 ? 3 : 2;
+#pragma unroll
+        for (int v = 0; v < NV; v++) {
+            const S* row = sv + (size_t)(2 + v) * svs;
+            const S ui = row[i];
+            S un[NF], r[NF];
+#pragma unroll
+            for (int j = 0; j < NF; j++) un[j] = row[fl[j] & NBR_LOCAL_MASK];
+            var_to_faces<DIM, NF>(ui, un, Tb, A.eps, limit, r);
+#pragma unroll
+            for (int j = 0; j < NF; j++) {
+                if (st[j] == 0xFFFF) continue;
+                stg[(long)st[j] * 6 + 3 + v] = r[j];
+                if (fl[j] & NBR_GHOST_BIT)
+                    stg[(long)far_stage_index((fl[j] & NBR_LEFT_BIT) != 0, st[j], nR, n_own_l) * 6 + 3 + v] = un[j];
+            }
+        }
+        if (DIM == 2) {
+            // 2-D: vz has no gradient (convective_flux.cpp:206-208) and a unit limiter: the value is copied
+            const S* row = sv + (size_t)4 * svs;
+#pragma unroll
+            for (int j = 0; j < NF; j++) {
+                if (st[j] == 0xFFFF) continue;
+                stg[(long)st[j] * 6 + 5] = row[i];
+                if (fl[j] & NBR_GHOST_BIT)
+                    stg[(long)far_stage_index((fl[j] & NBR_LEFT_BIT) != 0, st[j], nR, n_own_l) * 6 + 5] = row[fl[j] & NBR_LOCAL_MASK];
             }
         }
     }
 }
 
-// Work items of a block, in queue order: the N_TASKS (cell, variable) items of its tiles.  The warp that completes a
+// Work items of a block, in queue order: the N_TASKS = 2 T / 32 (32 cells, half of the variables) items of its tiles.  The warp that completes a
 // tile's last item sends the tile's side records off (the push list of the tile's record: bulk stores out of the
 // staging buffer) and hands the input stage back.  Input stages recycle through an mbarrier guarded by stage_tile
 // (see k_flux_pipe), the staging buffers through the monotone counter out_done.
 template <int DIM, int NF, int T, typename S>
 __global__ void __launch_bounds__(32 * (IBIS_PIPE_G_WARPS + IBIS_PIPE_G_LOADERS), 1)
-    k_grad_pipe(const FvArgs<S> A, const int* __restrict__ tile_list, const int n_list, const int nsi, const int nso) {
+    k_grad_pipe(const FvArgs<S> A, const int* __restrict__ tile_list, const int n_list, const int nsi, const int nso, const int pf) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t full[PIPE_MAX_STAGES];
     __shared__ int stage_tile[PIPE_MAX_STAGES], stage_free[PIPE_MAX_STAGES], done_tasks[PIPE_MAX_STAGES], out_done[PIPE_MAX_STAGES],
@@ -506,9 +506,9 @@ __global__ void __launch_bounds__(32 * (IBIS_PIPE_G_WARPS + IBIS_PIPE_G_LOADERS)
     const int ncw = (int)(blockDim.x >> 5) - IBIS_PIPE_G_LOADERS;
     const int svs = T + g.halo_cap;
     constexpr int WD_BYTES = 2 * NF * 3 * T * 8;
-    const size_t in_bytes = grad_stage_bytes<S>(NF, T, g.grec_stride, g.halo_cap);
-    const size_t out_bytes = grad_out_bytes<S>(g.stage_cap);
-    unsigned char* out_base = smem + (size_t)nsi * in_bytes;
+    const unsigned in_bytes = (unsigned)grad_stage_bytes<S>(NF, T, g.grec_stride, g.halo_cap);
+    const unsigned out_bytes = (unsigned)grad_out_bytes<S>(g.stage_cap);
+    unsigned char* out_base = smem + (unsigned)nsi * in_bytes;
     if (threadIdx.x == 0) {
         for (int s = 0; s < nsi; s++) {
             ac::mbar_init(&full[s], 33);          // the loader's arrive.expect_tx + one cp.async arrival per lane
@@ -529,7 +529,8 @@ __global__ void __launch_bounds__(32 * (IBIS_PIPE_G_WARPS + IBIS_PIPE_G_LOADERS)
         // same breath as its bulk copies.  One warp issues a tile's ~25 dependent instructions per lane in about a
         // microsecond: several loaders keep the stages full ----
         const int step = (int)gridDim.x, w = warp - ncw;
-        constexpr int NL = IBIS_PIPE_G_LOADERS, PF = (IBIS_PIPE_PREFETCH + NL - 1) / NL * NL;
+        constexpr int NL = IBIS_PIPE_G_LOADERS;
+        const int PF = (pf + NL - 1) / NL * NL;
         const int hoff = 4 * NF * T + 16 + 12 * g.push_cap;                   // halo list inside the record
         auto tile_at = [&](int k) { const int idx = (int)blockIdx.x + k * step; return tile_list ? __ldg(tile_list + idx) : idx; };
         int ids[PIPE_HALO_REGS], n_halo = 0, ids_n[PIPE_HALO_REGS], n_halo_n = 0;
@@ -543,7 +544,7 @@ __global__ void __launch_bounds__(32 * (IBIS_PIPE_G_WARPS + IBIS_PIPE_G_LOADERS)
         if (w < n_my) fetch_ids(tile_at(w), ids, n_halo);
         for (int k = w; k < n_my; k += NL) {
             const int t = tile_at(k), s = k % nsi;
-            if (k + PF < n_my && lane < 7) {                  // L2 prefetch of a later tile of this loader
+            if (PF > 0 && k + PF < n_my && lane < 7) {        // L2 prefetch of a later tile of this loader
                 const int tp = tile_at(k + PF);
                 int c0p, ncp;
                 tile_cells(g, tp, c0p, ncp);
@@ -553,7 +554,7 @@ __global__ void __launch_bounds__(32 * (IBIS_PIPE_G_WARPS + IBIS_PIPE_G_LOADERS)
             }
             if (k + NL < n_my) fetch_ids(tile_at(k + NL), ids_n, n_halo_n);   // in flight during the wait below
             if (k >= nsi && !pipe_spin_ge(&stage_free[s], k - nsi, A.pipe_dbg, 16 + PW_EMPTY, k)) return;
-            unsigned char* st = smem + (size_t)s * in_bytes;
+            unsigned char* st = smem + (unsigned)s * in_bytes;
             S* sv = reinterpret_cast<S*>(st + WD_BYTES + g.grec_stride);
             int c0, nc;
             tile_cells(g, t, c0, nc);
@@ -593,7 +594,7 @@ __global__ void __launch_bounds__(32 * (IBIS_PIPE_G_WARPS + IBIS_PIPE_G_LOADERS)
         return;
     }
     // ---- consumers ----
-    constexpr int N_THERMO = T / 16, NV = DIM == 3 ? 3 : 2, N_TASKS = N_THERMO + NV * (T / 32);
+    constexpr int N_TASKS = 2 * (T / 32);
     const int total = n_my * N_TASKS;
     const unsigned mT = pipe_magic(N_TASKS), mI = pipe_magic(nsi), mO = pipe_magic(nso);
     // the bulk stores this warp issued for tile pend_k out of staging buffer pend_o and has not yet seen drained
@@ -608,9 +609,9 @@ __global__ void __launch_bounds__(32 * (IBIS_PIPE_G_WARPS + IBIS_PIPE_G_LOADERS)
         }
         pend_o = -1;
     };
-    for (;;) {
-        const int item = pipe_next_item(&q_head, lane);
-        if (item >= total) break;
+    // the next item is claimed while the current one is worked on (see k_flux_pipe)
+    for (int item = pipe_next_item(&q_head, lane), next; item < total; item = next) {
+        next = pipe_next_item(&q_head, lane);
         const int k = pipe_div(item, mT), r = item - k * N_TASKS;
         const int ui = pipe_div(k, mI);
         const int s = k - ui * nsi, o = k - pipe_div(k, mO) * nso;
@@ -623,9 +624,9 @@ __global__ void __launch_bounds__(32 * (IBIS_PIPE_G_WARPS + IBIS_PIPE_G_LOADERS)
             flush_pending();
             if (!pipe_spin_ge(&out_done[o], k - nso, A.pipe_dbg, 16 + PW_OUT, k)) return;
         }
-        unsigned char* st = smem + (size_t)s * in_bytes;
+        unsigned char* st = smem + (unsigned)s * in_bytes;
         const GRec R = grec_view(st + WD_BYTES, NF, T, g.push_cap);
-        S* stg = reinterpret_cast<S*>(out_base + (size_t)o * out_bytes);
+        S* stg = reinterpret_cast<S*>(out_base + (unsigned)o * out_bytes);
         const double* wd = reinterpret_cast<const double*>(st);
         const S* sv = reinterpret_cast<const S*>(st + WD_BYTES + g.grec_stride);
         grad_task<DIM, NF, T, S>(A, wd, R, sv, svs, stg, r, nc_of[s], lane);
@@ -694,7 +695,7 @@ static void launch_grad_pipe_t(ibis_b200_ctx* c, const FvArgs<S>& A, const int* 
     auto kernel = k_grad_pipe<DIM, NF, T, S>;
     if (!set_smem(c, kernel, smem)) return;
     const int grid = n_list < c->n_sm ? n_list : c->n_sm;
-    kernel<<<grid, 32 * (IBIS_PIPE_G_WARPS + IBIS_PIPE_G_LOADERS), smem, c->stream>>>(A, list, n_list, nsi, nso);
+    kernel<<<grid, 32 * (IBIS_PIPE_G_WARPS + IBIS_PIPE_G_LOADERS), smem, c->stream>>>(A, list, n_list, nsi, nso, c->pipe_prefetch);
 }
 
 template <int DIM, int T, typename S>
@@ -751,7 +752,7 @@ static void launch_flux_pipe_k(ibis_b200_ctx* c, const FvArgs<S>& A) {
     auto kernel = k_flux_pipe<DIM, FLUX, S>;
     if (!set_smem(c, kernel, smem)) return;
     const int grid = A.g.n_tiles < c->n_sm ? A.g.n_tiles : c->n_sm;
-    kernel<<<grid, 32 * (IBIS_PIPE_F_WARPS + IBIS_PIPE_F_LOADERS), smem, c->stream>>>(A, nsi, nfb);
+    kernel<<<grid, 32 * (IBIS_PIPE_F_WARPS + IBIS_PIPE_F_LOADERS), smem, c->stream>>>(A, nsi, nfb, c->pipe_prefetch);
 }
 template <int DIM, typename S>
 static void launch_flux_pipe_dim(ibis_b200_ctx* c, const FvArgs<S>& A) {
