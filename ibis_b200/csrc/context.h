@@ -100,7 +100,7 @@ struct ibis_b200_ctx {
     double* sidesP_r = nullptr;
     ib::dual* sidesP_d = nullptr;
     int64_t p_total = 0;                 // records in a side-state array (all owned tiles)
-    int pipe_prefetch = 6;               // IBIS_B200_PREFETCH: L2 prefetch distance (tiles) of the pipelined kernels, 0 = off
+    int pipe_prefetch = 2;               // IBIS_B200_PREFETCH: L2 prefetch distance (tiles) of the pipelined kernels, 0 = off
     bool use_sides = true;               // IBIS_B200_SIDES=0: second order through the gather path (grad + limiter arrays)
     int last_fs = 0;                     // FlowStates handle of the last real evaluation (debug_gradients)
 

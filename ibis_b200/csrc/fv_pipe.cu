@@ -305,10 +305,11 @@ __global__ void __launch_bounds__(32 * (IBIS_PIPE_F_WARPS + IBIS_PIPE_F_LOADERS)
     const int NCH = (cap + 31) >> 5, NCL = (T + 31) >> 5, P = NCH + NCL;
     const int total = (n_my + 1) * P;
     const unsigned mP = pipe_magic(P), mI = pipe_magic(nsi), mO = pipe_magic(nfb);
-    // the next item is claimed while the current one is worked on (the claim -- a shared-memory atomic and a
-    // shuffle -- is a few hundred cycles of latency that nothing else in the item can hide)
-    for (int item = pipe_next_item(&q_head, lane), next; item < total; item = next) {
-        next = pipe_next_item(&q_head, lane);
+    // (claiming the next item while the current one is worked on hides the latency of the claim, but an item claimed
+    // by a busy warp cannot be started by an idle one: measured, that costs far more than it saves)
+    for (;;) {
+        const int item = pipe_next_item(&q_head, lane);
+        if (item >= total) break;
         const int m = pipe_div(item, mP), r = item - m * P;
         const bool is_flux = r < NCH;
         const int k = is_flux ? m : m - 1;
@@ -408,17 +409,22 @@ __host__ __device__ inline size_t grad_out_bytes(int stage_cap) {
     return ((size_t)stage_cap * 6 * sizeof(S) + 127) / 128 * 128;
 }
 
-// One work item of pass G': 32 cells of a tile x one half of the variables, one cell per lane.
-//   half 0: rho and the second thermodynamic variable, one after the other, then the thermodynamic closure
-//           (gas_model.h:91-117) of every face -> rho p T of the cell's side records;
-//   half 1: the velocity components, one after the other -> vx vy vz of the side records.
-// The cell's neighbour / staging indices are read once per item and serve all its variables.
+// One work item of pass G': 32 (cell, variable) pairs of a tile.
+//   items [0, T / 16):  16 cells x (rho, second thermodynamic variable) -- lanes 0-15 extrapolate rho, lanes 16-31
+//                       the other variable, of the same 16 cells; the two lanes of a cell then close the
+//                       thermodynamic state (gas_model.h:91-117) of half of the cell's faces each;
+//   the others:         32 cells x one velocity component (vx, vy[, vz]).
+// One code path computes the gradient, the limiter and the extrapolation of the lane's variable (var_to_faces);
+// only the epilogue differs.
 template <int DIM, int NF, int T, typename S>
 __device__ __forceinline__ void grad_task(const FvArgs<S>& A, const double* wd, const GRec& R, const S* sv, const int svs,
                                           S* stg, const int task, const int nc, const int lane) {
-    const int half = task & 1;
-    const int i = (task >> 1) * 32 + lane;
-    if (i >= nc) return;
+    constexpr int N_THERMO = T / 16;
+    const bool thermo = task < N_THERMO;
+    const int q = task - N_THERMO;
+    const int var = thermo ? (lane >> 4) : 2 + q / (T / 32);
+    const int i = thermo ? task * 16 + (lane & 15) : (q % (T / 32)) * 32 + lane;
+    const bool active = i < nc;
     const bool limit = A.limiter_on != 0;
     TileTables<NF, T> Tb;
     Tb.w = wd;
@@ -429,68 +435,65 @@ __device__ __forceinline__ void grad_task(const FvArgs<S>& A, const double* wd, 
         fl[j] = R.nbr[j * T + i];
         st[j] = R.stage[j * T + i];
     }
+    const S ui = sv[var * svs + i];
+    S un[NF], r[NF];
+#pragma unroll
+    for (int j = 0; j < NF; j++) un[j] = sv[var * svs + (fl[j] & NBR_LOCAL_MASK)];
+    var_to_faces<DIM, NF>(ui, un, Tb, A.eps, limit, r);
     const int nR = R.hdr[1], n_own_l = R.hdr[2];
-    if (half == 0) {
-        {
-            // rho: parked in its place in the side records while the second variable is worked out
-            const S ui = sv[i];
-            S un[NF], r0[NF];
+    if (thermo) {
+        S o[NF];
 #pragma unroll
-            for (int j = 0; j < NF; j++) un[j] = sv[fl[j] & NBR_LOCAL_MASK];
-            var_to_faces<DIM, NF>(ui, un, Tb, A.eps, limit, r0);
+        for (int j = 0; j < NF; j++) o[j] = shfl_xor_s(r[j], 16);
+        constexpr int H = (NF + 1) / 2;
 #pragma unroll
-            for (int j = 0; j < NF; j++)
-                if (st[j] != 0xFFFF) stg[(long)st[j] * 6] = r0[j];
+        for (int jj = 0; jj < H; jj++) {
+            const int j0 = jj, j1 = H + jj;
+            S rho_j, th_j;
+            int st_j;
+            if (j1 < NF) {
+                rho_j = var ? o[j1] : r[j0];
+                th_j = var ? r[j1] : o[j0];
+                st_j = var ? st[j1] : st[j0];
+            } else {
+                rho_j = r[j0];
+                th_j = o[j0];
+                st_j = var ? 0xFFFF : st[j0];
+            }
+            if (active && st_j != 0xFFFF) side_close_store(A.thermo, A.gas, rho_j, th_j, stg + (long)st_j * 6);
         }
-        const S ui = sv[svs + i];
-        S un[NF], r1[NF];
+        // the far side of a boundary interface is the ghost cell itself: zero gradient, unit limiter
+        // (convective_flux.cpp:281-300), i.e. its values, closed thermodynamically like any other side
 #pragma unroll
-        for (int j = 0; j < NF; j++) un[j] = sv[svs + (fl[j] & NBR_LOCAL_MASK)];
-        var_to_faces<DIM, NF>(ui, un, Tb, A.eps, limit, r1);
+        for (int j = 0; j < NF; j++) {
+            const bool gh = active && st[j] != 0xFFFF && (fl[j] & NBR_GHOST_BIT);
+            if (__any_sync(0xffffffffu, gh)) {
+                const S uo = shfl_xor_s(un[j], 16);
+                if (gh && var == 0) {
+                    const int far_idx = far_stage_index((fl[j] & NBR_LEFT_BIT) != 0, st[j], nR, n_own_l);
+                    side_close_store(A.thermo, A.gas, un[j], uo, stg + (long)far_idx * 6);
+                }
+            }
+        }
+    } else if (active) {
+        const int kq = 3 + (var - 2);
 #pragma unroll
         for (int j = 0; j < NF; j++) {
             if (st[j] == 0xFFFF) continue;
-            S* q = stg + (long)st[j] * 6;
-            side_close_store(A.thermo, A.gas, q[0], r1[j], q);
-            // the far side of a boundary interface is the ghost cell itself: zero gradient, unit limiter
-            // (convective_flux.cpp:281-300), i.e. its values, closed thermodynamically like any other side
-            if (fl[j] & NBR_GHOST_BIT)
-                side_close_store(A.thermo, A.gas, sv[fl[j] & NBR_LOCAL_MASK], un[j],
-                                 stg + (long)far_stage_index((fl[j] & NBR_LEFT_BIT) != 0, st[j], nR, n_own_l) * 6);
-        }
-    } else {
-        constexpr int NV = DIM == 3 ? 3 : 2;
-#pragma unroll
-        for (int v = 0; v < NV; v++) {
-            const S* row = sv + (size_t)(2 + v) * svs;
-            const S ui = row[i];
-            S un[NF], r[NF];
-#pragma unroll
-            for (int j = 0; j < NF; j++) un[j] = row[fl[j] & NBR_LOCAL_MASK];
-            var_to_faces<DIM, NF>(ui, un, Tb, A.eps, limit, r);
-#pragma unroll
-            for (int j = 0; j < NF; j++) {
-                if (st[j] == 0xFFFF) continue;
-                stg[(long)st[j] * 6 + 3 + v] = r[j];
-                if (fl[j] & NBR_GHOST_BIT)
-                    stg[(long)far_stage_index((fl[j] & NBR_LEFT_BIT) != 0, st[j], nR, n_own_l) * 6 + 3 + v] = un[j];
-            }
-        }
-        if (DIM == 2) {
-            // 2-D: vz has no gradient (convective_flux.cpp:206-208) and a unit limiter: the value is copied
-            const S* row = sv + (size_t)4 * svs;
-#pragma unroll
-            for (int j = 0; j < NF; j++) {
-                if (st[j] == 0xFFFF) continue;
-                stg[(long)st[j] * 6 + 5] = row[i];
-                if (fl[j] & NBR_GHOST_BIT)
-                    stg[(long)far_stage_index((fl[j] & NBR_LEFT_BIT) != 0, st[j], nR, n_own_l) * 6 + 5] = row[fl[j] & NBR_LOCAL_MASK];
+            S* qd = stg + (long)st[j] * 6;
+            qd[kq] = r[j];
+            // 2-D: vz has no gradient (convective_flux.cpp:206-208) and a unit limiter: the vy lane copies the value
+            if (DIM == 2 && var == 3) qd[5] = sv[4 * svs + i];
+            if (fl[j] & NBR_GHOST_BIT) {
+                S* f = stg + (long)far_stage_index((fl[j] & NBR_LEFT_BIT) != 0, st[j], nR, n_own_l) * 6;
+                f[kq] = un[j];
+                if (DIM == 2 && var == 3) f[5] = sv[4 * svs + (fl[j] & NBR_LOCAL_MASK)];
             }
         }
     }
 }
 
-// Work items of a block, in queue order: the N_TASKS = 2 T / 32 (32 cells, half of the variables) items of its tiles.  The warp that completes a
+// Work items of a block, in queue order: the N_TASKS (cell, variable) items of its tiles.  The warp that completes a
 // tile's last item sends the tile's side records off (the push list of the tile's record: bulk stores out of the
 // staging buffer) and hands the input stage back.  Input stages recycle through an mbarrier guarded by stage_tile
 // (see k_flux_pipe), the staging buffers through the monotone counter out_done.
@@ -594,7 +597,7 @@ __global__ void __launch_bounds__(32 * (IBIS_PIPE_G_WARPS + IBIS_PIPE_G_LOADERS)
         return;
     }
     // ---- consumers ----
-    constexpr int N_TASKS = 2 * (T / 32);
+    constexpr int N_THERMO = T / 16, NV = DIM == 3 ? 3 : 2, N_TASKS = N_THERMO + NV * (T / 32);
     const int total = n_my * N_TASKS;
     const unsigned mT = pipe_magic(N_TASKS), mI = pipe_magic(nsi), mO = pipe_magic(nso);
     // the bulk stores this warp issued for tile pend_k out of staging buffer pend_o and has not yet seen drained
@@ -609,21 +612,25 @@ __global__ void __launch_bounds__(32 * (IBIS_PIPE_G_WARPS + IBIS_PIPE_G_LOADERS)
         }
         pend_o = -1;
     };
-    // the next item is claimed while the current one is worked on (see k_flux_pipe)
-    for (int item = pipe_next_item(&q_head, lane), next; item < total; item = next) {
-        next = pipe_next_item(&q_head, lane);
+    for (;;) {
+        const int item = pipe_next_item(&q_head, lane);
+        if (item >= total) break;
         const int k = pipe_div(item, mT), r = item - k * N_TASKS;
         const int ui = pipe_div(k, mI);
         const int s = k - ui * nsi, o = k - pipe_div(k, mO) * nso;
         const bool had_pending = pend_o >= 0;
+        // Never block while sitting on an unpublished store: the tile this item waits for may (through the stage and
+        // staging-buffer rings) be waiting for exactly that publication.  The drain wait is deferred only past an
+        // item whose data is already there.
+        if (had_pending) {
+            const bool ready = *reinterpret_cast<volatile int*>(&stage_tile[s]) >= k && ac::mbar_test_wait(&full[s], ui & 1) &&
+                               (k < nso || (pend_o != o && *reinterpret_cast<volatile int*>(&out_done[o]) >= k - nso));
+            if (!__all_sync(0xffffffffu, ready)) flush_pending();
+        }
         if (!pipe_spin_ge(&stage_tile[s], k, A.pipe_dbg, 16 + PW_STAGE, k)) return;
         if (!pipe_wait(&full[s], ui & 1, A.pipe_dbg, 16 + PW_FULL, k)) return;
-        // the staging buffer is free once the stores of the tile nso tiles back have read it (never wait for
-        // another warp's publication while sitting on one's own)
-        if (k >= nso) {
-            flush_pending();
-            if (!pipe_spin_ge(&out_done[o], k - nso, A.pipe_dbg, 16 + PW_OUT, k)) return;
-        }
+        // the staging buffer is free once the stores of the tile nso tiles back have read it
+        if (k >= nso && !pipe_spin_ge(&out_done[o], k - nso, A.pipe_dbg, 16 + PW_OUT, k)) return;
         unsigned char* st = smem + (unsigned)s * in_bytes;
         const GRec R = grec_view(st + WD_BYTES, NF, T, g.push_cap);
         S* stg = reinterpret_cast<S*>(out_base + (unsigned)o * out_bytes);
