@@ -890,8 +890,9 @@ int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd_ref, con
                 unsigned short* nbr = reinterpret_cast<unsigned short*>(rec);
                 unsigned short* stg = nbr + (size_t)NFr * T;
                 int* hdr = reinterpret_cast<int*>(stg + (size_t)NFr * T);
-                int* pu = hdr + 4;
+                int* pu = hdr + 8;
                 int* hl = pu + 3 * (size_t)push_cap;
+                int has_ghost = 0;
                 const int64_t c0 = TL.c0[b], c1 = TL.c0[b + 1];
                 const std::vector<int>& h = halos[b];
                 for (int i = 0; i < T; i++)
@@ -906,12 +907,13 @@ int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd_ref, con
                             else local = T + (int)(std::lower_bound(h.begin(), h.end(), nb) - h.begin());
                             e = (unsigned short)local;
                             if (cf_out[(size_t)j * cs + cell] > 0) e |= NBR_LEFT_BIT;
-                            if (nb >= gd->n_cells) e |= NBR_GHOST_BIT;
+                            if (nb >= gd->n_cells) { e |= NBR_GHOST_BIT; has_ghost = 1; }
                         }
                         nbr[(size_t)j * T + i] = e;
                         stg[(size_t)j * T + i] = st;
                     }
                 hdr[0] = (int)h.size(); hdr[1] = TL.nR[b]; hdr[2] = TL.n_own_left(b); hdr[3] = (int)pushes[b].size();
+                hdr[4] = has_ghost; hdr[5] = hdr[6] = hdr[7] = 0;
                 for (size_t k = 0; k < pushes[b].size(); k++) {
                     pu[3 * k] = pushes[b][k].src; pu[3 * k + 1] = pushes[b][k].count; pu[3 * k + 2] = pushes[b][k].dst;
                 }

@@ -113,7 +113,7 @@ struct GridDev {
     //   t_grec   [tile], grec_stride bytes: u16 nbr[pipe_nf][tile] (tile-local index of the neighbour: < tile an own
     //            cell, >= tile entry (index - tile) of the halo list; bit 14: this cell is the LEFT cell of the
     //            interface, bit 15: the neighbour is a boundary ghost; an absent slot points at the cell itself) |
-    //            u16 stage[pipe_nf][tile] (cf_stage) | int hdr[4] = {n_halo, nR, n_own_l, n_push} |
+    //            u16 stage[pipe_nf][tile] (cf_stage) | int hdr[8] = {n_halo, nR, n_own_l, n_push, has_ghost, -, -, -} |
     //            int push[push_cap][3] = {first staged record, count, destination record in the side-state array}:
     //            where the records pass G' has staged for the tile go (the whole staging image into the tile's own
     //            array, then the runs a neighbouring tile needs into THAT tile's array) |
@@ -1275,7 +1275,7 @@ constexpr int NBR_LOCAL_MASK = 0x3FFF, NBR_LEFT_BIT = 0x4000, NBR_GHOST_BIT = 0x
 struct GRec {
     const unsigned short* nbr;     // [nf][T]
     const unsigned short* stage;   // [nf][T]
-    const int* hdr;                // n_halo, nR, n_own_l, n_push
+    const int* hdr;                // n_halo, nR, n_own_l, n_push, has_ghost (a cell of the tile has a boundary ghost neighbour)
     const int* push;               // [push_cap][3]
     const int* halo;               // [halo_cap]
 };
@@ -1284,11 +1284,11 @@ IBIS_HD GRec grec_view(const unsigned char* rec, int nf, int T, int push_cap) {
     R.nbr = reinterpret_cast<const unsigned short*>(rec);
     R.stage = R.nbr + (size_t)nf * T;
     R.hdr = reinterpret_cast<const int*>(R.stage + (size_t)nf * T);
-    R.push = R.hdr + 4;
+    R.push = R.hdr + 8;
     R.halo = R.push + 3 * (size_t)push_cap;
     return R;
 }
-IBIS_HD int grec_bytes(int nf, int T, int halo_cap, int push_cap) { return 4 * nf * T + 16 + 12 * push_cap + 4 * halo_cap; }
+IBIS_HD int grec_bytes(int nf, int T, int halo_cap, int push_cap) { return 4 * nf * T + 32 + 12 * push_cap + 4 * halo_cap; }
 
 // the thermodynamic pair (rho, second variable) extrapolated to one interface -> rho p T of the side record
 template <typename S>

@@ -29,16 +29,22 @@
 #include "context.h"
 
 #ifndef IBIS_PIPE_F_WARPS
-#define IBIS_PIPE_F_WARPS 18      // consumer warps of pass F'
+#define IBIS_PIPE_F_WARPS 14      // consumer warps of pass F'
 #endif
 #ifndef IBIS_PIPE_F_LOADERS
 #define IBIS_PIPE_F_LOADERS 2     // loader warps of pass F' (loader w takes the block's tiles w, w + NL, ...)
 #endif
 #ifndef IBIS_PIPE_G_WARPS
-#define IBIS_PIPE_G_WARPS 17      // consumer warps of pass G'
+#define IBIS_PIPE_G_WARPS 13      // consumer warps of pass G'
 #endif
 #ifndef IBIS_PIPE_G_LOADERS
 #define IBIS_PIPE_G_LOADERS 3     // loader warps of pass G'
+#endif
+#ifndef IBIS_PIPE_F_ROUNDS
+#define IBIS_PIPE_F_ROUNDS 1      // interfaces per lane of a flux item of pass F' (measured: 2 is slower)
+#endif
+#ifndef IBIS_PIPE_G_SPLITVEL
+#define IBIS_PIPE_G_SPLITVEL 0    // 1: a velocity item of pass G' covers 32 cells (one pass) instead of the whole tile
 #endif
 #ifndef IBIS_PIPE_PREFETCH
 #define IBIS_PIPE_PREFETCH 6      // a loader pulls a tile's data into L2 this many tiles (a multiple of its stride) ahead
@@ -82,50 +88,45 @@ __device__ __forceinline__ unsigned pipe_backoff(unsigned ns) {
     __nanosleep(ns);
     return ns < 512u ? ns * 2u : ns;
 }
-// the phase of an mbarrier
+// the phase of an mbarrier (the polling loops are out of line: the instruction cache should see the work, not the waits)
+__device__ __noinline__ bool pipe_wait_slow(uint64_t* bar, uint32_t parity, unsigned int* dbg, int kind, int k) {
+    const long long t0 = clock64();
+    unsigned ns = 64u;
+    for (int it = 1;; it++) {
+        ns = pipe_backoff(ns);
+        if (ac::mbar_test_wait(bar, parity)) return true;
+        if ((it & 63) == 0 && pipe_timed_out(t0, dbg, kind, k, parity)) return false;
+    }
+}
 __device__ __forceinline__ bool pipe_wait(uint64_t* bar, uint32_t parity, unsigned int* dbg, int kind, int k) {
     bool ok = ac::mbar_test_wait(bar, parity);
-    if (!ok) {
-        const long long t0 = clock64();
-        unsigned ns = 64u;
-        for (int it = 1;; it++) {
-            ns = pipe_backoff(ns);
-            if (ac::mbar_test_wait(bar, parity)) { ok = true; break; }
-            if ((it & 63) == 0 && pipe_timed_out(t0, dbg, kind, k, parity)) break;
-        }
-    }
+    if (!ok) ok = pipe_wait_slow(bar, parity, dbg, kind, k);
     return __all_sync(0xffffffffu, ok);
 }
 // a monotone counter in shared memory reaching `target` (no parity, hence no aliasing when a warp is late)
-__device__ __forceinline__ bool pipe_spin_ge(const int* p, int target, unsigned int* dbg, int kind, int k) {
+__device__ __noinline__ bool pipe_spin_slow(const int* p, int target, unsigned int* dbg, int kind, int k) {
     const volatile int* vp = p;
-    bool ok = *vp >= target;
-    if (!ok) {
-        const long long t0 = clock64();
-        unsigned ns = 64u;
-        for (int it = 1;; it++) {
-            ns = pipe_backoff(ns);
-            if (*vp >= target) { ok = true; break; }
-            if ((it & 63) == 0 && pipe_timed_out(t0, dbg, kind, k, (unsigned)target)) break;
-        }
+    const long long t0 = clock64();
+    unsigned ns = 64u;
+    for (int it = 1;; it++) {
+        ns = pipe_backoff(ns);
+        if (*vp >= target) return true;
+        if ((it & 63) == 0 && pipe_timed_out(t0, dbg, kind, k, (unsigned)target)) return false;
     }
+}
+__device__ __forceinline__ bool pipe_spin_ge(const int* p, int target, unsigned int* dbg, int kind, int k) {
+    bool ok = *reinterpret_cast<const volatile int*>(p) >= target;
+    if (!ok) ok = pipe_spin_slow(p, target, dbg, kind, k);
     ok = __all_sync(0xffffffffu, ok);
     __threadfence_block();
     return ok;
 }
-// the same for a single thread (the loaders run on one lane)
+// the same for a single thread (the loaders of pass F' run on one lane)
 __device__ __forceinline__ bool pipe_spin_ge_1(const int* p, int target, unsigned int* dbg, int kind, int k) {
-    const volatile int* vp = p;
-    if (*vp < target) {
-        const long long t0 = clock64();
-        unsigned ns = 64u;
-        for (int it = 1; *vp < target; it++) {
-            ns = pipe_backoff(ns);
-            if ((it & 63) == 0 && pipe_timed_out(t0, dbg, kind, k, (unsigned)target)) return false;
-        }
-    }
+    bool ok = *reinterpret_cast<const volatile int*>(p) >= target;
+    if (!ok) ok = pipe_spin_slow(p, target, dbg, kind, k);
     __threadfence_block();
-    return true;
+    return ok;
 }
 // next item of the block's ordered work queue
 __device__ __forceinline__ int pipe_next_item(int* head, int lane) {
@@ -195,8 +196,8 @@ __host__ __device__ inline size_t flux_fb_bytes(int cap, int frec_stride, int T,
     return (b + 127) / 128 * 128;
 }
 
-// Work items of a block, handed out in this order by one counter: for its m-th tile the NCH = ceil(cap / 32) flux
-// chunks (32 interfaces each), then the T / 32 cell parts of tile m - 1 (one lane per cell sums its faces; queued
+// Work items of a block, handed out in this order by one counter: for its m-th tile the NCH flux chunks
+// (32 interfaces each, one per lane), then the T / 32 cell parts of tile m - 1 (one lane per cell sums its faces; queued
 // behind the NEXT tile's chunks so that the fluxes they need are normally complete when a warp gets there).  A warp
 // holding an item of tile k first waits for stage_tile[s] >= k / fb_tile[o] >= k (the loader has re-designated the
 // stage / buffer) and only then tests the barrier's parity: neither can be recycled while an item of its tile is
@@ -302,7 +303,7 @@ __global__ void __launch_bounds__(32 * (IBIS_PIPE_F_WARPS + IBIS_PIPE_F_LOADERS)
         return;
     }
     // ---- consumers ----
-    const int NCH = (cap + 31) >> 5, NCL = (T + 31) >> 5, P = NCH + NCL;
+    const int NCH = (cap + 32 * IBIS_PIPE_F_ROUNDS - 1) / (32 * IBIS_PIPE_F_ROUNDS), NCL = (T + 31) >> 5, P = NCH + NCL;
     const int total = (n_my + 1) * P;
     const unsigned mP = pipe_magic(P), mI = pipe_magic(nsi), mO = pipe_magic(nfb);
     // (claiming the next item while the current one is worked on hides the latency of the claim, but an item claimed
@@ -324,21 +325,29 @@ __global__ void __launch_bounds__(32 * (IBIS_PIPE_F_WARPS + IBIS_PIPE_F_LOADERS)
             const unsigned char* st = smem + (unsigned)s * in_bytes;
             const S* Pt = reinterpret_cast<const S*>(st);
             const FRecA Ra = freca_view(st + offA, cap);
-            const int slot = r * 32 + lane;
-            const bool active = slot < n_slots_of[s];
-            FluxOperands<S> O;
-            if (active) flux_load_operands(Pt + (long)Ra.lidx[slot] * 6, Pt + (long)Ra.ridx[slot] * 6, Ra.frame + (long)slot * 6, O);
-            // the operands are in registers: once every chunk of the tile has said so the stage is the loader's again
-            __syncwarp();
-            if (lane == 0) {
-                __threadfence_block();
-                if (atomicAdd(&reads_done[s], 1) == NCH - 1) {
-                    reads_done[s] = 0;
-                    __threadfence_block();
-                    *reinterpret_cast<volatile int*>(&stage_free[s]) = k;
+            const int n_slots = n_slots_of[s];
+            // IBIS_PIPE_F_ROUNDS rounds of 32 interfaces; the operands of the last round are in registers before the
+            // stage is declared read
+#pragma unroll 1
+            for (int rr = 0; rr < IBIS_PIPE_F_ROUNDS; rr++) {
+                const int slot = r * (32 * IBIS_PIPE_F_ROUNDS) + rr * 32 + lane;
+                const bool active = slot < n_slots;
+                FluxOperands<S> O;
+                if (active) flux_load_operands(Pt + (long)Ra.lidx[slot] * 6, Pt + (long)Ra.ridx[slot] * 6, Ra.frame + (long)slot * 6, O);
+                if (rr == IBIS_PIPE_F_ROUNDS - 1) {
+                    // once every item of the tile has its operands the stage is the loader's again
+                    __syncwarp();
+                    if (lane == 0) {
+                        __threadfence_block();
+                        if (atomicAdd(&reads_done[s], 1) == NCH - 1) {
+                            reads_done[s] = 0;
+                            __threadfence_block();
+                            *reinterpret_cast<volatile int*>(&stage_free[s]) = k;
+                        }
+                    }
                 }
+                if (active) flux_from_operands<DIM, FLUX>(A, O, flux + (long)slot * 5);
             }
-            if (active) flux_from_operands<DIM, FLUX>(A, O, flux + (long)slot * 5);
             __syncwarp();
             if (lane == 0) {
                 __threadfence_block();
@@ -409,91 +418,90 @@ __host__ __device__ inline size_t grad_out_bytes(int stage_cap) {
     return ((size_t)stage_cap * 6 * sizeof(S) + 127) / 128 * 128;
 }
 
-// One work item of pass G': 32 (cell, variable) pairs of a tile.
-//   items [0, T / 16):  16 cells x (rho, second thermodynamic variable) -- lanes 0-15 extrapolate rho, lanes 16-31
-//                       the other variable, of the same 16 cells; the two lanes of a cell then close the
-//                       thermodynamic state (gas_model.h:91-117) of half of the cell's faces each;
-//   the others:         32 cells x one velocity component (vx, vy[, vz]).
-// One code path computes the gradient, the limiter and the extrapolation of the lane's variable (var_to_faces);
-// only the epilogue differs.
+// One work item of pass G', one cell per lane:
+//   items [0, T / 32):  32 cells x (rho, then the second thermodynamic variable), and the thermodynamic closure
+//                       (gas_model.h:91-117) of every face -> rho p T of the cell's side records;
+//   the others:         all T cells (T / 32 rounds of 32) x one velocity component -> vx | vy | vz of the records.
+// Items are of about the same size (two gradient + limiter + extrapolation passes each at T = 64).  ONE loop body
+// serves every pass of both kinds -- a single instance of var_to_faces in the kernel: with twenty warps at different
+// places of the code, its size is what the instruction cache sees (a variant with four inlined instances spent 37 %
+// of its stall samples waiting for instructions).
 template <int DIM, int NF, int T, typename S>
-__device__ __forceinline__ void grad_task(const FvArgs<S>& A, const double* wd, const GRec& R, const S* sv, const int svs,
+__device__ __forceinline__ void grad_item(const FvArgs<S>& A, const double* wd, const GRec& R, const S* sv, const int svs,
                                           S* stg, const int task, const int nc, const int lane) {
-    constexpr int N_THERMO = T / 16;
-    const bool thermo = task < N_THERMO;
-    const int q = task - N_THERMO;
-    const int var = thermo ? (lane >> 4) : 2 + q / (T / 32);
-    const int i = thermo ? task * 16 + (lane & 15) : (q % (T / 32)) * 32 + lane;
-    const bool active = i < nc;
+    constexpr int N_THERMO = T / 32;
     const bool limit = A.limiter_on != 0;
-    TileTables<NF, T> Tb;
-    Tb.w = wd;
-    Tb.idx = i;
-    int fl[NF], st[NF];
-#pragma unroll
-    for (int j = 0; j < NF; j++) {
-        fl[j] = R.nbr[j * T + i];
-        st[j] = R.stage[j * T + i];
-    }
-    const S ui = sv[var * svs + i];
-    S un[NF], r[NF];
-#pragma unroll
-    for (int j = 0; j < NF; j++) un[j] = sv[var * svs + (fl[j] & NBR_LOCAL_MASK)];
-    var_to_faces<DIM, NF>(ui, un, Tb, A.eps, limit, r);
+    const bool thermo = task < N_THERMO;
+    const bool ghosts = R.hdr[4] != 0;                    // warp-uniform: the tile has boundary interfaces at all
     const int nR = R.hdr[1], n_own_l = R.hdr[2];
-    if (thermo) {
-        S o[NF];
-#pragma unroll
-        for (int j = 0; j < NF; j++) o[j] = shfl_xor_s(r[j], 16);
-        constexpr int H = (NF + 1) / 2;
-#pragma unroll
-        for (int jj = 0; jj < H; jj++) {
-            const int j0 = jj, j1 = H + jj;
-            S rho_j, th_j;
-            int st_j;
-            if (j1 < NF) {
-                rho_j = var ? o[j1] : r[j0];
-                th_j = var ? r[j1] : o[j0];
-                st_j = var ? st[j1] : st[j0];
-            } else {
-                rho_j = r[j0];
-                th_j = o[j0];
-                st_j = var ? 0xFFFF : st[j0];
-            }
-            if (active && st_j != 0xFFFF) side_close_store(A.thermo, A.gas, rho_j, th_j, stg + (long)st_j * 6);
-        }
-        // the far side of a boundary interface is the ghost cell itself: zero gradient, unit limiter
-        // (convective_flux.cpp:281-300), i.e. its values, closed thermodynamically like any other side
+    constexpr int VR = IBIS_PIPE_G_SPLITVEL ? T / 32 : 1;  // velocity items per component
+    const int v = (task - N_THERMO) / VR;                 // velocity item: 0, 1, 2 = vx, vy, vz
+    const int vround = (task - N_THERMO) % VR;
+    const int n_pass = thermo ? 2 : (IBIS_PIPE_G_SPLITVEL ? 1 : T / 32);
+#pragma unroll 1
+    for (int pass = 0; pass < n_pass; pass++) {
+        const int i = (thermo ? task : (IBIS_PIPE_G_SPLITVEL ? vround : pass)) * 32 + lane;
+        if (i >= nc) continue;
+        const S* row = sv + (size_t)(thermo ? pass : 2 + v) * svs;
+        TileTables<NF, T> Tb;
+        Tb.w = wd;
+        Tb.idx = i;
+        int fl[NF], st[NF];
 #pragma unroll
         for (int j = 0; j < NF; j++) {
-            const bool gh = active && st[j] != 0xFFFF && (fl[j] & NBR_GHOST_BIT);
-            if (__any_sync(0xffffffffu, gh)) {
-                const S uo = shfl_xor_s(un[j], 16);
-                if (gh && var == 0) {
-                    const int far_idx = far_stage_index((fl[j] & NBR_LEFT_BIT) != 0, st[j], nR, n_own_l);
-                    side_close_store(A.thermo, A.gas, un[j], uo, stg + (long)far_idx * 6);
+            fl[j] = R.nbr[j * T + i];
+            st[j] = R.stage[j * T + i];
+        }
+        const S ui = row[i];
+        S un[NF], r[NF];
+#pragma unroll
+        for (int j = 0; j < NF; j++) un[j] = row[fl[j] & NBR_LOCAL_MASK];
+        var_to_faces<DIM, NF>(ui, un, Tb, A.eps, limit, r);
+        if (thermo) {
+            // rho (pass 0) and the second variable (pass 1) are parked in the first two places of the side records;
+            // after pass 1 ONE loop over the faces (not unrolled: a single instance of the closure in the kernel)
+            // closes every record in place
+#pragma unroll
+            for (int j = 0; j < NF; j++)
+                if (st[j] != 0xFFFF) stg[(long)st[j] * 6 + pass] = r[j];
+            if (pass == 1) {
+#pragma unroll 1
+                for (int j = 0; j < NF; j++) {
+                    const int e = R.nbr[j * T + i], sj = R.stage[j * T + i];
+                    if (sj == 0xFFFF) continue;
+                    S* q = stg + (long)sj * 6;
+                    side_close_store(A.thermo, A.gas, q[0], q[1], q);
+                    // the far side of a boundary interface is the ghost cell itself: zero gradient, unit limiter
+                    // (convective_flux.cpp:281-300), i.e. its values, closed thermodynamically like any other side
+                    if (ghosts && (e & NBR_GHOST_BIT))
+                        side_close_store(A.thermo, A.gas, sv[e & NBR_LOCAL_MASK], sv[svs + (e & NBR_LOCAL_MASK)],
+                                         stg + (long)far_stage_index((e & NBR_LEFT_BIT) != 0, sj, nR, n_own_l) * 6);
                 }
             }
-        }
-    } else if (active) {
-        const int kq = 3 + (var - 2);
+        } else {
 #pragma unroll
-        for (int j = 0; j < NF; j++) {
-            if (st[j] == 0xFFFF) continue;
-            S* qd = stg + (long)st[j] * 6;
-            qd[kq] = r[j];
-            // 2-D: vz has no gradient (convective_flux.cpp:206-208) and a unit limiter: the vy lane copies the value
-            if (DIM == 2 && var == 3) qd[5] = sv[4 * svs + i];
-            if (fl[j] & NBR_GHOST_BIT) {
-                S* f = stg + (long)far_stage_index((fl[j] & NBR_LEFT_BIT) != 0, st[j], nR, n_own_l) * 6;
-                f[kq] = un[j];
-                if (DIM == 2 && var == 3) f[5] = sv[4 * svs + (fl[j] & NBR_LOCAL_MASK)];
+            for (int j = 0; j < NF; j++) {
+                if (st[j] == 0xFFFF) continue;
+                stg[(long)st[j] * 6 + 3 + v] = r[j];
+                if (ghosts && (fl[j] & NBR_GHOST_BIT))
+                    stg[(long)far_stage_index((fl[j] & NBR_LEFT_BIT) != 0, st[j], nR, n_own_l) * 6 + 3 + v] = un[j];
+            }
+            if (DIM == 2 && v == 1) {
+                // 2-D: vz has no gradient (convective_flux.cpp:206-208) and a unit limiter: the value is copied
+                const S* rz = sv + (size_t)4 * svs;
+#pragma unroll
+                for (int j = 0; j < NF; j++) {
+                    if (st[j] == 0xFFFF) continue;
+                    stg[(long)st[j] * 6 + 5] = rz[i];
+                    if (ghosts && (fl[j] & NBR_GHOST_BIT))
+                        stg[(long)far_stage_index((fl[j] & NBR_LEFT_BIT) != 0, st[j], nR, n_own_l) * 6 + 5] = rz[fl[j] & NBR_LOCAL_MASK];
+                }
             }
         }
     }
 }
 
-// Work items of a block, in queue order: the N_TASKS (cell, variable) items of its tiles.  The warp that completes a
+// Work items of a block, in queue order: the N_TASKS = T / 32 + (2 | 3) items of its tiles (grad_item).  The warp that completes a
 // tile's last item sends the tile's side records off (the push list of the tile's record: bulk stores out of the
 // staging buffer) and hands the input stage back.  Input stages recycle through an mbarrier guarded by stage_tile
 // (see k_flux_pipe), the staging buffers through the monotone counter out_done.
@@ -534,7 +542,7 @@ __global__ void __launch_bounds__(32 * (IBIS_PIPE_G_WARPS + IBIS_PIPE_G_LOADERS)
         const int step = (int)gridDim.x, w = warp - ncw;
         constexpr int NL = IBIS_PIPE_G_LOADERS;
         const int PF = (pf + NL - 1) / NL * NL;
-        const int hoff = 4 * NF * T + 16 + 12 * g.push_cap;                   // halo list inside the record
+        const int hoff = 4 * NF * T + 32 + 12 * g.push_cap;                   // halo list inside the record
         auto tile_at = [&](int k) { const int idx = (int)blockIdx.x + k * step; return tile_list ? __ldg(tile_list + idx) : idx; };
         int ids[PIPE_HALO_REGS], n_halo = 0, ids_n[PIPE_HALO_REGS], n_halo_n = 0;
         auto fetch_ids = [&](int t, int* out, int& nh) {
@@ -597,7 +605,7 @@ __global__ void __launch_bounds__(32 * (IBIS_PIPE_G_WARPS + IBIS_PIPE_G_LOADERS)
         return;
     }
     // ---- consumers ----
-    constexpr int N_THERMO = T / 16, NV = DIM == 3 ? 3 : 2, N_TASKS = N_THERMO + NV * (T / 32);
+    constexpr int NV = DIM == 3 ? 3 : 2, N_TASKS = T / 32 + NV * (IBIS_PIPE_G_SPLITVEL ? T / 32 : 1);
     const int total = n_my * N_TASKS;
     const unsigned mT = pipe_magic(N_TASKS), mI = pipe_magic(nsi), mO = pipe_magic(nso);
     // the bulk stores this warp issued for tile pend_k out of staging buffer pend_o and has not yet seen drained
@@ -636,7 +644,7 @@ __global__ void __launch_bounds__(32 * (IBIS_PIPE_G_WARPS + IBIS_PIPE_G_LOADERS)
         S* stg = reinterpret_cast<S*>(out_base + (unsigned)o * out_bytes);
         const double* wd = reinterpret_cast<const double*>(st);
         const S* sv = reinterpret_cast<const S*>(st + WD_BYTES + g.grec_stride);
-        grad_task<DIM, NF, T, S>(A, wd, R, sv, svs, stg, r, nc_of[s], lane);
+        grad_item<DIM, NF, T, S>(A, wd, R, sv, svs, stg, r, nc_of[s], lane);
         ac::fence_proxy_async();                           // the staging writes -> visible to the TMA unit
         __syncwarp();
         int d = 0;
