@@ -38,7 +38,7 @@
 #define IBIS_PIPE_G_WARPS 13      // consumer warps of pass G'
 #endif
 #ifndef IBIS_PIPE_G_LOADERS
-#define IBIS_PIPE_G_LOADERS 3     // loader warps of pass G'
+#define IBIS_PIPE_G_LOADERS 2     // loader warps of pass G' (one more service warp sends the side records off)
 #endif
 #ifndef IBIS_PIPE_F_ROUNDS
 #define IBIS_PIPE_F_ROUNDS 1      // interfaces per lane of a flux item of pass F' (measured: 2 is slower)
@@ -413,9 +413,10 @@ __host__ __device__ inline size_t grad_stage_bytes(int nf, int T, int grec_strid
     size_t b = (size_t)2 * nf * 3 * T * 8 + (size_t)grec_stride + (size_t)5 * (T + halo_cap) * sizeof(S);
     return (b + 127) / 128 * 128;
 }
+// staging buffer = [side records stage_cap x 6 S | the tile's push list: int n_push, pad x 3, push[push_cap][3]]
 template <typename S>
-__host__ __device__ inline size_t grad_out_bytes(int stage_cap) {
-    return ((size_t)stage_cap * 6 * sizeof(S) + 127) / 128 * 128;
+__host__ __device__ inline size_t grad_out_bytes(int stage_cap, int push_cap) {
+    return ((size_t)stage_cap * 6 * sizeof(S) + 16 + (size_t)12 * push_cap + 127) / 128 * 128;
 }
 
 // One work item of pass G', one cell per lane:
@@ -501,24 +502,25 @@ __device__ __forceinline__ void grad_item(const FvArgs<S>& A, const double* wd, 
     }
 }
 
-// Work items of a block, in queue order: the N_TASKS = T / 32 + (2 | 3) items of its tiles (grad_item).  The warp that completes a
-// tile's last item sends the tile's side records off (the push list of the tile's record: bulk stores out of the
-// staging buffer) and hands the input stage back.  Input stages recycle through an mbarrier guarded by stage_tile
+// Work items of a block, in queue order: the N_TASKS items of its tiles (grad_item).  The warp that completes a
+// tile's last item hands the input stage back to the loaders and the staging buffer over to the store warp (the push
+// list of the tile's record: bulk stores out of the staging buffer).  Input stages recycle through an mbarrier guarded by stage_tile
 // (see k_flux_pipe), the staging buffers through the monotone counter out_done.
 template <int DIM, int NF, int T, typename S>
-__global__ void __launch_bounds__(32 * (IBIS_PIPE_G_WARPS + IBIS_PIPE_G_LOADERS), 1)
+__global__ void __launch_bounds__(32 * (IBIS_PIPE_G_WARPS + IBIS_PIPE_G_LOADERS + 1), 1)
     k_grad_pipe(const FvArgs<S> A, const int* __restrict__ tile_list, const int n_list, const int nsi, const int nso, const int pf) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t full[PIPE_MAX_STAGES];
-    __shared__ int stage_tile[PIPE_MAX_STAGES], stage_free[PIPE_MAX_STAGES], done_tasks[PIPE_MAX_STAGES], out_done[PIPE_MAX_STAGES],
-        nc_of[PIPE_MAX_STAGES], q_head;
+    __shared__ int stage_tile[PIPE_MAX_STAGES], stage_free[PIPE_MAX_STAGES], done_tasks[PIPE_MAX_STAGES], out_ready[PIPE_MAX_STAGES],
+        out_done[PIPE_MAX_STAGES], nc_of[PIPE_MAX_STAGES], q_head;
     const GridDev& g = A.g;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ncw = (int)(blockDim.x >> 5) - IBIS_PIPE_G_LOADERS;
+    const int ncw = (int)(blockDim.x >> 5) - IBIS_PIPE_G_LOADERS - 1;
     const int svs = T + g.halo_cap;
     constexpr int WD_BYTES = 2 * NF * 3 * T * 8;
     const unsigned in_bytes = (unsigned)grad_stage_bytes<S>(NF, T, g.grec_stride, g.halo_cap);
-    const unsigned out_bytes = (unsigned)grad_out_bytes<S>(g.stage_cap);
+    const unsigned out_bytes = (unsigned)grad_out_bytes<S>(g.stage_cap, g.push_cap);
+    const unsigned off_push = (unsigned)g.stage_cap * 6u * (unsigned)sizeof(S);   // push list inside a staging buffer
     unsigned char* out_base = smem + (unsigned)nsi * in_bytes;
     if (threadIdx.x == 0) {
         for (int s = 0; s < nsi; s++) {
@@ -527,12 +529,36 @@ __global__ void __launch_bounds__(32 * (IBIS_PIPE_G_WARPS + IBIS_PIPE_G_LOADERS)
             stage_free[s] = -1;
             done_tasks[s] = 0;
         }
-        for (int o = 0; o < nso; o++) out_done[o] = -1;
+        for (int o = 0; o < nso; o++) { out_done[o] = -1; out_ready[o] = -1; }
         q_head = 0;
         ac::fence_barrier_init();
     }
     __syncthreads();
     const int n_my = (int)blockIdx.x < n_list ? (n_list - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    if (warp == ncw + IBIS_PIPE_G_LOADERS) {
+        // ---- the store warp: when a tile's side records are complete in a staging buffer (out_ready) they leave as
+        // the bulk stores of the tile's push list; the buffer is free again (out_done) once the stores have read it ----
+        for (int k = 0; k < n_my; k++) {
+            const int o = k % nso;
+            if (!pipe_spin_ge(&out_ready[o], k, A.pipe_dbg, 16 + PW_DONE, k)) return;
+            ac::fence_proxy_async();
+            const unsigned char* ob = out_base + (unsigned)o * out_bytes;
+            const S* stg = reinterpret_cast<const S*>(ob);
+            const int* pl = reinterpret_cast<const int*>(ob + off_push);
+            const int n_push = pl[0];
+            for (int q = lane; q < n_push; q += 32) {
+                const int src = pl[4 + 3 * q], count = pl[5 + 3 * q], dst = pl[6 + 3 * q];
+                if (count > 0) ac::bulk_s2g(A.sidesP + (size_t)dst * 6, stg + (long)src * 6, (uint32_t)count * 6 * (uint32_t)sizeof(S));
+            }
+            ac::bulk_commit_wait_read();                   // the store warp has nothing else to do than to see them drained
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_block();
+                *reinterpret_cast<volatile int*>(&out_done[o]) = k;
+            }
+        }
+        return;
+    }
     if (warp >= ncw) {
         // ---- loaders: loader w takes the block's tiles w, w + NL, ...  Per tile the WLS slice, the record and five
         // state rows as bulk copies, the halo list's state as cp.async gathers; the halo ids of the loader's NEXT tile
@@ -608,33 +634,12 @@ __global__ void __launch_bounds__(32 * (IBIS_PIPE_G_WARPS + IBIS_PIPE_G_LOADERS)
     constexpr int NV = DIM == 3 ? 3 : 2, N_TASKS = T / 32 + NV * (IBIS_PIPE_G_SPLITVEL ? T / 32 : 1);
     const int total = n_my * N_TASKS;
     const unsigned mT = pipe_magic(N_TASKS), mI = pipe_magic(nsi), mO = pipe_magic(nso);
-    // the bulk stores this warp issued for tile pend_k out of staging buffer pend_o and has not yet seen drained
-    int pend_o = -1, pend_k = 0;
-    auto flush_pending = [&]() {
-        if (pend_o < 0) return;
-        ac::bulk_commit_wait_read();                       // the staging buffer may be written again after this
-        __syncwarp();
-        if (lane == 0) {
-            __threadfence_block();
-            *reinterpret_cast<volatile int*>(&out_done[pend_o]) = pend_k;
-        }
-        pend_o = -1;
-    };
     for (;;) {
         const int item = pipe_next_item(&q_head, lane);
         if (item >= total) break;
         const int k = pipe_div(item, mT), r = item - k * N_TASKS;
         const int ui = pipe_div(k, mI);
         const int s = k - ui * nsi, o = k - pipe_div(k, mO) * nso;
-        const bool had_pending = pend_o >= 0;
-        // Never block while sitting on an unpublished store: the tile this item waits for may (through the stage and
-        // staging-buffer rings) be waiting for exactly that publication.  The drain wait is deferred only past an
-        // item whose data is already there.
-        if (had_pending) {
-            const bool ready = *reinterpret_cast<volatile int*>(&stage_tile[s]) >= k && ac::mbar_test_wait(&full[s], ui & 1) &&
-                               (k < nso || (pend_o != o && *reinterpret_cast<volatile int*>(&out_done[o]) >= k - nso));
-            if (!__all_sync(0xffffffffu, ready)) flush_pending();
-        }
         if (!pipe_spin_ge(&stage_tile[s], k, A.pipe_dbg, 16 + PW_STAGE, k)) return;
         if (!pipe_wait(&full[s], ui & 1, A.pipe_dbg, 16 + PW_FULL, k)) return;
         // the staging buffer is free once the stores of the tile nso tiles back have read it
@@ -654,31 +659,22 @@ __global__ void __launch_bounds__(32 * (IBIS_PIPE_G_WARPS + IBIS_PIPE_G_LOADERS)
         }
         d = __shfl_sync(0xffffffffu, d, 0);
         if (d == N_TASKS - 1) {
-            // the tile's last item: its side records are complete in the staging buffer and leave as a handful of
-            // bulk stores; the input stage goes back to the loader at once, the staging buffer when this warp has
-            // seen the stores drained -- one item later, so that it does not sit and wait for them
+            // the tile's last item: its side records are complete in the staging buffer.  The push list moves next to
+            // them, the input stage goes back to the loaders, and the store warp takes over the buffer
             __threadfence_block();
-            flush_pending();
-            ac::fence_proxy_async();
+            int* pl = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(stg) + off_push);
             const int n_push = R.hdr[3];
-            for (int q = lane; q < n_push; q += 32) {
-                const int src = R.push[3 * q], count = R.push[3 * q + 1], dst = R.push[3 * q + 2];
-                if (count > 0) ac::bulk_s2g(A.sidesP + (size_t)dst * 6, stg + (long)src * 6, (uint32_t)count * 6 * (uint32_t)sizeof(S));
-            }
-            ac::bulk_commit();
+            if (lane == 0) pl[0] = n_push;
+            for (int q = lane; q < 3 * n_push; q += 32) pl[4 + q] = R.push[q];
             __syncwarp();
             if (lane == 0) {
                 done_tasks[s] = 0;
                 __threadfence_block();
                 *reinterpret_cast<volatile int*>(&stage_free[s]) = k;
+                *reinterpret_cast<volatile int*>(&out_ready[o]) = k;
             }
-            pend_o = o;
-            pend_k = k;
-        } else if (had_pending) {
-            flush_pending();
         }
     }
-    flush_pending();
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -696,13 +692,13 @@ static bool set_smem(ibis_b200_ctx* c, K kernel, size_t smem) {
 
 template <int DIM, int NF, int T, typename S>
 static void launch_grad_pipe_t(ibis_b200_ctx* c, const FvArgs<S>& A, const int* list, int n_list) {
-    const size_t in_b = grad_stage_bytes<S>(NF, T, A.g.grec_stride, A.g.halo_cap), out_b = grad_out_bytes<S>(A.g.stage_cap);
+    const size_t in_b = grad_stage_bytes<S>(NF, T, A.g.grec_stride, A.g.halo_cap), out_b = grad_out_bytes<S>(A.g.stage_cap, A.g.push_cap);
     // staging buffers: four when they fit (items + drain of a tile overlap the next tiles'), the rest input stages
     int nso = 4;
     while (nso > 1 && (size_t)nso * out_b + 2 * in_b > PIPE_SMEM_BUDGET) nso--;
     int nsi = (size_t)nso * out_b < PIPE_SMEM_BUDGET ? (int)((PIPE_SMEM_BUDGET - (size_t)nso * out_b) / in_b) : 0;
     if (nsi > PIPE_MAX_STAGES) nsi = PIPE_MAX_STAGES;
-    if (nsi < 2 || A.g.halo_cap > 32 * PIPE_HALO_REGS) {
+    if (nsi < 2 || nso < 2 || A.g.halo_cap > 32 * PIPE_HALO_REGS) {
         if (c->last_error.empty()) c->last_error = "pass G': a tile does not fit shared memory";
         return;
     }
@@ -710,7 +706,7 @@ static void launch_grad_pipe_t(ibis_b200_ctx* c, const FvArgs<S>& A, const int* 
     auto kernel = k_grad_pipe<DIM, NF, T, S>;
     if (!set_smem(c, kernel, smem)) return;
     const int grid = n_list < c->n_sm ? n_list : c->n_sm;
-    kernel<<<grid, 32 * (IBIS_PIPE_G_WARPS + IBIS_PIPE_G_LOADERS), smem, c->stream>>>(A, list, n_list, nsi, nso, c->pipe_prefetch);
+    kernel<<<grid, 32 * (IBIS_PIPE_G_WARPS + IBIS_PIPE_G_LOADERS + 1), smem, c->stream>>>(A, list, n_list, nsi, nso, c->pipe_prefetch);
 }
 
 template <int DIM, int T, typename S>
