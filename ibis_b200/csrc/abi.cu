@@ -1461,6 +1461,15 @@ int ibis_b200_debug_dual_ops(ibis_b200_ctx* c, const double* in5, double* out44)
     return c->last_error.empty() ? 0 : IBIS_B200_ECUDA;
 }
 
+int ibis_b200_debug_division_check(ibis_b200_ctx* c, int64_t n, uint64_t seed, uint64_t* mismatches) {
+    if (!c || !mismatches || n < 0) return fail(c, IBIS_B200_EINVAL, "null argument");
+    launch_division_check(c, n, seed, c->d_scalars + SC_BAD);
+    double v = 0;
+    int rc = fetch_scalars(c, SC_BAD, 1, &v);
+    *mismatches = (uint64_t)v;
+    return rc;
+}
+
 int ibis_b200_debug_gradients(ibis_b200_ctx* c, int var, double* grad, double* limiter) {
     if (var < 0 || var >= NVARS) return fail(c, IBIS_B200_EINVAL, "no gradients available");
     if (sides_path(c)) {
@@ -1640,16 +1649,35 @@ int ibis_b200_jfnk_apply_update(ibis_b200_ctx* c, int cq, int du_) {
 }
 
 // ---- vectors ----
+// Inner products on a decomposed grid.  A Krylov vector has n_cells * n_cons entries in reference numbering, owned
+// cells first (partition.py, box_grid.cpp); the entries of halo cells are copies nobody reads (the dual flow state of
+// a halo cell arrives through the halo exchange of compute_dudt).  Dots and norms therefore run over the owned prefix
+// and are summed over the ranks before anything is derived from them (square root, reciprocal, the axpy of
+// Gram-Schmidt): every rank sees the same Hessenberg entries and residual norms and takes the same decisions.
+static int dot_collective(ibis_b200_ctx* c, const double* a, const double* b, int64_t n, double* d_out, int post) {
+    if (c->n_ranks <= 1) {
+        launch_dot(c, a, b, n, d_out, post);
+        return 0;
+    }
+    const int64_t n_red = (n == c->n_cells * c->n_cons) ? c->n_owned * c->n_cons : n;
+    launch_dot(c, a, b, n_red, d_out, 0);
+    int rc = comm::allreduce(c, d_out, 1, comm::OP_SUM);
+    if (rc) return rc;
+    if (post) launch_scalar_post(c, d_out, post);
+    return 0;
+}
 int ibis_b200_vec_dot(ibis_b200_ctx* c, int a, int b, double* out) {
     Buffer *x = get_buf(c, a, BUF_VEC), *y = get_buf(c, b, BUF_VEC);
     if (!x || !y || x->n != y->n || !out) return fail(c, IBIS_B200_EHANDLE, "vec_dot: bad handles");
-    launch_dot(c, static_cast<double*>(x->d), static_cast<double*>(y->d), x->n, c->d_scalars + SC_DOT, 0);
+    int rc = dot_collective(c, static_cast<double*>(x->d), static_cast<double*>(y->d), x->n, c->d_scalars + SC_DOT, 0);
+    if (rc) return rc;
     return fetch_scalars(c, SC_DOT, 1, out);
 }
 int ibis_b200_vec_norm2(ibis_b200_ctx* c, int a, double* out) {
     Buffer* x = get_buf(c, a, BUF_VEC);
     if (!x || !out) return fail(c, IBIS_B200_EHANDLE, "vec_norm2: bad handle");
-    launch_dot(c, static_cast<double*>(x->d), static_cast<double*>(x->d), x->n, c->d_scalars + SC_NORM, 1);
+    int rc = dot_collective(c, static_cast<double*>(x->d), static_cast<double*>(x->d), x->n, c->d_scalars + SC_NORM, 1);
+    if (rc) return rc;
     return fetch_scalars(c, SC_NORM, 1, out);
 }
 int ibis_b200_vec_axpy(ibis_b200_ctx* c, int y, int x, double s) {
@@ -1687,10 +1715,12 @@ int ibis_b200_arnoldi_mgs(ibis_b200_ctx* c, int basis, int j, int w, int v, doub
     double* hs = c->d_scalars + SC_H;
     for (int i = 0; i <= j; i++) {
         const double* vi = static_cast<double*>(B->d) + (int64_t)i * B->stride;
-        launch_dot(c, wd, vi, W->n, hs + i, 0);                      // H(i,j) = dot(w, V_i)
+        int rc = dot_collective(c, wd, vi, W->n, hs + i, 0);         // H(i,j) = dot(w, V_i), summed over the ranks
+        if (rc) return rc;
         launch_axpy(c, wd, vi, 0.0, hs + i, -1.0, W->n);             // w += V_i * (-H(i,j))
     }
-    launch_dot(c, wd, wd, W->n, hs + j + 1, 2);                      // H(j+1,j) = norm2(w); hs[j+2] = 1/H
+    int rc = dot_collective(c, wd, wd, W->n, hs + j + 1, 2);         // H(j+1,j) = norm2(w); hs[j+2] = 1/H
+    if (rc) return rc;
     launch_scale(c, wd, vd, 0.0, hs + j + 2, W->n);                  // v = w * (1.0 / H(j+1,j))
     GPU_TRY(c, gpu::d2d(static_cast<double*>(B->d) + (int64_t)(j + 1) * B->stride, vd, V->n * sizeof(double), c->stream));
     return fetch_scalars(c, SC_H, j + 2, h);

@@ -203,9 +203,11 @@ template <typename S>
 void launch_flow_write(ibis_b200_ctx* c, S* const* fs, double* stage, int64_t n, int has_vz);
 void launch_gather_debug(ibis_b200_ctx* c, const double* src, int ncomp, int64_t n, double* out);
 void launch_dual_kat(ibis_b200_ctx* c, const double* in, double* out);   // solver_bodies.h::dual_kat_body, one thread
+void launch_division_check(ibis_b200_ctx* c, int64_t n, uint64_t seed, double* d_out);   // mismatches of div_pair / div_shared / div_z
 // vectors
 void launch_dot(ibis_b200_ctx* c, const double* a, const double* b, int64_t n, double* d_out,
                 int post);   // post: 0 none, 1 sqrt, 2 sqrt and also store 1/sqrt at d_out[1]
+void launch_scalar_post(ibis_b200_ctx* c, double* d_out, int post);   // the post step alone, after a cross-rank sum
 void launch_axpy(ibis_b200_ctx* c, double* y, const double* x, double s, const double* d_s,
                  double sign, int64_t n);
 void launch_scale(ibis_b200_ctx* c, const double* x, double* r, double s, const double* d_s,

@@ -110,43 +110,49 @@ IBIS_HD Flux5<S> flux_hanel(const Side<S>& L, const Side<S>& R_, const Gas<S>& g
 // finite_volume/flux_calculators/ausmdv.cpp:12-131
 template <typename S>
 IBIS_HD Flux5<S> flux_ausmdv(const Side<S>& L, const Side<S>& R_, const Gas<S>& g) {
+    // the quotients of the reference's expressions, two at a time where they are independent or share their
+    // denominator (scalar.h::div_pair / div_shared: the same quotients, bit for bit)
     S rL = L.rho, pL = L.p;
-    S pLrL = pL / rL;
+    S rR = R_.rho, pR = R_.p;
+    S pLrL, pRrR;
+    div_pair(pL, rL, pR, rR, pLrL, pRrR);
     S uL = L.u, vL = L.v, wL = L.w;
     S eL = g.Cv * L.T;
     S aL = speed_of_sound(L.T, g.R, g.gamma);
     S keL = 0.5 * (uL * uL + vL * vL + wL * wL);
     S HL = eL + pLrL + keL;
 
-    S rR = R_.rho, pR = R_.p;
-    S pRrR = pR / rR;
     S uR = R_.u, vR = R_.v, wR = R_.w;
     S eR = g.Cv * R_.T;
     S aR = speed_of_sound(R_.T, g.R, g.gamma);
     S keR = 0.5 * (uR * uR + vR * vR + wR * wR);
     S HR = eR + pRrR + keR;
 
-    S alphaL = 2.0 * pLrL / (pLrL + pRrR);
-    S alphaR = 2.0 * pRrR / (pLrL + pRrR);
+    S alphaL, alphaR;
+    div_shared(2.0 * pLrL, 2.0 * pRrR, pLrL + pRrR, alphaL, alphaR);
 
     S am = max_(aL, aR);
-    S ML = uL / am;
-    S MR = uR / am;
+    S ML, MR;
+    div_shared(uL, uR, am, ML, MR);
+    // (uL + am)^2 / (4 am) and -(uR - am)^2 / (4 am) of the subsonic branches
+    const bool subL = re(abs_(ML)) <= 1.0, subR = re(abs_(MR)) <= 1.0;
+    S qLs = S(0.0), qRs = S(0.0);
+    if (subL || subR) div_shared((uL + am) * (uL + am), -(uR - am) * (uR - am), 4.0 * am, qLs, qRs);
 
     S pLplus, uLplus;
     S duL = 0.5 * (uL + abs_(uL));
-    if (re(abs_(ML)) <= 1.0) {
+    if (subL) {
         pLplus = pL * (ML + 1.0) * (ML + 1.0) * (2.0 - ML) * 0.25;
-        uLplus = alphaL * ((uL + am) * (uL + am) / (4.0 * am) - duL) + duL;
+        uLplus = alphaL * (qLs - duL) + duL;
     } else {
         pLplus = div_z(pL * duL, uL);
         uLplus = duL;
     }
     S pRminus, uRminus;
     S duR = 0.5 * (uR - abs_(uR));
-    if (re(abs_(MR)) <= 1.0) {
+    if (subR) {
         pRminus = pR * (MR - 1.0) * (MR - 1.0) * (2.0 + MR) * 0.25;
-        uRminus = alphaR * (-(uR - am) * (uR - am) / (4.0 * am) - duR) + duR;
+        uRminus = alphaR * (qRs - duR) + duR;
     } else {
         pRminus = div_z(pR * duR, uR);
         uRminus = duR;

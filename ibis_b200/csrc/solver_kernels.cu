@@ -485,6 +485,53 @@ template void launch_pack_out<double>(ibis_b200_ctx*, double* const*, const int*
 template void launch_pack_out<dual>(ibis_b200_ctx*, dual* const*, const int*, int, int64_t, double*, double*);
 
 __global__ void k_dual_kat(const double* in, double* out) { dual_kat_body(in, out); }
+// operands for the division self-test: a 64-bit mix, shaped so that every exponent (denormals, zeros, infinities and
+// NaNs included) and both signs turn up, and so that equal and nearly equal operands are frequent
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
+    x += 0x9e3779b97f4a7c15ull;
+    x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull;
+    x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
+    return x ^ (x >> 31);
+}
+__device__ __forceinline__ double test_operand(unsigned long long r) {
+    const unsigned kind = (unsigned)(r >> 60);
+    if (kind == 0) return __longlong_as_double((long long)(r & 0x8000000000000000ull));             // +-0
+    if (kind == 1) return __longlong_as_double((long long)(r & 0x800fffffffffffffull));              // denormal
+    if (kind == 2) return __longlong_as_double((long long)((r & 0x8000000000000000ull) | 0x7ff0000000000000ull | ((r & 1) ? (r & 0xfffff) : 0)));
+    if (kind < 8) {                                                                                  // moderate magnitudes
+        const unsigned long long e = 1023 - 40 + ((r >> 52) & 0x7f) % 80;
+        return __longlong_as_double((long long)((r & 0x800fffffffffffffull) | (e << 52)));
+    }
+    return __longlong_as_double((long long)(r & ~(0xfull << 60) | ((r >> 4) & (0x7ull << 60))));    // any exponent
+}
+__device__ __forceinline__ bool same_bits(double a, double b) {
+    return __double_as_longlong(a) == __double_as_longlong(b) || (a != a && b != b);
+}
+__global__ void __launch_bounds__(256) k_division_check(long long n, unsigned long long seed, unsigned long long* bad) {
+    unsigned long long local = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long r = mix64(seed + 4 * (unsigned long long)i);
+        const double a1 = test_operand(r), b1 = test_operand(mix64(r + 1)), a2 = test_operand(mix64(r + 2));
+        double b2 = test_operand(mix64(r + 3));
+        if ((r & 0x300) == 0) b2 = a2;                       // equal operands
+        double q1, q2;
+        div_pair(a1, b1, a2, b2, q1, q2);
+        local += !same_bits(q1, a1 / b1) + !same_bits(q2, a2 / b2);
+        div_shared(a1, a2, b1, q1, q2);
+        local += !same_bits(q1, a1 / b1) + !same_bits(q2, a2 / b1);
+        local += !same_bits(div_z(a1, b2), a1 / b2);
+    }
+    if (local) atomicAdd(bad, local);
+}
+__global__ void k_u64_to_double(unsigned long long* p) { *reinterpret_cast<double*>(p) = (double)*p; }
+void launch_division_check(ibis_b200_ctx* c, int64_t n, uint64_t seed, double* d_out) {
+    unsigned long long* bad = reinterpret_cast<unsigned long long*>(d_out);
+    cudaMemsetAsync(bad, 0, 8, c->stream);
+    k_division_check<<<148 * 8, 256, 0, c->stream>>>((long long)n, (unsigned long long)seed, bad);
+    k_u64_to_double<<<1, 1, 0, c->stream>>>(bad);
+    CUDA_CHECK_LAUNCH(c);
+}
+
 void launch_dual_kat(ibis_b200_ctx* c, const double* in, double* out) {
     k_dual_kat<<<1, 1, 0, c->stream>>>(in, out);
     CUDA_CHECK_LAUNCH(c);
@@ -512,6 +559,16 @@ void launch_dot(ibis_b200_ctx* c, const double* a, const double* b, int64_t n, d
     k_dot_partial<<<nb, 256, 0, c->stream>>>(a, b, n, c->d_partials);
     CUDA_CHECK_LAUNCH(c);
     k_final_sum<1><<<1, 256, 0, c->stream>>>(c->d_partials, nb, d_out, post);
+    CUDA_CHECK_LAUNCH(c);
+}
+
+__global__ void k_scalar_post(double* out, int post) {
+    out[0] = sqrt(out[0]);
+    if (post == 2) out[1] = 1.0 / out[0];
+}
+void launch_scalar_post(ibis_b200_ctx* c, double* d_out, int post) {
+    if (!post) return;
+    k_scalar_post<<<1, 1, 0, c->stream>>>(d_out, post);
     CUDA_CHECK_LAUNCH(c);
 }
 

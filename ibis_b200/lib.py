@@ -232,6 +232,7 @@ class Library:
             "ibis_b200_apply_time_derivative": [vp, i, i, i, d],
             "ibis_b200_l2_norms": [vp, i, vp],
             "ibis_b200_debug_gradients": [vp, i, vp, vp], "ibis_b200_debug_dual_ops": [vp, vp, vp],
+            "ibis_b200_debug_division_check": [vp, i64, C.c_uint64, C.POINTER(C.c_uint64)],
             "ibis_b200_set_face_vertices": [vp, vp, i64], "ibis_b200_set_vertex_velocities": [vp, vp],
             "ibis_b200_compute_dudt_moving": [vp, i, i, i, i],
             "ibis_b200_set_cell_vertices": [vp, vp, vp], "ibis_b200_set_vertex_positions": [vp, vp],
@@ -572,6 +573,12 @@ class Context:
         out = np.zeros((self.n_faces, 3))
         self._ck(self.lib.ibis_b200_debug_face_velocities(self.h, _ptr(out)), "debug_face_velocities")
         return out
+
+    def debug_division_check(self, n, seed=1):
+        """-> number of quotients of the paired / shared device divisions that differ from the plain IEEE division"""
+        bad = C.c_uint64(0)
+        self._ck(self.lib.ibis_b200_debug_division_check(self.h, int(n), int(seed), C.byref(bad)), "debug_division_check")
+        return int(bad.value)
 
     def debug_dual_ops(self, x, y, r):
         """-> (22, 2) array of (re, du): see ibis_b200_debug_dual_ops in include/ibis_b200.h"""

@@ -272,6 +272,11 @@ int ibis_b200_debug_gradients(ibis_b200_ctx*, int var, double* grad, double* lim
  * in = {x.re, x.du, y.re, y.du, r}; out = 22 (re, du) pairs: x+y, x+=y, x+r, x-y, x-=y, x-r, r-x, x*y, x*=y,
  * x*r, x*=r, r*x, x/y, x/=y, x/r, x/=r, r/x, sqrt(x), abs(x), abs(x*x), x*x+2x, x*x-sqrt(x) */
 int ibis_b200_debug_dual_ops(ibis_b200_ctx*, const double* in5, double* out44);
+/* Self-test of the paired / shared fp64 divisions the flux calculators and the limiter use on the device
+ * (ibis_b200/csrc/scalar.h::div_pair, div_shared, div_z): n pseudo-random operand pairs per launch thread spanning
+ * the whole exponent range, zeros, infinities and NaNs included, each quotient compared bit for bit with the plain
+ * IEEE division.  *mismatches receives the number of differing quotients (0 expected). */
+int ibis_b200_debug_division_check(ibis_b200_ctx*, int64_t n, uint64_t seed, uint64_t* mismatches);
 
 /* ---- fused explicit step (solvers/runge_kutta.cpp:131-203) --------------------------- */
 /* One RungeKutta::take_step with the tableau a (row i has i entries, i = 1..stages-1,

@@ -461,6 +461,10 @@ void launch_pack_out(ibis_b200_ctx* c, S* const* comps, const int* map, int ncom
 template void launch_pack_out<double>(ibis_b200_ctx*, double* const*, const int*, int, int64_t, double*, double*);
 template void launch_pack_out<dual>(ibis_b200_ctx*, dual* const*, const int*, int, int64_t, double*, double*);
 
+void launch_division_check(ibis_b200_ctx* c, int64_t, uint64_t, double* d_out) {   // the host build divides plainly: nothing to compare
+    *d_out = 0.0;
+    c->launches++;
+}
 void launch_dual_kat(ibis_b200_ctx* c, const double* in, double* out) {
     dual_kat_body(in, out);
     c->launches++;
@@ -472,6 +476,12 @@ void launch_gather_debug(ibis_b200_ctx* c, const double* src, int ncomp, int64_t
         for (int q = 0; q < ncomp; q++) out[i * ncomp + q] = src[q * c->cstride + (perm ? perm[i] : i)];
 }
 
+void launch_scalar_post(ibis_b200_ctx* c, double* out, int post) {
+    if (!post) return;
+    out[0] = sqrt(out[0]);
+    if (post == 2) out[1] = 1.0 / out[0];
+    c->launches++;
+}
 void launch_dot(ibis_b200_ctx* c, const double* a, const double* b, int64_t n, double* out, int post) {
     double acc = 0.0;
     // IBIS_B200_EMU_DOT_LANES=4: another (equally valid) summation order, standing in for the
