@@ -234,7 +234,7 @@ int ensure_fv_temporaries(ibis_b200_ctx* c, bool want_grad = false, bool want_fl
     if (sides_path_for<S>(c)) {
         S** sp = (sizeof(S) == 8) ? reinterpret_cast<S**>(&c->sidesP_r) : reinterpret_cast<S**>(&c->sidesP_d);
         if (!*sp) {
-            int rc = dev_alloc_zero<S>(c, (int64_t)6 * std::max<int64_t>(c->p_total, 1), sp);
+            int rc = dev_alloc_zero<S>(c, (int64_t)SIDE_REC * std::max<int64_t>(c->p_total, 1), sp);
             if (rc) return fail(c, rc, "out of device memory (interface sides)");
         }
     }
@@ -748,8 +748,8 @@ int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd_ref, con
         UP2(out_off, di, out_off) UP2(out_slot, du16, out_slot) UP2(out_cell, di, out_cell) UP2(out_d, dd, out_d)
         g.n_out = n_out;
         // ---- packed per-tile records of the pipelined sides path (fv_pipe.cu; layout in fv_bodies.h::GridDev) ----
-        g.t_wd = nullptr; g.t_grec = nullptr; g.t_freca = nullptr; g.t_frec = nullptr; g.t_pinfo = nullptr;
-        g.grec_stride = g.freca_stride = g.frec_stride = g.halo_cap = g.push_cap = g.p_cap = 0;
+        g.t_wd = nullptr; g.t_grec = nullptr; g.t_freca = nullptr; g.t_frec = nullptr; g.t_pinfo = nullptr; g.t_pull = nullptr;
+        g.grec_stride = g.freca_stride = g.frec_stride = g.halo_cap = g.pull_cap = g.pull_stride = g.p_cap = 0;
         g.pipe_nf = max_faces < 3 ? 3 : max_faces;
         // the kernels recompute the interface normal as cross(t1, t2), the reference's own formula
         // (grid/interface.h:250): arrays that do not satisfy it bit for bit keep to the gather path
@@ -798,8 +798,9 @@ int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd_ref, con
                     }
                 std::sort(h.begin(), h.end());
                 h.erase(std::unique(h.begin(), h.end()), h.end());
-                n_stage[b] = ns;
+                n_stage[b] = (int)pad_to(ns, SIDE_EVEN);
             }
+            g.stage_cap = (int)pad_to(g.stage_cap, SIDE_EVEN);
             int halo_cap = 4;
             for (int b = 0; b < nt; b++) halo_cap = std::max<int>(halo_cap, (int)halos[b].size());
             halo_cap = (int)pad_to(halo_cap, 4);
@@ -810,17 +811,29 @@ int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd_ref, con
             if (halo_cap > 256) c->use_sides = false;
           if (c->use_sides) {
 
-            // side-state arrays of the owned tiles: where both sides of every flux slot live, who pushes what where
+            // side-state arrays: every tile's staging image goes to its own array (one bulk store of pass G'); pass F'
+            // assembles the image of an owned tile's interface sides from its own array and from runs of its
+            // neighbours' arrays (the far sides of its surface interfaces)
+            std::vector<int> pinfo((size_t)2 * std::max(nt, 1), 0);
+            int64_t ptotal = 0;
+            for (int b = 0; b < nt; b++) {
+                if (ptotal + n_stage[b] >= ((int64_t)1 << 31)) { ibis_b200_destroy(c); return fail(nullptr, IBIS_B200_EINVAL, "too many side records for 32-bit ids"); }
+                pinfo[2 * b] = (int)ptotal;
+                pinfo[2 * b + 1] = n_stage[b];
+                ptotal += n_stage[b];
+            }
+            c->p_total = ptotal;
             struct Foreign { int a, a_stage, slot, right; };
-            struct Push { int src, count, dst; };
-            std::vector<std::vector<Foreign>> foreign_of(n_tiles);
+            struct Pull { int src, count, dst; };
+            std::vector<std::vector<Pull>> pulls(std::max(n_tiles, 1));
+            std::vector<int> n_image(std::max(n_tiles, 1), 0);
             std::vector<int> lidx((size_t)capp * std::max(n_tiles, 1), 0), ridx((size_t)capp * std::max(n_tiles, 1), 0);
             bool bad_sides = false;
 #pragma omp parallel for schedule(dynamic, 64) reduction(|| : bad_sides)
             for (int b = 0; b < n_tiles; b++) {
                 const int nR = TL.nR[b], n_own_l = TL.n_own_left(b);
                 const int ns = (home0[b + 1] - home0[b]) + (foreign_off[b + 1] - foreign_off[b]);
-                std::vector<Foreign>& F = foreign_of[b];
+                std::vector<Foreign> F;
                 for (int sl = 0; sl < ns; sl++) {
                     const int f = face_of_slot(b, sl);
                     const int64_t cl[2] = {fl[f], fr[f]};
@@ -847,40 +860,45 @@ int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd_ref, con
                 std::sort(F.begin(), F.end(), [](const Foreign& x, const Foreign& y) {
                     return x.a != y.a ? x.a < y.a : x.a_stage != y.a_stage ? x.a_stage < y.a_stage : x.slot < y.slot;
                 });
-                for (size_t q = 0; q < F.size(); q++)
-                    (F[q].right ? ridx : lidx)[(size_t)capp * b + F[q].slot] = n_stage[b] + (int)q;
-            }
-            if (bad_sides) { ibis_b200_destroy(c); return fail(nullptr, IBIS_B200_EINVAL, "inconsistent tile tables"); }
-            std::vector<int> pinfo((size_t)2 * std::max(n_tiles, 1), 0);
-            int64_t ptotal = 0;
-            int p_cap = 4;
-            for (int b = 0; b < n_tiles; b++) {
-                const int np = n_stage[b] + (int)foreign_of[b].size();
-                if (ptotal + np >= ((int64_t)1 << 31)) { ibis_b200_destroy(c); return fail(nullptr, IBIS_B200_EINVAL, "too many side records for 32-bit ids"); }
-                pinfo[2 * b] = (int)ptotal;
-                pinfo[2 * b + 1] = np;
-                ptotal += np;
-                p_cap = std::max(p_cap, np);
-            }
-            c->p_total = ptotal;
-            g.p_cap = p_cap;
-            if (p_cap >= 0xFFFF) { ibis_b200_destroy(c); return fail(nullptr, IBIS_B200_EINVAL, "tile has too many side records"); }
-            std::vector<std::vector<Push>> pushes(nt);
-            for (int b = 0; b < n_tiles; b++) pushes[b].push_back({0, n_stage[b], pinfo[2 * b]});          // the staging image itself
-            for (int b = 0; b < n_tiles; b++) {
-                const std::vector<Foreign>& F = foreign_of[b];
+                // runs of consecutive records of one neighbour, widened to even boundaries
+                int image = n_stage[b];
                 for (size_t q = 0; q < F.size();) {
                     size_t e = q + 1;
                     while (e < F.size() && F[e].a == F[q].a && F[e].a_stage == F[q].a_stage + (int)(e - q)) e++;
-                    pushes[F[q].a].push_back({F[q].a_stage, (int)(e - q), pinfo[2 * b] + n_stage[b] + (int)q});
+                    const int s0 = F[q].a_stage / SIDE_EVEN * SIDE_EVEN;
+                    const int s1 = (int)pad_to(F[q].a_stage + (int)(e - q), SIDE_EVEN);      // <= n_stage[a], which is even
+                    pulls[b].push_back({pinfo[2 * F[q].a] + s0, s1 - s0, image});
+                    for (size_t k = q; k < e; k++)
+                        (F[k].right ? ridx : lidx)[(size_t)capp * b + F[k].slot] = image + (F[k].a_stage - s0);
+                    image += s1 - s0;
                     q = e;
                 }
+                n_image[b] = image;
             }
-            std::vector<std::vector<Foreign>>().swap(foreign_of);
-            int push_cap = 1;
-            for (int b = 0; b < nt; b++) push_cap = std::max<int>(push_cap, (int)pushes[b].size());
-            g.push_cap = push_cap;
-            g.grec_stride = (int)pad_to(grec_bytes(NFr, T, halo_cap, push_cap), 128);
+            if (bad_sides) { ibis_b200_destroy(c); return fail(nullptr, IBIS_B200_EINVAL, "inconsistent tile tables"); }
+            int p_cap = 4, pull_cap = 1;
+            for (int b = 0; b < n_tiles; b++) {
+                p_cap = std::max(p_cap, n_image[b]);
+                pull_cap = std::max<int>(pull_cap, (int)pulls[b].size());
+            }
+            g.p_cap = p_cap;
+            if (p_cap >= 0xFFFF) { ibis_b200_destroy(c); return fail(nullptr, IBIS_B200_EINVAL, "tile has too many side records"); }
+            // a loader lane issues one run: tiles that need more than a warp's worth keep to the gather path
+            if (pull_cap > 30) c->use_sides = false;
+            g.pull_cap = pull_cap;
+            g.pull_stride = 8 + 3 * pull_cap;
+            std::vector<int> tpull((size_t)g.pull_stride * std::max(n_tiles, 1), 0);
+            for (int b = 0; b < n_tiles; b++) {
+                int* r = &tpull[(size_t)g.pull_stride * b];
+                r[0] = pinfo[2 * b]; r[1] = pinfo[2 * b + 1];
+                r[2] = (home0[b + 1] - home0[b]) + (foreign_off[b + 1] - foreign_off[b]);
+                r[3] = (int)pulls[b].size(); r[4] = n_image[b];
+                for (size_t k = 0; k < pulls[b].size(); k++) {
+                    r[8 + 3 * k] = pulls[b][k].src; r[9 + 3 * k] = pulls[b][k].count; r[10 + 3 * k] = pulls[b][k].dst;
+                }
+            }
+            std::vector<std::vector<Pull>>().swap(pulls);
+            g.grec_stride = (int)pad_to(grec_bytes(NFr, T, halo_cap), 128);
             g.freca_stride = (int)pad_to(freca_bytes(capp), 128);
             g.frec_stride = (int)pad_to(frec_bytes(T), 128);
             std::vector<unsigned char> grec((size_t)g.grec_stride * std::max(nt, 1), 0);
@@ -890,8 +908,7 @@ int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd_ref, con
                 unsigned short* nbr = reinterpret_cast<unsigned short*>(rec);
                 unsigned short* stg = nbr + (size_t)NFr * T;
                 int* hdr = reinterpret_cast<int*>(stg + (size_t)NFr * T);
-                int* pu = hdr + 8;
-                int* hl = pu + 3 * (size_t)push_cap;
+                int* hl = hdr + 8;
                 int has_ghost = 0;
                 const int64_t c0 = TL.c0[b], c1 = TL.c0[b + 1];
                 const std::vector<int>& h = halos[b];
@@ -912,16 +929,12 @@ int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd_ref, con
                         nbr[(size_t)j * T + i] = e;
                         stg[(size_t)j * T + i] = st;
                     }
-                hdr[0] = (int)h.size(); hdr[1] = TL.nR[b]; hdr[2] = TL.n_own_left(b); hdr[3] = (int)pushes[b].size();
-                hdr[4] = has_ghost; hdr[5] = hdr[6] = hdr[7] = 0;
-                for (size_t k = 0; k < pushes[b].size(); k++) {
-                    pu[3 * k] = pushes[b][k].src; pu[3 * k + 1] = pushes[b][k].count; pu[3 * k + 2] = pushes[b][k].dst;
-                }
+                hdr[0] = (int)h.size(); hdr[1] = TL.nR[b]; hdr[2] = TL.n_own_left(b); hdr[3] = n_stage[b];
+                hdr[4] = has_ghost; hdr[5] = pinfo[2 * b]; hdr[6] = hdr[7] = 0;
                 for (size_t k = 0; k < h.size(); k++) hl[k] = h[k];
                 for (int k = (int)h.size(); k < halo_cap; k++) hl[k] = h.empty() ? (int)c0 : h[0];   // padding: any valid cell
             }
             std::vector<std::vector<int>>().swap(halos);
-            std::vector<std::vector<Push>>().swap(pushes);
             std::vector<unsigned char> freca((size_t)g.freca_stride * std::max(n_tiles, 1), 0);
             std::vector<unsigned char> frec((size_t)g.frec_stride * std::max(n_tiles, 1), 0);
 #pragma omp parallel for schedule(static)
@@ -973,16 +986,19 @@ int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd_ref, con
             rc = upload_vec(c, pinfo, &di);
             if (rc) { ibis_b200_destroy(c); return fail(nullptr, rc, "grid upload failed"); }
             g.t_pinfo = di;
+            rc = upload_vec(c, tpull, &di);
+            if (rc) { ibis_b200_destroy(c); return fail(nullptr, rc, "grid upload failed"); }
+            g.t_pull = di;
           }
         }
 #undef UP2
     }
     timer.lap("tile tables + upload");
     if (timer.on)
-        fprintf(stderr, "[ibis_b200 create] tile %d, tiles %d (+%d halo ring), slots/tile <= %d, staged sides/tile <= %d, side records/tile <= %d "
-                        "(%lld in all), halo list <= %d, pushes/tile <= %d, records %d + %d + %d B/tile\n", c->g.tile, c->g.n_tiles,
+        fprintf(stderr, "[ibis_b200 create] tile %d, tiles %d (+%d halo ring), slots/tile <= %d, staged sides/tile <= %d, image records/tile <= %d "
+                        "(%lld stored in all), halo list <= %d, pulled runs/tile <= %d, records %d + %d + %d B/tile\n", c->g.tile, c->g.n_tiles,
                 c->g.n_tiles_all - c->g.n_tiles, c->g.tile_cap, c->g.stage_cap, c->g.p_cap, (long long)c->p_total, c->g.halo_cap,
-                c->g.push_cap, c->g.grec_stride, c->g.freca_stride, c->g.frec_stride);
+                c->g.pull_cap, c->g.grec_stride, c->g.freca_stride, c->g.frec_stride);
     // WLS r-factors on the device (GridBlock::allocate_gradient_weights, grid.h:499-503)
     double* r = nullptr;
     rc = dev_alloc_zero<double>(c, 6 * cs, &r);

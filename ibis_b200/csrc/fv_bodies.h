@@ -113,16 +113,22 @@ struct GridDev {
     //   t_grec   [tile], grec_stride bytes: u16 nbr[pipe_nf][tile] (tile-local index of the neighbour: < tile an own
     //            cell, >= tile entry (index - tile) of the halo list; bit 14: this cell is the LEFT cell of the
     //            interface, bit 15: the neighbour is a boundary ghost; an absent slot points at the cell itself) |
-    //            u16 stage[pipe_nf][tile] (cf_stage) | int hdr[8] = {n_halo, nR, n_own_l, n_push, has_ghost, -, -, -} |
-    //            int push[push_cap][3] = {first staged record, count, destination record in the side-state array}:
-    //            where the records pass G' has staged for the tile go (the whole staging image into the tile's own
-    //            array, then the runs a neighbouring tile needs into THAT tile's array) |
+    //            u16 stage[pipe_nf][tile] (cf_stage) |
+    //            int hdr[8] = {n_halo, nR, n_own_l, n_stage, has_ghost, home, -, -} (n_stage: records of the tile's
+    //            staging image, an even number; home: first record of the tile's side-state array) |
     //            int halo[halo_cap] (cell ids of the neighbours outside the tile, no duplicates)
-    //   side-state array of owned tile b: records [t_pinfo[2b], + t_pinfo[2b+1]) of FvArgs::sidesP, 6 S each:
-    //            first the tile's own staging image (its cells' sides in the staging order of layout.h, the ghost
-    //            sides of its boundary interfaces included), then the sides its neighbours push
+    //   side-state array of tile b (halo-ring tiles included): records [t_pinfo[2b], + t_pinfo[2b+1]) of
+    //            FvArgs::sidesP, SIDE_REC S each: the tile's staging image (its cells' sides in the staging order of
+    //            layout.h, the ghost sides of its boundary interfaces included).  Pass G' writes it with ONE bulk
+    //            store; every side is stored once.
+    //   t_pull   [owned tile], pull_stride ints: {home, n_home, n_slots, n_pull, n_image, -, -, -} |
+    //            int pull[pull_cap][3] = {first record in FvArgs::sidesP, count, first record in the tile's image}:
+    //            the image of the tile's interface sides pass F' assembles in shared memory = its own array, then
+    //            the runs of the neighbouring tiles' arrays that hold the far sides of its surface interfaces
+    //            (first records and counts are even: 16-byte granularity of the bulk copies at 40 bytes a record;
+    //            a run may therefore carry one record more at either end than the tile needs)
     //   t_freca  [owned tile], freca_stride bytes: u16 lidx[tile_cap] | u16 ridx[tile_cap] (record, in the tile's
-    //            side-state array, of the left / right state of the interface in flux slot s) |
+    //            image, of the left / right state of the interface in flux slot s) |
     //            double frame[tile_cap][6] (t1 t2 of that interface: the normal is cross(t1, t2) as in the reference,
     //            grid/interface.h:250, util/vector3.h:153-160, recomputed bit for bit in the kernels)
     //   t_frec   [owned tile], frec_stride bytes: double vol[tile] | double sarea[6][tile] (-area * outsign, 0 for an
@@ -132,7 +138,8 @@ struct GridDev {
     const unsigned char* t_freca;
     const unsigned char* t_frec;
     const int* t_pinfo;
-    int grec_stride, freca_stride, frec_stride, halo_cap, push_cap, p_cap, pipe_nf;
+    const int* t_pull;
+    int grec_stride, freca_stride, frec_stride, halo_cap, pull_cap, pull_stride, p_cap, pipe_nf;
     // NOTE cf_slot, cf_out and cf_d are always MAXF slots wide (absent slots: 0xFFFF / 0 / 0) so
     // that the tiled kernel can load all slots unconditionally; cf_face, cf_nbr, cf_w are
     // max_faces wide.
@@ -163,7 +170,7 @@ struct FvArgs {
     S* grad;           // [(var*3 + comp)*cstride + cell]
     S* lim;            // [var*cstride + cell]
     S* flux;           // general path: [comp*fstride + face]
-    S* sidesP;         // sides path: the per-tile side-state arrays (GridDev::t_pinfo), 6 S per record: rho p T vx vy vz
+    S* sidesP;         // sides path: the per-tile side-state arrays (GridDev::t_pinfo), SIDE_REC S per record
     // sides path: when not null, pass F' also takes the minimum over the owned cells of the local
     // time step (estimate_dt fused into the first evaluation of a Runge-Kutta step): the bit
     // pattern of a positive double orders like the double, so the reduction is an integer atomicMin
@@ -1275,32 +1282,35 @@ constexpr int NBR_LOCAL_MASK = 0x3FFF, NBR_LEFT_BIT = 0x4000, NBR_GHOST_BIT = 0x
 struct GRec {
     const unsigned short* nbr;     // [nf][T]
     const unsigned short* stage;   // [nf][T]
-    const int* hdr;                // n_halo, nR, n_own_l, n_push, has_ghost (a cell of the tile has a boundary ghost neighbour)
-    const int* push;               // [push_cap][3]
+    const int* hdr;                // n_halo, nR, n_own_l, n_stage, has_ghost (a cell of the tile has a boundary ghost neighbour), home
     const int* halo;               // [halo_cap]
 };
-IBIS_HD GRec grec_view(const unsigned char* rec, int nf, int T, int push_cap) {
+IBIS_HD GRec grec_view(const unsigned char* rec, int nf, int T) {
     GRec R;
     R.nbr = reinterpret_cast<const unsigned short*>(rec);
     R.stage = R.nbr + (size_t)nf * T;
     R.hdr = reinterpret_cast<const int*>(R.stage + (size_t)nf * T);
-    R.push = R.hdr + 8;
-    R.halo = R.push + 3 * (size_t)push_cap;
+    R.halo = R.hdr + 8;
     return R;
 }
-IBIS_HD int grec_bytes(int nf, int T, int halo_cap, int push_cap) { return 4 * nf * T + 32 + 12 * push_cap + 4 * halo_cap; }
+IBIS_HD int grec_bytes(int nf, int T, int halo_cap) { return 4 * nf * T + 32 + 4 * halo_cap; }
 
-// the thermodynamic pair (rho, second variable) extrapolated to one interface -> rho p T of the side record
+// A side record = what linear_reconstruct extrapolates to one side of an interface (convective_flux.cpp:243-420):
+// rho, the second thermodynamic variable of the interpolator (p, T or u), vx, vy, vz.  40 bytes; the thermodynamic
+// closure (gas_model.h:91-117) is evaluated by the consumer, pass F', from the same two values with the same calls.
+constexpr int SIDE_REC = 5;
+constexpr int SIDE_EVEN = 2;       // first records and counts of bulk transfers are multiples of this
+// the thermodynamic pair (rho, second variable) of a side record -> rho p T of the side
 template <typename S>
-IBIS_HD void side_close_store(int thermo, const Gas<S>& gas, S rho, const S& th2, S* q) {
-    S p = S(0.0), Tj = S(0.0), e = S(0.0);
+IBIS_HD void side_close(int thermo, const Gas<S>& gas, const S& rho_in, const S& th2, S& rho, S& p, S& Tj) {
+    rho = rho_in;
+    p = S(0.0);
+    Tj = S(0.0);
+    S e = S(0.0);
     if (thermo == THERMO_RHO_P) p = th2;
     else if (thermo == THERMO_RHO_T) Tj = th2;
     else e = th2;
     thermo_close(thermo, gas, rho, p, Tj, e);
-    q[0] = rho;
-    q[1] = p;
-    q[2] = Tj;
 }
 // staging index of the far side of a boundary interface (the ghost cell's own values): the far side
 // sits at a fixed distance from the near side in the tile's staging buffer (layout.h)
@@ -1348,19 +1358,15 @@ IBIS_HD void pipe_grad_cell(const FvArgs<S>& A, const double* wd, const GRec& R,
 #pragma unroll
     for (int j = 0; j < NF; j++) {
         if (st[j] == 0xFFFF) continue;
-        S* q = stg + (long)st[j] * 6;
-        side_close_store(A.thermo, A.gas, r[0][j], r[1][j], q);
-        q[3] = r[2][j];
-        q[4] = r[3][j];
-        q[5] = r[4][j];
+        S* q = stg + (long)st[j] * SIDE_REC;
+#pragma unroll
+        for (int v = 0; v < 5; v++) q[v] = r[v][j];
         if (ghost[j]) {
             // the far side of a boundary interface is the ghost cell itself: zero gradient, unit limiter
             // (convective_flux.cpp:281-300), i.e. its values, closed thermodynamically like any other side
-            S* f = stg + (long)far_stage_index(left[j], st[j], nR, n_own_l) * 6;
-            side_close_store(A.thermo, A.gas, sv[0 * svs + nl[j]], sv[1 * svs + nl[j]], f);
-            f[3] = sv[2 * svs + nl[j]];
-            f[4] = sv[3 * svs + nl[j]];
-            f[5] = sv[4 * svs + nl[j]];
+            S* f = stg + (long)far_stage_index(left[j], st[j], nR, n_own_l) * SIDE_REC;
+#pragma unroll
+            for (int v = 0; v < 5; v++) f[v] = sv[v * svs + nl[j]];
         }
     }
 }
@@ -1426,14 +1432,14 @@ struct FluxOperands {
     double t1x, t1y, t1z, t2x, t2y, t2z;
 };
 template <typename S>
-IBIS_HD void flux_load_operands(const S* Ls, const S* Rs, const double* fr, FluxOperands<S>& O) {
+IBIS_HD void flux_load_operands(const FvArgs<S>& A, const S* Ls, const S* Rs, const double* fr, FluxOperands<S>& O) {
     typedef mem<S> M;
-    M::ld2(Ls, 0, O.L.rho, O.L.p);
-    M::ld2(Ls, 2, O.L.T, O.L.u);
-    M::ld2(Ls, 4, O.L.v, O.L.w);
-    M::ld2(Rs, 0, O.R.rho, O.R.p);
-    M::ld2(Rs, 2, O.R.T, O.R.u);
-    M::ld2(Rs, 4, O.R.v, O.R.w);
+    // 40-byte records: 8-byte alignment only
+    const S la = M::load(Ls, 0), lb = M::load(Ls, 1), ra = M::load(Rs, 0), rb = M::load(Rs, 1);
+    O.L.u = M::load(Ls, 2); O.L.v = M::load(Ls, 3); O.L.w = M::load(Ls, 4);
+    O.R.u = M::load(Rs, 2); O.R.v = M::load(Rs, 3); O.R.w = M::load(Rs, 4);
+    side_close(A.thermo, A.gas, la, lb, O.L.rho, O.L.p, O.L.T);
+    side_close(A.thermo, A.gas, ra, rb, O.R.rho, O.R.p, O.R.T);
     O.L.e = S(0.0);
     O.R.e = S(0.0);
     mem<double>::ld2(fr, 0, O.t1x, O.t1y);
@@ -1469,9 +1475,9 @@ IBIS_HD void flux_from_operands(const FvArgs<S>& A, const FluxOperands<S>& O, S*
     out[4] = F.energy;
 }
 template <int DIM, int FLUX, typename S>
-IBIS_HD void flux_from_sides6(const FvArgs<S>& A, const S* Ls, const S* Rs, const double* fr, S* out) {
+IBIS_HD void flux_from_sides(const FvArgs<S>& A, const S* Ls, const S* Rs, const double* fr, S* out) {
     FluxOperands<S> O;
-    flux_load_operands(Ls, Rs, fr, O);
+    flux_load_operands(A, Ls, Rs, fr, O);
     flux_from_operands<DIM, FLUX>(A, O, out);
 }
 

@@ -188,7 +188,7 @@ void launch_pack_pipe_tables(ibis_b200_ctx* c, double* t_wd) {
 // whole time a tile is being worked on.
 template <typename S>
 __host__ __device__ inline size_t flux_in_bytes(int p_cap, int freca_stride) {
-    return ((size_t)p_cap * 6 * sizeof(S) + 127) / 128 * 128 + (size_t)freca_stride;
+    return ((size_t)p_cap * SIDE_REC * sizeof(S) + 127) / 128 * 128 + (size_t)freca_stride;
 }
 template <typename S>
 __host__ __device__ inline size_t flux_fb_bytes(int cap, int frec_stride, int T, bool with_dt) {
@@ -237,27 +237,30 @@ __global__ void __launch_bounds__(32 * (IBIS_PIPE_F_WARPS + IBIS_PIPE_F_LOADERS)
     __syncthreads();
     const int n_my = (int)blockIdx.x < g.n_tiles ? (g.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     if (warp >= ncw) {
-        // ---- loaders: loader w takes the block's tiles w, w + NL, ...  Per tile three bulk copies (side-state
-        // array, interface record, cell record; + 4 rows with the fused dt), issued by lane 0, and the same ranges of a
-        // later tile of its own as L2 prefetches ----
-        if (lane != 0) return;
+        // ---- loaders: loader w takes the block's tiles w, w + NL, ...  Per tile: the tile's own side-state array,
+        // its interface record and its cell record (+ 4 rows with the fused dt) as bulk copies issued by lane 0, and
+        // the runs of the neighbouring tiles' arrays that complete the image of the tile's interface sides, one
+        // per lane from lane 1 on (GridDev::t_pull); the same ranges of a later tile of its own as L2 prefetches ----
         const int step = (int)gridDim.x, w = warp - ncw;
         constexpr int NL = IBIS_PIPE_F_LOADERS;
         const int PF = (pf + NL - 1) / NL * NL;
-        // {first record, record count} of the tile's side-state array and its slot count, fetched one tile ahead
-        int pi0 = 0, pi1 = 0, pi2 = 0;
-        if (w < n_my) {
-            const size_t t = (size_t)blockIdx.x + (size_t)w * step;
-            pi0 = __ldg(g.t_pinfo + 2 * t);
-            pi1 = __ldg(g.t_pinfo + 2 * t + 1);
-            pi2 = __ldg(g.tile_info + (size_t)TILE_INFO * t + 9);
-        }
+        // header {home, n_home, n_slots, n_pull, n_image} of the tile and this lane's run, fetched one tile ahead
+        int h0 = 0, h1 = 0, h2 = 0, h3 = 0, h4 = 0, ps = 0, pc = 0, pd = 0;
+        auto fetch_pull = [&](size_t t, int& a0, int& a1, int& a2, int& a3, int& a4, int& b0, int& b1, int& b2) {
+            const int* r = g.t_pull + t * (size_t)g.pull_stride;
+            a0 = __ldg(r); a1 = __ldg(r + 1); a2 = __ldg(r + 2); a3 = __ldg(r + 3); a4 = __ldg(r + 4);
+            b0 = b1 = b2 = 0;
+            if (lane >= 1 && lane <= g.pull_cap) {
+                b0 = __ldg(r + 8 + 3 * (lane - 1)); b1 = __ldg(r + 9 + 3 * (lane - 1)); b2 = __ldg(r + 10 + 3 * (lane - 1));
+            }
+        };
+        if (w < n_my) fetch_pull((size_t)blockIdx.x + (size_t)w * step, h0, h1, h2, h3, h4, ps, pc, pd);
         for (int k = w; k < n_my; k += NL) {
             const int t = (int)blockIdx.x + k * step, s = k % nsi, o = k % nfb;
-            if (PF > 0 && k + PF < n_my) {                    // L2 prefetch of a later tile of this loader
+            if (PF > 0 && k + PF < n_my && lane == 0) {       // L2 prefetch of a later tile of this loader
                 const size_t tp = (size_t)t + (size_t)PF * step;
                 const int q0 = __ldg(g.t_pinfo + 2 * tp), q1 = __ldg(g.t_pinfo + 2 * tp + 1);
-                ac::bulk_prefetch_l2(A.sidesP + (size_t)q0 * 6, (uint32_t)q1 * 6u * (uint32_t)sizeof(S));
+                ac::bulk_prefetch_l2(A.sidesP + (size_t)q0 * SIDE_REC, (uint32_t)q1 * (uint32_t)SIDE_REC * (uint32_t)sizeof(S));
                 ac::bulk_prefetch_l2(g.t_freca + tp * g.freca_stride, (uint32_t)g.freca_stride);
                 ac::bulk_prefetch_l2(g.t_frec + tp * g.frec_stride, (uint32_t)g.frec_stride);
                 if (with_dt) {
@@ -266,39 +269,37 @@ __global__ void __launch_bounds__(32 * (IBIS_PIPE_F_WARPS + IBIS_PIPE_F_LOADERS)
                     for (int v = 0; v < 4; v++) ac::bulk_prefetch_l2(A.fs[v < 3 ? F_VX + v : F_T] + c0p, (uint32_t)T * (uint32_t)sizeof(S));
                 }
             }
-            int nx0 = 0, nx1 = 0, nx2 = 0;                    // this loader's next tile, in flight during the waits
-            if (k + NL < n_my) {
-                const size_t tn = (size_t)t + (size_t)NL * step;
-                nx0 = __ldg(g.t_pinfo + 2 * tn);
-                nx1 = __ldg(g.t_pinfo + 2 * tn + 1);
-                nx2 = __ldg(g.tile_info + (size_t)TILE_INFO * tn + 9);
-            }
-            if (k >= nsi && !pipe_spin_ge_1(&stage_free[s], k - nsi, A.pipe_dbg, PW_EMPTY, k)) return;
-            if (k >= nfb && !pipe_spin_ge_1(&fb_done[o], k - nfb, A.pipe_dbg, PW_OUT, k)) return;
+            int n0 = 0, n1 = 0, n2 = 0, n3 = 0, n4 = 0, ns_ = 0, nc_ = 0, nd_ = 0;   // this loader's next tile, in flight during the waits
+            if (k + NL < n_my) fetch_pull((size_t)t + (size_t)NL * step, n0, n1, n2, n3, n4, ns_, nc_, nd_);
+            if (k >= nsi && !pipe_spin_ge(&stage_free[s], k - nsi, A.pipe_dbg, PW_EMPTY, k)) return;
+            if (k >= nfb && !pipe_spin_ge(&fb_done[o], k - nfb, A.pipe_dbg, PW_OUT, k)) return;
             int c0, nc;
             tile_cells(g, t, c0, nc);
             unsigned char* st = smem + (unsigned)s * in_bytes;
             unsigned char* fb = fb_base + (unsigned)o * fb_bytes;
-            n_slots_of[s] = pi2;
-            meta[o][0] = nc;
-            meta[o][1] = c0;
-            meta[o][2] = t;
-            __threadfence_block();
-            *reinterpret_cast<volatile int*>(&fb_tile[o]) = k;
-            *reinterpret_cast<volatile int*>(&stage_tile[s]) = k;
-            const uint32_t pbytes = (uint32_t)pi1 * 6u * (uint32_t)sizeof(S);
-            ac::mbar_arrive_expect_tx(&full_in[s], pbytes + (uint32_t)g.freca_stride);
-            ac::mbar_arrive_expect_tx(&rec_full[o], (uint32_t)g.frec_stride + (with_dt ? 4u * (uint32_t)T * (uint32_t)sizeof(S) : 0u));
-            ac::bulk_g2s(st, A.sidesP + (size_t)pi0 * 6, pbytes, &full_in[s]);
-            ac::bulk_g2s(st + offA, g.t_freca + (size_t)t * g.freca_stride, (uint32_t)g.freca_stride, &full_in[s]);
-            ac::bulk_g2s(fb + offRec, g.t_frec + (size_t)t * g.frec_stride, (uint32_t)g.frec_stride, &rec_full[o]);
-            if (with_dt)
-                for (int v = 0; v < 4; v++)
-                    ac::bulk_g2s(fb + offDt + (unsigned)v * (unsigned)T * (unsigned)sizeof(S), A.fs[v < 3 ? F_VX + v : F_T] + c0,
-                                 (uint32_t)T * (uint32_t)sizeof(S), &rec_full[o]);
-            pi0 = nx0;
-            pi1 = nx1;
-            pi2 = nx2;
+            constexpr uint32_t RB = (uint32_t)SIDE_REC * (uint32_t)sizeof(S);
+            if (lane == 0) {
+                n_slots_of[s] = h2;
+                meta[o][0] = nc;
+                meta[o][1] = c0;
+                meta[o][2] = t;
+                __threadfence_block();
+                *reinterpret_cast<volatile int*>(&fb_tile[o]) = k;
+                *reinterpret_cast<volatile int*>(&stage_tile[s]) = k;
+                ac::mbar_arrive_expect_tx(&full_in[s], (uint32_t)h4 * RB + (uint32_t)g.freca_stride);
+                ac::mbar_arrive_expect_tx(&rec_full[o], (uint32_t)g.frec_stride + (with_dt ? 4u * (uint32_t)T * (uint32_t)sizeof(S) : 0u));
+                ac::bulk_g2s(st, A.sidesP + (size_t)h0 * SIDE_REC, (uint32_t)h1 * RB, &full_in[s]);
+                ac::bulk_g2s(st + offA, g.t_freca + (size_t)t * g.freca_stride, (uint32_t)g.freca_stride, &full_in[s]);
+                ac::bulk_g2s(fb + offRec, g.t_frec + (size_t)t * g.frec_stride, (uint32_t)g.frec_stride, &rec_full[o]);
+                if (with_dt)
+                    for (int v = 0; v < 4; v++)
+                        ac::bulk_g2s(fb + offDt + (unsigned)v * (unsigned)T * (unsigned)sizeof(S), A.fs[v < 3 ? F_VX + v : F_T] + c0,
+                                     (uint32_t)T * (uint32_t)sizeof(S), &rec_full[o]);
+            }
+            __syncwarp();                                     // the runs follow the barrier's expect_tx
+            if (lane >= 1 && lane <= h3)
+                ac::bulk_g2s(st + (size_t)pd * RB, A.sidesP + (size_t)ps * SIDE_REC, (uint32_t)pc * RB, &full_in[s]);
+            h0 = n0; h1 = n1; h2 = n2; h3 = n3; h4 = n4; ps = ns_; pc = nc_; pd = nd_;
         }
         return;
     }
@@ -333,7 +334,7 @@ __global__ void __launch_bounds__(32 * (IBIS_PIPE_F_WARPS + IBIS_PIPE_F_LOADERS)
                 const int slot = r * (32 * IBIS_PIPE_F_ROUNDS) + rr * 32 + lane;
                 const bool active = slot < n_slots;
                 FluxOperands<S> O;
-                if (active) flux_load_operands(Pt + (long)Ra.lidx[slot] * 6, Pt + (long)Ra.ridx[slot] * 6, Ra.frame + (long)slot * 6, O);
+                if (active) flux_load_operands(A, Pt + (long)Ra.lidx[slot] * SIDE_REC, Pt + (long)Ra.ridx[slot] * SIDE_REC, Ra.frame + (long)slot * 6, O);
                 if (rr == IBIS_PIPE_F_ROUNDS - 1) {
                     // once every item of the tile has its operands the stage is the loader's again
                     __syncwarp();
@@ -413,15 +414,16 @@ __host__ __device__ inline size_t grad_stage_bytes(int nf, int T, int grec_strid
     size_t b = (size_t)2 * nf * 3 * T * 8 + (size_t)grec_stride + (size_t)5 * (T + halo_cap) * sizeof(S);
     return (b + 127) / 128 * 128;
 }
-// staging buffer = [side records stage_cap x 6 S | the tile's push list: int n_push, pad x 3, push[push_cap][3]]
+// staging buffer = [side records stage_cap x SIDE_REC S | int home, n_stage: where the image goes (first record of the
+// tile's side-state array, record count)]
 template <typename S>
-__host__ __device__ inline size_t grad_out_bytes(int stage_cap, int push_cap) {
-    return ((size_t)stage_cap * 6 * sizeof(S) + 16 + (size_t)12 * push_cap + 127) / 128 * 128;
+__host__ __device__ inline size_t grad_out_bytes(int stage_cap) {
+    return ((size_t)stage_cap * SIDE_REC * sizeof(S) + 16 + 127) / 128 * 128;
 }
 
 // One work item of pass G', one cell per lane:
-//   items [0, T / 32):  32 cells x (rho, then the second thermodynamic variable), and the thermodynamic closure
-//                       (gas_model.h:91-117) of every face -> rho p T of the cell's side records;
+//   items [0, T / 32):  32 cells x (rho, then the second thermodynamic variable) -> the first two places of the
+//                       cell's side records (pass F' closes them thermodynamically, gas_model.h:91-117);
 //   the others:         all T cells (T / 32 rounds of 32) x one velocity component -> vx | vy | vz of the records.
 // Items are of about the same size (two gradient + limiter + extrapolation passes each at T = 64).  ONE loop body
 // serves every pass of both kinds -- a single instance of var_to_faces in the kernel: with twenty warps at different
@@ -458,53 +460,33 @@ __device__ __forceinline__ void grad_item(const FvArgs<S>& A, const double* wd, 
 #pragma unroll
         for (int j = 0; j < NF; j++) un[j] = row[fl[j] & NBR_LOCAL_MASK];
         var_to_faces<DIM, NF>(ui, un, Tb, A.eps, limit, r);
-        if (thermo) {
-            // rho (pass 0) and the second variable (pass 1) are parked in the first two places of the side records;
-            // after pass 1 ONE loop over the faces (not unrolled: a single instance of the closure in the kernel)
-            // closes every record in place
+        // the far side of a boundary interface is the ghost cell itself: zero gradient, unit limiter
+        // (convective_flux.cpp:281-300), i.e. its values
+        const int slot_v = thermo ? pass : 2 + v;             // place of this variable in the side records
 #pragma unroll
-            for (int j = 0; j < NF; j++)
-                if (st[j] != 0xFFFF) stg[(long)st[j] * 6 + pass] = r[j];
-            if (pass == 1) {
-#pragma unroll 1
-                for (int j = 0; j < NF; j++) {
-                    const int e = R.nbr[j * T + i], sj = R.stage[j * T + i];
-                    if (sj == 0xFFFF) continue;
-                    S* q = stg + (long)sj * 6;
-                    side_close_store(A.thermo, A.gas, q[0], q[1], q);
-                    // the far side of a boundary interface is the ghost cell itself: zero gradient, unit limiter
-                    // (convective_flux.cpp:281-300), i.e. its values, closed thermodynamically like any other side
-                    if (ghosts && (e & NBR_GHOST_BIT))
-                        side_close_store(A.thermo, A.gas, sv[e & NBR_LOCAL_MASK], sv[svs + (e & NBR_LOCAL_MASK)],
-                                         stg + (long)far_stage_index((e & NBR_LEFT_BIT) != 0, sj, nR, n_own_l) * 6);
-                }
-            }
-        } else {
+        for (int j = 0; j < NF; j++) {
+            if (st[j] == 0xFFFF) continue;
+            stg[(long)st[j] * SIDE_REC + slot_v] = r[j];
+            if (ghosts && (fl[j] & NBR_GHOST_BIT))
+                stg[(long)far_stage_index((fl[j] & NBR_LEFT_BIT) != 0, st[j], nR, n_own_l) * SIDE_REC + slot_v] = un[j];
+        }
+        if (DIM == 2 && !thermo && v == 1) {
+            // 2-D: vz has no gradient (convective_flux.cpp:206-208) and a unit limiter: the value is copied
+            const S* rz = sv + (size_t)4 * svs;
 #pragma unroll
             for (int j = 0; j < NF; j++) {
                 if (st[j] == 0xFFFF) continue;
-                stg[(long)st[j] * 6 + 3 + v] = r[j];
+                stg[(long)st[j] * SIDE_REC + 4] = rz[i];
                 if (ghosts && (fl[j] & NBR_GHOST_BIT))
-                    stg[(long)far_stage_index((fl[j] & NBR_LEFT_BIT) != 0, st[j], nR, n_own_l) * 6 + 3 + v] = un[j];
-            }
-            if (DIM == 2 && v == 1) {
-                // 2-D: vz has no gradient (convective_flux.cpp:206-208) and a unit limiter: the value is copied
-                const S* rz = sv + (size_t)4 * svs;
-#pragma unroll
-                for (int j = 0; j < NF; j++) {
-                    if (st[j] == 0xFFFF) continue;
-                    stg[(long)st[j] * 6 + 5] = rz[i];
-                    if (ghosts && (fl[j] & NBR_GHOST_BIT))
-                        stg[(long)far_stage_index((fl[j] & NBR_LEFT_BIT) != 0, st[j], nR, n_own_l) * 6 + 5] = rz[fl[j] & NBR_LOCAL_MASK];
-                }
+                    stg[(long)far_stage_index((fl[j] & NBR_LEFT_BIT) != 0, st[j], nR, n_own_l) * SIDE_REC + 4] = rz[fl[j] & NBR_LOCAL_MASK];
             }
         }
     }
 }
 
 // Work items of a block, in queue order: the N_TASKS items of its tiles (grad_item).  The warp that completes a
-// tile's last item hands the input stage back to the loaders and the staging buffer over to the store warp (the push
-// list of the tile's record: bulk stores out of the staging buffer).  Input stages recycle through an mbarrier guarded by stage_tile
+// tile's last item hands the input stage back to the loaders and the staging buffer over to the store warp (one bulk
+// store of the staging image into the tile's side-state array).  Input stages recycle through an mbarrier guarded by stage_tile
 // (see k_flux_pipe), the staging buffers through the monotone counter out_done.
 template <int DIM, int NF, int T, typename S>
 __global__ void __launch_bounds__(32 * (IBIS_PIPE_G_WARPS + IBIS_PIPE_G_LOADERS + 1), 1)
@@ -519,8 +501,8 @@ __global__ void __launch_bounds__(32 * (IBIS_PIPE_G_WARPS + IBIS_PIPE_G_LOADERS 
     const int svs = T + g.halo_cap;
     constexpr int WD_BYTES = 2 * NF * 3 * T * 8;
     const unsigned in_bytes = (unsigned)grad_stage_bytes<S>(NF, T, g.grec_stride, g.halo_cap);
-    const unsigned out_bytes = (unsigned)grad_out_bytes<S>(g.stage_cap, g.push_cap);
-    const unsigned off_push = (unsigned)g.stage_cap * 6u * (unsigned)sizeof(S);   // push list inside a staging buffer
+    const unsigned out_bytes = (unsigned)grad_out_bytes<S>(g.stage_cap);
+    const unsigned off_dst = (unsigned)g.stage_cap * (unsigned)SIDE_REC * (unsigned)sizeof(S);   // {home, n_stage} inside a staging buffer
     unsigned char* out_base = smem + (unsigned)nsi * in_bytes;
     if (threadIdx.x == 0) {
         for (int s = 0; s < nsi; s++) {
@@ -536,26 +518,24 @@ __global__ void __launch_bounds__(32 * (IBIS_PIPE_G_WARPS + IBIS_PIPE_G_LOADERS 
     __syncthreads();
     const int n_my = (int)blockIdx.x < n_list ? (n_list - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     if (warp == ncw + IBIS_PIPE_G_LOADERS) {
-        // ---- the store warp: when a tile's side records are complete in a staging buffer (out_ready) they leave as
-        // the bulk stores of the tile's push list; the buffer is free again (out_done) once the stores have read it ----
+        // ---- the store warp: when a tile's side records are complete in a staging buffer (out_ready) the image leaves
+        // as one bulk store into the tile's side-state array; the buffer is free again (out_done) once the store has
+        // read it ----
         for (int k = 0; k < n_my; k++) {
             const int o = k % nso;
             if (!pipe_spin_ge(&out_ready[o], k, A.pipe_dbg, 16 + PW_DONE, k)) return;
             ac::fence_proxy_async();
             const unsigned char* ob = out_base + (unsigned)o * out_bytes;
             const S* stg = reinterpret_cast<const S*>(ob);
-            const int* pl = reinterpret_cast<const int*>(ob + off_push);
-            const int n_push = pl[0];
-            for (int q = lane; q < n_push; q += 32) {
-                const int src = pl[4 + 3 * q], count = pl[5 + 3 * q], dst = pl[6 + 3 * q];
-                if (count > 0) ac::bulk_s2g(A.sidesP + (size_t)dst * 6, stg + (long)src * 6, (uint32_t)count * 6 * (uint32_t)sizeof(S));
-            }
-            ac::bulk_commit_wait_read();                   // the store warp has nothing else to do than to see them drained
-            __syncwarp();
+            const int* pl = reinterpret_cast<const int*>(ob + off_dst);
             if (lane == 0) {
+                const int home = pl[0], n_stage = pl[1];
+                if (n_stage > 0) ac::bulk_s2g(A.sidesP + (size_t)home * SIDE_REC, stg, (uint32_t)n_stage * (uint32_t)SIDE_REC * (uint32_t)sizeof(S));
+                ac::bulk_commit_wait_read();               // the store warp has nothing else to do than to see it drained
                 __threadfence_block();
                 *reinterpret_cast<volatile int*>(&out_done[o]) = k;
             }
+            __syncwarp();
         }
         return;
     }
@@ -568,7 +548,7 @@ __global__ void __launch_bounds__(32 * (IBIS_PIPE_G_WARPS + IBIS_PIPE_G_LOADERS 
         const int step = (int)gridDim.x, w = warp - ncw;
         constexpr int NL = IBIS_PIPE_G_LOADERS;
         const int PF = (pf + NL - 1) / NL * NL;
-        const int hoff = 4 * NF * T + 32 + 12 * g.push_cap;                   // halo list inside the record
+        const int hoff = 4 * NF * T + 32;                                     // halo list inside the record
         auto tile_at = [&](int k) { const int idx = (int)blockIdx.x + k * step; return tile_list ? __ldg(tile_list + idx) : idx; };
         int ids[PIPE_HALO_REGS], n_halo = 0, ids_n[PIPE_HALO_REGS], n_halo_n = 0;
         auto fetch_ids = [&](int t, int* out, int& nh) {
@@ -645,7 +625,7 @@ __global__ void __launch_bounds__(32 * (IBIS_PIPE_G_WARPS + IBIS_PIPE_G_LOADERS 
         // the staging buffer is free once the stores of the tile nso tiles back have read it
         if (k >= nso && !pipe_spin_ge(&out_done[o], k - nso, A.pipe_dbg, 16 + PW_OUT, k)) return;
         unsigned char* st = smem + (unsigned)s * in_bytes;
-        const GRec R = grec_view(st + WD_BYTES, NF, T, g.push_cap);
+        const GRec R = grec_view(st + WD_BYTES, NF, T);
         S* stg = reinterpret_cast<S*>(out_base + (unsigned)o * out_bytes);
         const double* wd = reinterpret_cast<const double*>(st);
         const S* sv = reinterpret_cast<const S*>(st + WD_BYTES + g.grec_stride);
@@ -659,15 +639,13 @@ __global__ void __launch_bounds__(32 * (IBIS_PIPE_G_WARPS + IBIS_PIPE_G_LOADERS 
         }
         d = __shfl_sync(0xffffffffu, d, 0);
         if (d == N_TASKS - 1) {
-            // the tile's last item: its side records are complete in the staging buffer.  The push list moves next to
-            // them, the input stage goes back to the loaders, and the store warp takes over the buffer
+            // the tile's last item: its side records are complete in the staging buffer.  Their destination moves next
+            // to them, the input stage goes back to the loaders, and the store warp takes over the buffer
             __threadfence_block();
-            int* pl = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(stg) + off_push);
-            const int n_push = R.hdr[3];
-            if (lane == 0) pl[0] = n_push;
-            for (int q = lane; q < 3 * n_push; q += 32) pl[4 + q] = R.push[q];
-            __syncwarp();
             if (lane == 0) {
+                int* pl = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(stg) + off_dst);
+                pl[0] = R.hdr[5];
+                pl[1] = R.hdr[3];
                 done_tasks[s] = 0;
                 __threadfence_block();
                 *reinterpret_cast<volatile int*>(&stage_free[s]) = k;
@@ -692,7 +670,7 @@ static bool set_smem(ibis_b200_ctx* c, K kernel, size_t smem) {
 
 template <int DIM, int NF, int T, typename S>
 static void launch_grad_pipe_t(ibis_b200_ctx* c, const FvArgs<S>& A, const int* list, int n_list) {
-    const size_t in_b = grad_stage_bytes<S>(NF, T, A.g.grec_stride, A.g.halo_cap), out_b = grad_out_bytes<S>(A.g.stage_cap, A.g.push_cap);
+    const size_t in_b = grad_stage_bytes<S>(NF, T, A.g.grec_stride, A.g.halo_cap), out_b = grad_out_bytes<S>(A.g.stage_cap);
     // staging buffers: four when they fit (items + drain of a tile overlap the next tiles'), the rest input stages
     int nso = 4;
     while (nso > 1 && (size_t)nso * out_b + 2 * in_b > PIPE_SMEM_BUDGET) nso--;

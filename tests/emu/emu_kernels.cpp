@@ -141,8 +141,8 @@ void launch_pack_pipe_tables(ibis_b200_ctx* c, double* t_wd) {
 }
 
 // pass G' tile by tile, on the packed per-tile records the device kernel stages: the state of the tile's own
-// cells and of its halo list, every cell's five variables into the staging buffer, then the tile's push list (the
-// bulk stores of the device kernel) as memcpy
+// cells and of its halo list, every cell's five variables into the staging buffer, then the staging image into the
+// tile's side-state array (the bulk store of the device kernel) as memcpy
 template <typename S>
 void launch_grad_sides(ibis_b200_ctx* c, const FvArgs<S>& A, int which) {
     const GridDev& g = A.g;
@@ -151,11 +151,11 @@ void launch_grad_sides(ibis_b200_ctx* c, const FvArgs<S>& A, int which) {
     const int T = g.tile, NF = g.pipe_nf, svs = T + g.halo_cap;
 #pragma omp parallel
     {
-        std::vector<S> stg((size_t)6 * std::max(g.stage_cap, 1)), sv((size_t)5 * svs);
+        std::vector<S> stg((size_t)SIDE_REC * std::max(g.stage_cap, 1)), sv((size_t)5 * svs);
 #pragma omp for
         for (int k = 0; k < n_list; k++) {
             const int t = list ? list[k] : k;
-            const GRec R = grec_view(g.t_grec + (size_t)t * g.grec_stride, NF, T, g.push_cap);
+            const GRec R = grec_view(g.t_grec + (size_t)t * g.grec_stride, NF, T);
             const double* wd = g.t_wd + (size_t)t * 2 * NF * 3 * T;
             int c0, nc;
             tile_cells(g, t, c0, nc);
@@ -174,11 +174,8 @@ void launch_grad_sides(ibis_b200_ctx* c, const FvArgs<S>& A, int which) {
                 if (g.dim == 3) { GS_NF(3) } else { GS_NF(2) }
 #undef GS_NF
             }
-            for (int q = 0; q < R.hdr[3]; q++) {
-                const int src = R.push[3 * q], count = R.push[3 * q + 1];
-                S* dst = A.sidesP + (long)R.push[3 * q + 2] * 6;
-                for (long e = 0; e < (long)count * 6; e++) dst[e] = stg[(size_t)src * 6 + e];
-            }
+            S* dst = A.sidesP + (long)R.hdr[5] * SIDE_REC;
+            for (long e = 0; e < (long)R.hdr[3] * SIDE_REC; e++) dst[e] = stg[e];
         }
     }
     c->launches++;
@@ -186,23 +183,29 @@ void launch_grad_sides(ibis_b200_ctx* c, const FvArgs<S>& A, int which) {
 template void launch_grad_sides<double>(ibis_b200_ctx*, const FvArgs<double>&, int);
 template void launch_grad_sides<dual>(ibis_b200_ctx*, const FvArgs<dual>&, int);
 
-// pass F' tile by tile: the tile's side-state array and interface record, the fluxes, the cell sums from the
-// tile's cell record
+// pass F' tile by tile: the image of the tile's interface sides (its own side-state array + the pulled runs of its
+// neighbours' arrays: the bulk copies of the device kernel as memcpy), its interface record, the fluxes, the cell sums
+// from the tile's cell record
 template <typename S>
 void launch_flux_tile(ibis_b200_ctx* c, const FvArgs<S>& A) {
     const GridDev& g = A.g;
     const int T = g.tile, cap = g.tile_cap;
 #pragma omp parallel
     {
-        std::vector<S> flux((size_t)5 * std::max(cap, 1));
+        std::vector<S> flux((size_t)5 * std::max(cap, 1)), img((size_t)SIDE_REC * std::max(g.p_cap, 1));
 #pragma omp for
         for (int t = 0; t < g.n_tiles; t++) {
-            const int n = g.tile_info[TILE_INFO * t + 9];
-            const S* P = A.sidesP + (long)g.t_pinfo[2 * t] * 6;
+            const int* pl = g.t_pull + (size_t)g.pull_stride * t;
+            const int n = pl[2];
+            for (long e = 0; e < (long)pl[1] * SIDE_REC; e++) img[e] = A.sidesP[(long)pl[0] * SIDE_REC + e];
+            for (int q = 0; q < pl[3]; q++)
+                for (long e = 0; e < (long)pl[9 + 3 * q] * SIDE_REC; e++)
+                    img[(size_t)pl[10 + 3 * q] * SIDE_REC + e] = A.sidesP[(long)pl[8 + 3 * q] * SIDE_REC + e];
+            const S* P = img.data();
             const FRecA Ra = freca_view(g.t_freca + (size_t)t * g.freca_stride, cap);
 #define TILE_FLUX(D, F, O)                                                                          \
     for (int s = 0; s < n; s++)                                                                     \
-        flux_from_sides6<D, F>(A, P + (long)Ra.lidx[s] * 6, P + (long)Ra.ridx[s] * 6, Ra.frame + (long)s * 6, &flux[(size_t)s * 5]);
+        flux_from_sides<D, F>(A, P + (long)Ra.lidx[s] * SIDE_REC, P + (long)Ra.ridx[s] * SIDE_REC, Ra.frame + (long)s * 6, &flux[(size_t)s * 5]);
             EMU_FLUX_CALL(TILE_FLUX)
 #undef TILE_FLUX
             const FRec Rc = frec_view(g.t_frec + (size_t)t * g.frec_stride, T);
