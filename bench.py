@@ -33,10 +33,16 @@ KERNEL_NAMES = {"sides": ("k_grad_sides (gradients + limiters + MUSCL sides)", "
                 "gather": ("k_grad_limit (gradients + limiters)", "k_residual_tile (reconstruct + flux + surface integral)")}
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch and cell from the committed `ncu --set full`
-# capture of the same kernels (profiles/r01_summary.md), bytes per cell; scaled by the cell count
-TRAFFIC_NCU_PER_CELL = {"sides": {"G": 662.6, "F": 604.7}, "gather": {"G": 382.0, "F": 786.0}}
-TRAFFIC_NCU = {}
+def ncu_traffic_per_cell(path):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of pass G' / pass F', per cell, from the committed
+    `ncu --set full` capture of the shipped kernels: profiles/traffic.json, written by tools/ncu_traffic.py from the
+    raw page of the capture it names.  None when there is no capture for this path."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)
+        return t[path]
+    except Exception:                                                   # noqa: BLE001
+        return None
 
 
 def measured_peak():
@@ -122,8 +128,32 @@ def box_grid_fast(n, rank=0, world=1):
     return BoxGrid(n, n, n, slab=(n * rank // world, n * (rank + 1) // world))
 
 
+def host_threads():
+    """Every core this process may run on: the reference arm uses them all.  torch.distributed.run exports
+    OMP_NUM_THREADS=1 to its workers; the reference's OpenMP runtime must not inherit that."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    os.environ.setdefault("OMP_PROC_BIND", "false")
+    return n
+
+
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def cpu_reference_rate(n_cpu, min_seconds=10.0):
     """The reference's own Kokkos-OpenMP residual (oracle/_ref) on an n_cpu^3 box: evals/s."""
+    n_threads = host_threads()
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import cases
     import refharness as rh
@@ -132,7 +162,7 @@ def cpu_reference_rate(n_cpu, min_seconds=10.0):
     mesh, g = box_grid_host(n_cpu)
     path = f"/tmp/bench_box_{n_cpu}.su2"
     mesh.write(path)
-    rc = rh.RefCase(path, box_config())
+    rc = rh.RefCase(path, box_config(), num_threads=n_threads)
     prim = cases.perturbed_state(g, 3)
     t1 = rc.time_dudt(prim, 1)
     nrep = max(3, int(min_seconds / max(t1, 1e-6)))
@@ -141,9 +171,11 @@ def cpu_reference_rate(n_cpu, min_seconds=10.0):
     cores = rc.rl.num_threads
     rc.close()
     return {"value": g.n_cells * nrep / t, "unit": "cell-residual evals/s", "cores": cores,
-            "kind": "reference",
+            "kind": "reference", "cpu": cpu_model(), "n_edge": n_cpu,
             "sample": f"{nrep} FiniteVolume::compute_dudt calls of the compiled reference (Kokkos-OpenMP, "
-                      f"{cores} threads) on the {n_cpu}^3 = {g.n_cells}-cell box, same config and field"}
+                      f"{cores} threads, {cpu_model()}) on the {n_cpu}^3 = {g.n_cells}-cell box, same config and field; "
+                      "the bare residual evaluation, without the stage updates, dt estimate and conversions the GPU "
+                      "arm's RungeKutta steps include (conservative for the GPU arm)"}
 
 
 def cpu_port_rate(n_cpu, min_seconds=10.0):
@@ -162,7 +194,8 @@ def cpu_port_rate(n_cpu, min_seconds=10.0):
             restatement.compute_dudt(g, config, prim, True)
             nrep += 1
         t = time.perf_counter() - t0
-        return {"value": g.n_cells * nrep / t, "unit": "cell-residual evals/s", "cores": 1, "kind": "port",
+        return {"value": g.n_cells * nrep / t, "unit": "cell-residual evals/s", "cores": 1, "kind": "port", "n_edge": n_cpu,
+                "cpu": cpu_model(),
                 "sample": f"{nrep} evaluations of the numpy restatement of FiniteVolume::compute_dudt (oracle/restatement.py, "
                           f"one core) on the {n_cpu}^3 = {g.n_cells}-cell box, same config and field"}
     except Exception:                                            # the baseline is a report, never a reason to fail
@@ -177,9 +210,11 @@ def run_reference(args):
     if cb is None:
         print(json.dumps({"impl": "reference", "unavailable": "neither oracle/_ref/libibis_ref.so nor oracle/restatement.py usable"}))
         return
-    n_edge = args.n_cpu if cb["kind"] == "reference" else min(args.n_cpu, 32)
+    n_edge = cb["n_edge"]
     n_cells = n_edge ** 3
-    line = {"impl": "reference", "metric": "fp64 cell-residual evals/sec", "value": cb["value"],
+    # the compiled reference did not travel: say so at top level, a numpy port on one core is not "the reference"
+    impl = "reference" if cb["kind"] == "reference" else "reference-port(numpy restatement, 1 core)"
+    line = {"impl": impl, "metric": "fp64 cell-residual evals/sec", "value": cb["value"],
             "unit": "cell-residual evals/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 3.0 * n_cells / cb["value"] * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -188,6 +223,152 @@ def run_reference(args):
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "cell-residual evals/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ---- JFNK half of the path: one GMRES iteration of the steady solver =
+#   SteadyStateLinearisation::matrix_vector_product (steady_state.cpp:52-128): set the dual parts of the conserved
+#       state to the Krylov vector, conserved -> primitive, one dual-number residual evaluation, result = v / dt* - dR.du
+#   + one modified Gram-Schmidt step of Gmres::solve (gmres.cpp:144-150; dense_linear_algebra.h:185-309).
+# Algorithmic bytes per cell (n_cons = 5, doubles; dual = 16 B):
+#   dual second-order evaluation 1470 (the 1030 of the real one with 16-byte state / gradient / residual items)
+#   set_dual 80 + 40 + 80, cons_to_prim 80 + 112, set_vector 80 + 40 + 40                               = 552
+#   Gram-Schmidt step j: (j + 1) x [dot 80 + axpy 120] + norm 40 + scale 80 + copy into the basis 80     = 200 (j + 2)
+JFNK_EVAL_BYTES, JFNK_GLUE_BYTES = 1470, 552
+
+
+def jfnk_arnoldi_bytes(j):
+    return 200 * (j + 2)
+
+
+def run_jfnk_on(ctx, g, prim, m, cycles, warmup):
+    """cycles x m GMRES iterations (matvec + Arnoldi step) on an existing context -> timings (CUDA events on the
+    context's stream) and per-kernel-group roofline figures."""
+    import torch
+    n, nc = int(g.n_cells), 5
+    stream = torch.cuda.ExternalStream(ctx.stream_ptr())
+    fs, cq, tmp, dudt = ctx.fs_create(dual=True), ctx.cq_create(dual=True), ctx.cq_create(dual=True), ctx.cq_create(dual=True)
+    ctx.fs_upload(fs, prim, 0.0 * prim)
+    ctx.prim_to_cons(cq, fs)
+    v, w = ctx.vec_create(n * nc), ctx.vec_create(n * nc)
+    basis = ctx.basis_create(n * nc, m + 1)
+    rng = np.random.default_rng(7)
+    x0 = rng.standard_normal(n * nc)
+    ctx.vec_upload(v, x0 / np.linalg.norm(x0))
+    ctx.basis_set_col(basis, 0, v)
+    dt_star = 1e-4
+
+    def ev():
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(stream)
+        return e
+
+    def iteration(j, marks=None):
+        ctx.jfnk_set_dual(cq, v, tmp)
+        ctx.cons_to_prim(tmp, fs)
+        if marks is not None:
+            marks.append(ev())
+        ctx.compute_dudt(fs, dudt, True)
+        if marks is not None:
+            marks.append(ev())
+        ctx.jfnk_set_vector(dudt, v, dt_star, w)
+        if marks is not None:
+            marks.append(ev())
+        ctx.arnoldi_mgs(basis, j, w, v)
+        if marks is not None:
+            marks.append(ev())
+
+    for _ in range(warmup):
+        for j in range(m):
+            iteration(j)
+    ctx.sync()
+    t_glue = t_eval = t_arn = 0.0
+    l0 = ctx.launch_count()
+    with torch.cuda.stream(stream):
+        e0 = ev()
+        all_marks = []
+        for _ in range(cycles):
+            for j in range(m):
+                marks = [ev()]
+                iteration(j, marks)
+                all_marks.append(marks)
+        e1 = ev()
+    ctx.sync()
+    torch.cuda.synchronize()
+    launches = ctx.launch_count() - l0
+    for mk in all_marks:
+        t_glue += mk[0].elapsed_time(mk[1]) + mk[2].elapsed_time(mk[3])
+        t_eval += mk[1].elapsed_time(mk[2])
+        t_arn += mk[3].elapsed_time(mk[4])
+    ms_total = e0.elapsed_time(e1)
+    n_it = cycles * m
+    peak, peak_kind = measured_peak()
+    arn_bytes = sum(jfnk_arnoldi_bytes(j) for j in range(m)) * cycles * n
+
+    def roof(bytes_, ms):
+        a = bytes_ / (ms * 1e-3) / 1e9
+        return {"achieved": a, "frac": a / peak, "ms": ms / n_it}
+
+    # BLAS-1/2 of the Krylov solver alone (dense_linear_algebra.h): dot, axpy, gemv over the basis
+    def timed(fn, reps=10):
+        fn()
+        ctx.sync()
+        with torch.cuda.stream(stream):
+            a = ev()
+            for _ in range(reps):
+                fn()
+            b = ev()
+        ctx.sync()
+        return a.elapsed_time(b) / reps
+
+    y = np.linspace(0.1, 1.0, m)
+    blas = {
+        "dot": roof(16.0 * n * nc * n_it, timed(lambda: ctx.vec_dot(v, w)) * n_it),
+        "axpy": roof(24.0 * n * nc * n_it, timed(lambda: ctx.vec_axpy(w, v, 0.5)) * n_it),
+        "gemv(m=%d)" % m: roof(8.0 * (m + 1) * n * nc * n_it, timed(lambda: ctx.basis_gemv(basis, m, y, w)) * n_it),
+    }
+    for k in blas.values():
+        k.pop("ms")
+    total_bytes = (JFNK_EVAL_BYTES + JFNK_GLUE_BYTES) * n * n_it + arn_bytes
+    out = {"gmres_iterations": n_it, "krylov_dim": m, "ms_per_iteration": ms_total / n_it,
+           "iterations_per_s": n_it / (ms_total * 1e-3), "dual_evals_per_s": n * n_it / (ms_total * 1e-3),
+           "gpu_launches": int(launches),
+           "roofline": {"bound": "hbm", "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
+                        "iteration": dict(roof(total_bytes, ms_total), algorithmic_bytes_per_cell=total_bytes / n / n_it),
+                        "dual_evaluation": dict(roof(JFNK_EVAL_BYTES * n * n_it, t_eval), algorithmic_bytes_per_cell=JFNK_EVAL_BYTES),
+                        "matvec_glue": dict(roof(JFNK_GLUE_BYTES * n * n_it, t_glue), algorithmic_bytes_per_cell=JFNK_GLUE_BYTES),
+                        "arnoldi_mgs": dict(roof(arn_bytes, t_arn), algorithmic_bytes_per_cell=arn_bytes / n / n_it),
+                        "blas": blas}}
+    for h in (fs, cq, tmp, dudt, v, w, basis):
+        ctx.free(h)
+    return out
+
+
+def run_jfnk(args, n=None, as_secondary=False):
+    import torch
+    import cases
+    from ibis_b200.lib import Context
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    n = n or args.n
+    g = box_grid_fast(n)
+    prim = cases.perturbed_state(g, 3)
+    ctx = Context(g, box_config(), device=int(os.environ.get("LOCAL_RANK", "0")))
+    sampler = ClockSampler(0)
+    sampler.start()
+    r = run_jfnk_on(ctx, g, prim, args.krylov, max(1, args.steps // 2 if as_secondary else args.steps), 1 if as_secondary else max(1, args.warmup // 3))
+    clocks = sampler.stop()
+    ctx.close()
+    workload = (f"JFNK half of the path on the box {n}^3 = {n ** 3} hex cells: GMRES({args.krylov}) iterations, each one exact "
+                "Jacobian-vector product (dual-number second-order ausmdv residual, steady_state.cpp:52-128) + one modified "
+                "Gram-Schmidt step (gmres.cpp:144-150); perturbed field, random unit start vector")
+    r["config"] = {"workload": workload, "cells_total": n ** 3}
+    if as_secondary:
+        return r
+    line = {"metric": "dual fp64 cell-residual evals/sec (GMRES iterations x cells)", "value": r["dual_evals_per_s"],
+            "unit": "cell-residual evals/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": r["ms_per_iteration"] * args.krylov, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64 dual", "data": "synthetic", "config": r.pop("config"), "gpu_launches": r.pop("gpu_launches"),
+            "clocks": clocks, "roofline": r.pop("roofline"), "jfnk": r}
     print(json.dumps(line))
 
 
@@ -305,7 +486,8 @@ def run_gpu(args):
     name_G, name_F = KERNEL_NAMES[path]
     ach_G, ach_F = bytes_G * n_owned / tG / 1e9, bytes_F * n_owned / tF / 1e9
     dom = "G" if tG >= tF else "F"          # the dominant kernel = the one with the longer launches
-    TRAFFIC_NCU[path] = {k: v * n_owned for k, v in TRAFFIC_NCU_PER_CELL[path].items()}
+    per_cell = ncu_traffic_per_cell(path)
+    traffic = {k: per_cell[k] * n_owned for k in ("G", "F")} if per_cell else None
     line = {
         "metric": "fp64 cell-residual evals/sec", "value": value, "unit": "cell-residual evals/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
@@ -325,14 +507,17 @@ def run_gpu(args):
         "roofline": {"bound": "hbm", "kernel": name_G if dom == "G" else name_F,
                      "achieved": ach_G if dom == "G" else ach_F, "peak": peak, "unit": "GB/s",
                      "frac": (ach_G if dom == "G" else ach_F) / peak,
-                     "traffic": TRAFFIC_NCU.get(path, {}).get(dom), "peak_kind": peak_kind,
+                     "traffic": traffic[dom] if traffic else None,
+                     "traffic_source": per_cell.get("source") if per_cell else None, "peak_kind": peak_kind,
                      "algorithmic_bytes_per_cell": bytes_G if dom == "G" else bytes_F,
                      "avg_launch_ms": (tG if dom == "G" else tF) * 1e3,
                      "path": path,
                      "pass_G": {"kernel": name_G, "avg_launch_ms": tG * 1e3, "achieved": ach_G, "frac": ach_G / peak,
-                                "algorithmic_bytes_per_cell": bytes_G},
+                                "algorithmic_bytes_per_cell": bytes_G, "traffic": traffic["G"] if traffic else None,
+                                "dram_gbs": traffic["G"] / tG / 1e9 if traffic else None},
                      "pass_F": {"kernel": name_F, "avg_launch_ms": tF * 1e3, "achieved": ach_F, "frac": ach_F / peak,
-                                "algorithmic_bytes_per_cell": bytes_F},
+                                "algorithmic_bytes_per_cell": bytes_F, "traffic": traffic["F"] if traffic else None,
+                                "dram_gbs": traffic["F"] / tF / 1e9 if traffic else None},
                      "evaluation": {"achieved": ALG_BYTES_EVAL * n_owned / (tF + tG) / 1e9,
                                     "frac": ALG_BYTES_EVAL * n_owned / (tF + tG) / 1e9 / peak,
                                     "algorithmic_bytes_per_cell": ALG_BYTES_EVAL},
@@ -349,11 +534,17 @@ def run_gpu(args):
         per_rank = [None] * world
         dist.all_gather_object(per_rank, mine)
         line["per_rank"] = per_rank
+    ctx.close()
     if rank == 0:
+        if world == 1 and not args.no_secondary:
+            # the JFNK half of the path, measured on a box that fits beside nothing else (the headline context is closed)
+            try:
+                line["secondary"] = {"jfnk": run_jfnk(args, n=min(n, args.n_jfnk), as_secondary=True)}
+            except Exception as e:                                       # noqa: BLE001  (a report, never a reason to fail)
+                line["secondary"] = {"jfnk": {"error": str(e)[:300]}}
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_reference_rate(args.n_cpu)
         print(json.dumps(line))
-    ctx.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -366,11 +557,21 @@ def main():
     ap.add_argument("--impl", default="ibis_b200")
     ap.add_argument("--n", "--edge", dest="n", type=int, default=int(os.environ.get("IBIS_BENCH_N", "400")),
                     help="edge of the global hex box (400 -> the 64 M-cell grid of BASELINE.json)")
-    ap.add_argument("--n-cpu", type=int, default=64)
+    ap.add_argument("--n-cpu", type=int, default=128,
+                    help="edge of the box the reference arm / cpu_baseline leg runs (BASELINE.md section 4.3: 128)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--workload", default="explicit", choices=["explicit", "jfnk"],
+                    help="explicit: ssp-rk3 steps (the headline); jfnk: GMRES iterations of the steady solver")
+    ap.add_argument("--krylov", type=int, default=10, help="GMRES iterations per cycle of the jfnk workload")
+    ap.add_argument("--n-jfnk", type=int, default=200, help="edge of the box of the secondary jfnk measurement")
+    ap.add_argument("--no-secondary", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "jfnk":
+        if args.n == 400 and "IBIS_BENCH_N" not in os.environ:
+            args.n = 256            # dual state + Krylov basis of the 64 M-cell box do not fit beside each other
+        run_jfnk(args)
     else:
         run_gpu(args)
 

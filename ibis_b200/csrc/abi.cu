@@ -223,10 +223,10 @@ bool sides_path(const ibis_b200_ctx* c) {
     return c->use_sides && c->cfg.reconstruction_order == 2 && !c->cfg.viscous && !c->has_flux_actions;
 }
 
-// dual-number evaluations (16-byte scalars: one tile per SM in the sides kernels) measured 10 % faster
-// through the gather path (profiles/r01_summary.md), so the sides path serves the real evaluations
+// dual-number evaluations (16-byte scalars) take the pipelined sides kernels too unless IBIS_B200_DUAL_SIDES=0
+// sends them through the gather path (what round 1 did: its one-tile-per-block sides kernels were slower on duals)
 template <typename S>
-bool sides_path_for(const ibis_b200_ctx* c) { return sides_path(c) && sizeof(S) == sizeof(double); }
+bool sides_path_for(const ibis_b200_ctx* c) { return sides_path(c) && (sizeof(S) == sizeof(double) || c->dual_sides); }
 
 template <typename S>
 int ensure_fv_temporaries(ibis_b200_ctx* c, bool want_grad = false, bool want_flux = false) {
@@ -430,6 +430,7 @@ int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd_ref, con
     c->cfg = *cfg;
     if (const char* e = getenv("IBIS_B200_ORDERED_DOT")) c->ordered_dot = e[0] == '1';
     if (const char* e = getenv("IBIS_B200_SIDES")) c->use_sides = e[0] != '0';
+    if (const char* e = getenv("IBIS_B200_DUAL_SIDES")) c->dual_sides = e[0] != '0';
     if (const char* e = getenv("IBIS_B200_RK_UNFUSED")) c->rk_unfused = e[0] == '1';
     if (const char* e = getenv("IBIS_B200_PREFETCH")) c->pipe_prefetch = std::max(0, atoi(e));
     c->bc_actions.assign(cfg->bc_actions, cfg->bc_actions + cfg->n_bc_actions);

@@ -1296,21 +1296,29 @@ IBIS_HD GRec grec_view(const unsigned char* rec, int nf, int T) {
 IBIS_HD int grec_bytes(int nf, int T, int halo_cap) { return 4 * nf * T + 32 + 4 * halo_cap; }
 
 // A side record = what linear_reconstruct extrapolates to one side of an interface (convective_flux.cpp:243-420):
-// rho, the second thermodynamic variable of the interpolator (p, T or u), vx, vy, vz.  40 bytes; the thermodynamic
-// closure (gas_model.h:91-117) is evaluated by the consumer, pass F', from the same two values with the same calls.
+// rho, the second thermodynamic variable of the interpolator (p, T, or T = u / Cv: side_second below), vx, vy, vz.
+// 40 bytes; the rest of the thermodynamic closure (gas_model.h:91-117) is evaluated by the consumer, pass F'.
 constexpr int SIDE_REC = 5;
 constexpr int SIDE_EVEN = 2;       // first records and counts of bulk transfers are multiples of this
-// the thermodynamic pair (rho, second variable) of a side record -> rho p T of the side
+// The thermodynamic closure of a side (gas_model.h:91-117) is split so that the consumer has no division left to do
+// where that is possible.  The producer (pass G') stores, next to rho, what side_second returns for the second
+// reconstructed variable: T = u / Cv for rho_u (update_thermo_from_rhou's first line), the variable itself for
+// rho_T and rho_p.  The consumer (pass F') finishes with side_close: p = rho R T for rho_u and rho_T,
+// T = p / (rho R) for rho_p.  Same calls on the same values as thermo_close, hence the same bits.
 template <typename S>
-IBIS_HD void side_close(int thermo, const Gas<S>& gas, const S& rho_in, const S& th2, S& rho, S& p, S& Tj) {
+IBIS_HD S side_second(int thermo, const Gas<S>& gas, const S& th2) {
+    return thermo == THERMO_RHO_U ? th2 / gas.Cv : th2;
+}
+template <typename S>
+IBIS_HD void side_close(int thermo, const Gas<S>& gas, const S& rho_in, const S& second, S& rho, S& p, S& Tj) {
     rho = rho_in;
-    p = S(0.0);
-    Tj = S(0.0);
-    S e = S(0.0);
-    if (thermo == THERMO_RHO_P) p = th2;
-    else if (thermo == THERMO_RHO_T) Tj = th2;
-    else e = th2;
-    thermo_close(thermo, gas, rho, p, Tj, e);
+    if (thermo == THERMO_RHO_P) {
+        p = second;
+        Tj = T_from_rhop(rho, p, gas.R);
+    } else {
+        Tj = second;
+        p = p_from_rhoT(rho, Tj, gas.R);
+    }
 }
 // staging index of the far side of a boundary interface (the ghost cell's own values): the far side
 // sits at a fixed distance from the near side in the tile's staging buffer (layout.h)
@@ -1360,13 +1368,13 @@ IBIS_HD void pipe_grad_cell(const FvArgs<S>& A, const double* wd, const GRec& R,
         if (st[j] == 0xFFFF) continue;
         S* q = stg + (long)st[j] * SIDE_REC;
 #pragma unroll
-        for (int v = 0; v < 5; v++) q[v] = r[v][j];
+        for (int v = 0; v < 5; v++) q[v] = v == 1 ? side_second(A.thermo, A.gas, r[v][j]) : r[v][j];
         if (ghost[j]) {
             // the far side of a boundary interface is the ghost cell itself: zero gradient, unit limiter
             // (convective_flux.cpp:281-300), i.e. its values, closed thermodynamically like any other side
             S* f = stg + (long)far_stage_index(left[j], st[j], nR, n_own_l) * SIDE_REC;
 #pragma unroll
-            for (int v = 0; v < 5; v++) f[v] = sv[v * svs + nl[j]];
+            for (int v = 0; v < 5; v++) f[v] = v == 1 ? side_second(A.thermo, A.gas, sv[v * svs + nl[j]]) : sv[v * svs + nl[j]];
         }
     }
 }

@@ -255,20 +255,29 @@ __global__ void __launch_bounds__(32 * (IBIS_PIPE_F_WARPS + IBIS_PIPE_F_LOADERS)
             }
         };
         if (w < n_my) fetch_pull((size_t)blockIdx.x + (size_t)w * step, h0, h1, h2, h3, h4, ps, pc, pd);
+        // the prefetch tile's header and this lane's run: read one iteration before the prefetches are issued
+        int f0 = 0, f1 = 0, f2 = 0, f3 = 0, f4 = 0, fps = 0, fpc = 0, fpd = 0;
+        bool have_pf = false;
         for (int k = w; k < n_my; k += NL) {
             const int t = (int)blockIdx.x + k * step, s = k % nsi, o = k % nfb;
-            if (PF > 0 && k + PF < n_my && lane == 0) {       // L2 prefetch of a later tile of this loader
-                const size_t tp = (size_t)t + (size_t)PF * step;
-                const int q0 = __ldg(g.t_pinfo + 2 * tp), q1 = __ldg(g.t_pinfo + 2 * tp + 1);
-                ac::bulk_prefetch_l2(A.sidesP + (size_t)q0 * SIDE_REC, (uint32_t)q1 * (uint32_t)SIDE_REC * (uint32_t)sizeof(S));
-                ac::bulk_prefetch_l2(g.t_freca + tp * g.freca_stride, (uint32_t)g.freca_stride);
-                ac::bulk_prefetch_l2(g.t_frec + tp * g.frec_stride, (uint32_t)g.frec_stride);
-                if (with_dt) {
-                    int c0p, ncp;
-                    tile_cells(g, (int)tp, c0p, ncp);
-                    for (int v = 0; v < 4; v++) ac::bulk_prefetch_l2(A.fs[v < 3 ? F_VX + v : F_T] + c0p, (uint32_t)T * (uint32_t)sizeof(S));
+            if (have_pf) {                                    // L2 prefetch of tile k - NL + PF (list read an iteration ago)
+                const size_t tp = (size_t)t + (size_t)(PF - NL) * step;
+                constexpr uint32_t RBp = (uint32_t)SIDE_REC * (uint32_t)sizeof(S);
+                if (lane == 0) {
+                    ac::bulk_prefetch_l2(A.sidesP + (size_t)f0 * SIDE_REC, (uint32_t)f1 * RBp);
+                    ac::bulk_prefetch_l2(g.t_freca + tp * g.freca_stride, (uint32_t)g.freca_stride);
+                    ac::bulk_prefetch_l2(g.t_frec + tp * g.frec_stride, (uint32_t)g.frec_stride);
+                    if (with_dt) {
+                        int c0p, ncp;
+                        tile_cells(g, (int)tp, c0p, ncp);
+                        for (int v = 0; v < 4; v++) ac::bulk_prefetch_l2(A.fs[v < 3 ? F_VX + v : F_T] + c0p, (uint32_t)T * (uint32_t)sizeof(S));
+                    }
+                } else if (lane <= f3) {
+                    ac::bulk_prefetch_l2(A.sidesP + (size_t)fps * SIDE_REC, (uint32_t)fpc * RBp);
                 }
             }
+            have_pf = PF > 0 && k + PF < n_my;
+            if (have_pf) fetch_pull((size_t)t + (size_t)PF * step, f0, f1, f2, f3, f4, fps, fpc, fpd);
             int n0 = 0, n1 = 0, n2 = 0, n3 = 0, n4 = 0, ns_ = 0, nc_ = 0, nd_ = 0;   // this loader's next tile, in flight during the waits
             if (k + NL < n_my) fetch_pull((size_t)t + (size_t)NL * step, n0, n1, n2, n3, n4, ns_, nc_, nd_);
             if (k >= nsi && !pipe_spin_ge(&stage_free[s], k - nsi, A.pipe_dbg, PW_EMPTY, k)) return;
@@ -423,7 +432,7 @@ __host__ __device__ inline size_t grad_out_bytes(int stage_cap) {
 
 // One work item of pass G', one cell per lane:
 //   items [0, T / 32):  32 cells x (rho, then the second thermodynamic variable) -> the first two places of the
-//                       cell's side records (pass F' closes them thermodynamically, gas_model.h:91-117);
+//                       cell's side records (fv_bodies.h::side_second; pass F' finishes the closure, gas_model.h:91-117);
 //   the others:         all T cells (T / 32 rounds of 32) x one velocity component -> vx | vy | vz of the records.
 // Items are of about the same size (two gradient + limiter + extrapolation passes each at T = 64).  ONE loop body
 // serves every pass of both kinds -- a single instance of var_to_faces in the kernel: with twenty warps at different
@@ -463,12 +472,14 @@ __device__ __forceinline__ void grad_item(const FvArgs<S>& A, const double* wd, 
         // the far side of a boundary interface is the ghost cell itself: zero gradient, unit limiter
         // (convective_flux.cpp:281-300), i.e. its values
         const int slot_v = thermo ? pass : 2 + v;             // place of this variable in the side records
+        const bool second = thermo && pass == 1;              // fv_bodies.h::side_second: T = u / Cv for rho_u
 #pragma unroll
         for (int j = 0; j < NF; j++) {
             if (st[j] == 0xFFFF) continue;
-            stg[(long)st[j] * SIDE_REC + slot_v] = r[j];
+            stg[(long)st[j] * SIDE_REC + slot_v] = second ? side_second(A.thermo, A.gas, r[j]) : r[j];
             if (ghosts && (fl[j] & NBR_GHOST_BIT))
-                stg[(long)far_stage_index((fl[j] & NBR_LEFT_BIT) != 0, st[j], nR, n_own_l) * SIDE_REC + slot_v] = un[j];
+                stg[(long)far_stage_index((fl[j] & NBR_LEFT_BIT) != 0, st[j], nR, n_own_l) * SIDE_REC + slot_v] =
+                    second ? side_second(A.thermo, A.gas, un[j]) : un[j];
         }
         if (DIM == 2 && !thermo && v == 1) {
             // 2-D: vz has no gradient (convective_flux.cpp:206-208) and a unit limiter: the value is copied

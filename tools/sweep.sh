@@ -9,7 +9,7 @@ for spec in "$@"; do
   tag="${spec%%:*}"; envs=""; [[ "$spec" == *:* ]] && envs="${spec#*:}"
   lib="ibis_b200/lib/variants/$tag/libibis_b200.so"; [ "$tag" = default ] && lib="ibis_b200/lib/libibis_b200.so"
   out="gpurun_out/sweep_${tag}_$(echo "$envs" | tr ',=' '__').json"
-  env IBIS_B200_LIB=$lib $(echo "$envs" | tr ',' ' ') python bench.py --n $N --steps 4 --warmup 3 --no-cpu > "$out" 2> "$out.err" || { echo "$spec FAILED"; tail -3 "$out.err"; continue; }
+  env IBIS_B200_LIB=$lib $(echo "$envs" | tr ',' ' ') python bench.py --n $N --steps 4 --warmup 3 --no-cpu --no-secondary > "$out" 2> "$out.err" || { echo "$spec FAILED"; tail -3 "$out.err"; continue; }
   python - "$out" "$spec" <<'PY'
 import json, sys
 d = json.load(open(sys.argv[1])); r = d["roofline"]
