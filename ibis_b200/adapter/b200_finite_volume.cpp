@@ -14,8 +14,8 @@
 //
 // The flow state lives in the reference's Kokkos Views here (host memory with the OpenMP backend) and travels to the
 // device and back on every call: this adapter demonstrates the boundary and its parity, not the speed of the fused
-// path (ibis_b200_rk_step keeps everything resident).  Build: oracle/ref_build/Makefile,
-// target libibis_ref_b200.so; test: tests/test_gpu_dropin.py.
+// path (ibis_b200_rk_step keeps everything resident).  Build: oracle/ref_build/Makefile
+// (the drop-in library next to the compiled reference); test: tests/test_gpu_dropin.py.
 #include <finite_volume/finite_volume.h>
 #include <ibis_b200.h>
 
