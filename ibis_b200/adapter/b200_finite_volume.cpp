@@ -19,7 +19,9 @@
 #include <finite_volume/finite_volume.h>
 #include <ibis_b200.h>
 
+#include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <memory>
 #include <stdexcept>
@@ -261,7 +263,11 @@ Backend& backend_for(GridBlock<T>& grid) {
 // FlowStates<T> -> FlowStates rows rho p T e vx vy vz (include/ibis_b200.h conventions) -> device
 template <typename T>
 void upload_flow(Backend& b, const FlowStates<T>& fs) {
-    for (int64_t i = 0; i < b.n_total; i++) {
+    // a caller may hold fewer rows than the grid has cells + ghosts (count_bad_cells looks at valid cells only)
+    const int64_t n = std::min<int64_t>(b.n_total, (int64_t)fs.number_flow_states());
+    for (int64_t i = n; i < b.n_total; i++)
+        for (int k = 0; k < 7; k++) b.prim_re[7 * i + k] = b.prim_du[7 * i + k] = 0.0;
+    for (int64_t i = 0; i < n; i++) {
         const T v[7] = {fs.gas.rho(i), fs.gas.pressure(i), fs.gas.temp(i), fs.gas.energy(i), fs.vel.x(i), fs.vel.y(i), fs.vel.z(i)};
         for (int k = 0; k < 7; k++) {
             b.prim_re[7 * i + k] = re(v[k]);
@@ -287,6 +293,8 @@ size_t FiniteVolume<T>::compute_dudt(FlowStates<T>& flow_state, GridBlock<T>& gr
     (void)gas_model;
     (void)trans_prop;
     Backend& b = backend_for(grid);
+    static const bool trace = getenv("IBIS_B200_ADAPTER_TRACE") != nullptr;
+    if (trace) fprintf(stderr, "[ibis_b200 adapter] compute_dudt<%s>(allow_reconstruction = %d)\n", is_dual_v<T> ? "dual" : "real", (int)allow_reconstruction);
     upload_flow(b, flow_state);
     ck(b.ctx, ibis_b200_compute_dudt(b.ctx, b.fs, b.dudt, allow_reconstruction ? 1 : 0), "compute_dudt");
     // the boundary conditions have rewritten the ghost cells (finite_volume.cpp:62, 187-199): they go back into the

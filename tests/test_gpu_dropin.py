@@ -22,6 +22,7 @@ ROOT = os.path.dirname(HERE)
 REF_DIR = os.path.join(ROOT, "oracle", "_ref")
 DROPIN = os.path.join(REF_DIR, "libibis_ref_b200.so")
 STOCK = os.path.join(REF_DIR, "libibis_ref.so")
+PADMALLOC = os.path.join(REF_DIR, "libpadmalloc.so")
 CASES = os.path.join(HERE, "golden", "dropin")
 
 RUNNER = r"""
@@ -42,8 +43,12 @@ def solve_with(lib_path, case, tmp_path, tag, preload=None):
     shutil.copytree(os.path.join(CASES, case), work)
     os.makedirs(os.path.join(work, "log"), exist_ok=True)
     env = dict(os.environ)
-    if preload:
-        env["LD_PRELOAD"] = preload
+    # oracle/ref_build/padmalloc.c pads every allocation by 32 bytes: the reference's Gmres stores one Hessenberg
+    # column past its arrays when max_iters is reached (and its CubicSpline one element), which the stock build
+    # survives by luck of the heap layout and this one -- more host allocations in between -- does not
+    pre = [p for p in (preload, PADMALLOC if os.path.exists(PADMALLOC) else None) if p]
+    if pre:
+        env["LD_PRELOAD"] = " ".join(pre)
     r = subprocess.run([sys.executable, "-c", RUNNER, lib_path, work], capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, f"{tag} solve of {case} failed: rc {r.returncode}\n{r.stdout[-2000:]}\n{r.stderr[-2000:]}"
     flow = os.path.join(work, "io", "flow")
@@ -51,6 +56,38 @@ def solve_with(lib_path, case, tmp_path, tag, preload=None):
     expected = np.load(os.path.join(CASES, case, "expected.npz"))
     names = ["T", "p", "vx", "vy"] + (["vz"] if int(expected["dim"]) == 3 else [])
     return {k: np.fromfile(os.path.join(flow, dirs[-1], k)) for k in names}, len(dirs), r.stderr
+
+
+# The reference's EXAMPLES at about their own resolution (job.py unchanged through the reference's prep; what was
+# edited in config.json afterwards is listed in tests/golden/make_dropin_cases.py): 150 ssp-rk3 steps of the Mach 3
+# wedge (5 400 cells) and of the forward-facing step (4 032 cells), 60 steps of the viscous NACA 0012 (3 072 cells,
+# subsonic in/outflow, no-slip wall).
+EXAMPLES = {"example_wedge_transient": 0.0, "example_forward_facing_step": 0.0, "example_naca0012_viscous": 1e-11}
+
+
+def compare(case, got, expected, rtol):
+    for k, v in got.items():
+        want = expected["final_" + k]
+        if rtol == 0.0:
+            assert np.array_equal(v, want), f"{case}: {k} differs from the stock reference's snapshot"
+        else:
+            scale = max(1.0, float(np.abs(want).max()))
+            assert np.allclose(v, want, rtol=rtol, atol=rtol * scale), \
+                f"{case}: {k} off by {np.max(np.abs(v - want)) / scale:.3e} (relative to the field's scale)"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", sorted(EXAMPLES))
+def test_reference_examples_on_the_b200_residual(case, tmp_path):
+    import torch
+    assert torch.cuda.is_available()
+    if not os.path.exists(DROPIN):
+        pytest.skip("oracle/_ref/libibis_ref_b200.so not built (needs /root/reference at build time)")
+    expected = np.load(os.path.join(CASES, case, "expected.npz"))
+    got, n_snap, log = solve_with(DROPIN, case, tmp_path, "b200")
+    assert "[ibis_b200 adapter] FiniteVolume<" in log
+    assert n_snap == int(expected["n_snapshots"])
+    compare(case, got, expected, EXAMPLES[case])
 
 
 @pytest.mark.gpu
