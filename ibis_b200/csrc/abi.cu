@@ -23,8 +23,14 @@ namespace {
 
 thread_local std::string g_last_error;
 
+// Argument errors (EINVAL, EHANDLE) are the caller's and leave the context usable: they are reported by the call
+// that made them and by ibis_b200_last_error, nothing else.  Device, memory and communication failures are sticky:
+// last_error stays set and every later call that launches work returns ECUDA (the stream's state is unknown).
 int fail(ibis_b200_ctx* c, int code, const std::string& msg) {
-    if (c) c->last_error = msg;
+    if (c) {
+        c->last_message = msg;
+        if (code == IBIS_B200_ECUDA || code == IBIS_B200_ENOMEM || code == IBIS_B200_ECOMM) c->last_error = msg;
+    }
     g_last_error = msg;
     return code;
 }
@@ -377,7 +383,8 @@ constexpr int N_SCALARS = 16 + 1024;   // h / y of up to 1023 Krylov vectors
 extern "C" {
 
 const char* ibis_b200_last_error(const ibis_b200_ctx* c) {
-    return c ? c->last_error.c_str() : g_last_error.c_str();
+    if (!c) return g_last_error.c_str();
+    return !c->last_error.empty() ? c->last_error.c_str() : c->last_message.c_str();
 }
 
 int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd_ref, const ibis_b200_config* cfg, int device) {

@@ -57,7 +57,8 @@ struct ibis_b200_ctx {
     int device = 0;
     int n_sm = 148;                      // multiprocessors of the device (persistent grids)
     ib::gpu::stream_t stream = nullptr;
-    std::string last_error;
+    std::string last_error;              // sticky: a device / memory / communication failure (abi.cu::fail)
+    std::string last_message;            // the most recent failure of any kind, argument errors included
     int64_t launches = 0;
 
     // sizes

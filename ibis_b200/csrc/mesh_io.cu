@@ -60,10 +60,11 @@ std::string value_of(const char* b, const char* e) {      // NAME=VALUE -> VALUE
     return std::string(v, e);
 }
 // element line "type v0 v1 ..." -> type, n vertex ids padded with -1 to `width`; false when malformed
-bool parse_element(const char* b, int width, int32_t* type, int64_t* out) {
+// (strto* skip '\n' as white space: a token found past `end` belongs to the next line -- the line is short)
+bool parse_element(const char* b, const char* end, int width, int32_t* type, int64_t* out) {
     char* q = nullptr;
     const long t = strtol(b, &q, 10);
-    if (q == b) return false;
+    if (q == b || q > end) return false;
     const int n = t == 3 ? 2 : gb_num_vertices((int)t);      // 3 = line (boundary of a 2-D grid)
     if (n == 0 || n > width) return false;
     *type = (int32_t)t;
@@ -71,7 +72,7 @@ bool parse_element(const char* b, int width, int32_t* type, int64_t* out) {
     for (int k = 0; k < n; k++) {
         const char* s = q;
         out[k] = strtoll(s, &q, 10);
-        if (q == s) return false;
+        if (q == s || q > end) return false;
     }
     return true;
 }
@@ -99,14 +100,19 @@ int ibis_b200_mesh_read_su2(ibis_b200_mesh** out, const char* path) {
     Lines L(buf.data(), (size_t)fsize);
     const char *b, *e;
     // the next n lines of the file, as start pointers (each line ends at '\n' or '\0' for strto*)
-    auto index_lines = [&](int64_t n, std::vector<const char*>& starts) {
+    // (a section cannot hold more lines than the file has bytes: a corrupt count fails here, not in the allocator)
+    auto index_lines = [&](int64_t n, std::vector<const char*>& starts, std::vector<const char*>& ends) {
+        if (n > (int64_t)fsize) return false;
         starts.resize((size_t)n);
+        ends.resize((size_t)n);
         for (int64_t i = 0; i < n; i++) {
             if (!L.next(b, e)) return false;
             starts[i] = b;
+            ends[i] = e;
         }
         return true;
     };
+    try {
     while (L.next(b, e)) {
         if (starts_with(b, e, "NDIME")) {
             dim = atoi(value_of(b, e).c_str());
@@ -114,8 +120,8 @@ int ibis_b200_mesh_read_su2(ibis_b200_mesh** out, const char* path) {
                 return fail_global(IBIS_B200_EINVAL, "Invalid number of dimensions in su2 file");   // grid_io.cpp:199-202
         } else if (starts_with(b, e, "NPOIN")) {
             const int64_t n = atoll(value_of(b, e).c_str());
-            std::vector<const char*> starts;
-            if (dim == 0 || n < 0 || !index_lines(n, starts)) return fail_global(IBIS_B200_EINVAL, "truncated NPOIN section");
+            std::vector<const char*> starts, ends;
+            if (dim == 0 || n < 0 || !index_lines(n, starts, ends)) return fail_global(IBIS_B200_EINVAL, "truncated NPOIN section");
             m->vertices.assign((size_t)3 * n, 0.0);
             bool bad = false;
 #pragma omp parallel for schedule(static) reduction(|| : bad)
@@ -124,28 +130,28 @@ int ibis_b200_mesh_read_su2(ibis_b200_mesh** out, const char* path) {
                 for (int d = 0; d < dim; d++) {
                     char* q = nullptr;
                     m->vertices[(size_t)3 * i + d] = strtod(s, &q);
-                    if (q == s) bad = true;
+                    if (q == s || q > ends[i]) bad = true;
                     s = q;
                 }
             }
             if (bad) return fail_global(IBIS_B200_EINVAL, "malformed vertex line");
         } else if (starts_with(b, e, "NELEM")) {
             const int64_t n = atoll(value_of(b, e).c_str());
-            std::vector<const char*> starts;
-            if (n < 0 || !index_lines(n, starts)) return fail_global(IBIS_B200_EINVAL, "truncated NELEM section");
+            std::vector<const char*> starts, ends;
+            if (n < 0 || !index_lines(n, starts, ends)) return fail_global(IBIS_B200_EINVAL, "truncated NELEM section");
             m->cell_types.assign((size_t)n, 0);
             m->cell_vertices.assign((size_t)8 * n, -1);
             bool bad = false;
 #pragma omp parallel for schedule(static) reduction(|| : bad)
             for (int64_t i = 0; i < n; i++)
-                if (!parse_element(starts[i], 8, &m->cell_types[i], &m->cell_vertices[(size_t)8 * i])) bad = true;
+                if (!parse_element(starts[i], ends[i], 8, &m->cell_types[i], &m->cell_vertices[(size_t)8 * i])) bad = true;
             if (bad) return fail_global(IBIS_B200_EINVAL, "malformed or unsupported element line");
         } else if (starts_with(b, e, "MARKER_TAG")) {
             const std::string tag = value_of(b, e);
             if (!L.next(b, e)) return fail_global(IBIS_B200_EINVAL, "truncated marker");
             const int64_t n = atoll(value_of(b, e).c_str());
-            std::vector<const char*> starts;
-            if (n < 0 || !index_lines(n, starts)) return fail_global(IBIS_B200_EINVAL, "truncated marker");
+            std::vector<const char*> starts, ends;
+            if (n < 0 || !index_lines(n, starts, ends)) return fail_global(IBIS_B200_EINVAL, "truncated marker");
             auto& mk = markers[tag];                          // a repeated tag is appended to (grid_io.cpp:254-262)
             const size_t n0 = mk.first.size();
             mk.first.resize(n0 + (size_t)n);
@@ -153,7 +159,7 @@ int ibis_b200_mesh_read_su2(ibis_b200_mesh** out, const char* path) {
             bool bad = false;
 #pragma omp parallel for schedule(static) reduction(|| : bad)
             for (int64_t i = 0; i < n; i++)
-                if (!parse_element(starts[i], 4, &mk.first[n0 + i], &mk.second[4 * (n0 + i)])) bad = true;
+                if (!parse_element(starts[i], ends[i], 4, &mk.first[n0 + i], &mk.second[4 * (n0 + i)])) bad = true;
             if (bad) return fail_global(IBIS_B200_EINVAL, "malformed marker element line");
         }
     }
@@ -179,6 +185,11 @@ int ibis_b200_mesh_read_su2(ibis_b200_mesh** out, const char* path) {
     guard.m = nullptr;
     *out = m;
     return 0;
+    } catch (const std::bad_alloc&) {
+        return fail_global(IBIS_B200_ENOMEM, "out of host memory while reading the grid file");
+    } catch (const std::exception& ex) {
+        return fail_global(IBIS_B200_EINVAL, ex.what());
+    }
 }
 
 const ibis_b200_mesh_desc* ibis_b200_mesh_desc_of(const ibis_b200_mesh* m) { return m ? &m->desc : nullptr; }

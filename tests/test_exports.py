@@ -58,3 +58,4 @@ def test_headers_are_plain_c(header):
     r = subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-x", "c", "-fsyntax-only", "-I", ROOT, "-"],
                        input=f'#include "include/{header}"\n', text=True, capture_output=True)
     assert r.returncode == 0, r.stderr
+

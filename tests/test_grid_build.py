@@ -161,6 +161,20 @@ def test_native_su2_reader_quirks(tmp_path):
         f.write("NDIME= 3\nNPOIN= 5\n0 0 0\n1 0 0\n")
     with pytest.raises(IbisB200Error, match="truncated NPOIN"):
         libmod.read_su2(path, lib_path=L)
+    # a line with too few tokens must not borrow numbers from the line below (the reference tokenises line by line)
+    with open(path, "w") as f:
+        f.write("NDIME= 2\nNPOIN= 3\n0 0\n1\n0 1\nNELEM= 1\n5 0 1 2\n")
+    with pytest.raises(IbisB200Error, match="malformed vertex line"):
+        libmod.read_su2(path, lib_path=L)
+    with open(path, "w") as f:
+        f.write("NDIME= 2\nNPOIN= 4\n0 0\n1 0\n1 1\n0 1\nNELEM= 2\n5 0 1\n5 2 3 0\n")
+    with pytest.raises(IbisB200Error, match="malformed or unsupported element"):
+        libmod.read_su2(path, lib_path=L)
+    # a corrupt count fails as a truncated section, not in the allocator
+    with open(path, "w") as f:
+        f.write("NDIME= 2\nNPOIN= 900000000000000\n0 0\n")
+    with pytest.raises(IbisB200Error, match="truncated NPOIN"):
+        libmod.read_su2(path, lib_path=L)
 
 
 def test_empty_and_single_cell_grids():

@@ -74,3 +74,26 @@ def test_first_order_ignores_limiter_and_interpolator():
                dict(reconstruction_order=1)):
         other = cfg.make_config(3, cases.box3_bcs(), flux_calculator="ausmdv", **kw)
         assert np.array_equal(_residual(g, other, prim, False), base), kw
+
+
+def test_an_argument_error_does_not_poison_the_context():
+    """A bad handle is reported by the call that passed it (EHANDLE + message) and by nothing after it: the next
+    valid call on the same context succeeds (last_error used to stay set and turn every later
+    call into ECUDA)."""
+    import numpy as np
+    import cases
+    from emu_util import emu_lib
+    from ibis_b200.lib import Context, IbisB200Error
+    mesh, config, g, prim = cases.build_case("box3d_ausmdv")
+    ctx = Context(g, config, lib_path=emu_lib())
+    fs, dq = ctx.fs_create(), ctx.cq_create()
+    ctx.fs_upload(fs, prim)
+    with pytest.raises(IbisB200Error, match="bad handle"):
+        ctx.compute_dudt(12345, dq, True)
+    with pytest.raises(IbisB200Error):
+        ctx.rk_residual_norms()                       # "rk_residual_norms before rk_step"
+    ctx.compute_dudt(fs, dq, True)                    # would raise with a poisoned context
+    ctx.sync()
+    assert np.isfinite(ctx.cq_download(dq)[:g.n_cells]).all()
+    assert ctx.count_bad_cells(fs) == 0
+    ctx.close()
