@@ -356,6 +356,11 @@ int check_pipe_stall(ibis_b200_ctx* c) {
     if (!c->h_pipe_dbg || c->h_pipe_dbg[0] == 0) return 0;
     const unsigned int* d = c->h_pipe_dbg;
     char msg[256];
+    if (d[1] == 64u) {
+        snprintf(msg, sizeof msg, "halo exchange %u: a peer never published its cells (it had published %u); the ranks have made "
+                                  "different numbers of evaluations or a peer has failed", d[4], d[5]);
+        return fail(c, IBIS_B200_ECOMM, msg);
+    }
     snprintf(msg, sizeof msg, "pipelined kernel stalled and was aborted: barrier kind %u, block %u, warp %u, local tile %u, parity %u",
              d[1], d[2], d[3], d[4], d[5]);
     return fail(c, IBIS_B200_ECUDA, msg);

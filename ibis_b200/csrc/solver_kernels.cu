@@ -337,17 +337,35 @@ __global__ void __launch_bounds__(256) k_halo_push(Comps7<S> fs, const int* cell
 }
 
 // pull: wait until the peer has published this exchange (acquire), then scatter the segment; the
-// area is read past L1 (ld.global.cg): it was written by another GPU
+// area is read past L1 (ld.global.cg): it was written by another GPU.
+// The wait is bounded (about 10 s of SM clocks): a peer that died, returned early on an error or made a different
+// number of evaluations never publishes -- the block then records the stall in the context's abort word (the one the
+// pipelined kernels use; abi.cu::check_pipe_stall turns it into ECOMM at the next synchronise) and leaves the halo as it is.
+constexpr long long HALO_TIMEOUT_CLOCKS = 20000000000ll;
 template <typename S>
 __global__ void __launch_bounds__(256) k_halo_pull(Comps7<S> fs, const int* cells, long n, const S* area,
-                                                   const unsigned long long* flag, unsigned long long iter) {
+                                                   const unsigned long long* flag, unsigned long long iter, unsigned int* dbg) {
+    __shared__ int gave_up;
     if (threadIdx.x == 0) {
         unsigned long long seen;
-        do {
+        const long long t0 = clock64();
+        int stalled = 0;
+        for (unsigned it = 1;; it++) {
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(flag) : "memory");
-        } while (seen < iter);
+            if (seen >= iter) break;
+            if ((it & 1023u) == 0u && (*reinterpret_cast<volatile unsigned int*>(dbg) != 0u || clock64() - t0 > HALO_TIMEOUT_CLOCKS)) {
+                if (atomicCAS(dbg, 0u, 1u) == 0u) {
+                    dbg[1] = 64u; dbg[2] = blockIdx.x; dbg[3] = 0u; dbg[4] = (unsigned)iter; dbg[5] = (unsigned)seen;
+                    __threadfence_system();
+                }
+                stalled = 1;
+                break;
+            }
+        }
+        gave_up = stalled;
     }
     __syncthreads();
+    if (gave_up) return;
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int cidx = cells[i];
@@ -653,7 +671,7 @@ template void launch_halo_push<dual>(ibis_b200_ctx*, dual* const*, const int*, i
 template <typename S>
 void launch_halo_pull(ibis_b200_ctx* c, S* const* fs, const int* cells, int64_t n, const S* area,
                       const unsigned long long* flag, unsigned long long iter) {
-    k_halo_pull<S><<<n > 0 ? nblocks(n, 256) : 1, 256, 0, c->stream>>>(c7(fs), cells, n, area, flag, iter);
+    k_halo_pull<S><<<n > 0 ? nblocks(n, 256) : 1, 256, 0, c->stream>>>(c7(fs), cells, n, area, flag, iter, c->d_pipe_dbg);
     CUDA_CHECK_LAUNCH(c);
 }
 template void launch_halo_pull<double>(ibis_b200_ctx*, double* const*, const int*, int64_t, const double*, const unsigned long long*, unsigned long long);
