@@ -24,6 +24,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--edge", dest="n", type=int, default=48)
     ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--krylov", type=int, default=6, help="GMRES iterations of the decomposed JFNK check")
     ap.add_argument("--case", default=None,
                     help="a case of tests/cases.py (unstructured SU2 mesh) decomposed by recursive coordinate "
                          "bisection (ibis_b200/partition.py) instead of the box in slabs")
@@ -99,6 +100,52 @@ def main():
                           "cells_compared": seen, "cells_differing": mism, "dt_identical": bool(gathered[0][2] == wdts),
                           "l2_norms_decomposed": gathered[0][3], "l2_norms_whole": list(wnorms), "ok": bool(ok)}))
         wctx.close()
+    # ---- the JFNK half on the decomposed grid: m GMRES iterations (dual-number matvec + modified Gram-Schmidt) from
+    # the same global start vector.  Inner products run over owned cells and are summed over the ranks
+    # (abi.cu::dot_collective): every rank must see the Hessenberg columns of the undecomposed run (to rounding: the
+    # sums are taken in another order) and hold its part of the same Krylov vectors.
+    if not args.case:
+        m = args.krylov
+
+        def krylov(c, grid, prim_local, ids):
+            nloc = int(grid.n_cells)
+            f, q, tmp, dq = c.fs_create(dual=True), c.cq_create(dual=True), c.cq_create(dual=True), c.cq_create(dual=True)
+            c.fs_upload(f, prim_local, 0.0 * prim_local)
+            c.prim_to_cons(q, f)
+            v, w = c.vec_create(nloc * 5), c.vec_create(nloc * 5)
+            basis = c.basis_create(nloc * 5, m + 1)
+            x0 = np.sin(0.37 * ids[:, None] + np.arange(5)[None, :]).reshape(-1)
+            c.vec_upload(v, x0)
+            c.vec_scale(v, v, 1.0 / c.vec_norm2(v))
+            c.basis_set_col(basis, 0, v)
+            H = []
+            for j in range(m):
+                c.jfnk_set_dual(q, v, tmp)
+                c.cons_to_prim(tmp, f)
+                c.compute_dudt(f, dq, True)
+                c.jfnk_set_vector(dq, v, 1e-4, w)
+                H.append(c.arnoldi_mgs(basis, j, w, v).tolist())
+            return H, c.vec_download(v, nloc * 5).reshape(nloc, 5)
+
+        loc2 = np.ones((slab.n_total, 7))
+        loc2[:slab.n_cells] = gprim[gid]
+        Hd, vd = krylov(ctx, slab, loc2, gid)
+        gathered = [None] * world
+        dist.gather_object((gid[:slab.n_owned], Hd, vd[:slab.n_owned]), gathered if rank == 0 else None, dst=0)
+        if rank == 0:
+            wctx = Context(whole, config, device=local)
+            Hw, vw = krylov(wctx, whole, gprim, np.arange(n_global))
+            wctx.close()
+            okj, worst_h, worst_v = True, 0.0, 0.0
+            for g_ids, Hr, vr in gathered:
+                for a, b in zip(Hr, Hw):
+                    # relative to the column's largest entry (an entry that cancels to nearly zero has no relative accuracy)
+                    worst_h = max(worst_h, float(np.max(np.abs(np.array(a) - np.array(b))) / np.max(np.abs(b))))
+                worst_v = max(worst_v, float(np.max(np.abs(vr - vw[g_ids]))))
+            okj = worst_h < 1e-9 and worst_v < 1e-9
+            ok &= okj
+            print(json.dumps({"check": "decomposed GMRES == whole-grid GMRES", "grid": f"box {n}^3", "ranks": world, "krylov_dim": m,
+                              "max_diff_hessenberg_rel_to_column": worst_h, "max_abs_diff_last_krylov_vector": worst_v, "ok": bool(okj)}))
     ctx.close()
     dist.barrier()
     dist.destroy_process_group()
