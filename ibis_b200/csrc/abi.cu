@@ -15,6 +15,8 @@
 
 #include "comm.h"
 #include "context.h"
+#include <limits>
+
 #include "layout.h"
 
 using namespace ib;
@@ -1038,6 +1040,11 @@ int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd_ref, con
     c->n_red_blocks = 148 * 8;
     rc = dev_alloc_zero<double>(c, (int64_t)c->n_red_blocks * 8, &c->d_partials);
     if (!rc) rc = dev_alloc_zero<double>(c, N_SCALARS, &c->d_scalars);
+    if (!rc) {                                      // "the previous step" of the first asynchronous rk_step
+        const double big = std::numeric_limits<double>::max();
+        rc = gpu::h2d(c->d_scalars + SC_DT, &big, sizeof big, c->stream) != 0 ? IBIS_B200_ECUDA : 0;
+        if (!rc) rc = gpu::stream_sync(c->stream) != 0 ? IBIS_B200_ECUDA : 0;
+    }
     if (rc) { ibis_b200_destroy(c); return fail(nullptr, rc, "out of device memory"); }
     void* hp = nullptr;
     if (gpu::host_malloc(&hp, N_SCALARS * sizeof(double)) != 0) {
@@ -1063,6 +1070,7 @@ int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd_ref, con
     return 0;
 }
 
+static void ring_destroy(ibis_b200_ctx* c);      // the snapshot ring, below
 int ibis_b200_destroy(ibis_b200_ctx* c) {
     if (!c) return 0;
     gpu::set_device(c->device);
@@ -1074,6 +1082,7 @@ int ibis_b200_destroy(ibis_b200_ctx* c) {
     if (c->d_stage) gpu::dev_free(c->d_stage);
     if (c->h_scalars) gpu::host_free(c->h_scalars);
     if (c->h_pipe_dbg) gpu::host_free(c->h_pipe_dbg);
+    ring_destroy(c);
     if (c->stream) gpu::stream_destroy(c->stream);
     delete c;
     return 0;
@@ -1213,6 +1222,110 @@ int ibis_b200_flow_write_native(ibis_b200_ctx* c, int h, double* T, double* p, d
     GPU_TRY(c, gpu::stream_sync(c->stream));
     return c->last_error.empty() ? 0 : IBIS_B200_ECUDA;
 }
+// ---- snapshot ring: native_binary snapshots travel while the device computes ------------------------------------
+static int ring_init(ibis_b200_ctx* c) {
+    ibis_b200_ctx::SnapshotRing& r = c->ring;
+    if (r.ready) return 0;
+    const size_t bytes = (size_t)5 * (size_t)std::max<int64_t>(c->n_cells, 1) * sizeof(double);
+    GPU_TRY(c, gpu::stream_create(&r.up));
+    GPU_TRY(c, gpu::stream_create(&r.down));
+    for (int k = 0; k < 2; k++) {
+        void* p = nullptr;
+        if (gpu::dev_malloc(&p, bytes) != 0) return fail(c, IBIS_B200_ENOMEM, "out of device memory (snapshot ring)");
+        r.d_up[k] = static_cast<double*>(p);
+        if (gpu::dev_malloc(&p, bytes) != 0) return fail(c, IBIS_B200_ENOMEM, "out of device memory (snapshot ring)");
+        r.d_down[k] = static_cast<double*>(p);
+        GPU_TRY(c, gpu::event_create(&r.uploaded[k]));
+        GPU_TRY(c, gpu::event_create(&r.unpacked[k]));
+        GPU_TRY(c, gpu::event_create(&r.packed[k]));
+        GPU_TRY(c, gpu::event_create(&r.downloaded[k]));
+    }
+    r.ready = true;
+    return 0;
+}
+static void ring_destroy(ibis_b200_ctx* c) {
+    ibis_b200_ctx::SnapshotRing& r = c->ring;
+    if (!r.ready) return;
+    for (int k = 0; k < 2; k++) {
+        gpu::dev_free(r.d_up[k]);
+        gpu::dev_free(r.d_down[k]);
+        gpu::event_destroy(r.uploaded[k]);
+        gpu::event_destroy(r.unpacked[k]);
+        gpu::event_destroy(r.packed[k]);
+        gpu::event_destroy(r.downloaded[k]);
+    }
+    gpu::stream_destroy(r.up);
+    gpu::stream_destroy(r.down);
+    r.ready = false;
+}
+int ibis_b200_pinned_alloc(ibis_b200_ctx* c, int64_t bytes, void** out) {
+    if (!c || !out || bytes < 0) return fail(c, IBIS_B200_EINVAL, "null argument");
+    void* p = nullptr;
+    if (gpu::host_malloc(&p, (size_t)std::max<int64_t>(bytes, 8)) != 0) return fail(c, IBIS_B200_ENOMEM, "out of page-locked host memory");
+    *out = p;
+    return 0;
+}
+int ibis_b200_pinned_free(ibis_b200_ctx* c, void* p) {
+    (void)c;
+    if (p) gpu::host_free(p);
+    return 0;
+}
+int ibis_b200_snapshot_upload_begin(ibis_b200_ctx* c, int slot, const double* T, const double* p, const double* vx,
+                                    const double* vy, const double* vz) {
+    if (slot < 0 || slot > 1) return fail(c, IBIS_B200_EINVAL, "snapshot slot must be 0 or 1");
+    if (!T || !p || !vx || !vy || (c->dim == 3 && !vz)) return fail(c, IBIS_B200_EINVAL, "null host array");
+    int rc = ring_init(c);
+    if (rc) return rc;
+    ibis_b200_ctx::SnapshotRing& r = c->ring;
+    const int64_t n = c->n_cells;
+    // the slot is free once the compute stream has unpacked what it held
+    if (r.up_used[slot]) GPU_TRY(c, gpu::stream_wait_event(r.up, r.unpacked[slot]));
+    const double* src[5] = {T, p, vx, vy, vz};
+    for (int q = 0; q < (vz ? 5 : 4); q++) GPU_TRY(c, gpu::h2d(r.d_up[slot] + q * n, src[q], n * sizeof(double), r.up));
+    GPU_TRY(c, gpu::event_record(r.uploaded[slot], r.up));
+    return 0;
+}
+int ibis_b200_snapshot_upload_end(ibis_b200_ctx* c, int slot, int h) {
+    Buffer* b = get_buf(c, h, BUF_FS);
+    if (!b) return fail(c, IBIS_B200_EHANDLE, "not a FlowStates handle");
+    if (slot < 0 || slot > 1 || !c->ring.ready) return fail(c, IBIS_B200_EINVAL, "snapshot_upload_end without snapshot_upload_begin");
+    ibis_b200_ctx::SnapshotRing& r = c->ring;
+    const int64_t n = c->n_cells;
+    GPU_TRY(c, gpu::stream_wait_event(c->stream, r.uploaded[slot]));
+    if (b->is_dual) { dual* f[7]; comp_ptrs<dual>(b, f); launch_flow_read<dual>(c, r.d_up[slot], n, c->dim == 3, f); }
+    else { double* f[7]; comp_ptrs<double>(b, f); launch_flow_read<double>(c, r.d_up[slot], n, c->dim == 3, f); }
+    GPU_TRY(c, gpu::event_record(r.unpacked[slot], c->stream));
+    r.up_used[slot] = true;
+    return c->last_error.empty() ? 0 : IBIS_B200_ECUDA;
+}
+int ibis_b200_snapshot_download_begin(ibis_b200_ctx* c, int slot, int h, double* T, double* p, double* vx, double* vy, double* vz) {
+    Buffer* b = get_buf(c, h, BUF_FS);
+    if (!b) return fail(c, IBIS_B200_EHANDLE, "not a FlowStates handle");
+    if (slot < 0 || slot > 1) return fail(c, IBIS_B200_EINVAL, "snapshot slot must be 0 or 1");
+    if (!T || !p || !vx || !vy || (c->dim == 3 && !vz)) return fail(c, IBIS_B200_EINVAL, "null host array");
+    int rc = ring_init(c);
+    if (rc) return rc;
+    ibis_b200_ctx::SnapshotRing& r = c->ring;
+    const int64_t n = c->n_cells;
+    // the slot is free once its previous download has left the device
+    if (r.down_used[slot]) GPU_TRY(c, gpu::stream_wait_event(c->stream, r.downloaded[slot]));
+    if (b->is_dual) { dual* f[7]; comp_ptrs<dual>(b, f); launch_flow_write<dual>(c, f, r.d_down[slot], n, c->dim == 3); }
+    else { double* f[7]; comp_ptrs<double>(b, f); launch_flow_write<double>(c, f, r.d_down[slot], n, c->dim == 3); }
+    GPU_TRY(c, gpu::event_record(r.packed[slot], c->stream));
+    GPU_TRY(c, gpu::stream_wait_event(r.down, r.packed[slot]));
+    double* dst[5] = {T, p, vx, vy, vz};
+    for (int q = 0; q < (vz ? 5 : 4); q++) GPU_TRY(c, gpu::d2h(dst[q], r.d_down[slot] + q * n, n * sizeof(double), r.down));
+    GPU_TRY(c, gpu::event_record(r.downloaded[slot], r.down));
+    r.down_used[slot] = true;
+    return c->last_error.empty() ? 0 : IBIS_B200_ECUDA;
+}
+int ibis_b200_snapshot_download_end(ibis_b200_ctx* c, int slot) {
+    if (slot < 0 || slot > 1 || !c->ring.ready || !c->ring.down_used[slot])
+        return fail(c, IBIS_B200_EINVAL, "snapshot_download_end without snapshot_download_begin");
+    GPU_TRY(c, gpu::event_sync(c->ring.downloaded[slot]));
+    return check_pipe_stall(c);
+}
+
 int ibis_b200_cq_upload(ibis_b200_ctx* c, int h, const double* re_, const double* du_) {
     Buffer* b = get_buf(c, h, BUF_CQ);
     if (!b) return fail(c, IBIS_B200_EHANDLE, "not a ConservedQuantities handle");
@@ -1620,12 +1733,25 @@ int ibis_b200_rk_step(ibis_b200_ctx* c, int fs, int cq, int n_stages, const doub
         }
         launch_cons_to_prim<double>(c, uq, fq, c->n_total);                              // :193
     }
+    // dt == NULL and dt_stable == NULL: nothing returns to the host, the step stays asynchronous on the stream
+    // (ibis_b200_rk_last_dt fetches the two values later)
+    if (dt || dt_stable) {
+        double out[2];
+        rc = fetch_scalars(c, SC_DT_STABLE, 2, out);
+        if (dt_stable) *dt_stable = out[0];
+        if (dt) *dt = out[1];
+        if (rc) return rc;
+    }
+    return c->last_error.empty() ? 0 : IBIS_B200_ECUDA;
+}
+
+int ibis_b200_rk_last_dt(ibis_b200_ctx* c, double* dt, double* dt_stable) {
+    if (!c) return fail(c, IBIS_B200_EINVAL, "null argument");
     double out[2];
-    rc = fetch_scalars(c, SC_DT_STABLE, 2, out);
+    int rc = fetch_scalars(c, SC_DT_STABLE, 2, out);
     if (dt_stable) *dt_stable = out[0];
     if (dt) *dt = out[1];
-    if (rc) return rc;
-    return c->last_error.empty() ? 0 : IBIS_B200_ECUDA;
+    return rc;
 }
 
 int ibis_b200_rk_distinct_stages(ibis_b200_ctx* c, int distinct) {

@@ -38,6 +38,12 @@ inline int d2h(void* h, const void* d, size_t bytes, stream_t s) {
 inline int d2d(void* dst, const void* src, size_t bytes, stream_t s) {
     return (int)cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, s);
 }
+typedef cudaEvent_t event_t;
+inline int event_create(event_t* e) { return (int)cudaEventCreateWithFlags(e, cudaEventDisableTiming); }
+inline int event_destroy(event_t e) { return (int)cudaEventDestroy(e); }
+inline int event_record(event_t e, stream_t s) { return (int)cudaEventRecord(e, s); }
+inline int stream_wait_event(stream_t s, event_t e) { return (int)cudaStreamWaitEvent(s, e, 0); }
+inline int event_sync(event_t e) { return (int)cudaEventSynchronize(e); }
 inline const char* error_string(int e) { return cudaGetErrorString((cudaError_t)e); }
 inline int last_error() { return (int)cudaGetLastError(); }
 inline int sm_count(int dev) {
@@ -59,6 +65,12 @@ inline int memset_async(void* p, int v, size_t bytes, stream_t) { memset(p, v, b
 inline int h2d(void* d, const void* h, size_t bytes, stream_t) { memcpy(d, h, bytes); return 0; }
 inline int d2h(void* h, const void* d, size_t bytes, stream_t) { memcpy(h, d, bytes); return 0; }
 inline int d2d(void* dst, const void* src, size_t bytes, stream_t) { memmove(dst, src, bytes); return 0; }
+typedef void* event_t;
+inline int event_create(event_t* e) { *e = nullptr; return 0; }
+inline int event_destroy(event_t) { return 0; }
+inline int event_record(event_t, stream_t) { return 0; }
+inline int stream_wait_event(stream_t, event_t) { return 0; }
+inline int event_sync(event_t) { return 0; }
 inline const char* error_string(int) { return "host emulation error"; }
 inline int last_error() { return 0; }
 inline int sm_count(int) { return 1; }

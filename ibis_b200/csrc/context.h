@@ -117,6 +117,15 @@ struct ibis_b200_ctx {
     // I/O staging (reference AoS <-> internal SoA)
     double* d_stage = nullptr;
     int64_t stage_elems = 0;
+    // snapshot ring (abi.cu): two upload and two download slots of 5 x n_cells doubles, a stream for each direction
+    struct SnapshotRing {
+        bool ready = false;
+        ib::gpu::stream_t up = nullptr, down = nullptr;
+        double* d_up[2] = {nullptr, nullptr};
+        double* d_down[2] = {nullptr, nullptr};
+        ib::gpu::event_t uploaded[2], unpacked[2], packed[2], downloaded[2];
+        bool up_used[2] = {false, false}, down_used[2] = {false, false};
+    } ring;
 
     // explicit solver scratch: k_[stages], k_tmp_, flow_tmp_ (runge_kutta.cpp:45-52)
     std::vector<int> rk_k;            // handle of stage i (all equal when the stages alias)

@@ -134,7 +134,8 @@ __global__ void __launch_bounds__(256) k_count_bad_partial(Comps7<S> fs, long n,
 __global__ void k_rk_dt(const double* d_dt_stable, double cfl, double dt_prev, double t_remaining,
                         double* d_dt) {
     const double a = cfl * d_dt_stable[0];
-    const double b = 1.5 * dt_prev;
+    // dt_prev = NaN: the step the device took last (d_dt still holds it; DBL_MAX before the first step)
+    const double b = 1.5 * (dt_prev != dt_prev ? d_dt[0] : dt_prev);
     const double dt_startup = (b < a) ? b : a;                 // Ibis::min(a, b)
     d_dt[0] = (t_remaining < dt_startup) ? t_remaining : dt_startup;
 }

@@ -238,6 +238,10 @@ class Library:
             "ibis_b200_set_cell_vertices": [vp, vp, vp], "ibis_b200_set_vertex_positions": [vp, vp],
             "ibis_b200_move_vertices": [vp, d, i], "ibis_b200_get_vertex_positions": [vp, vp], "ibis_b200_debug_face_velocities": [vp, vp],
             "ibis_b200_rk_step": [vp, i, i, i, vp, vp, d, d, d, C.POINTER(d), C.POINTER(d)],
+            "ibis_b200_rk_last_dt": [vp, C.POINTER(d), C.POINTER(d)],
+            "ibis_b200_pinned_alloc": [vp, i64, C.POINTER(vp)], "ibis_b200_pinned_free": [vp, vp],
+            "ibis_b200_snapshot_upload_begin": [vp, i, vp, vp, vp, vp, vp], "ibis_b200_snapshot_upload_end": [vp, i, i],
+            "ibis_b200_snapshot_download_begin": [vp, i, i, vp, vp, vp, vp, vp], "ibis_b200_snapshot_download_end": [vp, i],
             "ibis_b200_rk_residual_norms": [vp, vp], "ibis_b200_rk_distinct_stages": [vp, i],
             "ibis_b200_jfnk_set_dual": [vp, i, i, i],
             "ibis_b200_jfnk_set_vector": [vp, i, i, d, i],
@@ -382,6 +386,9 @@ class Context:
 
     def close(self):
         if self.h:
+            for p in getattr(self, "_pinned", []):
+                self.lib.ibis_b200_pinned_free(self.h, p)
+            self._pinned = []
             self.lib.ibis_b200_destroy(self.h)
             self.h = C.c_void_p()
 
@@ -474,6 +481,36 @@ class Context:
         ptrs = [_ptr(x) for x in arrs] + ([None] if dim == 2 else [])
         self._ck(self.lib.ibis_b200_flow_write_native(self.h, h, *ptrs), "flow_write_native")
         return arrs
+
+    # snapshot ring (include/ibis_b200.h): native_binary arrays in and out while the device computes
+    def pinned_array(self, shape):
+        """a page-locked float64 host array owned by this context (freed by close())"""
+        n = int(np.prod(shape))
+        p = C.c_void_p()
+        self._ck(self.lib.ibis_b200_pinned_alloc(self.h, n * 8, C.byref(p)), "pinned_alloc")
+        self._pinned = getattr(self, "_pinned", [])
+        self._pinned.append(p)
+        buf = (C.c_double * n).from_address(p.value)
+        return np.frombuffer(buf, dtype=np.float64).reshape(shape)
+
+    def _rows(self, a):
+        """(5 or 4, n_cells) array -> the five row pointers T p vx vy vz (vz NULL in 2-D)"""
+        assert a.dtype == np.float64 and a.flags.c_contiguous and a.shape[1] == self.n_cells
+        base, row = a.ctypes.data, self.n_cells * 8
+        ptrs = [C.c_void_p(base + q * row) for q in range(a.shape[0])]
+        return ptrs + [None] * (5 - len(ptrs))
+
+    def snapshot_upload_begin(self, slot, arrays):
+        self._ck(self.lib.ibis_b200_snapshot_upload_begin(self.h, int(slot), *self._rows(arrays)), "snapshot_upload_begin")
+
+    def snapshot_upload_end(self, slot, fs):
+        self._ck(self.lib.ibis_b200_snapshot_upload_end(self.h, int(slot), fs), "snapshot_upload_end")
+
+    def snapshot_download_begin(self, slot, fs, arrays):
+        self._ck(self.lib.ibis_b200_snapshot_download_begin(self.h, int(slot), fs, *self._rows(arrays)), "snapshot_download_begin")
+
+    def snapshot_download_end(self, slot):
+        self._ck(self.lib.ibis_b200_snapshot_download_end(self.h, int(slot)), "snapshot_download_end")
 
     def copy(self, dst, src):
         self._ck(self.lib.ibis_b200_copy(self.h, dst, src), "copy")
@@ -595,6 +632,21 @@ class Context:
         self._ck(self.lib.ibis_b200_rk_step(self.h, fs, cq, len(bb), _ptr(a), _ptr(bb), float(cfl),
                                             float(dt_prev), float(t_remaining), C.byref(dt), C.byref(dts)),
                  "rk_step")
+        return dt.value, dts.value
+
+    def rk_step_async(self, fs, cq, a_rows, b, cfl, t_remaining):
+        """one RungeKutta::take_step enqueued on the stream, nothing read back: dt_prev is the previous step's dt on
+        the device; rk_last_dt() fetches (dt, dt_stable) of the last step"""
+        a = np.array([x for row in a_rows for x in row], dtype=np.float64)
+        if a.size == 0:
+            a = np.zeros(1)
+        bb = _as(b, np.float64)
+        self._ck(self.lib.ibis_b200_rk_step(self.h, fs, cq, len(bb), _ptr(a), _ptr(bb), float(cfl),
+                                            float("nan"), float(t_remaining), None, None), "rk_step")
+
+    def rk_last_dt(self):
+        dt, dts = C.c_double(0), C.c_double(0)
+        self._ck(self.lib.ibis_b200_rk_last_dt(self.h, C.byref(dt), C.byref(dts)), "rk_last_dt")
         return dt.value, dts.value
 
     def rk_residual_norms(self):

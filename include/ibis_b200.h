@@ -211,6 +211,26 @@ int ibis_b200_vec_download(ibis_b200_ctx*, int vec, double* x);
 int ibis_b200_flow_read_native(ibis_b200_ctx*, int fs, const double* T, const double* p, const double* vx,
                                const double* vy, const double* vz);
 int ibis_b200_flow_write_native(ibis_b200_ctx*, int fs, double* T, double* p, double* vx, double* vy, double* vz);
+/* Snapshot ring (the native flow IO fast path).  The same native_binary arrays, moved
+ * WHILE the device computes: two upload and two download slots of device staging, one copy stream per direction
+ * beside the compute stream, events between them.  Host arrays must be page-locked (ibis_b200_pinned_alloc) and
+ * stay untouched between a begin and its end.
+ *   upload_begin(slot, arrays)        the H2D copy of a snapshot starts on the upload stream; returns at once
+ *   upload_end(slot, fs)              the compute stream waits for it and unpacks into fs (NativeBinaryInput::read +
+ *                                     update_thermo_from_pT, native.cpp:280-336); returns at once
+ *   download_begin(slot, fs, arrays)  the compute stream packs fs into the slot, the download stream copies it out
+ *                                     (NativeBinaryOutput::write's arrays, native.cpp:200-262); returns at once
+ *   download_end(slot)                the host waits until that snapshot has landed in the host arrays
+ * With two slots, snapshot k + 1 arrives and snapshot k - 1 leaves while step k runs (bench.py's e2e loop;
+ * ibis_b200/native_io.py writes the reference's io/flow/NNNN files from the landed arrays). */
+int ibis_b200_pinned_alloc(ibis_b200_ctx*, int64_t bytes, void** host_ptr);
+int ibis_b200_pinned_free(ibis_b200_ctx*, void* host_ptr);
+int ibis_b200_snapshot_upload_begin(ibis_b200_ctx*, int slot, const double* T, const double* p, const double* vx,
+                                    const double* vy, const double* vz);
+int ibis_b200_snapshot_upload_end(ibis_b200_ctx*, int slot, int fs);
+int ibis_b200_snapshot_download_begin(ibis_b200_ctx*, int slot, int fs, double* T, double* p, double* vx, double* vy,
+                                      double* vz);
+int ibis_b200_snapshot_download_end(ibis_b200_ctx*, int slot);
 int ibis_b200_copy(ibis_b200_ctx*, int dst, int src);          /* deep_copy, same kind */
 int ibis_b200_zero(ibis_b200_ctx*, int buf);
 
@@ -283,7 +303,11 @@ int ibis_b200_debug_division_check(ibis_b200_ctx*, int64_t n, uint64_t seed, uin
  * concatenated), b (stages): stage evaluations, dt estimate
  * (dt = min(cfl*dt_stable, 1.5*dt_prev, t_max - t), runge_kutta.cpp:108-119), stage updates
  * and final update, entirely on the device stream.  fs/cq are the solver's flow_ /
- * conserved_quantities_.  Returns dt and dt_stable. */
+ * conserved_quantities_.  Returns dt and dt_stable.
+ * Asynchronous form: with dt == NULL and dt_stable == NULL nothing is read back and the call returns as soon as
+ * the step is enqueued; with dt_prev = NaN the "1.5 * dt_prev" of runge_kutta.cpp:113 takes the dt of the previous
+ * ibis_b200_rk_step from the device (DBL_MAX before the first).  A solver that plots / prints every k steps runs k
+ * such steps back to back and then calls ibis_b200_rk_last_dt (which synchronises). */
 int ibis_b200_rk_step(ibis_b200_ctx*, int fs, int cq, int n_stages, const double* a,
                       const double* b, double cfl, double dt_prev, double t_remaining,
                       double* dt, double* dt_stable);
@@ -293,6 +317,7 @@ int ibis_b200_rk_step(ibis_b200_ctx*, int fs, int cq, int n_stages, const double
  * to two stages are unaffected; for three or more the reference therefore does not integrate the
  * tableau it was given.  The default reproduces the reference bit for bit; distinct = 1 gives
  * each stage its own array (the scheme the tableau describes). */
+int ibis_b200_rk_last_dt(ibis_b200_ctx*, double* dt, double* dt_stable);
 int ibis_b200_rk_distinct_stages(ibis_b200_ctx*, int distinct);
 /* RungeKutta::L2_norms = k_[0].L2_norms() of the last rk_step (runge_kutta.cpp:264) */
 int ibis_b200_rk_residual_norms(ibis_b200_ctx*, double out[6]);

@@ -404,7 +404,7 @@ template void launch_count_bad<dual>(ibis_b200_ctx*, dual* const*, int64_t, doub
 void launch_rk_dt(ibis_b200_ctx* c, const double* d_dt_stable, double cfl, double dt_prev,
                   double t_remaining, double* d_dt) {
     const double a = cfl * d_dt_stable[0];
-    const double b = 1.5 * dt_prev;
+    const double b = 1.5 * (dt_prev != dt_prev ? d_dt[0] : dt_prev);
     const double s = (b < a) ? b : a;
     d_dt[0] = (t_remaining < s) ? t_remaining : s;
     c->launches++;

@@ -146,7 +146,13 @@ def main():
         for k, v in rh.read_flow(work, int(flow_dirs[-1]), dim).items():
             final["final_" + k] = v
         with open(os.path.join(work, "io/flow", flow_dirs[-1], "meta_data.json")) as f:
-            final["final_time"] = np.array(json.load(f)["time"])
+            text = f.read()
+        final["final_time"] = np.array(json.loads(text)["time"])
+        # the bytes NativeBinaryOutput::write put on disk beside the arrays (tests/test_flow_io.py)
+        final["final_meta_text"] = np.array(text)
+        final["final_dir"] = np.array(flow_dirs[-1])
+        with open(os.path.join(work, "io/flow/flows")) as f:
+            final["flows_text"] = np.array(f.read())
         finals[name] = {k[6:]: v for k, v in final.items() if k.startswith("final_") and k != "final_time"}
         np.savez_compressed(os.path.join(dst, "expected.npz"), **final)
         print(name, "rc", rc, "snapshots", len(flow_dirs), "cells", len(final["final_T"]), "t", float(final["final_time"]))

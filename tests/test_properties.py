@@ -97,3 +97,34 @@ def test_an_argument_error_does_not_poison_the_context():
     assert np.isfinite(ctx.cq_download(dq)[:g.n_cells]).all()
     assert ctx.count_bad_cells(fs) == 0
     ctx.close()
+
+
+def test_asynchronous_steps_equal_synchronous_steps():
+    """ibis_b200_rk_step with dt == NULL (nothing read back, dt_prev chained on the device) takes the same steps as
+    the form that returns dt every step: same dt sequence end point, same state bit for bit."""
+    import sys
+    import numpy as np
+    import cases
+    from emu_util import emu_lib
+    from ibis_b200 import config as cfg
+    from ibis_b200.lib import Context
+    mesh, config, g, prim = cases.build_case("box3d_ausmdv")
+    tab = cfg.BUTCHER["ssp-rk3"]
+    out = []
+    for mode in ("sync", "async"):
+        ctx = Context(g, config, lib_path=emu_lib())
+        fs, cq = ctx.fs_create(), ctx.cq_create()
+        ctx.fs_upload(fs, prim)
+        ctx.prim_to_cons(cq, fs)
+        dt = sys.float_info.max
+        for _ in range(4):
+            if mode == "sync":
+                dt, dts = ctx.rk_step(fs, cq, tab["a"], tab["b"], 0.5, dt, 1.0)
+            else:
+                ctx.rk_step_async(fs, cq, tab["a"], tab["b"], 0.5, 1.0)
+        if mode == "async":
+            dt, dts = ctx.rk_last_dt()
+        out.append((dt, dts, ctx.fs_download(fs)))
+        ctx.close()
+    assert out[0][0] == out[1][0] and out[0][1] == out[1][1]
+    assert np.array_equal(out[0][2], out[1][2])
