@@ -447,6 +447,7 @@ int ibis_b200_create(ibis_b200_ctx** out, const ibis_b200_grid_desc* gd_ref, con
     if (const char* e = getenv("IBIS_B200_DUAL_SIDES")) c->dual_sides = e[0] != '0';
     if (const char* e = getenv("IBIS_B200_RK_UNFUSED")) c->rk_unfused = e[0] == '1';
     if (const char* e = getenv("IBIS_B200_PREFETCH")) c->pipe_prefetch = std::max(0, atoi(e));
+    if (const char* e = getenv("IBIS_B200_F_STAGES")) c->pipe_f_stages = std::max(0, atoi(e));
     c->bc_actions.assign(cfg->bc_actions, cfg->bc_actions + cfg->n_bc_actions);
     c->cfg.bc_actions = nullptr;
     c->dim = gd->dim;

@@ -102,6 +102,7 @@ struct ibis_b200_ctx {
     ib::dual* sidesP_d = nullptr;
     int64_t p_total = 0;                 // records in a side-state array (all owned tiles)
     int pipe_prefetch = 2;               // IBIS_B200_PREFETCH: L2 prefetch distance (tiles) of the pipelined kernels, 0 = off
+    int pipe_f_stages = 0;               // input stages of pass F' (0: default; IBIS_B200_F_STAGES)
     bool use_sides = true;               // IBIS_B200_SIDES=0: second order through the gather path (grad + limiter arrays)
     bool dual_sides = true;               // IBIS_B200_DUAL_SIDES=0: dual-number evaluations through the gather path
     int last_fs = 0;                     // FlowStates handle of the last real evaluation (debug_gradients)

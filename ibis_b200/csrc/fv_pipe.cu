@@ -733,7 +733,8 @@ static void launch_flux_pipe_k(ibis_b200_ctx* c, const FvArgs<S>& A) {
     const size_t in_b = flux_in_bytes<S>(A.g.p_cap, A.g.freca_stride);
     const size_t fb_b = flux_fb_bytes<S>(A.g.tile_cap, A.g.frec_stride, A.g.tile, A.dt_out != nullptr);
     // three input stages cover the load latency; the rest of shared memory holds flux buffers
-    int nsi = 3;
+    // (IBIS_B200_F_STAGES: sweep knob)
+    int nsi = c->pipe_f_stages > 0 ? c->pipe_f_stages : 3;
     int nfb = PIPE_SMEM_BUDGET > (size_t)nsi * in_b ? (int)((PIPE_SMEM_BUDGET - (size_t)nsi * in_b) / fb_b) : 0;
     if (nfb < 3) {
         nsi = 2;
