@@ -81,6 +81,16 @@ __device__ __forceinline__ bool pipe_timed_out(long long t0, unsigned int* dbg, 
     }
     return false;
 }
+// Ordering between the warps of a block (flag published after data / data read after flag): an acquire-release fence
+// at block scope.  __threadfence_block() is the sequentially consistent one (MEMBAR.SC.CTA), which every item paid
+// for several times on its critical path.
+__device__ __forceinline__ void pipe_fence() {
+#ifdef IBIS_PIPE_SC_FENCE
+    __threadfence_block();
+#else
+    asm volatile("fence.acq_rel.cta;" ::: "memory");
+#endif
+}
 // Waits poll with a growing sleep instead of suspending on the barrier: a stage barrier sees some forty events per
 // phase (one per bulk copy), and an event-driven sleep wakes every waiting warp at each of them -- measured, that
 // cost more issue slots than the work itself.
@@ -118,14 +128,14 @@ __device__ __forceinline__ bool pipe_spin_ge(const int* p, int target, unsigned 
     bool ok = *reinterpret_cast<const volatile int*>(p) >= target;
     if (!ok) ok = pipe_spin_slow(p, target, dbg, kind, k);
     ok = __all_sync(0xffffffffu, ok);
-    __threadfence_block();
+    pipe_fence();
     return ok;
 }
 // the same for a single thread (the loaders of pass F' run on one lane)
 __device__ __forceinline__ bool pipe_spin_ge_1(const int* p, int target, unsigned int* dbg, int kind, int k) {
     bool ok = *reinterpret_cast<const volatile int*>(p) >= target;
     if (!ok) ok = pipe_spin_slow(p, target, dbg, kind, k);
-    __threadfence_block();
+    pipe_fence();
     return ok;
 }
 // next item of the block's ordered work queue
@@ -292,7 +302,7 @@ __global__ void __launch_bounds__(32 * (IBIS_PIPE_F_WARPS + IBIS_PIPE_F_LOADERS)
                 meta[o][0] = nc;
                 meta[o][1] = c0;
                 meta[o][2] = t;
-                __threadfence_block();
+                pipe_fence();
                 *reinterpret_cast<volatile int*>(&fb_tile[o]) = k;
                 *reinterpret_cast<volatile int*>(&stage_tile[s]) = k;
                 ac::mbar_arrive_expect_tx(&full_in[s], (uint32_t)h4 * RB + (uint32_t)g.freca_stride);
@@ -348,10 +358,10 @@ __global__ void __launch_bounds__(32 * (IBIS_PIPE_F_WARPS + IBIS_PIPE_F_LOADERS)
                     // once every item of the tile has its operands the stage is the loader's again
                     __syncwarp();
                     if (lane == 0) {
-                        __threadfence_block();
+                        pipe_fence();
                         if (atomicAdd(&reads_done[s], 1) == NCH - 1) {
                             reads_done[s] = 0;
-                            __threadfence_block();
+                            pipe_fence();
                             *reinterpret_cast<volatile int*>(&stage_free[s]) = k;
                         }
                     }
@@ -360,7 +370,7 @@ __global__ void __launch_bounds__(32 * (IBIS_PIPE_F_WARPS + IBIS_PIPE_F_LOADERS)
             }
             __syncwarp();
             if (lane == 0) {
-                __threadfence_block();
+                pipe_fence();
                 atomicAdd(&done_items[o], 1);
             }
         } else {
@@ -393,11 +403,11 @@ __global__ void __launch_bounds__(32 * (IBIS_PIPE_F_WARPS + IBIS_PIPE_F_LOADERS)
             ac::fence_proxy_async();            // reads of the cell record precede the next bulk copy into the buffer
             __syncwarp();
             if (lane == 0) {
-                __threadfence_block();
+                pipe_fence();
                 if (atomicAdd(&done_items[o], 1) == P - 1) {
                     // the tile's last item: the buffer goes back to the loader
                     done_items[o] = 0;
-                    __threadfence_block();
+                    pipe_fence();
                     *reinterpret_cast<volatile int*>(&fb_done[o]) = k;
                 }
             }
@@ -543,7 +553,7 @@ __global__ void __launch_bounds__(32 * (IBIS_PIPE_G_WARPS + IBIS_PIPE_G_LOADERS 
                 const int home = pl[0], n_stage = pl[1];
                 if (n_stage > 0) ac::bulk_s2g(A.sidesP + (size_t)home * SIDE_REC, stg, (uint32_t)n_stage * (uint32_t)SIDE_REC * (uint32_t)sizeof(S));
                 ac::bulk_commit_wait_read();               // the store warp has nothing else to do than to see it drained
-                __threadfence_block();
+                pipe_fence();
                 *reinterpret_cast<volatile int*>(&out_done[o]) = k;
             }
             __syncwarp();
@@ -590,7 +600,7 @@ __global__ void __launch_bounds__(32 * (IBIS_PIPE_G_WARPS + IBIS_PIPE_G_LOADERS 
             const bool bulk_own = ((size_t)c0 * sizeof(S)) % 16 == 0;
             if (lane == 0) {
                 nc_of[s] = nc;
-                __threadfence_block();
+                pipe_fence();
                 *reinterpret_cast<volatile int*>(&stage_tile[s]) = k;
                 ac::mbar_arrive_expect_tx(&full[s], (uint32_t)WD_BYTES + (uint32_t)g.grec_stride +
                                                         (bulk_own ? 5u * (uint32_t)T * (uint32_t)sizeof(S) : 0u));
@@ -645,20 +655,20 @@ __global__ void __launch_bounds__(32 * (IBIS_PIPE_G_WARPS + IBIS_PIPE_G_LOADERS 
         __syncwarp();
         int d = 0;
         if (lane == 0) {
-            __threadfence_block();
+            pipe_fence();
             d = atomicAdd(&done_tasks[s], 1);
         }
         d = __shfl_sync(0xffffffffu, d, 0);
         if (d == N_TASKS - 1) {
             // the tile's last item: its side records are complete in the staging buffer.  Their destination moves next
             // to them, the input stage goes back to the loaders, and the store warp takes over the buffer
-            __threadfence_block();
+            pipe_fence();
             if (lane == 0) {
                 int* pl = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(stg) + off_dst);
                 pl[0] = R.hdr[5];
                 pl[1] = R.hdr[3];
                 done_tasks[s] = 0;
-                __threadfence_block();
+                pipe_fence();
                 *reinterpret_cast<volatile int*>(&stage_free[s]) = k;
                 *reinterpret_cast<volatile int*>(&out_ready[o]) = k;
             }
