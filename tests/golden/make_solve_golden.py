@@ -44,7 +44,12 @@ def main():
     names = sys.argv[1:] or list(sc.SOLVE_CASES)
     # ONE OpenMP thread: the reference's parallel_reduce then sums in index order, which makes the
     # fixtures independent of the machine they were generated on
-    rl = rh.RefLib.get(1)
+    # IBIS_REF_THREADS=8 python tests/golden/make_solve_golden.py steady_wedge2d  ->  solve_steady_wedge2d_t8.npz:
+    # the same run with the reference's reductions summed by eight threads, i.e. in another order.  The difference
+    # between the two fixtures is the reference's OWN spread on this case (tests/test_gpu_solvers.py).
+    n_threads = int(os.environ.get("IBIS_REF_THREADS", "1"))
+    suffix = "" if n_threads == 1 else f"_t{n_threads}"
+    rl = rh.RefLib.get(n_threads)
     for name in names:
         mesh, config, g, prim0, snap = sc.build_solve_case(name)
         case_dir = os.path.join("/tmp/ibis_solve_golden", name)
@@ -63,7 +68,7 @@ def main():
                 rows = [ln.split() for ln in open(p).read().strip().split("\n")[1:] if ln.strip()]
                 if rows:
                     out["log_" + log.split(".")[0]] = np.array(rows, dtype=np.float64)
-        np.savez_compressed(os.path.join(HERE, "solve_" + name + ".npz"), **out)
+        np.savez_compressed(os.path.join(HERE, "solve_" + name + suffix + ".npz"), **out)
         print(name, "rc", rc, "cells", g.n_cells, "snapshots", flow_dirs, "t", float(out["final_time"]))
 
 

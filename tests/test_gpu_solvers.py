@@ -27,7 +27,21 @@ def _require_cuda():
 # Parity at 1e-9 is therefore checked with the reference's summation order (IBIS_B200_ORDERED_DOT=1:
 # dot / norm2 summed in index order, as the one-thread reference that made the fixture); the default
 # two-stage tree reduction is checked at the sensitivity the case has.
-ORDER_SENSITIVE = {"steady_wedge2d": 2e-2}
+#
+# How sensitive "the case" is, is measured on the reference itself: tests/golden/solve_steady_wedge2d_t8.npz is the same
+# run of the compiled reference with EIGHT OpenMP threads summing its reductions (make_solve_golden.py,
+# IBIS_REF_THREADS=8).  The two reference fixtures differ by up to 3.7e-4 of the field's scale after the run's eleven
+# steps; the product with its production reductions is held to fifty times the reference's own spread.
+def _reference_spread(name):
+    import os
+    a = np.load(os.path.join(solve_parity.GOLDEN, f"solve_{name}.npz"))
+    b = np.load(os.path.join(solve_parity.GOLDEN, f"solve_{name}_t8.npz"))
+    vscale = np.sqrt(a["final_vx"] ** 2 + a["final_vy"] ** 2).max()
+    return max(np.abs(a[k] - b[k]).max() / (vscale if k.startswith("final_v") else np.abs(a[k]).max())
+               for k in ("final_T", "final_p", "final_vx", "final_vy"))
+
+
+ORDER_SENSITIVE = {"steady_wedge2d": 50.0 * _reference_spread("steady_wedge2d")}
 
 
 @pytest.mark.parametrize("name", sorted(sc.SOLVE_CASES))
