@@ -39,6 +39,18 @@ def _residual(g, prim, config, monkeypatch, sides, dual=False):
     return out, dt
 
 
+def test_sides_path_equals_gather_path_on_a_box_that_is_not_a_power_of_two(monkeypatch):
+    """200^3 = 8 M cells (the per-rank size of the 8-GPU bench): the Morton bricks do not tile the box evenly"""
+    import torch
+    assert torch.cuda.is_available()
+    g = BoxGrid(200)
+    prim = cases.perturbed_state(g, 3)
+    a, dta = _residual(g, prim, _config("ausmdv"), monkeypatch, "1")
+    b, dtb = _residual(g, prim, _config("ausmdv"), monkeypatch, "0")
+    assert np.array_equal(a, b) and dta == dtb
+    assert np.isfinite(a[:g.n_cells]).all()
+
+
 @pytest.mark.parametrize("flux", ["ausmdv", "ldfss2"])
 def test_sides_path_equals_gather_path_on_two_million_cells(flux, monkeypatch):
     import torch
@@ -55,7 +67,11 @@ def test_sides_path_equals_gather_path_on_two_million_cells(flux, monkeypatch):
         assert np.isfinite(du_[:g.n_cells]).all()
 
 
-def test_reference_itself_on_a_64_cubed_box(monkeypatch):
+@pytest.mark.parametrize("n", [64, 128])
+def test_reference_itself_on_a_whole_box(n, monkeypatch):
+    """The compiled reference (Kokkos-OpenMP, oracle/_ref) evaluates the bench configuration on the n^3 box on this
+    machine's host cores; the CUDA residual must equal it bit for bit.  128^3 = 2.1 M cells is the box the bench's
+    reference arm times."""
     import torch
     assert torch.cuda.is_available()
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -64,7 +80,6 @@ def test_reference_itself_on_a_64_cubed_box(monkeypatch):
         pytest.skip("oracle/_ref/libibis_ref.so did not travel to this box")
     from ibis_b200 import grid as gridmod
     from ibis_b200 import su2
-    n = 64
     mesh = su2.box_hex(n)
     g = gridmod.build_grid(mesh, ["west", "east", "south", "north", "bottom", "top"])
     path = "/tmp/test_scale_box.su2"
