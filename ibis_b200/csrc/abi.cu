@@ -321,6 +321,8 @@ int compute_dudt_impl(ibis_b200_ctx* c, Buffer* fs, Buffer* dudt, bool allow_rec
         launch_bc(c, A, IBIS_B200_PHASE_PRE_RECONSTRUCTION);
         launch_grad_sides(c, A, 2);
         launch_flux_tile(c, A);
+        rc = comm::halo_exchange_join(c);              // the pushes (side stream) have read the flow state
+        if (rc) return rc;
         if (!c->last_error.empty()) return IBIS_B200_ECUDA;
         return 0;
     }

@@ -4,6 +4,8 @@
 #include <string>
 #include <vector>
 
+#include <cstdlib>
+
 #include "comm.h"
 
 namespace ib {
@@ -261,9 +263,37 @@ int halo_exchange(ibis_b200_ctx* c, S* const* fs) {
     return c->last_error.empty() ? 0 : IBIS_B200_ECUDA;
 }
 bool halo_split(const ibis_b200_ctx* c) { return c->halo.p2p && c->halo.n_peers > 0 && c->n_ranks > 1; }
+// The overlapped exchange: the pushes read the flow state and write into the peers' memory, nothing this rank's
+// evaluation waits for -- they go onto a side stream (forked from the compute stream by an event) and run BESIDE the
+// early tiles of pass G' (the persistent kernel leaves registers and thread slots free on every SM; the push kernels
+// use no shared memory).  halo_exchange_join makes the compute stream wait for them before the flow state is
+// overwritten (end of the evaluation).  IBIS_B200_PUSH_STREAM=0 keeps them on the compute stream.
 template <typename S>
 int halo_exchange_begin(ibis_b200_ctx* c, S* const* fs) {
-    return halo_split(c) ? halo_push_p2p<S>(c, fs) : 0;
+    if (!halo_split(c)) return 0;
+    Halo& h = c->halo;
+    static const bool side = !(getenv("IBIS_B200_PUSH_STREAM") && getenv("IBIS_B200_PUSH_STREAM")[0] == '0');
+    if (!side) return halo_push_p2p<S>(c, fs);
+    if (!h.side_ready) {
+        if (gpu::stream_create(&h.push_stream) != 0 || gpu::event_create(&h.fork) != 0 || gpu::event_create(&h.pushed) != 0)
+            return comm_fail(c, "halo exchange: cannot create the push stream");
+        h.side_ready = true;
+    }
+    if (gpu::event_record(h.fork, c->stream) != 0 || gpu::stream_wait_event(h.push_stream, h.fork) != 0)
+        return comm_fail(c, "halo exchange: fork failed");
+    gpu::stream_t main_stream = c->stream;
+    c->stream = h.push_stream;                       // the launchers take the context's stream
+    int rc = halo_push_p2p<S>(c, fs);
+    c->stream = main_stream;
+    if (gpu::event_record(h.pushed, h.push_stream) != 0) return comm_fail(c, "halo exchange: join event failed");
+    h.push_pending = true;
+    return rc;
+}
+int halo_exchange_join(ibis_b200_ctx* c) {
+    Halo& h = c->halo;
+    if (!h.push_pending) return 0;
+    h.push_pending = false;
+    return gpu::stream_wait_event(c->stream, h.pushed) != 0 ? comm_fail(c, "halo exchange: join failed") : 0;
 }
 template <typename S>
 int halo_exchange_end(ibis_b200_ctx* c, S* const* fs) {

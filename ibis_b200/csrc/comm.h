@@ -30,6 +30,9 @@ int halo_exchange_begin(ibis_b200_ctx* c, S* const* fs);
 template <typename S>
 int halo_exchange_end(ibis_b200_ctx* c, S* const* fs);
 bool halo_split(const ibis_b200_ctx* c);
+// the compute stream waits for the pushes of halo_exchange_begin (they run on a side stream): call before the flow
+// state they read is overwritten
+int halo_exchange_join(ibis_b200_ctx* c);
 // peer-memory (NVLink P2P) data path: export this rank's receive allocation, map a peer's, switch on
 int p2p_export(ibis_b200_ctx* c, void* handle64, int64_t* n_recv);
 int p2p_import(ibis_b200_ctx* c, int peer_index, const void* handle64, int64_t peer_n_recv,

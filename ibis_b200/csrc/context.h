@@ -49,6 +49,10 @@ struct Halo {
     std::vector<int> peer_my_slot;             // my index in the peer's peer list (its flag for me)
     unsigned* d_counters = nullptr;            // last-block counters, one per peer
     unsigned long long iter = 0;               // exchanges done (same on every rank)
+    // the pushes of the overlapped exchange run on their own stream, beside the early tiles of pass G'
+    ib::gpu::stream_t push_stream = nullptr;
+    ib::gpu::event_t fork, pushed;
+    bool side_ready = false, push_pending = false;
 };
 
 }  // namespace ib

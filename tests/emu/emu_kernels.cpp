@@ -588,6 +588,7 @@ template int halo_exchange_begin<double>(ibis_b200_ctx*, double* const*);
 template int halo_exchange_begin<dual>(ibis_b200_ctx*, dual* const*);
 template int halo_exchange_end<double>(ibis_b200_ctx*, double* const*);
 template int halo_exchange_end<dual>(ibis_b200_ctx*, dual* const*);
+int halo_exchange_join(ibis_b200_ctx*) { return 0; }
 bool halo_split(const ibis_b200_ctx*) { return true; }   // the emulation always takes the early / late order
 int p2p_export(ibis_b200_ctx*, void*, int64_t*) { return IBIS_B200_ECOMM; }
 int p2p_import(ibis_b200_ctx*, int, const void*, int64_t, int64_t, int) { return IBIS_B200_ECOMM; }
