@@ -29,6 +29,37 @@ def hot():
     for _ in range(2):
         dt, _ = ctx.rk_step(fs, cq, tab["a"], tab["b"], 0.5, dt, 1.0)
     assert ctx.count_bad_cells(fs) == 0
+    # round 2: asynchronous steps, the snapshot ring (two copy streams), a dual evaluation through the pipelined
+    # kernels, one GMRES iteration
+    host = [ctx.pinned_array((5, ctx.n_cells)) for _ in range(3)]
+    for q, a in enumerate(ctx.flow_write_native(fs)):
+        host[0][q] = a
+    ctx.snapshot_upload_begin(0, host[0])
+    for k in range(4):
+        ctx.snapshot_upload_end(k & 1, fs)
+        if k < 3:
+            ctx.snapshot_upload_begin((k & 1) ^ 1, host[0])
+        ctx.prim_to_cons(cq, fs)
+        ctx.rk_step_async(fs, cq, tab["a"], tab["b"], 0.5, 1.0)
+        if k >= 2:
+            ctx.snapshot_download_end(k & 1)
+        ctx.snapshot_download_begin(k & 1, fs, host[1 + (k & 1)])
+    ctx.snapshot_download_end(0)
+    ctx.snapshot_download_end(1)
+    assert np.isfinite(host[1]).all() and np.isfinite(host[2]).all() and ctx.rk_last_dt()[0] > 0
+    n = ctx.n_cells
+    fd, qd, td, dd = ctx.fs_create(dual=True), ctx.cq_create(dual=True), ctx.cq_create(dual=True), ctx.cq_create(dual=True)
+    ctx.fs_upload(fd, prim, 1e-3 * prim)
+    ctx.prim_to_cons(qd, fd)
+    v, w, basis = ctx.vec_create(n * 5), ctx.vec_create(n * 5), ctx.basis_create(n * 5, 3)
+    ctx.vec_upload(v, np.full(n * 5, 1.0 / np.sqrt(n * 5.0)))
+    ctx.basis_set_col(basis, 0, v)
+    for j in range(2):
+        ctx.jfnk_set_dual(qd, v, td)
+        ctx.cons_to_prim(td, fd)
+        ctx.compute_dudt(fd, dd, True)
+        ctx.jfnk_set_vector(dd, v, 1e-4, w)
+        assert np.isfinite(ctx.arnoldi_mgs(basis, j, w, v)).all()
     ctx.close()
     print("memcheck walk (hot path) ok")
 
