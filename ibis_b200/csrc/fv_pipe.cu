@@ -46,9 +46,6 @@
 #ifndef IBIS_PIPE_G_SPLITVEL
 #define IBIS_PIPE_G_SPLITVEL 0    // 1: a velocity item of pass G' covers 32 cells (one pass) instead of the whole tile
 #endif
-#ifndef IBIS_PIPE_G_PAIR
-#define IBIS_PIPE_G_PAIR 0        // 1: pass G' takes two variables of a cell per pass where it can (shared table loads)
-#endif
 #ifndef IBIS_PIPE_PREFETCH
 #define IBIS_PIPE_PREFETCH 6      // a loader pulls a tile's data into L2 this many tiles (a multiple of its stride) ahead
 #endif
@@ -443,119 +440,6 @@ __host__ __device__ inline size_t grad_out_bytes(int stage_cap) {
     return ((size_t)stage_cap * SIDE_REC * sizeof(S) + 16 + 127) / 128 * 128;
 }
 
-#if IBIS_PIPE_G_PAIR
-// Two variables of one cell at once: the WLS weights, the face offsets and the neighbour / staging indices are read
-// once for both, and two independent fp64 dependency chains are in flight.  Per variable exactly the operations of
-// var_to_faces, in its order (the streams only interleave).
-template <int DIM, int NF, typename TT, typename S>
-__device__ __forceinline__ void var2_to_faces(const S& ua, const S* una, const S& ub, const S* unb, const TT& Tt, double eps,
-                                              bool limit, S* ra, S* rb) {
-    S gxa = S(0.0), gya = S(0.0), gza = S(0.0), mina = ua, maxa = ua;
-    S gxb = S(0.0), gyb = S(0.0), gzb = S(0.0), minb = ub, maxb = ub;
-#pragma unroll
-    for (int j = 0; j < NF; j++) {
-        const double w0 = Tt.W(j, 0), w1 = Tt.W(j, 1), w2 = (DIM == 3) ? Tt.W(j, 2) : 0.0;
-        const S da = una[j] - ua, db = unb[j] - ub;
-        gxa += w0 * da; gxb += w0 * db;
-        gya += w1 * da; gyb += w1 * db;
-        gza += w2 * da; gzb += w2 * db;
-        mina = min_(mina, una[j]); minb = min_(minb, unb[j]);
-        maxa = max_(maxa, una[j]); maxb = max_(maxb, unb[j]);
-    }
-    S dla[NF], dlb[NF];
-#pragma unroll
-    for (int j = 0; j < NF; j++) {
-        const double d0 = Tt.D(j, 0), d1 = Tt.D(j, 1), d2 = Tt.D(j, 2);
-        dla[j] = gxa * d0 + gya * d1 + gza * d2;
-        dlb[j] = gxb * d0 + gyb * d1 + gzb * d2;
-    }
-    const S pa = limit ? bj_phi<NF>(dla, ua, mina, maxa, eps) : S(1.0);
-    const S pb = limit ? bj_phi<NF>(dlb, ub, minb, maxb, eps) : S(1.0);
-#pragma unroll
-    for (int j = 0; j < NF; j++) {
-        ra[j] = ua + pa * dla[j];
-        rb[j] = ub + pb * dlb[j];
-    }
-}
-
-// One work item of pass G' (paired form), one cell per lane:
-//   items [0, T / 32):  32 cells x (rho, second thermodynamic variable) in ONE pass;
-//   item T / 32:        all T cells x (vx, vy), T / 32 passes (2-D: + the copy of vz);
-//   item T / 32 + 1:    (3-D) all T cells x vz, T / 32 single-variable passes.
-template <int DIM, int NF, int T, typename S>
-__device__ __forceinline__ void grad_item(const FvArgs<S>& A, const double* wd, const GRec& R, const S* sv, const int svs,
-                                          S* stg, const int task, const int nc, const int lane) {
-    constexpr int N_THERMO = T / 32;
-    const bool limit = A.limiter_on != 0;
-    const bool thermo = task < N_THERMO;
-    const bool single = task == N_THERMO + 1;             // vz alone
-    const bool ghosts = R.hdr[4] != 0;
-    const int nR = R.hdr[1], n_own_l = R.hdr[2];
-    const int n_pass = thermo ? 1 : T / 32;
-    const int va = thermo ? 0 : (single ? 4 : 2), vb = va + 1;      // rows of the state / places in the side records
-#pragma unroll 1
-    for (int pass = 0; pass < n_pass; pass++) {
-        const int i = (thermo ? task : pass) * 32 + lane;
-        if (i >= nc) continue;
-        TileTables<NF, T> Tb;
-        Tb.w = wd;
-        Tb.idx = i;
-        int fl[NF], st[NF];
-#pragma unroll
-        for (int j = 0; j < NF; j++) {
-            fl[j] = R.nbr[j * T + i];
-            st[j] = R.stage[j * T + i];
-        }
-        const S* rowa = sv + (size_t)va * svs;
-        const S ua = rowa[i];
-        S una[NF], ra[NF];
-#pragma unroll
-        for (int j = 0; j < NF; j++) una[j] = rowa[fl[j] & NBR_LOCAL_MASK];
-        if (single) {
-            var_to_faces<DIM, NF>(ua, una, Tb, A.eps, limit, ra);
-#pragma unroll
-            for (int j = 0; j < NF; j++) {
-                if (st[j] == 0xFFFF) continue;
-                stg[(long)st[j] * SIDE_REC + va] = ra[j];
-                if (ghosts && (fl[j] & NBR_GHOST_BIT))
-                    stg[(long)far_stage_index((fl[j] & NBR_LEFT_BIT) != 0, st[j], nR, n_own_l) * SIDE_REC + va] = una[j];
-            }
-            continue;
-        }
-        const S* rowb = sv + (size_t)vb * svs;
-        const S ub = rowb[i];
-        S unb[NF], rb[NF];
-#pragma unroll
-        for (int j = 0; j < NF; j++) unb[j] = rowb[fl[j] & NBR_LOCAL_MASK];
-        var2_to_faces<DIM, NF>(ua, una, ub, unb, Tb, A.eps, limit, ra, rb);
-        // the far side of a boundary interface is the ghost cell itself: zero gradient, unit limiter
-        // (convective_flux.cpp:281-300), i.e. its values; fv_bodies.h::side_second: T = u / Cv for rho_u
-#pragma unroll
-        for (int j = 0; j < NF; j++) {
-            if (st[j] == 0xFFFF) continue;
-            S* q = stg + (long)st[j] * SIDE_REC;
-            q[va] = ra[j];
-            q[vb] = thermo ? side_second(A.thermo, A.gas, rb[j]) : rb[j];
-            if (ghosts && (fl[j] & NBR_GHOST_BIT)) {
-                S* f = stg + (long)far_stage_index((fl[j] & NBR_LEFT_BIT) != 0, st[j], nR, n_own_l) * SIDE_REC;
-                f[va] = una[j];
-                f[vb] = thermo ? side_second(A.thermo, A.gas, unb[j]) : unb[j];
-            }
-        }
-        if (DIM == 2 && !thermo) {
-            // 2-D: vz has no gradient (convective_flux.cpp:206-208) and a unit limiter: the value is copied
-            const S* rz = sv + (size_t)4 * svs;
-#pragma unroll
-            for (int j = 0; j < NF; j++) {
-                if (st[j] == 0xFFFF) continue;
-                stg[(long)st[j] * SIDE_REC + 4] = rz[i];
-                if (ghosts && (fl[j] & NBR_GHOST_BIT))
-                    stg[(long)far_stage_index((fl[j] & NBR_LEFT_BIT) != 0, st[j], nR, n_own_l) * SIDE_REC + 4] = rz[fl[j] & NBR_LOCAL_MASK];
-            }
-        }
-    }
-}
-#else
 // One work item of pass G', one cell per lane:
 //   items [0, T / 32):  32 cells x (rho, then the second thermodynamic variable) -> the first two places of the
 //                       cell's side records (fv_bodies.h::side_second; pass F' finishes the closure, gas_model.h:91-117);
@@ -620,8 +504,6 @@ __device__ __forceinline__ void grad_item(const FvArgs<S>& A, const double* wd, 
         }
     }
 }
-
-#endif
 
 // Work items of a block, in queue order: the N_TASKS items of its tiles (grad_item).  The warp that completes a
 // tile's last item hands the input stage back to the loaders and the staging buffer over to the store warp (one bulk
@@ -750,11 +632,7 @@ __global__ void __launch_bounds__(32 * (IBIS_PIPE_G_WARPS + IBIS_PIPE_G_LOADERS 
         return;
     }
     // ---- consumers ----
-#if IBIS_PIPE_G_PAIR
-    constexpr int N_TASKS = T / 32 + (DIM == 3 ? 2 : 1);
-#else
     constexpr int NV = DIM == 3 ? 3 : 2, N_TASKS = T / 32 + NV * (IBIS_PIPE_G_SPLITVEL ? T / 32 : 1);
-#endif
     const int total = n_my * N_TASKS;
     const unsigned mT = pipe_magic(N_TASKS), mI = pipe_magic(nsi), mO = pipe_magic(nso);
     for (;;) {
