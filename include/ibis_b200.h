@@ -261,7 +261,7 @@ int ibis_b200_l2_norms(ibis_b200_ctx*, int cq, double out[6]);
  * to the interface (boundary.cpp:420-426), and the geometric-conservation-law term -U dV/dt / V
  * (finite_volume.cpp:99-128).  The vertex velocities are what the reference's GridMotionDriver
  * produces (rigid_body_translation.cpp:14-27: one constant vector; shock fitting is not built); moving
- * the vertices and recomputing the geometry between stages is not built yet either.
+ * the vertices and recomputing the geometry between stages: ibis_b200_move_vertices below.
  * face_vertices: Interfaces::vertex_ids (grid/interface.h:331) = ibis_b200_grid_face_vertices, n_faces x 4
  * padded with -1, set once; vertex_vel: n_vertices x 3, copied at the call. */
 int ibis_b200_set_face_vertices(ibis_b200_ctx*, const int64_t* face_vertices, int64_t n_vertices);

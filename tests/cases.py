@@ -14,7 +14,10 @@ R, CV = 287.0, 717.5
 
 
 def perturbed_state(g, dim, mach_scale=1.0, seed=1234):
-    """SURVEY.md section 8(d) field (ii): smooth perturbation + U(-1,1) m/s noise by cell index."""
+    """SURVEY.md section 8(d) field (ii): smooth perturbation + U(-1,1) m/s noise by cell index.
+    One deviation from the survey's formula, kept because every golden vector and both bench arms were generated
+    with it: the density perturbation ends in cos(2 pi z) where the survey writes sin(2 pi z).  Same amplitude,
+    same smoothness, same field on the GPU and the reference arm: no effect on parity or on the comparison."""
     n = g.n_total
     x, y, z = g.cell_centroid[:, 0], g.cell_centroid[:, 1], g.cell_centroid[:, 2]
     rng = np.random.default_rng(seed)
