@@ -66,9 +66,12 @@ EXAMPLE_CASES = {
     # on reaching max_iters its Gmres stores a Hessenberg column past its arrays -- the stock build survives that by
     # luck of the heap layout, any other link order does not.  The steady solver is held to the reference on
     # tests/minimal/steady_state_uniform_stream here and on the five steady runs of tests/solve_cases.py.
-    # examples/naca0012 with SteadyState(...) swapped in (BASELINE.json configs[2], _naca_steady_job below) has no
-    # fixture: the reference itself dies of heap corruption on it ("munmap_chunk(): invalid pointer", viscous or not)
-    # before the first step completes.
+    # examples/naca0012 with SteadyState(...) swapped in (BASELINE.json configs[2], _naca_steady_job above) is prepared by
+    # the reference's prep but has no expected snapshot: the reference itself dies of heap corruption on it
+    # ("munmap_chunk(): invalid pointer", viscous or not) before the first step completes.  The product runs it
+    # (tests/test_prep_configs.py::test_naca0012_steady_state_runs: residual norms fall, no bad cells).
+    "example_naca0012_steady": dict(job="naca0012/job.py", job_filter=_naca_steady_job,
+                                    grid=lambda su2: su2.naca0012_omesh(96, 32), edit={}, prep_only=True),
 }
 
 
@@ -139,6 +142,9 @@ def main():
                 shutil.copy(src, out)
         import time
         t0 = time.time()
+        if spec is not None and spec.get("prep_only"):
+            print(name, "prepared (no reference solve)")
+            continue
         rc = rl.solve(work)
         print(f"  reference solve: {time.time() - t0:.1f} s", flush=True)
         flow_dirs = sorted(d for d in os.listdir(os.path.join(work, "io/flow")) if d.isdigit())

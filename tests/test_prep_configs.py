@@ -66,3 +66,45 @@ def test_prepared_reference_cases_on_the_gpu(case):
     import torch
     assert torch.cuda.is_available(), "GPU tests need a CUDA device"
     _run(case)
+
+
+def _naca_steady(lib_path=None, host_lib=None):
+    """BASELINE.json configs[2]'s steady variant: examples/naca0012/job.py with SteadyState(...) swapped in for
+    RungeKutta(...), prepared by the reference's own prep (viscous, subsonic in/outflow, adiabatic no-slip wall, JFNK +
+    GMRES(30)).  The reference itself cannot run it (heap corruption before its first step completes:
+    tests/golden/make_dropin_cases.py), so there is no snapshot to compare with; the product must run its twelve
+    Newton steps, keep every cell physical and bring the global residual down."""
+    case = "example_naca0012_steady"
+    with open(os.path.join(DROPIN, case, "config", "config.json")) as f:
+        config = json.load(f)
+    assert config["solver"]["name"] == "steady_state" and config["viscous_flux"]["enabled"]
+    mesh = libmod.read_su2(os.path.join(DROPIN, case, "io", "grid", "0000", "block_0000.su2"), lib_path=lib_path)
+    g = libmod.build_grid(mesh, None, lib_path=lib_path)
+    ctx = Context(g, config, lib_path=lib_path)
+    try:
+        fs = ctx.fs_create()
+        native_io.read_snapshot(ctx, fs, os.path.join(DROPIN, case, "io", "flow"), 0)
+        prim0 = ctx.fs_download(fs)
+        norms = []
+        out, rep = host.solve(ctx, config, prim0, host_lib=host_lib, on_residuals=lambda step, t, nm: norms.append(nm[0]))
+        fs2 = ctx.fs_create()
+        ctx.fs_upload(fs2, out)
+        assert ctx.count_bad_cells(fs2) == 0
+    finally:
+        ctx.close()
+    assert rep["status"] == 0 and rep["steps"] == config["solver"]["max_steps"]
+    n = g.n_cells
+    assert np.isfinite(out[:n]).all() and (out[:n, 0] > 0).all() and (out[:n, 2] > 0).all()
+    assert len(norms) >= 2 and norms[-1] < 0.5 * norms[0], norms
+
+
+def test_naca0012_steady_state_runs_on_the_host_emulation():
+    from emu_util import emu_host_lib, emu_lib
+    _naca_steady(emu_lib(), emu_host_lib())
+
+
+@pytest.mark.gpu
+def test_naca0012_steady_state_runs_on_the_gpu():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    _naca_steady()
