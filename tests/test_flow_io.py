@@ -175,3 +175,34 @@ def test_snapshots_overlap_steps_gpu():
     import torch
     assert torch.cuda.is_available(), "GPU tests need a CUDA device"
     _check_overlap()
+
+
+def test_snapshot_ring_rejects_misuse_without_poisoning_the_context():
+    """bad slot numbers, an `end` without its `begin`, null arrays: EINVAL / EHANDLE from the call itself, and the
+    context keeps working afterwards"""
+    from emu_util import emu_lib
+    from ibis_b200.lib import IbisB200Error
+    mesh, config, g, prim = cases.build_case("quad2d_ausmdv")
+    ctx = Context(g, config, lib_path=emu_lib())
+    try:
+        fs = ctx.fs_create()
+        ctx.fs_upload(fs, prim)
+        host = ctx.pinned_array((4, ctx.n_cells))
+        with pytest.raises(IbisB200Error, match="without snapshot_upload_begin"):
+            ctx.snapshot_upload_end(0, fs)
+        with pytest.raises(IbisB200Error, match="without snapshot_download_begin"):
+            ctx.snapshot_download_end(1)
+        with pytest.raises(IbisB200Error, match="slot must be 0 or 1"):
+            ctx.snapshot_download_begin(2, fs, host)
+        with pytest.raises(IbisB200Error, match="not a FlowStates handle"):
+            ctx.snapshot_download_begin(0, 9999, host)
+        ctx.snapshot_download_begin(0, fs, host)
+        with pytest.raises(IbisB200Error, match="without snapshot_download_begin"):
+            ctx.snapshot_download_end(1)                   # slot 1 was never used
+        ctx.snapshot_download_end(0)
+        assert np.array_equal(host[0], prim[:ctx.n_cells, 2]) and np.array_equal(host[3], prim[:ctx.n_cells, 5])
+        ctx.snapshot_upload_begin(1, host)
+        ctx.snapshot_upload_end(1, fs)
+        assert np.array_equal(ctx.fs_download(fs)[:ctx.n_cells, 2], prim[:ctx.n_cells, 2])
+    finally:
+        ctx.close()
