@@ -128,16 +128,17 @@ IBIS_HD Flux5<S> flux_ausmdv(const Side<S>& L, const Side<S>& R_, const Gas<S>& 
     S keR = 0.5 * (uR * uR + vR * vR + wR * wR);
     S HR = eR + pRrR + keR;
 
-    S alphaL, alphaR;
-    div_shared(2.0 * pLrL, 2.0 * pRrR, pLrL + pRrR, alphaL, alphaR);
-
     S am = max_(aL, aR);
     S ML, MR;
     div_shared(uL, uR, am, ML, MR);
-    // (uL + am)^2 / (4 am) and -(uR - am)^2 / (4 am) of the subsonic branches
+    // alphaL, alphaR (ausmdv.cpp:38-39) and (uL + am)^2 / (4 am), -(uR - am)^2 / (4 am) are read by the subsonic
+    // branches only: a supersonic interface (both sides) skips their three reciprocals
     const bool subL = re(abs_(ML)) <= 1.0, subR = re(abs_(MR)) <= 1.0;
-    S qLs = S(0.0), qRs = S(0.0);
-    if (subL || subR) div_shared((uL + am) * (uL + am), -(uR - am) * (uR - am), 4.0 * am, qLs, qRs);
+    S alphaL = S(0.0), alphaR = S(0.0), qLs = S(0.0), qRs = S(0.0);
+    if (subL || subR) {
+        div_shared(2.0 * pLrL, 2.0 * pRrR, pLrL + pRrR, alphaL, alphaR);
+        div_shared((uL + am) * (uL + am), -(uR - am) * (uR - am), 4.0 * am, qLs, qRs);
+    }
 
     S pLplus, uLplus;
     S duL = 0.5 * (uL + abs_(uL));
